@@ -1,0 +1,187 @@
+"""ctypes binding of the CPU oracle (oracle/simian_oracle.cpp).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, by __graft_entry__.smoke() and by
+bench.py's cpu_baseline / --impl reference legs -- never by simian_b200/.
+The method names mirror the product's low-level binding
+(simian_b200/capi.py) so one model-builder function can drive both.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "_build", "libsimian_oracle.so")
+
+
+class OracleStats(C.Structure):
+    _fields_ = [
+        ("total_events", C.c_uint64),
+        ("windows", C.c_uint64),
+        ("synch_events", C.c_uint64),
+        ("digest", C.c_uint64),
+        ("state_checksum", C.c_uint64),
+        ("ties", C.c_uint64),
+        ("distinguishable_ties", C.c_uint64),
+        ("emitted", C.c_uint64),
+        ("dropped_past_end", C.c_uint64),
+        ("last_time", C.c_double),
+        ("run_seconds", C.c_double),
+        ("error", C.c_int32),
+        ("pad_", C.c_int32),
+    ]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_ if k != "pad_"}
+
+
+EVENT_DTYPE = np.dtype(
+    [("time", "<f8"), ("dst", "<u4"), ("src", "<u4"), ("handler", "<u2"),
+     ("flags", "<u2"), ("seq", "<u4"), ("data", "<u8")], align=False)
+assert EVENT_DTYPE.itemsize == 32
+
+
+def build(force=False):
+    """Compile the oracle with the recipe in oracle/Makefile."""
+    if force or not os.path.exists(LIB_PATH) or any(
+            os.path.getmtime(os.path.join(HERE, p)) > os.path.getmtime(LIB_PATH)
+            for p in ("simian_oracle.cpp", "../include/simian_spec.h",
+                      "../include/simian_models.h")):
+        subprocess.check_call(["make", "-s", "-C", HERE])
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(build())
+        vp, cp, d, u64, u32, i = (C.c_void_p, C.c_char_p, C.c_double,
+                                  C.c_uint64, C.c_uint32, C.c_int)
+        sig = {
+            "oracle_hash_name": (d, [cp]),
+            "oracle_create": (vp, [cp, d, d, d, i, i]),
+            "oracle_destroy": (None, [vp]),
+            "oracle_set_seed": (None, [vp, u64]),
+            "oracle_last_error": (cp, [vp]),
+            "oracle_define_class": (i, [vp, cp, u32]),
+            "oracle_set_class_params": (i, [vp, cp, vp, u32]),
+            "oracle_add_entities": (i, [vp, cp, u32, u32]),
+            "oracle_first_id": (i, [vp, cp]),
+            "oracle_base_rank": (i, [vp, cp]),
+            "oracle_intern_service": (i, [vp, cp]),
+            "oracle_attach_service": (i, [vp, cp, cp, cp]),
+            "oracle_sched_service": (i, [vp, d, cp, u64, cp, u32]),
+            "oracle_sched_service_bulk": (i, [vp, d, cp, u64, cp, u32, u32, u32]),
+            "oracle_sched_events": (i, [vp, vp, u64]),
+            "oracle_run": (i, [vp, C.POINTER(OracleStats)]),
+            "oracle_read_counts": (i, [vp, cp, vp]),
+            "oracle_read_trace_hashes": (i, [vp, cp, vp]),
+            "oracle_read_state": (i, [vp, cp, vp]),
+            "oracle_q_new": (vp, [i]),
+            "oracle_q_free": (None, [vp]),
+            "oracle_q_push": (None, [vp, d, u64]),
+            "oracle_q_len": (u64, [vp]),
+            "oracle_q_peek": (d, [vp]),
+            "oracle_q_pop": (d, [vp, C.POINTER(u64)]),
+            "oracle_spec_log": (d, [d]),
+            "oracle_spec_mix64": (u64, [u64]),
+            "oracle_spec_rng_key": (u64, [u64, u32, u64]),
+            "oracle_spec_rng_draw": (u64, [u64, u32]),
+            "oracle_spec_u01": (d, [u64]),
+            "oracle_spec_u01_open": (d, [u64]),
+            "oracle_spec_exponential": (d, [u64, d]),
+            "oracle_spec_trace_step": (u64, [u64, d, u32, u32, u64]),
+            "oracle_spec_digest_term": (u64, [u32, u64, u64]),
+        }
+        for name, (res, args) in sig.items():
+            f = getattr(L, name)
+            f.restype, f.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+class OracleError(RuntimeError):
+    pass
+
+
+class Oracle:
+    """Low-level handle; same method names as simian_b200.capi.Engine."""
+
+    def __init__(self, name, start, end, min_delay, size=1, tie_mode=0, seed=1):
+        self.L = lib()
+        self.h = self.L.oracle_create(name.encode(), start, end, min_delay,
+                                      size, tie_mode)
+        self.L.oracle_set_seed(self.h, seed)
+        self.classes = {}
+
+    def close(self):
+        if self.h:
+            self.L.oracle_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def _ck(self, rc):
+        if rc:
+            raise OracleError("oracle error %d: %s" % (
+                rc, self.L.oracle_last_error(self.h).decode()))
+
+    def define_class(self, name, state_bytes=0):
+        self.classes[name] = state_bytes
+        return self.L.oracle_define_class(self.h, name.encode(), state_bytes)
+
+    def set_class_params(self, name, blob):
+        buf = (C.c_char * len(blob)).from_buffer_copy(blob)
+        self._ck(self.L.oracle_set_class_params(self.h, name.encode(), buf,
+                                                len(blob)))
+
+    def add_entities(self, name, first, count):
+        self._ck(self.L.oracle_add_entities(self.h, name.encode(), first, count))
+
+    def first_id(self, name):
+        return self.L.oracle_first_id(self.h, name.encode())
+
+    def base_rank(self, name):
+        return self.L.oracle_base_rank(self.h, name.encode())
+
+    def intern_service(self, name):
+        return self.L.oracle_intern_service(self.h, name.encode())
+
+    def attach_service(self, cls, service, fn):
+        self._ck(self.L.oracle_attach_service(self.h, cls.encode(),
+                                              service.encode(), fn.encode()))
+
+    def sched_service(self, time, service, data, rx, rx_id):
+        self._ck(self.L.oracle_sched_service(self.h, time, service.encode(),
+                                             data, rx.encode(), rx_id))
+
+    def sched_service_bulk(self, time, service, data, rx, first, count, repeat=1):
+        self._ck(self.L.oracle_sched_service_bulk(
+            self.h, time, service.encode(), data, rx.encode(), first, count,
+            repeat))
+
+    def sched_events(self, events):
+        ev = np.ascontiguousarray(events, dtype=EVENT_DTYPE)
+        self._ck(self.L.oracle_sched_events(self.h, ev.ctypes.data, len(ev)))
+
+    def run(self, check=True):
+        st = OracleStats()
+        rc = self.L.oracle_run(self.h, C.byref(st))
+        if check:
+            self._ck(rc)
+        return st.as_dict()
+
+    def _read(self, fn, name, n):
+        out = np.zeros(n, dtype=np.uint64)
+        self._ck(fn(self.h, name.encode(), out.ctypes.data))
+        return out
+
+    def read_counts(self, name, n):
+        return self._read(self.L.oracle_read_counts, name, n)
+
+    def read_trace_hashes(self, name, n):
+        return self._read(self.L.oracle_read_trace_hashes, name, n)
