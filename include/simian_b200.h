@@ -1,0 +1,188 @@
+/*
+ * simian_b200.h -- C-ABI of libsimian_b200.so, the B200-native drop-in for the
+ * event-oriented service path of SimianJS (eventQ.js + simian.js + entity.js).
+ *
+ * Plain C: pointers, sizes, doubles.  No torch / CUDA types.  Every entry point
+ * names the reference interface it replaces (paths relative to /root/reference).
+ * The reference's own native boundary is the `masala` object of
+ * SimianJS/MasalaChai/masala.cpp:39-146 (natives return false + pending
+ * exception on failure); here every call returns an int status (0 = ok) and
+ * simian_last_error() yields the message the JS facade rethrows.
+ *
+ * Ownership: the engine owns all device memory.  Host pointers are borrowed
+ * for the duration of the call; results are copied into caller buffers.
+ * Threading: one host thread per engine; calls are not re-entrant; one engine
+ * = one MPI rank of the reference = one GPU (simian.js:71-79).
+ */
+#ifndef SIMIAN_B200_H
+#define SIMIAN_B200_H
+
+#include <stdint.h>
+
+#include "simian_spec.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct simian_engine simian_engine;
+
+/* status codes; 1..4 mirror the reference's thrown errors */
+enum simian_status {
+  SIMIAN_OK = 0,
+  SIMIAN_ERR_LOOKAHEAD = 1,    /* entity.js:44 "attempted to send with too little delay" */
+  SIMIAN_ERR_IDLE_SEND = 2,    /* entity.js:42 "Cannot send an event when Simian is idle" */
+  SIMIAN_ERR_OUT_OF_ORDER = 3, /* simian.js:125 "Out of order event"                      */
+  SIMIAN_ERR_RUNNING = 4,      /* simian.js:215 "Cannot add new entity when Simian is running!" */
+  SIMIAN_ERR_UNKNOWN_NAME = 5, /* entity / service / device function not registered       */
+  SIMIAN_ERR_BAD_ARGUMENT = 6,
+  SIMIAN_ERR_POOL_EXHAUSTED = 7, /* event pool (pages) full: raise option "pool_events"   */
+  SIMIAN_ERR_WINDOW_OVERFLOW = 8, /* one entity block has more due pages than a CTA lists */
+  SIMIAN_ERR_ENTITY_BURST = 9,   /* one entity has more due events than fit on chip       */
+  SIMIAN_ERR_SELF_PENDING = 10,  /* too many same-window self-sends pending on an entity  */
+  SIMIAN_ERR_OUTBOX_FULL = 11,   /* cross-GPU staging buffer full: raise "outbox_events"  */
+  SIMIAN_ERR_RING_SPAN = 12,     /* window spans the whole calendar ring: raise "bucket_width" */
+  SIMIAN_ERR_CUDA = 13,
+  SIMIAN_ERR_NO_DEVICE = 14 /* no CUDA device: there is NO CPU fallback                   */
+};
+
+/* What Simian.run prints (simian.js:159-164) plus the parity quantities. */
+typedef struct simian_stats {
+  uint64_t total_events;   /* "SIMULATED EVENTS" of this rank (simian.js:133)          */
+  uint64_t windows;        /* iterations of the window loop (simian.js:119)            */
+  uint64_t synch_events;   /* simian.js:145                                            */
+  uint64_t digest;         /* sum over local entities of simian_digest_term            */
+  uint64_t state_checksum; /* sum over local entities of folded user state             */
+  uint64_t ties;           /* same-entity equal-time commits seen                      */
+  uint64_t distinguishable_ties;
+  uint64_t emitted;          /* events created by reqService and not dropped           */
+  uint64_t dropped_past_end; /* time > endTime (entity.js:48)                          */
+  double last_time;          /* engine.now after run (max committed time)              */
+  double run_seconds;        /* host wall clock around run ("SIMULATION FINISHED IN")  */
+  double device_seconds;     /* CUDA-event time of the window loop on the engine stream */
+  uint64_t kernel_launches;  /* kernels of this library launched inside run            */
+  uint64_t redistributions;  /* far-future list redistribution passes                  */
+  uint64_t far_appends;
+  uint64_t pages_allocated;
+  int32_t error;
+  int32_t pad_;
+} simian_stats;
+
+const char *simian_version(void);
+
+/* new Simian(simName, startTime, endTime, minDelay, useMPI)   simian.js:36-84
+ * rank/size play MPI.rank()/MPI.size() (simian.js:73-75): one engine per GPU.
+ * device < 0 selects cuda device `rank % deviceCount`.  Returns NULL on failure
+ * (simian_last_error(NULL) tells why; in particular when no GPU is present). */
+simian_engine *simian_create(const char *simName, double startTime,
+                             double endTime, double minDelay, int rank,
+                             int size, int device);
+
+/* Simian.exit                                                  simian.js:90-97 */
+void simian_destroy(simian_engine *e);
+
+const char *simian_last_error(simian_engine *e);
+
+/* Engine tunables, all optional, before the first run:
+ *   "seed"            engine seed of the shared counter-based RNG (default 1)
+ *   "bucket_width"    calendar sub-bucket width in simulated time (default minDelay/4)
+ *   "ring_buckets"    calendar ring length, power of two (default 2048)
+ *   "pool_events"     event pool capacity in records (default 4x initial + slack)
+ *   "outbox_events"   per-peer cross-GPU staging capacity in records
+ *   "launch_batch"    window kernels enqueued between host polls
+ *   "tie_check"       1: count same-entity time ties (default 1)             */
+int simian_set_option(simian_engine *e, const char *key, double value);
+
+/* Entity classes.  An entity class = the `name` of addEntity plus the JS class
+ * object (simian.js:211-229).  stateBytes (multiple of 8) of per-entity user
+ * state live in HBM, zero-initialised unless initState is given.            */
+int simian_define_class(simian_engine *e, const char *className,
+                        uint32_t stateBytes);
+int simian_set_class_params(simian_engine *e, const char *className,
+                            const void *params, uint32_t bytes);
+
+/* addEntity(name, klass, num) for num = firstNum .. firstNum+count-1
+ * (simian.js:211-229).  Only entities with getOffsetRank == rank are
+ * instantiated (simian.js:221-223).  Instances of a class are added
+ * contiguously from 0; SIMIAN_ERR_RUNNING while running (simian.js:215).     */
+int simian_add_entities(simian_engine *e, const char *className,
+                        uint32_t firstNum, uint32_t count,
+                        const void *initState /* nullable, count*stateBytes */);
+
+/* attachService(klass, name, fun)   simian.js:207-209 / entity.js:70-72 with
+ * fun = a __device__ handler compiled into the library, looked up by name
+ * ("phold_generate", "noop", ...).                                           */
+int simian_attach_service(simian_engine *e, const char *className,
+                          const char *serviceName, const char *deviceFnName);
+
+/* interned id of a service name (the `name` field of an event)              */
+int simian_intern_service(simian_engine *e, const char *serviceName);
+
+/* global entity id of className(0); ids of a class are contiguous           */
+int64_t simian_first_id(simian_engine *e, const char *className);
+
+/* getBaseRank(name) = hash(name) % size   simian.js:192-194, hash.js:21-26  */
+int simian_base_rank(simian_engine *e, const char *className);
+double simian_hash_name(const char *name);
+
+/* schedService(time, eventName, data, rx, rxId)             simian.js:170-190 */
+int simian_sched_service(simian_engine *e, double time, const char *serviceName,
+                         uint64_t data, const char *rx, uint32_t rxId);
+
+/* the model-script loop
+ *   for k < repeat: for i < count: schedService(time, name, data, rx, first+i)
+ * (phold-noop-noMPI.js:47) built on the device, no host loop.               */
+int simian_sched_service_bulk(simian_engine *e, double time,
+                              const char *serviceName, uint64_t data,
+                              const char *rx, uint32_t firstId, uint32_t count,
+                              uint32_t repeat);
+
+/* Batch injection from a HOST buffer of POD records (dst/src = global ids).
+ * Same meaning as n schedService / pre-run reqService calls; this is the call
+ * the end-to-end benchmark times (host->device copy included).              */
+int simian_sched_events(simian_engine *e, const simian_event_t *hostEvents,
+                        uint64_t n);
+
+/* Simian.run()                                               simian.js:99-168
+ * size == 1: the whole window loop runs here.  size > 1: use the stepping
+ * calls below (the host runs the collectives, mpi.cpp:364-476).             */
+int simian_run(simian_engine *e, simian_stats *out);
+
+/* ---- stepping interface for size > 1 (one window = simian.js:120-148) ---- */
+/* allocate calendar / pools, ingest scheduled events, compute window 0      */
+int simian_run_begin(simian_engine *e);
+/* drain every local event below the window bound (simian.js:122-134)        */
+int simian_window_process(simian_engine *e);
+/* per-peer staged record counts of this window, to host (sndCounts,
+ * mpi.cpp:21,461); also returns the device buffers to exchange.             */
+int simian_window_outbox(simian_engine *e, uint32_t *hostCounts /* [size] */,
+                         void **devOutbox, uint64_t *recordsPerPeerCapacity);
+/* received records (device pointer, contiguous) -> local calendar
+ * (simian.js:138-142)                                                        */
+int simian_window_ingest(simian_engine *e, const void *devRecords, uint64_t n);
+/* local minLeft candidate (simian.js:143) written to a device buffer of two
+ * doubles {minLeft, -needRedistribution}; allreduce(MIN) it (simian.js:144) */
+int simian_window_local_min(simian_engine *e, void **devMinVec);
+/* consume the allreduced vector, set up the next window; *done = 1 when
+ * globalMinLeft > endTime (simian.js:119)                                    */
+int simian_window_advance(simian_engine *e, int *done);
+int simian_run_end(simian_engine *e, simian_stats *out);
+/* stream the engine launches on (a cudaStream_t); pass torch's current
+ * stream so collectives and kernels are ordered                             */
+int simian_set_stream(simian_engine *e, void *cudaStream);
+
+/* ---- results: what the parity tests compare ------------------------------ */
+/* per-entity committed-event counts of className(first .. first+count-1);
+ * entries of entities living on other ranks are left untouched              */
+int simian_read_counts(simian_engine *e, const char *className, uint32_t first,
+                       uint32_t count, uint64_t *out);
+int simian_read_trace_hashes(simian_engine *e, const char *className,
+                             uint32_t first, uint32_t count, uint64_t *out);
+/* getEntity(name, num) state read-back (simian.js:200-205)                  */
+int simian_read_state(simian_engine *e, const char *className, uint32_t first,
+                      uint32_t count, void *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIMIAN_B200_H */

@@ -1,0 +1,115 @@
+// device_types.cuh -- HBM-resident data layout of the simian-b200 engine.
+//
+// Replaces (paths relative to /root/reference):
+//   SimianJS/eventQ.js        one binary heap of boxed event objects per rank
+//   SimianJS/simian.js:53-59  entities{} / eventList[] / eventQueue
+// with
+//   * a paged CALENDAR in HBM: cell (time sub-bucket, entity block) -> chain of
+//     2-KB pages of 32-byte POD event records (one DRAM sector per record);
+//   * per-entity core state {commit count, trace hash} (16 B) + per-class user
+//     state, indexed by local slot;
+//   * a double-buffered device-resident window descriptor (the LBTS state of
+//     simian.js:118-149) so the host never has to see a timestamp.
+#pragma once
+#include <stdint.h>
+
+#include "../../include/simian_models.h"
+#include "../../include/simian_spec.h"
+
+#ifndef SIMIAN_EPB
+#define SIMIAN_EPB 1024 // entities per block (one CTA owns one block)
+#endif
+#ifndef SIMIAN_THREADS
+#define SIMIAN_THREADS 512 // threads per CTA of the window kernel
+#endif
+#ifndef SIMIAN_PAGE
+#define SIMIAN_PAGE 64 // records per page (2 KB)
+#endif
+#ifndef SIMIAN_REFS
+#define SIMIAN_REFS 12288 // due-event references a CTA groups per pass
+#endif
+#ifndef SIMIAN_PGMAX
+#define SIMIAN_PGMAX 2048 // pages a CTA can list per window
+#endif
+
+#define SIMIAN_MAX_CLASSES 8
+#define SIMIAN_MAX_SERVICES 32
+#define SIMIAN_MAX_CELLS 96 // sub-buckets one window may span
+#define SIMIAN_NONE 0xFFFFFFFFu
+#define SIMIAN_KEY_NONE 0xFFFFFFFFFFFFFFFFull
+#define SIMIAN_SELF_MAX 8 // same-window self-sends pending per entity
+
+struct __align__(16) EntityCore {
+  uint64_t count; // committed events                (numEvents, per entity)
+  uint64_t hash;  // order-sensitive trace hash
+};
+
+struct DevClass {
+  uint32_t first_id;  // global id of instance 0
+  uint32_t count;     // instances over all ranks
+  uint32_t rank_off;  // (rank - baseRank) mod size: first local num
+  uint32_t slot_base; // first local slot of this class on this rank
+  uint32_t n_local;   // local instances
+  uint32_t base_rank; // getBaseRank(name)                 simian.js:192-194
+  uint32_t state_bytes;
+  uint32_t pad_;
+  uint8_t *state;     // n_local * state_bytes
+  const void *params; // model parameters (device copy)
+  uint8_t fn_of_service[SIMIAN_MAX_SERVICES]; // service id -> builtin fn
+};
+
+// LBTS / window descriptor (simian.js:118-120,143-147), device resident.
+struct WinState {
+  double gmin; // globalMinLeft: every event below it is committed
+  double hi;   // epoch = gmin + minDelay; events with time < hi run now
+  long long tb_lo, tb_hi; // calendar sub-buckets the window touches
+  long long tb_clean;     // every sub-bucket below it has been recycled
+  long long tb_clean_new; // redistribution pass: recycle up to here first
+  uint32_t done;          // gmin > endTime                  simian.js:119
+  uint32_t redist;        // this launch is a far-list redistribution pass
+  uint32_t far_row;       // which of the two far rows receives appends
+  uint32_t pad_;
+  unsigned long long alloc_limit; // pages allocatable in this launch
+};
+
+// Global accumulators (atomics), reset by the advance step.
+struct DevAcc {
+  unsigned long long min_key;    // min time key of leftover/emitted/ingested
+  unsigned long long far_min[2]; // min time key in far row 0 / 1
+  unsigned long long alloc_head, free_tail; // page ring cursors
+  unsigned long long committed, emitted, dropped, ties, dist_ties;
+  unsigned long long max_key; // max committed time key
+  unsigned long long windows, redistributions, far_appends, page_allocs,
+      leaked_pages;
+  unsigned int ticket;
+  unsigned int error; // sticky, first error wins
+  unsigned int window_index;
+  unsigned int pad_;
+  double minvec[2]; // {local minLeft candidate, local far min} for allreduce
+};
+
+struct DevCfg {
+  double start, end, min_delay, inf_time;
+  uint64_t seed;
+  int rank, size;
+  int n_classes, tie_check;
+  DevClass cls[SIMIAN_MAX_CLASSES];
+  // entities
+  EntityCore *core;
+  uint32_t n_slots, n_blocks;
+  // calendar
+  double inv_w;
+  uint32_t ring, ring_mask;
+  uint32_t *cell_cur; // [(ring+2) * n_blocks], row-major by sub-bucket slot
+  simian_event_t *pool;
+  uint32_t *page_next, *page_fill;
+  uint32_t *free_ring;
+  uint32_t n_pages, pad0_;
+  uint32_t *snap_cur, *snap_fill; // [n_blocks] head snapshot of row tb_hi
+  WinState *win;                  // [2]
+  DevAcc *acc;
+  // cross-GPU staging (size > 1)
+  simian_event_t *outbox; // [size][outbox_cap]
+  uint32_t *outbox_count; // [size]
+  uint32_t outbox_cap, pad1_;
+};

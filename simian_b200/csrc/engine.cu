@@ -1,0 +1,676 @@
+// engine.cu -- host side of libsimian_b200.so: the C-ABI of include/simian_b200.h
+// over the kernels of kernels.cuh.  No CPU fallback: without a CUDA device
+// simian_create fails with SIMIAN_ERR_NO_DEVICE.
+//
+// Replaces the JS engine object of SimianJS/simian.js (constructor :36-84,
+// run :99-168, schedService :170-190, addEntity :211-229, attachService
+// :207-209) and Entity.reqService (SimianJS/entity.js:35-68, on the device).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <chrono>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/simian_b200.h"
+#include "kernels.cuh"
+
+namespace {
+
+std::string g_create_error;
+
+struct HostClass {
+  std::string name;
+  uint32_t first_id = 0, count = 0, state_bytes = 0;
+  double name_hash = 0;
+  std::vector<uint8_t> params;
+  std::vector<uint8_t> init_state; // count * state_bytes when given
+  bool has_init = false;
+  uint8_t fn_of_service[SIMIAN_MAX_SERVICES];
+  // resolved at setup
+  uint32_t base_rank = 0, rank_off = 0, slot_base = 0, n_local = 0;
+  uint8_t *d_state = nullptr;
+  void *d_params = nullptr;
+};
+
+struct SchedOp { // a recorded schedService call, replayed on the device at run
+  int kind = 0;  // 0 bulk, 1 host records
+  double time = 0;
+  uint32_t handler = 0;
+  uint64_t data = 0;
+  int cls = 0;
+  uint32_t first = 0, count = 0, repeat = 0, seq_base = 0;
+  std::vector<simian_event_t> recs;
+};
+
+int builtin_fn_by_name(const char *n) {
+  if (!strcmp(n, "phold_generate")) return SIMIAN_FN_PHOLD_GENERATE;
+  if (!strcmp(n, "noop")) return SIMIAN_FN_COUNT_ONLY;
+  return SIMIAN_FN_NONE;
+}
+
+} // namespace
+
+struct simian_engine {
+  std::string name;
+  double start, end, min_delay, inf_time;
+  int rank, size, device;
+  // options
+  uint64_t seed = 1;
+  double bucket_width = 0;
+  uint32_t ring = 2048;
+  uint64_t pool_events = 0, outbox_events = 0;
+  int launch_batch = 16, tie_check = 1;
+  // model
+  std::vector<HostClass> classes;
+  std::map<std::string, int> class_ix;
+  std::map<std::string, int> service_ix;
+  std::vector<SchedOp> ops;
+  uint32_t n_ids = 0, sched_seq = 0;
+  uint64_t initial_events = 0;
+  // state
+  bool running = false, set_up = false, stepping = false;
+  std::string err;
+  int err_code = 0;
+  // device
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  DevCfg cfg;
+  std::vector<void *> allocs;
+  uint32_t win_ix = 0;
+  uint64_t launches = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  unsigned long long *d_digest = nullptr;
+  DevAcc *h_acc = nullptr; // pinned
+  WinState *h_win = nullptr;
+  uint32_t *h_counts = nullptr;
+  std::chrono::steady_clock::time_point t_begin;
+  size_t smem_bytes = sizeof(WindowShared);
+
+  int fail(int code, const std::string &m) {
+    if (!err_code) {
+      err_code = code;
+      err = m;
+    }
+    return code;
+  }
+};
+
+#define CK(call)                                                                       \
+  do {                                                                                 \
+    cudaError_t _e = (call);                                                           \
+    if (_e != cudaSuccess)                                                             \
+      return e->fail(SIMIAN_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e)); \
+  } while (0)
+
+namespace {
+
+const char *status_text(int code) {
+  switch (code) {
+    case SIMIAN_ERR_LOOKAHEAD: return "attempted to send with too little delay";
+    case SIMIAN_ERR_IDLE_SEND: return "Cannot send an event when Simian is idle";
+    case SIMIAN_ERR_OUT_OF_ORDER: return "Out of order event";
+    case SIMIAN_ERR_RUNNING: return "Cannot add new entity when Simian is running!";
+    case SIMIAN_ERR_UNKNOWN_NAME: return "unknown entity / service / device function";
+    case SIMIAN_ERR_POOL_EXHAUSTED: return "event pool exhausted: raise option pool_events";
+    case SIMIAN_ERR_WINDOW_OVERFLOW: return "too many due pages for one entity block in one window";
+    case SIMIAN_ERR_ENTITY_BURST: return "one entity has too many due events in one window";
+    case SIMIAN_ERR_SELF_PENDING: return "too many same-window self-sends pending on one entity";
+    case SIMIAN_ERR_OUTBOX_FULL: return "cross-GPU outbox full: raise option outbox_events";
+    case SIMIAN_ERR_RING_SPAN: return "window spans too many calendar sub-buckets: raise option bucket_width";
+    default: return "error";
+  }
+}
+
+template <class T>
+int dev_alloc(simian_engine *e, T **p, size_t n) {
+  void *q = nullptr;
+  size_t bytes = (n ? n : 1) * sizeof(T);
+  CK(cudaMalloc(&q, bytes));
+  e->allocs.push_back(q);
+  *p = (T *)q;
+  return 0;
+}
+
+uint32_t local_count(uint32_t count, uint32_t rank_off, uint32_t g) {
+  return count > rank_off ? (count - rank_off + g - 1) / g : 0;
+}
+
+// allocate the HBM layout, initialise it, replay schedService, set up window 0
+int setup(simian_engine *e) {
+  if (e->set_up) return 0;
+  DevCfg &c = e->cfg;
+  memset(&c, 0, sizeof c);
+  c.start = e->start;
+  c.end = e->end;
+  c.min_delay = e->min_delay;
+  c.inf_time = e->inf_time;
+  c.seed = e->seed;
+  c.rank = e->rank;
+  c.size = e->size;
+  c.tie_check = e->tie_check;
+  c.n_classes = (int)e->classes.size();
+  if (c.n_classes == 0) return e->fail(SIMIAN_ERR_BAD_ARGUMENT, "no entities added");
+  uint32_t g = (uint32_t)e->size, slot = 0;
+  for (int k = 0; k < c.n_classes; k++) {
+    HostClass &h = e->classes[k];
+    h.base_rank = (uint32_t)fmod(h.name_hash, (double)e->size); // simian.js:192-194
+    h.rank_off = ((uint32_t)e->rank + g - h.base_rank % g) % g;
+    h.n_local = local_count(h.count, h.rank_off, g);
+    h.slot_base = slot;
+    slot += h.n_local;
+    DevClass &d = c.cls[k];
+    d.first_id = h.first_id;
+    d.count = h.count;
+    d.rank_off = h.rank_off;
+    d.slot_base = h.slot_base;
+    d.n_local = h.n_local;
+    d.base_rank = h.base_rank;
+    d.state_bytes = h.state_bytes;
+    memcpy(d.fn_of_service, h.fn_of_service, sizeof d.fn_of_service);
+    if (dev_alloc(e, &h.d_state, (size_t)h.n_local * h.state_bytes)) return e->err_code;
+    if (h.state_bytes && h.n_local) {
+      if (h.has_init) {
+        std::vector<uint8_t> loc((size_t)h.n_local * h.state_bytes);
+        for (uint32_t j = 0; j < h.n_local; j++)
+          memcpy(&loc[(size_t)j * h.state_bytes],
+                 &h.init_state[(size_t)(j * g + h.rank_off) * h.state_bytes], h.state_bytes);
+        CK(cudaMemcpyAsync(h.d_state, loc.data(), loc.size(), cudaMemcpyHostToDevice, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+      } else {
+        CK(cudaMemsetAsync(h.d_state, 0, (size_t)h.n_local * h.state_bytes, e->stream));
+      }
+    }
+    d.state = h.d_state;
+    uint8_t *dp = nullptr;
+    if (dev_alloc(e, &dp, h.params.size())) return e->err_code;
+    if (!h.params.empty())
+      CK(cudaMemcpyAsync(dp, h.params.data(), h.params.size(), cudaMemcpyHostToDevice, e->stream));
+    h.d_params = dp;
+    d.params = dp;
+  }
+  c.n_slots = slot;
+  c.n_blocks = (slot + EPB - 1) / EPB;
+  if (c.n_blocks == 0) c.n_blocks = 1;
+  double w = e->bucket_width > 0 ? e->bucket_width : e->min_delay / 4.0;
+  c.inv_w = 1.0 / w;
+  uint32_t ring = 256;
+  while (ring < e->ring) ring <<= 1;
+  c.ring = ring;
+  c.ring_mask = ring - 1;
+  uint64_t local_initial = e->initial_events / g + 1;
+  uint64_t pool_events = e->pool_events
+                             ? e->pool_events
+                             : 3 * local_initial + (uint64_t)PAGE * (256ull * c.n_blocks + 1024ull);
+  uint64_t n_pages = (pool_events + PAGE - 1) / PAGE;
+  if (n_pages > 0xFFFFFFFFull / PAGE) n_pages = 0xFFFFFFFFull / PAGE;
+  c.n_pages = (uint32_t)n_pages;
+  size_t n_cells = (size_t)(ring + 2) * c.n_blocks;
+  if (dev_alloc(e, &c.core, c.n_slots)) return e->err_code;
+  if (dev_alloc(e, &c.cell_cur, n_cells)) return e->err_code;
+  if (dev_alloc(e, &c.pool, (size_t)c.n_pages * PAGE)) return e->err_code;
+  if (dev_alloc(e, &c.page_next, c.n_pages)) return e->err_code;
+  if (dev_alloc(e, &c.page_fill, c.n_pages)) return e->err_code;
+  if (dev_alloc(e, &c.free_ring, c.n_pages)) return e->err_code;
+  if (dev_alloc(e, &c.snap_cur, c.n_blocks)) return e->err_code;
+  if (dev_alloc(e, &c.snap_fill, c.n_blocks)) return e->err_code;
+  if (dev_alloc(e, &c.win, 2)) return e->err_code;
+  if (dev_alloc(e, &c.acc, 1)) return e->err_code;
+  if (dev_alloc(e, &e->d_digest, 2)) return e->err_code;
+  if (e->size > 1) {
+    uint64_t cap = e->outbox_events ? e->outbox_events : 2 * local_initial / g + 65536;
+    c.outbox_cap = (uint32_t)cap;
+    if (dev_alloc(e, &c.outbox, (size_t)e->size * cap)) return e->err_code;
+    if (dev_alloc(e, &c.outbox_count, (size_t)e->size)) return e->err_code;
+  }
+  CK(cudaMallocHost((void **)&e->h_acc, sizeof(DevAcc)));
+  CK(cudaMallocHost((void **)&e->h_win, 2 * sizeof(WinState)));
+  CK(cudaMallocHost((void **)&e->h_counts, sizeof(uint32_t) * (size_t)e->size));
+  CK(cudaEventCreate(&e->ev0));
+  CK(cudaEventCreate(&e->ev1));
+  CK(cudaFuncSetAttribute(k_window, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          (int)e->smem_bytes));
+  CK(cudaFuncSetAttribute(k_local_min, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          (int)e->smem_bytes));
+  k_init<<<296, 256, 0, e->stream>>>(c, (uint32_t)n_cells);
+  CK(cudaGetLastError());
+  // replay schedService (simian.js:170-190)
+  for (SchedOp &op : e->ops) {
+    if (op.kind == 0) {
+      unsigned long long total = (unsigned long long)op.count * op.repeat;
+      int grid = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
+      if (grid < 1) grid = 1;
+      k_sched_bulk<<<grid, 256, 0, e->stream>>>(c, op.time, op.handler, op.data, op.cls, op.first,
+                                                op.count, op.repeat, op.seq_base);
+      CK(cudaGetLastError());
+    } else if (!op.recs.empty()) {
+      simian_event_t *d = nullptr;
+      size_t bytes = op.recs.size() * sizeof(simian_event_t);
+      CK(cudaMalloc((void **)&d, bytes));
+      CK(cudaMemcpyAsync(d, op.recs.data(), bytes, cudaMemcpyHostToDevice, e->stream));
+      uint64_t n = op.recs.size();
+      int grid = (int)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184);
+      k_ingest<<<grid, 256, 0, e->stream>>>(c, d, n, 1, 0, 0);
+      CK(cudaGetLastError());
+      CK(cudaStreamSynchronize(e->stream));
+      CK(cudaFree(d));
+    }
+  }
+  e->ops.clear();
+  k_begin<<<1, NTHREADS, 0, e->stream>>>(c);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(e->stream));
+  e->win_ix = 0;
+  e->launches = 0;
+  e->set_up = true;
+  return 0;
+}
+
+int poll(simian_engine *e) { // device flags -> pinned host copies
+  CK(cudaMemcpyAsync(e->h_acc, e->cfg.acc, sizeof(DevAcc), cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaMemcpyAsync(e->h_win, e->cfg.win, 2 * sizeof(WinState), cudaMemcpyDeviceToHost,
+                     e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  if (e->h_acc->error) return e->fail((int)e->h_acc->error, status_text((int)e->h_acc->error));
+  return 0;
+}
+
+int collect(simian_engine *e, simian_stats *out) {
+  CK(cudaMemsetAsync(e->d_digest, 0, 2 * sizeof(unsigned long long), e->stream));
+  k_digest<<<592, 256, 0, e->stream>>>(e->cfg, e->d_digest);
+  CK(cudaGetLastError());
+  unsigned long long dg[2];
+  CK(cudaMemcpyAsync(dg, e->d_digest, sizeof dg, cudaMemcpyDeviceToHost, e->stream));
+  int rc = poll(e);
+  if (out) {
+    memset(out, 0, sizeof *out);
+    const DevAcc &a = *e->h_acc;
+    out->total_events = a.committed;
+    out->windows = a.windows;
+    out->synch_events = e->size > 1 ? 2 * a.windows : 0; // simian.js:145
+    out->digest = dg[0];
+    out->state_checksum = dg[1];
+    out->ties = a.ties;
+    out->distinguishable_ties = a.dist_ties;
+    out->emitted = a.emitted;
+    out->dropped_past_end = a.dropped;
+    out->last_time = a.max_key ? simian_key_time(a.max_key) : e->start;
+    out->run_seconds =
+        std::chrono::duration<double>(std::chrono::steady_clock::now() - e->t_begin).count();
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, e->ev0, e->ev1) == cudaSuccess) out->device_seconds = ms * 1e-3;
+    out->kernel_launches = e->launches;
+    out->redistributions = a.redistributions;
+    out->far_appends = a.far_appends;
+    out->pages_allocated = a.page_allocs;
+    out->error = e->err_code;
+  }
+  return rc ? rc : e->err_code;
+}
+
+} // namespace
+
+extern "C" {
+
+const char *simian_version(void) { return "simian-b200 0.1.0 (sm_100a)"; }
+
+double simian_hash_name(const char *str) { // hash.js:21-26
+  double res = 5381;
+  size_t i = strlen(str);
+  while (i--) res = 33 * res + (double)(unsigned char)str[i];
+  return res;
+}
+
+simian_engine *simian_create(const char *simName, double startTime, double endTime,
+                             double minDelay, int rank, int size, int device) {
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev == 0) {
+    g_create_error = std::string("no CUDA device (") +
+                     (ce == cudaSuccess ? "device count 0" : cudaGetErrorString(ce)) +
+                     "): simian-b200 has no CPU fallback";
+    return nullptr;
+  }
+  if (size < 1 || rank < 0 || rank >= size) {
+    g_create_error = "bad rank/size";
+    return nullptr;
+  }
+  simian_engine *e = new simian_engine();
+  e->name = simName ? simName : "simian";
+  e->start = startTime;
+  e->end = (endTime != 0.0) ? endTime : 1e100;  // simian.js:41
+  e->min_delay = (minDelay != 0.0) ? minDelay : 1; // simian.js:42
+  e->inf_time = simian_inf_time(endTime, minDelay); // simian.js:64 (raw arguments)
+  e->rank = rank;
+  e->size = size;
+  e->device = device >= 0 ? device : rank % ndev;
+  if (cudaSetDevice(e->device) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    g_create_error = "cudaSetDevice / cudaStreamCreate failed";
+    delete e;
+    return nullptr;
+  }
+  e->own_stream = true;
+  return e;
+}
+
+void simian_destroy(simian_engine *e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  if (e->stream) cudaStreamSynchronize(e->stream);
+  for (void *p : e->allocs) cudaFree(p);
+  if (e->h_acc) cudaFreeHost(e->h_acc);
+  if (e->h_win) cudaFreeHost(e->h_win);
+  if (e->h_counts) cudaFreeHost(e->h_counts);
+  if (e->ev0) cudaEventDestroy(e->ev0);
+  if (e->ev1) cudaEventDestroy(e->ev1);
+  if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
+  delete e;
+}
+
+const char *simian_last_error(simian_engine *e) {
+  return e ? e->err.c_str() : g_create_error.c_str();
+}
+
+int simian_set_option(simian_engine *e, const char *key, double v) {
+  if (e->set_up) return e->fail(SIMIAN_ERR_RUNNING, "options must be set before the first run");
+  std::string k = key;
+  if (k == "seed") e->seed = (uint64_t)v;
+  else if (k == "bucket_width") e->bucket_width = v;
+  else if (k == "ring_buckets") e->ring = (uint32_t)v;
+  else if (k == "pool_events") e->pool_events = (uint64_t)v;
+  else if (k == "outbox_events") e->outbox_events = (uint64_t)v;
+  else if (k == "launch_batch") e->launch_batch = v < 1 ? 1 : (int)v;
+  else if (k == "tie_check") e->tie_check = v != 0;
+  else return e->fail(SIMIAN_ERR_BAD_ARGUMENT, "unknown option " + k);
+  return 0;
+}
+
+int simian_set_stream(simian_engine *e, void *s) {
+  if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
+  e->stream = (cudaStream_t)s;
+  e->own_stream = false;
+  return 0;
+}
+
+int simian_define_class(simian_engine *e, const char *className, uint32_t stateBytes) {
+  auto it = e->class_ix.find(className);
+  if (it != e->class_ix.end()) return it->second;
+  if (e->set_up) return -e->fail(SIMIAN_ERR_RUNNING, "classes must be defined before the first run");
+  if ((int)e->classes.size() >= SIMIAN_MAX_CLASSES || (stateBytes & 7u))
+    return -e->fail(SIMIAN_ERR_BAD_ARGUMENT, "too many classes or stateBytes not a multiple of 8");
+  HostClass h;
+  h.name = className;
+  h.state_bytes = stateBytes;
+  h.name_hash = simian_hash_name(className);
+  h.first_id = e->n_ids;
+  memset(h.fn_of_service, 0, sizeof h.fn_of_service);
+  e->classes.push_back(h);
+  e->class_ix[className] = (int)e->classes.size() - 1;
+  return (int)e->classes.size() - 1;
+}
+
+int simian_set_class_params(simian_engine *e, const char *className, const void *p,
+                            uint32_t bytes) {
+  auto it = e->class_ix.find(className);
+  if (it == e->class_ix.end()) return e->fail(SIMIAN_ERR_UNKNOWN_NAME, "unknown class");
+  if (e->set_up) return e->fail(SIMIAN_ERR_RUNNING, "parameters must be set before the first run");
+  e->classes[it->second].params.assign((const uint8_t *)p, (const uint8_t *)p + bytes);
+  return 0;
+}
+
+int simian_add_entities(simian_engine *e, const char *className, uint32_t firstNum,
+                        uint32_t count, const void *initState) {
+  if (e->running || e->set_up) // simian.js:215
+    return e->fail(SIMIAN_ERR_RUNNING, status_text(SIMIAN_ERR_RUNNING));
+  int ci = simian_define_class(e, className, 0);
+  if (ci < 0) return -ci;
+  HostClass &h = e->classes[ci];
+  if (firstNum != h.count || h.first_id + h.count != e->n_ids)
+    return e->fail(SIMIAN_ERR_BAD_ARGUMENT,
+                   "instances of a class must be added contiguously from 0, class after class");
+  if (initState && h.state_bytes) {
+    h.init_state.resize((size_t)(h.count + count) * h.state_bytes, 0);
+    memcpy(&h.init_state[(size_t)h.count * h.state_bytes], initState,
+           (size_t)count * h.state_bytes);
+    h.has_init = true;
+  } else if (h.has_init) {
+    h.init_state.resize((size_t)(h.count + count) * h.state_bytes, 0);
+  }
+  h.count += count;
+  e->n_ids += count;
+  return 0;
+}
+
+int simian_intern_service(simian_engine *e, const char *serviceName) {
+  auto it = e->service_ix.find(serviceName);
+  if (it != e->service_ix.end()) return it->second;
+  int id = (int)e->service_ix.size();
+  if (id >= SIMIAN_MAX_SERVICES) return -e->fail(SIMIAN_ERR_BAD_ARGUMENT, "too many services");
+  e->service_ix[serviceName] = id;
+  return id;
+}
+
+int simian_attach_service(simian_engine *e, const char *className, const char *serviceName,
+                          const char *deviceFnName) {
+  if (e->set_up) return e->fail(SIMIAN_ERR_RUNNING, "services must be attached before the first run");
+  int ci = simian_define_class(e, className, 0);
+  if (ci < 0) return -ci;
+  int fn = builtin_fn_by_name(deviceFnName);
+  if (!fn)
+    return e->fail(SIMIAN_ERR_UNKNOWN_NAME, std::string("no device function named ") + deviceFnName);
+  int sid = simian_intern_service(e, serviceName);
+  if (sid < 0) return -sid;
+  e->classes[ci].fn_of_service[sid] = (uint8_t)fn;
+  return 0;
+}
+
+int64_t simian_first_id(simian_engine *e, const char *className) {
+  auto it = e->class_ix.find(className);
+  return it == e->class_ix.end() ? -1 : (int64_t)e->classes[it->second].first_id;
+}
+
+int simian_base_rank(simian_engine *e, const char *className) {
+  auto it = e->class_ix.find(className);
+  if (it == e->class_ix.end()) return -1;
+  return (int)fmod(e->classes[it->second].name_hash, (double)e->size);
+}
+
+int simian_sched_service_bulk(simian_engine *e, double time, const char *serviceName,
+                              uint64_t data, const char *rx, uint32_t firstId, uint32_t count,
+                              uint32_t repeat) {
+  if (e->set_up) return e->fail(SIMIAN_ERR_RUNNING, "schedService after the run started");
+  auto it = e->class_ix.find(rx);
+  if (it == e->class_ix.end()) return e->fail(SIMIAN_ERR_UNKNOWN_NAME, "unknown entity class");
+  HostClass &h = e->classes[it->second];
+  if ((uint64_t)firstId + count > h.count) return e->fail(SIMIAN_ERR_UNKNOWN_NAME, "no such entity");
+  int sid = simian_intern_service(e, serviceName);
+  if (sid < 0) return -sid;
+  uint32_t seq_base = e->sched_seq;
+  e->sched_seq += count * repeat;
+  if (time > e->end) return 0; // simian.js:173
+  if (time < e->start) return e->fail(SIMIAN_ERR_OUT_OF_ORDER, "schedService before startTime");
+  SchedOp op;
+  op.kind = 0;
+  op.time = time;
+  op.handler = (uint32_t)sid;
+  op.data = data;
+  op.cls = it->second;
+  op.first = firstId;
+  op.count = count;
+  op.repeat = repeat;
+  op.seq_base = seq_base;
+  e->ops.push_back(std::move(op));
+  e->initial_events += (uint64_t)count * repeat;
+  return 0;
+}
+
+int simian_sched_service(simian_engine *e, double time, const char *serviceName, uint64_t data,
+                         const char *rx, uint32_t rxId) {
+  return simian_sched_service_bulk(e, time, serviceName, data, rx, rxId, 1, 1);
+}
+
+int simian_sched_events(simian_engine *e, const simian_event_t *ev, uint64_t n) {
+  if (e->set_up) return e->fail(SIMIAN_ERR_RUNNING, "schedService after the run started");
+  SchedOp op;
+  op.kind = 1;
+  op.recs.assign(ev, ev + n);
+  for (uint64_t i = 0; i < n; i++) {
+    if (ev[i].dst >= e->n_ids) return e->fail(SIMIAN_ERR_UNKNOWN_NAME, "no such entity");
+    if (ev[i].time < e->start) return e->fail(SIMIAN_ERR_OUT_OF_ORDER, "event before startTime");
+  }
+  e->ops.push_back(std::move(op));
+  e->initial_events += n;
+  return 0;
+}
+
+int simian_run_begin(simian_engine *e) {
+  if (e->err_code) return e->err_code;
+  CK(cudaSetDevice(e->device));
+  e->t_begin = std::chrono::steady_clock::now();
+  int rc = setup(e);
+  if (rc) return rc;
+  e->running = true;
+  CK(cudaEventRecord(e->ev0, e->stream));
+  return 0;
+}
+
+int simian_window_process(simian_engine *e) {
+  k_window<<<e->cfg.n_blocks, NTHREADS, e->smem_bytes, e->stream>>>(e->cfg, e->win_ix,
+                                                                  e->size == 1);
+  CK(cudaGetLastError());
+  e->launches++;
+  return 0;
+}
+
+int simian_window_outbox(simian_engine *e, uint32_t *hostCounts, void **devOutbox,
+                         uint64_t *cap) {
+  if (e->size == 1) {
+    hostCounts[0] = 0;
+  } else {
+    CK(cudaMemcpyAsync(e->h_counts, e->cfg.outbox_count, sizeof(uint32_t) * (size_t)e->size,
+                       cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    memcpy(hostCounts, e->h_counts, sizeof(uint32_t) * (size_t)e->size);
+  }
+  if (devOutbox) *devOutbox = e->cfg.outbox;
+  if (cap) *cap = e->cfg.outbox_cap;
+  return 0;
+}
+
+int simian_window_ingest(simian_engine *e, const void *devRecords, uint64_t n) {
+  if (!n) return 0;
+  int grid = (int)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184);
+  k_ingest<<<grid, 256, 0, e->stream>>>(e->cfg, (const simian_event_t *)devRecords, n, 0, 1,
+                                        e->win_ix);
+  CK(cudaGetLastError());
+  e->launches++;
+  return 0;
+}
+
+int simian_window_local_min(simian_engine *e, void **devMinVec) {
+  k_local_min<<<1, NTHREADS, e->smem_bytes, e->stream>>>(e->cfg, e->win_ix);
+  CK(cudaGetLastError());
+  e->launches++;
+  if (devMinVec) *devMinVec = (void *)e->cfg.acc->minvec;
+  return 0;
+}
+
+int simian_window_advance(simian_engine *e, int *done) {
+  k_advance<<<1, NTHREADS, 0, e->stream>>>(e->cfg, e->win_ix);
+  CK(cudaGetLastError());
+  e->launches++;
+  e->win_ix++;
+  int rc = poll(e);
+  if (rc) return rc;
+  if (done) *done = (int)e->h_win[e->win_ix & 1u].done;
+  return 0;
+}
+
+int simian_run_end(simian_engine *e, simian_stats *out) {
+  cudaEventRecord(e->ev1, e->stream);
+  e->running = false;
+  return collect(e, out);
+}
+
+int simian_run(simian_engine *e, simian_stats *out) {
+  if (e->size != 1)
+    return e->fail(SIMIAN_ERR_BAD_ARGUMENT,
+                   "size > 1: drive the windows with the stepping calls (the host runs the collectives)");
+  int rc = simian_run_begin(e);
+  if (rc) return rc;
+  int batch = e->launch_batch;
+  for (;;) {
+    for (int i = 0; i < batch; i++) {
+      k_window<<<e->cfg.n_blocks, NTHREADS, e->smem_bytes, e->stream>>>(e->cfg, e->win_ix, 1);
+      e->win_ix++;
+      e->launches++;
+    }
+    CK(cudaGetLastError());
+    rc = poll(e);
+    if (rc) break;
+    if (e->h_win[e->win_ix & 1u].done) break;
+    if (e->h_acc->window_index != e->win_ix) { // a launch made no progress
+      rc = e->fail(SIMIAN_ERR_CUDA, "window kernel did not advance");
+      break;
+    }
+    if (batch < 256) batch *= 2;
+  }
+  int rc2 = simian_run_end(e, out);
+  return rc ? rc : rc2;
+}
+
+static int read_core(simian_engine *e, const char *className, uint32_t first, uint32_t count,
+                     uint64_t *out, int which) {
+  auto it = e->class_ix.find(className);
+  if (it == e->class_ix.end()) return e->fail(SIMIAN_ERR_UNKNOWN_NAME, "unknown class");
+  if (!e->set_up) return e->fail(SIMIAN_ERR_BAD_ARGUMENT, "nothing has run yet");
+  HostClass &h = e->classes[it->second];
+  if ((uint64_t)first + count > h.count) return e->fail(SIMIAN_ERR_UNKNOWN_NAME, "no such entity");
+  std::vector<EntityCore> loc(h.n_local);
+  CK(cudaSetDevice(e->device));
+  CK(cudaMemcpy(loc.data(), e->cfg.core + h.slot_base, sizeof(EntityCore) * (size_t)h.n_local,
+                cudaMemcpyDeviceToHost));
+  uint32_t g = (uint32_t)e->size;
+  for (uint32_t j = 0; j < h.n_local; j++) {
+    uint32_t num = j * g + h.rank_off;
+    if (num >= first && num < first + count) out[num - first] = which ? loc[j].hash : loc[j].count;
+  }
+  return 0;
+}
+
+int simian_read_counts(simian_engine *e, const char *className, uint32_t first, uint32_t count,
+                       uint64_t *out) {
+  return read_core(e, className, first, count, out, 0);
+}
+
+int simian_read_trace_hashes(simian_engine *e, const char *className, uint32_t first,
+                             uint32_t count, uint64_t *out) {
+  return read_core(e, className, first, count, out, 1);
+}
+
+int simian_read_state(simian_engine *e, const char *className, uint32_t first, uint32_t count,
+                      void *out) {
+  auto it = e->class_ix.find(className);
+  if (it == e->class_ix.end()) return e->fail(SIMIAN_ERR_UNKNOWN_NAME, "unknown class");
+  if (!e->set_up) return e->fail(SIMIAN_ERR_BAD_ARGUMENT, "nothing has run yet");
+  HostClass &h = e->classes[it->second];
+  if ((uint64_t)first + count > h.count) return e->fail(SIMIAN_ERR_UNKNOWN_NAME, "no such entity");
+  if (!h.state_bytes) return 0;
+  std::vector<uint8_t> loc((size_t)h.n_local * h.state_bytes);
+  CK(cudaSetDevice(e->device));
+  CK(cudaMemcpy(loc.data(), h.d_state, loc.size(), cudaMemcpyDeviceToHost));
+  uint32_t g = (uint32_t)e->size;
+  for (uint32_t j = 0; j < h.n_local; j++) {
+    uint32_t num = j * g + h.rank_off;
+    if (num >= first && num < first + count)
+      memcpy((uint8_t *)out + (size_t)(num - first) * h.state_bytes,
+             &loc[(size_t)j * h.state_bytes], h.state_bytes);
+  }
+  return 0;
+}
+
+} // extern "C"

@@ -1,0 +1,1157 @@
+// kernels.cuh -- hand-written sm_100a kernels of the simian-b200 window loop.
+//
+// One lookahead window of the reference (SimianJS/simian.js:119-148) is ONE
+// launch of k_window:
+//   K2  coalesced dequeue of every event below the window bound from the
+//       block's calendar cells                       (eventQ.pop, eventQ.js:53-92)
+//   K3  handlers of all entities in parallel, each entity's events in
+//       (time, handler, src, seq) order               (simian.js:124-133)
+//   K4  emit: lock-free paged append of 32-B records into the destination
+//       cell, or into the per-peer outbox             (entity.js:47-67, eventQ.push)
+//   K1  LBTS: block min-reduction of leftover + emitted times, one atomicMin
+//       per CTA, last CTA computes the next window    (simian.js:120,143-147)
+// Compiled with -fmad=false: include/simian_spec.h must see no FMA contraction.
+#pragma once
+#include "device_types.cuh"
+
+#define EPB SIMIAN_EPB
+#define NTHREADS SIMIAN_THREADS
+#define PAGE SIMIAN_PAGE
+#define NREFS SIMIAN_REFS
+#define PGMAX SIMIAN_PGMAX
+#define PG_FREE_FLAG 0x8000u
+
+// ---------------------------------------------------------------- helpers --
+
+struct RecBits { // the 32-byte record as four 64-bit words
+  unsigned long long q0, q1, q2, q3;
+  __device__ __forceinline__ double time() const { return __longlong_as_double((long long)q0); }
+  __device__ __forceinline__ uint32_t dst() const { return (uint32_t)q1; }
+  __device__ __forceinline__ uint32_t src() const { return (uint32_t)(q1 >> 32); }
+  __device__ __forceinline__ uint32_t handler() const { return (uint32_t)(q2 & 0xFFFFu); }
+  __device__ __forceinline__ uint32_t flags() const { return (uint32_t)((q2 >> 16) & 0xFFFFu); }
+  __device__ __forceinline__ uint32_t seq() const { return (uint32_t)(q2 >> 32); }
+  __device__ __forceinline__ unsigned long long data() const { return q3; }
+};
+
+__device__ __forceinline__ RecBits make_rec(double time, uint32_t dst, uint32_t src,
+                                            uint32_t handler, uint32_t flags,
+                                            uint32_t seq, unsigned long long data) {
+  RecBits r;
+  r.q0 = (unsigned long long)__double_as_longlong(time);
+  r.q1 = (unsigned long long)dst | ((unsigned long long)src << 32);
+  r.q2 = (unsigned long long)(handler & 0xFFFFu) | ((unsigned long long)(flags & 0xFFFFu) << 16) |
+         ((unsigned long long)seq << 32);
+  r.q3 = data;
+  return r;
+}
+
+// one 256-bit transaction per record: a scattered append is exactly one sector
+__device__ __forceinline__ void st_rec(simian_event_t *p, const RecBits &r) {
+  asm volatile("st.global.v4.u64 [%0], {%1,%2,%3,%4};" ::"l"(p), "l"(r.q0), "l"(r.q1),
+               "l"(r.q2), "l"(r.q3)
+               : "memory");
+}
+__device__ __forceinline__ RecBits ld_rec(const simian_event_t *p) {
+  RecBits r;
+  asm volatile("ld.global.v4.u64 {%0,%1,%2,%3}, [%4];"
+               : "=l"(r.q0), "=l"(r.q1), "=l"(r.q2), "=l"(r.q3)
+               : "l"(p));
+  return r;
+}
+// first half only: {time, dst|src}
+__device__ __forceinline__ void ld_rec_head(const simian_event_t *p, unsigned long long &q0,
+                                            unsigned long long &q1) {
+  asm volatile("ld.global.v2.u64 {%0,%1}, [%2];" : "=l"(q0), "=l"(q1) : "l"(p));
+}
+// L2-coherent loads (bypass L1) for data other CTAs wrote in this launch
+__device__ __forceinline__ uint32_t ld_cg(const uint32_t *p) {
+  uint32_t v;
+  asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ unsigned long long ld_cg64(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(v) : "l"(p));
+  return v;
+}
+
+__device__ __forceinline__ long long tb_of(const DevCfg &c, double t) {
+  double x = (t - c.start) * c.inv_w;
+  if (!(x < 4.0e18)) return 4000000000000000000LL; // +inf / NaN / huge
+  if (x < -4.0e18) return -4000000000000000000LL;
+  return __double2ll_rd(x);
+}
+
+__device__ __forceinline__ void set_error(const DevCfg &c, unsigned int code) {
+  atomicCAS(&c.acc->error, 0u, code);
+}
+
+// entity id <-> (rank, slot) under the reference placement
+//   getOffsetRank(name, num) = (baseRanks[name] + num) % size   simian.js:196-198
+__device__ __forceinline__ int class_of_gid(const DevCfg &c, uint32_t gid) {
+  int k = 0;
+#pragma unroll 1
+  for (int i = 1; i < c.n_classes; i++)
+    if (gid >= c.cls[i].first_id) k = i;
+  return k;
+}
+__device__ __forceinline__ void route_gid(const DevCfg &c, uint32_t gid, int &rank,
+                                          uint32_t &slot) {
+  int k = class_of_gid(c, gid);
+  const DevClass &cl = c.cls[k];
+  uint32_t num = gid - cl.first_id;
+  if (c.size == 1) {
+    rank = 0;
+    slot = cl.slot_base + num;
+  } else {
+    uint32_t g = (uint32_t)c.size;
+    rank = (int)((cl.base_rank + num) % g);
+    // slot on the OWNING rank: classes are laid out in the same order there
+    // and class k's slot_base on rank r is sum over earlier classes of their
+    // local counts on r -- recomputed here because it differs per rank.
+    uint32_t sb = 0;
+    for (int i = 0; i < k; i++) {
+      const DevClass &ci = c.cls[i];
+      uint32_t ro = ((uint32_t)rank + g - ci.base_rank % g) % g;
+      sb += (ci.count > ro) ? (ci.count - ro + g - 1) / g : 0;
+    }
+    slot = sb + num / g;
+  }
+}
+__device__ __forceinline__ uint32_t gid_of_slot(const DevCfg &c, uint32_t slot, int &k) {
+  k = 0;
+#pragma unroll 1
+  for (int i = 1; i < c.n_classes; i++)
+    if (slot >= c.cls[i].slot_base) k = i;
+  const DevClass &cl = c.cls[k];
+  uint32_t j = slot - cl.slot_base;
+  return cl.first_id + (c.size == 1 ? j : j * (uint32_t)c.size + cl.rank_off);
+}
+
+// ------------------------------------------------------ paged cell append --
+
+struct AppendCtx { // per-CTA, in shared memory
+  uint32_t far_appends, page_allocs;
+};
+
+#define SIMIAN_LOCKED 0xFFFFFFFEu // cell head while its first page is installed
+
+__device__ __forceinline__ void append_ctx_init(AppendCtx &ax) {
+  if (threadIdx.x == 0) ax.far_appends = ax.page_allocs = 0;
+}
+
+// Pop a page from the free ring.  Pages pushed during a launch become
+// allocatable only after the next advance step raises alloc_limit, so a launch
+// never pops a ring slot that is being written.
+__device__ __forceinline__ uint32_t page_get(const DevCfg &c, AppendCtx &ax,
+                                             unsigned long long alloc_limit) {
+  unsigned long long i = atomicAdd(&c.acc->alloc_head, 1ull);
+  if (i >= alloc_limit) {
+    set_error(c, SIMIAN_ERR_POOL_EXHAUSTED);
+    return SIMIAN_NONE;
+  }
+  atomicAdd(&ax.page_allocs, 1u);
+  return c.free_ring[i % c.n_pages];
+}
+
+__device__ __forceinline__ void page_free(const DevCfg &c, uint32_t p) {
+  unsigned long long pos = atomicAdd(&c.acc->free_tail, 1ull);
+  c.free_ring[pos % c.n_pages] = p;
+}
+
+// call from all threads at the end of any kernel that appended
+__device__ __forceinline__ void append_ctx_flush(const DevCfg &c, AppendCtx &ax) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (ax.far_appends) atomicAdd(&c.acc->far_appends, (unsigned long long)ax.far_appends);
+    if (ax.page_allocs) atomicAdd(&c.acc->page_allocs, (unsigned long long)ax.page_allocs);
+  }
+}
+
+// eventQ.push (eventQ.js:29-43) as an append to the cell's page chain.
+// Slot claim = one atomicAdd on the head page's fill counter.  Exactly one
+// thread installs a page: the one whose claim returned PAGE (first overflow),
+// or the winner of the NONE->LOCKED CAS for an empty cell; the others wait for
+// the head to change (starvation-free under independent thread scheduling).
+__device__ __forceinline__ void cell_append(const DevCfg &c, AppendCtx &ax,
+                                            unsigned long long alloc_limit, uint32_t cell,
+                                            const RecBits &r) {
+  uint32_t *curp = c.cell_cur + cell;
+#pragma unroll 1
+  for (;;) {
+    uint32_t p = ld_cg(curp);
+    if (p == SIMIAN_LOCKED) {
+      if (ld_cg(&c.acc->error)) return;
+      __nanosleep(40);
+      continue;
+    }
+    if (p == SIMIAN_NONE) {
+      if (atomicCAS(curp, SIMIAN_NONE, SIMIAN_LOCKED) == SIMIAN_NONE) {
+        uint32_t np = page_get(c, ax, alloc_limit);
+        if (np == SIMIAN_NONE) {
+          atomicExch(curp, SIMIAN_NONE);
+          return; // sticky error set
+        }
+        c.page_next[np] = SIMIAN_NONE;
+        c.page_fill[np] = 1; // slot 0 is ours
+        st_rec(c.pool + (size_t)np * PAGE, r);
+        __threadfence();
+        atomicExch(curp, np);
+        return;
+      }
+      continue;
+    }
+    uint32_t i = atomicAdd(&c.page_fill[p], 1u);
+    if (i < (uint32_t)PAGE) {
+      st_rec(c.pool + ((size_t)p * PAGE + i), r);
+      return;
+    }
+    if (i == (uint32_t)PAGE) { // first overflow: install the next page
+      uint32_t np = page_get(c, ax, alloc_limit);
+      if (np == SIMIAN_NONE) return;
+      c.page_next[np] = p;
+      c.page_fill[np] = 1;
+      st_rec(c.pool + (size_t)np * PAGE, r);
+      __threadfence();
+      atomicExch(curp, np);
+      return;
+    }
+#pragma unroll 1
+    while (ld_cg(curp) == p) { // wait for the installer
+      if (ld_cg(&c.acc->error)) return;
+      __nanosleep(40);
+    }
+  }
+}
+
+// route a record whose dst is a LOCAL SLOT into the calendar or the far row
+__device__ __forceinline__ void append_local(const DevCfg &c, AppendCtx &ax, long long tb_clean,
+                                             uint32_t far_row, unsigned long long alloc_limit,
+                                             const RecBits &r) {
+  uint32_t b = r.dst() / EPB;
+  long long tb = tb_of(c, r.time());
+  uint32_t cell;
+  if (tb < tb_clean) {
+    set_error(c, SIMIAN_ERR_OUT_OF_ORDER);
+    return;
+  }
+  if (tb - tb_clean < (long long)c.ring) {
+    cell = (uint32_t)(tb & (long long)c.ring_mask) * c.n_blocks + b;
+  } else {
+    cell = (c.ring + far_row) * c.n_blocks + b;
+    atomicMin(&c.acc->far_min[far_row], simian_time_key(r.time()));
+    atomicAdd(&ax.far_appends, 1u);
+  }
+  cell_append(c, ax, alloc_limit, cell, r);
+}
+
+// ------------------------------------------------------------ init / load --
+
+__global__ void k_init(const __grid_constant__ DevCfg c, uint32_t n_cells) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t j = i; j < c.n_pages; j += stride) {
+    c.free_ring[j] = (uint32_t)j;
+    c.page_fill[j] = 0;
+    c.page_next[j] = SIMIAN_NONE;
+  }
+  for (size_t j = i; j < n_cells; j += stride) c.cell_cur[j] = SIMIAN_NONE;
+  for (size_t j = i; j < c.n_blocks; j += stride) {
+    c.snap_cur[j] = SIMIAN_NONE;
+    c.snap_fill[j] = 0;
+  }
+  for (size_t j = i; j < c.n_slots; j += stride) {
+    EntityCore z;
+    z.count = 0;
+    z.hash = 0;
+    c.core[j] = z;
+  }
+  if (i == 0) {
+    DevAcc *a = c.acc;
+    a->min_key = SIMIAN_KEY_NONE;
+    a->far_min[0] = a->far_min[1] = SIMIAN_KEY_NONE;
+    a->alloc_head = 0;
+    a->free_tail = c.n_pages;
+    a->committed = a->emitted = a->dropped = a->ties = a->dist_ties = 0;
+    a->max_key = 0;
+    a->windows = a->redistributions = a->far_appends = a->page_allocs = a->leaked_pages = 0;
+    a->ticket = 0;
+    a->error = 0;
+    a->window_index = 0;
+    a->minvec[0] = a->minvec[1] = 0;
+    WinState w;
+    w.gmin = c.start;
+    w.hi = c.start + c.min_delay;
+    w.tb_lo = 0;
+    w.tb_hi = 0;
+    w.tb_clean = tb_of(c, c.start);
+    w.tb_clean_new = w.tb_clean;
+    w.done = 0;
+    w.redist = 0;
+    w.far_row = 0;
+    w.pad_ = 0;
+    w.alloc_limit = c.n_pages;
+    c.win[0] = w;
+    c.win[1] = w;
+  }
+  for (size_t j = i; j < (size_t)c.size; j += stride)
+    if (c.outbox_count) c.outbox_count[j] = 0;
+}
+
+// schedService loop on the device (simian.js:170-190 for every (k, i))
+__global__ void k_sched_bulk(const __grid_constant__ DevCfg c, double time, uint32_t handler, unsigned long long data,
+                             int cls, uint32_t first, uint32_t count, uint32_t repeat,
+                             uint32_t seq_base) {
+  __shared__ AppendCtx ax;
+  append_ctx_init(ax);
+  __syncthreads();
+  const WinState &W = c.win[0];
+  unsigned long long total = (unsigned long long)count * repeat;
+  unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  for (unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+       idx < total; idx += stride) {
+    uint32_t i = (uint32_t)(idx % count);
+    uint32_t gid = c.cls[cls].first_id + first + i;
+    int rank;
+    uint32_t slot;
+    route_gid(c, gid, rank, slot);
+    if (rank != c.rank) continue; // only the owner pushes (simian.js:177)
+    RecBits r = make_rec(time, slot, SIMIAN_NULL_ENTITY, handler, SIMIAN_EVF_SCHED,
+                         seq_base + (uint32_t)idx, data);
+    append_local(c, ax, W.tb_clean, W.far_row, W.alloc_limit, r);
+  }
+  append_ctx_flush(c, ax);
+}
+
+// Records -> local calendar.  dst_is_gid: records come from the host API
+// (global ids, owner filter); otherwise from a peer's outbox (dst = our slot).
+__global__ void k_ingest(const __grid_constant__ DevCfg c, const simian_event_t *recs, unsigned long long n,
+                         int dst_is_gid, int track_min, uint32_t win_ix) {
+  __shared__ AppendCtx ax;
+  __shared__ unsigned long long smin;
+  append_ctx_init(ax);
+  if (threadIdx.x == 0) smin = SIMIAN_KEY_NONE;
+  __syncthreads();
+  const WinState &W = c.win[win_ix & 1u];
+  unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  unsigned long long mn = SIMIAN_KEY_NONE;
+  for (unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+       idx < n; idx += stride) {
+    RecBits r = ld_rec(recs + idx);
+    if (dst_is_gid) {
+      if (r.time() > c.end) continue; // simian.js:173
+      int rank;
+      uint32_t slot;
+      route_gid(c, r.dst(), rank, slot);
+      if (rank != c.rank) continue;
+      r.q1 = (unsigned long long)slot | (r.q1 & 0xFFFFFFFF00000000ull);
+    }
+    unsigned long long k = simian_time_key(r.time());
+    mn = k < mn ? k : mn;
+    append_local(c, ax, W.tb_clean, W.far_row, W.alloc_limit, r);
+  }
+  if (track_min) {
+    for (int o = 16; o; o >>= 1) {
+      unsigned long long x = __shfl_xor_sync(0xffffffffu, mn, o);
+      mn = x < mn ? x : mn;
+    }
+    if ((threadIdx.x & 31) == 0 && mn != SIMIAN_KEY_NONE) atomicMin(&smin, mn);
+    __syncthreads();
+    if (threadIdx.x == 0 && smin != SIMIAN_KEY_NONE) atomicMin(&c.acc->min_key, smin);
+  }
+  append_ctx_flush(c, ax);
+}
+
+// ---------------------------------------------------------- window kernel --
+
+struct WindowShared {
+  WinState W;
+  AppendCtx ax;
+  unsigned long long min_key, max_key, free_base;
+  uint32_t committed, emitted, dropped, ties, dties;
+  uint32_t npg, nfree, nfree_w, total_due, pass_lo, pass_hi, is_last, found;
+  long long scan_j;
+  uint32_t warp_tmp[32];
+  uint32_t cnt[EPB];
+  uint32_t off[EPB + 1];
+  uint32_t pg_id[PGMAX];
+  uint16_t pg_cnt[PGMAX];
+  uint32_t refs[NREFS];
+};
+
+// per-thread accumulators of the handler phase
+struct ThreadAcc {
+  unsigned long long min_key, max_key;
+  uint32_t committed, emitted, dropped, ties, dties;
+};
+
+// what a handler reaches through `self` on the device (see simian_models.h)
+struct DevCtx {
+  const DevCfg &c;
+  WindowShared &sh;
+  ThreadAcc &ta;
+  const DevClass *cl;
+  uint32_t self_gid, self_slot;
+  unsigned long long commit_idx, key;
+  uint32_t n_emit;
+  double now_;
+  uint32_t handler_, src_;
+  unsigned long long data_;
+  // same-window self-sends (rx omitted, offset < minDelay allowed: entity.js:41)
+  int npend;
+  double pend_time[SIMIAN_SELF_MAX];
+  unsigned long long pend_q2[SIMIAN_SELF_MAX], pend_data[SIMIAN_SELF_MAX];
+
+  __device__ __forceinline__ DevCtx(const DevCfg &c_, WindowShared &sh_, ThreadAcc &ta_)
+      : c(c_), sh(sh_), ta(ta_), npend(0) {}
+
+  __device__ __forceinline__ double now() const { return now_; }
+  __device__ __forceinline__ uint32_t self_id() const { return self_gid; }
+  __device__ __forceinline__ unsigned long long draw(uint32_t i) const {
+    return simian_rng_draw(key, i);
+  }
+  __device__ __forceinline__ uint16_t handler() const { return (uint16_t)handler_; }
+  __device__ __forceinline__ const void *params() const { return cl->params; }
+  __device__ __forceinline__ void *state() const {
+    return cl->state_bytes
+               ? (void *)(cl->state + (size_t)(self_slot - cl->slot_base) * cl->state_bytes)
+               : nullptr;
+  }
+  __device__ __forceinline__ uint32_t src() const { return src_; }
+
+  // Entity.reqService (entity.js:35-68)
+  __device__ __forceinline__ void req_service(double offset, uint16_t service,
+                                              unsigned long long data, uint32_t rx) {
+    uint32_t k = n_emit++;
+    if (rx != SIMIAN_NULL_ENTITY && offset < c.min_delay) { // entity.js:41-45
+      set_error(c, SIMIAN_ERR_LOOKAHEAD);
+      return;
+    }
+    double time = now_ + offset; // entity.js:47
+    if (time > c.end) {          // entity.js:48
+      ta.dropped++;
+      return;
+    }
+    uint32_t seq = simian_emit_seq(commit_idx, k);
+    ta.emitted++;
+    const WinState &W = sh.W;
+    if (rx == SIMIAN_NULL_ENTITY) { // entity.js:50-51
+      if (time < now_) {
+        set_error(c, SIMIAN_ERR_OUT_OF_ORDER); // simian.js:124-125 at pop time
+        return;
+      }
+      if (time < W.hi) { // lands inside this window: stays with the entity
+        if (npend >= SIMIAN_SELF_MAX) {
+          set_error(c, SIMIAN_ERR_SELF_PENDING);
+          return;
+        }
+        pend_time[npend] = time;
+        pend_q2[npend] = (unsigned long long)service | ((unsigned long long)seq << 32);
+        pend_data[npend] = data;
+        npend++;
+        return;
+      }
+      RecBits r = make_rec(time, self_slot, self_gid, service, 0, seq, data);
+      unsigned long long tk = simian_time_key(time);
+      ta.min_key = tk < ta.min_key ? tk : ta.min_key;
+      append_local(c, sh.ax, W.tb_clean, W.far_row, W.alloc_limit, r);
+      return;
+    }
+    int rank;
+    uint32_t slot;
+    route_gid(c, rx, rank, slot); // getOffsetRank, entity.js:62
+    RecBits r = make_rec(time, slot, self_gid, service, 0, seq, data);
+    unsigned long long tk = simian_time_key(time);
+    if (rank == c.rank) { // entity.js:64
+      ta.min_key = tk < ta.min_key ? tk : ta.min_key;
+      append_local(c, sh.ax, W.tb_clean, W.far_row, W.alloc_limit, r);
+    } else { // entity.js:66: staged for the per-window exchange
+      uint32_t i = atomicAdd(&c.outbox_count[rank], 1u);
+      if (i >= c.outbox_cap) {
+        set_error(c, SIMIAN_ERR_OUTBOX_FULL);
+        return;
+      }
+      st_rec(c.outbox + ((size_t)rank * c.outbox_cap + i), r);
+    }
+  }
+};
+
+__device__ __forceinline__ void run_handler(DevCtx &ctx, uint32_t fn) {
+  switch (fn) {
+    case SIMIAN_FN_PHOLD_GENERATE:
+      simian_phold_generate(ctx);
+      break;
+    case SIMIAN_FN_COUNT_ONLY:
+      simian_noop(ctx);
+      break;
+    default:
+      set_error(ctx.c, SIMIAN_ERR_UNKNOWN_NAME);
+  }
+}
+
+// key order (time, handler, src, seq): a < b
+__device__ __forceinline__ bool key_lt(unsigned long long a1, unsigned long long a2, uint32_t a3,
+                                       unsigned long long b1, unsigned long long b2,
+                                       uint32_t b3) {
+  if (a1 != b1) return a1 < b1;
+  if (a2 != b2) return a2 < b2;
+  return a3 < b3;
+}
+
+// All due events of one entity, in order (simian.js:122-134 restricted to one
+// entity; entities never interact inside a window because cross-entity sends
+// carry offset >= minDelay, entity.js:41).
+__device__ __noinline__ void process_entity(const DevCfg &c, WindowShared &sh, ThreadAcc &ta,
+                                            uint32_t slot, const uint32_t *refs, uint32_t n) {
+  int k;
+  DevCtx ctx(c, sh, ta);
+  ctx.self_slot = slot;
+  ctx.self_gid = gid_of_slot(c, slot, k);
+  ctx.cl = &c.cls[k];
+  EntityCore st = c.core[slot];
+  unsigned long long p1 = 0, p2 = 0;
+  uint32_t p3 = 0;
+  bool have_prev = false, have_last = false;
+  double last_time = 0;
+  unsigned long long last_q = 0, last_data = 0;
+  uint32_t taken = 0;
+#pragma unroll 1
+  for (;;) {
+    // next event of the static group: min key strictly above the previous one
+    bool have_g = false;
+    RecBits g;
+    unsigned long long g1 = 0, g2 = 0;
+    uint32_t g3 = 0;
+    if (taken < n) {
+      if (n == 1) {
+        g = ld_rec(c.pool + refs[0]);
+        have_g = true;
+      } else {
+#pragma unroll 1
+        for (uint32_t j = 0; j < n; j++) {
+          RecBits r = ld_rec(c.pool + refs[j]);
+          unsigned long long k1 = simian_time_key(r.time());
+          unsigned long long k2 = ((unsigned long long)r.handler() << 32) | r.src();
+          uint32_t k3 = r.seq();
+          if (have_prev && !key_lt(p1, p2, p3, k1, k2, k3)) continue;
+          if (!have_g || key_lt(k1, k2, k3, g1, g2, g3)) {
+            g = r;
+            g1 = k1;
+            g2 = k2;
+            g3 = k3;
+            have_g = true;
+          }
+        }
+      }
+      if (n == 1) {
+        g1 = simian_time_key(g.time());
+        g2 = ((unsigned long long)g.handler() << 32) | g.src();
+        g3 = g.seq();
+      }
+    }
+    // earliest pending same-window self-send
+    int pj = -1;
+    for (int j = 0; j < ctx.npend; j++)
+      if (pj < 0 || ctx.pend_time[j] < ctx.pend_time[pj] ||
+          (ctx.pend_time[j] == ctx.pend_time[pj] && ctx.pend_q2[j] < ctx.pend_q2[pj]))
+        pj = j;
+    double time;
+    uint32_t handler, src;
+    unsigned long long data;
+    if (pj >= 0 && (!have_g || ctx.pend_time[pj] < g.time())) {
+      time = ctx.pend_time[pj];
+      handler = (uint32_t)(ctx.pend_q2[pj] & 0xFFFFu);
+      src = ctx.self_gid;
+      data = ctx.pend_data[pj];
+      ctx.npend--;
+      ctx.pend_time[pj] = ctx.pend_time[ctx.npend];
+      ctx.pend_q2[pj] = ctx.pend_q2[ctx.npend];
+      ctx.pend_data[pj] = ctx.pend_data[ctx.npend];
+    } else if (have_g) {
+      time = g.time();
+      handler = g.handler();
+      src = g.src();
+      data = g.data();
+      p1 = g1;
+      p2 = g2;
+      p3 = g3;
+      have_prev = true;
+      taken++;
+    } else
+      break;
+
+    // commit (simian.js:124-133)
+    if (c.tie_check && have_last && time == last_time) {
+      ta.ties++;
+      unsigned long long q = ((unsigned long long)handler << 32) | src;
+      if (q != last_q || data != last_data) ta.dties++;
+    }
+    last_time = time;
+    last_q = ((unsigned long long)handler << 32) | src;
+    last_data = data;
+    have_last = true;
+    st.hash = simian_trace_step(st.hash, time, handler, src, data);
+    unsigned long long idx = st.count;
+    st.count = idx + 1;
+    ta.committed++;
+    unsigned long long tk = simian_time_key(time);
+    ta.max_key = tk > ta.max_key ? tk : ta.max_key;
+
+    ctx.commit_idx = idx;
+    ctx.key = simian_rng_key(c.seed, ctx.self_gid, idx);
+    ctx.n_emit = 0;
+    ctx.now_ = time; // simian.js:126
+    ctx.handler_ = handler;
+    ctx.src_ = src;
+    ctx.data_ = data;
+    uint32_t fn = handler < SIMIAN_MAX_SERVICES ? ctx.cl->fn_of_service[handler] : 0;
+    run_handler(ctx, fn); // simian.js:129-131
+  }
+  c.core[slot] = st;
+}
+
+// block-wide exclusive scan of sh.cnt[EPB] into sh.off[EPB+1]; returns total
+__device__ __forceinline__ uint32_t block_scan_counts(WindowShared &sh) {
+  constexpr int ITEMS = EPB / NTHREADS;
+  static_assert(EPB % NTHREADS == 0, "EPB must be a multiple of the CTA size");
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  uint32_t v[ITEMS], s = 0;
+#pragma unroll
+  for (int i = 0; i < ITEMS; i++) {
+    v[i] = sh.cnt[tid * ITEMS + i];
+    s += v[i];
+  }
+  uint32_t inc = s;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t x = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += x;
+  }
+  if (lane == 31) sh.warp_tmp[wid] = inc;
+  __syncthreads();
+  if (wid == 0) {
+    uint32_t w = lane < NTHREADS / 32 ? sh.warp_tmp[lane] : 0, winc = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t x = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= o) winc += x;
+    }
+    sh.warp_tmp[lane] = winc - w; // exclusive warp prefix
+    if (lane == 31) sh.off[EPB] = winc;
+  }
+  __syncthreads();
+  uint32_t ex = sh.warp_tmp[wid] + inc - s;
+#pragma unroll
+  for (int i = 0; i < ITEMS; i++) {
+    sh.off[tid * ITEMS + i] = ex;
+    ex += v[i];
+  }
+  __syncthreads();
+  return sh.off[EPB];
+}
+
+// walk one cell's page chain into the CTA's page list
+__device__ __forceinline__ void list_cell_pages(const DevCfg &c, WindowShared &sh, uint32_t head,
+                                                uint32_t head_cnt, uint32_t flag) {
+  uint32_t p = head, cntp = head_cnt;
+#pragma unroll 1
+  while (p != SIMIAN_NONE) {
+    uint32_t idx = atomicAdd(&sh.npg, 1u);
+    if (idx < PGMAX) {
+      sh.pg_id[idx] = p;
+      sh.pg_cnt[idx] = (uint16_t)(cntp | flag);
+    }
+    p = c.page_next[p];
+    cntp = PAGE;
+  }
+}
+
+// ------- LBTS candidate + next-window set-up (one CTA, all threads) --------
+
+// local minLeft candidate (simian.js:143): min over every pending local event.
+// acc->min_key already holds leftovers of row tb_hi + everything appended since
+// the last advance; rows above tb_hi are searched only when that candidate does
+// not already lie in row tb_hi (sparse case: the window jumped over idle time).
+__device__ void local_min_candidate(const DevCfg &c, const WinState &W, WindowShared &sh,
+                                    unsigned long long &cand_out,
+                                    unsigned long long &far_out) {
+  const int tid = threadIdx.x;
+  DevAcc *a = c.acc;
+  unsigned long long far = ld_cg64(&a->far_min[W.far_row]);
+  unsigned long long cand = ld_cg64(&a->min_key);
+  cand = far < cand ? far : cand;
+  long long jmax = W.tb_clean + (long long)c.ring - 1;
+  if (cand != SIMIAN_KEY_NONE) {
+    long long tc = tb_of(c, simian_key_time(cand));
+    jmax = tc < jmax ? tc : jmax;
+  }
+  long long j0 = W.tb_hi + 1;
+  // first non-empty sub-bucket row in [j0, jmax], (row, block) pairs in row-major order
+  if (tid == 0) sh.scan_j = 0x7FFFFFFFFFFFFFFFLL;
+  __syncthreads();
+  if (j0 <= jmax) {
+    unsigned long long total = (unsigned long long)(jmax - j0 + 1) * c.n_blocks;
+    for (unsigned long long base = 0; base < total; base += (unsigned long long)NTHREADS * 8) {
+#pragma unroll 1
+      for (int u = 0; u < 8; u++) {
+        unsigned long long i = base + (unsigned long long)u * NTHREADS + tid;
+        if (i < total) {
+          long long j = j0 + (long long)(i / c.n_blocks);
+          uint32_t b = (uint32_t)(i % c.n_blocks);
+          if (ld_cg(&c.cell_cur[(uint32_t)(j & (long long)c.ring_mask) * c.n_blocks + b]) !=
+              SIMIAN_NONE)
+            atomicMin((unsigned long long *)&sh.scan_j, (unsigned long long)j);
+        }
+      }
+      __syncthreads();
+      if (sh.scan_j != 0x7FFFFFFFFFFFFFFFLL) break;
+    }
+  }
+  __syncthreads();
+  long long jf = sh.scan_j;
+  __syncthreads();
+  if (jf != 0x7FFFFFFFFFFFFFFFLL) {
+    if (tid == 0) sh.min_key = SIMIAN_KEY_NONE;
+    __syncthreads();
+    unsigned long long mn = SIMIAN_KEY_NONE;
+    uint32_t row = (uint32_t)(jf & (long long)c.ring_mask) * c.n_blocks;
+    for (uint32_t b = tid; b < c.n_blocks; b += NTHREADS) {
+      uint32_t p = ld_cg(&c.cell_cur[row + b]);
+      while (p != SIMIAN_NONE) {
+        uint32_t f = ld_cg(&c.page_fill[p]);
+        f = f < PAGE ? f : PAGE;
+        for (uint32_t s = 0; s < f; s++) {
+          unsigned long long q0 =
+              ld_cg64((const unsigned long long *)(c.pool + ((size_t)p * PAGE + s)));
+          unsigned long long kk = simian_time_key(__longlong_as_double((long long)q0));
+          mn = kk < mn ? kk : mn;
+        }
+        p = ld_cg(&c.page_next[p]);
+      }
+    }
+    if (mn != SIMIAN_KEY_NONE) atomicMin(&sh.min_key, mn);
+    __syncthreads();
+    unsigned long long m2 = sh.min_key;
+    cand = m2 < cand ? m2 : cand;
+    __syncthreads();
+  }
+  cand_out = cand;
+  far_out = far;
+}
+
+// Write window k+1 given globalMinLeft (simian.js:119-120,144-147).
+__device__ void setup_next_window(const DevCfg &c, const WinState &W, WinState *Wn, double gmin,
+                                  double far_min_time, bool after_redist) {
+  const int tid = threadIdx.x;
+  DevAcc *a = c.acc;
+  __shared__ WinState nw;
+  if (tid == 0) {
+    nw = W;
+    nw.redist = 0;
+    if (after_redist) {
+      nw.tb_clean = W.tb_clean_new;
+      nw.far_row = W.far_row ^ 1u;
+      a->far_min[W.far_row] = SIMIAN_KEY_NONE;
+      a->redistributions++;
+      gmin = W.gmin; // the window that was postponed
+    } else {
+      nw.tb_clean = W.tb_hi; // rows below tb_hi were recycled by this window
+      a->windows++;
+    }
+    nw.gmin = gmin;
+    nw.hi = gmin + c.min_delay; // epoch, simian.js:120
+    nw.done = !(gmin <= c.end); // simian.js:119
+    nw.tb_lo = tb_of(c, nw.gmin);
+    nw.tb_hi = tb_of(c, nw.hi);
+    if (nw.tb_lo < nw.tb_clean) nw.tb_lo = nw.tb_clean;
+    nw.tb_clean_new = nw.tb_clean;
+    if (!nw.done) {
+      // Spend the next launch on a recycle + far-row redistribution pass when a
+      // far-future event comes due, or when the window jumped so far over idle
+      // time that un-recycled rows would alias the rows it reads.
+      if (!after_redist &&
+          (far_min_time < nw.hi || nw.tb_hi - nw.tb_clean >= (long long)(c.ring / 2))) {
+        nw.redist = 1;
+        nw.tb_clean_new = nw.tb_lo;
+      }
+      if (nw.tb_hi - nw.tb_lo + 1 > SIMIAN_MAX_CELLS)
+        atomicCAS(&a->error, 0u, (unsigned int)SIMIAN_ERR_RING_SPAN);
+    }
+    nw.alloc_limit = ld_cg64(&a->free_tail);
+    a->min_key = SIMIAN_KEY_NONE;
+    a->ticket = 0;
+    a->window_index++;
+  }
+  __syncthreads();
+  // snapshot the heads of row tb_hi: appends of the next launch may target it
+  if (!nw.done) {
+    uint32_t row = (uint32_t)(nw.tb_hi & (long long)c.ring_mask) * c.n_blocks;
+    for (uint32_t b = tid; b < c.n_blocks; b += blockDim.x) {
+      uint32_t p = ld_cg(&c.cell_cur[row + b]);
+      uint32_t f = 0;
+      if (p != SIMIAN_NONE) {
+        f = ld_cg(&c.page_fill[p]);
+        f = f < PAGE ? f : PAGE;
+      }
+      c.snap_cur[b] = p;
+      c.snap_fill[b] = f;
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    *Wn = nw;
+    if (nw.done) { // later launches of either parity must see the end
+      c.win[0] = nw;
+      c.win[1] = nw;
+    }
+  }
+}
+
+// free a whole cell (pages -> ring, head cleared); one thread
+__device__ __forceinline__ void free_cell(const DevCfg &c, uint32_t cell) {
+  uint32_t p = c.cell_cur[cell];
+  while (p != SIMIAN_NONE) {
+    uint32_t nx = c.page_next[p];
+    page_free(c, p);
+    p = nx;
+  }
+  c.cell_cur[cell] = SIMIAN_NONE;
+}
+
+// Far-row redistribution for block b (own cells only: no cross-CTA traffic).
+__device__ void redistribute_block(const DevCfg &c, WindowShared &sh, uint32_t b) {
+  const WinState &W = sh.W;
+  const int tid = threadIdx.x;
+  // 1. recycle rows [tb_clean, tb_clean_new): only dead records remain there
+  long long nrec = W.tb_clean_new - W.tb_clean;
+  if (nrec > (long long)c.ring) nrec = c.ring;
+  for (long long i = tid; i < nrec; i += NTHREADS) {
+    long long tb = W.tb_clean + i;
+    free_cell(c, (uint32_t)(tb & (long long)c.ring_mask) * c.n_blocks + b);
+  }
+  __syncthreads();
+  // 2. move the far row: into the calendar when within the new horizon, else
+  //    into the other far row
+  uint32_t far_cell = (c.ring + W.far_row) * c.n_blocks + b;
+  uint32_t other = W.far_row ^ 1u;
+  if (tid == 0) sh.npg = 0;
+  __syncthreads();
+  if (tid == 0) {
+    uint32_t head = c.cell_cur[far_cell];
+    uint32_t hc = 0;
+    if (head != SIMIAN_NONE) {
+      hc = c.page_fill[head];
+      hc = hc < PAGE ? hc : PAGE;
+    }
+    list_cell_pages(c, sh, head, hc, PG_FREE_FLAG);
+  }
+  __syncthreads();
+  uint32_t npg = sh.npg;
+  if (npg > PGMAX) {
+    if (tid == 0) set_error(c, SIMIAN_ERR_WINDOW_OVERFLOW);
+    npg = PGMAX;
+  }
+  for (uint32_t i = tid; i < npg * PAGE; i += NTHREADS) {
+    uint32_t pg = i / PAGE, s = i % PAGE;
+    if (s >= (uint32_t)(sh.pg_cnt[pg] & 0x7FFFu)) continue;
+    RecBits r = ld_rec(c.pool + ((size_t)sh.pg_id[pg] * PAGE + s));
+    append_local(c, sh.ax, W.tb_clean_new, other, W.alloc_limit, r);
+  }
+  __syncthreads();
+  for (uint32_t i = tid; i < npg; i += NTHREADS) page_free(c, sh.pg_id[i]);
+  if (tid == 0) c.cell_cur[far_cell] = SIMIAN_NONE;
+}
+
+// One lookahead window (or one redistribution pass) for entity block blockIdx.x.
+// fuse_advance != 0 (size == 1): the last CTA to finish computes window k+1.
+__global__ void __launch_bounds__(NTHREADS)
+    k_window(const __grid_constant__ DevCfg c, uint32_t win_ix, int fuse_advance) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  WindowShared &sh = *reinterpret_cast<WindowShared *>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31;
+  const uint32_t b = blockIdx.x;
+  const WinState *Wg = &c.win[win_ix & 1u];
+  if (Wg->done) return; // simian.js:119: enqueued past the end of the run
+  if (tid == 0) sh.found = ld_cg(&c.acc->error);
+  __syncthreads();
+  if (sh.found) return; // sticky error: CTA-uniform exit
+
+  if (tid == 0) {
+    sh.W = *Wg;
+    sh.min_key = SIMIAN_KEY_NONE;
+    sh.max_key = 0;
+    sh.committed = sh.emitted = sh.dropped = sh.ties = sh.dties = 0;
+    sh.npg = 0;
+    sh.nfree = 0;
+    sh.nfree_w = 0;
+    sh.is_last = 0;
+  }
+  append_ctx_init(sh.ax);
+  for (int i = tid; i < EPB; i += NTHREADS) sh.cnt[i] = 0;
+  __syncthreads();
+  const WinState &W = sh.W;
+
+  ThreadAcc ta;
+  ta.min_key = SIMIAN_KEY_NONE;
+  ta.max_key = 0;
+  ta.committed = ta.emitted = ta.dropped = ta.ties = ta.dties = 0;
+
+  if (W.redist) {
+    redistribute_block(c, sh, b);
+  } else {
+    // ---- K2a: list the pages of this block's cells in rows [tb_lo, tb_hi]
+    int ncell = (int)(W.tb_hi - W.tb_lo + 1);
+    if (tid < ncell) {
+      long long tb = W.tb_lo + tid;
+      uint32_t cell = (uint32_t)(tb & (long long)c.ring_mask) * c.n_blocks + b;
+      uint32_t head, hc = 0, flag = 0;
+      if (tb == W.tb_hi) { // may be appended to during this launch: snapshot
+        head = c.snap_cur[b];
+        hc = c.snap_fill[b];
+      } else {
+        head = c.cell_cur[cell];
+        if (head != SIMIAN_NONE) {
+          hc = c.page_fill[head];
+          hc = hc < PAGE ? hc : PAGE;
+        }
+        flag = PG_FREE_FLAG; // fully below the bound: recycled after this window
+      }
+      list_cell_pages(c, sh, head, hc, flag);
+    }
+    __syncthreads();
+    uint32_t npg = sh.npg;
+    if (npg > PGMAX) {
+      if (tid == 0) set_error(c, SIMIAN_ERR_WINDOW_OVERFLOW);
+      npg = 0;
+    }
+    // ---- K2b: histogram of due events per local entity; leftover min (K1)
+    const uint32_t slot0 = b * EPB;
+    for (uint32_t i = tid; i < npg * PAGE; i += NTHREADS) {
+      uint32_t pg = i / PAGE, s = i % PAGE;
+      if (s >= (uint32_t)(sh.pg_cnt[pg] & 0x7FFFu)) continue;
+      unsigned long long q0, q1;
+      ld_rec_head(c.pool + ((size_t)sh.pg_id[pg] * PAGE + s), q0, q1);
+      double t = __longlong_as_double((long long)q0);
+      if (t < W.hi) {
+        if (t >= W.gmin) {
+          uint32_t le = (uint32_t)q1 - slot0;
+          if (le < EPB) atomicAdd(&sh.cnt[le], 1u);
+        }
+      } else {
+        unsigned long long tk = simian_time_key(t);
+        ta.min_key = tk < ta.min_key ? tk : ta.min_key;
+      }
+    }
+    __syncthreads();
+    uint32_t total = block_scan_counts(sh);
+    // ---- passes over entity sub-ranges whose due events fit in sh.refs
+    uint32_t e_lo = 0;
+#pragma unroll 1
+    while (e_lo < EPB && total) {
+      if (tid == 0) {
+        uint32_t base = sh.off[e_lo];
+        uint32_t lo = e_lo, hi = EPB; // largest e_hi with off[e_hi]-base <= NREFS
+        while (lo < hi) {
+          uint32_t mid = (lo + hi + 1) >> 1;
+          if (sh.off[mid] - base <= NREFS) lo = mid; else hi = mid - 1;
+        }
+        sh.pass_hi = lo;
+      }
+      __syncthreads();
+      uint32_t e_hi = sh.pass_hi;
+      if (e_hi == e_lo) { // a single entity with more than NREFS due events
+        if (tid == 0) set_error(c, SIMIAN_ERR_ENTITY_BURST);
+        break;
+      }
+      uint32_t base = sh.off[e_lo];
+      if (sh.off[e_hi] != base) {
+        // K2c: group references by entity (second read hits L2)
+        for (uint32_t i = tid; i < npg * PAGE; i += NTHREADS) {
+          uint32_t pg = i / PAGE, s = i % PAGE;
+          if (s >= (uint32_t)(sh.pg_cnt[pg] & 0x7FFFu)) continue;
+          uint32_t ref = sh.pg_id[pg] * PAGE + s;
+          unsigned long long q0, q1;
+          ld_rec_head(c.pool + ref, q0, q1);
+          double t = __longlong_as_double((long long)q0);
+          if (t < W.hi && t >= W.gmin) {
+            uint32_t le = (uint32_t)q1 - slot0;
+            if (le >= e_lo && le < e_hi) {
+              uint32_t r = atomicSub(&sh.cnt[le], 1u) - 1u;
+              sh.refs[sh.off[le] - base + r] = ref;
+            }
+          }
+        }
+        __syncthreads();
+        // K3 + K4: handlers, one thread per entity
+        for (uint32_t le = e_lo + tid; le < e_hi; le += NTHREADS) {
+          uint32_t n = sh.off[le + 1] - sh.off[le];
+          if (n) process_entity(c, sh, ta, slot0 + le, &sh.refs[sh.off[le] - base], n);
+        }
+        __syncthreads();
+      }
+      e_lo = e_hi;
+    }
+    // ---- recycle rows [tb_clean, tb_hi): pages back to the ring, heads cleared
+    {
+      // rows listed above (flagged pages)
+      uint32_t mine = 0;
+      for (uint32_t i = tid; i < npg; i += NTHREADS)
+        if (sh.pg_cnt[i] & PG_FREE_FLAG) mine++;
+      uint32_t pos = 0;
+      if (mine) pos = atomicAdd(&sh.nfree, mine);
+      __syncthreads();
+      if (tid == 0 && sh.nfree)
+        sh.free_base = atomicAdd(&c.acc->free_tail, (unsigned long long)sh.nfree);
+      __syncthreads();
+      for (uint32_t i = tid; i < npg; i += NTHREADS)
+        if (sh.pg_cnt[i] & PG_FREE_FLAG)
+          c.free_ring[(sh.free_base + pos++) % c.n_pages] = sh.pg_id[i];
+      if (tid < ncell - 1) {
+        long long tb = W.tb_lo + tid;
+        c.cell_cur[(uint32_t)(tb & (long long)c.ring_mask) * c.n_blocks + b] = SIMIAN_NONE;
+      }
+      // rows the window jumped over (dead records only)
+      long long nskip = W.tb_lo - W.tb_clean;
+      if (nskip > (long long)c.ring) nskip = c.ring;
+      for (long long i = tid; i < nskip; i += NTHREADS) {
+        long long tb = W.tb_clean + i;
+        if (tb >= W.tb_lo) break;
+        free_cell(c, (uint32_t)(tb & (long long)c.ring_mask) * c.n_blocks + b);
+      }
+    }
+  }
+
+  // ---- K1: CTA reduction of the accumulators, one atomic each per CTA
+  for (int o = 16; o; o >>= 1) {
+    unsigned long long x = __shfl_xor_sync(0xffffffffu, ta.min_key, o);
+    ta.min_key = x < ta.min_key ? x : ta.min_key;
+    unsigned long long y = __shfl_xor_sync(0xffffffffu, ta.max_key, o);
+    ta.max_key = y > ta.max_key ? y : ta.max_key;
+    ta.committed += __shfl_xor_sync(0xffffffffu, ta.committed, o);
+    ta.emitted += __shfl_xor_sync(0xffffffffu, ta.emitted, o);
+    ta.dropped += __shfl_xor_sync(0xffffffffu, ta.dropped, o);
+    ta.ties += __shfl_xor_sync(0xffffffffu, ta.ties, o);
+    ta.dties += __shfl_xor_sync(0xffffffffu, ta.dties, o);
+  }
+  if (lane == 0) {
+    if (ta.min_key != SIMIAN_KEY_NONE) atomicMin(&sh.min_key, ta.min_key);
+    if (ta.max_key) atomicMax(&sh.max_key, ta.max_key);
+    if (ta.committed) atomicAdd(&sh.committed, ta.committed);
+    if (ta.emitted) atomicAdd(&sh.emitted, ta.emitted);
+    if (ta.dropped) atomicAdd(&sh.dropped, ta.dropped);
+    if (ta.ties) atomicAdd(&sh.ties, ta.ties);
+    if (ta.dties) atomicAdd(&sh.dties, ta.dties);
+  }
+  append_ctx_flush(c, sh.ax); // contains __syncthreads()
+  if (tid == 0) {
+    DevAcc *a = c.acc;
+    if (sh.min_key != SIMIAN_KEY_NONE) atomicMin(&a->min_key, sh.min_key);
+    if (sh.max_key) atomicMax(&a->max_key, sh.max_key);
+    if (sh.committed) atomicAdd(&a->committed, (unsigned long long)sh.committed);
+    if (sh.emitted) atomicAdd(&a->emitted, (unsigned long long)sh.emitted);
+    if (sh.dropped) atomicAdd(&a->dropped, (unsigned long long)sh.dropped);
+    if (sh.ties) atomicAdd(&a->ties, (unsigned long long)sh.ties);
+    if (sh.dties) atomicAdd(&a->dist_ties, (unsigned long long)sh.dties);
+  }
+  if (!fuse_advance) return;
+  // ---- last CTA computes the next window (simian.js:147)
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) sh.is_last = (atomicAdd(&c.acc->ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!sh.is_last) return;
+  __threadfence();
+  WinState *Wn = &c.win[(win_ix + 1u) & 1u];
+  if (W.redist) {
+    setup_next_window(c, W, Wn, W.gmin, 0.0, true);
+  } else {
+    unsigned long long cand, far;
+    local_min_candidate(c, W, sh, cand, far);
+    double gmin = cand == SIMIAN_KEY_NONE ? c.inf_time : simian_key_time(cand); // simian.js:147
+    double farT = far == SIMIAN_KEY_NONE ? __longlong_as_double(0x7FF0000000000000LL)
+                                         : simian_key_time(far);
+    setup_next_window(c, W, Wn, gmin, farT, false);
+  }
+}
+
+// size > 1: local minLeft candidate after the exchange (simian.js:143)
+__global__ void __launch_bounds__(NTHREADS) k_local_min(const __grid_constant__ DevCfg c, uint32_t win_ix) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  WindowShared &sh = *reinterpret_cast<WindowShared *>(smem_raw);
+  const WinState &W = c.win[win_ix & 1u];
+  unsigned long long cand, far;
+  if (W.redist || W.done) {
+    cand = far = SIMIAN_KEY_NONE;
+  } else {
+    local_min_candidate(c, W, sh, cand, far);
+  }
+  if (threadIdx.x == 0) {
+    const double inf = __longlong_as_double(0x7FF0000000000000LL);
+    c.acc->minvec[0] = cand == SIMIAN_KEY_NONE ? c.inf_time : simian_key_time(cand);
+    c.acc->minvec[1] = far == SIMIAN_KEY_NONE ? inf : simian_key_time(far);
+  }
+}
+
+// size > 1: consume the allreduced {globalMinLeft, min far} (simian.js:144)
+__global__ void __launch_bounds__(NTHREADS) k_advance(const __grid_constant__ DevCfg c, uint32_t win_ix) {
+  const WinState W = c.win[win_ix & 1u];
+  WinState *Wn = &c.win[(win_ix + 1u) & 1u];
+  if (W.done) {
+    if (threadIdx.x == 0) *Wn = W;
+    return;
+  }
+  if (W.redist)
+    setup_next_window(c, W, Wn, W.gmin, 0.0, true);
+  else
+    setup_next_window(c, W, Wn, c.acc->minvec[0], c.acc->minvec[1], false);
+  // outbox counters were consumed by the exchange
+  if (threadIdx.x < c.size && c.outbox_count) c.outbox_count[threadIdx.x] = 0;
+}
+
+// first window: gmin = startTime even when the queue is empty (simian.js:118)
+__global__ void __launch_bounds__(NTHREADS) k_begin(const __grid_constant__ DevCfg c) {
+  WinState W = c.win[0];
+  __shared__ WinState w0;
+  if (threadIdx.x == 0) {
+    w0 = W;
+    w0.tb_hi = w0.tb_clean; // nothing recycled yet
+  }
+  __syncthreads();
+  const double inf = __longlong_as_double(0x7FF0000000000000LL);
+  unsigned long long far = c.acc->far_min[0];
+  setup_next_window(c, w0, &c.win[0], c.start, far == SIMIAN_KEY_NONE ? inf : simian_key_time(far),
+                    false);
+  if (threadIdx.x == 0) {
+    c.acc->windows = 0;
+    c.acc->window_index = 0;
+  }
+}
+
+// ------------------------------------------------------------- reductions --
+
+// digest = sum of simian_digest_term over local entities; state checksum
+__global__ void k_digest(const __grid_constant__ DevCfg c, unsigned long long *out /* [2] */) {
+  unsigned long long dg = 0, sc = 0;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x; s < c.n_slots; s += stride) {
+    int k;
+    uint32_t gid = gid_of_slot(c, (uint32_t)s, k);
+    EntityCore st = c.core[s];
+    dg += simian_digest_term(gid, st.count, st.hash);
+    const DevClass &cl = c.cls[k];
+    unsigned long long acc = simian_mix64((unsigned long long)gid + 1ull);
+    const unsigned long long *w =
+        (const unsigned long long *)(cl.state + (size_t)(s - cl.slot_base) * cl.state_bytes);
+    for (uint32_t i = 0; i < cl.state_bytes / 8; i++) acc = simian_state_fold(acc, w[i]);
+    sc += acc;
+  }
+  for (int o = 16; o; o >>= 1) {
+    dg += __shfl_xor_sync(0xffffffffu, dg, o);
+    sc += __shfl_xor_sync(0xffffffffu, sc, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(&out[0], dg);
+    atomicAdd(&out[1], sc);
+  }
+}

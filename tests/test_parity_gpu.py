@@ -1,0 +1,98 @@
+"""-m gpu: the CUDA engine, called through the C-ABI, against the CPU oracle
+and the committed SimianPie goldens.  Bit-exact on everything."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from helpers import assert_parity, run_engine_phold, run_oracle_phold
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "phold_simianpie.json")
+
+
+def golden_cases():
+    with open(GOLD) as f:
+        return json.load(f)["cases"]
+
+
+@pytest.mark.parametrize("case", golden_cases(), ids=lambda c: c["name"])
+def test_engine_matches_simianpie_goldens(case):
+    opts = {}
+    if case["min_delay"] < 1e-3:
+        opts["bucket_width"] = 1.0 / 64
+    st, cnt, h = run_engine_phold(case, **opts)
+    assert st["total_events"] == case["total_events"]
+    assert list(cnt) == case["counts"]
+    assert ["%016x" % x for x in h] == case["hashes"]
+    assert "%016x" % st["digest"] == case["digest"]
+    assert float(st["last_time"]).hex() == case["last_time_hex"]
+
+
+CASES = [
+    dict(name="one_block", n=1000, per_entity=1, min_delay=0.05, lookahead=0.05,
+         p_remote=0.0, mode=0, end=30.0, seed=1),
+    dict(name="multi_block_ross", n=5000, per_entity=16, min_delay=0.1,
+         lookahead=0.1, p_remote=0.1, mode=1, end=6.0, seed=2),
+    dict(name="ragged_last_block", n=1025, per_entity=3, min_delay=0.1,
+         lookahead=0.1, p_remote=0.3, mode=1, end=8.0, seed=3),
+    dict(name="other_group", n=4096, per_entity=8, min_delay=0.1,
+         lookahead=0.1, p_remote=0.5, mode=2, groups=8, end=5.0, seed=4),
+    dict(name="small_lookahead", n=3000, per_entity=16, min_delay=0.01,
+         lookahead=0.01, p_remote=0.1, mode=1, end=1.5, seed=5),
+    dict(name="burst_64_per_entity", n=2048, per_entity=64, min_delay=0.1,
+         lookahead=0.1, p_remote=0.1, mode=1, end=1.0, seed=6),
+    dict(name="single_entity", n=1, per_entity=5, min_delay=0.1, lookahead=0.1,
+         p_remote=0.0, mode=0, end=50.0, seed=7),
+    dict(name="lambda_half", n=777, per_entity=4, min_delay=0.2, lookahead=0.25,
+         p_remote=0.2, lam=0.5, mode=1, end=20.0, seed=8),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: c["name"])
+def test_engine_matches_oracle(case, oracle_mod):
+    so, co, ho = run_oracle_phold(oracle_mod, case)
+    se, ce, he = run_engine_phold(case)
+    assert_parity(so, co, ho, se, ce, he)
+
+
+def test_sparse_windows_and_far_list(oracle_mod):
+    """config-1 shape: minDelay << mean delay, so almost every event goes
+    through the far-future list and the window jumps over idle time."""
+    case = dict(name="sparse", n=200, per_entity=1, min_delay=1e-3,
+                lookahead=1e-3, p_remote=0.0, mode=0, end=4.0, seed=9)
+    so, co, ho = run_oracle_phold(oracle_mod, case)
+    # default bucket width (minDelay/4) -> horizon 0.5: far list exercised
+    se, ce, he = run_engine_phold(case, ring_buckets=256)
+    assert_parity(so, co, ho, se, ce, he)
+    assert se["far_appends"] > 0 and se["redistributions"] > 0
+    # tuned bucket width
+    se, ce, he = run_engine_phold(case, bucket_width=1.0 / 32)
+    assert_parity(so, co, ho, se, ce, he)
+
+
+def test_empty_run_and_end_time_zero_events(oracle_mod):
+    """no scheduled events: one window at startTime, then done (simian.js:118,147)"""
+    from simian_b200 import capi
+    e = capi.Engine("empty", 0.0, 5.0, 0.5)
+    e.define_class("Node", 0)
+    e.add_entities("Node", 0, 10)
+    e.attach_service("Node", "generate", "phold_generate")
+    st = e.run()
+    assert st["total_events"] == 0 and st["windows"] == 1
+    o = oracle_mod.Oracle("empty", 0.0, 5.0, 0.5)
+    o.define_class("Node", 0)
+    o.add_entities("Node", 0, 10)
+    assert o.run()["windows"] == 1
+
+
+def test_lookahead_violation_is_an_error():
+    """entity.js:41-45: rx given and offset < minDelay must throw"""
+    from simian_b200 import capi
+    from simian_b200.workloads import build_phold
+    e = capi.Engine("bad", 0.0, 5.0, 0.5)
+    build_phold(e, 64, 1, lookahead=0.0, lam=1000.0)  # offsets << minDelay
+    with pytest.raises(capi.SimianError) as ei:
+        e.run()
+    assert ei.value.code == 1
