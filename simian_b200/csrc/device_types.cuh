@@ -104,7 +104,7 @@ struct DevCfg {
   simian_event_t *pool;
   uint32_t *page_next, *page_fill;
   uint32_t *free_ring;
-  uint32_t n_pages, pad0_;
+  uint32_t n_pages, n_ids;
   uint32_t *snap_cur, *snap_fill; // [n_blocks] head snapshot of row tb_hi
   WinState *win;                  // [2]
   DevAcc *acc;

@@ -43,7 +43,8 @@ struct SchedOp { // a recorded schedService call, replayed on the device at run
   uint64_t data = 0;
   int cls = 0;
   uint32_t first = 0, count = 0, repeat = 0, seq_base = 0;
-  std::vector<simian_event_t> recs;
+  simian_event_t *d_recs = nullptr; // kind 1: uploaded at call time
+  uint64_t n_recs = 0;
 };
 
 int builtin_fn_by_name(const char *n) {
@@ -153,6 +154,7 @@ int setup(simian_engine *e) {
   c.size = e->size;
   c.tie_check = e->tie_check;
   c.n_classes = (int)e->classes.size();
+  c.n_ids = e->n_ids;
   if (c.n_classes == 0) return e->fail(SIMIAN_ERR_BAD_ARGUMENT, "no entities added");
   uint32_t g = (uint32_t)e->size, slot = 0;
   for (int k = 0; k < c.n_classes; k++) {
@@ -246,17 +248,14 @@ int setup(simian_engine *e) {
       k_sched_bulk<<<grid, 256, 0, e->stream>>>(c, op.time, op.handler, op.data, op.cls, op.first,
                                                 op.count, op.repeat, op.seq_base);
       CK(cudaGetLastError());
-    } else if (!op.recs.empty()) {
-      simian_event_t *d = nullptr;
-      size_t bytes = op.recs.size() * sizeof(simian_event_t);
-      CK(cudaMalloc((void **)&d, bytes));
-      CK(cudaMemcpyAsync(d, op.recs.data(), bytes, cudaMemcpyHostToDevice, e->stream));
-      uint64_t n = op.recs.size();
+    } else if (op.n_recs) {
+      uint64_t n = op.n_recs;
       int grid = (int)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184);
-      k_ingest<<<grid, 256, 0, e->stream>>>(c, d, n, 1, 0, 0);
+      k_ingest<<<grid, 256, 0, e->stream>>>(c, op.d_recs, n, 1, 0, 0);
       CK(cudaGetLastError());
       CK(cudaStreamSynchronize(e->stream));
-      CK(cudaFree(d));
+      CK(cudaFree(op.d_recs));
+      op.d_recs = nullptr;
     }
   }
   e->ops.clear();
@@ -362,6 +361,8 @@ void simian_destroy(simian_engine *e) {
   cudaSetDevice(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
   for (void *p : e->allocs) cudaFree(p);
+  for (SchedOp &op : e->ops)
+    if (op.d_recs) cudaFree(op.d_recs);
   if (e->h_acc) cudaFreeHost(e->h_acc);
   if (e->h_win) cudaFreeHost(e->h_win);
   if (e->h_counts) cudaFreeHost(e->h_counts);
@@ -515,14 +516,18 @@ int simian_sched_service(simian_engine *e, double time, const char *serviceName,
 
 int simian_sched_events(simian_engine *e, const simian_event_t *ev, uint64_t n) {
   if (e->set_up) return e->fail(SIMIAN_ERR_RUNNING, "schedService after the run started");
+  if (!n) return 0;
+  // straight host -> HBM copy from the caller's buffer (fast when it is pinned);
+  // ids and times are validated on the device when the records are ingested
+  CK(cudaSetDevice(e->device));
   SchedOp op;
   op.kind = 1;
-  op.recs.assign(ev, ev + n);
-  for (uint64_t i = 0; i < n; i++) {
-    if (ev[i].dst >= e->n_ids) return e->fail(SIMIAN_ERR_UNKNOWN_NAME, "no such entity");
-    if (ev[i].time < e->start) return e->fail(SIMIAN_ERR_OUT_OF_ORDER, "event before startTime");
-  }
-  e->ops.push_back(std::move(op));
+  op.n_recs = n;
+  CK(cudaMalloc((void **)&op.d_recs, n * sizeof(simian_event_t)));
+  CK(cudaMemcpyAsync(op.d_recs, ev, n * sizeof(simian_event_t), cudaMemcpyHostToDevice,
+                     e->stream));
+  CK(cudaStreamSynchronize(e->stream)); // the host buffer is only borrowed
+  e->ops.push_back(op);
   e->initial_events += n;
   return 0;
 }

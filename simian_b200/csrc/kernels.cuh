@@ -341,6 +341,14 @@ __global__ void k_ingest(const __grid_constant__ DevCfg c, const simian_event_t 
     RecBits r = ld_rec(recs + idx);
     if (dst_is_gid) {
       if (r.time() > c.end) continue; // simian.js:173
+      if (r.dst() >= c.n_ids) {
+        set_error(c, SIMIAN_ERR_UNKNOWN_NAME);
+        continue;
+      }
+      if (r.time() < c.start) {
+        set_error(c, SIMIAN_ERR_OUT_OF_ORDER);
+        continue;
+      }
       int rank;
       uint32_t slot;
       route_gid(c, r.dst(), rank, slot);
