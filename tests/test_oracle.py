@@ -1,0 +1,240 @@
+"""-m "not gpu": the CPU oracle against the reference's own fixtures, the
+committed SimianPie goldens and the pure-Python transcription of the spec."""
+import json
+import math
+import os
+import random
+
+import numpy as np
+import pytest
+
+from helpers import run_oracle_phold
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "phold_simianpie.json")
+
+
+def golden_cases():
+    with open(GOLD) as f:
+        return json.load(f)["cases"]
+
+
+# ---- eventQ.js ------------------------------------------------------------
+
+def test_heap_fixture_from_simianlua(oracle_mod):
+    """the only heap fixture the reference holds: SimianLua/eventQ.lua:62"""
+    L = oracle_mod.lib()
+    q = L.oracle_q_new(0)
+    data = [7878, 78217, 90, 1, 425, 10]
+    for i, t in enumerate(data):
+        L.oracle_q_push(q, float(t), i)
+    assert L.oracle_q_peek(q) == 1.0
+    out = [L.oracle_q_pop(q, None) for _ in data]
+    assert out == sorted(map(float, data))
+    assert L.oracle_q_len(q) == 0
+    L.oracle_q_free(q)
+
+
+def test_heap_sortedness_like_test_Q_js(oracle_mod):
+    """SimianJS/Tests/test.Q.js:14-21: push random times, pop all, never
+    'Out of order'; plus interleaved push/pop."""
+    L = oracle_mod.lib()
+    rnd = random.Random(5)
+    q = L.oracle_q_new(0)
+    n = 200000
+    for i in range(n):
+        L.oracle_q_push(q, rnd.random(), i)
+    prev = -1.0
+    for _ in range(n // 2):
+        t = L.oracle_q_pop(q, None)
+        assert t >= prev
+        prev = t
+    for i in range(n // 4):
+        L.oracle_q_push(q, prev + rnd.random(), i)
+    while L.oracle_q_len(q):
+        t = L.oracle_q_pop(q, None)
+        assert t >= prev
+        prev = t
+    L.oracle_q_free(q)
+
+
+def test_heap_equal_time_order_is_shape_dependent(oracle_mod):
+    """eventQ.js compares .time only (:36,:62,:66): ten equal-time pushes pop
+    as 0,9,8,...,1 -- not FIFO."""
+    import ctypes
+    L = oracle_mod.lib()
+    q = L.oracle_q_new(0)
+    for i in range(10):
+        L.oracle_q_push(q, 1.0, i)
+    tags = []
+    for _ in range(10):
+        tag = ctypes.c_uint64()
+        L.oracle_q_pop(q, ctypes.byref(tag))
+        tags.append(tag.value)
+    assert tags == [0, 9, 8, 7, 6, 5, 4, 3, 2, 1]
+    L.oracle_q_free(q)
+
+
+# ---- hash.js / placement ----------------------------------------------------
+
+def test_hash_js_values(oracle_mod):
+    L = oracle_mod.lib()
+    assert L.oracle_hash_name(b"Node") == 6385183179.0
+    # reference arithmetic: doubles, string iterated backwards
+    res = 5381.0
+    for ch in reversed("PDES_LANL_Node"):
+        res = 33 * res + ord(ch)
+    assert L.oracle_hash_name(b"PDES_LANL_Node") == res
+    assert res > 2.0 ** 53  # inexact: % size is taken on the rounded double
+
+
+@pytest.mark.parametrize("size,base", [(1, 0), (2, 1), (4, 3), (8, 3)])
+def test_base_rank_node(oracle_mod, size, base):
+    o = oracle_mod.Oracle("x", 0.0, 1.0, 0.1, size=size)
+    o.define_class("Node", 0)
+    assert o.base_rank("Node") == base
+
+
+# ---- spec header vs its Python transcription --------------------------------
+
+def test_spec_bit_exact_vs_pyspec(oracle_mod):
+    from oracle import pyspec
+    L = oracle_mod.lib()
+    rnd = random.Random(11)
+    for _ in range(20000):
+        x = rnd.getrandbits(64)
+        assert L.oracle_spec_mix64(x) == pyspec.mix64(x)
+        assert L.oracle_spec_u01(x) == pyspec.u01(x)
+        u = pyspec.u01_open(x)
+        assert L.oracle_spec_u01_open(x) == u
+        assert 0.0 < u < 1.0
+        assert L.oracle_spec_log(u) == pyspec.log(u)
+        assert L.oracle_spec_exponential(x, 2.0) == pyspec.exponential(x, 2.0)
+        e, c = rnd.getrandbits(32), rnd.getrandbits(40)
+        k = pyspec.rng_key(x, e, c)
+        assert L.oracle_spec_rng_key(x, e, c) == k
+        assert L.oracle_spec_rng_draw(k, 3) == pyspec.rng_draw(k, 3)
+        t = rnd.random() * 100
+        assert L.oracle_spec_trace_step(x, t, 3, e, c) == pyspec.trace_step(x, t, 3, e, c)
+        assert L.oracle_spec_digest_term(e, c, x) == pyspec.digest_term(e, c, x)
+
+
+def test_portable_log_is_accurate(oracle_mod):
+    L = oracle_mod.lib()
+    rnd = random.Random(3)
+    worst = 0.0
+    for _ in range(50000):
+        x = rnd.random() * 10 ** rnd.uniform(-300, 300)
+        got, ref = L.oracle_spec_log(x), math.log(x)
+        ulp = math.ulp(ref) if ref else 2.0 ** -1074
+        worst = max(worst, abs(got - ref) / ulp)
+    assert worst <= 1.0
+    assert L.oracle_spec_log(1.0) == 0.0
+    assert L.oracle_spec_log(2.0 ** -53) == math.log(2.0 ** -53)
+
+
+def test_u01_index_never_reaches_n(oracle_mod):
+    L = oracle_mod.lib()
+    top = (1 << 64) - 1
+    for n in (1, 2, 3, 10, 1000, 1 << 20, (1 << 24) - 1, 1 << 24, 1 << 31):
+        assert int(L.oracle_spec_u01(top) * float(n)) < n
+
+
+# ---- oracle vs the unmodified reference engine (SimianPie) -------------------
+
+@pytest.mark.parametrize("case", golden_cases(), ids=lambda c: c["name"])
+@pytest.mark.parametrize("size", [1, 2, 3, 8])
+@pytest.mark.parametrize("tie_mode", [0, 1])
+def test_oracle_matches_simianpie_goldens(oracle_mod, case, size, tie_mode):
+    st, cnt, h = run_oracle_phold(oracle_mod, case, size=size, tie_mode=tie_mode)
+    assert st["total_events"] == case["total_events"]
+    assert st["distinguishable_ties"] == 0 == case["distinguishable_ties"]
+    assert st["ties"] == case["ties"]
+    assert list(cnt) == case["counts"]
+    assert ["%016x" % x for x in h] == case["hashes"]
+    assert "%016x" % st["digest"] == case["digest"]
+    assert float(st["last_time"]).hex() == case["last_time_hex"]
+    assert st["synch_events"] == (0 if size == 1 else 2 * size * st["windows"])
+
+
+# ---- engine semantics -----------------------------------
+
+def _noop_world(oracle_mod, end, min_delay, times, size=1):
+    o = oracle_mod.Oracle("sem", 0.0, end, min_delay, size=size)
+    o.define_class("Node", 0)
+    o.add_entities("Node", 0, 4)
+    o.attach_service("Node", "tick", "noop")
+    for i, t in enumerate(times):
+        o.sched_service(t, "tick", i, "Node", i % 4)
+    return o
+
+
+def test_event_at_exactly_end_time_runs_and_later_is_dropped(oracle_mod):
+    o = _noop_world(oracle_mod, 5.0, 1.0, [0.0, 5.0, 5.0000001, 7.0])
+    st = o.run()
+    assert st["total_events"] == 2  # simian.js:119,173
+    assert st["last_time"] == 5.0
+
+
+def test_windows_skip_idle_time(oracle_mod):
+    """gmin jumps to the next event: windows are not on a fixed grid (:147)"""
+    o = _noop_world(oracle_mod, 100.0, 1.0, [0.5, 0.9, 50.0, 50.5, 99.0])
+    st = o.run()
+    # windows: [0,1) {0.5,0.9}; [50,51) {50,50.5}; [99,100) {99}; then inf
+    assert st["total_events"] == 5 and st["windows"] == 3
+
+
+def test_first_window_starts_at_start_time_even_if_empty(oracle_mod):
+    o = _noop_world(oracle_mod, 10.0, 1.0, [])
+    st = o.run()
+    assert st["total_events"] == 0 and st["windows"] == 1  # :118
+
+
+def test_lookahead_violation_throws(oracle_mod):
+    from simian_b200.workloads import build_phold
+    o = oracle_mod.Oracle("bad", 0.0, 5.0, 0.5)
+    build_phold(o, 64, 1, lookahead=0.0, lam=1000.0)
+    with pytest.raises(oracle_mod.OracleError) as ei:
+        o.run()
+    assert "too little delay" in str(ei.value)  # entity.js:44
+
+
+def test_add_entities_while_running_is_refused(oracle_mod):
+    # simian.js:215 is unreachable from outside run(); the contiguity rule of
+    # the bulk addEntities is what the binding enforces
+    o = oracle_mod.Oracle("x", 0.0, 1.0, 0.1)
+    o.define_class("Node", 0)
+    o.add_entities("Node", 0, 4)
+    with pytest.raises(oracle_mod.OracleError):
+        o.add_entities("Node", 10, 4)
+
+
+def test_results_do_not_depend_on_rank_count(oracle_mod):
+    case = dict(n=600, per_entity=4, min_delay=0.1, lookahead=0.1, p_remote=0.3,
+                mode=1, end=6.0, seed=21)
+    ref = run_oracle_phold(oracle_mod, case, size=1)
+    for size in (2, 4, 7):
+        st, cnt, h = run_oracle_phold(oracle_mod, case, size=size)
+        assert st["digest"] == ref[0]["digest"]
+        assert st["windows"] == ref[0]["windows"]
+        np.testing.assert_array_equal(cnt, ref[1])
+        np.testing.assert_array_equal(h, ref[2])
+
+
+def test_sched_events_equals_sched_service(oracle_mod):
+    from simian_b200.workloads import build_phold, phold_params_blob
+    case = dict(n=300, per_entity=2, min_delay=0.1, lookahead=0.1, p_remote=0.1,
+                mode=1, end=4.0, seed=2)
+    ref = run_oracle_phold(oracle_mod, case)
+    o = oracle_mod.Oracle("ev", 0.0, case["end"], case["min_delay"], seed=2)
+    o.define_class("Node", 0)
+    o.add_entities("Node", 0, case["n"])
+    o.attach_service("Node", "generate", "phold_generate")
+    o.set_class_params("Node", phold_params_blob(0, case["n"], 0.1, 1.0, 0.1, 1, 1))
+    ev = np.zeros(case["n"] * 2, dtype=oracle_mod.EVENT_DTYPE)
+    ev["dst"] = np.tile(np.arange(case["n"], dtype=np.uint32), 2)
+    ev["src"] = 0xFFFFFFFF
+    ev["flags"] = 1
+    ev["seq"] = np.arange(len(ev), dtype=np.uint32)
+    o.sched_events(ev)
+    st = o.run()
+    assert st["digest"] == ref[0]["digest"]
