@@ -90,7 +90,8 @@ const char *simian_last_error(simian_engine *e);
  *   "pool_events"     event pool capacity in records (default 4x initial + slack)
  *   "outbox_events"   per-peer cross-GPU staging capacity in records
  *   "launch_batch"    window kernels enqueued between host polls
- *   "tie_check"       1: count same-entity time ties (default 1)             */
+ *   "tie_check"       1: count same-entity time ties (default 1)
+ *   "force_sequential" 1: always run handlers one thread per entity (testing)  */
 int simian_set_option(simian_engine *e, const char *key, double value);
 
 /* Entity classes.  An entity class = the `name` of addEntity plus the JS class

@@ -36,6 +36,14 @@ enum simian_builtin_fn {
   SIMIAN_FN__END
 };
 
+/* A handler is PURE when it neither touches state() nor sends to itself with
+ * rx omitted below the window bound: its effect depends only on (self id,
+ * commit index, now, handler, src, data).  The engine then runs it with one
+ * thread per EVENT instead of one thread per entity.                         */
+SIMIAN_HD int simian_fn_is_pure(int fn) {
+  return fn == SIMIAN_FN_PHOLD_GENERATE || fn == SIMIAN_FN_COUNT_ONLY;
+}
+
 /* -------------------------------------------------------------- PHOLD ---- */
 
 /* destination modes */

@@ -93,6 +93,7 @@ struct DevCfg {
   uint64_t seed;
   int rank, size;
   int n_classes, tie_check;
+  int all_pure, pad2_; // every attached handler is stateless: thread-per-event path
   DevClass cls[SIMIAN_MAX_CLASSES];
   // entities
   EntityCore *core;
@@ -100,12 +101,15 @@ struct DevCfg {
   // calendar
   double inv_w;
   uint32_t ring, ring_mask;
-  uint32_t *cell_cur; // [(ring+2) * n_blocks], row-major by sub-bucket slot
+  // cell head word = (head page << 32) | records claimed in the head page;
+  // [(ring+2) * n_blocks], row-major by sub-bucket slot; the last two rows are
+  // the far-future rows
+  unsigned long long *cell_state;
   simian_event_t *pool;
-  uint32_t *page_next, *page_fill;
+  uint32_t *page_next; // older page of the same cell (always full)
   uint32_t *free_ring;
   uint32_t n_pages, n_ids;
-  uint32_t *snap_cur, *snap_fill; // [n_blocks] head snapshot of row tb_hi
+  unsigned long long *snap; // [n_blocks] head words of row tb_hi at window start
   WinState *win;                  // [2]
   DevAcc *acc;
   // cross-GPU staging (size > 1)

@@ -64,7 +64,7 @@ struct simian_engine {
   double bucket_width = 0;
   uint32_t ring = 2048;
   uint64_t pool_events = 0, outbox_events = 0;
-  int launch_batch = 16, tie_check = 1;
+  int launch_batch = 16, tie_check = 1, force_sequential = 0;
   // model
   std::vector<HostClass> classes;
   std::map<std::string, int> class_ix;
@@ -155,6 +155,7 @@ int setup(simian_engine *e) {
   c.tie_check = e->tie_check;
   c.n_classes = (int)e->classes.size();
   c.n_ids = e->n_ids;
+  c.all_pure = e->force_sequential ? 0 : 1;
   if (c.n_classes == 0) return e->fail(SIMIAN_ERR_BAD_ARGUMENT, "no entities added");
   uint32_t g = (uint32_t)e->size, slot = 0;
   for (int k = 0; k < c.n_classes; k++) {
@@ -173,6 +174,8 @@ int setup(simian_engine *e) {
     d.base_rank = h.base_rank;
     d.state_bytes = h.state_bytes;
     memcpy(d.fn_of_service, h.fn_of_service, sizeof d.fn_of_service);
+    for (int sidx = 0; sidx < SIMIAN_MAX_SERVICES; sidx++)
+      if (h.fn_of_service[sidx] && !simian_fn_is_pure(h.fn_of_service[sidx])) c.all_pure = 0;
     if (dev_alloc(e, &h.d_state, (size_t)h.n_local * h.state_bytes)) return e->err_code;
     if (h.state_bytes && h.n_local) {
       if (h.has_init) {
@@ -212,13 +215,11 @@ int setup(simian_engine *e) {
   c.n_pages = (uint32_t)n_pages;
   size_t n_cells = (size_t)(ring + 2) * c.n_blocks;
   if (dev_alloc(e, &c.core, c.n_slots)) return e->err_code;
-  if (dev_alloc(e, &c.cell_cur, n_cells)) return e->err_code;
+  if (dev_alloc(e, &c.cell_state, n_cells)) return e->err_code;
   if (dev_alloc(e, &c.pool, (size_t)c.n_pages * PAGE)) return e->err_code;
   if (dev_alloc(e, &c.page_next, c.n_pages)) return e->err_code;
-  if (dev_alloc(e, &c.page_fill, c.n_pages)) return e->err_code;
   if (dev_alloc(e, &c.free_ring, c.n_pages)) return e->err_code;
-  if (dev_alloc(e, &c.snap_cur, c.n_blocks)) return e->err_code;
-  if (dev_alloc(e, &c.snap_fill, c.n_blocks)) return e->err_code;
+  if (dev_alloc(e, &c.snap, c.n_blocks)) return e->err_code;
   if (dev_alloc(e, &c.win, 2)) return e->err_code;
   if (dev_alloc(e, &c.acc, 1)) return e->err_code;
   if (dev_alloc(e, &e->d_digest, 2)) return e->err_code;
@@ -386,6 +387,7 @@ int simian_set_option(simian_engine *e, const char *key, double v) {
   else if (k == "outbox_events") e->outbox_events = (uint64_t)v;
   else if (k == "launch_batch") e->launch_batch = v < 1 ? 1 : (int)v;
   else if (k == "tie_check") e->tie_check = v != 0;
+  else if (k == "force_sequential") e->force_sequential = v != 0;
   else return e->fail(SIMIAN_ERR_BAD_ARGUMENT, "unknown option " + k);
   return 0;
 }

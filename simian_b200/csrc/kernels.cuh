@@ -135,7 +135,8 @@ struct AppendCtx { // per-CTA, in shared memory
   uint32_t far_appends, page_allocs;
 };
 
-#define SIMIAN_LOCKED 0xFFFFFFFEu // cell head while its first page is installed
+// head word of an empty cell: no page, "full" so the first append installs one
+#define CELL_EMPTY (((unsigned long long)SIMIAN_NONE << 32) | (unsigned long long)PAGE)
 
 __device__ __forceinline__ void append_ctx_init(AppendCtx &ax) {
   if (threadIdx.x == 0) ax.far_appends = ax.page_allocs = 0;
@@ -170,55 +171,34 @@ __device__ __forceinline__ void append_ctx_flush(const DevCfg &c, AppendCtx &ax)
 }
 
 // eventQ.push (eventQ.js:29-43) as an append to the cell's page chain.
-// Slot claim = one atomicAdd on the head page's fill counter.  Exactly one
-// thread installs a page: the one whose claim returned PAGE (first overflow),
-// or the winner of the NONE->LOCKED CAS for an empty cell; the others wait for
-// the head to change (starvation-free under independent thread scheduling).
+// ONE 64-bit atomicAdd on the cell's head word claims a slot and names the
+// page in the same L2 round trip.  Exactly one thread installs a new page: the
+// one whose claim returned PAGE (first overflow; an empty cell is born "full");
+// later claimants wait for the page field to change (starvation-free under
+// independent thread scheduling).
 __device__ __forceinline__ void cell_append(const DevCfg &c, AppendCtx &ax,
                                             unsigned long long alloc_limit, uint32_t cell,
                                             const RecBits &r) {
-  uint32_t *curp = c.cell_cur + cell;
+  unsigned long long *hp = c.cell_state + cell;
 #pragma unroll 1
   for (;;) {
-    uint32_t p = ld_cg(curp);
-    if (p == SIMIAN_LOCKED) {
-      if (ld_cg(&c.acc->error)) return;
-      __nanosleep(40);
-      continue;
-    }
-    if (p == SIMIAN_NONE) {
-      if (atomicCAS(curp, SIMIAN_NONE, SIMIAN_LOCKED) == SIMIAN_NONE) {
-        uint32_t np = page_get(c, ax, alloc_limit);
-        if (np == SIMIAN_NONE) {
-          atomicExch(curp, SIMIAN_NONE);
-          return; // sticky error set
-        }
-        c.page_next[np] = SIMIAN_NONE;
-        c.page_fill[np] = 1; // slot 0 is ours
-        st_rec(c.pool + (size_t)np * PAGE, r);
-        __threadfence();
-        atomicExch(curp, np);
-        return;
-      }
-      continue;
-    }
-    uint32_t i = atomicAdd(&c.page_fill[p], 1u);
+    unsigned long long old = atomicAdd(hp, 1ull);
+    uint32_t p = (uint32_t)(old >> 32), i = (uint32_t)old;
     if (i < (uint32_t)PAGE) {
       st_rec(c.pool + ((size_t)p * PAGE + i), r);
       return;
     }
     if (i == (uint32_t)PAGE) { // first overflow: install the next page
       uint32_t np = page_get(c, ax, alloc_limit);
-      if (np == SIMIAN_NONE) return;
+      if (np == SIMIAN_NONE) return; // sticky error set
       c.page_next[np] = p;
-      c.page_fill[np] = 1;
-      st_rec(c.pool + (size_t)np * PAGE, r);
+      st_rec(c.pool + (size_t)np * PAGE, r); // slot 0 is ours
       __threadfence();
-      atomicExch(curp, np);
+      atomicExch(hp, ((unsigned long long)np << 32) | 1ull);
       return;
     }
 #pragma unroll 1
-    while (ld_cg(curp) == p) { // wait for the installer
+    while ((uint32_t)(ld_cg64(hp) >> 32) == p) { // wait for the installer
       if (ld_cg(&c.acc->error)) return;
       __nanosleep(40);
     }
@@ -253,14 +233,10 @@ __global__ void k_init(const __grid_constant__ DevCfg c, uint32_t n_cells) {
   size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t j = i; j < c.n_pages; j += stride) {
     c.free_ring[j] = (uint32_t)j;
-    c.page_fill[j] = 0;
     c.page_next[j] = SIMIAN_NONE;
   }
-  for (size_t j = i; j < n_cells; j += stride) c.cell_cur[j] = SIMIAN_NONE;
-  for (size_t j = i; j < c.n_blocks; j += stride) {
-    c.snap_cur[j] = SIMIAN_NONE;
-    c.snap_fill[j] = 0;
-  }
+  for (size_t j = i; j < n_cells; j += stride) c.cell_state[j] = CELL_EMPTY;
+  for (size_t j = i; j < c.n_blocks; j += stride) c.snap[j] = CELL_EMPTY;
   for (size_t j = i; j < c.n_slots; j += stride) {
     EntityCore z;
     z.count = 0;
@@ -385,7 +361,8 @@ struct WindowShared {
   uint32_t off[EPB + 1];
   uint32_t pg_id[PGMAX];
   uint16_t pg_cnt[PGMAX];
-  uint32_t refs[NREFS];
+  uint32_t refs[NREFS];   // due-event references grouped by local entity
+  uint16_t ent_of[NREFS]; // local entity of refs[i] (thread-per-event path)
 };
 
 // per-thread accumulators of the handler phase
@@ -395,6 +372,9 @@ struct ThreadAcc {
 };
 
 // what a handler reaches through `self` on the device (see simian_models.h)
+// SEQ: one thread per entity (stateful handlers, same-window self-sends);
+// !SEQ: one thread per event (pure handlers).
+template <bool SEQ>
 struct DevCtx {
   const DevCfg &c;
   WindowShared &sh;
@@ -408,8 +388,8 @@ struct DevCtx {
   unsigned long long data_;
   // same-window self-sends (rx omitted, offset < minDelay allowed: entity.js:41)
   int npend;
-  double pend_time[SIMIAN_SELF_MAX];
-  unsigned long long pend_q2[SIMIAN_SELF_MAX], pend_data[SIMIAN_SELF_MAX];
+  double pend_time[SEQ ? SIMIAN_SELF_MAX : 1];
+  unsigned long long pend_q2[SEQ ? SIMIAN_SELF_MAX : 1], pend_data[SEQ ? SIMIAN_SELF_MAX : 1];
 
   __device__ __forceinline__ DevCtx(const DevCfg &c_, WindowShared &sh_, ThreadAcc &ta_)
       : c(c_), sh(sh_), ta(ta_), npend(0) {}
@@ -450,7 +430,7 @@ struct DevCtx {
         return;
       }
       if (time < W.hi) { // lands inside this window: stays with the entity
-        if (npend >= SIMIAN_SELF_MAX) {
+        if (!SEQ || npend >= SIMIAN_SELF_MAX) {
           set_error(c, SIMIAN_ERR_SELF_PENDING);
           return;
         }
@@ -485,7 +465,8 @@ struct DevCtx {
   }
 };
 
-__device__ __forceinline__ void run_handler(DevCtx &ctx, uint32_t fn) {
+template <bool SEQ>
+__device__ __forceinline__ void run_handler(DevCtx<SEQ> &ctx, uint32_t fn) {
   switch (fn) {
     case SIMIAN_FN_PHOLD_GENERATE:
       simian_phold_generate(ctx);
@@ -513,7 +494,7 @@ __device__ __forceinline__ bool key_lt(unsigned long long a1, unsigned long long
 __device__ __noinline__ void process_entity(const DevCfg &c, WindowShared &sh, ThreadAcc &ta,
                                             uint32_t slot, const uint32_t *refs, uint32_t n) {
   int k;
-  DevCtx ctx(c, sh, ta);
+  DevCtx<true> ctx(c, sh, ta);
   ctx.self_slot = slot;
   ctx.self_gid = gid_of_slot(c, slot, k);
   ctx.cl = &c.cls[k];
@@ -619,6 +600,83 @@ __device__ __noinline__ void process_entity(const DevCfg &c, WindowShared &sh, T
   c.core[slot] = st;
 }
 
+// ---- thread-per-event path (pure handlers) --------------------------------
+// Phase A, one thread per entity: put the entity's due events in
+// (time, handler, src, seq) order, run the commit bookkeeping (tie check, trace
+// hash chain, commit count) -- cheap and inherently sequential per entity.
+__device__ __forceinline__ void order_entity(const DevCfg &c, WindowShared &sh, ThreadAcc &ta,
+                                             uint32_t slot, uint32_t le, uint32_t pos0,
+                                             uint32_t n) {
+  EntityCore st = c.core[slot];
+  uint32_t *g = &sh.refs[pos0];
+  double last_time = 0;
+  unsigned long long last_q = 0, last_data = 0;
+#pragma unroll 1
+  for (uint32_t a = 0; a < n; a++) {
+    RecBits best = ld_rec(c.pool + g[a]);
+    if (a + 1 < n) { // selection: min key of g[a..n)
+      unsigned long long b1 = simian_time_key(best.time());
+      unsigned long long b2 = ((unsigned long long)best.handler() << 32) | best.src();
+      uint32_t bj = a;
+#pragma unroll 1
+      for (uint32_t j = a + 1; j < n; j++) {
+        RecBits r = ld_rec(c.pool + g[j]);
+        unsigned long long k1 = simian_time_key(r.time());
+        unsigned long long k2 = ((unsigned long long)r.handler() << 32) | r.src();
+        if (key_lt(k1, k2, r.seq(), b1, b2, best.seq())) {
+          best = r;
+          b1 = k1;
+          b2 = k2;
+          bj = j;
+        }
+      }
+      uint32_t tmp = g[a];
+      g[a] = g[bj];
+      g[bj] = tmp;
+    }
+    sh.ent_of[pos0 + a] = (uint16_t)le;
+    double time = best.time();
+    unsigned long long q = ((unsigned long long)best.handler() << 32) | best.src();
+    if (c.tie_check && a && time == last_time) {
+      ta.ties++;
+      if (q != last_q || best.data() != last_data) ta.dties++;
+    }
+    last_time = time;
+    last_q = q;
+    last_data = best.data();
+    st.hash = simian_trace_step(st.hash, time, best.handler(), best.src(), best.data());
+    st.count++;
+    unsigned long long tk = simian_time_key(time);
+    ta.max_key = tk > ta.max_key ? tk : ta.max_key;
+  }
+  ta.committed += n;
+  c.core[slot] = st;
+}
+
+// Phase B, one thread per EVENT: RNG, log, destination, emit (simian.js:129-131
+// with a pure handler; its commit index is the entity's new count - n + rank).
+__device__ __forceinline__ void emit_event(const DevCfg &c, WindowShared &sh, ThreadAcc &ta,
+                                           uint32_t slot0, uint32_t base, uint32_t i) {
+  uint32_t le = sh.ent_of[i];
+  uint32_t o0 = sh.off[le] - base, n = sh.off[le + 1] - sh.off[le];
+  uint32_t slot = slot0 + le;
+  RecBits r = ld_rec(c.pool + sh.refs[i]);
+  int k;
+  DevCtx<false> ctx(c, sh, ta);
+  ctx.self_slot = slot;
+  ctx.self_gid = gid_of_slot(c, slot, k);
+  ctx.cl = &c.cls[k];
+  ctx.commit_idx = c.core[slot].count - n + (i - o0);
+  ctx.key = simian_rng_key(c.seed, ctx.self_gid, ctx.commit_idx);
+  ctx.n_emit = 0;
+  ctx.now_ = r.time(); // simian.js:126
+  ctx.handler_ = r.handler();
+  ctx.src_ = r.src();
+  ctx.data_ = r.data();
+  uint32_t h = r.handler();
+  run_handler(ctx, h < SIMIAN_MAX_SERVICES ? ctx.cl->fn_of_service[h] : 0);
+}
+
 // block-wide exclusive scan of sh.cnt[EPB] into sh.off[EPB+1]; returns total
 __device__ __forceinline__ uint32_t block_scan_counts(WindowShared &sh) {
   constexpr int ITEMS = EPB / NTHREADS;
@@ -707,8 +765,8 @@ __device__ void local_min_candidate(const DevCfg &c, const WinState &W, WindowSh
         if (i < total) {
           long long j = j0 + (long long)(i / c.n_blocks);
           uint32_t b = (uint32_t)(i % c.n_blocks);
-          if (ld_cg(&c.cell_cur[(uint32_t)(j & (long long)c.ring_mask) * c.n_blocks + b]) !=
-              SIMIAN_NONE)
+          if ((uint32_t)(ld_cg64(&c.cell_state[(uint32_t)(j & (long long)c.ring_mask) *
+                                                   c.n_blocks + b]) >> 32) != SIMIAN_NONE)
             atomicMin((unsigned long long *)&sh.scan_j, (unsigned long long)j);
         }
       }
@@ -725,9 +783,9 @@ __device__ void local_min_candidate(const DevCfg &c, const WinState &W, WindowSh
     unsigned long long mn = SIMIAN_KEY_NONE;
     uint32_t row = (uint32_t)(jf & (long long)c.ring_mask) * c.n_blocks;
     for (uint32_t b = tid; b < c.n_blocks; b += NTHREADS) {
-      uint32_t p = ld_cg(&c.cell_cur[row + b]);
+      unsigned long long hw = ld_cg64(&c.cell_state[row + b]);
+      uint32_t p = (uint32_t)(hw >> 32), f = (uint32_t)hw;
       while (p != SIMIAN_NONE) {
-        uint32_t f = ld_cg(&c.page_fill[p]);
         f = f < PAGE ? f : PAGE;
         for (uint32_t s = 0; s < f; s++) {
           unsigned long long q0 =
@@ -736,6 +794,7 @@ __device__ void local_min_candidate(const DevCfg &c, const WinState &W, WindowSh
           mn = kk < mn ? kk : mn;
         }
         p = ld_cg(&c.page_next[p]);
+        f = PAGE;
       }
     }
     if (mn != SIMIAN_KEY_NONE) atomicMin(&sh.min_key, mn);
@@ -795,16 +854,8 @@ __device__ void setup_next_window(const DevCfg &c, const WinState &W, WinState *
   // snapshot the heads of row tb_hi: appends of the next launch may target it
   if (!nw.done) {
     uint32_t row = (uint32_t)(nw.tb_hi & (long long)c.ring_mask) * c.n_blocks;
-    for (uint32_t b = tid; b < c.n_blocks; b += blockDim.x) {
-      uint32_t p = ld_cg(&c.cell_cur[row + b]);
-      uint32_t f = 0;
-      if (p != SIMIAN_NONE) {
-        f = ld_cg(&c.page_fill[p]);
-        f = f < PAGE ? f : PAGE;
-      }
-      c.snap_cur[b] = p;
-      c.snap_fill[b] = f;
-    }
+    for (uint32_t b = tid; b < c.n_blocks; b += blockDim.x)
+      c.snap[b] = ld_cg64(&c.cell_state[row + b]);
   }
   __syncthreads();
   if (tid == 0) {
@@ -818,13 +869,13 @@ __device__ void setup_next_window(const DevCfg &c, const WinState &W, WinState *
 
 // free a whole cell (pages -> ring, head cleared); one thread
 __device__ __forceinline__ void free_cell(const DevCfg &c, uint32_t cell) {
-  uint32_t p = c.cell_cur[cell];
+  uint32_t p = (uint32_t)(c.cell_state[cell] >> 32);
   while (p != SIMIAN_NONE) {
     uint32_t nx = c.page_next[p];
     page_free(c, p);
     p = nx;
   }
-  c.cell_cur[cell] = SIMIAN_NONE;
+  c.cell_state[cell] = CELL_EMPTY;
 }
 
 // Far-row redistribution for block b (own cells only: no cross-CTA traffic).
@@ -846,13 +897,9 @@ __device__ void redistribute_block(const DevCfg &c, WindowShared &sh, uint32_t b
   if (tid == 0) sh.npg = 0;
   __syncthreads();
   if (tid == 0) {
-    uint32_t head = c.cell_cur[far_cell];
-    uint32_t hc = 0;
-    if (head != SIMIAN_NONE) {
-      hc = c.page_fill[head];
-      hc = hc < PAGE ? hc : PAGE;
-    }
-    list_cell_pages(c, sh, head, hc, PG_FREE_FLAG);
+    unsigned long long hw = c.cell_state[far_cell];
+    uint32_t hc = (uint32_t)hw;
+    list_cell_pages(c, sh, (uint32_t)(hw >> 32), hc < PAGE ? hc : PAGE, PG_FREE_FLAG);
   }
   __syncthreads();
   uint32_t npg = sh.npg;
@@ -868,7 +915,7 @@ __device__ void redistribute_block(const DevCfg &c, WindowShared &sh, uint32_t b
   }
   __syncthreads();
   for (uint32_t i = tid; i < npg; i += NTHREADS) page_free(c, sh.pg_id[i]);
-  if (tid == 0) c.cell_cur[far_cell] = SIMIAN_NONE;
+  if (tid == 0) c.cell_state[far_cell] = CELL_EMPTY;
 }
 
 // One lookahead window (or one redistribution pass) for entity block blockIdx.x.
@@ -913,19 +960,12 @@ __global__ void __launch_bounds__(NTHREADS)
     if (tid < ncell) {
       long long tb = W.tb_lo + tid;
       uint32_t cell = (uint32_t)(tb & (long long)c.ring_mask) * c.n_blocks + b;
-      uint32_t head, hc = 0, flag = 0;
-      if (tb == W.tb_hi) { // may be appended to during this launch: snapshot
-        head = c.snap_cur[b];
-        hc = c.snap_fill[b];
-      } else {
-        head = c.cell_cur[cell];
-        if (head != SIMIAN_NONE) {
-          hc = c.page_fill[head];
-          hc = hc < PAGE ? hc : PAGE;
-        }
-        flag = PG_FREE_FLAG; // fully below the bound: recycled after this window
-      }
-      list_cell_pages(c, sh, head, hc, flag);
+      // row tb_hi may be appended to during this launch: use the snapshot; rows
+      // fully below the bound are recycled after this window
+      unsigned long long hw = (tb == W.tb_hi) ? c.snap[b] : c.cell_state[cell];
+      uint32_t hc = (uint32_t)hw;
+      list_cell_pages(c, sh, (uint32_t)(hw >> 32), hc < PAGE ? hc : PAGE,
+                      (tb == W.tb_hi) ? 0u : PG_FREE_FLAG);
     }
     __syncthreads();
     uint32_t npg = sh.npg;
@@ -991,10 +1031,22 @@ __global__ void __launch_bounds__(NTHREADS)
           }
         }
         __syncthreads();
-        // K3 + K4: handlers, one thread per entity
-        for (uint32_t le = e_lo + tid; le < e_hi; le += NTHREADS) {
-          uint32_t n = sh.off[le + 1] - sh.off[le];
-          if (n) process_entity(c, sh, ta, slot0 + le, &sh.refs[sh.off[le] - base], n);
+        if (c.all_pure) {
+          // K3a: per entity, order + commit bookkeeping
+          for (uint32_t le = e_lo + tid; le < e_hi; le += NTHREADS) {
+            uint32_t n = sh.off[le + 1] - sh.off[le];
+            if (n) order_entity(c, sh, ta, slot0 + le, le, sh.off[le] - base, n);
+          }
+          __syncthreads();
+          // K3b + K4: per EVENT, handler + emit
+          uint32_t m = sh.off[e_hi] - base;
+          for (uint32_t i = tid; i < m; i += NTHREADS) emit_event(c, sh, ta, slot0, base, i);
+        } else {
+          // K3 + K4: stateful handlers, one thread per entity
+          for (uint32_t le = e_lo + tid; le < e_hi; le += NTHREADS) {
+            uint32_t n = sh.off[le + 1] - sh.off[le];
+            if (n) process_entity(c, sh, ta, slot0 + le, &sh.refs[sh.off[le] - base], n);
+          }
         }
         __syncthreads();
       }
@@ -1017,7 +1069,7 @@ __global__ void __launch_bounds__(NTHREADS)
           c.free_ring[(sh.free_base + pos++) % c.n_pages] = sh.pg_id[i];
       if (tid < ncell - 1) {
         long long tb = W.tb_lo + tid;
-        c.cell_cur[(uint32_t)(tb & (long long)c.ring_mask) * c.n_blocks + b] = SIMIAN_NONE;
+        c.cell_state[(uint32_t)(tb & (long long)c.ring_mask) * c.n_blocks + b] = CELL_EMPTY;
       }
       // rows the window jumped over (dead records only)
       long long nskip = W.tb_lo - W.tb_clean;

@@ -70,6 +70,4 @@ def test_product_never_touches_the_oracle():
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".js", ".cc")):
                 text = open(os.path.join(dirpath, f)).read()
-                assert "oracle" not in text.lower() or f == "workloads.py" and \
-                    "import oracle" not in text and "from oracle" not in text, \
-                    os.path.join(dirpath, f)
+                assert "oracle" not in text.lower(), os.path.join(dirpath, f)

@@ -51,9 +51,12 @@ CASES = [
 
 
 @pytest.mark.parametrize("case", CASES, ids=lambda c: c["name"])
-def test_engine_matches_oracle(case, oracle_mod):
+@pytest.mark.parametrize("sequential", [0, 1], ids=["per_event", "per_entity"])
+def test_engine_matches_oracle(case, sequential, oracle_mod):
+    """both handler mappings: one thread per event (pure handlers) and one
+    thread per entity (the general path)"""
     so, co, ho = run_oracle_phold(oracle_mod, case)
-    se, ce, he = run_engine_phold(case)
+    se, ce, he = run_engine_phold(case, force_sequential=sequential)
     assert_parity(so, co, ho, se, ce, he)
 
 
