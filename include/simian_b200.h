@@ -85,7 +85,7 @@ const char *simian_last_error(simian_engine *e);
 
 /* Engine tunables, all optional, before the first run:
  *   "seed"            engine seed of the shared counter-based RNG (default 1)
- *   "bucket_width"    calendar sub-bucket width in simulated time (default minDelay/4)
+ *   "bucket_width"    calendar sub-bucket width in simulated time (default minDelay/8)
  *   "ring_buckets"    calendar ring length, power of two (default 2048)
  *   "pool_events"     event pool capacity in records (default 4x initial + slack)
  *   "outbox_events"   per-peer cross-GPU staging capacity in records
@@ -182,6 +182,10 @@ int simian_read_trace_hashes(simian_engine *e, const char *className,
 /* getEntity(name, num) state read-back (simian.js:200-205)                  */
 int simian_read_state(simian_engine *e, const char *className, uint32_t first,
                       uint32_t count, void *out);
+
+/* diagnostic only: summed SM cycles spent in each phase of the window kernel
+ * by all CTAs (zeros unless the library was built with SIMIAN_PROFILE_PHASES) */
+int simian_debug_phase_cycles(simian_engine *e, uint64_t *out12);
 
 #ifdef __cplusplus
 }

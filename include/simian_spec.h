@@ -182,13 +182,21 @@ SIMIAN_HD double simian_exponential(uint64_t draw, double lambda) {
 /* Per-entity order-sensitive chain over the events the entity commits, in
  * commit order.  Covers what the reference handler sees: (time, service
  * name, tx/txId, data) -- simian.js:126-131.  `seq` is NOT hashed.          */
-SIMIAN_HD uint64_t simian_trace_step(uint64_t h, double time, uint32_t handler,
-                                     uint32_t src, uint64_t data) {
+/* per-event part (order independent, computable in parallel) */
+SIMIAN_HD uint64_t simian_trace_event(double time, uint32_t handler, uint32_t src,
+                                      uint64_t data) {
   uint64_t x = simian_mix64(simian_f64_bits(time) +
                             SIMIAN_GOLD * ((((uint64_t)handler) << 32) | src));
-  x = simian_mix64(x ^ data);
+  return simian_mix64(x ^ data);
+}
+/* chain part (sequential per entity, a few integer operations) */
+SIMIAN_HD uint64_t simian_trace_chain(uint64_t h, uint64_t x) {
   h = (h ^ x) * SIMIAN_GOLD;
   return h ^ (h >> 29);
+}
+SIMIAN_HD uint64_t simian_trace_step(uint64_t h, double time, uint32_t handler,
+                                     uint32_t src, uint64_t data) {
+  return simian_trace_chain(h, simian_trace_event(time, handler, src, data));
 }
 
 /* order-insensitive across entities, order-sensitive within each entity     */

@@ -7,7 +7,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsimian_b200.so")
+LIB_PATH = os.environ.get("SIMIAN_B200_LIB") or os.path.join(
+    HERE, "libsimian_b200.so")  # the env override selects a tuning variant
 
 EVENT_DTYPE = np.dtype(
     [("time", "<f8"), ("dst", "<u4"), ("src", "<u4"), ("handler", "<u2"),
@@ -75,6 +76,7 @@ SIGNATURES = {
     "simian_read_counts": (_i, [_vp, _cp, _u32, _u32, _vp]),
     "simian_read_trace_hashes": (_i, [_vp, _cp, _u32, _u32, _vp]),
     "simian_read_state": (_i, [_vp, _cp, _u32, _u32, _vp]),
+    "simian_debug_phase_cycles": (_i, [_vp, C.POINTER(_u64)]),
 }
 
 _lib = None
@@ -222,6 +224,11 @@ class Engine:
 
     def set_stream(self, cuda_stream):
         self._ck(self.L.simian_set_stream(self.h, cuda_stream))
+
+    def debug_phase_cycles(self):
+        out = (_u64 * 12)()
+        self._ck(self.L.simian_debug_phase_cycles(self.h, out))
+        return list(out)
 
     # ---- results --------------------------------------------------------
     def _read(self, fn, name, n, first=0):

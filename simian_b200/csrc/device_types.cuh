@@ -26,10 +26,14 @@
 #define SIMIAN_PAGE 64 // records per page (2 KB)
 #endif
 #ifndef SIMIAN_REFS
-#define SIMIAN_REFS 12288 // due-event references a CTA groups per pass
+#define SIMIAN_REFS 2048 // due-event references a CTA groups per pass
 #endif
 #ifndef SIMIAN_PGMAX
-#define SIMIAN_PGMAX 2048 // pages a CTA can list per window
+#define SIMIAN_PGMAX 1024 // pages a CTA can list per window
+#endif
+
+#ifndef SIMIAN_MINBLOCKS
+#define SIMIAN_MINBLOCKS 2 // __launch_bounds__ min CTAs/SM of the window kernel
 #endif
 
 #define SIMIAN_MAX_CLASSES 8
@@ -86,6 +90,7 @@ struct DevAcc {
   unsigned int window_index;
   unsigned int pad_;
   double minvec[2]; // {local minLeft candidate, local far min} for allreduce
+  unsigned long long phase_cycles[12]; // SIMIAN_PROFILE_PHASES builds only
 };
 
 struct DevCfg {

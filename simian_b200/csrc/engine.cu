@@ -200,7 +200,7 @@ int setup(simian_engine *e) {
   c.n_slots = slot;
   c.n_blocks = (slot + EPB - 1) / EPB;
   if (c.n_blocks == 0) c.n_blocks = 1;
-  double w = e->bucket_width > 0 ? e->bucket_width : e->min_delay / 4.0;
+  double w = e->bucket_width > 0 ? e->bucket_width : e->min_delay / 8.0;
   c.inv_w = 1.0 / w;
   uint32_t ring = 256;
   while (ring < e->ring) ring <<= 1;
@@ -646,6 +646,13 @@ static int read_core(simian_engine *e, const char *className, uint32_t first, ui
     uint32_t num = j * g + h.rank_off;
     if (num >= first && num < first + count) out[num - first] = which ? loc[j].hash : loc[j].count;
   }
+  return 0;
+}
+
+// diagnostic: summed SM cycles per k_window phase (SIMIAN_PROFILE_PHASES builds)
+int simian_debug_phase_cycles(simian_engine *e, uint64_t *out12) {
+  if (!e->h_acc) return SIMIAN_ERR_BAD_ARGUMENT;
+  for (int i = 0; i < 12; i++) out12[i] = e->h_acc->phase_cycles[i];
   return 0;
 }
 

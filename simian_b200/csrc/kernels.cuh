@@ -21,6 +21,20 @@
 #define PGMAX SIMIAN_PGMAX
 #define PG_FREE_FLAG 0x8000u
 
+// per-phase SM-cycle accounting of k_window (diagnostic builds only)
+#ifdef SIMIAN_PROFILE_PHASES
+#define PHASE(k)                                                                 \
+  do {                                                                           \
+    if (threadIdx.x == 0) {                                                      \
+      long long _t = clock64();                                                  \
+      atomicAdd(&c.acc->phase_cycles[k], (unsigned long long)(_t - sh.t_last));  \
+      sh.t_last = _t;                                                            \
+    }                                                                            \
+  } while (0)
+#else
+#define PHASE(k) do { } while (0)
+#endif
+
 // ---------------------------------------------------------------- helpers --
 
 struct RecBits { // the 32-byte record as four 64-bit words
@@ -193,7 +207,8 @@ __device__ __forceinline__ void cell_append(const DevCfg &c, AppendCtx &ax,
       if (np == SIMIAN_NONE) return; // sticky error set
       c.page_next[np] = p;
       st_rec(c.pool + (size_t)np * PAGE, r); // slot 0 is ours
-      __threadfence();
+      // no fence: appenders of this launch only write into the page; chains
+      // and records are read after a launch boundary or after the ticket fence
       atomicExch(hp, ((unsigned long long)np << 32) | 1ull);
       return;
     }
@@ -256,6 +271,7 @@ __global__ void k_init(const __grid_constant__ DevCfg c, uint32_t n_cells) {
     a->error = 0;
     a->window_index = 0;
     a->minvec[0] = a->minvec[1] = 0;
+    for (int q = 0; q < 12; q++) a->phase_cycles[q] = 0;
     WinState w;
     w.gmin = c.start;
     w.hi = c.start + c.min_delay;
@@ -349,20 +365,24 @@ __global__ void k_ingest(const __grid_constant__ DevCfg c, const simian_event_t 
 
 // ---------------------------------------------------------- window kernel --
 
+#define LIST_END 0xFFFFu
+
 struct WindowShared {
   WinState W;
   AppendCtx ax;
   unsigned long long min_key, max_key, free_base;
   uint32_t committed, emitted, dropped, ties, dties;
-  uint32_t npg, nfree, nfree_w, total_due, pass_lo, pass_hi, is_last, found;
-  long long scan_j;
-  uint32_t warp_tmp[32];
-  uint32_t cnt[EPB];
-  uint32_t off[EPB + 1];
-  uint32_t pg_id[PGMAX];
+  uint32_t npg, nfree, total, is_last, found, stack_n, pass_lo, pass_hi;
+  long long scan_j, t_last;
+  uint32_t rstack[64];          // entity sub-ranges still to process (lo, hi)
+  uint32_t head[EPB];           // per local entity: index of its first due event
+  uint32_t pg_id[PGMAX];        // pages of this block's cells in the window rows
   uint16_t pg_cnt[PGMAX];
-  uint32_t refs[NREFS];   // due-event references grouped by local entity
-  uint16_t ent_of[NREFS]; // local entity of refs[i] (thread-per-event path)
+  uint32_t refs[NREFS];         // due events: pool index of the record
+  uint32_t tq[NREFS];           // due events: time quantised inside the window
+  unsigned long long xs[NREFS]; // due events: order-independent trace word
+  uint16_t nxt[NREFS];          // next due event of the same entity
+  uint16_t rk[NREFS];           // rank of the event inside its entity
 };
 
 // per-thread accumulators of the handler phase
@@ -492,7 +512,9 @@ __device__ __forceinline__ bool key_lt(unsigned long long a1, unsigned long long
 // entity; entities never interact inside a window because cross-entity sends
 // carry offset >= minDelay, entity.js:41).
 __device__ __noinline__ void process_entity(const DevCfg &c, WindowShared &sh, ThreadAcc &ta,
-                                            uint32_t slot, const uint32_t *refs, uint32_t n) {
+                                            uint32_t slot, uint32_t first) {
+  uint32_t n = 0;
+  for (uint32_t j = first; j != LIST_END; j = sh.nxt[j]) n++;
   int k;
   DevCtx<true> ctx(c, sh, ta);
   ctx.self_slot = slot;
@@ -514,12 +536,12 @@ __device__ __noinline__ void process_entity(const DevCfg &c, WindowShared &sh, T
     uint32_t g3 = 0;
     if (taken < n) {
       if (n == 1) {
-        g = ld_rec(c.pool + refs[0]);
+        g = ld_rec(c.pool + sh.refs[first]);
         have_g = true;
       } else {
 #pragma unroll 1
-        for (uint32_t j = 0; j < n; j++) {
-          RecBits r = ld_rec(c.pool + refs[j]);
+        for (uint32_t j = first; j != LIST_END; j = sh.nxt[j]) {
+          RecBits r = ld_rec(c.pool + sh.refs[j]);
           unsigned long long k1 = simian_time_key(r.time());
           unsigned long long k2 = ((unsigned long long)r.handler() << 32) | r.src();
           uint32_t k3 = r.seq();
@@ -601,72 +623,66 @@ __device__ __noinline__ void process_entity(const DevCfg &c, WindowShared &sh, T
 }
 
 // ---- thread-per-event path (pure handlers) --------------------------------
-// Phase A, one thread per entity: put the entity's due events in
-// (time, handler, src, seq) order, run the commit bookkeeping (tie check, trace
-// hash chain, commit count) -- cheap and inherently sequential per entity.
-__device__ __forceinline__ void order_entity(const DevCfg &c, WindowShared &sh, ThreadAcc &ta,
-                                             uint32_t slot, uint32_t le, uint32_t pos0,
-                                             uint32_t n) {
-  EntityCore st = c.core[slot];
-  uint32_t *g = &sh.refs[pos0];
-  double last_time = 0;
-  unsigned long long last_q = 0, last_data = 0;
+// Phase RB, one thread per EVENT: rank of the event inside its entity's list
+// under (time, handler, src, seq) -- decided from the quantised times in shared
+// memory, exact keys only on a quantisation collision -- tie check against its
+// predecessor, the order-independent part of the trace hash, then the handler
+// itself (simian.js:129-131): RNG, log, destination, emit.
+// Commit index = the entity's committed count + rank.
+__device__ __forceinline__ void rank_and_emit(const DevCfg &c, WindowShared &sh, ThreadAcc &ta,
+                                              uint32_t slot0, uint32_t i) {
+  RecBits r = ld_rec(c.pool + sh.refs[i]);
+  const uint32_t le = r.dst() - slot0, slot = r.dst();
+  const unsigned long long count0 = c.core[slot].count; // may miss to DRAM: issued early
+  const uint32_t myq = sh.tq[i];
+  uint32_t rank = 0;
+  bool have_pred = false;
+  RecBits pred;
 #pragma unroll 1
-  for (uint32_t a = 0; a < n; a++) {
-    RecBits best = ld_rec(c.pool + g[a]);
-    if (a + 1 < n) { // selection: min key of g[a..n)
-      unsigned long long b1 = simian_time_key(best.time());
-      unsigned long long b2 = ((unsigned long long)best.handler() << 32) | best.src();
-      uint32_t bj = a;
-#pragma unroll 1
-      for (uint32_t j = a + 1; j < n; j++) {
-        RecBits r = ld_rec(c.pool + g[j]);
-        unsigned long long k1 = simian_time_key(r.time());
-        unsigned long long k2 = ((unsigned long long)r.handler() << 32) | r.src();
-        if (key_lt(k1, k2, r.seq(), b1, b2, best.seq())) {
-          best = r;
-          b1 = k1;
-          b2 = k2;
-          bj = j;
+  for (uint32_t j = sh.head[le]; j != LIST_END; j = sh.nxt[j]) {
+    if (j == i) continue;
+    uint32_t qj = sh.tq[j];
+    if (qj < myq) {
+      rank++;
+    } else if (qj == myq) { // quantisation collision (or a true tie): exact keys
+      RecBits o = ld_rec(c.pool + sh.refs[j]);
+      bool before;
+      if (o.time() != r.time()) {
+        before = o.time() < r.time();
+      } else {
+        unsigned long long a2 = ((unsigned long long)o.handler() << 32) | o.src();
+        unsigned long long b2 = ((unsigned long long)r.handler() << 32) | r.src();
+        before = a2 != b2 ? a2 < b2 : o.seq() < r.seq();
+        if (before) { // equal-time predecessor: keep the latest one
+          if (!have_pred) {
+            pred = o;
+            have_pred = true;
+          } else {
+            unsigned long long p2 = ((unsigned long long)pred.handler() << 32) | pred.src();
+            if (p2 != a2 ? p2 < a2 : pred.seq() < o.seq()) pred = o;
+          }
         }
       }
-      uint32_t tmp = g[a];
-      g[a] = g[bj];
-      g[bj] = tmp;
+      rank += before ? 1u : 0u;
     }
-    sh.ent_of[pos0 + a] = (uint16_t)le;
-    double time = best.time();
-    unsigned long long q = ((unsigned long long)best.handler() << 32) | best.src();
-    if (c.tie_check && a && time == last_time) {
-      ta.ties++;
-      if (q != last_q || best.data() != last_data) ta.dties++;
-    }
-    last_time = time;
-    last_q = q;
-    last_data = best.data();
-    st.hash = simian_trace_step(st.hash, time, best.handler(), best.src(), best.data());
-    st.count++;
-    unsigned long long tk = simian_time_key(time);
-    ta.max_key = tk > ta.max_key ? tk : ta.max_key;
   }
-  ta.committed += n;
-  c.core[slot] = st;
-}
+  if (c.tie_check && have_pred) {
+    ta.ties++;
+    if (pred.q1 >> 32 != r.q1 >> 32 || pred.handler() != r.handler() || pred.q3 != r.q3)
+      ta.dties++;
+  }
+  sh.xs[i] = simian_trace_event(r.time(), r.handler(), r.src(), r.data());
+  sh.rk[i] = (uint16_t)rank;
+  unsigned long long tk = simian_time_key(r.time());
+  ta.max_key = tk > ta.max_key ? tk : ta.max_key;
+  ta.committed++;
 
-// Phase B, one thread per EVENT: RNG, log, destination, emit (simian.js:129-131
-// with a pure handler; its commit index is the entity's new count - n + rank).
-__device__ __forceinline__ void emit_event(const DevCfg &c, WindowShared &sh, ThreadAcc &ta,
-                                           uint32_t slot0, uint32_t base, uint32_t i) {
-  uint32_t le = sh.ent_of[i];
-  uint32_t o0 = sh.off[le] - base, n = sh.off[le + 1] - sh.off[le];
-  uint32_t slot = slot0 + le;
-  RecBits r = ld_rec(c.pool + sh.refs[i]);
   int k;
   DevCtx<false> ctx(c, sh, ta);
   ctx.self_slot = slot;
   ctx.self_gid = gid_of_slot(c, slot, k);
   ctx.cl = &c.cls[k];
-  ctx.commit_idx = c.core[slot].count - n + (i - o0);
+  ctx.commit_idx = count0 + rank;
   ctx.key = simian_rng_key(c.seed, ctx.self_gid, ctx.commit_idx);
   ctx.n_emit = 0;
   ctx.now_ = r.time(); // simian.js:126
@@ -677,44 +693,85 @@ __device__ __forceinline__ void emit_event(const DevCfg &c, WindowShared &sh, Th
   run_handler(ctx, h < SIMIAN_MAX_SERVICES ? ctx.cl->fn_of_service[h] : 0);
 }
 
-// block-wide exclusive scan of sh.cnt[EPB] into sh.off[EPB+1]; returns total
-__device__ __forceinline__ uint32_t block_scan_counts(WindowShared &sh) {
-  constexpr int ITEMS = EPB / NTHREADS;
-  static_assert(EPB % NTHREADS == 0, "EPB must be a multiple of the CTA size");
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  uint32_t v[ITEMS], s = 0;
-#pragma unroll
-  for (int i = 0; i < ITEMS; i++) {
-    v[i] = sh.cnt[tid * ITEMS + i];
-    s += v[i];
+// Phase H, one thread per entity: fold the trace words in rank (= commit)
+// order and publish the new commit count; a few integer operations per event.
+__device__ __forceinline__ void chain_entity(const DevCfg &c, WindowShared &sh, uint32_t slot,
+                                             uint32_t first) {
+  EntityCore st = c.core[slot];
+  uint32_t n = 0;
+  if (sh.nxt[first] == LIST_END) {
+    st.hash = simian_trace_chain(st.hash, sh.xs[first]);
+    n = 1;
+  } else {
+    for (uint32_t j = first; j != LIST_END; j = sh.nxt[j]) n++;
+#pragma unroll 1
+    for (uint32_t r = 0; r < n; r++)
+      for (uint32_t j = first; j != LIST_END; j = sh.nxt[j])
+        if (sh.rk[j] == r) {
+          st.hash = simian_trace_chain(st.hash, sh.xs[j]);
+          break;
+        }
   }
-  uint32_t inc = s;
+  st.count += n;
+  c.core[slot] = st;
+}
+
+// K2: ONE coalesced pass over the block's pages.  Every record whose time is
+// inside [gmin, hi) and whose entity is inside [e_lo, e_hi) is pushed onto its
+// entity's list in shared memory (eventQ.pop for all of them at once,
+// eventQ.js:53-92); on the first pass the minimum time >= hi is tracked (K1).
+// Positions are claimed with one shared-memory atomic per warp.
+__device__ __forceinline__ void collect_due(const DevCfg &c, WindowShared &sh, ThreadAcc &ta,
+                                            uint32_t slot0, uint32_t npg, uint32_t e_lo,
+                                            uint32_t e_hi, bool first, double qscale) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  const WinState &W = sh.W;
+  const uint32_t lim = npg * PAGE;
+  constexpr int U = 4;
+  for (uint32_t base = 0; base < lim; base += U * NTHREADS) {
+    unsigned long long q0[U], q1[U];
+    uint32_t ref[U];
+    bool ok[U];
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    uint32_t x = __shfl_up_sync(0xffffffffu, inc, o);
-    if (lane >= o) inc += x;
-  }
-  if (lane == 31) sh.warp_tmp[wid] = inc;
-  __syncthreads();
-  if (wid == 0) {
-    uint32_t w = lane < NTHREADS / 32 ? sh.warp_tmp[lane] : 0, winc = w;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      uint32_t x = __shfl_up_sync(0xffffffffu, winc, o);
-      if (lane >= o) winc += x;
+    for (int u = 0; u < U; u++) {
+      uint32_t i = base + u * NTHREADS + tid;
+      uint32_t pg = i / PAGE, sl = i % PAGE;
+      ok[u] = i < lim && sl < (uint32_t)(sh.pg_cnt[pg < PGMAX ? pg : 0] & 0x7FFFu);
+      ref[u] = ok[u] ? sh.pg_id[pg] * PAGE + sl : 0;
+      if (ok[u]) ld_rec_head(c.pool + ref[u], q0[u], q1[u]);
     }
-    sh.warp_tmp[lane] = winc - w; // exclusive warp prefix
-    if (lane == 31) sh.off[EPB] = winc;
-  }
-  __syncthreads();
-  uint32_t ex = sh.warp_tmp[wid] + inc - s;
 #pragma unroll
-  for (int i = 0; i < ITEMS; i++) {
-    sh.off[tid * ITEMS + i] = ex;
-    ex += v[i];
+    for (int u = 0; u < U; u++) {
+      bool due = false;
+      uint32_t le = 0;
+      double t = 0;
+      if (ok[u]) {
+        t = __longlong_as_double((long long)q0[u]);
+        if (t < W.hi) {
+          le = (uint32_t)q1[u] - slot0;
+          due = t >= W.gmin && le >= e_lo && le < e_hi;
+        } else if (first) {
+          unsigned long long tk = simian_time_key(t);
+          ta.min_key = tk < ta.min_key ? tk : ta.min_key;
+        }
+      }
+      unsigned m = __ballot_sync(0xffffffffu, due);
+      if (m) {
+        uint32_t p0 = 0;
+        int leader = __ffs(m) - 1;
+        if (lane == leader) p0 = atomicAdd(&sh.total, (uint32_t)__popc(m));
+        p0 = __shfl_sync(0xffffffffu, p0, leader);
+        if (due) {
+          uint32_t pos = p0 + __popc(m & ((1u << lane) - 1u));
+          if (pos < NREFS) {
+            sh.refs[pos] = ref[u];
+            sh.tq[pos] = __double2uint_rd((t - W.gmin) * qscale);
+            sh.nxt[pos] = (uint16_t)atomicExch(&sh.head[le], pos);
+          }
+        }
+      }
+    }
   }
-  __syncthreads();
-  return sh.off[EPB];
 }
 
 // walk one cell's page chain into the CTA's page list
@@ -920,7 +977,7 @@ __device__ void redistribute_block(const DevCfg &c, WindowShared &sh, uint32_t b
 
 // One lookahead window (or one redistribution pass) for entity block blockIdx.x.
 // fuse_advance != 0 (size == 1): the last CTA to finish computes window k+1.
-__global__ void __launch_bounds__(NTHREADS)
+__global__ void __launch_bounds__(NTHREADS, SIMIAN_MINBLOCKS)
     k_window(const __grid_constant__ DevCfg c, uint32_t win_ix, int fuse_advance) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   WindowShared &sh = *reinterpret_cast<WindowShared *>(smem_raw);
@@ -933,19 +990,19 @@ __global__ void __launch_bounds__(NTHREADS)
   if (sh.found) return; // sticky error: CTA-uniform exit
 
   if (tid == 0) {
+    sh.t_last = clock64();
     sh.W = *Wg;
     sh.min_key = SIMIAN_KEY_NONE;
     sh.max_key = 0;
     sh.committed = sh.emitted = sh.dropped = sh.ties = sh.dties = 0;
     sh.npg = 0;
     sh.nfree = 0;
-    sh.nfree_w = 0;
     sh.is_last = 0;
   }
   append_ctx_init(sh.ax);
-  for (int i = tid; i < EPB; i += NTHREADS) sh.cnt[i] = 0;
   __syncthreads();
   const WinState &W = sh.W;
+  PHASE(0);
 
   ThreadAcc ta;
   ta.min_key = SIMIAN_KEY_NONE;
@@ -968,90 +1025,79 @@ __global__ void __launch_bounds__(NTHREADS)
                       (tb == W.tb_hi) ? 0u : PG_FREE_FLAG);
     }
     __syncthreads();
+    PHASE(1);
     uint32_t npg = sh.npg;
     if (npg > PGMAX) {
       if (tid == 0) set_error(c, SIMIAN_ERR_WINDOW_OVERFLOW);
       npg = 0;
     }
-    // ---- K2b: histogram of due events per local entity; leftover min (K1)
+    // ---- K2..K4 over entity sub-ranges; normally ONE pass over [0, EPB).  A
+    // sub-range whose due events overflow the shared-memory lists is halved
+    // and retried (bursts such as the 16 events/entity at t = 0).
     const uint32_t slot0 = b * EPB;
-    for (uint32_t i = tid; i < npg * PAGE; i += NTHREADS) {
-      uint32_t pg = i / PAGE, s = i % PAGE;
-      if (s >= (uint32_t)(sh.pg_cnt[pg] & 0x7FFFu)) continue;
-      unsigned long long q0, q1;
-      ld_rec_head(c.pool + ((size_t)sh.pg_id[pg] * PAGE + s), q0, q1);
-      double t = __longlong_as_double((long long)q0);
-      if (t < W.hi) {
-        if (t >= W.gmin) {
-          uint32_t le = (uint32_t)q1 - slot0;
-          if (le < EPB) atomicAdd(&sh.cnt[le], 1u);
+    const double qscale = 4294967295.0 / (W.hi - W.gmin);
+    if (tid == 0) {
+      sh.rstack[0] = 0;
+      sh.rstack[1] = EPB;
+      sh.stack_n = 1;
+    }
+    bool first = true;
+#pragma unroll 1
+    for (;;) {
+      __syncthreads();
+      if (sh.stack_n == 0) break;
+      __syncthreads();
+      if (tid == 0) {
+        sh.stack_n--;
+        sh.pass_lo = sh.rstack[2 * sh.stack_n];
+        sh.pass_hi = sh.rstack[2 * sh.stack_n + 1];
+        sh.total = 0;
+      }
+      for (int i = tid; i < EPB; i += NTHREADS) sh.head[i] = LIST_END;
+      __syncthreads();
+      const uint32_t e_lo = sh.pass_lo, e_hi = sh.pass_hi;
+      collect_due(c, sh, ta, slot0, npg, e_lo, e_hi, first, qscale);
+      first = false;
+      __syncthreads();
+      PHASE(2);
+      const uint32_t m = sh.total;
+      if (m > NREFS) { // overflow: halve the entity range and retry
+        if (e_hi - e_lo <= 1 || sh.stack_n >= 30) {
+          if (tid == 0) set_error(c, SIMIAN_ERR_ENTITY_BURST);
+          break;
+        }
+        __syncthreads();
+        if (tid == 0) {
+          uint32_t mid = (e_lo + e_hi) >> 1;
+          sh.rstack[2 * sh.stack_n] = mid;
+          sh.rstack[2 * sh.stack_n + 1] = e_hi;
+          sh.rstack[2 * sh.stack_n + 2] = e_lo;
+          sh.rstack[2 * sh.stack_n + 3] = mid;
+          sh.stack_n += 2;
+        }
+        continue;
+      }
+      if (m == 0) continue;
+      if (c.all_pure) {
+        // K3 + K4, one thread per EVENT: rank, tie check, handler, emit
+        for (uint32_t i = tid; i < m; i += NTHREADS) rank_and_emit(c, sh, ta, slot0, i);
+        __syncthreads();
+        PHASE(5);
+        // per entity: fold the trace hash chain, publish the commit count
+        for (uint32_t le = e_lo + tid; le < e_hi; le += NTHREADS) {
+          uint32_t f = sh.head[le];
+          if (f != LIST_END) chain_entity(c, sh, slot0 + le, f);
         }
       } else {
-        unsigned long long tk = simian_time_key(t);
-        ta.min_key = tk < ta.min_key ? tk : ta.min_key;
+        // K3 + K4: stateful handlers, one thread per entity
+        for (uint32_t le = e_lo + tid; le < e_hi; le += NTHREADS) {
+          uint32_t f = sh.head[le];
+          if (f != LIST_END) process_entity(c, sh, ta, slot0 + le, f);
+        }
       }
+      PHASE(6);
     }
     __syncthreads();
-    uint32_t total = block_scan_counts(sh);
-    // ---- passes over entity sub-ranges whose due events fit in sh.refs
-    uint32_t e_lo = 0;
-#pragma unroll 1
-    while (e_lo < EPB && total) {
-      if (tid == 0) {
-        uint32_t base = sh.off[e_lo];
-        uint32_t lo = e_lo, hi = EPB; // largest e_hi with off[e_hi]-base <= NREFS
-        while (lo < hi) {
-          uint32_t mid = (lo + hi + 1) >> 1;
-          if (sh.off[mid] - base <= NREFS) lo = mid; else hi = mid - 1;
-        }
-        sh.pass_hi = lo;
-      }
-      __syncthreads();
-      uint32_t e_hi = sh.pass_hi;
-      if (e_hi == e_lo) { // a single entity with more than NREFS due events
-        if (tid == 0) set_error(c, SIMIAN_ERR_ENTITY_BURST);
-        break;
-      }
-      uint32_t base = sh.off[e_lo];
-      if (sh.off[e_hi] != base) {
-        // K2c: group references by entity (second read hits L2)
-        for (uint32_t i = tid; i < npg * PAGE; i += NTHREADS) {
-          uint32_t pg = i / PAGE, s = i % PAGE;
-          if (s >= (uint32_t)(sh.pg_cnt[pg] & 0x7FFFu)) continue;
-          uint32_t ref = sh.pg_id[pg] * PAGE + s;
-          unsigned long long q0, q1;
-          ld_rec_head(c.pool + ref, q0, q1);
-          double t = __longlong_as_double((long long)q0);
-          if (t < W.hi && t >= W.gmin) {
-            uint32_t le = (uint32_t)q1 - slot0;
-            if (le >= e_lo && le < e_hi) {
-              uint32_t r = atomicSub(&sh.cnt[le], 1u) - 1u;
-              sh.refs[sh.off[le] - base + r] = ref;
-            }
-          }
-        }
-        __syncthreads();
-        if (c.all_pure) {
-          // K3a: per entity, order + commit bookkeeping
-          for (uint32_t le = e_lo + tid; le < e_hi; le += NTHREADS) {
-            uint32_t n = sh.off[le + 1] - sh.off[le];
-            if (n) order_entity(c, sh, ta, slot0 + le, le, sh.off[le] - base, n);
-          }
-          __syncthreads();
-          // K3b + K4: per EVENT, handler + emit
-          uint32_t m = sh.off[e_hi] - base;
-          for (uint32_t i = tid; i < m; i += NTHREADS) emit_event(c, sh, ta, slot0, base, i);
-        } else {
-          // K3 + K4: stateful handlers, one thread per entity
-          for (uint32_t le = e_lo + tid; le < e_hi; le += NTHREADS) {
-            uint32_t n = sh.off[le + 1] - sh.off[le];
-            if (n) process_entity(c, sh, ta, slot0 + le, &sh.refs[sh.off[le] - base], n);
-          }
-        }
-        __syncthreads();
-      }
-      e_lo = e_hi;
-    }
     // ---- recycle rows [tb_clean, tb_hi): pages back to the ring, heads cleared
     {
       // rows listed above (flagged pages)
@@ -1082,6 +1128,7 @@ __global__ void __launch_bounds__(NTHREADS)
     }
   }
 
+  PHASE(7);
   // ---- K1: CTA reduction of the accumulators, one atomic each per CTA
   for (int o = 16; o; o >>= 1) {
     unsigned long long x = __shfl_xor_sync(0xffffffffu, ta.min_key, o);
@@ -1114,6 +1161,7 @@ __global__ void __launch_bounds__(NTHREADS)
     if (sh.ties) atomicAdd(&a->ties, (unsigned long long)sh.ties);
     if (sh.dties) atomicAdd(&a->dist_ties, (unsigned long long)sh.dties);
   }
+  PHASE(8);
   if (!fuse_advance) return;
   // ---- last CTA computes the next window (simian.js:147)
   __threadfence();
@@ -1133,6 +1181,7 @@ __global__ void __launch_bounds__(NTHREADS)
                                          : simian_key_time(far);
     setup_next_window(c, W, Wn, gmin, farT, false);
   }
+  PHASE(9);
 }
 
 // size > 1: local minLeft candidate after the exchange (simian.js:143)

@@ -1,0 +1,31 @@
+#!/usr/bin/env python
+"""Per-phase SM-cycle breakdown of k_window on BASELINE config 2.
+Needs a library built with -DSIMIAN_PROFILE_PHASES, e.g.
+  make -C simian_b200/csrc variant NAME=prof DEFS="-DSIMIAN_PROFILE_PHASES"
+  SIMIAN_B200_LIB=$PWD/simian_b200/libsimian_b200_prof.so python tools/phase_profile.py
+"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from simian_b200 import capi  # noqa: E402
+from simian_b200.workloads import CONFIGS, build_phold  # noqa: E402
+
+c = dict(CONFIGS[sys.argv[1] if len(sys.argv) > 1 else "config2_phold_1m"])
+for rep in range(2):
+    e = capi.Engine("p", 0.0, c["end"], c["min_delay"], seed=1)
+    build_phold(e, c["n"], c["per_entity"], c["lookahead"], c["p_remote"], 1.0,
+                c["mode"], c["groups"])
+    st = e.run()
+    ph = e.debug_phase_cycles()
+    e.close()
+tot = sum(ph) or 1
+names = ["0 init/W", "1 list pages", "2 hist scan", "3 prefix", "4 select+fill",
+         "5 rank+emit", "6 chain", "7 recycle", "8 reduce/flush",
+         "9 advance(last CTA)"]
+print("events %d dev %.2f ms  ev/s %.3e  launches %d" % (
+    st["total_events"], st["device_seconds"] * 1e3,
+    st["total_events"] / st["device_seconds"], st["kernel_launches"]))
+for n, v in zip(names, ph):
+    print("%-22s %6.2f%%  %12d cycles" % (n, 100.0 * v / tot, v))
+print("total cycles %d over %d windows" % (tot, st["windows"]))
