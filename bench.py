@@ -213,7 +213,9 @@ def main():
             e.close()
             return st
         from simian_b200.distributed import run_distributed_phold
-        return run_distributed_phold(cfg, rank, world, local_rank)
+        st = run_distributed_phold(cfg, rank, world, local_rank)
+        st.pop("_engine").close()
+        return st
 
     for _ in range(args.warmup):
         one_step_resident()

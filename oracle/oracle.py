@@ -81,6 +81,15 @@ def lib():
             "oracle_read_counts": (i, [vp, cp, vp]),
             "oracle_read_trace_hashes": (i, [vp, cp, vp]),
             "oracle_read_state": (i, [vp, cp, vp]),
+            "oracle_step_begin": (None, [vp]),
+            "oracle_step_process": (i, [vp, i, d]),
+            "oracle_step_outbox": (u64, [vp, i, i, vp, u64]),
+            "oracle_step_ingest": (None, [vp, i, vp, u64]),
+            "oracle_step_min_left": (d, [vp, i]),
+            "oracle_step_end": (i, [vp, i, C.POINTER(OracleStats)]),
+            "oracle_start_time": (d, [vp]),
+            "oracle_end_time": (d, [vp]),
+            "oracle_owner_rank": (i, [vp, u32]),
             "oracle_q_new": (vp, [i]),
             "oracle_q_free": (None, [vp]),
             "oracle_q_push": (None, [vp, d, u64]),
@@ -185,3 +194,58 @@ class Oracle:
 
     def read_trace_hashes(self, name, n):
         return self._read(self.L.oracle_read_trace_hashes, name, n)
+
+
+class OracleRankEngine:
+    """One rank of an oracle world behind the RankEngine protocol of
+    simian_b200/distributed.py (CPU tensors).  Lets the gloo tests drive the
+    product's window/exchange loop without a GPU."""
+
+    def __init__(self, oracle, rank, size):
+        import torch
+        self.torch = torch
+        self.o, self.rank, self.size = oracle, rank, size
+        self.L = oracle.L
+        self.gmin = self.L.oracle_start_time(oracle.h)
+        self.end_time = self.L.oracle_end_time(oracle.h)
+        self.minvec = torch.zeros(2, dtype=torch.float64)
+
+    def begin(self):
+        self.L.oracle_step_begin(self.o.h)
+
+    def process(self):
+        rc = self.L.oracle_step_process(self.o.h, self.rank, self.gmin)
+        self.o._ck(rc)
+
+    def outbox(self):
+        counts, bufs = [], []
+        for peer in range(self.size):
+            n = self.L.oracle_step_outbox(self.o.h, self.rank, peer, None, 0)
+            arr = np.zeros(max(n, 1), dtype=EVENT_DTYPE)
+            got = self.L.oracle_step_outbox(self.o.h, self.rank, peer,
+                                            arr.ctypes.data, n) if n else 0
+            counts.append(int(got))
+            bufs.append(self.torch.from_numpy(arr.view(np.int64).reshape(-1, 4))[:got])
+        return counts, bufs
+
+    def new_inbox(self, n):
+        return self.torch.zeros((max(n, 1), 4), dtype=self.torch.int64)
+
+    def ingest(self, inbox, n):
+        if n:
+            arr = np.ascontiguousarray(inbox[:n].numpy())
+            self.L.oracle_step_ingest(self.o.h, self.rank, arr.ctypes.data, n)
+
+    def local_min(self):
+        self.minvec[0] = self.L.oracle_step_min_left(self.o.h, self.rank)
+        self.minvec[1] = float("inf")
+        return self.minvec
+
+    def advance(self):
+        self.gmin = float(self.minvec[0])  # allreduced by the driver
+        return not (self.gmin <= self.end_time)  # simian.js:119
+
+    def end(self):
+        st = OracleStats()
+        self.o._ck(self.L.oracle_step_end(self.o.h, self.rank, C.byref(st)))
+        return st.as_dict()

@@ -607,6 +607,92 @@ int oracle_read_state(void *o, const char *className, void *out) {
   return 0;
 }
 
+/* ---- one rank at a time, collectives done by the caller -------------------
+ * The same window loop as oracle_run (simian.js:118-149), cut at the places
+ * where the reference crosses into MPI (simian.js:137,140,144), so that the
+ * test suite can run `size` processes over gloo, each stepping ITS rank of an
+ * identically constructed world, and exercise the product's host-side window
+ * driver (simian_b200/distributed.py) without a GPU.                          */
+void oracle_step_begin(void *o) {
+  World *w = (World *)o;
+  w->running = true; /* simian.js:117 */
+}
+
+/* simian.js:120-134 for one rank */
+int oracle_step_process(void *o, int rank, double globalMinLeft) {
+  World *w = (World *)o;
+  Rank &r = w->ranks[rank];
+  double epoch = globalMinLeft + w->minDelay; /* :120 */
+  w->windows++; /* each process steps exactly one rank of its world */
+  while (r.q.length() && (r.q.peek() < epoch) && !w->error) { /* :122 */
+    simian_event_t cur = r.q.pop();
+    if (r.now > cur.time) {
+      w->fail(ORACLE_ERR_OUT_OF_ORDER, "Out of order event");
+      break;
+    }
+    r.now = cur.time;
+    dispatch(w, &r, cur);
+    if (w->error) break;
+    r.numEvents++;
+  }
+  return w->error;
+}
+
+/* sndCounts[peer] and the staged events (mpi.cpp:439-476); clears them */
+uint64_t oracle_step_outbox(void *o, int rank, int peer, simian_event_t *out,
+                            uint64_t cap) {
+  World *w = (World *)o;
+  std::vector<simian_event_t> &box = w->ranks[rank].outbox[peer];
+  uint64_t n = box.size();
+  if (out) {
+    if (n > cap) n = cap;
+    if (n) memcpy(out, box.data(), n * sizeof(simian_event_t));
+    box.clear();
+    w->ranks[rank].sndCounts[peer] = 0;
+  }
+  return n;
+}
+
+/* probe/recv/push (simian.js:138-142) */
+void oracle_step_ingest(void *o, int rank, const simian_event_t *ev, uint64_t n) {
+  World *w = (World *)o;
+  for (uint64_t i = 0; i < n; i++) w->ranks[rank].q.push(ev[i]);
+}
+
+/* minLeft (simian.js:143) */
+double oracle_step_min_left(void *o, int rank) {
+  World *w = (World *)o;
+  Rank &r = w->ranks[rank];
+  r.synchEvents += 2; /* :145 */
+  return r.q.length() ? r.q.peek() : w->infTime;
+}
+
+/* per-rank results after the loop */
+int oracle_step_end(void *o, int rank, oracle_stats *out) {
+  World *w = (World *)o;
+  w->running = false;
+  memset(out, 0, sizeof(*out));
+  Rank &r = w->ranks[rank];
+  out->total_events = r.numEvents;
+  out->synch_events = r.synchEvents;
+  out->windows = w->windows;
+  uint64_t dg = 0;
+  for (uint32_t g = 0; g < w->n_ids; g++)
+    if (w->offset_rank(g) == rank) dg += simian_digest_term(g, w->count[g], w->hash[g]);
+  out->digest = dg;
+  out->ties = w->ties;
+  out->distinguishable_ties = w->dist_ties;
+  out->emitted = w->emitted;
+  out->dropped_past_end = w->dropped;
+  out->last_time = r.now;
+  out->error = w->error;
+  return w->error;
+}
+
+double oracle_start_time(void *o) { return ((World *)o)->startTime; }
+double oracle_end_time(void *o) { return ((World *)o)->endTime; }
+int oracle_owner_rank(void *o, uint32_t gid) { return ((World *)o)->offset_rank(gid); }
+
 /* ---- bare eventQ access, for pinning the heap against the reference's
  * fixtures (SimianLua/eventQ.lua:62, SimianJS/Tests/test.Q.js:14-21) ------- */
 void *oracle_q_new(int tie_mode) {

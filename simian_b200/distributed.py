@@ -1,0 +1,158 @@
+"""Host-side window driver for size > 1: one process per GPU, the collectives
+of the reference's MPI loop done with torch.distributed (NCCL over NVLink on
+GPUs, gloo in the CPU tests).
+
+Reference protocol replaced (SimianJS/simian.js:136-145, MasalaChai/mpi.cpp):
+  alltoallSum()  MPI_Alltoall of per-peer send counts  mpi.cpp:418-437
+      -> all_gather of the `size` outbox counters
+  sendAndCount / probe / recv  one blocking MPI_Send of a msgpack blob per
+  remote event + MPI_Probe/MPI_Recv per event           mpi.cpp:439-476,318-362
+      -> ONE alltoallv of fixed 32-byte POD records per window
+  allreduce(minLeft, MIN)  MPI_Allreduce on one double   mpi.cpp:364-390
+      -> all_reduce(MIN) of {minLeft, min far-future time} straight from the
+         engine's device buffer
+The engine side of each step is a C-ABI call (simian_window_*), see
+include/simian_b200.h.  Nothing here touches event payloads on the host.
+
+RankEngine protocol (what drive_windows needs from a rank):
+  begin(); process(); outbox() -> (counts, [per-peer tensor views (n,4) int64]);
+  new_inbox(n) -> tensor; ingest(inbox, n); local_min() -> float64[2] tensor;
+  advance() -> done; end() -> stats dict
+"""
+import torch
+import torch.distributed as dist
+
+
+class _DevBuf:
+    """zero-copy torch view of engine-owned device memory"""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {
+            "shape": (nbytes,), "typestr": "|u1", "data": (ptr, False),
+            "version": 2}
+
+
+def _device_view(ptr, nbytes, dtype, device):
+    t = torch.as_tensor(_DevBuf(ptr, nbytes), device=device)
+    return t.view(dtype)
+
+
+class GpuRankEngine:
+    """simian_b200.capi.Engine (one GPU = one rank) behind the RankEngine
+    protocol; every method is one C-ABI call plus zero-copy tensor views."""
+
+    def __init__(self, engine, device):
+        self.e, self.device = engine, torch.device(device)
+        self.size = engine.size
+        self._outbox = None
+        self._minvec = None
+        # engine kernels and NCCL collectives are ordered on torch's stream
+        engine.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def begin(self):
+        self.e.run_begin()
+
+    def process(self):
+        self.e.window_process()
+
+    def outbox(self):
+        counts, ptr, cap = self.e.window_outbox()  # D2H of `size` counters
+        if self._outbox is None:
+            self._outbox = _device_view(ptr, self.size * cap * 32, torch.int64,
+                                        self.device).view(self.size, cap, 4)
+        return counts, [self._outbox[p, :counts[p]] for p in range(self.size)]
+
+    def new_inbox(self, n):
+        if getattr(self, "_inbox", None) is None or self._inbox.shape[0] < n:
+            self._inbox = torch.empty((max(n, 1024) * 5 // 4, 4), dtype=torch.int64,
+                                      device=self.device)
+        return self._inbox
+
+    def ingest(self, inbox, n):
+        if n:
+            self.e.window_ingest(inbox.data_ptr(), n)
+
+    def local_min(self):
+        ptr = self.e.window_local_min()
+        if self._minvec is None:
+            self._minvec = _device_view(ptr, 16, torch.float64, self.device)
+        return self._minvec
+
+    def advance(self):
+        return self.e.window_advance()
+
+    def end(self):
+        return self.e.run_end()
+
+
+def _exchange(rank, size, sends, recv_counts, inbox, group=None):
+    """alltoallv of (n,4) int64 record tensors; returns #records received."""
+    offs, total = [], 0
+    for p in range(size):
+        offs.append(total)
+        total += recv_counts[p]
+    if dist.get_backend(group) == "nccl":
+        outs = [inbox[offs[p]:offs[p] + recv_counts[p]] for p in range(size)]
+        dist.all_to_all(outs, [s.contiguous() for s in sends], group=group)
+    else:  # gloo has no all_to_all: point-to-point pairs
+        ops = []
+        for p in range(size):
+            if p == rank:
+                continue
+            if sends[p].shape[0]:
+                ops.append(dist.P2POp(dist.isend, sends[p].contiguous(), p, group))
+            if recv_counts[p]:
+                ops.append(dist.P2POp(dist.irecv, inbox[offs[p]:offs[p] + recv_counts[p]],
+                                      p, group))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+    return total
+
+
+def drive_windows(eng, rank, size, group=None, max_windows=None):
+    """Simian.run for size > 1 (simian.js:118-149): window loop with the
+    per-window exchange and min-allreduce.  Returns the rank's stats dict with
+    the window count."""
+    eng.begin()
+    windows = 0
+    while True:
+        eng.process()                                   # simian.js:122-134
+        counts, sends = eng.outbox()
+        counts[rank] = 0
+        dev = sends[0].device
+        mine = torch.tensor(counts, dtype=torch.int64, device=dev)
+        table = [torch.empty_like(mine) for _ in range(size)]
+        dist.all_gather(table, mine, group=group)       # alltoallSum, :137
+        recv_counts = [int(x) for x in torch.stack(table)[:, rank].tolist()]
+        recv_counts[rank] = 0
+        n_in = sum(recv_counts)
+        inbox = eng.new_inbox(n_in)
+        _exchange(rank, size, sends, recv_counts, inbox, group)   # :138-142
+        eng.ingest(inbox, n_in)
+        mv = eng.local_min()                            # :143
+        dist.all_reduce(mv, op=dist.ReduceOp.MIN, group=group)    # :144
+        windows += 1
+        if eng.advance():                               # :119
+            break
+        if max_windows and windows >= max_windows:
+            break
+    st = eng.end()
+    st["driver_windows"] = windows
+    return st
+
+
+def run_distributed_phold(cfg, rank, world, local_rank, seed=1, **options):
+    """One PHOLD step on `world` GPUs (one process each); returns this rank's
+    stats.  cfg: a dict of simian_b200.workloads.CONFIGS shape."""
+    from . import capi
+    from .workloads import build_phold
+    device = torch.device("cuda", local_rank)
+    e = capi.Engine("phold", 0.0, cfg["end"], cfg["min_delay"], rank=rank,
+                    size=world, device=local_rank, seed=seed, **options)
+    build_phold(e, cfg["n"], cfg["per_entity"], cfg["lookahead"], cfg["p_remote"],
+                cfg.get("lam", 1.0), cfg["mode"], cfg["groups"])
+    eng = GpuRankEngine(e, device)
+    st = drive_windows(eng, rank, world)
+    st["_engine"] = e
+    return st
