@@ -475,7 +475,13 @@ struct DevCtx {
       ta.min_key = tk < ta.min_key ? tk : ta.min_key;
       append_local(c, sh.ax, W.tb_clean, W.far_row, W.alloc_limit, r);
     } else { // entity.js:66: staged for the per-window exchange
-      uint32_t i = atomicAdd(&c.outbox_count[rank], 1u);
+      // warp-aggregated claim: one atomic per (warp, destination rank)
+      unsigned act = __activemask();
+      unsigned peers = __match_any_sync(act, rank);
+      int leader = __ffs(peers) - 1, ln = threadIdx.x & 31;
+      uint32_t i = 0;
+      if (ln == leader) i = atomicAdd(&c.outbox_count[rank], (uint32_t)__popc(peers));
+      i = __shfl_sync(peers, i, leader) + __popc(peers & ((1u << ln) - 1u));
       if (i >= c.outbox_cap) {
         set_error(c, SIMIAN_ERR_OUTBOX_FULL);
         return;
