@@ -87,7 +87,7 @@ const char *simian_last_error(simian_engine *e);
  *   "seed"            engine seed of the shared counter-based RNG (default 1)
  *   "bucket_width"    calendar sub-bucket width in simulated time (default minDelay/8)
  *   "ring_buckets"    calendar ring length, power of two (default 2048)
- *   "pool_events"     event pool capacity in records (default 4x initial + slack)
+ *   "pool_events"     event pool capacity in records (default 2x initial + one page per calendar cell)
  *   "outbox_events"   per-peer cross-GPU staging capacity in records
  *   "launch_batch"    window kernels enqueued between host polls
  *   "tie_check"       1: count same-entity time ties (default 1)

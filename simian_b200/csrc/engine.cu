@@ -207,9 +207,12 @@ int setup(simian_engine *e) {
   c.ring = ring;
   c.ring_mask = ring - 1;
   uint64_t local_initial = e->initial_events / g + 1;
+  // default pool: twice the initial events + one (partial) page for every cell
+  // of the ring, the upper bound on simultaneously open pages
   uint64_t pool_events = e->pool_events
                              ? e->pool_events
-                             : 3 * local_initial + (uint64_t)PAGE * (256ull * c.n_blocks + 1024ull);
+                             : 2 * local_initial +
+                                   (uint64_t)PAGE * ((uint64_t)(ring + 2) * c.n_blocks + 1024ull);
   uint64_t n_pages = (pool_events + PAGE - 1) / PAGE;
   if (n_pages > 0xFFFFFFFFull / PAGE) n_pages = 0xFFFFFFFFull / PAGE;
   c.n_pages = (uint32_t)n_pages;
