@@ -144,6 +144,14 @@ int simian_sched_service_bulk(simian_engine *e, double time,
 int simian_sched_events(simian_engine *e, const simian_event_t *hostEvents,
                         uint64_t n);
 
+/* `new entityClass(name, out, engine, num)` bodies (simian.js:227): entity
+ * constructors may run handler code and call reqService before run()
+ * (pdes_lanl_benchmarkV8.js:255-256).  Runs the named device function once per
+ * local instance at now = startTime; it is not an event.  expectedEvents: how
+ * many events the constructors will send in total (pool sizing hint).       */
+int simian_construct_entities(simian_engine *e, const char *className,
+                              const char *deviceFnName, uint64_t expectedEvents);
+
 /* Simian.run()                                               simian.js:99-168
  * size == 1: the whole window loop runs here.  size > 1: use the stepping
  * calls below (the host runs the collectives, mpi.cpp:364-476).             */

@@ -33,6 +33,7 @@ enum simian_builtin_fn {
   SIMIAN_FN_LANL_RECEIVE = 3,   /* "lanl_receive"   */
   SIMIAN_FN_LANL_FINISH = 4,    /* "lanl_finish"    */
   SIMIAN_FN_COUNT_ONLY = 5,     /* "noop"           */
+  SIMIAN_FN_LANL_CONSTRUCT = 6, /* "lanl_construct": entity constructor, not a service */
   SIMIAN_FN__END
 };
 
@@ -98,5 +99,175 @@ SIMIAN_HD void simian_phold_generate(Ctx &ctx) {
 /* "noop": commit only (counts + trace hash), emits nothing. */
 template <class Ctx>
 SIMIAN_HD void simian_noop(Ctx &) {}
+
+/* ------------------------------------------- LANL PDES benchmark (V8) ---- */
+/* SimianJS/Examples/pdes_lanl_benchmarkV8.js:99-343.  Followed: the documented
+ * intent (:16-85) and the handler bodies (:259-309) with the shared RNG in
+ * place of masala.random (each handler invocation draws draw(0), draw(1), ...
+ * of its own committed event; the reference re-seeds the global stream from
+ * the event payload at handler entry, :260,:291 -- same idea).  Deviations,
+ * all stated in DESIGN.md: p_send == 0 and p_list == 0 only (Math.pow is not
+ * portable; r_min is passed in as a parameter); the weighted sum `value` is
+ * stored in the entity state instead of being discarded (:308) so the compute
+ * loop is observable; the statistics fan-in to entity 0 (:311-342, an N-way
+ * distinguishable time tie) is done off-path by reading entity
+ * state, FinishHandler only commits.                                         */
+
+#define SIMIAN_LANL_TIME_BINS 16
+#define SIMIAN_CTOR_COMMIT 0xFFFFFFFFFFFFFFFFull /* commit index of a constructor call */
+
+typedef struct simian_lanl_params {
+  uint32_t first_id; /* global id of PDES_LANL_Node(0) */
+  uint32_t n_ent;    /* :99  */
+  double s_ent, q_avg, p_receive;       /* :100-102 */
+  double m_ent, ops_ent, ops_sigma;     /* :106,108,109 */
+  double cache_friendliness;            /* :110 */
+  double end_time;  /* the MODEL's endTime (:115); engine end = max(end,2)+3*minDelay (:349) */
+  double min_delay; /* :116 */
+  double r_min;     /* pow(1-p_receive, n_ent)  (:196), computed by the host */
+  uint32_t time_bins; /* :112, <= SIMIAN_LANL_TIME_BINS */
+  uint16_t svc_send, svc_receive; /* interned ids of "SendHandler" / "ReceiveHandler" */
+  uint16_t svc_finish, pad0_;
+  uint32_t pad1_;
+} simian_lanl_params_t; /* 104 bytes */
+
+/* per-entity state (:202-252); the list of list_size doubles follows it */
+typedef struct simian_lanl_state {
+  double local_intersend_delay, q_target, last_scheduled; /* :215-217,228,230 */
+  double ops, ops_max, ops_min, ops_mean, value_sink;     /* :222,236-238,308 */
+  int64_t q_size;                                         /* :229 */
+  uint64_t send_count, receive_count, ops_count;          /* :233-235 */
+  uint32_t list_size, active_elements;                    /* :221,223 */
+  uint32_t time_sends[SIMIAN_LANL_TIME_BINS];             /* :239-240 */
+} simian_lanl_state_t; /* 168 bytes */
+
+SIMIAN_HD double simian_floor(double x) { /* Math.floor for |x| < 2^52 */
+  double t = (double)(long long)x;
+  return (t > x) ? t - 1.0 : t;
+}
+SIMIAN_HD double simian_ceil(double x) { return -simian_floor(-x); }
+
+#if defined(__CUDA_ARCH__)
+#define SIMIAN_SQRT(x) __dsqrt_rn(x)
+#else
+#define SIMIAN_SQRT(x) __builtin_sqrt(x)
+#endif
+
+/* SendHandler body (:259-288); also run by the constructor (:256) */
+template <class Ctx>
+SIMIAN_HD void simian_lanl_send_body(Ctx &ctx, uint32_t &di) {
+  const simian_lanl_params_t *p = (const simian_lanl_params_t *)ctx.params();
+  simian_lanl_state_t *st = (simian_lanl_state_t *)ctx.state();
+  const double now = ctx.now(), endTime = p->end_time;
+  st->send_count++;
+  st->q_size--;
+  uint32_t bin = (uint32_t)simian_floor(now / (endTime + 0.0001) * (double)p->time_bins); /* :263 */
+  if (bin < SIMIAN_LANL_TIME_BINS) st->time_sends[bin]++;
+  /* reschedule myself until the queue is full or time has run out (:267-274) */
+  while (((double)st->q_size < st->q_target) && !(st->last_scheduled > endTime)) {
+    double own_delay = simian_exponential(ctx.draw(di++), 1.0 / st->local_intersend_delay);
+    st->last_scheduled = st->last_scheduled + own_delay;
+    if (st->last_scheduled < endTime) {
+      st->q_size++;
+      ctx.req_service(st->last_scheduled - now, p->svc_send, ctx.draw(di++), SIMIAN_NULL_ENTITY);
+    }
+  }
+  /* computation request to the destination entity (:276-287) */
+  double dest;
+  if (p->p_receive == 1.0)
+    dest = 0;
+  else if (p->p_receive == 0)
+    dest = simian_floor((double)p->n_ent * simian_u01(ctx.draw(di++)));
+  else {
+    double U = (1.0 - p->r_min) * simian_u01(ctx.draw(di++)) + p->r_min;
+    if (!(U > 0.0)) U = 2.2250738585072014e-308;
+    dest = simian_floor(simian_ceil(simian_log(U) / simian_log(1.0 - p->p_receive))) - 1;
+    if (dest < 0) dest = 0;
+    if (dest > (double)(p->n_ent - 1)) dest = (double)(p->n_ent - 1);
+  }
+  uint64_t new_seed = ctx.draw(di++);
+  if (now + p->min_delay < endTime)
+    ctx.req_service(p->min_delay, p->svc_receive, new_seed, p->first_id + (uint32_t)dest);
+}
+
+template <class Ctx>
+SIMIAN_HD void simian_lanl_send(Ctx &ctx) {
+  uint32_t di = 0;
+  simian_lanl_send_body(ctx, di);
+}
+
+/* gauss(mu, sigma) (:180-193): Box-Muller polar method */
+template <class Ctx>
+SIMIAN_HD double simian_lanl_gauss(Ctx &ctx, uint32_t &di, double mu, double sigma) {
+  double x1, x2, w;
+  do {
+    x1 = 2.0 * simian_u01(ctx.draw(di++)) - 1.0;
+    x2 = 2.0 * simian_u01(ctx.draw(di++)) - 1.0;
+    w = (x1 * x1) + (x2 * x2);
+  } while (w >= 1.0 || w == 0.0);
+  w = SIMIAN_SQRT((-2.0 * simian_log(w)) / w);
+  return ((x1 * w) * sigma) + mu;
+}
+
+/* ReceiveHandler (:290-309): randomly weighted subset sum over the list */
+template <class Ctx>
+SIMIAN_HD void simian_lanl_receive(Ctx &ctx) {
+  const simian_lanl_params_t *p = (const simian_lanl_params_t *)ctx.params();
+  simian_lanl_state_t *st = (simian_lanl_state_t *)ctx.state();
+  const double *list = (const double *)(st + 1);
+  uint32_t di = 0;
+  double r_ops = simian_floor(simian_lanl_gauss(ctx, di, st->ops, st->ops * p->ops_sigma));
+  if (!(r_ops > 1.0)) r_ops = 1.0;                                       /* max(1, ..) */
+  double r_active = simian_floor((double)st->active_elements * (r_ops / st->ops));
+  if (r_active > (double)st->list_size) r_active = (double)st->list_size; /* :295 */
+  if (!(r_active > 1.0)) r_active = 1.0;                                  /* :296 */
+  double r_ops_per_element = simian_floor(r_ops / r_active);              /* :297 */
+  st->receive_count++;
+  if (r_ops > st->ops_max) st->ops_max = r_ops;
+  if (r_ops < st->ops_min) st->ops_min = r_ops;
+  st->ops_mean = (st->ops_mean * (double)(st->receive_count - 1) + r_ops) / (double)st->receive_count;
+  uint32_t na = (uint32_t)r_active, nj = (uint32_t)r_ops_per_element;
+  double value = 0;
+  for (uint32_t i = 0; i < na; i++) { /* :304-307 */
+    double li = list[i];
+    for (uint32_t j = 0; j < nj; j++) value += li * simian_u01(ctx.draw(di++));
+    st->ops_count += nj;
+  }
+  st->value_sink += value;
+}
+
+/* FinishHandler (:311-315): the stats fan-in is done off-path */
+template <class Ctx>
+SIMIAN_HD void simian_lanl_finish(Ctx &) {}
+
+/* constructor PDES_LANL_Node (:203-257), p_send == 0 and p_list == 0 */
+template <class Ctx>
+SIMIAN_HD void simian_lanl_construct(Ctx &ctx) {
+  const simian_lanl_params_t *p = (const simian_lanl_params_t *)ctx.params();
+  simian_lanl_state_t *st = (simian_lanl_state_t *)ctx.state();
+  double *list = (double *)(st + 1);
+  uint32_t di = 0;
+  double prob = 1.0 / (double)p->n_ent;                                    /* :208 */
+  double target_global_sends = (double)p->n_ent * p->s_ent;                /* :198 */
+  double target_sends = simian_floor(prob * target_global_sends);          /* :213 */
+  st->local_intersend_delay =
+      (target_sends > 0) ? p->end_time / target_sends : 10 * p->end_time;  /* :214-216 */
+  st->list_size = (uint32_t)simian_floor(prob * (double)p->n_ent * p->m_ent);   /* :221 */
+  st->ops = simian_floor(prob * (double)p->n_ent * p->ops_ent);                 /* :222 */
+  st->active_elements = (uint32_t)simian_floor(p->cache_friendliness * (double)st->list_size);
+  for (uint32_t i = 0; i < st->list_size; i++) list[i] = simian_u01(ctx.draw(di++)); /* :226 */
+  st->q_target = (p->q_avg / p->s_ent) * target_sends;                     /* :228 */
+  st->q_size = 1;
+  st->last_scheduled = ctx.now();
+  st->send_count = st->receive_count = st->ops_count = 0;
+  st->ops_max = 0;
+  st->ops_min = 1e100;
+  st->ops_mean = 0.0;
+  st->value_sink = 0.0;
+  for (uint32_t i = 0; i < SIMIAN_LANL_TIME_BINS; i++) st->time_sends[i] = 0;
+  /* :255 FinishUp at end of time, :256 first SendHandler call */
+  ctx.req_service(p->end_time - ctx.now(), p->svc_finish, 0ull, SIMIAN_NULL_ENTITY);
+  simian_lanl_send_body(ctx, di);
+}
 
 #endif /* SIMIAN_MODELS_H */

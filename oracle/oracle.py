@@ -77,6 +77,7 @@ def lib():
             "oracle_sched_service": (i, [vp, d, cp, u64, cp, u32]),
             "oracle_sched_service_bulk": (i, [vp, d, cp, u64, cp, u32, u32, u32]),
             "oracle_sched_events": (i, [vp, vp, u64]),
+            "oracle_construct_entities": (i, [vp, cp, cp]),
             "oracle_run": (i, [vp, C.POINTER(OracleStats)]),
             "oracle_read_counts": (i, [vp, cp, vp]),
             "oracle_read_trace_hashes": (i, [vp, cp, vp]),
@@ -176,6 +177,14 @@ class Oracle:
     def sched_events(self, events):
         ev = np.ascontiguousarray(events, dtype=EVENT_DTYPE)
         self._ck(self.L.oracle_sched_events(self.h, ev.ctypes.data, len(ev)))
+
+    def construct_entities(self, cls, fn, expected_events=0):
+        self._ck(self.L.oracle_construct_entities(self.h, cls.encode(), fn.encode()))
+
+    def read_state(self, name, n, state_bytes):
+        out = np.zeros(n * state_bytes, dtype=np.uint8)
+        self._ck(self.L.oracle_read_state(self.h, name.encode(), out.ctypes.data))
+        return out
 
     def run(self, check=True):
         st = OracleStats()

@@ -95,6 +95,109 @@ def run_case(Simian, case):
     return out
 
 
+LANL_CASES = [
+    dict(name="lanl_uniform", n_ent=48, s_ent=20.0, q_avg=1.0, p_receive=0.0,
+         m_ent=40.0, ops_ent=60.0, ops_sigma=0.1, cache_friendliness=0.5,
+         end_time=20.0, min_delay=1.0, time_bins=10, seed=5),
+    dict(name="lanl_hot_spots_q3", n_ent=40, s_ent=15.0, q_avg=3.0,
+         p_receive=0.05, m_ent=64.0, ops_ent=100.0, ops_sigma=0.3,
+         cache_friendliness=0.25, end_time=12.0, min_delay=0.5, time_bins=8,
+         seed=9),
+]
+LANL_SERVICES = {"SendHandler": 0, "ReceiveHandler": 1, "FinishHandler": 2}
+
+
+def run_lanl_case(Simian, case):
+    """pdes_lanl_benchmarkV8.js "MAIN" (:346-356) on the unmodified SimianPie
+    engine; handlers = oracle/pyspec.py transcription of simian_models.h."""
+    n = case["n_ent"]
+    P = pyspec.LanlParams(n, case["s_ent"], case["q_avg"], case["p_receive"],
+                          case["m_ent"], case["ops_ent"], case["ops_sigma"],
+                          case["cache_friendliness"], case["end_time"],
+                          case["min_delay"], case["time_bins"])
+    eng = Simian("pin_" + case["name"], 0.0,
+                 max(case["end_time"], 2) + 3 * case["min_delay"],
+                 case["min_delay"], False, silent=True)
+    stats = {"ties": 0, "dist_ties": 0}
+
+    class Ctx:
+        def __init__(self, ent, commit_idx):
+            self.ent = ent
+            self.now = ent.engine.now
+            self.key = pyspec.rng_key(case["seed"], ent.num, commit_idx)
+
+        def draw(self, i):
+            return pyspec.rng_draw(self.key, i)
+
+        def req_service(self, offset, service, data, rx):
+            if rx is None:
+                self.ent.reqService(offset, service, data)
+            else:
+                self.ent.reqService(offset, service, data, "PDES_LANL_Node", rx)
+
+    class PDES_LANL_Node(eng.Entity):
+        def __init__(self, baseInfo, *args):
+            super(PDES_LANL_Node, self).__init__(baseInfo)
+            self.count = 0
+            self.hash = 0
+            self.last = None
+            pyspec.lanl_construct(P, self, Ctx(self, pyspec.CTOR_COMMIT))
+
+        def _commit(self, service, data, txId):
+            now = self.engine.now
+            src = pyspec.NULL_ENTITY if txId is None else txId
+            h = LANL_SERVICES[service]
+            cur = (now, h, src, data)
+            if self.last is not None and self.last[0] == now:
+                stats["ties"] += 1
+                if self.last != cur:
+                    stats["dist_ties"] += 1
+            self.last = cur
+            idx = self.count
+            self.hash = pyspec.trace_step(self.hash, now, h, src, data)
+            self.count = idx + 1
+            return Ctx(self, idx)
+
+        def SendHandler(self, data, tx, txId):
+            pyspec.lanl_send(P, self, self._commit("SendHandler", data, txId))
+
+        def ReceiveHandler(self, data, tx, txId):
+            pyspec.lanl_receive(P, self, self._commit("ReceiveHandler", data, txId))
+
+        def FinishHandler(self, data, tx, txId):
+            self._commit("FinishHandler", data, txId)
+
+    for i in range(n):
+        eng.addEntity("PDES_LANL_Node", PDES_LANL_Node, i)
+    eng.run()
+    ents = [eng.getEntity("PDES_LANL_Node", i) for i in range(n)]
+    counts = [e.count for e in ents]
+    hashes = [e.hash for e in ents]
+    digest = 0
+    for i in range(n):
+        digest = (digest + pyspec.digest_term(i, counts[i], hashes[i])) & pyspec.M64
+    out = dict(case)
+    out.update(
+        total_events=sum(counts), last_time_hex=float(eng.now).hex(),
+        digest="%016x" % digest, counts=counts,
+        hashes=["%016x" % h for h in hashes], ties=stats["ties"],
+        distinguishable_ties=stats["dist_ties"],
+        state=dict(
+            send_count=[e.send_count for e in ents],
+            receive_count=[e.receive_count for e in ents],
+            ops_count=[e.ops_count for e in ents],
+            q_size=[e.q_size for e in ents],
+            time_sends=[e.time_sends for e in ents],
+            last_scheduled=[float(e.last_scheduled).hex() for e in ents],
+            ops_max=[float(e.ops_max).hex() for e in ents],
+            ops_min=[float(e.ops_min).hex() for e in ents],
+            ops_mean=[float(e.ops_mean).hex() for e in ents],
+            value_sink=[float(e.value_sink).hex() for e in ents],
+            list_head=[[float(x).hex() for x in e.list[:4]] for e in ents]))
+    eng.exit()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reference", default="/root/reference")
@@ -120,6 +223,26 @@ def main():
                    "reference_engine": "SimianPie/simian.py (unmodified)",
                    "cases": res}, f, separators=(",", ":"))
     print("wrote", out_path, os.path.getsize(out_path), "bytes")
+    # LANL PDES benchmark: the t = minDelay requests of the constructors tie at
+    # hot destinations; SimianPie pops equal times FIFO (simian.py:286-287),
+    # which for these equals the engine's (time, handler, src, seq) order.
+    with tempfile.TemporaryDirectory() as tmp:
+        os.chdir(tmp)
+        try:
+            lres = [run_lanl_case(Simian, c) for c in LANL_CASES]
+        finally:
+            os.chdir(cwd)
+    for r in lres:
+        print(r["name"], "events", r["total_events"], "digest", r["digest"],
+              "ties", r["ties"], "distinguishable", r["distinguishable_ties"])
+    lpath = os.path.join(os.path.dirname(out_path), "lanl_simianpie.json")
+    with open(lpath, "w") as f:
+        json.dump({"generator": "oracle/pin_simianpie.py",
+                   "reference_engine": "SimianPie/simian.py (unmodified)",
+                   "tie_order": "FIFO (SimianPie); equals the engine order "
+                                "(oracle tie_mode=1) on these cases",
+                   "cases": lres}, f, separators=(",", ":"))
+    print("wrote", lpath, os.path.getsize(lpath), "bytes")
 
 
 if __name__ == "__main__":

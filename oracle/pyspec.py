@@ -119,3 +119,141 @@ def phold_generate(seed, me, commit_idx, n_entities, p_remote, lam, lookahead,
             target = row * g + (me % g + hop) % g
     offset = exponential(rng_draw(key, 2), lam) + lookahead
     return target, offset
+
+
+# ---- LANL PDES benchmark handlers: transcription of include/simian_models.h --
+# (simian_lanl_construct / _send / _receive / _finish).  `ctx` supplies
+#   now, draw(i) -> u64, req_service(offset, service_name, data, rx_num_or_None)
+# `st` is any object with the fields of simian_lanl_state_t plus `list`.
+
+CTOR_COMMIT = M64
+LANL_TIME_BINS = 16
+
+
+def sfloor(x):
+    """simian_floor: Math.floor for |x| < 2^52 via truncation"""
+    t = float(int(x))
+    return t - 1.0 if t > x else t
+
+
+def sceil(x):
+    return -sfloor(-x)
+
+
+class LanlParams:
+    def __init__(self, n_ent, s_ent, q_avg, p_receive, m_ent, ops_ent, ops_sigma,
+                 cache_friendliness, end_time, min_delay, time_bins):
+        import math
+        self.n_ent, self.s_ent, self.q_avg, self.p_receive = n_ent, s_ent, q_avg, p_receive
+        self.m_ent, self.ops_ent, self.ops_sigma = m_ent, ops_ent, ops_sigma
+        self.cache_friendliness, self.end_time, self.min_delay = cache_friendliness, end_time, min_delay
+        self.time_bins = time_bins
+        self.r_min = math.pow(1.0 - p_receive, n_ent)
+
+
+class _Di:
+    """the running draw index `di` of a handler invocation"""
+    def __init__(self):
+        self.i = 0
+
+    def next(self):
+        i = self.i
+        self.i += 1
+        return i
+
+
+def lanl_send_body(p, st, ctx, di):
+    now, end_time = ctx.now, p.end_time
+    st.send_count += 1
+    st.q_size -= 1
+    b = int(sfloor(now / (end_time + 0.0001) * float(p.time_bins)))
+    if 0 <= b < LANL_TIME_BINS:
+        st.time_sends[b] += 1
+    while (float(st.q_size) < st.q_target) and not (st.last_scheduled > end_time):
+        own_delay = exponential(ctx.draw(di.next()), 1.0 / st.local_intersend_delay)
+        st.last_scheduled = st.last_scheduled + own_delay
+        if st.last_scheduled < end_time:
+            st.q_size += 1
+            ctx.req_service(st.last_scheduled - now, "SendHandler", ctx.draw(di.next()), None)
+    if p.p_receive == 1.0:
+        dest = 0.0
+    elif p.p_receive == 0:
+        dest = sfloor(float(p.n_ent) * u01(ctx.draw(di.next())))
+    else:
+        U = (1.0 - p.r_min) * u01(ctx.draw(di.next())) + p.r_min
+        if not (U > 0.0):
+            U = 2.2250738585072014e-308
+        dest = sfloor(sceil(log(U) / log(1.0 - p.p_receive))) - 1
+        if dest < 0:
+            dest = 0.0
+        if dest > float(p.n_ent - 1):
+            dest = float(p.n_ent - 1)
+    new_seed = ctx.draw(di.next())
+    if now + p.min_delay < end_time:
+        ctx.req_service(p.min_delay, "ReceiveHandler", new_seed, int(dest))
+
+
+def lanl_send(p, st, ctx):
+    lanl_send_body(p, st, ctx, _Di())
+
+
+def lanl_gauss(ctx, di, mu, sigma):
+    import math
+    while True:
+        x1 = 2.0 * u01(ctx.draw(di.next())) - 1.0
+        x2 = 2.0 * u01(ctx.draw(di.next())) - 1.0
+        w = (x1 * x1) + (x2 * x2)
+        if not (w >= 1.0 or w == 0.0):
+            break
+    w = math.sqrt((-2.0 * log(w)) / w)
+    return ((x1 * w) * sigma) + mu
+
+
+def lanl_receive(p, st, ctx):
+    di = _Di()
+    r_ops = sfloor(lanl_gauss(ctx, di, st.ops, st.ops * p.ops_sigma))
+    if not (r_ops > 1.0):
+        r_ops = 1.0
+    r_active = sfloor(float(st.active_elements) * (r_ops / st.ops))
+    if r_active > float(st.list_size):
+        r_active = float(st.list_size)
+    if not (r_active > 1.0):
+        r_active = 1.0
+    r_ops_per_element = sfloor(r_ops / r_active)
+    st.receive_count += 1
+    if r_ops > st.ops_max:
+        st.ops_max = r_ops
+    if r_ops < st.ops_min:
+        st.ops_min = r_ops
+    st.ops_mean = (st.ops_mean * float(st.receive_count - 1) + r_ops) / float(st.receive_count)
+    na, nj = int(r_active), int(r_ops_per_element)
+    value = 0.0
+    for i in range(na):
+        li = st.list[i]
+        for _ in range(nj):
+            value += li * u01(ctx.draw(di.next()))
+        st.ops_count += nj
+    st.value_sink += value
+
+
+def lanl_construct(p, st, ctx):
+    di = _Di()
+    prob = 1.0 / float(p.n_ent)
+    target_global_sends = float(p.n_ent) * p.s_ent
+    target_sends = sfloor(prob * target_global_sends)
+    st.local_intersend_delay = (p.end_time / target_sends) if target_sends > 0 else 10 * p.end_time
+    st.list_size = int(sfloor(prob * float(p.n_ent) * p.m_ent))
+    st.ops = sfloor(prob * float(p.n_ent) * p.ops_ent)
+    st.active_elements = int(sfloor(p.cache_friendliness * float(st.list_size)))
+    st.list = [u01(ctx.draw(di.next())) for _ in range(st.list_size)]
+    st.q_target = (p.q_avg / p.s_ent) * target_sends
+    st.q_size = 1
+    st.last_scheduled = ctx.now
+    st.send_count = st.receive_count = st.ops_count = 0
+    st.ops_max = 0.0
+    st.ops_min = 1e100
+    st.ops_mean = 0.0
+    st.value_sink = 0.0
+    st.time_sends = [0] * LANL_TIME_BINS
+    ctx.req_service(p.end_time - ctx.now, "FinishHandler", 0, None)
+    lanl_send_body(p, st, ctx, di)

@@ -306,6 +306,15 @@ void dispatch(World *w, Rank *r, const simian_event_t &ev) {
     case SIMIAN_FN_COUNT_ONLY:
       simian_noop(ctx);
       break;
+    case SIMIAN_FN_LANL_SEND:
+      simian_lanl_send(ctx);
+      break;
+    case SIMIAN_FN_LANL_RECEIVE:
+      simian_lanl_receive(ctx);
+      break;
+    case SIMIAN_FN_LANL_FINISH:
+      simian_lanl_finish(ctx);
+      break;
     default:
       w->fail(ORACLE_ERR_UNKNOWN, "unknown builtin function");
   }
@@ -314,6 +323,10 @@ void dispatch(World *w, Rank *r, const simian_event_t &ev) {
 int fn_by_name(const char *n) {
   if (!strcmp(n, "phold_generate")) return SIMIAN_FN_PHOLD_GENERATE;
   if (!strcmp(n, "noop")) return SIMIAN_FN_COUNT_ONLY;
+  if (!strcmp(n, "lanl_send")) return SIMIAN_FN_LANL_SEND;
+  if (!strcmp(n, "lanl_receive")) return SIMIAN_FN_LANL_RECEIVE;
+  if (!strcmp(n, "lanl_finish")) return SIMIAN_FN_LANL_FINISH;
+  if (!strcmp(n, "lanl_construct")) return SIMIAN_FN_LANL_CONSTRUCT;
   return SIMIAN_FN_NONE;
 }
 
@@ -465,6 +478,37 @@ int oracle_sched_service(void *o, double time, const char *serviceName,
   /* every rank runs the same script; only the owner pushes (:177,188) */
   w->ranks[recvRank].q.push(e);
   return 0;
+}
+
+/* `new entityClass(...)` bodies (simian.js:227): entity constructors may run
+ * handler code and call reqService before run() (pdes_lanl_benchmarkV8.js:
+ * 255-256).  Runs the named constructor once per instance, in num order, on
+ * the owning rank, at now = startTime; it is not an event (no commit).       */
+int oracle_construct_entities(void *o, const char *className, const char *fnName) {
+  World *w = (World *)o;
+  if (!w->class_ix.count(className)) return ORACLE_ERR_UNKNOWN;
+  int fn = fn_by_name(fnName);
+  ClassInfo &c = w->classes[w->class_ix[className]];
+  for (uint32_t i = 0; i < c.count && !w->error; i++) {
+    uint32_t gid = c.first_id + i;
+    HostCtx ctx;
+    ctx.w = w;
+    ctx.r = &w->ranks[w->offset_rank(gid)];
+    ctx.ev = nullptr;
+    ctx.self = gid;
+    ctx.commit_idx = SIMIAN_CTOR_COMMIT;
+    ctx.key = simian_rng_key(w->seed, gid, SIMIAN_CTOR_COMMIT);
+    ctx.n_emit = 0;
+    ctx.cls = &c;
+    switch (fn) {
+      case SIMIAN_FN_LANL_CONSTRUCT:
+        simian_lanl_construct(ctx);
+        break;
+      default:
+        w->fail(ORACLE_ERR_UNKNOWN, "unknown constructor function");
+    }
+  }
+  return w->error;
 }
 
 /* the model-script loop `for i: for k<repeat: schedService(time,...,rx,i)` */

@@ -63,6 +63,7 @@ SIGNATURES = {
     "simian_sched_service": (_i, [_vp, _d, _cp, _u64, _cp, _u32]),
     "simian_sched_service_bulk": (_i, [_vp, _d, _cp, _u64, _cp, _u32, _u32, _u32]),
     "simian_sched_events": (_i, [_vp, _vp, _u64]),
+    "simian_construct_entities": (_i, [_vp, _cp, _cp, _u64]),
     "simian_run": (_i, [_vp, C.POINTER(Stats)]),
     "simian_run_begin": (_i, [_vp]),
     "simian_window_process": (_i, [_vp]),
@@ -180,6 +181,10 @@ class Engine:
     def sched_events(self, events):
         ev = np.ascontiguousarray(events, dtype=EVENT_DTYPE)
         self._ck(self.L.simian_sched_events(self.h, ev.ctypes.data, len(ev)))
+
+    def construct_entities(self, cls, fn, expected_events=0):
+        self._ck(self.L.simian_construct_entities(self.h, cls.encode(), fn.encode(),
+                                                  int(expected_events)))
 
     def run(self, check=True):
         st = Stats()

@@ -37,7 +37,7 @@ struct HostClass {
 };
 
 struct SchedOp { // a recorded schedService call, replayed on the device at run
-  int kind = 0;  // 0 bulk, 1 host records
+  int kind = 0;  // 0 bulk, 1 host records, 2 entity constructors
   double time = 0;
   uint32_t handler = 0;
   uint64_t data = 0;
@@ -50,6 +50,10 @@ struct SchedOp { // a recorded schedService call, replayed on the device at run
 int builtin_fn_by_name(const char *n) {
   if (!strcmp(n, "phold_generate")) return SIMIAN_FN_PHOLD_GENERATE;
   if (!strcmp(n, "noop")) return SIMIAN_FN_COUNT_ONLY;
+  if (!strcmp(n, "lanl_send")) return SIMIAN_FN_LANL_SEND;
+  if (!strcmp(n, "lanl_receive")) return SIMIAN_FN_LANL_RECEIVE;
+  if (!strcmp(n, "lanl_finish")) return SIMIAN_FN_LANL_FINISH;
+  if (!strcmp(n, "lanl_construct")) return SIMIAN_FN_LANL_CONSTRUCT;
   return SIMIAN_FN_NONE;
 }
 
@@ -251,6 +255,12 @@ int setup(simian_engine *e) {
       if (grid < 1) grid = 1;
       k_sched_bulk<<<grid, 256, 0, e->stream>>>(c, op.time, op.handler, op.data, op.cls, op.first,
                                                 op.count, op.repeat, op.seq_base);
+      CK(cudaGetLastError());
+    } else if (op.kind == 2) {
+      uint32_t nl = e->classes[op.cls].n_local;
+      int grid = (int)((nl + 127) / 128 < 2368 ? (nl + 127) / 128 : 2368);
+      if (grid < 1) grid = 1;
+      k_construct<<<grid, 128, 0, e->stream>>>(c, op.cls, op.handler);
       CK(cudaGetLastError());
     } else if (op.n_recs) {
       uint64_t n = op.n_recs;
@@ -534,6 +544,23 @@ int simian_sched_events(simian_engine *e, const simian_event_t *ev, uint64_t n) 
   CK(cudaStreamSynchronize(e->stream)); // the host buffer is only borrowed
   e->ops.push_back(op);
   e->initial_events += n;
+  return 0;
+}
+
+int simian_construct_entities(simian_engine *e, const char *className, const char *deviceFnName,
+                              uint64_t expectedEvents) {
+  if (e->set_up) return e->fail(SIMIAN_ERR_RUNNING, status_text(SIMIAN_ERR_RUNNING));
+  auto it = e->class_ix.find(className);
+  if (it == e->class_ix.end()) return e->fail(SIMIAN_ERR_UNKNOWN_NAME, "unknown entity class");
+  int fn = builtin_fn_by_name(deviceFnName);
+  if (!fn)
+    return e->fail(SIMIAN_ERR_UNKNOWN_NAME, std::string("no device function named ") + deviceFnName);
+  SchedOp op;
+  op.kind = 2;
+  op.cls = it->second;
+  op.handler = (uint32_t)fn;
+  e->ops.push_back(op);
+  e->initial_events += expectedEvents;
   return 0;
 }
 

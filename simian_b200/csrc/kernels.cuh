@@ -364,6 +364,7 @@ __global__ void k_ingest(const __grid_constant__ DevCfg c, const simian_event_t 
 }
 
 // ---------------------------------------------------------- window kernel --
+// (k_construct, which needs the handler context, is defined after it below)
 
 #define LIST_END 0xFFFFu
 
@@ -397,7 +398,8 @@ struct ThreadAcc {
 template <bool SEQ>
 struct DevCtx {
   const DevCfg &c;
-  WindowShared &sh;
+  const WinState &W; // window bound / recycle frontier / far row in force
+  AppendCtx &ax;
   ThreadAcc &ta;
   const DevClass *cl;
   uint32_t self_gid, self_slot;
@@ -411,8 +413,9 @@ struct DevCtx {
   double pend_time[SEQ ? SIMIAN_SELF_MAX : 1];
   unsigned long long pend_q2[SEQ ? SIMIAN_SELF_MAX : 1], pend_data[SEQ ? SIMIAN_SELF_MAX : 1];
 
-  __device__ __forceinline__ DevCtx(const DevCfg &c_, WindowShared &sh_, ThreadAcc &ta_)
-      : c(c_), sh(sh_), ta(ta_), npend(0) {}
+  __device__ __forceinline__ DevCtx(const DevCfg &c_, const WinState &W_, AppendCtx &ax_,
+                                    ThreadAcc &ta_)
+      : c(c_), W(W_), ax(ax_), ta(ta_), npend(0) {}
 
   __device__ __forceinline__ double now() const { return now_; }
   __device__ __forceinline__ uint32_t self_id() const { return self_gid; }
@@ -443,7 +446,6 @@ struct DevCtx {
     }
     uint32_t seq = simian_emit_seq(commit_idx, k);
     ta.emitted++;
-    const WinState &W = sh.W;
     if (rx == SIMIAN_NULL_ENTITY) { // entity.js:50-51
       if (time < now_) {
         set_error(c, SIMIAN_ERR_OUT_OF_ORDER); // simian.js:124-125 at pop time
@@ -463,7 +465,7 @@ struct DevCtx {
       RecBits r = make_rec(time, self_slot, self_gid, service, 0, seq, data);
       unsigned long long tk = simian_time_key(time);
       ta.min_key = tk < ta.min_key ? tk : ta.min_key;
-      append_local(c, sh.ax, W.tb_clean, W.far_row, W.alloc_limit, r);
+      append_local(c, ax, W.tb_clean, W.far_row, W.alloc_limit, r);
       return;
     }
     int rank;
@@ -473,7 +475,7 @@ struct DevCtx {
     unsigned long long tk = simian_time_key(time);
     if (rank == c.rank) { // entity.js:64
       ta.min_key = tk < ta.min_key ? tk : ta.min_key;
-      append_local(c, sh.ax, W.tb_clean, W.far_row, W.alloc_limit, r);
+      append_local(c, ax, W.tb_clean, W.far_row, W.alloc_limit, r);
     } else { // entity.js:66: staged for the per-window exchange
       // warp-aggregated claim: one atomic per (warp, destination rank)
       unsigned act = __activemask();
@@ -500,9 +502,59 @@ __device__ __forceinline__ void run_handler(DevCtx<SEQ> &ctx, uint32_t fn) {
     case SIMIAN_FN_COUNT_ONLY:
       simian_noop(ctx);
       break;
+    case SIMIAN_FN_LANL_SEND:
+      simian_lanl_send(ctx);
+      break;
+    case SIMIAN_FN_LANL_RECEIVE:
+      simian_lanl_receive(ctx);
+      break;
+    case SIMIAN_FN_LANL_FINISH:
+      simian_lanl_finish(ctx);
+      break;
+    case SIMIAN_FN_LANL_CONSTRUCT:
+      simian_lanl_construct(ctx);
+      break;
     default:
       set_error(ctx.c, SIMIAN_ERR_UNKNOWN_NAME);
   }
+}
+
+// `new entityClass(...)` bodies (simian.js:227) on the device: the named
+// constructor runs once per local instance at now = startTime; not an event.
+// Everything it sends goes to the calendar (no window is open yet).
+__global__ void k_construct(const __grid_constant__ DevCfg c, int cls, uint32_t fn) {
+  __shared__ AppendCtx ax;
+  __shared__ WinState W;
+  append_ctx_init(ax);
+  if (threadIdx.x == 0) {
+    W = c.win[0];
+    W.hi = __longlong_as_double(0xFFF0000000000000LL); // -inf: nothing is "inside the window"
+  }
+  __syncthreads();
+  const DevClass &cl = c.cls[cls];
+  ThreadAcc ta;
+  ta.min_key = SIMIAN_KEY_NONE;
+  ta.max_key = 0;
+  ta.committed = ta.emitted = ta.dropped = ta.ties = ta.dties = 0;
+  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < cl.n_local;
+       j += gridDim.x * blockDim.x) {
+    DevCtx<false> ctx(c, W, ax, ta);
+    int k;
+    ctx.self_slot = cl.slot_base + j;
+    ctx.self_gid = gid_of_slot(c, ctx.self_slot, k);
+    ctx.cl = &cl;
+    ctx.commit_idx = SIMIAN_CTOR_COMMIT;
+    ctx.key = simian_rng_key(c.seed, ctx.self_gid, SIMIAN_CTOR_COMMIT);
+    ctx.n_emit = 0;
+    ctx.now_ = c.start; // simian.js:44
+    ctx.handler_ = 0;
+    ctx.src_ = SIMIAN_NULL_ENTITY;
+    ctx.data_ = 0;
+    run_handler(ctx, fn);
+  }
+  if (ta.emitted) atomicAdd(&c.acc->emitted, (unsigned long long)ta.emitted);
+  if (ta.dropped) atomicAdd(&c.acc->dropped, (unsigned long long)ta.dropped);
+  append_ctx_flush(c, ax);
 }
 
 // key order (time, handler, src, seq): a < b
@@ -522,7 +574,7 @@ __device__ __noinline__ void process_entity(const DevCfg &c, WindowShared &sh, T
   uint32_t n = 0;
   for (uint32_t j = first; j != LIST_END; j = sh.nxt[j]) n++;
   int k;
-  DevCtx<true> ctx(c, sh, ta);
+  DevCtx<true> ctx(c, sh.W, sh.ax, ta);
   ctx.self_slot = slot;
   ctx.self_gid = gid_of_slot(c, slot, k);
   ctx.cl = &c.cls[k];
@@ -684,7 +736,7 @@ __device__ __forceinline__ void rank_and_emit(const DevCfg &c, WindowShared &sh,
   ta.committed++;
 
   int k;
-  DevCtx<false> ctx(c, sh, ta);
+  DevCtx<false> ctx(c, sh.W, sh.ax, ta);
   ctx.self_slot = slot;
   ctx.self_gid = gid_of_slot(c, slot, k);
   ctx.cl = &c.cls[k];

@@ -50,3 +50,84 @@ CONFIGS = {
         n=1 << 22, per_entity=16, min_delay=0.01, lookahead=0.01, p_remote=0.1,
         mode=PHOLD_ROSS_REMOTE, groups=1, end=2.0),
 }
+
+
+# ---- LANL PDES benchmark (SimianJS/Examples/pdes_lanl_benchmarkV8.js) --------
+
+import math  # noqa: E402
+
+import numpy as np  # noqa: E402
+
+LANL_CLASS = "PDES_LANL_Node"
+LANL_TIME_BINS = 16  # SIMIAN_LANL_TIME_BINS
+# simian_lanl_state_t (include/simian_models.h), 168 bytes; the list follows it
+LANL_STATE_DTYPE = np.dtype([
+    ("local_intersend_delay", "<f8"), ("q_target", "<f8"),
+    ("last_scheduled", "<f8"), ("ops", "<f8"), ("ops_max", "<f8"),
+    ("ops_min", "<f8"), ("ops_mean", "<f8"), ("value_sink", "<f8"),
+    ("q_size", "<i8"), ("send_count", "<u8"), ("receive_count", "<u8"),
+    ("ops_count", "<u8"), ("list_size", "<u4"), ("active_elements", "<u4"),
+    ("time_sends", "<u4", (LANL_TIME_BINS,))])
+assert LANL_STATE_DTYPE.itemsize == 168
+
+
+def lanl_list_size(n_ent, m_ent):
+    """this.list_size (pdes_lanl_benchmarkV8.js:221), p_list == 0; evaluated in
+    the same order as the handler: (prob * n_ent) * m_ent in f64."""
+    return int(math.floor((1.0 / n_ent) * n_ent * m_ent))
+
+
+def lanl_state_bytes(n_ent, m_ent):
+    return LANL_STATE_DTYPE.itemsize + 8 * lanl_list_size(n_ent, m_ent)
+
+
+def lanl_engine_end(end_time, min_delay):
+    """max(endTime, 2) + 3*minDelay  (pdes_lanl_benchmarkV8.js:349)"""
+    return max(end_time, 2) + 3 * min_delay
+
+
+def lanl_params_blob(first_id, n_ent, s_ent, q_avg, p_receive, m_ent, ops_ent,
+                     ops_sigma, cache_friendliness, end_time, min_delay,
+                     time_bins, svc_send, svc_receive, svc_finish):
+    """Pack simian_lanl_params_t (include/simian_models.h), 104 bytes."""
+    r_min = math.pow(1.0 - p_receive, n_ent)  # :196
+    blob = struct.pack("<II10dIHHHHI", first_id, n_ent, s_ent, q_avg, p_receive,
+                       m_ent, ops_ent, ops_sigma, cache_friendliness, end_time,
+                       min_delay, r_min, time_bins, svc_send, svc_receive,
+                       svc_finish, 0, 0)
+    assert len(blob) == 104
+    return blob
+
+
+def build_lanl(eng, n_ent, s_ent=100.0, q_avg=1.0, p_receive=0.0, m_ent=1000.0,
+               ops_ent=1000.0, ops_sigma=0.1, cache_friendliness=0.5,
+               end_time=100.0, min_delay=1.0, time_bins=10):
+    """The "MAIN" of pdes_lanl_benchmarkV8.js:346-356: one addEntity loop whose
+    constructors schedule FinishHandler and run the first SendHandler.  The
+    engine must have been created with end = lanl_engine_end(end_time,
+    min_delay).  p_send == 0 and p_list == 0 (see simian_models.h)."""
+    assert time_bins <= LANL_TIME_BINS
+    eng.define_class(LANL_CLASS, lanl_state_bytes(n_ent, m_ent))
+    eng.add_entities(LANL_CLASS, 0, n_ent)
+    eng.attach_service(LANL_CLASS, "SendHandler", "lanl_send")
+    eng.attach_service(LANL_CLASS, "ReceiveHandler", "lanl_receive")
+    eng.attach_service(LANL_CLASS, "FinishHandler", "lanl_finish")
+    ids = [eng.intern_service(s) for s in
+           ("SendHandler", "ReceiveHandler", "FinishHandler")]
+    eng.set_class_params(LANL_CLASS, lanl_params_blob(
+        eng.first_id(LANL_CLASS), n_ent, s_ent, q_avg, p_receive, m_ent,
+        ops_ent, ops_sigma, cache_friendliness, end_time, min_delay, time_bins,
+        *ids))
+    # each constructor sends FinishHandler + up to ceil(q_target) timers + 1 request
+    per = 3 + int(math.ceil(q_avg))
+    eng.construct_entities(LANL_CLASS, "lanl_construct", n_ent * per)
+    return eng
+
+
+def lanl_states(raw, n_ent, m_ent):
+    """split simian_read_state bytes into (struct array, lists[n, list_size])"""
+    sb = lanl_state_bytes(n_ent, m_ent)
+    a = np.frombuffer(bytes(raw), dtype=np.uint8).reshape(n_ent, sb)
+    st = a[:, :168].copy().view(LANL_STATE_DTYPE).reshape(n_ent)
+    lists = a[:, 168:].copy().view("<f8").reshape(n_ent, -1)
+    return st, lists

@@ -46,3 +46,68 @@ def assert_parity(st_o, cnt_o, h_o, st_e, cnt_e, h_e):
     assert st_e["emitted"] == st_o["emitted"]
     assert st_e["dropped_past_end"] == st_o["dropped_past_end"]
     assert st_e["ties"] == st_o["ties"]
+
+
+# ---- LANL PDES benchmark ------------------------------------------------------
+
+LANL_KEYS = ("n_ent", "s_ent", "q_avg", "p_receive", "m_ent", "ops_ent",
+             "ops_sigma", "cache_friendliness", "end_time", "min_delay",
+             "time_bins")
+
+
+def build_lanl_case(eng, case):
+    from simian_b200.workloads import build_lanl
+    build_lanl(eng, **{k: case[k] for k in LANL_KEYS})
+    return eng
+
+
+def read_lanl(handle, case):
+    """-> (counts, hashes, state struct array, lists)"""
+    from simian_b200.workloads import (LANL_CLASS, lanl_state_bytes,
+                                       lanl_states)
+    n = case["n_ent"]
+    raw = handle.read_state(LANL_CLASS, n, lanl_state_bytes(n, case["m_ent"]))
+    st, lists = lanl_states(raw, n, case["m_ent"])
+    return (handle.read_counts(LANL_CLASS, n),
+            handle.read_trace_hashes(LANL_CLASS, n), st, lists)
+
+
+def run_oracle_lanl(oracle_mod, case, size=1, tie_mode=1):
+    from simian_b200.workloads import lanl_engine_end
+    o = oracle_mod.Oracle(case.get("name", "lanl"), 0.0,
+                          lanl_engine_end(case["end_time"], case["min_delay"]),
+                          case["min_delay"], size=size, tie_mode=tie_mode,
+                          seed=case.get("seed", 1))
+    build_lanl_case(o, case)
+    st = o.run()
+    return (st,) + read_lanl(o, case)
+
+
+def run_engine_lanl(case, **options):
+    from simian_b200 import capi
+    from simian_b200.workloads import lanl_engine_end
+    e = capi.Engine(case.get("name", "lanl"), 0.0,
+                    lanl_engine_end(case["end_time"], case["min_delay"]),
+                    case["min_delay"], seed=case.get("seed", 1), **options)
+    build_lanl_case(e, case)
+    st = e.run()
+    out = (st,) + read_lanl(e, case)
+    e.close()
+    return out
+
+
+def assert_lanl_golden(case, st, counts, hashes, state, lists):
+    """against tests/golden/lanl_simianpie.json (unmodified SimianPie engine)"""
+    assert st["total_events"] == case["total_events"]
+    assert list(counts) == case["counts"]
+    assert ["%016x" % x for x in hashes] == case["hashes"]
+    assert "%016x" % st["digest"] == case["digest"]
+    assert float(st["last_time"]).hex() == case["last_time_hex"]
+    assert st["ties"] == case["ties"]
+    g = case["state"]
+    for k in ("send_count", "receive_count", "ops_count", "q_size"):
+        assert [int(x) for x in state[k]] == g[k], k
+    for k in ("last_scheduled", "ops_max", "ops_min", "ops_mean", "value_sink"):
+        assert [float(x).hex() for x in state[k]] == g[k], k
+    assert [[int(x) for x in row] for row in state["time_sends"]] == g["time_sends"]
+    assert [[float(x).hex() for x in row[:4]] for row in lists] == g["list_head"]

@@ -238,3 +238,52 @@ def test_sched_events_equals_sched_service(oracle_mod):
     o.sched_events(ev)
     st = o.run()
     assert st["digest"] == ref[0]["digest"]
+
+
+# ---- LANL PDES benchmark (pdes_lanl_benchmarkV8.js) ---------------------------
+
+LANL_GOLD = os.path.join(os.path.dirname(__file__), "golden", "lanl_simianpie.json")
+
+
+def lanl_golden_cases():
+    with open(LANL_GOLD) as f:
+        return json.load(f)["cases"]
+
+
+@pytest.mark.parametrize("case", lanl_golden_cases(), ids=lambda c: c["name"])
+def test_oracle_lanl_matches_simianpie_goldens(oracle_mod, case):
+    """constructors that send (pdes_lanl_benchmarkV8.js:255-256), same-window
+    self-timers, the geometric hot-spot destination and the ReceiveHandler
+    compute loop, against the unmodified SimianPie engine."""
+    from helpers import assert_lanl_golden, run_oracle_lanl
+    out = run_oracle_lanl(oracle_mod, case, tie_mode=1)
+    assert_lanl_golden(case, *out)
+
+
+@pytest.mark.parametrize("case", lanl_golden_cases(), ids=lambda c: c["name"])
+def test_oracle_lanl_literal_js_heap_same_counts_and_state(oracle_mod, case):
+    """the t = minDelay requests of the constructors are distinguishable
+    same-entity ties: under the literal JS heap order (tie_mode 0)
+    only the order-sensitive trace hashes of the tied entities may differ --
+    counts and the full entity state are order independent."""
+    from helpers import run_oracle_lanl
+    s1, c1, h1, st1, l1 = run_oracle_lanl(oracle_mod, case, tie_mode=1)
+    s0, c0, h0, st0, l0 = run_oracle_lanl(oracle_mod, case, tie_mode=0)
+    assert s0["total_events"] == s1["total_events"]
+    np.testing.assert_array_equal(c0, c1)
+    assert st0.tobytes() == st1.tobytes() and l0.tobytes() == l1.tobytes()
+    assert s0["state_checksum"] == s1["state_checksum"]
+    assert s0["distinguishable_ties"] == case["distinguishable_ties"] > 0
+    assert (h0 != h1).sum() <= 2 * case["distinguishable_ties"]
+
+
+def test_oracle_lanl_multi_rank_equals_single_rank(oracle_mod):
+    from helpers import run_oracle_lanl
+    case = lanl_golden_cases()[1]
+    ref = run_oracle_lanl(oracle_mod, case, size=1)
+    for size in (2, 3):
+        out = run_oracle_lanl(oracle_mod, case, size=size)
+        assert out[0]["total_events"] == ref[0]["total_events"]
+        assert out[0]["digest"] == ref[0]["digest"]
+        assert out[0]["state_checksum"] == ref[0]["state_checksum"]
+        np.testing.assert_array_equal(out[2], ref[2])

@@ -99,3 +99,64 @@ def test_lookahead_violation_is_an_error():
     with pytest.raises(capi.SimianError) as ei:
         e.run()
     assert ei.value.code == 1
+
+
+# ---- LANL PDES benchmark (stateful handlers, constructors that send) ----------
+
+LANL_GOLD = os.path.join(os.path.dirname(__file__), "golden", "lanl_simianpie.json")
+
+
+def lanl_golden_cases():
+    with open(LANL_GOLD) as f:
+        return json.load(f)["cases"]
+
+
+@pytest.mark.parametrize("case", lanl_golden_cases(), ids=lambda c: c["name"])
+def test_engine_lanl_matches_simianpie_goldens(case):
+    from helpers import assert_lanl_golden, run_engine_lanl
+    out = run_engine_lanl(case)
+    assert out[0]["error"] == 0
+    assert_lanl_golden(case, *out)
+
+
+LANL_CASES = [
+    dict(name="lanl_multi_block", n_ent=3000, s_ent=10.0, q_avg=1.0,
+         p_receive=0.0, m_ent=32.0, ops_ent=48.0, ops_sigma=0.1,
+         cache_friendliness=0.5, end_time=10.0, min_delay=1.0, time_bins=10,
+         seed=2),
+    dict(name="lanl_hot_spots", n_ent=2500, s_ent=12.0, q_avg=2.0,
+         p_receive=0.002, m_ent=24.0, ops_ent=30.0, ops_sigma=0.2,
+         cache_friendliness=0.5, end_time=8.0, min_delay=0.5, time_bins=16,
+         seed=4),
+    dict(name="lanl_all_to_entity0", n_ent=300, s_ent=6.0, q_avg=1.0,
+         p_receive=1.0, m_ent=8.0, ops_ent=10.0, ops_sigma=0.0,
+         cache_friendliness=1.0, end_time=6.0, min_delay=1.0, time_bins=4,
+         seed=6),
+    dict(name="lanl_deep_timer_queue", n_ent=1100, s_ent=40.0, q_avg=6.0,
+         p_receive=0.0, m_ent=16.0, ops_ent=16.0, ops_sigma=0.5,
+         cache_friendliness=0.75, end_time=4.0, min_delay=0.25, time_bins=8,
+         seed=8),
+]
+
+
+@pytest.mark.parametrize("case", LANL_CASES, ids=lambda c: c["name"])
+def test_engine_lanl_matches_oracle(case, oracle_mod):
+    """bit-exact counts, trace hashes (engine tie order = oracle tie_mode 1),
+    the whole per-entity state incl. the f64 lists, window and emit counts"""
+    from helpers import run_engine_lanl, run_oracle_lanl
+    so, co, ho, sto, lo = run_oracle_lanl(oracle_mod, case, tie_mode=1)
+    se, ce, he, ste, le = run_engine_lanl(case)
+    assert se["error"] == 0
+    assert se["total_events"] == so["total_events"]
+    np.testing.assert_array_equal(ce, co)
+    np.testing.assert_array_equal(he, ho)
+    assert ste.tobytes() == sto.tobytes()
+    assert le.tobytes() == lo.tobytes()
+    assert se["digest"] == so["digest"]
+    assert se["state_checksum"] == so["state_checksum"]
+    assert float(se["last_time"]).hex() == float(so["last_time"]).hex()
+    assert se["windows"] == so["windows"]
+    assert se["emitted"] == so["emitted"]
+    assert se["dropped_past_end"] == so["dropped_past_end"]
+    assert se["ties"] == so["ties"]
+    assert se["distinguishable_ties"] == so["distinguishable_ties"]
