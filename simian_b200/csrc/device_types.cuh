@@ -17,23 +17,28 @@
 #include "../../include/simian_spec.h"
 
 #ifndef SIMIAN_EPB
-#define SIMIAN_EPB 1024 // entities per block (one CTA owns one block)
+#define SIMIAN_EPB 512 // entities per block (one CTA owns one block)
 #endif
 #ifndef SIMIAN_THREADS
-#define SIMIAN_THREADS 512 // threads per CTA of the window kernel
+#define SIMIAN_THREADS 256 // threads per CTA of the window kernel
 #endif
 #ifndef SIMIAN_PAGE
 #define SIMIAN_PAGE 64 // records per page (2 KB)
 #endif
 #ifndef SIMIAN_REFS
-#define SIMIAN_REFS 2048 // due-event references a CTA groups per pass
+#define SIMIAN_REFS (4 * SIMIAN_THREADS) // due events a CTA holds on chip per pass
 #endif
 #ifndef SIMIAN_PGMAX
-#define SIMIAN_PGMAX 1024 // pages a CTA can list per window
+#define SIMIAN_PGMAX (SIMIAN_EPB + SIMIAN_EPB / 4) // pages a CTA can list per window
 #endif
+#ifndef SIMIAN_BC
+#define SIMIAN_BC 64 // free pages an entity block keeps for itself (block page cache)
+#endif
+#define SIMIAN_BC_FILL 32 // refill target / initial fill of a block page cache
+#define SIMIAN_BC_LOW 8   // refill from the global ring below this
 
 #ifndef SIMIAN_MINBLOCKS
-#define SIMIAN_MINBLOCKS 2 // __launch_bounds__ min CTAs/SM of the window kernel
+#define SIMIAN_MINBLOCKS 3 // __launch_bounds__ min CTAs/SM of the window kernel
 #endif
 
 #define SIMIAN_MAX_CLASSES 8
@@ -85,12 +90,20 @@ struct DevAcc {
   unsigned long long max_key; // max committed time key
   unsigned long long windows, redistributions, far_appends, page_allocs,
       leaked_pages;
+  unsigned long long appended; // records put into the local calendar, ever
   unsigned int ticket;
   unsigned int error; // sticky, first error wins
   unsigned int window_index;
   unsigned int pad_;
   double minvec[2]; // {local minLeft candidate, local far min} for allreduce
   unsigned long long phase_cycles[12]; // SIMIAN_PROFILE_PHASES builds only
+};
+
+// per-CTA results of one k_window launch: plain stores, summed by the last CTA
+// (no same-address atomics on the hot path)
+struct __align__(64) BlockPart {
+  unsigned long long min_key, max_key;
+  uint32_t committed, emitted, dropped, ties, dties, appended, far_appends, page_allocs;
 };
 
 struct DevCfg {
@@ -117,6 +130,11 @@ struct DevCfg {
   unsigned long long *snap; // [n_blocks] head words of row tb_hi at window start
   WinState *win;                  // [2]
   DevAcc *acc;
+  BlockPart *part; // [n_blocks]
+  // block page caches: pages an entity block recycled and will reuse, so that
+  // steady-state windows never touch the global free ring
+  uint32_t *bcache; // [n_blocks][SIMIAN_BC]
+  uint32_t *bcount; // [n_blocks]
   // cross-GPU staging (size > 1)
   simian_event_t *outbox; // [size][outbox_cap]
   uint32_t *outbox_count; // [size]

@@ -216,7 +216,8 @@ int setup(simian_engine *e) {
   uint64_t pool_events = e->pool_events
                              ? e->pool_events
                              : 2 * local_initial +
-                                   (uint64_t)PAGE * ((uint64_t)(ring + 2) * c.n_blocks + 1024ull);
+                                   (uint64_t)PAGE * ((uint64_t)(ring + 2) * c.n_blocks + 1024ull +
+                                                     (uint64_t)SIMIAN_BC * c.n_blocks);
   uint64_t n_pages = (pool_events + PAGE - 1) / PAGE;
   if (n_pages > 0xFFFFFFFFull / PAGE) n_pages = 0xFFFFFFFFull / PAGE;
   c.n_pages = (uint32_t)n_pages;
@@ -229,6 +230,9 @@ int setup(simian_engine *e) {
   if (dev_alloc(e, &c.snap, c.n_blocks)) return e->err_code;
   if (dev_alloc(e, &c.win, 2)) return e->err_code;
   if (dev_alloc(e, &c.acc, 1)) return e->err_code;
+  if (dev_alloc(e, &c.part, c.n_blocks)) return e->err_code;
+  if (dev_alloc(e, &c.bcache, (size_t)c.n_blocks * SIMIAN_BC)) return e->err_code;
+  if (dev_alloc(e, &c.bcount, c.n_blocks)) return e->err_code;
   if (dev_alloc(e, &e->d_digest, 2)) return e->err_code;
   if (e->size > 1) {
     uint64_t cap = e->outbox_events ? e->outbox_events : 2 * local_initial / g + 65536;

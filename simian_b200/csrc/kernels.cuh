@@ -37,7 +37,7 @@
 
 // ---------------------------------------------------------------- helpers --
 
-struct RecBits { // the 32-byte record as four 64-bit words
+struct __align__(16) RecBits { // the 32-byte record as four 64-bit words
   unsigned long long q0, q1, q2, q3;
   __device__ __forceinline__ double time() const { return __longlong_as_double((long long)q0); }
   __device__ __forceinline__ uint32_t dst() const { return (uint32_t)q1; }
@@ -66,6 +66,16 @@ __device__ __forceinline__ void st_rec(simian_event_t *p, const RecBits &r) {
                "l"(r.q2), "l"(r.q3)
                : "memory");
 }
+// Same record as two 128-bit stores.  Used inside __noinline__ functions: ptxas
+// 12.9 turns the 256-bit form into a single 64-bit store there (seen in SASS:
+// LDL.64 + STG.E.64), silently dropping 24 of the 32 bytes.
+__device__ __forceinline__ void st_rec_2x16(simian_event_t *p, unsigned long long q0,
+                                            unsigned long long q1, unsigned long long q2,
+                                            unsigned long long q3) {
+  asm volatile("st.global.v2.u64 [%0], {%1,%2};" ::"l"(p), "l"(q0), "l"(q1) : "memory");
+  asm volatile("st.global.v2.u64 [%0], {%1,%2};" ::"l"((char *)p + 16), "l"(q2), "l"(q3)
+               : "memory");
+}
 __device__ __forceinline__ RecBits ld_rec(const simian_event_t *p) {
   RecBits r;
   asm volatile("ld.global.v4.u64 {%0,%1,%2,%3}, [%4];"
@@ -77,6 +87,14 @@ __device__ __forceinline__ RecBits ld_rec(const simian_event_t *p) {
 __device__ __forceinline__ void ld_rec_head(const simian_event_t *p, unsigned long long &q0,
                                             unsigned long long &q1) {
   asm volatile("ld.global.v2.u64 {%0,%1}, [%2];" : "=l"(q0), "=l"(q1) : "l"(p));
+}
+// 16 bytes global -> shared without passing through registers (LDGSTS)
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *src) {
+  uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.wait_all;" ::: "memory");
 }
 // L2-coherent loads (bypass L1) for data other CTAs wrote in this launch
 __device__ __forceinline__ uint32_t ld_cg(const uint32_t *p) {
@@ -147,13 +165,17 @@ __device__ __forceinline__ uint32_t gid_of_slot(const DevCfg &c, uint32_t slot, 
 
 struct AppendCtx { // per-CTA, in shared memory
   uint32_t far_appends, page_allocs;
+  // the entity block's own free pages (k_window only; pgc_have == 0 elsewhere):
+  // a stack, popped from the top with a shared-memory atomic
+  uint32_t pgc_take, pgc_have;
+  uint32_t pgc[SIMIAN_BC];
 };
 
 // head word of an empty cell: no page, "full" so the first append installs one
 #define CELL_EMPTY (((unsigned long long)SIMIAN_NONE << 32) | (unsigned long long)PAGE)
 
 __device__ __forceinline__ void append_ctx_init(AppendCtx &ax) {
-  if (threadIdx.x == 0) ax.far_appends = ax.page_allocs = 0;
+  if (threadIdx.x == 0) ax.far_appends = ax.page_allocs = ax.pgc_take = ax.pgc_have = 0;
 }
 
 // Pop a page from the free ring.  Pages pushed during a launch become
@@ -161,12 +183,16 @@ __device__ __forceinline__ void append_ctx_init(AppendCtx &ax) {
 // never pops a ring slot that is being written.
 __device__ __forceinline__ uint32_t page_get(const DevCfg &c, AppendCtx &ax,
                                              unsigned long long alloc_limit) {
+  atomicAdd(&ax.page_allocs, 1u);
+  if (ax.pgc_have) { // block cache first: a shared-memory atomic, no L2 round trip
+    uint32_t k = atomicAdd(&ax.pgc_take, 1u);
+    if (k < ax.pgc_have) return ax.pgc[ax.pgc_have - 1u - k];
+  }
   unsigned long long i = atomicAdd(&c.acc->alloc_head, 1ull);
   if (i >= alloc_limit) {
     set_error(c, SIMIAN_ERR_POOL_EXHAUSTED);
     return SIMIAN_NONE;
   }
-  atomicAdd(&ax.page_allocs, 1u);
   return c.free_ring[i % c.n_pages];
 }
 
@@ -175,7 +201,8 @@ __device__ __forceinline__ void page_free(const DevCfg &c, uint32_t p) {
   c.free_ring[pos % c.n_pages] = p;
 }
 
-// call from all threads at the end of any kernel that appended
+// call from all threads at the end of a kernel that appended (not k_window,
+// which reports through its BlockPart)
 __device__ __forceinline__ void append_ctx_flush(const DevCfg &c, AppendCtx &ax) {
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -184,29 +211,36 @@ __device__ __forceinline__ void append_ctx_flush(const DevCfg &c, AppendCtx &ax)
   }
 }
 
+// sum a per-thread count of appended records into acc->appended (one atomic per warp)
+__device__ __forceinline__ void appended_flush(const DevCfg &c, uint32_t n) {
+  for (int o = 16; o; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+  if ((threadIdx.x & 31) == 0 && n) atomicAdd(&c.acc->appended, (unsigned long long)n);
+}
+
 // eventQ.push (eventQ.js:29-43) as an append to the cell's page chain.
 // ONE 64-bit atomicAdd on the cell's head word claims a slot and names the
 // page in the same L2 round trip.  Exactly one thread installs a new page: the
 // one whose claim returned PAGE (first overflow; an empty cell is born "full");
 // later claimants wait for the page field to change (starvation-free under
 // independent thread scheduling).
-__device__ __forceinline__ void cell_append(const DevCfg &c, AppendCtx &ax,
-                                            unsigned long long alloc_limit, uint32_t cell,
-                                            const RecBits &r) {
-  unsigned long long *hp = c.cell_state + cell;
+// Everything after a claim that did not land inside the head page.
+__device__ __noinline__ void cell_append_slow(const DevCfg &c, AppendCtx &ax,
+                                              unsigned long long alloc_limit,
+                                              unsigned long long *hp, unsigned long long old,
+                                              unsigned long long q0, unsigned long long q1,
+                                              unsigned long long q2, unsigned long long q3) {
 #pragma unroll 1
   for (;;) {
-    unsigned long long old = atomicAdd(hp, 1ull);
     uint32_t p = (uint32_t)(old >> 32), i = (uint32_t)old;
     if (i < (uint32_t)PAGE) {
-      st_rec(c.pool + ((size_t)p * PAGE + i), r);
+      st_rec_2x16(c.pool + ((size_t)p * PAGE + i), q0, q1, q2, q3);
       return;
     }
     if (i == (uint32_t)PAGE) { // first overflow: install the next page
       uint32_t np = page_get(c, ax, alloc_limit);
       if (np == SIMIAN_NONE) return; // sticky error set
       c.page_next[np] = p;
-      st_rec(c.pool + (size_t)np * PAGE, r); // slot 0 is ours
+      st_rec_2x16(c.pool + (size_t)np * PAGE, q0, q1, q2, q3); // slot 0 is ours
       // no fence: appenders of this launch only write into the page; chains
       // and records are read after a launch boundary or after the ticket fence
       atomicExch(hp, ((unsigned long long)np << 32) | 1ull);
@@ -217,28 +251,43 @@ __device__ __forceinline__ void cell_append(const DevCfg &c, AppendCtx &ax,
       if (ld_cg(&c.acc->error)) return;
       __nanosleep(40);
     }
+    old = atomicAdd(hp, 1ull);
   }
+}
+
+__device__ __forceinline__ void cell_append(const DevCfg &c, AppendCtx &ax,
+                                            unsigned long long alloc_limit, uint32_t cell,
+                                            const RecBits &r) {
+  unsigned long long *hp = c.cell_state + cell;
+  unsigned long long old = atomicAdd(hp, 1ull);
+  if ((uint32_t)old < (uint32_t)PAGE)
+    st_rec(c.pool + ((size_t)(uint32_t)(old >> 32) * PAGE + (uint32_t)old), r);
+  else
+    cell_append_slow(c, ax, alloc_limit, hp, old, r.q0, r.q1, r.q2, r.q3);
+}
+
+// calendar cell of a record whose dst is a LOCAL SLOT (SIMIAN_NONE: error set)
+__device__ __forceinline__ uint32_t cell_of_local(const DevCfg &c, AppendCtx &ax,
+                                                  long long tb_clean, uint32_t far_row,
+                                                  double time, uint32_t dst_slot) {
+  uint32_t b = dst_slot / EPB;
+  long long tb = tb_of(c, time);
+  if (tb < tb_clean) {
+    set_error(c, SIMIAN_ERR_OUT_OF_ORDER);
+    return SIMIAN_NONE;
+  }
+  if (tb - tb_clean < (long long)c.ring) return (uint32_t)(tb & (long long)c.ring_mask) * c.n_blocks + b;
+  atomicMin(&c.acc->far_min[far_row], simian_time_key(time));
+  atomicAdd(&ax.far_appends, 1u);
+  return (c.ring + far_row) * c.n_blocks + b;
 }
 
 // route a record whose dst is a LOCAL SLOT into the calendar or the far row
 __device__ __forceinline__ void append_local(const DevCfg &c, AppendCtx &ax, long long tb_clean,
                                              uint32_t far_row, unsigned long long alloc_limit,
                                              const RecBits &r) {
-  uint32_t b = r.dst() / EPB;
-  long long tb = tb_of(c, r.time());
-  uint32_t cell;
-  if (tb < tb_clean) {
-    set_error(c, SIMIAN_ERR_OUT_OF_ORDER);
-    return;
-  }
-  if (tb - tb_clean < (long long)c.ring) {
-    cell = (uint32_t)(tb & (long long)c.ring_mask) * c.n_blocks + b;
-  } else {
-    cell = (c.ring + far_row) * c.n_blocks + b;
-    atomicMin(&c.acc->far_min[far_row], simian_time_key(r.time()));
-    atomicAdd(&ax.far_appends, 1u);
-  }
-  cell_append(c, ax, alloc_limit, cell, r);
+  uint32_t cell = cell_of_local(c, ax, tb_clean, far_row, r.time(), r.dst());
+  if (cell != SIMIAN_NONE) cell_append(c, ax, alloc_limit, cell, r);
 }
 
 // ------------------------------------------------------------ init / load --
@@ -252,6 +301,14 @@ __global__ void k_init(const __grid_constant__ DevCfg c, uint32_t n_cells) {
   }
   for (size_t j = i; j < n_cells; j += stride) c.cell_state[j] = CELL_EMPTY;
   for (size_t j = i; j < c.n_blocks; j += stride) c.snap[j] = CELL_EMPTY;
+  // block page caches start with SIMIAN_BC_FILL pages each when the pool allows
+  const uint32_t fill =
+      ((unsigned long long)c.n_blocks * SIMIAN_BC_FILL * 2ull <= c.n_pages) ? SIMIAN_BC_FILL : 0u;
+  for (size_t j = i; j < (size_t)c.n_blocks * SIMIAN_BC; j += stride) {
+    uint32_t bb = (uint32_t)(j / SIMIAN_BC), k = (uint32_t)(j % SIMIAN_BC);
+    c.bcache[j] = k < fill ? bb * fill + k : SIMIAN_NONE;
+    if (k == 0) c.bcount[bb] = fill;
+  }
   for (size_t j = i; j < c.n_slots; j += stride) {
     EntityCore z;
     z.count = 0;
@@ -262,11 +319,12 @@ __global__ void k_init(const __grid_constant__ DevCfg c, uint32_t n_cells) {
     DevAcc *a = c.acc;
     a->min_key = SIMIAN_KEY_NONE;
     a->far_min[0] = a->far_min[1] = SIMIAN_KEY_NONE;
-    a->alloc_head = 0;
+    a->alloc_head = (unsigned long long)c.n_blocks * fill; // ring slots [0, alloc_head) went to the caches
     a->free_tail = c.n_pages;
     a->committed = a->emitted = a->dropped = a->ties = a->dist_ties = 0;
     a->max_key = 0;
     a->windows = a->redistributions = a->far_appends = a->page_allocs = a->leaked_pages = 0;
+    a->appended = 0;
     a->ticket = 0;
     a->error = 0;
     a->window_index = 0;
@@ -301,6 +359,7 @@ __global__ void k_sched_bulk(const __grid_constant__ DevCfg c, double time, uint
   const WinState &W = c.win[0];
   unsigned long long total = (unsigned long long)count * repeat;
   unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  uint32_t napp = 0;
   for (unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
        idx < total; idx += stride) {
     uint32_t i = (uint32_t)(idx % count);
@@ -312,7 +371,9 @@ __global__ void k_sched_bulk(const __grid_constant__ DevCfg c, double time, uint
     RecBits r = make_rec(time, slot, SIMIAN_NULL_ENTITY, handler, SIMIAN_EVF_SCHED,
                          seq_base + (uint32_t)idx, data);
     append_local(c, ax, W.tb_clean, W.far_row, W.alloc_limit, r);
+    napp++;
   }
+  appended_flush(c, napp);
   append_ctx_flush(c, ax);
 }
 
@@ -328,6 +389,7 @@ __global__ void k_ingest(const __grid_constant__ DevCfg c, const simian_event_t 
   const WinState &W = c.win[win_ix & 1u];
   unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
   unsigned long long mn = SIMIAN_KEY_NONE;
+  uint32_t napp = 0;
   for (unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
        idx < n; idx += stride) {
     RecBits r = ld_rec(recs + idx);
@@ -350,7 +412,9 @@ __global__ void k_ingest(const __grid_constant__ DevCfg c, const simian_event_t 
     unsigned long long k = simian_time_key(r.time());
     mn = k < mn ? k : mn;
     append_local(c, ax, W.tb_clean, W.far_row, W.alloc_limit, r);
+    napp++;
   }
+  appended_flush(c, napp);
   if (track_min) {
     for (int o = 16; o; o >>= 1) {
       unsigned long long x = __shfl_xor_sync(0xffffffffu, mn, o);
@@ -367,30 +431,56 @@ __global__ void k_ingest(const __grid_constant__ DevCfg c, const simian_event_t 
 // (k_construct, which needs the handler context, is defined after it below)
 
 #define LIST_END 0xFFFFu
+#define EV_PER_THREAD ((NREFS + NTHREADS - 1) / NTHREADS)
+static_assert(EV_PER_THREAD <= 4, "ranks are packed 8 bits each into one register");
+#define RSTACK_MAX 80 // entity sub-ranges a CTA can have pending
 
 struct WindowShared {
   WinState W;
   AppendCtx ax;
-  unsigned long long min_key, max_key, free_base;
-  uint32_t committed, emitted, dropped, ties, dties;
+  unsigned long long min_key, max_key, free_base, ring_base;
+  uint32_t committed, emitted, dropped, ties, dties, appended;
   uint32_t npg, nfree, total, is_last, found, stack_n, pass_lo, pass_hi;
   long long scan_j, t_last;
-  uint32_t rstack[64];          // entity sub-ranges still to process (lo, hi)
-  uint32_t head[EPB];           // per local entity: index of its first due event
-  uint32_t pg_id[PGMAX];        // pages of this block's cells in the window rows
+  uint32_t rstack[2 * RSTACK_MAX]; // entity sub-ranges still to process (lo, hi)
+  uint32_t head[EPB];              // per local entity: index of its first due event
+  uint32_t pg_id[PGMAX];           // pages of this block's cells in the window rows
   uint16_t pg_cnt[PGMAX];
-  uint32_t refs[NREFS];         // due events: pool index of the record
-  uint32_t tq[NREFS];           // due events: time quantised inside the window
-  unsigned long long xs[NREFS]; // due events: order-independent trace word
   uint16_t nxt[NREFS];          // next due event of the same entity
-  uint16_t rk[NREFS];           // rank of the event inside its entity
+  unsigned long long xs[NREFS]; // trace words, stored in commit order along the entity list
+  EntityCore core_s[EPB];       // {commit count, trace hash} of the entities with due events
+  // due events: the 32-byte records themselves, as two 16-byte halves (no bank
+  // conflicts).  The thread-per-event path overwrites slot i with the record
+  // event i emits (staged, then appended).
+  ulonglong2 lo[NREFS]; // {time, dst | src << 32}
+  ulonglong2 hi[NREFS]; // {handler | flags << 16 | seq << 32, data}
 };
+
+__device__ __forceinline__ RecBits slot_get(const WindowShared &sh, uint32_t i) {
+  ulonglong2 a = sh.lo[i], b = sh.hi[i];
+  RecBits r;
+  r.q0 = a.x;
+  r.q1 = a.y;
+  r.q2 = b.x;
+  r.q3 = b.y;
+  return r;
+}
+__device__ __forceinline__ void slot_put(WindowShared &sh, uint32_t i, const RecBits &r) {
+  sh.lo[i] = make_ulonglong2(r.q0, r.q1);
+  sh.hi[i] = make_ulonglong2(r.q2, r.q3);
+}
 
 // per-thread accumulators of the handler phase
 struct ThreadAcc {
   unsigned long long min_key, max_key;
-  uint32_t committed, emitted, dropped, ties, dties;
+  uint32_t committed, emitted, dropped, ties, dties, appended;
 };
+
+__device__ __forceinline__ void thread_acc_init(ThreadAcc &ta) {
+  ta.min_key = SIMIAN_KEY_NONE;
+  ta.max_key = 0;
+  ta.committed = ta.emitted = ta.dropped = ta.ties = ta.dties = ta.appended = 0;
+}
 
 // what a handler reaches through `self` on the device (see simian_models.h)
 // SEQ: one thread per entity (stateful handlers, same-window self-sends);
@@ -408,6 +498,10 @@ struct DevCtx {
   double now_;
   uint32_t handler_, src_;
   unsigned long long data_;
+  // !SEQ: where the first locally routed record is staged (shared-memory slot
+  // index) instead of being appended right away; SIMIAN_NONE = append directly
+  WindowShared *stage_sh;
+  uint32_t stage;
   // same-window self-sends (rx omitted, offset < minDelay allowed: entity.js:41)
   int npend;
   double pend_time[SEQ ? SIMIAN_SELF_MAX : 1];
@@ -415,7 +509,7 @@ struct DevCtx {
 
   __device__ __forceinline__ DevCtx(const DevCfg &c_, const WinState &W_, AppendCtx &ax_,
                                     ThreadAcc &ta_)
-      : c(c_), W(W_), ax(ax_), ta(ta_), npend(0) {}
+      : c(c_), W(W_), ax(ax_), ta(ta_), stage_sh(nullptr), stage(SIMIAN_NONE), npend(0) {}
 
   __device__ __forceinline__ double now() const { return now_; }
   __device__ __forceinline__ uint32_t self_id() const { return self_gid; }
@@ -430,6 +524,18 @@ struct DevCtx {
                : nullptr;
   }
   __device__ __forceinline__ uint32_t src() const { return src_; }
+
+  __device__ __forceinline__ void put_local(const RecBits &r) {
+    unsigned long long tk = simian_time_key(r.time());
+    ta.min_key = tk < ta.min_key ? tk : ta.min_key;
+    ta.appended++;
+    if (!SEQ && stage != SIMIAN_NONE) { // K4 is done by the append phase of k_window
+      slot_put(*stage_sh, stage, r);
+      stage = SIMIAN_NONE;
+    } else {
+      append_local(c, ax, W.tb_clean, W.far_row, W.alloc_limit, r);
+    }
+  }
 
   // Entity.reqService (entity.js:35-68)
   __device__ __forceinline__ void req_service(double offset, uint16_t service,
@@ -462,20 +568,15 @@ struct DevCtx {
         npend++;
         return;
       }
-      RecBits r = make_rec(time, self_slot, self_gid, service, 0, seq, data);
-      unsigned long long tk = simian_time_key(time);
-      ta.min_key = tk < ta.min_key ? tk : ta.min_key;
-      append_local(c, ax, W.tb_clean, W.far_row, W.alloc_limit, r);
+      put_local(make_rec(time, self_slot, self_gid, service, 0, seq, data));
       return;
     }
     int rank;
     uint32_t slot;
     route_gid(c, rx, rank, slot); // getOffsetRank, entity.js:62
     RecBits r = make_rec(time, slot, self_gid, service, 0, seq, data);
-    unsigned long long tk = simian_time_key(time);
     if (rank == c.rank) { // entity.js:64
-      ta.min_key = tk < ta.min_key ? tk : ta.min_key;
-      append_local(c, ax, W.tb_clean, W.far_row, W.alloc_limit, r);
+      put_local(r);
     } else { // entity.js:66: staged for the per-window exchange
       // warp-aggregated claim: one atomic per (warp, destination rank)
       unsigned act = __activemask();
@@ -492,6 +593,16 @@ struct DevCtx {
     }
   }
 };
+
+// the pure handlers only (thread-per-event path: simian_fn_is_pure)
+__device__ __forceinline__ void run_pure_handler(DevCtx<false> &ctx, uint32_t fn) {
+  if (fn == SIMIAN_FN_PHOLD_GENERATE)
+    simian_phold_generate(ctx);
+  else if (fn == SIMIAN_FN_COUNT_ONLY)
+    simian_noop(ctx);
+  else
+    set_error(ctx.c, SIMIAN_ERR_UNKNOWN_NAME);
+}
 
 template <bool SEQ>
 __device__ __forceinline__ void run_handler(DevCtx<SEQ> &ctx, uint32_t fn) {
@@ -533,9 +644,7 @@ __global__ void k_construct(const __grid_constant__ DevCfg c, int cls, uint32_t 
   __syncthreads();
   const DevClass &cl = c.cls[cls];
   ThreadAcc ta;
-  ta.min_key = SIMIAN_KEY_NONE;
-  ta.max_key = 0;
-  ta.committed = ta.emitted = ta.dropped = ta.ties = ta.dties = 0;
+  thread_acc_init(ta);
   for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < cl.n_local;
        j += gridDim.x * blockDim.x) {
     DevCtx<false> ctx(c, W, ax, ta);
@@ -554,6 +663,8 @@ __global__ void k_construct(const __grid_constant__ DevCfg c, int cls, uint32_t 
   }
   if (ta.emitted) atomicAdd(&c.acc->emitted, (unsigned long long)ta.emitted);
   if (ta.dropped) atomicAdd(&c.acc->dropped, (unsigned long long)ta.dropped);
+  if (ta.min_key != SIMIAN_KEY_NONE) atomicMin(&c.acc->min_key, ta.min_key);
+  appended_flush(c, ta.appended);
   append_ctx_flush(c, ax);
 }
 
@@ -568,7 +679,7 @@ __device__ __forceinline__ bool key_lt(unsigned long long a1, unsigned long long
 
 // All due events of one entity, in order (simian.js:122-134 restricted to one
 // entity; entities never interact inside a window because cross-entity sends
-// carry offset >= minDelay, entity.js:41).
+// carry offset >= minDelay, entity.js:41).  The records are in shared memory.
 __device__ __noinline__ void process_entity(const DevCfg &c, WindowShared &sh, ThreadAcc &ta,
                                             uint32_t slot, uint32_t first) {
   uint32_t n = 0;
@@ -578,7 +689,7 @@ __device__ __noinline__ void process_entity(const DevCfg &c, WindowShared &sh, T
   ctx.self_slot = slot;
   ctx.self_gid = gid_of_slot(c, slot, k);
   ctx.cl = &c.cls[k];
-  EntityCore st = c.core[slot];
+  EntityCore st = sh.core_s[slot % EPB];
   unsigned long long p1 = 0, p2 = 0;
   uint32_t p3 = 0;
   bool have_prev = false, have_last = false;
@@ -589,34 +700,24 @@ __device__ __noinline__ void process_entity(const DevCfg &c, WindowShared &sh, T
   for (;;) {
     // next event of the static group: min key strictly above the previous one
     bool have_g = false;
-    RecBits g;
+    uint32_t gj = 0;
     unsigned long long g1 = 0, g2 = 0;
     uint32_t g3 = 0;
     if (taken < n) {
-      if (n == 1) {
-        g = ld_rec(c.pool + sh.refs[first]);
-        have_g = true;
-      } else {
 #pragma unroll 1
-        for (uint32_t j = first; j != LIST_END; j = sh.nxt[j]) {
-          RecBits r = ld_rec(c.pool + sh.refs[j]);
-          unsigned long long k1 = simian_time_key(r.time());
-          unsigned long long k2 = ((unsigned long long)r.handler() << 32) | r.src();
-          uint32_t k3 = r.seq();
-          if (have_prev && !key_lt(p1, p2, p3, k1, k2, k3)) continue;
-          if (!have_g || key_lt(k1, k2, k3, g1, g2, g3)) {
-            g = r;
-            g1 = k1;
-            g2 = k2;
-            g3 = k3;
-            have_g = true;
-          }
+      for (uint32_t j = first; j != LIST_END; j = sh.nxt[j]) {
+        const RecBits r = slot_get(sh, j);
+        unsigned long long k1 = simian_time_key(r.time());
+        unsigned long long k2 = ((unsigned long long)r.handler() << 32) | r.src();
+        uint32_t k3 = r.seq();
+        if (have_prev && !key_lt(p1, p2, p3, k1, k2, k3)) continue;
+        if (!have_g || key_lt(k1, k2, k3, g1, g2, g3)) {
+          gj = j;
+          g1 = k1;
+          g2 = k2;
+          g3 = k3;
+          have_g = true;
         }
-      }
-      if (n == 1) {
-        g1 = simian_time_key(g.time());
-        g2 = ((unsigned long long)g.handler() << 32) | g.src();
-        g3 = g.seq();
       }
     }
     // earliest pending same-window self-send
@@ -628,7 +729,8 @@ __device__ __noinline__ void process_entity(const DevCfg &c, WindowShared &sh, T
     double time;
     uint32_t handler, src;
     unsigned long long data;
-    if (pj >= 0 && (!have_g || ctx.pend_time[pj] < g.time())) {
+    if (pj >= 0 &&
+        (!have_g || ctx.pend_time[pj] < __longlong_as_double((long long)sh.lo[gj].x))) {
       time = ctx.pend_time[pj];
       handler = (uint32_t)(ctx.pend_q2[pj] & 0xFFFFu);
       src = ctx.self_gid;
@@ -638,6 +740,7 @@ __device__ __noinline__ void process_entity(const DevCfg &c, WindowShared &sh, T
       ctx.pend_q2[pj] = ctx.pend_q2[ctx.npend];
       ctx.pend_data[pj] = ctx.pend_data[ctx.npend];
     } else if (have_g) {
+      const RecBits g = slot_get(sh, gj);
       time = g.time();
       handler = g.handler();
       src = g.src();
@@ -681,47 +784,47 @@ __device__ __noinline__ void process_entity(const DevCfg &c, WindowShared &sh, T
 }
 
 // ---- thread-per-event path (pure handlers) --------------------------------
-// Phase RB, one thread per EVENT: rank of the event inside its entity's list
-// under (time, handler, src, seq) -- decided from the quantised times in shared
-// memory, exact keys only on a quantisation collision -- tie check against its
-// predecessor, the order-independent part of the trace hash, then the handler
-// itself (simian.js:129-131): RNG, log, destination, emit.
-// Commit index = the entity's committed count + rank.
-__device__ __forceinline__ void rank_and_emit(const DevCfg &c, WindowShared &sh, ThreadAcc &ta,
-                                              uint32_t slot0, uint32_t i) {
-  RecBits r = ld_rec(c.pool + sh.refs[i]);
-  const uint32_t le = r.dst() - slot0, slot = r.dst();
-  const unsigned long long count0 = c.core[slot].count; // may miss to DRAM: issued early
-  const uint32_t myq = sh.tq[i];
+// Phase A1, one thread per EVENT: rank of the event inside its entity's list
+// under (time, handler, src, seq), tie check against its predecessor, and the
+// order-independent part of the trace hash, which is parked on the rank-th
+// node of the entity's list so that the chain phase reads it in commit order.
+// Returns the rank.
+__device__ __forceinline__ uint32_t rank_event(const DevCfg &c, WindowShared &sh, ThreadAcc &ta,
+                                               uint32_t slot0, uint32_t i) {
+  const ulonglong2 a = sh.lo[i];
+  const uint32_t le = (uint32_t)a.y - slot0;
+  const double tr = __longlong_as_double((long long)a.x);
   uint32_t rank = 0;
   bool have_pred = false;
   RecBits pred;
+  const uint32_t first = sh.head[le];
+  const ulonglong2 bh = sh.hi[i];
+  RecBits r;
+  r.q0 = a.x;
+  r.q1 = a.y;
+  r.q2 = bh.x;
+  r.q3 = bh.y;
 #pragma unroll 1
-  for (uint32_t j = sh.head[le]; j != LIST_END; j = sh.nxt[j]) {
+  for (uint32_t j = first; j != LIST_END; j = sh.nxt[j]) {
     if (j == i) continue;
-    uint32_t qj = sh.tq[j];
-    if (qj < myq) {
+    const double to = __longlong_as_double((long long)sh.lo[j].x);
+    if (to < tr) {
       rank++;
-    } else if (qj == myq) { // quantisation collision (or a true tie): exact keys
-      RecBits o = ld_rec(c.pool + sh.refs[j]);
-      bool before;
-      if (o.time() != r.time()) {
-        before = o.time() < r.time();
-      } else {
-        unsigned long long a2 = ((unsigned long long)o.handler() << 32) | o.src();
-        unsigned long long b2 = ((unsigned long long)r.handler() << 32) | r.src();
-        before = a2 != b2 ? a2 < b2 : o.seq() < r.seq();
-        if (before) { // equal-time predecessor: keep the latest one
-          if (!have_pred) {
-            pred = o;
-            have_pred = true;
-          } else {
-            unsigned long long p2 = ((unsigned long long)pred.handler() << 32) | pred.src();
-            if (p2 != a2 ? p2 < a2 : pred.seq() < o.seq()) pred = o;
-          }
+    } else if (to == tr) { // a true same-entity time tie: the defined order decides
+      const RecBits o = slot_get(sh, j);
+      unsigned long long a2 = ((unsigned long long)o.handler() << 32) | o.src();
+      unsigned long long b2 = ((unsigned long long)r.handler() << 32) | r.src();
+      bool before = a2 != b2 ? a2 < b2 : o.seq() < r.seq();
+      if (before) { // equal-time predecessor: keep the latest one
+        rank++;
+        if (!have_pred) {
+          pred = o;
+          have_pred = true;
+        } else {
+          unsigned long long p2 = ((unsigned long long)pred.handler() << 32) | pred.src();
+          if (p2 != a2 ? p2 < a2 : pred.seq() < o.seq()) pred = o;
         }
       }
-      rank += before ? 1u : 0u;
     }
   }
   if (c.tie_check && have_pred) {
@@ -729,18 +832,30 @@ __device__ __forceinline__ void rank_and_emit(const DevCfg &c, WindowShared &sh,
     if (pred.q1 >> 32 != r.q1 >> 32 || pred.handler() != r.handler() || pred.q3 != r.q3)
       ta.dties++;
   }
-  sh.xs[i] = simian_trace_event(r.time(), r.handler(), r.src(), r.data());
-  sh.rk[i] = (uint16_t)rank;
-  unsigned long long tk = simian_time_key(r.time());
+  uint32_t t = first;
+  for (uint32_t s = 0; s < rank; s++) t = sh.nxt[t];
+  sh.xs[t] = simian_trace_event(tr, r.handler(), r.src(), r.data());
+  unsigned long long tk = simian_time_key(tr);
   ta.max_key = tk > ta.max_key ? tk : ta.max_key;
   ta.committed++;
+  return rank;
+}
 
+// Phase A2, one thread per EVENT: the handler itself (simian.js:129-131): RNG,
+// log, destination.  Commit index = the entity's committed count + rank.  The
+// record it sends to a local entity replaces the consumed one in slot i.
+__device__ __forceinline__ void run_event(const DevCfg &c, WindowShared &sh, ThreadAcc &ta,
+                                          uint32_t slot0, uint32_t i, uint32_t rank) {
+  const RecBits r = slot_get(sh, i);
+  const uint32_t slot = r.dst();
   int k;
   DevCtx<false> ctx(c, sh.W, sh.ax, ta);
+  ctx.stage_sh = &sh;
+  ctx.stage = i;
   ctx.self_slot = slot;
   ctx.self_gid = gid_of_slot(c, slot, k);
   ctx.cl = &c.cls[k];
-  ctx.commit_idx = count0 + rank;
+  ctx.commit_idx = sh.core_s[slot - slot0].count + rank;
   ctx.key = simian_rng_key(c.seed, ctx.self_gid, ctx.commit_idx);
   ctx.n_emit = 0;
   ctx.now_ = r.time(); // simian.js:126
@@ -748,40 +863,35 @@ __device__ __forceinline__ void rank_and_emit(const DevCfg &c, WindowShared &sh,
   ctx.src_ = r.src();
   ctx.data_ = r.data();
   uint32_t h = r.handler();
-  run_handler(ctx, h < SIMIAN_MAX_SERVICES ? ctx.cl->fn_of_service[h] : 0);
+  run_pure_handler(ctx, h < SIMIAN_MAX_SERVICES ? ctx.cl->fn_of_service[h] : 0);
+  if (ctx.stage != SIMIAN_NONE) sh.lo[i].y = 0xFFFFFFFFFFFFFFFFull; // nothing staged
 }
 
-// Phase H, one thread per entity: fold the trace words in rank (= commit)
-// order and publish the new commit count; a few integer operations per event.
+// Phase C, one thread per entity: fold the trace words, already in commit
+// order along the list, and publish the new commit count.
 __device__ __forceinline__ void chain_entity(const DevCfg &c, WindowShared &sh, uint32_t slot,
-                                             uint32_t first) {
-  EntityCore st = c.core[slot];
+                                             uint32_t le, uint32_t first) {
+  EntityCore st = sh.core_s[le];
   uint32_t n = 0;
-  if (sh.nxt[first] == LIST_END) {
-    st.hash = simian_trace_chain(st.hash, sh.xs[first]);
-    n = 1;
-  } else {
-    for (uint32_t j = first; j != LIST_END; j = sh.nxt[j]) n++;
 #pragma unroll 1
-    for (uint32_t r = 0; r < n; r++)
-      for (uint32_t j = first; j != LIST_END; j = sh.nxt[j])
-        if (sh.rk[j] == r) {
-          st.hash = simian_trace_chain(st.hash, sh.xs[j]);
-          break;
-        }
+  for (uint32_t j = first; j != LIST_END; j = sh.nxt[j]) {
+    st.hash = simian_trace_chain(st.hash, sh.xs[j]);
+    n++;
   }
   st.count += n;
   c.core[slot] = st;
 }
 
 // K2: ONE coalesced pass over the block's pages.  Every record whose time is
-// inside [gmin, hi) and whose entity is inside [e_lo, e_hi) is pushed onto its
-// entity's list in shared memory (eventQ.pop for all of them at once,
-// eventQ.js:53-92); on the first pass the minimum time >= hi is tracked (K1).
-// Positions are claimed with one shared-memory atomic per warp.
+// inside [gmin, hi) and whose entity is inside [e_lo, e_hi) is copied into a
+// shared-memory slot (cp.async, no registers) and pushed onto its entity's
+// list (eventQ.pop for all of them at once, eventQ.js:53-92); the first event
+// of an entity also fetches the entity's {count, hash}.  On the first pass the
+// minimum time >= hi is tracked (K1).  Slots are claimed with one
+// shared-memory atomic per warp.
 __device__ __forceinline__ void collect_due(const DevCfg &c, WindowShared &sh, ThreadAcc &ta,
                                             uint32_t slot0, uint32_t npg, uint32_t e_lo,
-                                            uint32_t e_hi, bool first, double qscale) {
+                                            uint32_t e_hi, bool first) {
   const int tid = threadIdx.x, lane = tid & 31;
   const WinState &W = sh.W;
   const uint32_t lim = npg * PAGE;
@@ -802,9 +912,8 @@ __device__ __forceinline__ void collect_due(const DevCfg &c, WindowShared &sh, T
     for (int u = 0; u < U; u++) {
       bool due = false;
       uint32_t le = 0;
-      double t = 0;
       if (ok[u]) {
-        t = __longlong_as_double((long long)q0[u]);
+        double t = __longlong_as_double((long long)q0[u]);
         if (t < W.hi) {
           le = (uint32_t)q1[u] - slot0;
           due = t >= W.gmin && le >= e_lo && le < e_hi;
@@ -822,14 +931,17 @@ __device__ __forceinline__ void collect_due(const DevCfg &c, WindowShared &sh, T
         if (due) {
           uint32_t pos = p0 + __popc(m & ((1u << lane) - 1u));
           if (pos < NREFS) {
-            sh.refs[pos] = ref[u];
-            sh.tq[pos] = __double2uint_rd((t - W.gmin) * qscale);
-            sh.nxt[pos] = (uint16_t)atomicExch(&sh.head[le], pos);
+            sh.lo[pos] = make_ulonglong2(q0[u], q1[u]);
+            cp_async16(&sh.hi[pos], (const char *)(c.pool + ref[u]) + 16);
+            uint32_t prev = atomicExch(&sh.head[le], pos);
+            sh.nxt[pos] = (uint16_t)prev;
+            if (prev == LIST_END) cp_async16(&sh.core_s[le], &c.core[slot0 + le]);
           }
         }
       }
     }
   }
+  cp_async_wait_all();
 }
 
 // walk one cell's page chain into the CTA's page list
@@ -863,6 +975,9 @@ __device__ void local_min_candidate(const DevCfg &c, const WinState &W, WindowSh
   unsigned long long cand = ld_cg64(&a->min_key);
   cand = far < cand ? far : cand;
   long long jmax = W.tb_clean + (long long)c.ring - 1;
+  // nothing pending at all (every appended record has been committed): the
+  // rows need not be searched (end of the run, simian.js:147 `infTime`)
+  if (ld_cg64(&a->appended) == ld_cg64(&a->committed)) jmax = W.tb_hi;
   if (cand != SIMIAN_KEY_NONE) {
     long long tc = tb_of(c, simian_key_time(cand));
     jmax = tc < jmax ? tc : jmax;
@@ -961,6 +1076,10 @@ __device__ void setup_next_window(const DevCfg &c, const WinState &W, WinState *
         atomicCAS(&a->error, 0u, (unsigned int)SIMIAN_ERR_RING_SPAN);
     }
     nw.alloc_limit = ld_cg64(&a->free_tail);
+#ifdef SIMIAN_PROFILE_PHASES
+    if (a->windows == 1) // steady-state windows only: drop the t = 0 burst window
+      for (int q = 0; q < 12; q++) a->phase_cycles[q] = 0;
+#endif
     a->min_key = SIMIAN_KEY_NONE;
     a->ticket = 0;
     a->window_index++;
@@ -1033,6 +1152,73 @@ __device__ void redistribute_block(const DevCfg &c, WindowShared &sh, uint32_t b
   if (tid == 0) c.cell_state[far_cell] = CELL_EMPTY;
 }
 
+// Sum the per-CTA results of the launch into the global accumulators (one CTA,
+// all threads; runs after the ticket fence, so every BlockPart is visible).
+__device__ void reduce_parts(const DevCfg &c, WindowShared &sh) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  unsigned long long mn = SIMIAN_KEY_NONE, mx = 0;
+  unsigned long long v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (uint32_t b = tid; b < c.n_blocks; b += blockDim.x) {
+    const BlockPart *p = &c.part[b];
+    unsigned long long a0 = ld_cg64(&p->min_key), a1 = ld_cg64(&p->max_key);
+    mn = a0 < mn ? a0 : mn;
+    mx = a1 > mx ? a1 : mx;
+    const uint32_t *w = &p->committed;
+#pragma unroll
+    for (int k = 0; k < 8; k++) v[k] += ld_cg(w + k);
+  }
+  for (int o = 16; o; o >>= 1) {
+    unsigned long long x = __shfl_xor_sync(0xffffffffu, mn, o);
+    mn = x < mn ? x : mn;
+    unsigned long long y = __shfl_xor_sync(0xffffffffu, mx, o);
+    mx = y > mx ? y : mx;
+#pragma unroll
+    for (int k = 0; k < 8; k++) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+  }
+  __shared__ unsigned long long red[10];
+  if (tid < 10) red[tid] = tid == 0 ? SIMIAN_KEY_NONE : 0ull;
+  __syncthreads();
+  if (lane == 0) {
+    if (mn != SIMIAN_KEY_NONE) atomicMin(&red[0], mn);
+    if (mx) atomicMax(&red[1], mx);
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+      if (v[k]) atomicAdd(&red[2 + k], v[k]);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    DevAcc *a = c.acc;
+    unsigned long long m0 = ld_cg64(&a->min_key); // ingested / scheduled since the last advance
+    a->min_key = red[0] < m0 ? red[0] : m0;
+    unsigned long long m1 = ld_cg64(&a->max_key);
+    a->max_key = red[1] > m1 ? red[1] : m1;
+    a->committed += red[2];
+    a->emitted += red[3];
+    a->dropped += red[4];
+    a->ties += red[5];
+    a->dist_ties += red[6];
+    a->appended += red[7];
+    a->far_appends += red[8];
+    a->page_allocs += red[9];
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// 64-bit min / max over the warp with redux.sync on the two halves
+__device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v) {
+  uint32_t hi = (uint32_t)(v >> 32), lo = (uint32_t)v;
+  uint32_t mh = __reduce_min_sync(0xffffffffu, hi);
+  uint32_t ml = __reduce_min_sync(0xffffffffu, hi == mh ? lo : 0xFFFFFFFFu);
+  return ((unsigned long long)mh << 32) | ml;
+}
+__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v) {
+  uint32_t hi = (uint32_t)(v >> 32), lo = (uint32_t)v;
+  uint32_t mh = __reduce_max_sync(0xffffffffu, hi);
+  uint32_t ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+  return ((unsigned long long)mh << 32) | ml;
+}
+
 // One lookahead window (or one redistribution pass) for entity block blockIdx.x.
 // fuse_advance != 0 (size == 1): the last CTA to finish computes window k+1.
 __global__ void __launch_bounds__(NTHREADS, SIMIAN_MINBLOCKS)
@@ -1044,34 +1230,35 @@ __global__ void __launch_bounds__(NTHREADS, SIMIAN_MINBLOCKS)
   const WinState *Wg = &c.win[win_ix & 1u];
   if (Wg->done) return; // simian.js:119: enqueued past the end of the run
   if (tid == 0) sh.found = ld_cg(&c.acc->error);
-  __syncthreads();
-  if (sh.found) return; // sticky error: CTA-uniform exit
-
+  // the block's own free pages (written by this block's CTA of the previous launch)
+  if (tid < SIMIAN_BC) sh.ax.pgc[tid] = c.bcache[(size_t)b * SIMIAN_BC + tid];
   if (tid == 0) {
     sh.t_last = clock64();
     sh.W = *Wg;
     sh.min_key = SIMIAN_KEY_NONE;
     sh.max_key = 0;
-    sh.committed = sh.emitted = sh.dropped = sh.ties = sh.dties = 0;
+    sh.committed = sh.emitted = sh.dropped = sh.ties = sh.dties = sh.appended = 0;
     sh.npg = 0;
     sh.nfree = 0;
     sh.is_last = 0;
+    sh.ax.far_appends = sh.ax.page_allocs = sh.ax.pgc_take = 0;
+    sh.ax.pgc_have = c.bcount[b];
   }
-  append_ctx_init(sh.ax);
   __syncthreads();
+  if (sh.found) return; // sticky error: CTA-uniform exit
   const WinState &W = sh.W;
   PHASE(0);
 
   ThreadAcc ta;
-  ta.min_key = SIMIAN_KEY_NONE;
-  ta.max_key = 0;
-  ta.committed = ta.emitted = ta.dropped = ta.ties = ta.dties = 0;
+  thread_acc_init(ta);
+  uint32_t npg = 0;
+  int ncell = 0;
 
   if (W.redist) {
     redistribute_block(c, sh, b);
   } else {
     // ---- K2a: list the pages of this block's cells in rows [tb_lo, tb_hi]
-    int ncell = (int)(W.tb_hi - W.tb_lo + 1);
+    ncell = (int)(W.tb_hi - W.tb_lo + 1);
     if (tid < ncell) {
       long long tb = W.tb_lo + tid;
       uint32_t cell = (uint32_t)(tb & (long long)c.ring_mask) * c.n_blocks + b;
@@ -1084,16 +1271,15 @@ __global__ void __launch_bounds__(NTHREADS, SIMIAN_MINBLOCKS)
     }
     __syncthreads();
     PHASE(1);
-    uint32_t npg = sh.npg;
+    npg = sh.npg;
     if (npg > PGMAX) {
       if (tid == 0) set_error(c, SIMIAN_ERR_WINDOW_OVERFLOW);
       npg = 0;
     }
     // ---- K2..K4 over entity sub-ranges; normally ONE pass over [0, EPB).  A
-    // sub-range whose due events overflow the shared-memory lists is halved
+    // sub-range whose due events overflow the shared-memory slots is split
     // and retried (bursts such as the 16 events/entity at t = 0).
     const uint32_t slot0 = b * EPB;
-    const double qscale = 4294967295.0 / (W.hi - W.gmin);
     if (tid == 0) {
       sh.rstack[0] = 0;
       sh.rstack[1] = EPB;
@@ -1114,63 +1300,146 @@ __global__ void __launch_bounds__(NTHREADS, SIMIAN_MINBLOCKS)
       for (int i = tid; i < EPB; i += NTHREADS) sh.head[i] = LIST_END;
       __syncthreads();
       const uint32_t e_lo = sh.pass_lo, e_hi = sh.pass_hi;
-      collect_due(c, sh, ta, slot0, npg, e_lo, e_hi, first, qscale);
+      collect_due(c, sh, ta, slot0, npg, e_lo, e_hi, first);
       first = false;
       __syncthreads();
       PHASE(2);
       const uint32_t m = sh.total;
-      if (m > NREFS) { // overflow: halve the entity range and retry
-        if (e_hi - e_lo <= 1 || sh.stack_n >= 30) {
+      if (m > NREFS) { // overflow: split the entity range and retry
+        if (e_hi - e_lo <= 1) {
           if (tid == 0) set_error(c, SIMIAN_ERR_ENTITY_BURST);
           break;
         }
         __syncthreads();
         if (tid == 0) {
-          uint32_t mid = (e_lo + e_hi) >> 1;
-          sh.rstack[2 * sh.stack_n] = mid;
-          sh.rstack[2 * sh.stack_n + 1] = e_hi;
-          sh.rstack[2 * sh.stack_n + 2] = e_lo;
-          sh.rstack[2 * sh.stack_n + 3] = mid;
-          sh.stack_n += 2;
+          uint32_t parts = m / (NREFS * 3u / 4u) + 1u, span = e_hi - e_lo;
+          if (parts > span) parts = span;
+          if (parts > 16u) parts = 16u;
+          if (sh.stack_n + parts > RSTACK_MAX) parts = 2;
+          for (uint32_t q = parts; q-- > 0;) { // lowest sub-range on top of the stack
+            sh.rstack[2 * sh.stack_n] = e_lo + (uint32_t)((unsigned long long)span * q / parts);
+            sh.rstack[2 * sh.stack_n + 1] =
+                e_lo + (uint32_t)((unsigned long long)span * (q + 1) / parts);
+            sh.stack_n++;
+          }
         }
         continue;
       }
       if (m == 0) continue;
       if (c.all_pure) {
-        // K3 + K4, one thread per EVENT: rank, tie check, handler, emit
-        for (uint32_t i = tid; i < m; i += NTHREADS) rank_and_emit(c, sh, ta, slot0, i);
+        // A1, one thread per EVENT: rank (kept in a register), tie check, trace word
+        uint32_t rkpack = 0; // EV_PER_THREAD ranks, 8 bits each
+#pragma unroll 1
+        for (int u = 0; u < EV_PER_THREAD; u++) {
+          uint32_t i = tid + u * NTHREADS;
+          if (i < m) {
+            uint32_t r = rank_event(c, sh, ta, slot0, i);
+            if (r > 255u) set_error(c, SIMIAN_ERR_ENTITY_BURST);
+            rkpack |= (r & 255u) << (8 * u);
+          }
+        }
         __syncthreads();
+        PHASE(3);
+        // A2 (K3), one thread per EVENT: handler; the sent record is staged in
+        // the consumed record's slot
+#pragma unroll 1
+        for (int u = 0; u < EV_PER_THREAD; u++) {
+          uint32_t i = tid + u * NTHREADS;
+          if (i < m) run_event(c, sh, ta, slot0, i, (rkpack >> (8 * u)) & 255u);
+        }
+        __syncthreads();
+        PHASE(4);
+        // B (K4), one thread per EVENT: append the staged records; the claims
+        // of all of a thread's events are in flight together
+        {
+          unsigned long long old[EV_PER_THREAD];
+          uint32_t cell[EV_PER_THREAD];
+#pragma unroll
+          for (int u = 0; u < EV_PER_THREAD; u++) {
+            uint32_t i = tid + u * NTHREADS;
+            cell[u] = SIMIAN_NONE;
+            if (i < m) {
+              ulonglong2 a = sh.lo[i];
+              if ((uint32_t)a.y != SIMIAN_NONE)
+                cell[u] = cell_of_local(c, sh.ax, W.tb_clean, W.far_row,
+                                        __longlong_as_double((long long)a.x), (uint32_t)a.y);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < EV_PER_THREAD; u++)
+            if (cell[u] != SIMIAN_NONE) old[u] = atomicAdd(c.cell_state + cell[u], 1ull);
+#pragma unroll
+          for (int u = 0; u < EV_PER_THREAD; u++)
+            if (cell[u] != SIMIAN_NONE) {
+              const RecBits r = slot_get(sh, tid + u * NTHREADS);
+              if ((uint32_t)old[u] < (uint32_t)PAGE)
+                st_rec(c.pool + ((size_t)(uint32_t)(old[u] >> 32) * PAGE + (uint32_t)old[u]), r);
+              else
+                cell_append_slow(c, sh.ax, W.alloc_limit, c.cell_state + cell[u], old[u], r.q0, r.q1,
+                                 r.q2, r.q3);
+            }
+        }
         PHASE(5);
-        // per entity: fold the trace hash chain, publish the commit count
+        // C, one thread per entity: fold the trace hash chain, publish the count
         for (uint32_t le = e_lo + tid; le < e_hi; le += NTHREADS) {
           uint32_t f = sh.head[le];
-          if (f != LIST_END) chain_entity(c, sh, slot0 + le, f);
+          if (f != LIST_END) chain_entity(c, sh, slot0 + le, le, f);
         }
       } else {
-        // K3 + K4: stateful handlers, one thread per entity
+        // K3 + K4: stateful handlers, one thread per entity.  A separate
+        // accumulator keeps `ta` of the thread-per-event path in registers
+        // (process_entity is not inlined).
+        ThreadAcc t2;
+        thread_acc_init(t2);
         for (uint32_t le = e_lo + tid; le < e_hi; le += NTHREADS) {
           uint32_t f = sh.head[le];
-          if (f != LIST_END) process_entity(c, sh, ta, slot0 + le, f);
+          if (f != LIST_END) process_entity(c, sh, t2, slot0 + le, f);
         }
+        ta.min_key = t2.min_key < ta.min_key ? t2.min_key : ta.min_key;
+        ta.max_key = t2.max_key > ta.max_key ? t2.max_key : ta.max_key;
+        ta.committed += t2.committed;
+        ta.emitted += t2.emitted;
+        ta.dropped += t2.dropped;
+        ta.ties += t2.ties;
+        ta.dties += t2.dties;
+        ta.appended += t2.appended;
       }
       PHASE(6);
     }
-    __syncthreads();
-    // ---- recycle rows [tb_clean, tb_hi): pages back to the ring, heads cleared
-    {
-      // rows listed above (flagged pages)
-      uint32_t mine = 0;
+  }
+  __syncthreads();
+  // ---- recycle: the pages of rows [tb_clean, tb_hi) go onto the block's own
+  // page stack (what does not fit: to the global ring), heads are cleared
+  {
+    const uint32_t have = sh.ax.pgc_have;
+    const uint32_t rem = have - (sh.ax.pgc_take < have ? sh.ax.pgc_take : have);
+    uint32_t mine = 0;
+    if (!W.redist)
       for (uint32_t i = tid; i < npg; i += NTHREADS)
         if (sh.pg_cnt[i] & PG_FREE_FLAG) mine++;
-      uint32_t pos = 0;
-      if (mine) pos = atomicAdd(&sh.nfree, mine);
-      __syncthreads();
-      if (tid == 0 && sh.nfree)
-        sh.free_base = atomicAdd(&c.acc->free_tail, (unsigned long long)sh.nfree);
-      __syncthreads();
+    uint32_t pos = 0;
+    if (mine) pos = atomicAdd(&sh.nfree, mine);
+    __syncthreads();
+    const uint32_t nfree = sh.nfree;
+    const uint32_t room = SIMIAN_BC - rem;             // free pages the stack still takes
+    const uint32_t over = nfree > room ? nfree - room : 0; // the rest goes to the ring
+    uint32_t cnt = rem + (nfree - over);                   // stack height after recycling
+    // low stack: take pages from the ring for the next window (one atomic)
+    const uint32_t need = (cnt < SIMIAN_BC_LOW) ? SIMIAN_BC_FILL - cnt : 0u;
+    if (tid == 0) {
+      if (over) sh.free_base = atomicAdd(&c.acc->free_tail, (unsigned long long)over);
+      if (need) sh.ring_base = atomicAdd(&c.acc->alloc_head, (unsigned long long)need);
+    }
+    if (over || need) __syncthreads();
+    if (!W.redist) {
       for (uint32_t i = tid; i < npg; i += NTHREADS)
-        if (sh.pg_cnt[i] & PG_FREE_FLAG)
-          c.free_ring[(sh.free_base + pos++) % c.n_pages] = sh.pg_id[i];
+        if (sh.pg_cnt[i] & PG_FREE_FLAG) {
+          uint32_t k = pos++;
+          if (k < nfree - over)
+            sh.ax.pgc[rem + k] = sh.pg_id[i];
+          else
+            c.free_ring[(sh.free_base + (k - (nfree - over))) % c.n_pages] = sh.pg_id[i];
+        }
       if (tid < ncell - 1) {
         long long tb = W.tb_lo + tid;
         c.cell_state[(uint32_t)(tb & (long long)c.ring_mask) * c.n_blocks + b] = CELL_EMPTY;
@@ -1184,40 +1453,54 @@ __global__ void __launch_bounds__(NTHREADS, SIMIAN_MINBLOCKS)
         free_cell(c, (uint32_t)(tb & (long long)c.ring_mask) * c.n_blocks + b);
       }
     }
+    if (need) {
+      // ring slots beyond alloc_limit are not valid yet: take only what is
+      unsigned long long lim = W.alloc_limit, base = sh.ring_base;
+      uint32_t okn = base >= lim ? 0u : (lim - base < need ? (uint32_t)(lim - base) : need);
+      if ((uint32_t)tid < okn) sh.ax.pgc[cnt + tid] = c.free_ring[(base + tid) % c.n_pages];
+      if (tid == 0 && okn < need)
+        atomicAdd(&c.acc->leaked_pages, (unsigned long long)(need - okn));
+      cnt += okn;
+    }
+    __syncthreads();
+    if (tid < (int)cnt) c.bcache[(size_t)b * SIMIAN_BC + tid] = sh.ax.pgc[tid];
+    if (tid == 0) c.bcount[b] = cnt;
   }
 
   PHASE(7);
-  // ---- K1: CTA reduction of the accumulators, one atomic each per CTA
-  for (int o = 16; o; o >>= 1) {
-    unsigned long long x = __shfl_xor_sync(0xffffffffu, ta.min_key, o);
-    ta.min_key = x < ta.min_key ? x : ta.min_key;
-    unsigned long long y = __shfl_xor_sync(0xffffffffu, ta.max_key, o);
-    ta.max_key = y > ta.max_key ? y : ta.max_key;
-    ta.committed += __shfl_xor_sync(0xffffffffu, ta.committed, o);
-    ta.emitted += __shfl_xor_sync(0xffffffffu, ta.emitted, o);
-    ta.dropped += __shfl_xor_sync(0xffffffffu, ta.dropped, o);
-    ta.ties += __shfl_xor_sync(0xffffffffu, ta.ties, o);
-    ta.dties += __shfl_xor_sync(0xffffffffu, ta.dties, o);
+  // ---- K1: CTA reduction of the accumulators into this CTA's BlockPart
+  {
+    unsigned long long mn = warp_min_u64(ta.min_key), mx = warp_max_u64(ta.max_key);
+    uint32_t s0 = __reduce_add_sync(0xffffffffu, ta.committed);
+    uint32_t s1 = __reduce_add_sync(0xffffffffu, ta.emitted);
+    uint32_t s2 = __reduce_add_sync(0xffffffffu, ta.dropped);
+    uint32_t s3 = __reduce_add_sync(0xffffffffu, ta.ties);
+    uint32_t s4 = __reduce_add_sync(0xffffffffu, ta.dties);
+    uint32_t s5 = __reduce_add_sync(0xffffffffu, ta.appended);
+    if (lane == 0) {
+      if (mn != SIMIAN_KEY_NONE) atomicMin(&sh.min_key, mn);
+      if (mx) atomicMax(&sh.max_key, mx);
+      if (s0) atomicAdd(&sh.committed, s0);
+      if (s1) atomicAdd(&sh.emitted, s1);
+      if (s2) atomicAdd(&sh.dropped, s2);
+      if (s3) atomicAdd(&sh.ties, s3);
+      if (s4) atomicAdd(&sh.dties, s4);
+      if (s5) atomicAdd(&sh.appended, s5);
+    }
   }
-  if (lane == 0) {
-    if (ta.min_key != SIMIAN_KEY_NONE) atomicMin(&sh.min_key, ta.min_key);
-    if (ta.max_key) atomicMax(&sh.max_key, ta.max_key);
-    if (ta.committed) atomicAdd(&sh.committed, ta.committed);
-    if (ta.emitted) atomicAdd(&sh.emitted, ta.emitted);
-    if (ta.dropped) atomicAdd(&sh.dropped, ta.dropped);
-    if (ta.ties) atomicAdd(&sh.ties, ta.ties);
-    if (ta.dties) atomicAdd(&sh.dties, ta.dties);
-  }
-  append_ctx_flush(c, sh.ax); // contains __syncthreads()
+  __syncthreads();
   if (tid == 0) {
-    DevAcc *a = c.acc;
-    if (sh.min_key != SIMIAN_KEY_NONE) atomicMin(&a->min_key, sh.min_key);
-    if (sh.max_key) atomicMax(&a->max_key, sh.max_key);
-    if (sh.committed) atomicAdd(&a->committed, (unsigned long long)sh.committed);
-    if (sh.emitted) atomicAdd(&a->emitted, (unsigned long long)sh.emitted);
-    if (sh.dropped) atomicAdd(&a->dropped, (unsigned long long)sh.dropped);
-    if (sh.ties) atomicAdd(&a->ties, (unsigned long long)sh.ties);
-    if (sh.dties) atomicAdd(&a->dist_ties, (unsigned long long)sh.dties);
+    BlockPart *p = &c.part[b];
+    p->min_key = sh.min_key;
+    p->max_key = sh.max_key;
+    p->committed = sh.committed;
+    p->emitted = sh.emitted;
+    p->dropped = sh.dropped;
+    p->ties = sh.ties;
+    p->dties = sh.dties;
+    p->appended = sh.appended;
+    p->far_appends = sh.ax.far_appends;
+    p->page_allocs = sh.ax.page_allocs;
   }
   PHASE(8);
   if (!fuse_advance) return;
@@ -1228,6 +1511,7 @@ __global__ void __launch_bounds__(NTHREADS, SIMIAN_MINBLOCKS)
   __syncthreads();
   if (!sh.is_last) return;
   __threadfence();
+  reduce_parts(c, sh);
   WinState *Wn = &c.win[(win_ix + 1u) & 1u];
   if (W.redist) {
     setup_next_window(c, W, Wn, W.gmin, 0.0, true);
@@ -1248,6 +1532,7 @@ __global__ void __launch_bounds__(NTHREADS) k_local_min(const __grid_constant__ 
   WindowShared &sh = *reinterpret_cast<WindowShared *>(smem_raw);
   const WinState &W = c.win[win_ix & 1u];
   unsigned long long cand, far;
+  if (!W.done) reduce_parts(c, sh); // the BlockParts of this window's k_window launch
   if (W.redist || W.done) {
     cand = far = SIMIAN_KEY_NONE;
   } else {
