@@ -30,6 +30,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 BYTES_PER_EVENT = 96  # 32 read + 32 write + 16 + 16 state
+# dram__bytes_read.sum + dram__bytes_write.sum of one steady-state k_window launch
+# (config 2, ~1.68 M committed events): profiles/r1_j_k_window_ncu_full.csv
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 89337600 + 59158272
 
 
 def load_peaks():
@@ -302,9 +305,15 @@ def main():
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH if world == 1 else None,
+                     "algorithmic_bytes_per_launch": BYTES_PER_EVENT * (events // max(windows, 1)),
                      "kernel": "k_window", "peak_kind": peak_kind,
-                     "bytes_per_event": BYTES_PER_EVENT},
+                     "bytes_per_event": BYTES_PER_EVENT,
+                     "note": "achieved = committed events/s per GPU x 96 B over the whole "
+                             "timed window loop (k_window is >99% of it); traffic = "
+                             "dram read+write bytes of one steady-state k_window launch, "
+                             "ncu --set full, profiles/r1_j_k_window_ncu_full.csv"},
     }
     if e2e is not None:
         line["e2e"] = e2e

@@ -23,7 +23,7 @@
 #define SIMIAN_THREADS 256 // threads per CTA of the window kernel
 #endif
 #ifndef SIMIAN_PAGE
-#define SIMIAN_PAGE 64 // records per page (2 KB)
+#define SIMIAN_PAGE 128 // records per page (4 KB)
 #endif
 #ifndef SIMIAN_REFS
 #define SIMIAN_REFS (4 * SIMIAN_THREADS) // due events a CTA holds on chip per pass

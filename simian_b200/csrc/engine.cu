@@ -66,7 +66,7 @@ struct simian_engine {
   // options
   uint64_t seed = 1;
   double bucket_width = 0;
-  uint32_t ring = 2048;
+  uint32_t ring = 1024;
   uint64_t pool_events = 0, outbox_events = 0;
   int launch_batch = 16, tie_check = 1, force_sequential = 0;
   // model
