@@ -176,6 +176,29 @@ int simian_window_local_min(simian_engine *e, void **devMinVec);
  * globalMinLeft > endTime (simian.js:119)                                    */
 int simian_window_advance(simian_engine *e, int *done);
 int simian_run_end(simian_engine *e, simian_stats *out);
+
+/* ---- device-driven exchange: peers' outboxes mapped over NVLink ----------
+ * Replaces sendAndCount + alltoallSum + probe/recv (mpi.cpp:418-476,318-362)
+ * without a host round trip: each rank publishes CUDA-IPC handles of its
+ * (double-buffered) outbox, maps its peers', and after the window's
+ * allreduce(MIN) (mpi.cpp:380 -- it also orders the exchange) PULLS the
+ * records staged for it straight out of the peers' memory into its calendar.
+ * Per window: simian_window_process, simian_window_local_min, allreduce(MIN),
+ * simian_window_pull, simian_window_advance_async; simian_poll once per batch
+ * of windows.  One process per GPU, all GPUs on one NVLink/NVSwitch box.      */
+/* allocate the HBM layout and replay schedService now (idempotent)          */
+int simian_setup(simian_engine *e);
+/* blob == NULL: *written = blob size.  Otherwise fills the blob to publish. */
+int simian_ipc_export(simian_engine *e, void *blob, uint64_t blobBytes, uint64_t *written);
+int simian_ipc_import(simian_engine *e, int peerRank, const void *blob, uint64_t blobBytes);
+int simian_window_pull(simian_engine *e);
+/* device address of the two doubles simian_window_local_min writes           */
+int simian_minvec_ptr(simian_engine *e, void **devMinVec);
+/* simian_window_advance without the host read-back                          */
+int simian_window_advance_async(simian_engine *e);
+/* device flags -> host: sticky error as return value, *done (simian.js:119) */
+int simian_poll(simian_engine *e, int *done);
+
 /* stream the engine launches on (a cudaStream_t); pass torch's current
  * stream so collectives and kernels are ordered                             */
 int simian_set_stream(simian_engine *e, void *cudaStream);

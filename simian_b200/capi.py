@@ -73,6 +73,13 @@ SIGNATURES = {
     "simian_window_local_min": (_i, [_vp, C.POINTER(_vp)]),
     "simian_window_advance": (_i, [_vp, C.POINTER(_i)]),
     "simian_run_end": (_i, [_vp, C.POINTER(Stats)]),
+    "simian_setup": (_i, [_vp]),
+    "simian_ipc_export": (_i, [_vp, _vp, _u64, C.POINTER(_u64)]),
+    "simian_ipc_import": (_i, [_vp, _i, _vp, _u64]),
+    "simian_window_pull": (_i, [_vp]),
+    "simian_window_advance_async": (_i, [_vp]),
+    "simian_poll": (_i, [_vp, C.POINTER(_i)]),
+    "simian_minvec_ptr": (_i, [_vp, C.POINTER(_vp)]),
     "simian_set_stream": (_i, [_vp, _vp]),
     "simian_read_counts": (_i, [_vp, _cp, _u32, _u32, _vp]),
     "simian_read_trace_hashes": (_i, [_vp, _cp, _u32, _u32, _vp]),
@@ -215,9 +222,41 @@ class Engine:
         self._ck(self.L.simian_window_local_min(self.h, C.byref(ptr)))
         return ptr.value
 
+    def window_local_min_ptr(self):
+        """device address of the {minLeft, min far time} pair (no launch)"""
+        ptr = _vp()
+        self._ck(self.L.simian_minvec_ptr(self.h, C.byref(ptr)))
+        return ptr.value
+
     def window_advance(self):
         done = _i()
         self._ck(self.L.simian_window_advance(self.h, C.byref(done)))
+        return bool(done.value)
+
+    # ---- device-driven exchange over peer memory -------------------------
+    def setup(self):
+        self._ck(self.L.simian_setup(self.h))
+
+    def ipc_export(self):
+        n = _u64()
+        self._ck(self.L.simian_ipc_export(self.h, None, 0, C.byref(n)))
+        buf = C.create_string_buffer(n.value)
+        self._ck(self.L.simian_ipc_export(self.h, buf, n.value, C.byref(n)))
+        return buf.raw[:n.value]
+
+    def ipc_import(self, peer_rank, blob):
+        buf = C.create_string_buffer(bytes(blob), len(blob))
+        self._ck(self.L.simian_ipc_import(self.h, peer_rank, buf, len(blob)))
+
+    def window_pull(self):
+        self._ck(self.L.simian_window_pull(self.h))
+
+    def window_advance_async(self):
+        self._ck(self.L.simian_window_advance_async(self.h))
+
+    def poll(self):
+        done = _i()
+        self._ck(self.L.simian_poll(self.h, C.byref(done)))
         return bool(done.value)
 
     def run_end(self, check=True):

@@ -41,6 +41,7 @@
 #define SIMIAN_MINBLOCKS 3 // __launch_bounds__ min CTAs/SM of the window kernel
 #endif
 
+#define SIMIAN_MAX_RANKS 16 // GPUs of one box (peer memory over NVLink)
 #define SIMIAN_MAX_CLASSES 8
 #define SIMIAN_MAX_SERVICES 32
 #define SIMIAN_MAX_CELLS 96 // sub-buckets one window may span
@@ -77,7 +78,7 @@ struct WinState {
   uint32_t done;          // gmin > endTime                  simian.js:119
   uint32_t redist;        // this launch is a far-list redistribution pass
   uint32_t far_row;       // which of the two far rows receives appends
-  uint32_t pad_;
+  uint32_t parity;        // window index & 1: which outbox this window fills
   unsigned long long alloc_limit; // pages allocatable in this launch
 };
 
@@ -135,8 +136,12 @@ struct DevCfg {
   // steady-state windows never touch the global free ring
   uint32_t *bcache; // [n_blocks][SIMIAN_BC]
   uint32_t *bcount; // [n_blocks]
-  // cross-GPU staging (size > 1)
-  simian_event_t *outbox; // [size][outbox_cap]
-  uint32_t *outbox_count; // [size]
+  // cross-GPU staging (size > 1), double buffered by window parity: the
+  // records window k sends stay readable by the peers until window k+2
+  simian_event_t *outbox; // [2][size][outbox_cap]
+  uint32_t *outbox_count; // [2][size]
   uint32_t outbox_cap, pad1_;
+  // the peers' outboxes, mapped over NVLink (CUDA IPC); null = not connected
+  const simian_event_t *peer_outbox[SIMIAN_MAX_RANKS];
+  const uint32_t *peer_count[SIMIAN_MAX_RANKS];
 };

@@ -94,6 +94,7 @@ struct simian_engine {
   uint32_t *h_counts = nullptr;
   std::chrono::steady_clock::time_point t_begin;
   size_t smem_bytes = sizeof(WindowShared);
+  void *peer_map[2 * SIMIAN_MAX_RANKS] = {}; // cudaIpcOpenMemHandle results
 
   int fail(int code, const std::string &m) {
     if (!err_code) {
@@ -237,8 +238,8 @@ int setup(simian_engine *e) {
   if (e->size > 1) {
     uint64_t cap = e->outbox_events ? e->outbox_events : 2 * local_initial / g + 65536;
     c.outbox_cap = (uint32_t)cap;
-    if (dev_alloc(e, &c.outbox, (size_t)e->size * cap)) return e->err_code;
-    if (dev_alloc(e, &c.outbox_count, (size_t)e->size)) return e->err_code;
+    if (dev_alloc(e, &c.outbox, 2 * (size_t)e->size * cap)) return e->err_code;
+    if (dev_alloc(e, &c.outbox_count, 2 * (size_t)e->size)) return e->err_code;
   }
   CK(cudaMallocHost((void **)&e->h_acc, sizeof(DevAcc)));
   CK(cudaMallocHost((void **)&e->h_win, 2 * sizeof(WinState)));
@@ -378,6 +379,8 @@ void simian_destroy(simian_engine *e) {
   if (!e) return;
   cudaSetDevice(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
+  for (void *p : e->peer_map)
+    if (p) cudaIpcCloseMemHandle(p);
   for (void *p : e->allocs) cudaFree(p);
   for (SchedOp &op : e->ops)
     if (op.d_recs) cudaFree(op.d_recs);
@@ -568,6 +571,88 @@ int simian_construct_entities(simian_engine *e, const char *className, const cha
   return 0;
 }
 
+int simian_setup(simian_engine *e) {
+  if (e->err_code) return e->err_code;
+  CK(cudaSetDevice(e->device));
+  return setup(e);
+}
+
+namespace {
+struct IpcBlob { // what one rank publishes to its peers
+  cudaIpcMemHandle_t outbox, count;
+  uint64_t cap;
+  int32_t rank, size;
+};
+} // namespace
+
+int simian_ipc_export(simian_engine *e, void *blob, uint64_t blobBytes, uint64_t *written) {
+  if (written) *written = sizeof(IpcBlob);
+  if (!blob) return 0; // size query
+  if (blobBytes < sizeof(IpcBlob)) return e->fail(SIMIAN_ERR_BAD_ARGUMENT, "ipc blob too small");
+  if (e->size < 2) return e->fail(SIMIAN_ERR_BAD_ARGUMENT, "ipc export needs size > 1");
+  int rc = simian_setup(e);
+  if (rc) return rc;
+  IpcBlob b;
+  memset(&b, 0, sizeof b);
+  CK(cudaIpcGetMemHandle(&b.outbox, e->cfg.outbox));
+  CK(cudaIpcGetMemHandle(&b.count, e->cfg.outbox_count));
+  b.cap = e->cfg.outbox_cap;
+  b.rank = e->rank;
+  b.size = e->size;
+  memcpy(blob, &b, sizeof b);
+  return 0;
+}
+
+int simian_ipc_import(simian_engine *e, int peerRank, const void *blob, uint64_t blobBytes) {
+  if (blobBytes < sizeof(IpcBlob) || peerRank < 0 || peerRank >= e->size ||
+      peerRank >= SIMIAN_MAX_RANKS || peerRank == e->rank)
+    return e->fail(SIMIAN_ERR_BAD_ARGUMENT, "bad ipc import");
+  int rc = simian_setup(e);
+  if (rc) return rc;
+  IpcBlob b;
+  memcpy(&b, blob, sizeof b);
+  if (b.rank != peerRank || b.size != e->size || b.cap != e->cfg.outbox_cap)
+    return e->fail(SIMIAN_ERR_BAD_ARGUMENT, "ipc blob does not match this world");
+  void *po = nullptr, *pc = nullptr;
+  CK(cudaIpcOpenMemHandle(&po, b.outbox, cudaIpcMemLazyEnablePeerAccess));
+  CK(cudaIpcOpenMemHandle(&pc, b.count, cudaIpcMemLazyEnablePeerAccess));
+  e->peer_map[2 * peerRank] = po;
+  e->peer_map[2 * peerRank + 1] = pc;
+  e->cfg.peer_outbox[peerRank] = (const simian_event_t *)po;
+  e->cfg.peer_count[peerRank] = (const uint32_t *)pc;
+  return 0;
+}
+
+int simian_window_pull(simian_engine *e) {
+  if (e->size < 2) return 0;
+  const uint32_t bpp = 148; // blocks per peer
+  k_pull<<<(e->size - 1) * bpp, 256, 0, e->stream>>>(e->cfg, e->win_ix, bpp);
+  CK(cudaGetLastError());
+  e->launches++;
+  return 0;
+}
+
+int simian_minvec_ptr(simian_engine *e, void **devMinVec) {
+  if (!e->set_up) return e->fail(SIMIAN_ERR_BAD_ARGUMENT, "call simian_setup first");
+  *devMinVec = (void *)e->cfg.acc->minvec;
+  return 0;
+}
+
+int simian_window_advance_async(simian_engine *e) {
+  k_advance<<<1, NTHREADS, 0, e->stream>>>(e->cfg, e->win_ix);
+  CK(cudaGetLastError());
+  e->launches++;
+  e->win_ix++;
+  return 0;
+}
+
+int simian_poll(simian_engine *e, int *done) {
+  int rc = poll(e);
+  if (rc) return rc;
+  if (done) *done = (int)e->h_win[e->win_ix & 1u].done;
+  return 0;
+}
+
 int simian_run_begin(simian_engine *e) {
   if (e->err_code) return e->err_code;
   CK(cudaSetDevice(e->device));
@@ -592,12 +677,13 @@ int simian_window_outbox(simian_engine *e, uint32_t *hostCounts, void **devOutbo
   if (e->size == 1) {
     hostCounts[0] = 0;
   } else {
-    CK(cudaMemcpyAsync(e->h_counts, e->cfg.outbox_count, sizeof(uint32_t) * (size_t)e->size,
-                       cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(e->h_counts, e->cfg.outbox_count + (size_t)(e->win_ix & 1u) * e->size,
+                       sizeof(uint32_t) * (size_t)e->size, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     memcpy(hostCounts, e->h_counts, sizeof(uint32_t) * (size_t)e->size);
   }
-  if (devOutbox) *devOutbox = e->cfg.outbox;
+  if (devOutbox) // the outbox this window filled (double buffered by window parity)
+    *devOutbox = e->cfg.outbox + (size_t)(e->win_ix & 1u) * e->size * e->cfg.outbox_cap;
   if (cap) *cap = e->cfg.outbox_cap;
   return 0;
 }

@@ -340,12 +340,12 @@ __global__ void k_init(const __grid_constant__ DevCfg c, uint32_t n_cells) {
     w.done = 0;
     w.redist = 0;
     w.far_row = 0;
-    w.pad_ = 0;
+    w.parity = 0;
     w.alloc_limit = c.n_pages;
     c.win[0] = w;
     c.win[1] = w;
   }
-  for (size_t j = i; j < (size_t)c.size; j += stride)
+  for (size_t j = i; j < 2 * (size_t)c.size; j += stride)
     if (c.outbox_count) c.outbox_count[j] = 0;
 }
 
@@ -424,6 +424,42 @@ __global__ void k_ingest(const __grid_constant__ DevCfg c, const simian_event_t 
     __syncthreads();
     if (threadIdx.x == 0 && smin != SIMIAN_KEY_NONE) atomicMin(&c.acc->min_key, smin);
   }
+  append_ctx_flush(c, ax);
+}
+
+// Cross-GPU exchange, receiver side (simian.js:138-142): the records the peers
+// staged for this rank in window win_ix are read straight out of THEIR
+// outboxes over NVLink (coalesced 32-byte records) and appended to the local
+// calendar -- alltoallv and ingest in one kernel, counts never visit the host.
+// Runs after the window's allreduce, which orders it behind every peer's
+// k_window.  gridDim.x = (size - 1) * blocks_per_peer.
+__global__ void k_pull(const __grid_constant__ DevCfg c, uint32_t win_ix, uint32_t blocks_per_peer) {
+  __shared__ AppendCtx ax;
+  append_ctx_init(ax);
+  __syncthreads();
+  const WinState &W = c.win[win_ix & 1u];
+  uint32_t napp = 0;
+  if (!W.done) {
+    const uint32_t q = blockIdx.x / blocks_per_peer, sub = blockIdx.x % blocks_per_peer;
+    const uint32_t p = ((uint32_t)c.rank + 1u + q) % (uint32_t)c.size; // never c.rank
+    const uint32_t box = W.parity * (uint32_t)c.size + (uint32_t)c.rank;
+    const uint32_t *pc = c.peer_count[p];
+    const simian_event_t *src = c.peer_outbox[p];
+    if (pc && src) {
+      uint32_t n = *(const volatile uint32_t *)(pc + box);
+      n = n < c.outbox_cap ? n : c.outbox_cap;
+      src += (size_t)box * c.outbox_cap;
+      for (uint32_t idx = sub * blockDim.x + threadIdx.x; idx < n;
+           idx += blocks_per_peer * blockDim.x) {
+        RecBits r = ld_rec(src + idx);
+        append_local(c, ax, W.tb_clean, W.far_row, W.alloc_limit, r);
+        napp++;
+      }
+    } else {
+      set_error(c, SIMIAN_ERR_BAD_ARGUMENT); // peers were never connected
+    }
+  }
+  appended_flush(c, napp);
   append_ctx_flush(c, ax);
 }
 
@@ -578,18 +614,23 @@ struct DevCtx {
     if (rank == c.rank) { // entity.js:64
       put_local(r);
     } else { // entity.js:66: staged for the per-window exchange
+      // the receiver has not seen it when the LBTS candidates are reduced:
+      // the sender's candidate covers it (simian.js:143-144)
+      unsigned long long tk = simian_time_key(time);
+      ta.min_key = tk < ta.min_key ? tk : ta.min_key;
       // warp-aggregated claim: one atomic per (warp, destination rank)
+      const uint32_t box = W.parity * (uint32_t)c.size + (uint32_t)rank;
       unsigned act = __activemask();
       unsigned peers = __match_any_sync(act, rank);
       int leader = __ffs(peers) - 1, ln = threadIdx.x & 31;
       uint32_t i = 0;
-      if (ln == leader) i = atomicAdd(&c.outbox_count[rank], (uint32_t)__popc(peers));
+      if (ln == leader) i = atomicAdd(&c.outbox_count[box], (uint32_t)__popc(peers));
       i = __shfl_sync(peers, i, leader) + __popc(peers & ((1u << ln) - 1u));
       if (i >= c.outbox_cap) {
         set_error(c, SIMIAN_ERR_OUTBOX_FULL);
         return;
       }
-      st_rec(c.outbox + ((size_t)rank * c.outbox_cap + i), r);
+      st_rec(c.outbox + ((size_t)box * c.outbox_cap + i), r);
     }
   }
 };
@@ -1083,6 +1124,7 @@ __device__ void setup_next_window(const DevCfg &c, const WinState &W, WinState *
     a->min_key = SIMIAN_KEY_NONE;
     a->ticket = 0;
     a->window_index++;
+    nw.parity = a->window_index & 1u;
   }
   __syncthreads();
   // snapshot the heads of row tb_hi: appends of the next launch may target it
@@ -1557,8 +1599,11 @@ __global__ void __launch_bounds__(NTHREADS) k_advance(const __grid_constant__ De
     setup_next_window(c, W, Wn, W.gmin, 0.0, true);
   else
     setup_next_window(c, W, Wn, c.acc->minvec[0], c.acc->minvec[1], false);
-  // outbox counters were consumed by the exchange
-  if (threadIdx.x < c.size && c.outbox_count) c.outbox_count[threadIdx.x] = 0;
+  // The outbox the NEXT window fills was sent two windows ago; every peer has
+  // read it (its pull precedes the allreduce this advance follows).  The one
+  // just sent may still be being read: it is left alone.
+  if (threadIdx.x < c.size && c.outbox_count)
+    c.outbox_count[((W.parity ^ 1u) * (uint32_t)c.size) + threadIdx.x] = 0;
 }
 
 // first window: gmin = startTime even when the queue is empty (simian.js:118)
@@ -1577,6 +1622,7 @@ __global__ void __launch_bounds__(NTHREADS) k_begin(const __grid_constant__ DevC
   if (threadIdx.x == 0) {
     c.acc->windows = 0;
     c.acc->window_index = 0;
+    c.win[0].parity = 0;
   }
 }
 

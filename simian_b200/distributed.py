@@ -44,7 +44,7 @@ class GpuRankEngine:
     def __init__(self, engine, device):
         self.e, self.device = engine, torch.device(device)
         self.size = engine.size
-        self._outbox = None
+        self._outbox = {}  # device address -> view (double buffered by window parity)
         self._minvec = None
         # engine kernels and NCCL collectives are ordered on torch's stream
         engine.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
@@ -57,10 +57,11 @@ class GpuRankEngine:
 
     def outbox(self):
         counts, ptr, cap = self.e.window_outbox()  # D2H of `size` counters
-        if self._outbox is None:
-            self._outbox = _device_view(ptr, self.size * cap * 32, torch.int64,
-                                        self.device).view(self.size, cap, 4)
-        return counts, [self._outbox[p, :counts[p]] for p in range(self.size)]
+        box = self._outbox.get(ptr)
+        if box is None:
+            box = self._outbox[ptr] = _device_view(
+                ptr, self.size * cap * 32, torch.int64, self.device).view(self.size, cap, 4)
+        return counts, [box[p, :counts[p]] for p in range(self.size)]
 
     def new_inbox(self, n):
         if getattr(self, "_inbox", None) is None or self._inbox.shape[0] < n:
@@ -83,6 +84,51 @@ class GpuRankEngine:
 
     def end(self):
         return self.e.run_end()
+
+
+def connect_peers(engine, rank, size, group=None):
+    """Publish this rank's outbox (CUDA-IPC handles) and map every peer's:
+    one all_gather of a ~150-byte blob per rank, once per engine."""
+    blob = engine.ipc_export()
+    blobs = [None] * size
+    dist.all_gather_object(blobs, blob, group=group)
+    for p in range(size):
+        if p != rank:
+            engine.ipc_import(p, blobs[p])
+
+
+def drive_windows_p2p(engine, rank, size, device, group=None, batch=8,
+                      max_batch=64):
+    """Simian.run for size > 1 (simian.js:118-149) with the device-driven
+    exchange: no host round trip inside a batch of windows.  Per window:
+      k_window           events below the bound; remote sends -> outbox[parity],
+                         and into this rank's LBTS candidate       :122-134, entity.js:66
+      k_local_min        minLeft candidate                          :143
+      all_reduce(MIN)    {minLeft, min far time}; orders the pull   :144 (mpi.cpp:380)
+      k_pull             peers' outboxes -> local calendar, NVLink  :137-142
+      k_advance          next window                                :119-120
+    The host polls `done`/error once per batch; windows launched past the end
+    are no-ops on every rank (the window sequence is global)."""
+    engine.set_stream(torch.cuda.current_stream(device).cuda_stream)
+    connect_peers(engine, rank, size, group)
+    engine.run_begin()
+    ptr = engine.window_local_min_ptr()
+    mv = _device_view(ptr, 16, torch.float64, device)
+    windows = 0
+    while True:
+        for _ in range(batch):
+            engine.window_process()
+            engine.window_local_min()
+            dist.all_reduce(mv, op=dist.ReduceOp.MIN, group=group)
+            engine.window_pull()
+            engine.window_advance_async()
+            windows += 1
+        if engine.poll():
+            break
+        batch = min(2 * batch, max_batch)
+    st = engine.run_end()
+    st["driver_windows"] = windows
+    return st
 
 
 def _exchange(rank, size, sends, recv_counts, inbox, group=None):
@@ -142,17 +188,22 @@ def drive_windows(eng, rank, size, group=None, max_windows=None):
     return st
 
 
-def run_distributed_phold(cfg, rank, world, local_rank, seed=1, **options):
+def run_distributed_phold(cfg, rank, world, local_rank, seed=1, driver="p2p",
+                          **options):
     """One PHOLD step on `world` GPUs (one process each); returns this rank's
-    stats.  cfg: a dict of simian_b200.workloads.CONFIGS shape."""
+    stats.  cfg: a dict of simian_b200.workloads.CONFIGS shape.  driver: "p2p"
+    (device-driven pull over NVLink) or "nccl" (host-driven alltoallv)."""
     from . import capi
     from .workloads import build_phold
     device = torch.device("cuda", local_rank)
+    options = dict(options)
     e = capi.Engine("phold", 0.0, cfg["end"], cfg["min_delay"], rank=rank,
                     size=world, device=local_rank, seed=seed, **options)
     build_phold(e, cfg["n"], cfg["per_entity"], cfg["lookahead"], cfg["p_remote"],
                 cfg.get("lam", 1.0), cfg["mode"], cfg["groups"])
-    eng = GpuRankEngine(e, device)
-    st = drive_windows(eng, rank, world)
+    if driver == "p2p":
+        st = drive_windows_p2p(e, rank, world, device)
+    else:
+        st = drive_windows(GpuRankEngine(e, device), rank, world)
     st["_engine"] = e
     return st

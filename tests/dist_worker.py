@@ -44,6 +44,9 @@ def main():
     ap.add_argument("--engine", default="oracle")
     ap.add_argument("--backend", default="gloo")
     ap.add_argument("--cases", default="ross,other_group,uniform_sparse")
+    ap.add_argument("--driver", default="p2p", choices=["p2p", "nccl"],
+                    help="cuda engine: device-driven pull over NVLink, or the "
+                         "host-driven NCCL alltoallv")
     a = ap.parse_args()
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -79,7 +82,11 @@ def main():
             e = capi.Engine("dist", 0.0, c["end"], c["min_delay"], rank=rank,
                             size=world, device=local, seed=c["seed"], **opts)
             build(e, c, world)
-            st = drive_windows(GpuRankEngine(e, "cuda:%d" % local), rank, world)
+            if a.driver == "p2p":
+                from simian_b200.distributed import drive_windows_p2p
+                st = drive_windows_p2p(e, rank, world, torch.device("cuda", local))
+            else:
+                st = drive_windows(GpuRankEngine(e, "cuda:%d" % local), rank, world)
             cnt = e.read_counts("Node", c["n"])
             h = e.read_trace_hashes("Node", c["n"])
             base = e.base_rank("Node")
