@@ -214,6 +214,10 @@ int simian_read_trace_hashes(simian_engine *e, const char *className,
 int simian_read_state(simian_engine *e, const char *className, uint32_t first,
                       uint32_t count, void *out);
 
+/* Engines of the same shape reuse the HBM of destroyed ones (process-wide
+ * cache, SIMIAN_B200_CACHE_GB, default 64); this returns it all to CUDA.     */
+void simian_trim_cache(void);
+
 /* diagnostic only: summed SM cycles spent in each phase of the window kernel
  * by all CTAs (zeros unless the library was built with SIMIAN_PROFILE_PHASES) */
 int simian_debug_phase_cycles(simian_engine *e, uint64_t *out12);

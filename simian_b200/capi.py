@@ -85,6 +85,7 @@ SIGNATURES = {
     "simian_read_trace_hashes": (_i, [_vp, _cp, _u32, _u32, _vp]),
     "simian_read_state": (_i, [_vp, _cp, _u32, _u32, _vp]),
     "simian_debug_phase_cycles": (_i, [_vp, C.POINTER(_u64)]),
+    "simian_trim_cache": (None, []),
 }
 
 _lib = None

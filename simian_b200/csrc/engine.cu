@@ -12,15 +12,87 @@
 
 #include <chrono>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
 #include "../../include/simian_b200.h"
 #include "kernels.cuh"
 
+extern "C" void simian_trim_cache(void);
+
 namespace {
 
 std::string g_create_error;
+
+// Process-wide cache of device allocations, keyed by (device, bytes): an engine
+// built with the same shape as a destroyed one reuses its HBM instead of paying
+// cudaFree + cudaMalloc of multi-GB pools (tens of ms per engine).  Everything
+// an engine reads is (re)initialised by k_init / setup, never assumed zero.
+struct CacheKey {
+  int device;
+  size_t bytes;
+  bool operator<(const CacheKey &o) const {
+    return device != o.device ? device < o.device : bytes < o.bytes;
+  }
+};
+std::multimap<CacheKey, void *> g_alloc_cache;
+size_t g_alloc_cache_bytes = 0;
+std::mutex g_alloc_cache_mu;
+
+// pinned host bounce buffers for result read-back (pageable D2H runs at a few GB/s)
+std::multimap<size_t, void *> g_pinned_cache;
+
+void *pinned_take(size_t bytes) {
+  {
+    std::lock_guard<std::mutex> g(g_alloc_cache_mu);
+    auto it = g_pinned_cache.lower_bound(bytes);
+    if (it != g_pinned_cache.end() && it->first <= 2 * bytes + 4096) {
+      void *p = it->second;
+      g_pinned_cache.erase(it);
+      return p;
+    }
+  }
+  void *p = nullptr;
+  if (cudaMallocHost(&p, bytes) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+
+void pinned_give(size_t bytes, void *p) {
+  std::lock_guard<std::mutex> g(g_alloc_cache_mu);
+  if (g_pinned_cache.size() >= 8) {
+    cudaFreeHost(p);
+    return;
+  }
+  g_pinned_cache.emplace(bytes, p);
+}
+
+size_t alloc_cache_limit() {
+  const char *s = getenv("SIMIAN_B200_CACHE_GB");
+  double gb = s ? atof(s) : 64.0;
+  return (size_t)(gb * 1073741824.0);
+}
+
+void *cache_take(int device, size_t bytes) {
+  std::lock_guard<std::mutex> g(g_alloc_cache_mu);
+  auto it = g_alloc_cache.find(CacheKey{device, bytes});
+  if (it == g_alloc_cache.end()) return nullptr;
+  void *p = it->second;
+  g_alloc_cache.erase(it);
+  g_alloc_cache_bytes -= bytes;
+  return p;
+}
+
+bool cache_give(int device, size_t bytes, void *p) {
+  std::lock_guard<std::mutex> g(g_alloc_cache_mu);
+  if (g_alloc_cache_bytes + bytes > alloc_cache_limit()) return false;
+  g_alloc_cache.emplace(CacheKey{device, bytes}, p);
+  g_alloc_cache_bytes += bytes;
+  return true;
+}
 
 struct HostClass {
   std::string name;
@@ -44,7 +116,8 @@ struct SchedOp { // a recorded schedService call, replayed on the device at run
   int cls = 0;
   uint32_t first = 0, count = 0, repeat = 0, seq_base = 0;
   simian_event_t *d_recs = nullptr; // kind 1: uploaded at call time
-  uint64_t n_recs = 0;
+  uint64_t n_recs = 0, d_bytes = 0;
+  bool ingested = false; // kind 1: already in the calendar (early layout)
 };
 
 int builtin_fn_by_name(const char *n) {
@@ -78,13 +151,16 @@ struct simian_engine {
   uint64_t initial_events = 0;
   // state
   bool running = false, set_up = false, stepping = false;
+  bool laid_out = false;            // HBM layout allocated + initialised (may precede set_up)
+  uint64_t laid_out_initial = 0;    // initial_events the pool was sized for
+  cudaStream_t copy_stream = nullptr; // H2D of simian_sched_events, overlapped with ingest
   std::string err;
   int err_code = 0;
   // device
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   DevCfg cfg;
-  std::vector<void *> allocs;
+  std::vector<std::pair<void *, size_t>> allocs;
   uint32_t win_ix = 0;
   uint64_t launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -133,10 +209,18 @@ const char *status_text(int code) {
 
 template <class T>
 int dev_alloc(simian_engine *e, T **p, size_t n) {
-  void *q = nullptr;
   size_t bytes = (n ? n : 1) * sizeof(T);
-  CK(cudaMalloc(&q, bytes));
-  e->allocs.push_back(q);
+  bytes = (bytes + 511) & ~(size_t)511;
+  void *q = cache_take(e->device, bytes);
+  if (!q) {
+    cudaError_t ce = cudaMalloc(&q, bytes);
+    if (ce != cudaSuccess) { // make room: drop the cache and retry once
+      cudaGetLastError();
+      simian_trim_cache();
+      CK(cudaMalloc(&q, bytes));
+    }
+  }
+  e->allocs.push_back({q, bytes});
   *p = (T *)q;
   return 0;
 }
@@ -146,8 +230,25 @@ uint32_t local_count(uint32_t count, uint32_t rank_off, uint32_t g) {
 }
 
 // allocate the HBM layout, initialise it, replay schedService, set up window 0
-int setup(simian_engine *e) {
-  if (e->set_up) return 0;
+// give everything the layout allocated back (a model-changing call arrived
+// after an early layout): the scheduled records are still on the device
+void teardown_layout(simian_engine *e) {
+  if (!e->laid_out || e->set_up) return;
+  cudaStreamSynchronize(e->stream);
+  for (auto &a : e->allocs)
+    if (!cache_give(e->device, a.second, a.first)) cudaFree(a.first);
+  e->allocs.clear();
+  for (SchedOp &op : e->ops) op.ingested = false;
+  for (HostClass &h : e->classes) {
+    h.d_state = nullptr;
+    h.d_params = nullptr;
+  }
+  e->d_digest = nullptr;
+  e->laid_out = false;
+}
+
+int setup_layout(simian_engine *e) {
+  if (e->laid_out) return 0;
   DevCfg &c = e->cfg;
   memset(&c, 0, sizeof c);
   c.start = e->start;
@@ -241,17 +342,40 @@ int setup(simian_engine *e) {
     if (dev_alloc(e, &c.outbox, 2 * (size_t)e->size * cap)) return e->err_code;
     if (dev_alloc(e, &c.outbox_count, 2 * (size_t)e->size)) return e->err_code;
   }
-  CK(cudaMallocHost((void **)&e->h_acc, sizeof(DevAcc)));
-  CK(cudaMallocHost((void **)&e->h_win, 2 * sizeof(WinState)));
-  CK(cudaMallocHost((void **)&e->h_counts, sizeof(uint32_t) * (size_t)e->size));
-  CK(cudaEventCreate(&e->ev0));
-  CK(cudaEventCreate(&e->ev1));
+  if (!e->h_acc) {
+    CK(cudaMallocHost((void **)&e->h_acc, sizeof(DevAcc)));
+    CK(cudaMallocHost((void **)&e->h_win, 2 * sizeof(WinState)));
+    CK(cudaMallocHost((void **)&e->h_counts, sizeof(uint32_t) * (size_t)e->size));
+    CK(cudaEventCreate(&e->ev0));
+    CK(cudaEventCreate(&e->ev1));
+  }
   CK(cudaFuncSetAttribute(k_window, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           (int)e->smem_bytes));
   CK(cudaFuncSetAttribute(k_local_min, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           (int)e->smem_bytes));
   k_init<<<296, 256, 0, e->stream>>>(c, (uint32_t)n_cells);
   CK(cudaGetLastError());
+  e->laid_out = true;
+  e->laid_out_initial = e->initial_events;
+  return 0;
+}
+
+int ingest_records(simian_engine *e, const simian_event_t *d, uint64_t n, cudaStream_t st) {
+  if (!n) return 0;
+  int grid = (int)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184);
+  k_ingest<<<grid, 256, 0, st>>>(e->cfg, d, n, 1, 0, 0);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// allocate the HBM layout, initialise it, replay schedService, set up window 0
+int setup(simian_engine *e) {
+  if (e->set_up) return 0;
+  // an early layout sized for far fewer initial events than were scheduled since
+  if (e->laid_out && e->initial_events > 2 * e->laid_out_initial + 1024) teardown_layout(e);
+  int rc = setup_layout(e);
+  if (rc) return rc;
+  DevCfg &c = e->cfg;
   // replay schedService (simian.js:170-190)
   for (SchedOp &op : e->ops) {
     if (op.kind == 0) {
@@ -268,12 +392,9 @@ int setup(simian_engine *e) {
       k_construct<<<grid, 128, 0, e->stream>>>(c, op.cls, op.handler);
       CK(cudaGetLastError());
     } else if (op.n_recs) {
-      uint64_t n = op.n_recs;
-      int grid = (int)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184);
-      k_ingest<<<grid, 256, 0, e->stream>>>(c, op.d_recs, n, 1, 0, 0);
-      CK(cudaGetLastError());
+      if (!op.ingested && ingest_records(e, op.d_recs, op.n_recs, e->stream)) return e->err_code;
       CK(cudaStreamSynchronize(e->stream));
-      CK(cudaFree(op.d_recs));
+      if (!cache_give(e->device, op.d_bytes, op.d_recs)) cudaFree(op.d_recs);
       op.d_recs = nullptr;
     }
   }
@@ -335,6 +456,21 @@ extern "C" {
 
 const char *simian_version(void) { return "simian-b200 0.1.0 (sm_100a)"; }
 
+void simian_trim_cache(void) {
+  std::lock_guard<std::mutex> g(g_alloc_cache_mu);
+  int cur = 0;
+  cudaGetDevice(&cur);
+  for (auto &kv : g_alloc_cache) {
+    cudaSetDevice(kv.first.device);
+    cudaFree(kv.second);
+  }
+  cudaSetDevice(cur);
+  g_alloc_cache.clear();
+  g_alloc_cache_bytes = 0;
+  for (auto &kv : g_pinned_cache) cudaFreeHost(kv.second);
+  g_pinned_cache.clear();
+}
+
 double simian_hash_name(const char *str) { // hash.js:21-26
   double res = 5381;
   size_t i = strlen(str);
@@ -381,9 +517,11 @@ void simian_destroy(simian_engine *e) {
   if (e->stream) cudaStreamSynchronize(e->stream);
   for (void *p : e->peer_map)
     if (p) cudaIpcCloseMemHandle(p);
-  for (void *p : e->allocs) cudaFree(p);
+  for (auto &a : e->allocs)
+    if (!cache_give(e->device, a.second, a.first)) cudaFree(a.first);
   for (SchedOp &op : e->ops)
-    if (op.d_recs) cudaFree(op.d_recs);
+    if (op.d_recs && !cache_give(e->device, op.d_bytes, op.d_recs)) cudaFree(op.d_recs);
+  if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
   if (e->h_acc) cudaFreeHost(e->h_acc);
   if (e->h_win) cudaFreeHost(e->h_win);
   if (e->h_counts) cudaFreeHost(e->h_counts);
@@ -399,6 +537,7 @@ const char *simian_last_error(simian_engine *e) {
 
 int simian_set_option(simian_engine *e, const char *key, double v) {
   if (e->set_up) return e->fail(SIMIAN_ERR_RUNNING, "options must be set before the first run");
+  teardown_layout(e);
   std::string k = key;
   if (k == "seed") e->seed = (uint64_t)v;
   else if (k == "bucket_width") e->bucket_width = v;
@@ -423,6 +562,7 @@ int simian_define_class(simian_engine *e, const char *className, uint32_t stateB
   auto it = e->class_ix.find(className);
   if (it != e->class_ix.end()) return it->second;
   if (e->set_up) return -e->fail(SIMIAN_ERR_RUNNING, "classes must be defined before the first run");
+  teardown_layout(e);
   if ((int)e->classes.size() >= SIMIAN_MAX_CLASSES || (stateBytes & 7u))
     return -e->fail(SIMIAN_ERR_BAD_ARGUMENT, "too many classes or stateBytes not a multiple of 8");
   HostClass h;
@@ -441,6 +581,7 @@ int simian_set_class_params(simian_engine *e, const char *className, const void 
   auto it = e->class_ix.find(className);
   if (it == e->class_ix.end()) return e->fail(SIMIAN_ERR_UNKNOWN_NAME, "unknown class");
   if (e->set_up) return e->fail(SIMIAN_ERR_RUNNING, "parameters must be set before the first run");
+  teardown_layout(e);
   e->classes[it->second].params.assign((const uint8_t *)p, (const uint8_t *)p + bytes);
   return 0;
 }
@@ -449,6 +590,7 @@ int simian_add_entities(simian_engine *e, const char *className, uint32_t firstN
                         uint32_t count, const void *initState) {
   if (e->running || e->set_up) // simian.js:215
     return e->fail(SIMIAN_ERR_RUNNING, status_text(SIMIAN_ERR_RUNNING));
+  teardown_layout(e);
   int ci = simian_define_class(e, className, 0);
   if (ci < 0) return -ci;
   HostClass &h = e->classes[ci];
@@ -480,6 +622,7 @@ int simian_intern_service(simian_engine *e, const char *serviceName) {
 int simian_attach_service(simian_engine *e, const char *className, const char *serviceName,
                           const char *deviceFnName) {
   if (e->set_up) return e->fail(SIMIAN_ERR_RUNNING, "services must be attached before the first run");
+  teardown_layout(e);
   int ci = simian_define_class(e, className, 0);
   if (ci < 0) return -ci;
   int fn = builtin_fn_by_name(deviceFnName);
@@ -539,18 +682,41 @@ int simian_sched_service(simian_engine *e, double time, const char *serviceName,
 int simian_sched_events(simian_engine *e, const simian_event_t *ev, uint64_t n) {
   if (e->set_up) return e->fail(SIMIAN_ERR_RUNNING, "schedService after the run started");
   if (!n) return 0;
-  // straight host -> HBM copy from the caller's buffer (fast when it is pinned);
-  // ids and times are validated on the device when the records are ingested
+  // Host -> HBM from the caller's buffer (fast when it is pinned), in chunks on
+  // a copy stream.  When the model is already described (entities added) the
+  // HBM layout is allocated now and every chunk goes into the calendar while
+  // the next one is still crossing PCIe; otherwise the records wait on the
+  // device for simian_run.  Ids and times are validated by the ingest kernel.
   CK(cudaSetDevice(e->device));
   SchedOp op;
   op.kind = 1;
   op.n_recs = n;
-  CK(cudaMalloc((void **)&op.d_recs, n * sizeof(simian_event_t)));
-  CK(cudaMemcpyAsync(op.d_recs, ev, n * sizeof(simian_event_t), cudaMemcpyHostToDevice,
-                     e->stream));
-  CK(cudaStreamSynchronize(e->stream)); // the host buffer is only borrowed
-  e->ops.push_back(op);
+  op.d_bytes = (n * sizeof(simian_event_t) + 511) & ~(size_t)511;
+  op.d_recs = (simian_event_t *)cache_take(e->device, op.d_bytes);
+  if (!op.d_recs) CK(cudaMalloc((void **)&op.d_recs, op.d_bytes));
   e->initial_events += n;
+  bool early = !e->classes.empty() && e->n_ids > 0 && e->err_code == 0;
+  if (early && setup_layout(e)) return e->err_code;
+  if (!e->copy_stream) CK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+  const uint64_t chunk = 1ull << 20; // records (32 MB)
+  std::vector<cudaEvent_t> evs;
+  for (uint64_t off = 0; off < n; off += chunk) {
+    uint64_t m = n - off < chunk ? n - off : chunk;
+    CK(cudaMemcpyAsync(op.d_recs + off, ev + off, m * sizeof(simian_event_t),
+                       cudaMemcpyHostToDevice, e->copy_stream));
+    if (early) {
+      cudaEvent_t done;
+      CK(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+      CK(cudaEventRecord(done, e->copy_stream));
+      CK(cudaStreamWaitEvent(e->stream, done, 0));
+      evs.push_back(done);
+      if (ingest_records(e, op.d_recs + off, m, e->stream)) return e->err_code;
+    }
+  }
+  CK(cudaStreamSynchronize(e->copy_stream)); // the host buffer is only borrowed
+  for (cudaEvent_t d : evs) cudaEventDestroy(d);
+  op.ingested = early;
+  e->ops.push_back(op);
   return 0;
 }
 
@@ -757,15 +923,32 @@ static int read_core(simian_engine *e, const char *className, uint32_t first, ui
   if (!e->set_up) return e->fail(SIMIAN_ERR_BAD_ARGUMENT, "nothing has run yet");
   HostClass &h = e->classes[it->second];
   if ((uint64_t)first + count > h.count) return e->fail(SIMIAN_ERR_UNKNOWN_NAME, "no such entity");
-  std::vector<EntityCore> loc(h.n_local);
+  if (!h.n_local || !count) return 0;
   CK(cudaSetDevice(e->device));
-  CK(cudaMemcpy(loc.data(), e->cfg.core + h.slot_base, sizeof(EntityCore) * (size_t)h.n_local,
-                cudaMemcpyDeviceToHost));
+  // one field of the 16-byte entity records, contiguous, then ONE copy
+  unsigned long long *tmp = nullptr;
+  if (dev_alloc(e, &tmp, (size_t)h.n_local)) return e->err_code;
+  k_gather_core<<<592, 256, 0, e->stream>>>(e->cfg, h.slot_base, h.n_local, which, tmp);
+  CK(cudaGetLastError());
   uint32_t g = (uint32_t)e->size;
-  for (uint32_t j = 0; j < h.n_local; j++) {
-    uint32_t num = j * g + h.rank_off;
-    if (num >= first && num < first + count) out[num - first] = which ? loc[j].hash : loc[j].count;
+  size_t pin_bytes = sizeof(uint64_t) * (size_t)h.n_local;
+  uint64_t *loc = (uint64_t *)pinned_take(pin_bytes);
+  if (!loc) return e->fail(SIMIAN_ERR_CUDA, "cudaMallocHost failed");
+  CK(cudaMemcpyAsync(loc, tmp, pin_bytes, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  if (g == 1) { // local index == num
+    memcpy(out, loc + first, sizeof(uint64_t) * (size_t)count);
+  } else {
+    for (uint32_t j = 0; j < h.n_local; j++) {
+      uint32_t num = j * g + h.rank_off;
+      if (num >= first && num < first + count) out[num - first] = loc[j];
+    }
   }
+  pinned_give(pin_bytes, loc);
+  // hand the scratch buffer straight back to the allocation cache
+  auto a = e->allocs.back();
+  e->allocs.pop_back();
+  if (!cache_give(e->device, a.second, a.first)) cudaFree(a.first);
   return 0;
 }
 

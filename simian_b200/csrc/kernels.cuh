@@ -1628,6 +1628,17 @@ __global__ void __launch_bounds__(NTHREADS) k_begin(const __grid_constant__ DevC
 
 // ------------------------------------------------------------- reductions --
 
+// one field of the entity records of a class, contiguous (result read-back)
+__global__ void k_gather_core(const __grid_constant__ DevCfg c, uint32_t slot_base, uint32_t n,
+                              int which, unsigned long long *out) {
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+    EntityCore st = c.core[slot_base + j];
+    out[j] = which ? st.hash : st.count;
+  }
+}
+
+
 // digest = sum of simian_digest_term over local entities; state checksum
 __global__ void k_digest(const __grid_constant__ DevCfg c, unsigned long long *out /* [2] */) {
   unsigned long long dg = 0, sc = 0;
