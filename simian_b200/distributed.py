@@ -98,7 +98,7 @@ def connect_peers(engine, rank, size, group=None):
 
 
 def drive_windows_p2p(engine, rank, size, device, group=None, batch=8,
-                      max_batch=64):
+                      max_batch=64, profile=False):
     """Simian.run for size > 1 (simian.js:118-149) with the device-driven
     exchange: no host round trip inside a batch of windows.  Per window:
       k_window           events below the bound; remote sends -> outbox[parity],
@@ -115,19 +115,45 @@ def drive_windows_p2p(engine, rank, size, device, group=None, batch=8,
     ptr = engine.window_local_min_ptr()
     mv = _device_view(ptr, 16, torch.float64, device)
     windows = 0
+    marks = []  # profile: CUDA events around every step of every window
+
+    def mark():
+        if profile:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            marks.append(ev)
+
     while True:
         for _ in range(batch):
+            mark()
             engine.window_process()
+            mark()
             engine.window_local_min()
+            mark()
             dist.all_reduce(mv, op=dist.ReduceOp.MIN, group=group)
+            mark()
             engine.window_pull()
+            mark()
             engine.window_advance_async()
+            mark()
             windows += 1
         if engine.poll():
             break
         batch = min(2 * batch, max_batch)
     st = engine.run_end()
     st["driver_windows"] = windows
+    if profile:
+        names = ["k_window", "k_local_min", "all_reduce", "k_pull", "k_advance"]
+        tot = dict.fromkeys(names, 0.0)
+        first = dict.fromkeys(names, 0.0)
+        for w in range(windows):
+            for j, nm in enumerate(names):
+                ms = marks[6 * w + j].elapsed_time(marks[6 * w + j + 1])
+                tot[nm] += ms
+                if w == 0:
+                    first[nm] = ms
+        st["phase_ms"] = tot
+        st["phase_ms_first_window"] = first
     return st
 
 

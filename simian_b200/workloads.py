@@ -46,6 +46,12 @@ CONFIGS = {
     "config3_phold_16m": dict(n=1 << 24, per_entity=16, min_delay=0.1,
                               lookahead=0.1, p_remote=0.5,
                               mode=PHOLD_OTHER_GROUP, groups=8, end=5.0),
+    # LANL PDES benchmark V8-style: per-event compute over
+    # an 8-KB list per entity, geometric hot-spot destinations
+    "config4_lanl": dict(kind="lanl", n_ent=1 << 20, s_ent=100.0, q_avg=1.0,
+                         p_receive=1e-5, m_ent=1000.0, ops_ent=1000.0,
+                         ops_sigma=0.1, cache_friendliness=0.5, end_time=100.0,
+                         min_delay=1.0, time_bins=10),
     "config5_phold_4m_small_lookahead": dict(
         n=1 << 22, per_entity=16, min_delay=0.01, lookahead=0.01, p_remote=0.1,
         mode=PHOLD_ROSS_REMOTE, groups=1, end=2.0),

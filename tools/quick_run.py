@@ -12,13 +12,24 @@ scale = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
 opts = dict(kv.split("=") for kv in sys.argv[3:])
 opts = {k: float(v) for k, v in opts.items()}
 c = dict(CONFIGS[name])
-c["n"] = max(c["groups"], int(c["n"] * scale) // c["groups"] * c["groups"])
-for rep in range(3):
-    e = capi.Engine(name, 0.0, c["end"], c["min_delay"], seed=1, **opts)
-    build_phold(e, c["n"], c["per_entity"], c["lookahead"], c["p_remote"], 1.0,
-                c["mode"], c["groups"])
-    st = e.run()
-    e.close()
+if c.get("kind") == "lanl":
+    from simian_b200.workloads import build_lanl, lanl_engine_end  # noqa: E402
+    c.pop("kind")
+    c["n_ent"] = max(1, int(c["n_ent"] * scale))
+    for rep in range(2):
+        e = capi.Engine(name, 0.0, lanl_engine_end(c["end_time"], c["min_delay"]),
+                        c["min_delay"], seed=1, **opts)
+        build_lanl(e, **c)
+        st = e.run()
+        e.close()
+else:
+    c["n"] = max(c["groups"], int(c["n"] * scale) // c["groups"] * c["groups"])
+    for rep in range(3):
+        e = capi.Engine(name, 0.0, c["end"], c["min_delay"], seed=1, **opts)
+        build_phold(e, c["n"], c["per_entity"], c["lookahead"], c["p_remote"], 1.0,
+                    c["mode"], c["groups"])
+        st = e.run()
+        e.close()
 print("%s x%g %s: events %d windows %d dev %.2f ms  %.3e ev/s  pages %d far %d redist %d" % (
     name, scale, opts, st["total_events"], st["windows"], st["device_seconds"] * 1e3,
     st["total_events"] / st["device_seconds"], st["pages_allocated"], st["far_appends"],
