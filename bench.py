@@ -307,7 +307,8 @@ def main():
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak,
                      "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH if world == 1 else None,
-                     "algorithmic_bytes_per_launch": BYTES_PER_EVENT * (events // max(windows, 1)),
+                     "algorithmic_bytes_per_launch":
+                         BYTES_PER_EVENT * (events // max(windows, 1) // world),
                      "kernel": "k_window", "peak_kind": peak_kind,
                      "bytes_per_event": BYTES_PER_EVENT,
                      "note": "achieved = committed events/s per GPU x 96 B over the whole "

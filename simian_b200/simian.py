@@ -207,10 +207,9 @@ class Simian(object):
                 self.stats = self._h.run()
             else:
                 import torch
-                from .distributed import GpuRankEngine, drive_windows
+                from .distributed import drive_windows_p2p
                 dev = torch.device("cuda", torch.cuda.current_device())
-                self.stats = drive_windows(GpuRankEngine(self._h, dev), self.rank,
-                                           self.size)
+                self.stats = drive_windows_p2p(self._h, self.rank, self.size, dev)
         finally:
             self.running = False
         self.now = self.stats["last_time"]
