@@ -101,31 +101,47 @@ def workload_for(n_gpus, scale):
     return c
 
 
-def cpu_baseline_sample(cfg, seconds_hint=12.0):
+def host_cores():
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    return max(1, min(n, 64))
+
+
+def cpu_baseline_sample(cfg, cores=None):
     """The oracle (CPU port of the reference algorithm) on a bounded sample of
-    the same workload shape: fewer entities, same per-entity load and delays."""
+    the same workload shape -- fewer entities, same per-entity load and delays --
+    run the way the reference runs on a multi-core host: one rank per core
+    (mpirun -np <cores>; here the ranks of one oracle world on host threads,
+    meeting at the window's two collectives, simian.js:136-145)."""
     from oracle import oracle as om
     from simian_b200.workloads import build_phold
     om.build()
-    n = min(cfg["n"], 1 << 17)
-    n = max(cfg["groups"], n // cfg["groups"] * cfg["groups"])
-    o = om.Oracle("cpu_baseline", 0.0, cfg["end"], cfg["min_delay"], seed=1)
+    cores = cores or host_cores()
+    groups = max(cfg["groups"], 1)
+    n = min(cfg["n"], (1 << 16) * max(1, min(cores, 8)))
+    unit = groups * cores // __import__("math").gcd(groups, cores)
+    n = max(unit, n // unit * unit)
+    o = om.Oracle("cpu_baseline", 0.0, cfg["end"], cfg["min_delay"], size=cores,
+                  seed=1, threads=cores)
     build_phold(o, n, cfg["per_entity"], cfg["lookahead"], cfg["p_remote"], 1.0,
                 cfg["mode"], cfg["groups"])
     st = o.run()
     o.close()
     return {"value": st["total_events"] / st["run_seconds"], "unit": "events/s",
-            "cores": 1, "kind": "port",
+            "cores": cores, "kind": "port",
             "sample": "%d entities x%d events, endTime %g: %d events in %.2f s "
-                      "(oracle/simian_oracle.cpp, 1 thread)" % (
+                      "(oracle/simian_oracle.cpp, %d ranks on %d host threads)" % (
                           n, cfg["per_entity"], cfg["end"], st["total_events"],
-                          st["run_seconds"]),
+                          st["run_seconds"], cores, cores),
             "events": st["total_events"], "seconds": st["run_seconds"]}
 
 
 def run_reference(args, rank, world):
     """--impl reference: the reference's CPU implementation of the path (the
-    oracle port; SimianJS/Lua cannot run in this image) on the host cores."""
+    oracle port; SimianJS/Lua cannot run in this image) on all host cores, one
+    rank per core as under mpirun."""
     if rank != 0:
         return
     cfg = workload_for(args.gpus, args.scale)
@@ -144,7 +160,7 @@ def run_reference(args, rank, world):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": cfg["label"], "sample": last["sample"]},
-            "cpu_baseline": {"value": v, "unit": "events/s", "cores": 1,
+            "cpu_baseline": {"value": v, "unit": "events/s", "cores": last["cores"],
                              "kind": "port", "sample": last["sample"]},
             "e2e": {"value": v, "unit": "events/s", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0}}

@@ -78,6 +78,7 @@ def lib():
             "oracle_sched_service_bulk": (i, [vp, d, cp, u64, cp, u32, u32, u32]),
             "oracle_sched_events": (i, [vp, vp, u64]),
             "oracle_construct_entities": (i, [vp, cp, cp]),
+            "oracle_set_threads": (None, [vp, i]),
             "oracle_run": (i, [vp, C.POINTER(OracleStats)]),
             "oracle_read_counts": (i, [vp, cp, vp]),
             "oracle_read_trace_hashes": (i, [vp, cp, vp]),
@@ -121,11 +122,13 @@ class OracleError(RuntimeError):
 class Oracle:
     """Low-level handle; same method names as simian_b200.capi.Engine."""
 
-    def __init__(self, name, start, end, min_delay, size=1, tie_mode=0, seed=1):
+    def __init__(self, name, start, end, min_delay, size=1, tie_mode=0, seed=1,
+                 threads=1):
         self.L = lib()
         self.h = self.L.oracle_create(name.encode(), start, end, min_delay,
                                       size, tie_mode)
         self.L.oracle_set_seed(self.h, seed)
+        self.L.oracle_set_threads(self.h, threads)
         self.classes = {}
 
     def close(self):

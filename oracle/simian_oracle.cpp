@@ -38,8 +38,10 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
 #include <chrono>
 #include <map>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -155,6 +157,10 @@ struct Rank {
   EventQ q;
   double now;
   uint64_t numEvents = 0, synchEvents = 0;
+  /* parity statistics, per rank so that ranks can run on separate threads */
+  uint64_t ties = 0, dist_ties = 0, emitted = 0, dropped = 0;
+  int error = 0;
+  std::string errmsg;
   std::vector<uint32_t> sndCounts;                 /* mpi.cpp:21 */
   std::vector<std::vector<simian_event_t>> outbox; /* MPI_Send per event */
 };
@@ -180,6 +186,22 @@ struct World {
   /* stats */
   uint64_t windows = 0, ties = 0, dist_ties = 0, emitted = 0, dropped = 0;
   double last_time = 0, run_seconds = 0;
+  int threads = 1; /* ranks stepped concurrently by oracle_run (1 = sequential) */
+
+  /* fold the per-rank statistics into the world's (after a window / at the end) */
+  void gather_rank_stats() {
+    for (auto &r : ranks) {
+      ties += r.ties;
+      dist_ties += r.dist_ties;
+      emitted += r.emitted;
+      dropped += r.dropped;
+      r.ties = r.dist_ties = r.emitted = r.dropped = 0;
+      if (r.error && !error) {
+        error = r.error;
+        errmsg = r.errmsg;
+      }
+    }
+  }
 
   uint16_t intern_service(const char *s) {
     auto it = service_ix.find(s);
@@ -232,15 +254,16 @@ struct HostCtx {
   void req_service(double offset, uint16_t service, uint64_t data, uint32_t rx) {
     uint32_t k = n_emit++;
     if ((rx != SIMIAN_NULL_ENTITY) && (offset < w->minDelay)) { /* :41 */
-      if (!w->running)
-        w->fail(ORACLE_ERR_IDLE_SEND, "Cannot send an event when Simian is idle");
-      else
-        w->fail(ORACLE_ERR_LOOKAHEAD, "attempted to send with too little delay");
+      if (!r->error) {
+        r->error = w->running ? ORACLE_ERR_LOOKAHEAD : ORACLE_ERR_IDLE_SEND;
+        r->errmsg = w->running ? "attempted to send with too little delay"
+                               : "Cannot send an event when Simian is idle";
+      }
       return;
     }
     double time = r->now + offset; /* :47 */
     if (time > w->endTime) {       /* :48 */
-      w->dropped++;
+      r->dropped++;
       return;
     }
     if (rx == SIMIAN_NULL_ENTITY) rx = self; /* :50-51 */
@@ -252,7 +275,7 @@ struct HostCtx {
     e.flags = 0;
     e.seq = simian_emit_seq(commit_idx, k);
     e.data = data;
-    w->emitted++;
+    r->emitted++;
     int recvRank = w->offset_rank(rx); /* :62 */
     int myRank = (int)(r - &w->ranks[0]);
     if (recvRank == myRank)
@@ -270,16 +293,19 @@ void dispatch(World *w, Rank *r, const simian_event_t &ev) {
   /* `entity[curEvent.name]` (simian.js:130) */
   auto it = c.fn_of_service.find(ev.handler);
   if (it == c.fn_of_service.end()) {
-    w->fail(ORACLE_ERR_UNKNOWN, "service is not a function");
+    if (!r->error) {
+      r->error = ORACLE_ERR_UNKNOWN;
+      r->errmsg = "service is not a function";
+    }
     return;
   }
   /* commit bookkeeping: what parity is measured on */
   uint64_t idx = w->count[gid];
   Last &l = w->last[gid];
   if (l.valid && l.time == ev.time) {
-    w->ties++;
+    r->ties++;
     if (l.handler != ev.handler || l.src != ev.src || l.data != ev.data)
-      w->dist_ties++;
+      r->dist_ties++;
   }
   l.time = ev.time;
   l.handler = ev.handler;
@@ -316,7 +342,10 @@ void dispatch(World *w, Rank *r, const simian_event_t &ev) {
       simian_lanl_finish(ctx);
       break;
     default:
-      w->fail(ORACLE_ERR_UNKNOWN, "unknown builtin function");
+      if (!r->error) {
+        r->error = ORACLE_ERR_UNKNOWN;
+        r->errmsg = "unknown builtin function";
+      }
   }
 }
 
@@ -377,6 +406,8 @@ void *oracle_create(const char *simName, double startTime, double endTime,
 
 void oracle_destroy(void *o) { delete (World *)o; }
 void oracle_set_seed(void *o, uint64_t seed) { ((World *)o)->seed = seed; }
+/* host threads oracle_run steps the ranks on (default 1) */
+void oracle_set_threads(void *o, int n) { ((World *)o)->threads = n < 1 ? 1 : n; }
 const char *oracle_last_error(void *o) { return ((World *)o)->errmsg.c_str(); }
 
 int oracle_define_class(void *o, const char *className, uint32_t stateBytes) {
@@ -507,6 +538,7 @@ int oracle_construct_entities(void *o, const char *className, const char *fnName
       default:
         w->fail(ORACLE_ERR_UNKNOWN, "unknown constructor function");
     }
+    w->gather_rank_stats();
   }
   return w->error;
 }
@@ -535,7 +567,62 @@ int oracle_sched_events(void *o, const simian_event_t *ev, uint64_t n) {
   return 0;
 }
 
-/* Simian.run  (simian.js:99-168), all `size` ranks in lock-step */
+/* simian.js:122-134 for one rank: drain every event below the epoch */
+static void rank_window(World *w, Rank &r, double epoch) {
+  while (r.q.length() && (r.q.peek() < epoch) && !r.error) { /* :122 */
+    simian_event_t cur = r.q.pop();                          /* :123 */
+    if (r.now > cur.time) {                                  /* :124-125 */
+      r.error = ORACLE_ERR_OUT_OF_ORDER;
+      r.errmsg = "Out of order event";
+      break;
+    }
+    r.now = cur.time; /* :126 */
+    dispatch(w, &r, cur);
+    if (r.error) break;
+    r.numEvents++; /* :133 */
+  }
+}
+
+/* simian.js:137-143 for one rank: receive what the others sent, then minLeft.
+ * alltoallSum (mpi.cpp:418-437) then probe/recv/push (:138-142).
+ * MPI_Probe(ANY_SOURCE) order is unspecified in the reference; here: by source
+ * rank, then send order.                                                     */
+static double rank_exchange(World *w, int ri) {
+  Rank &r = w->ranks[ri];
+  for (int src = 0; src < w->size; src++) {
+    std::vector<simian_event_t> &box = w->ranks[src].outbox[ri];
+    for (const simian_event_t &e : box) r.q.push(e);
+    box.clear();
+    w->ranks[src].sndCounts[ri] = 0;
+  }
+  r.synchEvents += 2;                               /* :145 */
+  return r.q.length() ? r.q.peek() : w->infTime;   /* :143 */
+}
+
+namespace {
+/* sense-reversing barrier for the rank threads (the MPI collectives of the
+ * reference are the synchronisation points of its ranks, mpi.cpp:422,380) */
+struct SpinBarrier {
+  std::atomic<int> count{0}, sense{0};
+  int n = 1;
+  void wait() {
+    int s = sense.load(std::memory_order_acquire);
+    if (count.fetch_add(1, std::memory_order_acq_rel) == n - 1) {
+      count.store(0, std::memory_order_relaxed);
+      sense.store(s ^ 1, std::memory_order_release);
+    } else {
+      int spins = 0;
+      while (sense.load(std::memory_order_acquire) == s)
+        if (++spins > 2000) std::this_thread::yield();
+    }
+  }
+};
+}  // namespace
+
+/* Simian.run  (simian.js:99-168).  All `size` ranks in lock-step: one after the
+ * other on the calling thread (threads == 1), or -- like the reference under
+ * mpirun, one process per core -- on `threads` host threads, ranks dealt
+ * round-robin, meeting at the two collectives of the window.  Same results.  */
 int oracle_run(void *o, oracle_stats *out) {
   World *w = (World *)o;
   auto t0 = std::chrono::steady_clock::now();
@@ -544,47 +631,57 @@ int oracle_run(void *o, oracle_stats *out) {
   const int size = w->size;
   w->running = true;                   /* :117 */
   double globalMinLeft = w->startTime; /* :118 */
-  while (globalMinLeft <= endTime && !w->error) { /* :119 */
-    double epoch = globalMinLeft + minDelay;      /* :120 */
-    w->windows++;
-    for (int ri = 0; ri < size && !w->error; ri++) {
-      Rank &r = w->ranks[ri];
-      while (r.q.length() && (r.q.peek() < epoch)) { /* :122 */
-        simian_event_t cur = r.q.pop();              /* :123 */
-        if (r.now > cur.time) {                      /* :124-125 */
-          w->fail(ORACLE_ERR_OUT_OF_ORDER, "Out of order event");
-          break;
+  int nthreads = w->threads < size ? w->threads : size;
+  if (nthreads <= 1 || size == 1) {
+    while (globalMinLeft <= endTime && !w->error) { /* :119 */
+      double epoch = globalMinLeft + minDelay;      /* :120 */
+      w->windows++;
+      for (int ri = 0; ri < size; ri++) rank_window(w, w->ranks[ri], epoch);
+      w->gather_rank_stats();
+      if (w->error) break;
+      if (size > 1) { /* :136-145 */
+        double gmin = infTime;
+        for (int ri = 0; ri < size; ri++) {
+          double minLeft = rank_exchange(w, ri);
+          if (minLeft < gmin) gmin = minLeft; /* :144 MIN */
         }
-        r.now = cur.time; /* :126 */
-        dispatch(w, &r, cur);
-        if (w->error) break;
-        r.numEvents++; /* :133 */
+        globalMinLeft = gmin;
+      } else {
+        Rank &r = w->ranks[0];
+        globalMinLeft = r.q.length() ? r.q.peek() : infTime; /* :147 */
       }
     }
-    if (size > 1) { /* :136-145 */
-      double gmin = infTime;
-      for (int ri = 0; ri < size; ri++) {
-        Rank &r = w->ranks[ri];
-        /* alltoallSum (mpi.cpp:418-437) then probe/recv/push (:138-142).
-         * MPI_Probe(ANY_SOURCE) order is unspecified in the reference; here:
-         * by source rank, then send order. */
-        for (int src = 0; src < size; src++) {
-          std::vector<simian_event_t> &box = w->ranks[src].outbox[ri];
-          for (const simian_event_t &e : box) r.q.push(e);
-          box.clear();
-          w->ranks[src].sndCounts[ri] = 0;
+  } else {
+    SpinBarrier bar;
+    bar.n = nthreads;
+    std::vector<double> minLeft(size, infTime);
+    std::atomic<int> stop{0};
+    double gml = globalMinLeft;
+    auto worker = [&](int t) {
+      for (;;) {
+        double epoch = gml + minDelay; /* :120 */
+        for (int ri = t; ri < size; ri += nthreads) rank_window(w, w->ranks[ri], epoch);
+        bar.wait(); /* every MPI_Send of the window has been posted */
+        for (int ri = t; ri < size; ri += nthreads) minLeft[ri] = rank_exchange(w, ri);
+        bar.wait(); /* MPI_Allreduce(MIN) */
+        if (t == 0) {
+          w->windows++;
+          w->gather_rank_stats();
+          double gmin = infTime;
+          for (int ri = 0; ri < size; ri++)
+            if (minLeft[ri] < gmin) gmin = minLeft[ri];
+          gml = gmin;
+          if (!(gml <= endTime) || w->error) stop.store(1); /* :119 */
         }
+        bar.wait();
+        if (stop.load()) break;
       }
-      for (int ri = 0; ri < size; ri++) {
-        Rank &r = w->ranks[ri];
-        double minLeft = r.q.length() ? r.q.peek() : infTime; /* :143 */
-        if (minLeft < gmin) gmin = minLeft;                   /* :144 MIN */
-        r.synchEvents += 2;                                   /* :145 */
-      }
-      globalMinLeft = gmin;
-    } else {
-      Rank &r = w->ranks[0];
-      globalMinLeft = r.q.length() ? r.q.peek() : infTime; /* :147 */
+    };
+    if (globalMinLeft <= endTime) {
+      std::vector<std::thread> th;
+      for (int t = 1; t < nthreads; t++) th.emplace_back(worker, t);
+      worker(0);
+      for (auto &x : th) x.join();
     }
   }
   w->running = false;
@@ -668,17 +765,8 @@ int oracle_step_process(void *o, int rank, double globalMinLeft) {
   Rank &r = w->ranks[rank];
   double epoch = globalMinLeft + w->minDelay; /* :120 */
   w->windows++; /* each process steps exactly one rank of its world */
-  while (r.q.length() && (r.q.peek() < epoch) && !w->error) { /* :122 */
-    simian_event_t cur = r.q.pop();
-    if (r.now > cur.time) {
-      w->fail(ORACLE_ERR_OUT_OF_ORDER, "Out of order event");
-      break;
-    }
-    r.now = cur.time;
-    dispatch(w, &r, cur);
-    if (w->error) break;
-    r.numEvents++;
-  }
+  rank_window(w, r, epoch);
+  w->gather_rank_stats();
   return w->error;
 }
 

@@ -287,3 +287,30 @@ def test_oracle_lanl_multi_rank_equals_single_rank(oracle_mod):
         assert out[0]["digest"] == ref[0]["digest"]
         assert out[0]["state_checksum"] == ref[0]["state_checksum"]
         np.testing.assert_array_equal(out[2], ref[2])
+
+
+# ---- ranks on host threads (bench.py --impl reference) -------------------------
+
+@pytest.mark.parametrize("size,threads", [(4, 4), (5, 2), (8, 3)])
+def test_oracle_threaded_ranks_equal_sequential(oracle_mod, size, threads):
+    """oracle_run steps the ranks on host threads exactly like the sequential
+    lock-step loop: same counts, hashes, digest, windows, statistics."""
+    case = dict(name="thr", n=4000, per_entity=8, min_delay=0.1, lookahead=0.1,
+                p_remote=0.5, mode=2, groups=size, end=4.0, seed=3)
+    n = case["n"] // size * size
+    out = []
+    for thr in (1, threads):
+        o = oracle_mod.Oracle("thr", 0.0, case["end"], case["min_delay"], size=size,
+                              seed=case["seed"], threads=thr)
+        from simian_b200.workloads import build_phold
+        build_phold(o, n, case["per_entity"], case["lookahead"], case["p_remote"], 1.0,
+                    case["mode"], size)
+        st = o.run()
+        out.append((st, o.read_counts("Node", n), o.read_trace_hashes("Node", n)))
+    (s1, c1, h1), (s2, c2, h2) = out
+    for k in ("total_events", "windows", "digest", "ties", "distinguishable_ties",
+              "emitted", "dropped_past_end", "synch_events"):
+        assert s1[k] == s2[k], k
+    assert float(s1["last_time"]).hex() == float(s2["last_time"]).hex()
+    np.testing.assert_array_equal(c1, c2)
+    np.testing.assert_array_equal(h1, h2)
