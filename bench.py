@@ -167,19 +167,23 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
-def make_host_events(cfg, torch, np, capi):
+def make_host_events(cfg, torch, np, capi, rank=0, world=1):
     """The initial schedService calls of the model script as POD records in
-    PINNED host memory (phold-noop-noMPI.js:47), seq in call order."""
+    PINNED host memory (phold-noop-noMPI.js:47), seq in call order.  world > 1:
+    the calls this rank's process acts on (only the owner pushes, simian.js:177)."""
     n, per = cfg["n"], cfg["per_entity"]
-    total = n * per
+    base = int(capi.lib().simian_hash_name(b"Node") % world)  # simian.js:192-194
+    ids = np.arange((rank - base) % world, n, world, dtype=np.uint32)
+    total = len(ids) * per
     buf = torch.empty(total * 32, dtype=torch.uint8, pin_memory=True)
     ev = buf.numpy().view(capi.EVENT_DTYPE)
     ev["time"] = 0.0
-    ev["dst"] = np.tile(np.arange(n, dtype=np.uint32), per)
+    ev["dst"] = np.tile(ids, per)
     ev["src"] = capi.NULL_ENTITY
     ev["handler"] = 0
     ev["flags"] = 1
-    ev["seq"] = np.arange(total, dtype=np.uint32)
+    ev["seq"] = (np.repeat(np.arange(per, dtype=np.uint32), len(ids)) * np.uint32(n)
+                 + np.tile(ids, per))
     ev["data"] = 0
     return buf, ev
 
@@ -261,41 +265,54 @@ def main():
         dev_s, events, launches = float(tmax[0]), int(t[1]), int(t[2])
     value = events / dev_s
 
-    # ---- end to end through the C-ABI with host buffers (N=1 form) ----------
+    # ---- end to end through the C-ABI with HOST buffers ----------------------
+    # every step: pinned host records -> simian_sched_events (H2D) -> run ->
+    # per-entity counts + trace hashes of the rank's entities read back (D2H)
     e2e = None
-    if not args.no_e2e and world == 1:
-        buf, ev = make_host_events(cfg, torch, np, capi)
+    if not args.no_e2e:
+        buf, ev = make_host_events(cfg, torch, np, capi, rank, world)
         n = cfg["n"]
 
         def one_step_e2e():
-            e = capi.Engine("bench_e2e", 0.0, cfg["end"], cfg["min_delay"], seed=1,
-                            device=local_rank)
             from simian_b200.workloads import phold_params_blob
+            e = capi.Engine("bench_e2e", 0.0, cfg["end"], cfg["min_delay"], seed=1,
+                            rank=rank, size=world, device=local_rank)
             e.define_class("Node", 0)
             e.add_entities("Node", 0, n)
             e.attach_service("Node", "generate", "phold_generate")
             e.set_class_params("Node", phold_params_blob(
                 0, n, cfg["p_remote"], 1.0, cfg["lookahead"], cfg["mode"], cfg["groups"]))
             e.sched_events(ev)                      # H2D of the step's inputs
-            st = e.run()
+            if world == 1:
+                st = e.run()
+            else:
+                from simian_b200.distributed import drive_windows_p2p
+                st = drive_windows_p2p(e, rank, world, torch.device("cuda", local_rank))
             counts = e.read_counts("Node", n)       # D2H of the step's results
             hashes = e.read_trace_hashes("Node", n)
             e.close()
             return st, counts, hashes
         one_step_e2e()
-        torch.cuda.synchronize()
+        barrier()
         t0 = time.perf_counter()
         ev_e2e = 0
         ksteps = max(1, min(args.steps, 3))
         for _ in range(ksteps):
             st2, counts, hashes = one_step_e2e()
             ev_e2e += st2["total_events"]
-        torch.cuda.synchronize()
+        barrier()
         t_e2e = time.perf_counter() - t0
         assert int(counts.sum()) == st2["total_events"]
+        n_local = len(ev) // cfg["per_entity"]
+        if dist is not None:
+            t = torch.tensor([t_e2e, float(ev_e2e)], dtype=torch.float64, device="cuda")
+            tmax = t.clone()
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            t_e2e, ev_e2e = float(tmax[0]), int(t[1])
         e2e = {"value": ev_e2e / t_e2e, "unit": "events/s",
-               "h2d_bytes_per_step": int(ev.nbytes + 48),
-               "d2h_bytes_per_step": int(counts.nbytes + hashes.nbytes + 160),
+               "h2d_bytes_per_step": int(ev.nbytes + 48) * world,
+               "d2h_bytes_per_step": int(16 * n_local + 160) * world,
                "steps": ksteps, "ms_per_step": 1e3 * t_e2e / ksteps}
 
     if rank != 0:

@@ -183,19 +183,30 @@ int simian_run_end(simian_engine *e, simian_stats *out);
  * (double-buffered) outbox, maps its peers', and after the window's
  * allreduce(MIN) (mpi.cpp:380 -- it also orders the exchange) PULLS the
  * records staged for it straight out of the peers' memory into its calendar.
- * Per window: simian_window_process, simian_window_local_min, allreduce(MIN),
- * simian_window_pull, simian_window_advance_async; simian_poll once per batch
- * of windows.  One process per GPU, all GPUs on one NVLink/NVSwitch box.      */
+ * Per window: simian_window_process, simian_window_publish_min,
+ * simian_window_pull(wait), simian_window_advance_async(fromPeers) -- no
+ * collective library in the loop -- or simian_window_local_min, an external
+ * allreduce(MIN), simian_window_pull(0), simian_window_advance_async(0);
+ * simian_poll once per batch of windows.  One process per GPU, all GPUs on one
+ * NVLink/NVSwitch box.                                                        */
 /* allocate the HBM layout and replay schedService now (idempotent)          */
 int simian_setup(simian_engine *e);
 /* blob == NULL: *written = blob size.  Otherwise fills the blob to publish. */
 int simian_ipc_export(simian_engine *e, void *blob, uint64_t blobBytes, uint64_t *written);
 int simian_ipc_import(simian_engine *e, int peerRank, const void *blob, uint64_t blobBytes);
-int simian_window_pull(simian_engine *e);
+/* waitForPeers != 0: first wait (on the device) until every rank has
+ * published this window's LBTS candidate, i.e. finished its window           */
+int simian_window_pull(simian_engine *e, int waitForPeers);
+/* simian_window_local_min + allreduce(MIN), send half: the candidate is also
+ * written into every peer's exchange slots over NVLink (mpi.cpp:364-390
+ * without a collective library or the host)                                  */
+int simian_window_publish_min(simian_engine *e);
 /* device address of the two doubles simian_window_local_min writes           */
 int simian_minvec_ptr(simian_engine *e, void **devMinVec);
-/* simian_window_advance without the host read-back                          */
-int simian_window_advance_async(simian_engine *e);
+/* simian_window_advance without the host read-back.  minFromPeers != 0: the
+ * global minimum is taken over the exchange slots (receive half of the
+ * peer-memory allreduce) instead of the vector at simian_minvec_ptr          */
+int simian_window_advance_async(simian_engine *e, int minFromPeers);
 /* device flags -> host: sticky error as return value, *done (simian.js:119) */
 int simian_poll(simian_engine *e, int *done);
 

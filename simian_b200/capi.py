@@ -76,8 +76,9 @@ SIGNATURES = {
     "simian_setup": (_i, [_vp]),
     "simian_ipc_export": (_i, [_vp, _vp, _u64, C.POINTER(_u64)]),
     "simian_ipc_import": (_i, [_vp, _i, _vp, _u64]),
-    "simian_window_pull": (_i, [_vp]),
-    "simian_window_advance_async": (_i, [_vp]),
+    "simian_window_pull": (_i, [_vp, _i]),
+    "simian_window_publish_min": (_i, [_vp]),
+    "simian_window_advance_async": (_i, [_vp, _i]),
     "simian_poll": (_i, [_vp, C.POINTER(_i)]),
     "simian_minvec_ptr": (_i, [_vp, C.POINTER(_vp)]),
     "simian_set_stream": (_i, [_vp, _vp]),
@@ -249,11 +250,14 @@ class Engine:
         buf = C.create_string_buffer(bytes(blob), len(blob))
         self._ck(self.L.simian_ipc_import(self.h, peer_rank, buf, len(blob)))
 
-    def window_pull(self):
-        self._ck(self.L.simian_window_pull(self.h))
+    def window_pull(self, wait_for_peers=False):
+        self._ck(self.L.simian_window_pull(self.h, int(wait_for_peers)))
 
-    def window_advance_async(self):
-        self._ck(self.L.simian_window_advance_async(self.h))
+    def window_publish_min(self):
+        self._ck(self.L.simian_window_publish_min(self.h))
+
+    def window_advance_async(self, min_from_peers=False):
+        self._ck(self.L.simian_window_advance_async(self.h, int(min_from_peers)))
 
     def poll(self):
         done = _i()

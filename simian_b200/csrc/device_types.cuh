@@ -107,6 +107,14 @@ struct __align__(64) BlockPart {
   uint32_t committed, emitted, dropped, ties, dties, appended, far_appends, page_allocs;
 };
 
+// one rank's LBTS candidate as published to a peer (allreduce(MIN) over NVLink
+// peer memory, mpi.cpp:364-390): data first, then seq = window number + 1
+struct __align__(32) MinSlot {
+  double min_left, far_min;
+  unsigned long long seq;
+  unsigned long long pad_;
+};
+
 struct DevCfg {
   double start, end, min_delay, inf_time;
   uint64_t seed;
@@ -144,4 +152,8 @@ struct DevCfg {
   // the peers' outboxes, mapped over NVLink (CUDA IPC); null = not connected
   const simian_event_t *peer_outbox[SIMIAN_MAX_RANKS];
   const uint32_t *peer_count[SIMIAN_MAX_RANKS];
+  // LBTS exchange slots: every rank WRITES its {minLeft, min far time, window
+  // number} into slot [parity][its rank] of every peer's array (and its own)
+  MinSlot *xch;                          // [2][size], local
+  MinSlot *peer_xch[SIMIAN_MAX_RANKS];   // peers' arrays (peer_xch[rank] == xch)
 };

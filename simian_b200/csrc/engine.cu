@@ -170,7 +170,7 @@ struct simian_engine {
   uint32_t *h_counts = nullptr;
   std::chrono::steady_clock::time_point t_begin;
   size_t smem_bytes = sizeof(WindowShared);
-  void *peer_map[2 * SIMIAN_MAX_RANKS] = {}; // cudaIpcOpenMemHandle results
+  void *peer_map[3 * SIMIAN_MAX_RANKS] = {}; // cudaIpcOpenMemHandle results
 
   int fail(int code, const std::string &m) {
     if (!err_code) {
@@ -341,6 +341,8 @@ int setup_layout(simian_engine *e) {
     c.outbox_cap = (uint32_t)cap;
     if (dev_alloc(e, &c.outbox, 2 * (size_t)e->size * cap)) return e->err_code;
     if (dev_alloc(e, &c.outbox_count, 2 * (size_t)e->size)) return e->err_code;
+    if (dev_alloc(e, &c.xch, 2 * (size_t)e->size)) return e->err_code;
+    c.peer_xch[e->rank] = c.xch;
   }
   if (!e->h_acc) {
     CK(cudaMallocHost((void **)&e->h_acc, sizeof(DevAcc)));
@@ -747,7 +749,7 @@ int simian_setup(simian_engine *e) {
 
 namespace {
 struct IpcBlob { // what one rank publishes to its peers
-  cudaIpcMemHandle_t outbox, count;
+  cudaIpcMemHandle_t outbox, count, xch;
   uint64_t cap;
   int32_t rank, size;
 };
@@ -764,6 +766,9 @@ int simian_ipc_export(simian_engine *e, void *blob, uint64_t blobBytes, uint64_t
   memset(&b, 0, sizeof b);
   CK(cudaIpcGetMemHandle(&b.outbox, e->cfg.outbox));
   CK(cudaIpcGetMemHandle(&b.count, e->cfg.outbox_count));
+  CK(cudaIpcGetMemHandle(&b.xch, e->cfg.xch));
+  // k_init has zeroed the exchange slots before any peer can write into them
+  CK(cudaStreamSynchronize(e->stream));
   b.cap = e->cfg.outbox_cap;
   b.rank = e->rank;
   b.size = e->size;
@@ -781,20 +786,30 @@ int simian_ipc_import(simian_engine *e, int peerRank, const void *blob, uint64_t
   memcpy(&b, blob, sizeof b);
   if (b.rank != peerRank || b.size != e->size || b.cap != e->cfg.outbox_cap)
     return e->fail(SIMIAN_ERR_BAD_ARGUMENT, "ipc blob does not match this world");
-  void *po = nullptr, *pc = nullptr;
+  void *po = nullptr, *pc = nullptr, *px = nullptr;
   CK(cudaIpcOpenMemHandle(&po, b.outbox, cudaIpcMemLazyEnablePeerAccess));
   CK(cudaIpcOpenMemHandle(&pc, b.count, cudaIpcMemLazyEnablePeerAccess));
-  e->peer_map[2 * peerRank] = po;
-  e->peer_map[2 * peerRank + 1] = pc;
+  CK(cudaIpcOpenMemHandle(&px, b.xch, cudaIpcMemLazyEnablePeerAccess));
+  e->peer_map[3 * peerRank] = po;
+  e->peer_map[3 * peerRank + 1] = pc;
+  e->peer_map[3 * peerRank + 2] = px;
+  e->cfg.peer_xch[peerRank] = (MinSlot *)px;
   e->cfg.peer_outbox[peerRank] = (const simian_event_t *)po;
   e->cfg.peer_count[peerRank] = (const uint32_t *)pc;
   return 0;
 }
 
-int simian_window_pull(simian_engine *e) {
+int simian_window_publish_min(simian_engine *e) {
+  k_local_min<<<1, NTHREADS, e->smem_bytes, e->stream>>>(e->cfg, e->win_ix, 1);
+  CK(cudaGetLastError());
+  e->launches++;
+  return 0;
+}
+
+int simian_window_pull(simian_engine *e, int waitForPeers) {
   if (e->size < 2) return 0;
   const uint32_t bpp = 148; // blocks per peer
-  k_pull<<<(e->size - 1) * bpp, 256, 0, e->stream>>>(e->cfg, e->win_ix, bpp);
+  k_pull<<<(e->size - 1) * bpp, 256, 0, e->stream>>>(e->cfg, e->win_ix, bpp, waitForPeers);
   CK(cudaGetLastError());
   e->launches++;
   return 0;
@@ -806,8 +821,8 @@ int simian_minvec_ptr(simian_engine *e, void **devMinVec) {
   return 0;
 }
 
-int simian_window_advance_async(simian_engine *e) {
-  k_advance<<<1, NTHREADS, 0, e->stream>>>(e->cfg, e->win_ix);
+int simian_window_advance_async(simian_engine *e, int minFromPeers) {
+  k_advance<<<1, NTHREADS, 0, e->stream>>>(e->cfg, e->win_ix, minFromPeers);
   CK(cudaGetLastError());
   e->launches++;
   e->win_ix++;
@@ -867,7 +882,7 @@ int simian_window_ingest(simian_engine *e, const void *devRecords, uint64_t n) {
 }
 
 int simian_window_local_min(simian_engine *e, void **devMinVec) {
-  k_local_min<<<1, NTHREADS, e->smem_bytes, e->stream>>>(e->cfg, e->win_ix);
+  k_local_min<<<1, NTHREADS, e->smem_bytes, e->stream>>>(e->cfg, e->win_ix, 0);
   CK(cudaGetLastError());
   e->launches++;
   if (devMinVec) *devMinVec = (void *)e->cfg.acc->minvec;
@@ -875,7 +890,7 @@ int simian_window_local_min(simian_engine *e, void **devMinVec) {
 }
 
 int simian_window_advance(simian_engine *e, int *done) {
-  k_advance<<<1, NTHREADS, 0, e->stream>>>(e->cfg, e->win_ix);
+  k_advance<<<1, NTHREADS, 0, e->stream>>>(e->cfg, e->win_ix, 0);
   CK(cudaGetLastError());
   e->launches++;
   e->win_ix++;

@@ -345,8 +345,15 @@ __global__ void k_init(const __grid_constant__ DevCfg c, uint32_t n_cells) {
     c.win[0] = w;
     c.win[1] = w;
   }
-  for (size_t j = i; j < 2 * (size_t)c.size; j += stride)
+  for (size_t j = i; j < 2 * (size_t)c.size; j += stride) {
     if (c.outbox_count) c.outbox_count[j] = 0;
+    if (c.xch) {
+      MinSlot z;
+      z.min_left = z.far_min = 0;
+      z.seq = z.pad_ = 0;
+      c.xch[j] = z;
+    }
+  }
 }
 
 // schedService loop on the device (simian.js:170-190 for every (k, i))
@@ -433,11 +440,24 @@ __global__ void k_ingest(const __grid_constant__ DevCfg c, const simian_event_t 
 // calendar -- alltoallv and ingest in one kernel, counts never visit the host.
 // Runs after the window's allreduce, which orders it behind every peer's
 // k_window.  gridDim.x = (size - 1) * blocks_per_peer.
-__global__ void k_pull(const __grid_constant__ DevCfg c, uint32_t win_ix, uint32_t blocks_per_peer) {
+__global__ void k_pull(const __grid_constant__ DevCfg c, uint32_t win_ix, uint32_t blocks_per_peer,
+                       int wait_flags) {
   __shared__ AppendCtx ax;
   append_ctx_init(ax);
-  __syncthreads();
   const WinState &W = c.win[win_ix & 1u];
+  if (wait_flags && !W.done && threadIdx.x < (unsigned)c.size) {
+    // every rank has published window win_ix's candidate, i.e. finished its
+    // k_window: the outboxes are complete (the barrier MPI_Alltoall is, mpi.cpp:422)
+    const volatile unsigned long long *f =
+        &c.xch[W.parity * (uint32_t)c.size + threadIdx.x].seq;
+    const unsigned long long want = (unsigned long long)win_ix + 1ull;
+    while (*f != want) {
+      if (ld_cg(&c.acc->error)) break;
+      __nanosleep(100);
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
   uint32_t napp = 0;
   if (!W.done) {
     const uint32_t q = blockIdx.x / blocks_per_peer, sub = blockIdx.x % blocks_per_peer;
@@ -1569,7 +1589,8 @@ __global__ void __launch_bounds__(NTHREADS, SIMIAN_MINBLOCKS)
 }
 
 // size > 1: local minLeft candidate after the exchange (simian.js:143)
-__global__ void __launch_bounds__(NTHREADS) k_local_min(const __grid_constant__ DevCfg c, uint32_t win_ix) {
+__global__ void __launch_bounds__(NTHREADS) k_local_min(const __grid_constant__ DevCfg c, uint32_t win_ix,
+                                                        int publish) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   WindowShared &sh = *reinterpret_cast<WindowShared *>(smem_raw);
   const WinState &W = c.win[win_ix & 1u];
@@ -1580,25 +1601,53 @@ __global__ void __launch_bounds__(NTHREADS) k_local_min(const __grid_constant__ 
   } else {
     local_min_candidate(c, W, sh, cand, far);
   }
+  const double inf = __longlong_as_double(0x7FF0000000000000LL);
+  const double m0 = cand == SIMIAN_KEY_NONE ? c.inf_time : simian_key_time(cand);
+  const double m1 = far == SIMIAN_KEY_NONE ? inf : simian_key_time(far);
   if (threadIdx.x == 0) {
-    const double inf = __longlong_as_double(0x7FF0000000000000LL);
-    c.acc->minvec[0] = cand == SIMIAN_KEY_NONE ? c.inf_time : simian_key_time(cand);
-    c.acc->minvec[1] = far == SIMIAN_KEY_NONE ? inf : simian_key_time(far);
+    c.acc->minvec[0] = m0;
+    c.acc->minvec[1] = m1;
+  }
+  // allreduce(MIN) over peer memory, send half: one thread per peer writes this
+  // rank's candidate into the peer's slot array -- data, fence, then the flag
+  if (publish && !W.done && threadIdx.x < (unsigned)c.size) {
+    MinSlot *dst = c.peer_xch[threadIdx.x];
+    if (dst) {
+      dst += W.parity * (uint32_t)c.size + (uint32_t)c.rank;
+      *(volatile double *)&dst->min_left = m0;
+      *(volatile double *)&dst->far_min = m1;
+      __threadfence_system();
+      *(volatile unsigned long long *)&dst->seq = (unsigned long long)win_ix + 1ull;
+    } else {
+      set_error(c, SIMIAN_ERR_BAD_ARGUMENT); // peers were never connected
+    }
   }
 }
 
 // size > 1: consume the allreduced {globalMinLeft, min far} (simian.js:144)
-__global__ void __launch_bounds__(NTHREADS) k_advance(const __grid_constant__ DevCfg c, uint32_t win_ix) {
+__global__ void __launch_bounds__(NTHREADS) k_advance(const __grid_constant__ DevCfg c, uint32_t win_ix,
+                                                      int from_xch) {
   const WinState W = c.win[win_ix & 1u];
   WinState *Wn = &c.win[(win_ix + 1u) & 1u];
   if (W.done) {
     if (threadIdx.x == 0) *Wn = W;
     return;
   }
+  double g0 = c.acc->minvec[0], g1 = c.acc->minvec[1];
+  if (from_xch) { // allreduce(MIN), receive half: every flag was seen by k_pull
+    g0 = g1 = __longlong_as_double(0x7FF0000000000000LL);
+    for (int p = 0; p < c.size; p++) {
+      const MinSlot *sl = &c.xch[W.parity * (uint32_t)c.size + p];
+      double a = *(const volatile double *)&sl->min_left;
+      double b2 = *(const volatile double *)&sl->far_min;
+      g0 = a < g0 ? a : g0;
+      g1 = b2 < g1 ? b2 : g1;
+    }
+  }
   if (W.redist)
     setup_next_window(c, W, Wn, W.gmin, 0.0, true);
   else
-    setup_next_window(c, W, Wn, c.acc->minvec[0], c.acc->minvec[1], false);
+    setup_next_window(c, W, Wn, g0, g1, false);
   // The outbox the NEXT window fills was sent two windows ago; every peer has
   // read it (its pull precedes the allreduce this advance follows).  The one
   // just sent may still be being read: it is left alone.

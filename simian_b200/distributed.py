@@ -98,7 +98,7 @@ def connect_peers(engine, rank, size, group=None):
 
 
 def drive_windows_p2p(engine, rank, size, device, group=None, batch=8,
-                      max_batch=64, profile=False):
+                      max_batch=64, profile=False, allreduce="peer"):
     """Simian.run for size > 1 (simian.js:118-149) with the device-driven
     exchange: no host round trip inside a batch of windows.  Per window:
       k_window           events below the bound; remote sends -> outbox[parity],
@@ -108,7 +108,12 @@ def drive_windows_p2p(engine, rank, size, device, group=None, batch=8,
       k_pull             peers' outboxes -> local calendar, NVLink  :137-142
       k_advance          next window                                :119-120
     The host polls `done`/error once per batch; windows launched past the end
-    are no-ops on every rank (the window sequence is global)."""
+    are no-ops on every rank (the window sequence is global).
+    allreduce="peer" (default): the MIN-allreduce itself runs over NVLink peer
+    memory -- k_local_min writes this rank's candidate into every peer's
+    exchange slots, k_pull waits for all of them, k_advance takes the minimum --
+    so a window is four kernel launches and no collective-library call;
+    allreduce="nccl": torch.distributed all_reduce as drawn above."""
     engine.set_stream(torch.cuda.current_stream(device).cuda_stream)
     connect_peers(engine, rank, size, group)
     engine.run_begin()
@@ -128,13 +133,21 @@ def drive_windows_p2p(engine, rank, size, device, group=None, batch=8,
             mark()
             engine.window_process()
             mark()
-            engine.window_local_min()
-            mark()
-            dist.all_reduce(mv, op=dist.ReduceOp.MIN, group=group)
-            mark()
-            engine.window_pull()
-            mark()
-            engine.window_advance_async()
+            if allreduce == "peer":
+                engine.window_publish_min()
+                mark()
+                mark()
+                engine.window_pull(True)
+                mark()
+                engine.window_advance_async(True)
+            else:
+                engine.window_local_min()
+                mark()
+                dist.all_reduce(mv, op=dist.ReduceOp.MIN, group=group)
+                mark()
+                engine.window_pull(False)
+                mark()
+                engine.window_advance_async(False)
             mark()
             windows += 1
         if engine.poll():

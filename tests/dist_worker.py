@@ -44,7 +44,7 @@ def main():
     ap.add_argument("--engine", default="oracle")
     ap.add_argument("--backend", default="gloo")
     ap.add_argument("--cases", default="ross,other_group,uniform_sparse")
-    ap.add_argument("--driver", default="p2p", choices=["p2p", "nccl"],
+    ap.add_argument("--driver", default="p2p", choices=["p2p", "p2p_nccl", "nccl"],
                     help="cuda engine: device-driven pull over NVLink, or the "
                          "host-driven NCCL alltoallv")
     a = ap.parse_args()
@@ -82,9 +82,10 @@ def main():
             e = capi.Engine("dist", 0.0, c["end"], c["min_delay"], rank=rank,
                             size=world, device=local, seed=c["seed"], **opts)
             build(e, c, world)
-            if a.driver == "p2p":
+            if a.driver in ("p2p", "p2p_nccl"):
                 from simian_b200.distributed import drive_windows_p2p
-                st = drive_windows_p2p(e, rank, world, torch.device("cuda", local))
+                st = drive_windows_p2p(e, rank, world, torch.device("cuda", local),
+                                       allreduce="peer" if a.driver == "p2p" else "nccl")
             else:
                 st = drive_windows(GpuRankEngine(e, "cuda:%d" % local), rank, world)
             cnt = e.read_counts("Node", c["n"])

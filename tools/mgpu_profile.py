@@ -14,7 +14,8 @@ cfg = bench.workload_for(world, 1.0)
 for rep in range(2):
     e = capi.Engine("p", 0.0, cfg["end"], cfg["min_delay"], rank=rank, size=world, device=local, seed=1)
     build_phold(e, cfg["n"], cfg["per_entity"], cfg["lookahead"], cfg["p_remote"], 1.0, cfg["mode"], cfg["groups"])
-    st = drive_windows_p2p(e, rank, world, torch.device("cuda", local), profile=True)
+    st = drive_windows_p2p(e, rank, world, torch.device("cuda", local), profile=True,
+                           allreduce=os.environ.get("SIMIAN_ALLREDUCE", "peer"))
     e.close()
 if rank == 0:
     print(json.dumps({"windows": st["windows"], "driver_windows": st["driver_windows"], "events": st["total_events"],
