@@ -100,8 +100,10 @@ struct DevAcc {
   unsigned long long phase_cycles[12]; // SIMIAN_PROFILE_PHASES builds only
 };
 
-// per-CTA results of one k_window launch: plain stores, summed by the last CTA
-// (no same-address atomics on the hot path)
+// results of one k_window launch: every CTA adds into slot (block index mod
+// SIMIAN_PART_SLOTS) with result-less atomics -- 64 cache lines instead of one
+// -- and the last CTA sums the slots in a single round trip
+#define SIMIAN_PART_SLOTS 64
 struct __align__(64) BlockPart {
   unsigned long long min_key, max_key;
   uint32_t committed, emitted, dropped, ties, dties, appended, far_appends, page_allocs;
@@ -139,7 +141,7 @@ struct DevCfg {
   unsigned long long *snap; // [n_blocks] head words of row tb_hi at window start
   WinState *win;                  // [2]
   DevAcc *acc;
-  BlockPart *part; // [n_blocks]
+  BlockPart *part; // [SIMIAN_PART_SLOTS]
   // block page caches: pages an entity block recycled and will reuse, so that
   // steady-state windows never touch the global free ring
   uint32_t *bcache; // [n_blocks][SIMIAN_BC]

@@ -332,7 +332,7 @@ int setup_layout(simian_engine *e) {
   if (dev_alloc(e, &c.snap, c.n_blocks)) return e->err_code;
   if (dev_alloc(e, &c.win, 2)) return e->err_code;
   if (dev_alloc(e, &c.acc, 1)) return e->err_code;
-  if (dev_alloc(e, &c.part, c.n_blocks)) return e->err_code;
+  if (dev_alloc(e, &c.part, SIMIAN_PART_SLOTS)) return e->err_code;
   if (dev_alloc(e, &c.bcache, (size_t)c.n_blocks * SIMIAN_BC)) return e->err_code;
   if (dev_alloc(e, &c.bcount, c.n_blocks)) return e->err_code;
   if (dev_alloc(e, &e->d_digest, 2)) return e->err_code;

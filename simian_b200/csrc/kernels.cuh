@@ -301,6 +301,14 @@ __global__ void k_init(const __grid_constant__ DevCfg c, uint32_t n_cells) {
   }
   for (size_t j = i; j < n_cells; j += stride) c.cell_state[j] = CELL_EMPTY;
   for (size_t j = i; j < c.n_blocks; j += stride) c.snap[j] = CELL_EMPTY;
+  for (size_t j = i; j < SIMIAN_PART_SLOTS; j += stride) {
+    BlockPart z;
+    z.min_key = SIMIAN_KEY_NONE;
+    z.max_key = 0;
+    z.committed = z.emitted = z.dropped = z.ties = z.dties = z.appended = z.far_appends =
+        z.page_allocs = 0;
+    c.part[j] = z;
+  }
   // block page caches start with SIMIAN_BC_FILL pages each when the pool allows
   const uint32_t fill =
       ((unsigned long long)c.n_blocks * SIMIAN_BC_FILL * 2ull <= c.n_pages) ? SIMIAN_BC_FILL : 0u;
@@ -1150,8 +1158,19 @@ __device__ void setup_next_window(const DevCfg &c, const WinState &W, WinState *
   // snapshot the heads of row tb_hi: appends of the next launch may target it
   if (!nw.done) {
     uint32_t row = (uint32_t)(nw.tb_hi & (long long)c.ring_mask) * c.n_blocks;
-    for (uint32_t b = tid; b < c.n_blocks; b += blockDim.x)
-      c.snap[b] = ld_cg64(&c.cell_state[row + b]);
+    for (uint32_t b0 = 0; b0 < c.n_blocks; b0 += 8 * blockDim.x) { // 8 loads in flight per thread
+      unsigned long long v[8];
+#pragma unroll
+      for (int q = 0; q < 8; q++) {
+        uint32_t b = b0 + q * blockDim.x + tid;
+        if (b < c.n_blocks) v[q] = ld_cg64(&c.cell_state[row + b]);
+      }
+#pragma unroll
+      for (int q = 0; q < 8; q++) {
+        uint32_t b = b0 + q * blockDim.x + tid;
+        if (b < c.n_blocks) c.snap[b] = v[q];
+      }
+    }
   }
   __syncthreads();
   if (tid == 0) {
@@ -1214,38 +1233,52 @@ __device__ void redistribute_block(const DevCfg &c, WindowShared &sh, uint32_t b
   if (tid == 0) c.cell_state[far_cell] = CELL_EMPTY;
 }
 
-// Sum the per-CTA results of the launch into the global accumulators (one CTA,
-// all threads; runs after the ticket fence, so every BlockPart is visible).
+// 64-bit min / max over the warp with redux.sync on the two halves
+__device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v) {
+  uint32_t hi = (uint32_t)(v >> 32), lo = (uint32_t)v;
+  uint32_t mh = __reduce_min_sync(0xffffffffu, hi);
+  uint32_t ml = __reduce_min_sync(0xffffffffu, hi == mh ? lo : 0xFFFFFFFFu);
+  return ((unsigned long long)mh << 32) | ml;
+}
+__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v) {
+  uint32_t hi = (uint32_t)(v >> 32), lo = (uint32_t)v;
+  uint32_t mh = __reduce_max_sync(0xffffffffu, hi);
+  uint32_t ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+  return ((unsigned long long)mh << 32) | ml;
+}
+
+// Sum the launch's results into the global accumulators (one CTA, all threads;
+// runs after the ticket fence, so every CTA's contribution is visible).  The
+// CTAs add into SIMIAN_PART_SLOTS accumulator slots (block index mod slots), so
+// this is ONE round trip, not a loop over the blocks; the slots are cleared
+// for the next launch.
 __device__ void reduce_parts(const DevCfg &c, WindowShared &sh) {
-  const int tid = threadIdx.x, lane = tid & 31;
-  unsigned long long mn = SIMIAN_KEY_NONE, mx = 0;
-  unsigned long long v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (uint32_t b = tid; b < c.n_blocks; b += blockDim.x) {
-    const BlockPart *p = &c.part[b];
-    unsigned long long a0 = ld_cg64(&p->min_key), a1 = ld_cg64(&p->max_key);
-    mn = a0 < mn ? a0 : mn;
-    mx = a1 > mx ? a1 : mx;
-    const uint32_t *w = &p->committed;
-#pragma unroll
-    for (int k = 0; k < 8; k++) v[k] += ld_cg(w + k);
-  }
-  for (int o = 16; o; o >>= 1) {
-    unsigned long long x = __shfl_xor_sync(0xffffffffu, mn, o);
-    mn = x < mn ? x : mn;
-    unsigned long long y = __shfl_xor_sync(0xffffffffu, mx, o);
-    mx = y > mx ? y : mx;
-#pragma unroll
-    for (int k = 0; k < 8; k++) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
-  }
+  const int tid = threadIdx.x;
   __shared__ unsigned long long red[10];
   if (tid < 10) red[tid] = tid == 0 ? SIMIAN_KEY_NONE : 0ull;
   __syncthreads();
-  if (lane == 0) {
-    if (mn != SIMIAN_KEY_NONE) atomicMin(&red[0], mn);
-    if (mx) atomicMax(&red[1], mx);
+  if (tid < SIMIAN_PART_SLOTS) {
+    BlockPart *p = &c.part[tid];
+    unsigned long long mn = ld_cg64(&p->min_key), mx = ld_cg64(&p->max_key);
+    uint32_t v[8];
+    const uint32_t *w = &p->committed;
 #pragma unroll
-    for (int k = 0; k < 8; k++)
-      if (v[k]) atomicAdd(&red[2 + k], v[k]);
+    for (int q = 0; q < 8; q++) v[q] = ld_cg(w + q);
+    p->min_key = SIMIAN_KEY_NONE;
+    p->max_key = 0;
+#pragma unroll
+    for (int q = 0; q < 8; q++) (&p->committed)[q] = 0;
+    mn = warp_min_u64(mn);
+    mx = warp_max_u64(mx);
+#pragma unroll
+    for (int q = 0; q < 8; q++) v[q] = __reduce_add_sync(0xffffffffu, v[q]);
+    if ((tid & 31) == 0) {
+      if (mn != SIMIAN_KEY_NONE) atomicMin(&red[0], mn);
+      if (mx) atomicMax(&red[1], mx);
+#pragma unroll
+      for (int q = 0; q < 8; q++)
+        if (v[q]) atomicAdd(&red[2 + q], (unsigned long long)v[q]);
+    }
   }
   __syncthreads();
   if (tid == 0) {
@@ -1265,20 +1298,6 @@ __device__ void reduce_parts(const DevCfg &c, WindowShared &sh) {
     __threadfence();
   }
   __syncthreads();
-}
-
-// 64-bit min / max over the warp with redux.sync on the two halves
-__device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v) {
-  uint32_t hi = (uint32_t)(v >> 32), lo = (uint32_t)v;
-  uint32_t mh = __reduce_min_sync(0xffffffffu, hi);
-  uint32_t ml = __reduce_min_sync(0xffffffffu, hi == mh ? lo : 0xFFFFFFFFu);
-  return ((unsigned long long)mh << 32) | ml;
-}
-__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v) {
-  uint32_t hi = (uint32_t)(v >> 32), lo = (uint32_t)v;
-  uint32_t mh = __reduce_max_sync(0xffffffffu, hi);
-  uint32_t ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
-  return ((unsigned long long)mh << 32) | ml;
 }
 
 // One lookahead window (or one redistribution pass) for entity block blockIdx.x.
@@ -1551,18 +1570,20 @@ __global__ void __launch_bounds__(NTHREADS, SIMIAN_MINBLOCKS)
     }
   }
   __syncthreads();
-  if (tid == 0) {
-    BlockPart *p = &c.part[b];
-    p->min_key = sh.min_key;
-    p->max_key = sh.max_key;
-    p->committed = sh.committed;
-    p->emitted = sh.emitted;
-    p->dropped = sh.dropped;
-    p->ties = sh.ties;
-    p->dties = sh.dties;
-    p->appended = sh.appended;
-    p->far_appends = sh.ax.far_appends;
-    p->page_allocs = sh.ax.page_allocs;
+  if (tid < 10) { // one thread per field: independent, result-less atomics
+    BlockPart *p = &c.part[b % SIMIAN_PART_SLOTS];
+    switch (tid) {
+      case 0: if (sh.min_key != SIMIAN_KEY_NONE) atomicMin(&p->min_key, sh.min_key); break;
+      case 1: if (sh.max_key) atomicMax(&p->max_key, sh.max_key); break;
+      case 2: if (sh.committed) atomicAdd(&p->committed, sh.committed); break;
+      case 3: if (sh.emitted) atomicAdd(&p->emitted, sh.emitted); break;
+      case 4: if (sh.dropped) atomicAdd(&p->dropped, sh.dropped); break;
+      case 5: if (sh.ties) atomicAdd(&p->ties, sh.ties); break;
+      case 6: if (sh.dties) atomicAdd(&p->dties, sh.dties); break;
+      case 7: if (sh.appended) atomicAdd(&p->appended, sh.appended); break;
+      case 8: if (sh.ax.far_appends) atomicAdd(&p->far_appends, sh.ax.far_appends); break;
+      default: if (sh.ax.page_allocs) atomicAdd(&p->page_allocs, sh.ax.page_allocs); break;
+    }
   }
   PHASE(8);
   if (!fuse_advance) return;
