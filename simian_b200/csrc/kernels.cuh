@@ -737,13 +737,15 @@ __global__ void k_construct(const __grid_constant__ DevCfg c, int cls, uint32_t 
   append_ctx_flush(c, ax);
 }
 
-// key order (time, handler, src, seq): a < b
+// key order (time, handler, src, seq), then the slot index so that identical
+// records are all taken, in a fixed order: a < b
 __device__ __forceinline__ bool key_lt(unsigned long long a1, unsigned long long a2, uint32_t a3,
-                                       unsigned long long b1, unsigned long long b2,
-                                       uint32_t b3) {
+                                       uint32_t a4, unsigned long long b1,
+                                       unsigned long long b2, uint32_t b3, uint32_t b4) {
   if (a1 != b1) return a1 < b1;
   if (a2 != b2) return a2 < b2;
-  return a3 < b3;
+  if (a3 != b3) return a3 < b3;
+  return a4 < b4;
 }
 
 // All due events of one entity, in order (simian.js:122-134 restricted to one
@@ -760,7 +762,7 @@ __device__ __noinline__ void process_entity(const DevCfg &c, WindowShared &sh, T
   ctx.cl = &c.cls[k];
   EntityCore st = sh.core_s[slot % EPB];
   unsigned long long p1 = 0, p2 = 0;
-  uint32_t p3 = 0;
+  uint32_t p3 = 0, p4 = 0;
   bool have_prev = false, have_last = false;
   double last_time = 0;
   unsigned long long last_q = 0, last_data = 0;
@@ -779,8 +781,8 @@ __device__ __noinline__ void process_entity(const DevCfg &c, WindowShared &sh, T
         unsigned long long k1 = simian_time_key(r.time());
         unsigned long long k2 = ((unsigned long long)r.handler() << 32) | r.src();
         uint32_t k3 = r.seq();
-        if (have_prev && !key_lt(p1, p2, p3, k1, k2, k3)) continue;
-        if (!have_g || key_lt(k1, k2, k3, g1, g2, g3)) {
+        if (have_prev && !key_lt(p1, p2, p3, p4, k1, k2, k3, j)) continue;
+        if (!have_g || key_lt(k1, k2, k3, j, g1, g2, g3, gj)) {
           gj = j;
           g1 = k1;
           g2 = k2;
@@ -817,6 +819,7 @@ __device__ __noinline__ void process_entity(const DevCfg &c, WindowShared &sh, T
       p1 = g1;
       p2 = g2;
       p3 = g3;
+      p4 = gj;
       have_prev = true;
       taken++;
     } else
@@ -883,7 +886,9 @@ __device__ __forceinline__ uint32_t rank_event(const DevCfg &c, WindowShared &sh
       const RecBits o = slot_get(sh, j);
       unsigned long long a2 = ((unsigned long long)o.handler() << 32) | o.src();
       unsigned long long b2 = ((unsigned long long)r.handler() << 32) | r.src();
-      bool before = a2 != b2 ? a2 < b2 : o.seq() < r.seq();
+      // identical records (same key down to seq) are ordered by their slot: any
+      // order of indistinguishable events commits the same thing
+      bool before = a2 != b2 ? a2 < b2 : (o.seq() != r.seq() ? o.seq() < r.seq() : j < i);
       if (before) { // equal-time predecessor: keep the latest one
         rank++;
         if (!have_pred) {
@@ -891,7 +896,7 @@ __device__ __forceinline__ uint32_t rank_event(const DevCfg &c, WindowShared &sh
           have_pred = true;
         } else {
           unsigned long long p2 = ((unsigned long long)pred.handler() << 32) | pred.src();
-          if (p2 != a2 ? p2 < a2 : pred.seq() < o.seq()) pred = o;
+          if (p2 != a2 ? p2 < a2 : pred.seq() <= o.seq()) pred = o;
         }
       }
     }

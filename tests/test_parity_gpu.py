@@ -160,3 +160,40 @@ def test_engine_lanl_matches_oracle(case, oracle_mod):
     assert se["dropped_past_end"] == so["dropped_past_end"]
     assert se["ties"] == so["ties"]
     assert se["distinguishable_ties"] == so["distinguishable_ties"]
+
+
+def test_identical_records_are_all_committed(oracle_mod):
+    """two schedService calls that produce byte-identical records (same time,
+    service, data, seq): the reference executes both (eventQ holds both); the
+    engine must not collapse them, on either handler mapping"""
+    from simian_b200 import capi
+    from simian_b200.workloads import phold_params_blob
+    n = 300
+    ev = np.zeros(2 * n, dtype=capi.EVENT_DTYPE)
+    ev["time"] = 0.25
+    ev["dst"] = np.tile(np.arange(n, dtype=np.uint32), 2)
+    ev["src"] = capi.NULL_ENTITY
+    ev["handler"] = 0
+    ev["flags"] = 1
+    ev["seq"] = 7
+    outs = []
+    for make in ("oracle", 0, 1):
+        if make == "oracle":
+            h = oracle_mod.Oracle("dup", 0.0, 3.0, 0.1, seed=5)
+        else:
+            h = capi.Engine("dup", 0.0, 3.0, 0.1, seed=5, force_sequential=make)
+        h.define_class("Node", 0)
+        h.add_entities("Node", 0, n)
+        h.attach_service("Node", "generate", "phold_generate")
+        h.set_class_params("Node", phold_params_blob(0, n, 0.2, 1.0, 0.1, 1, 1))
+        h.sched_events(ev)
+        st = h.run()
+        outs.append((st, h.read_counts("Node", n), h.read_trace_hashes("Node", n)))
+        h.close()
+    so, co, ho = outs[0]
+    assert so["total_events"] > 2 * n
+    for se, ce, he in outs[1:]:
+        assert se["total_events"] == so["total_events"]
+        np.testing.assert_array_equal(ce, co)
+        np.testing.assert_array_equal(he, ho)
+        assert se["digest"] == so["digest"]
