@@ -17,7 +17,7 @@
 #include "../../include/simian_spec.h"
 
 #ifndef SIMIAN_EPB
-#define SIMIAN_EPB 512 // entities per block (one CTA owns one block)
+#define SIMIAN_EPB 512 // max entities per block (one CTA owns one block)
 #endif
 #ifndef SIMIAN_THREADS
 #define SIMIAN_THREADS 256 // threads per CTA of the window kernel
@@ -127,6 +127,10 @@ struct DevCfg {
   // entities
   EntityCore *core;
   uint32_t n_slots, n_blocks;
+  // entities per block, <= SIMIAN_EPB: chosen at setup so that the grid of the
+  // window kernel fills whole waves of resident CTAs (epb_inv = ceil(2^64/epb))
+  uint32_t epb, pad3_;
+  unsigned long long epb_inv;
   // calendar
   double inv_w;
   uint32_t ring, ring_mask;

@@ -142,6 +142,7 @@ struct simian_engine {
   uint32_t ring = 1024;
   uint64_t pool_events = 0, outbox_events = 0;
   int launch_batch = 16, tie_check = 1, force_sequential = 0;
+  uint32_t epb_override = 0; // option "block_entities"
   // model
   std::vector<HostClass> classes;
   std::map<std::string, int> class_ix;
@@ -250,6 +251,10 @@ void teardown_layout(simian_engine *e) {
 int setup_layout(simian_engine *e) {
   if (e->laid_out) return 0;
   DevCfg &c = e->cfg;
+  CK(cudaFuncSetAttribute(k_window, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          (int)e->smem_bytes));
+  CK(cudaFuncSetAttribute(k_local_min, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          (int)e->smem_bytes));
   memset(&c, 0, sizeof c);
   c.start = e->start;
   c.end = e->end;
@@ -304,7 +309,14 @@ int setup_layout(simian_engine *e) {
     d.params = dp;
   }
   c.n_slots = slot;
-  c.n_blocks = (slot + EPB - 1) / EPB;
+  // Entities per block (option "block_entities", <= SIMIAN_EPB).  Shrinking the
+  // block so that the grid fills whole waves of resident CTAs was measured on
+  // config 2 (480 instead of 512: 4.92 instead of 4.61 waves) and gained nothing:
+  // CTAs do not run in lock-step waves, and smaller blocks pay more per-CTA overhead.
+  c.epb = e->epb_override ? e->epb_override : EPB;
+  if (c.epb > EPB || c.epb < 1) return e->fail(SIMIAN_ERR_BAD_ARGUMENT, "bad block_entities");
+  c.epb_inv = ~0ull / c.epb + 1ull; // ceil(2^64 / epb): x / epb == umul64hi(x, epb_inv) for x < 2^32
+  c.n_blocks = (slot + c.epb - 1) / c.epb;
   if (c.n_blocks == 0) c.n_blocks = 1;
   double w = e->bucket_width > 0 ? e->bucket_width : e->min_delay / 8.0;
   c.inv_w = 1.0 / w;
@@ -351,10 +363,6 @@ int setup_layout(simian_engine *e) {
     CK(cudaEventCreate(&e->ev0));
     CK(cudaEventCreate(&e->ev1));
   }
-  CK(cudaFuncSetAttribute(k_window, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                          (int)e->smem_bytes));
-  CK(cudaFuncSetAttribute(k_local_min, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                          (int)e->smem_bytes));
   k_init<<<296, 256, 0, e->stream>>>(c, (uint32_t)n_cells);
   CK(cudaGetLastError());
   e->laid_out = true;
@@ -549,6 +557,7 @@ int simian_set_option(simian_engine *e, const char *key, double v) {
   else if (k == "launch_batch") e->launch_batch = v < 1 ? 1 : (int)v;
   else if (k == "tie_check") e->tie_check = v != 0;
   else if (k == "force_sequential") e->force_sequential = v != 0;
+  else if (k == "block_entities") e->epb_override = (uint32_t)v;
   else return e->fail(SIMIAN_ERR_BAD_ARGUMENT, "unknown option " + k);
   return 0;
 }

@@ -270,7 +270,7 @@ __device__ __forceinline__ void cell_append(const DevCfg &c, AppendCtx &ax,
 __device__ __forceinline__ uint32_t cell_of_local(const DevCfg &c, AppendCtx &ax,
                                                   long long tb_clean, uint32_t far_row,
                                                   double time, uint32_t dst_slot) {
-  uint32_t b = dst_slot / EPB;
+  uint32_t b = (uint32_t)__umul64hi((unsigned long long)dst_slot, c.epb_inv); // dst_slot / epb
   long long tb = tb_of(c, time);
   if (tb < tb_clean) {
     set_error(c, SIMIAN_ERR_OUT_OF_ORDER);
@@ -760,7 +760,7 @@ __device__ __noinline__ void process_entity(const DevCfg &c, WindowShared &sh, T
   ctx.self_slot = slot;
   ctx.self_gid = gid_of_slot(c, slot, k);
   ctx.cl = &c.cls[k];
-  EntityCore st = sh.core_s[slot % EPB];
+  EntityCore st = sh.core_s[slot - blockIdx.x * c.epb];
   unsigned long long p1 = 0, p2 = 0;
   uint32_t p3 = 0, p4 = 0;
   bool have_prev = false, have_last = false;
@@ -1365,10 +1365,10 @@ __global__ void __launch_bounds__(NTHREADS, SIMIAN_MINBLOCKS)
     // ---- K2..K4 over entity sub-ranges; normally ONE pass over [0, EPB).  A
     // sub-range whose due events overflow the shared-memory slots is split
     // and retried (bursts such as the 16 events/entity at t = 0).
-    const uint32_t slot0 = b * EPB;
+    const uint32_t slot0 = b * c.epb;
     if (tid == 0) {
       sh.rstack[0] = 0;
-      sh.rstack[1] = EPB;
+      sh.rstack[1] = c.epb;
       sh.stack_n = 1;
     }
     bool first = true;
@@ -1383,7 +1383,7 @@ __global__ void __launch_bounds__(NTHREADS, SIMIAN_MINBLOCKS)
         sh.pass_hi = sh.rstack[2 * sh.stack_n + 1];
         sh.total = 0;
       }
-      for (int i = tid; i < EPB; i += NTHREADS) sh.head[i] = LIST_END;
+      for (uint32_t i = tid; i < c.epb; i += NTHREADS) sh.head[i] = LIST_END;
       __syncthreads();
       const uint32_t e_lo = sh.pass_lo, e_hi = sh.pass_hi;
       collect_due(c, sh, ta, slot0, npg, e_lo, e_hi, first);
