@@ -15,6 +15,7 @@
  *   const void* params()                per-class model parameters
  *   void*    state()                    per-entity user state (may be null)
  *   uint32_t src()                      tx/txId of the event  simian.js:131
+ *   uint64_t data()                     the event's payload   simian.js:131
  *   void req_service(double offset, uint16_t service, uint64_t data,
  *                    uint32_t rx)       self.reqService(...)  entity.js:35-68
  *        rx == SIMIAN_NULL_ENTITY  <=>  rx omitted (send to self, no lookahead
@@ -34,6 +35,10 @@ enum simian_builtin_fn {
   SIMIAN_FN_LANL_FINISH = 4,    /* "lanl_finish"    */
   SIMIAN_FN_COUNT_ONLY = 5,     /* "noop"           */
   SIMIAN_FN_LANL_CONSTRUCT = 6, /* "lanl_construct": entity constructor, not a service */
+  SIMIAN_FN_HELLO_GENERATE = 7, /* "hello_generate" */
+  SIMIAN_FN_HELLO_SQUARE = 8,   /* "hello_square"   */
+  SIMIAN_FN_HELLO_SQRT = 9,     /* "hello_sqrt"     */
+  SIMIAN_FN_HELLO_RESULT = 10,  /* "hello_result"   */
   SIMIAN_FN__END
 };
 
@@ -42,7 +47,8 @@ enum simian_builtin_fn {
  * commit index, now, handler, src, data).  The engine then runs it with one
  * thread per EVENT instead of one thread per entity.                         */
 SIMIAN_HD int simian_fn_is_pure(int fn) {
-  return fn == SIMIAN_FN_PHOLD_GENERATE || fn == SIMIAN_FN_COUNT_ONLY;
+  return fn == SIMIAN_FN_PHOLD_GENERATE || fn == SIMIAN_FN_COUNT_ONLY ||
+         (fn >= SIMIAN_FN_HELLO_GENERATE && fn <= SIMIAN_FN_HELLO_RESULT);
 }
 
 /* -------------------------------------------------------------- PHOLD ---- */
@@ -269,5 +275,42 @@ SIMIAN_HD void simian_lanl_construct(Ctx &ctx) {
   ctx.req_service(p->end_time - ctx.now(), p->svc_finish, 0ull, SIMIAN_NULL_ENTITY);
   simian_lanl_send_body(ctx, di);
 }
+
+/* ------------------------------------------------- hello.js (two classes) */
+/* SimianJS/Examples/hello.js:27-93: Alice and Bob entities; `generate` sends a
+ * number to a random Alice ("square") or Bob ("sqrt") and reschedules itself
+ * with rx omitted; the receiver replies "result" to tx/txId.  The payload is
+ * the f64 as its 64 bits.  Integer delays: many same-entity time ties.
+ * draw 0 = target class, draw 1 = target id, draw 2 = data.                  */
+typedef struct simian_hello_params {
+  uint32_t alice_first, bob_first; /* global ids of Alice(0) / Bob(0) */
+  uint32_t count, pad_;            /* hello.js:25 */
+  uint16_t svc_generate, svc_square, svc_sqrt, svc_result;
+} simian_hello_params_t; /* 24 bytes */
+
+template <class Ctx>
+SIMIAN_HD void simian_hello_generate(Ctx &ctx) { /* hello.js:32-48 / :68-84 */
+  const simian_hello_params_t *p = (const simian_hello_params_t *)ctx.params();
+  uint32_t target = (uint32_t)(simian_u01(ctx.draw(0)) * 2.0);          /* :36 */
+  uint32_t targetId = (uint32_t)(simian_u01(ctx.draw(1)) * (double)p->count); /* :37 */
+  double data = simian_u01(ctx.draw(2)) * 100.0;                        /* :39 */
+  ctx.req_service(10.0, target ? p->svc_sqrt : p->svc_square, simian_f64_bits(data),
+                  (target ? p->bob_first : p->alice_first) + targetId); /* :46 */
+  ctx.req_service(25.0, p->svc_generate, 0ull, SIMIAN_NULL_ENTITY);      /* :47 */
+}
+template <class Ctx>
+SIMIAN_HD void simian_hello_square(Ctx &ctx) { /* hello.js:50-52 */
+  const simian_hello_params_t *p = (const simian_hello_params_t *)ctx.params();
+  double d = simian_bits_f64(ctx.data());
+  ctx.req_service(10.0, p->svc_result, simian_f64_bits(d * d), ctx.src());
+}
+template <class Ctx>
+SIMIAN_HD void simian_hello_sqrt(Ctx &ctx) { /* hello.js:86-88 */
+  const simian_hello_params_t *p = (const simian_hello_params_t *)ctx.params();
+  double d = simian_bits_f64(ctx.data());
+  ctx.req_service(10.0, p->svc_result, simian_f64_bits(SIMIAN_SQRT(d)), ctx.src());
+}
+template <class Ctx>
+SIMIAN_HD void simian_hello_result(Ctx &) {} /* hello.js:54-59: logs only */
 
 #endif /* SIMIAN_MODELS_H */

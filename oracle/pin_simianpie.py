@@ -198,6 +198,89 @@ def run_lanl_case(Simian, case):
     return out
 
 
+HELLO_CASES = [
+    dict(name="hello_10", count=10, end=400.0, min_delay=1e-4, seed=2),
+    dict(name="hello_37", count=37, end=300.0, min_delay=0.5, seed=6),
+]
+HELLO_SVC = {"generate": 0, "square": 1, "sqrt": 2, "result": 3}
+
+
+def run_hello_case(Simian, case):
+    """SimianJS/Examples/hello.js on the unmodified SimianPie engine; handlers =
+    transcription of simian_hello_* (simian_models.h).  Global ids: Alice(i) = i,
+    Bob(i) = count + i."""
+    import math
+    count = case["count"]
+    eng = Simian("pin_" + case["name"], 0.0, case["end"], case["min_delay"], False,
+                 silent=True)
+    stats = {"ties": 0, "dist_ties": 0}
+    first = {"Alice": 0, "Bob": count}
+
+    class Base(eng.Entity):
+        def __init__(self, baseInfo, *args):
+            super(Base, self).__init__(baseInfo)
+            self.gid = first[self.name] + self.num
+            self.count = 0
+            self.hash = 0
+            self.last = None
+            self.dist_tied = False
+
+        def _commit(self, service, data, tx, txId):
+            now = self.engine.now
+            src = pyspec.NULL_ENTITY if txId is None else first[tx] + txId
+            d = 0 if data is None else pyspec.f64_bits(data)
+            h = HELLO_SVC[service]
+            cur = (now, h, src, d)
+            if self.last is not None and self.last[0] == now:
+                stats["ties"] += 1
+                if self.last != cur:
+                    stats["dist_ties"] += 1
+                    self.dist_tied = True
+            self.last = cur
+            idx = self.count
+            self.hash = pyspec.trace_step(self.hash, now, h, src, d)
+            self.count = idx + 1
+            return idx
+
+        def generate(self, data, tx, txId):                      # hello.js:32-48
+            idx = self._commit("generate", data, tx, txId)
+            t, tid, val = pyspec.hello_generate(case["seed"], self.gid, idx, count)
+            self.reqService(10, "sqrt" if t else "square", val, "Bob" if t else "Alice", tid)
+            self.reqService(25, "generate", None)
+
+        def result(self, data, tx, txId):                        # hello.js:54-59
+            self._commit("result", data, tx, txId)
+
+    class Alice(Base):
+        def square(self, data, tx, txId):                        # hello.js:50-52
+            self._commit("square", data, tx, txId)
+            self.reqService(10, "result", data * data, tx, txId)
+
+    class Bob(Base):
+        def sqrt(self, data, tx, txId):                          # hello.js:86-88
+            self._commit("sqrt", data, tx, txId)
+            self.reqService(10, "result", math.sqrt(data), tx, txId)
+
+    for i in range(count):                                       # hello.js:98-101
+        eng.addEntity("Alice", Alice, i)
+        eng.addEntity("Bob", Bob, i)
+    for i in range(count):                                       # hello.js:103-106
+        eng.schedService(0, "generate", None, "Alice", i)
+        eng.schedService(50, "generate", None, "Bob", i)
+    eng.run()
+    ents = ([eng.getEntity("Alice", i) for i in range(count)] +
+            [eng.getEntity("Bob", i) for i in range(count)])
+    out = dict(case)
+    out.update(total_events=sum(e.count for e in ents),
+               last_time_hex=float(eng.now).hex(),
+               counts=[e.count for e in ents],
+               hashes=["%016x" % e.hash for e in ents],
+               order_dependent=[bool(e.dist_tied) for e in ents],
+               ties=stats["ties"], distinguishable_ties=stats["dist_ties"])
+    eng.exit()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reference", default="/root/reference")
@@ -243,6 +326,24 @@ def main():
                                 "(oracle tie_mode=1) on these cases",
                    "cases": lres}, f, separators=(",", ":"))
     print("wrote", lpath, os.path.getsize(lpath), "bytes")
+    # hello.js: integer delays -> many distinguishable same-entity ties, whose
+    # order is engine specific (FIFO here, heap shape in SimianJS): counts are
+    # pinned for every entity, trace hashes for the entities that saw none.
+    with tempfile.TemporaryDirectory() as tmp:
+        os.chdir(tmp)
+        try:
+            hres = [run_hello_case(Simian, c) for c in HELLO_CASES]
+        finally:
+            os.chdir(cwd)
+    for r in hres:
+        print(r["name"], "events", r["total_events"], "ties", r["ties"], "distinguishable",
+              r["distinguishable_ties"], "order-dependent entities", sum(r["order_dependent"]))
+    hpath = os.path.join(os.path.dirname(out_path), "hello_simianpie.json")
+    with open(hpath, "w") as f:
+        json.dump({"generator": "oracle/pin_simianpie.py",
+                   "reference_engine": "SimianPie/simian.py (unmodified)",
+                   "cases": hres}, f, separators=(",", ":"))
+    print("wrote", hpath, os.path.getsize(hpath), "bytes")
 
 
 if __name__ == "__main__":

@@ -257,3 +257,14 @@ def lanl_construct(p, st, ctx):
     st.time_sends = [0] * LANL_TIME_BINS
     ctx.req_service(p.end_time - ctx.now, "FinishHandler", 0, None)
     lanl_send_body(p, st, ctx, di)
+
+
+# ---- hello.js handlers: transcription of simian_hello_* (simian_models.h) ------
+
+def hello_generate(seed, gid, commit_idx, count):
+    """-> (target class 0=Alice/1=Bob, target id, data f64)"""
+    key = rng_key(seed, gid, commit_idx)
+    target = int(u01(rng_draw(key, 0)) * 2.0)
+    target_id = int(u01(rng_draw(key, 1)) * float(count))
+    data = u01(rng_draw(key, 2)) * 100.0
+    return target, target_id, data

@@ -60,25 +60,36 @@ enum {
 };
 
 /* ---- SimianJS/eventQ.js : binary heap, head = least time ----------------- */
+struct QItem {
+  simian_event_t e;
+  uint64_t ec; /* push counter: only tie_mode 2 looks at it */
+};
+
 struct EventQ {
-  std::vector<simian_event_t> list;
-  int tie_mode; /* 0: literal JS (time only); 1: engine's defined order */
+  std::vector<QItem> list;
+  uint64_t ec = 0;
+  /* 0: literal JS (time only, eventQ.js:36,62,66); 1: the engine's defined order
+   * (time, handler, src, seq); 2: FIFO among equal times, the order of the
+   * reference's Python twin (heapq of (time, ec, e), SimianPie/simian.py:286-287) */
+  int tie_mode;
 
   /* `a.time < b.time` (eventQ.js:36) */
-  bool lt(const simian_event_t &a, const simian_event_t &b) const {
-    if (!tie_mode) return a.time < b.time;
-    return simian_event_before(a.time, a.handler, a.src, a.seq, b.time,
-                               b.handler, b.src, b.seq) != 0;
+  bool lt(const QItem &a, const QItem &b) const {
+    if (tie_mode == 0) return a.e.time < b.e.time;
+    if (tie_mode == 2) return a.e.time != b.e.time ? a.e.time < b.e.time : a.ec < b.ec;
+    return simian_event_before(a.e.time, a.e.handler, a.e.src, a.e.seq, b.e.time,
+                               b.e.handler, b.e.src, b.e.seq) != 0;
   }
 
-  void push(const simian_event_t &item) { /* eventQ.js:29-43 */
+  void push(const simian_event_t &ev) { /* eventQ.js:29-43 */
+    QItem item{ev, ec++};
     size_t curPos, parentPos = list.size();
     list.push_back(item);
     while (parentPos > 0) {
       curPos = parentPos;
       parentPos = parentPos / 2; /* floor(parentPos/2) on a 0-based array */
       if (lt(list[curPos], list[parentPos])) {
-        simian_event_t temp = list[curPos];
+        QItem temp = list[curPos];
         list[curPos] = list[parentPos];
         list[parentPos] = temp;
       } else
@@ -86,15 +97,15 @@ struct EventQ {
     }
   }
 
-  double peek() const { return list[0].time; } /* eventQ.js:45-47 */
-  size_t length() const { return list.size(); } /* eventQ.js:49-51 */
+  double peek() const { return list[0].e.time; } /* eventQ.js:45-47 */
+  size_t length() const { return list.size(); }   /* eventQ.js:49-51 */
 
   simian_event_t pop() { /* eventQ.js:53-92 */
     size_t length = list.size() - 1;
-    simian_event_t temp = list[0];
+    QItem temp = list[0];
     list[0] = list[length];
     list[length] = temp;
-    simian_event_t topItem = list.back();
+    QItem topItem = list.back();
     list.pop_back();
     size_t curPos = 0, left = 1, right = 2, min = 0;
     int state = 0;
@@ -128,7 +139,7 @@ struct EventQ {
         state = 0;
       }
     }
-    return topItem;
+    return topItem.e;
   }
 };
 
@@ -249,6 +260,7 @@ struct HostCtx {
                : nullptr;
   }
   uint32_t src() const { return ev ? ev->src : SIMIAN_NULL_ENTITY; }
+  uint64_t data() const { return ev ? ev->data : 0; }
 
   /* Entity.reqService  (entity.js:35-68) */
   void req_service(double offset, uint16_t service, uint64_t data, uint32_t rx) {
@@ -341,6 +353,18 @@ void dispatch(World *w, Rank *r, const simian_event_t &ev) {
     case SIMIAN_FN_LANL_FINISH:
       simian_lanl_finish(ctx);
       break;
+    case SIMIAN_FN_HELLO_GENERATE:
+      simian_hello_generate(ctx);
+      break;
+    case SIMIAN_FN_HELLO_SQUARE:
+      simian_hello_square(ctx);
+      break;
+    case SIMIAN_FN_HELLO_SQRT:
+      simian_hello_sqrt(ctx);
+      break;
+    case SIMIAN_FN_HELLO_RESULT:
+      simian_hello_result(ctx);
+      break;
     default:
       if (!r->error) {
         r->error = ORACLE_ERR_UNKNOWN;
@@ -356,6 +380,10 @@ int fn_by_name(const char *n) {
   if (!strcmp(n, "lanl_receive")) return SIMIAN_FN_LANL_RECEIVE;
   if (!strcmp(n, "lanl_finish")) return SIMIAN_FN_LANL_FINISH;
   if (!strcmp(n, "lanl_construct")) return SIMIAN_FN_LANL_CONSTRUCT;
+  if (!strcmp(n, "hello_generate")) return SIMIAN_FN_HELLO_GENERATE;
+  if (!strcmp(n, "hello_square")) return SIMIAN_FN_HELLO_SQUARE;
+  if (!strcmp(n, "hello_sqrt")) return SIMIAN_FN_HELLO_SQRT;
+  if (!strcmp(n, "hello_result")) return SIMIAN_FN_HELLO_RESULT;
   return SIMIAN_FN_NONE;
 }
 
@@ -444,6 +472,7 @@ int oracle_add_entities(void *o, const char *className, uint32_t first,
   if (!w->class_ix.count(className)) oracle_define_class(o, className, 0);
   int ci = w->class_ix[className];
   ClassInfo &c = w->classes[ci];
+  if (c.count == 0) c.first_id = w->n_ids; /* ids are dealt when the first instance arrives */
   if (first != c.count || c.first_id + c.count != w->n_ids) {
     w->fail(ORACLE_ERR_UNKNOWN, "entities must be added contiguously");
     return ORACLE_ERR_UNKNOWN;

@@ -127,6 +127,10 @@ int builtin_fn_by_name(const char *n) {
   if (!strcmp(n, "lanl_receive")) return SIMIAN_FN_LANL_RECEIVE;
   if (!strcmp(n, "lanl_finish")) return SIMIAN_FN_LANL_FINISH;
   if (!strcmp(n, "lanl_construct")) return SIMIAN_FN_LANL_CONSTRUCT;
+  if (!strcmp(n, "hello_generate")) return SIMIAN_FN_HELLO_GENERATE;
+  if (!strcmp(n, "hello_square")) return SIMIAN_FN_HELLO_SQUARE;
+  if (!strcmp(n, "hello_sqrt")) return SIMIAN_FN_HELLO_SQRT;
+  if (!strcmp(n, "hello_result")) return SIMIAN_FN_HELLO_RESULT;
   return SIMIAN_FN_NONE;
 }
 
@@ -605,6 +609,7 @@ int simian_add_entities(simian_engine *e, const char *className, uint32_t firstN
   int ci = simian_define_class(e, className, 0);
   if (ci < 0) return -ci;
   HostClass &h = e->classes[ci];
+  if (h.count == 0) h.first_id = e->n_ids; // ids are dealt when the first instance arrives
   if (firstNum != h.count || h.first_id + h.count != e->n_ids)
     return e->fail(SIMIAN_ERR_BAD_ARGUMENT,
                    "instances of a class must be added contiguously from 0, class after class");

@@ -588,6 +588,7 @@ struct DevCtx {
                : nullptr;
   }
   __device__ __forceinline__ uint32_t src() const { return src_; }
+  __device__ __forceinline__ unsigned long long data() const { return data_; }
 
   __device__ __forceinline__ void put_local(const RecBits &r) {
     unsigned long long tk = simian_time_key(r.time());
@@ -669,6 +670,14 @@ __device__ __forceinline__ void run_pure_handler(DevCtx<false> &ctx, uint32_t fn
     simian_phold_generate(ctx);
   else if (fn == SIMIAN_FN_COUNT_ONLY)
     simian_noop(ctx);
+  else if (fn == SIMIAN_FN_HELLO_GENERATE)
+    simian_hello_generate(ctx);
+  else if (fn == SIMIAN_FN_HELLO_SQUARE)
+    simian_hello_square(ctx);
+  else if (fn == SIMIAN_FN_HELLO_SQRT)
+    simian_hello_sqrt(ctx);
+  else if (fn == SIMIAN_FN_HELLO_RESULT)
+    simian_hello_result(ctx);
   else
     set_error(ctx.c, SIMIAN_ERR_UNKNOWN_NAME);
 }
@@ -693,6 +702,18 @@ __device__ __forceinline__ void run_handler(DevCtx<SEQ> &ctx, uint32_t fn) {
       break;
     case SIMIAN_FN_LANL_CONSTRUCT:
       simian_lanl_construct(ctx);
+      break;
+    case SIMIAN_FN_HELLO_GENERATE:
+      simian_hello_generate(ctx);
+      break;
+    case SIMIAN_FN_HELLO_SQUARE:
+      simian_hello_square(ctx);
+      break;
+    case SIMIAN_FN_HELLO_SQRT:
+      simian_hello_sqrt(ctx);
+      break;
+    case SIMIAN_FN_HELLO_RESULT:
+      simian_hello_result(ctx);
       break;
     default:
       set_error(ctx.c, SIMIAN_ERR_UNKNOWN_NAME);

@@ -112,6 +112,7 @@ class Simian(object):
                               rank=self.rank, size=self.size, device=device,
                               seed=seed, **options)
         self._classes = {}
+        self._added = {}     # class -> instances announced by addEntity, not yet in the engine
         self._pending = []   # host records injected before run
         self._seq = 0
         self.out = None      # the per-rank log "<name>.<rank>.out" is opt-in
@@ -157,9 +158,21 @@ class Simian(object):
         self._register_class(name, entityClass)
         ents = self.entities.setdefault(name, {})
         self.baseRanks[name] = self.getBaseRank(name)
-        self._h.add_entities(name, num, 1)
+        # The engine numbers entities class after class; model scripts may
+        # interleave classes (hello.js:98-101), so the instances are counted
+        # here and handed over in one piece per class (_flush_entities).
+        first, cnt = self._added.get(name, (num, 0))
+        if num != first + cnt:
+            raise SimianError(6, "instances of %s must be added as 0, 1, 2, ..." % name)
+        self._added[name] = (first, cnt + 1)
         if self.getOffsetRank(name, num) == self.rank:            # simian.js:223
             ents[num] = entityClass(name, self.out, self, num, *theArgs)
+
+    def _flush_entities(self):
+        for name in self._classes:            # registration order = id order
+            if name in self._added:
+                first, cnt = self._added.pop(name)
+                self._h.add_entities(name, first, cnt)
 
     def addEntities(self, name, entityClass, first, count):
         """Bulk form of the model-script loop `for i: addEntity(name, K, i)`
@@ -169,6 +182,7 @@ class Simian(object):
             raise SimianError(4, "Cannot add new entity when Simian is running!")
         self._register_class(name, entityClass)
         self.baseRanks[name] = self.getBaseRank(name)
+        self._flush_entities()
         self._h.add_entities(name, first, count)
         self.entities.setdefault(name, _LazyEntities(self, name, entityClass))
 
@@ -176,19 +190,27 @@ class Simian(object):
         self._h.set_class_params(name, bytes(blob))
 
     def firstId(self, name):
+        """global id of instance 0 (needs every entity to have been added)"""
+        self._flush_entities()
         return self._h.first_id(name)
+
+    def internService(self, name):
+        return self._h.intern_service(name)
 
     def schedService(self, time, eventName, data, rx, rxId):      # simian.js:170-190
         if time > self.endTime:
             return
+        self._flush_entities()
         self._h.sched_service(time, eventName, int(data or 0), rx, rxId)
 
     def schedServiceBulk(self, time, eventName, data, rx, first, count, repeat=1):
+        self._flush_entities()
         self._h.sched_service_bulk(time, eventName, int(data or 0), rx, first,
                                    count, repeat)
 
     def _inject(self, time, eventName, data, rx, rxId, tx, txId):
         import numpy as np
+        self._flush_entities()
         ev = np.zeros(1, dtype=capi.EVENT_DTYPE)
         ev["time"] = time
         ev["dst"] = self._h.first_id(rx) + rxId
@@ -201,6 +223,7 @@ class Simian(object):
 
     # ---- run ------------------------------------------------------------------
     def run(self):                                                # simian.js:99-168
+        self._flush_entities()
         self.running = True
         try:
             if self.size == 1:

@@ -137,3 +137,36 @@ def lanl_states(raw, n_ent, m_ent):
     st = a[:, :168].copy().view(LANL_STATE_DTYPE).reshape(n_ent)
     lists = a[:, 168:].copy().view("<f8").reshape(n_ent, -1)
     return st, lists
+
+
+# ---- hello.js: two entity classes, data-carrying events, replies to tx/txId ----
+
+HELLO_SERVICES = ("generate", "square", "sqrt", "result")
+
+
+def hello_params_blob(alice_first, bob_first, count, ids):
+    """Pack simian_hello_params_t (include/simian_models.h), 24 bytes."""
+    blob = struct.pack("<IIIIHHHH", alice_first, bob_first, count, 0, *ids)
+    assert len(blob) == 24
+    return blob
+
+
+def build_hello(eng, count, t_alice=0.0, t_bob=50.0):
+    """SimianJS/Examples/hello.js:96-109: `count` Alice and `count` Bob
+    entities, one initial `generate` each (Alice at 0, Bob at 50)."""
+    ids = [eng.intern_service(s) for s in HELLO_SERVICES]
+    for cls in ("Alice", "Bob"):
+        eng.define_class(cls, 0)
+        eng.add_entities(cls, 0, count)
+    eng.attach_service("Alice", "generate", "hello_generate")
+    eng.attach_service("Alice", "square", "hello_square")
+    eng.attach_service("Alice", "result", "hello_result")
+    eng.attach_service("Bob", "generate", "hello_generate")
+    eng.attach_service("Bob", "sqrt", "hello_sqrt")
+    eng.attach_service("Bob", "result", "hello_result")
+    blob = hello_params_blob(eng.first_id("Alice"), eng.first_id("Bob"), count, ids)
+    eng.set_class_params("Alice", blob)
+    eng.set_class_params("Bob", blob)
+    eng.sched_service_bulk(t_alice, "generate", 0, "Alice", 0, count, 1)
+    eng.sched_service_bulk(t_bob, "generate", 0, "Bob", 0, count, 1)
+    return eng

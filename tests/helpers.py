@@ -111,3 +111,18 @@ def assert_lanl_golden(case, st, counts, hashes, state, lists):
         assert [float(x).hex() for x in state[k]] == g[k], k
     assert [[int(x) for x in row] for row in state["time_sends"]] == g["time_sends"]
     assert [[float(x).hex() for x in row[:4]] for row in lists] == g["list_head"]
+
+
+# ---- hello.js (two classes) ----------------------------------------------------
+
+def run_hello(handle_factory, case):
+    """-> (stats, counts[2*count], hashes[2*count]) in global id order"""
+    from simian_b200.workloads import build_hello
+    h = handle_factory()
+    build_hello(h, case["count"])
+    st = h.run()
+    n = case["count"]
+    counts = np.concatenate([h.read_counts("Alice", n), h.read_counts("Bob", n)])
+    hashes = np.concatenate([h.read_trace_hashes("Alice", n), h.read_trace_hashes("Bob", n)])
+    h.close()
+    return st, counts, hashes

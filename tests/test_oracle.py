@@ -314,3 +314,39 @@ def test_oracle_threaded_ranks_equal_sequential(oracle_mod, size, threads):
     assert float(s1["last_time"]).hex() == float(s2["last_time"]).hex()
     np.testing.assert_array_equal(c1, c2)
     np.testing.assert_array_equal(h1, h2)
+
+
+# ---- hello.js: two classes, payloads, replies, integer delays --------------------
+
+HELLO_GOLD = os.path.join(os.path.dirname(__file__), "golden", "hello_simianpie.json")
+
+
+def hello_golden_cases():
+    with open(HELLO_GOLD) as f:
+        return json.load(f)["cases"]
+
+
+@pytest.mark.parametrize("case", hello_golden_cases(), ids=lambda c: c["name"])
+def test_oracle_hello_matches_simianpie(oracle_mod, case):
+    """multi-class placement, f64 payloads, replies to tx/txId against the
+    unmodified SimianPie engine.  With SimianPie's FIFO order of equal times
+    (tie_mode 2) everything matches, trace hashes of all entities included;
+    with the literal JS heap (0) and the engine's order (1) the counts match
+    and the hashes of the entities that saw no distinguishable tie."""
+    from helpers import run_hello
+    for tie_mode in (2, 0, 1):
+        st, counts, hashes = run_hello(
+            lambda: oracle_mod.Oracle(case["name"], 0.0, case["end"], case["min_delay"],
+                                      tie_mode=tie_mode, seed=case["seed"]), case)
+        assert st["total_events"] == case["total_events"]
+        assert list(counts) == case["counts"]
+        assert float(st["last_time"]).hex() == case["last_time_hex"]
+        assert st["ties"] == case["ties"]
+        hx = ["%016x" % x for x in hashes]
+        if tie_mode == 2:
+            assert hx == case["hashes"]
+            assert st["distinguishable_ties"] == case["distinguishable_ties"]
+        else:
+            for i, dep in enumerate(case["order_dependent"]):
+                if not dep:
+                    assert hx[i] == case["hashes"][i]

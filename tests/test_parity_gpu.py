@@ -197,3 +197,49 @@ def test_identical_records_are_all_committed(oracle_mod):
         np.testing.assert_array_equal(ce, co)
         np.testing.assert_array_equal(he, ho)
         assert se["digest"] == so["digest"]
+
+
+# ---- hello.js: two entity classes, payloads, replies to tx/txId ------------------
+
+HELLO_GOLD = os.path.join(os.path.dirname(__file__), "golden", "hello_simianpie.json")
+
+
+def hello_golden_cases():
+    with open(HELLO_GOLD) as f:
+        return json.load(f)["cases"]
+
+
+HELLO_CASES = hello_golden_cases() + [
+    dict(name="hello_two_blocks", count=700, end=260.0, min_delay=0.5, seed=3),
+    dict(name="hello_sparse_default_buckets", count=40, end=120.0, min_delay=0.01, seed=4,
+         default_buckets=True),
+]
+
+
+@pytest.mark.parametrize("case", HELLO_CASES, ids=lambda c: c["name"])
+@pytest.mark.parametrize("sequential", [0, 1], ids=["per_event", "per_entity"])
+def test_engine_hello_matches_oracle(case, sequential, oracle_mod):
+    """engine order of equal-time events = oracle tie_mode 1: bit-exact counts,
+    trace hashes, digest, tie statistics; entities of both classes share blocks"""
+    from helpers import run_hello
+    from simian_b200 import capi
+    opts = {} if case.get("default_buckets") else {"bucket_width": 1.0}
+    so, co, ho = run_hello(
+        lambda: oracle_mod.Oracle(case["name"], 0.0, case["end"], case["min_delay"],
+                                  tie_mode=1, seed=case["seed"]), case)
+    se, ce, he = run_hello(
+        lambda: capi.Engine(case["name"], 0.0, case["end"], case["min_delay"],
+                            seed=case["seed"], force_sequential=sequential, **opts), case)
+    assert se["error"] == 0
+    assert se["total_events"] == so["total_events"]
+    np.testing.assert_array_equal(ce, co)
+    np.testing.assert_array_equal(he, ho)
+    assert se["digest"] == so["digest"]
+    assert float(se["last_time"]).hex() == float(so["last_time"]).hex()
+    assert se["windows"] == so["windows"]
+    assert se["emitted"] == so["emitted"]
+    assert se["ties"] == so["ties"] > 0
+    assert se["distinguishable_ties"] == so["distinguishable_ties"] > 0
+    if "counts" in case:  # the unmodified SimianPie engine
+        assert list(ce) == case["counts"]
+        assert se["total_events"] == case["total_events"]

@@ -55,3 +55,47 @@ def test_reference_error_behaviour():
     with pytest.raises(capi.SimianError):         # unknown device function name
         eng.attachService(Node, "other", device_fn("no_such_fn"))
     eng.exit()
+
+
+def test_hello_script_shape_matches_simianpie_golden():
+    """SimianJS/Examples/hello.js:96-109 against the mirror API: two classes
+    added interleaved, schedService per entity, run; per-entity counts equal
+    the unmodified SimianPie engine's (tests/golden/hello_simianpie.json)."""
+    import json
+    import os
+    from simian_b200.simian import Entity, Simian, device_fn
+    from simian_b200.workloads import HELLO_SERVICES, hello_params_blob
+    gold = os.path.join(os.path.dirname(__file__), "golden", "hello_simianpie.json")
+    with open(gold) as f:
+        case = json.load(f)["cases"][0]
+    count = case["count"]
+
+    class Alice(Entity):
+        generate = device_fn("hello_generate")
+        square = device_fn("hello_square")
+        result = device_fn("hello_result")
+
+    class Bob(Entity):
+        generate = device_fn("hello_generate")
+        sqrt = device_fn("hello_sqrt")
+        result = device_fn("hello_result")
+
+    eng = Simian("HELLO", 0, case["end"], case["min_delay"], False, seed=case["seed"],
+                 bucket_width=1.0)
+    ids = [eng.internService(s) for s in HELLO_SERVICES]
+    for i in range(count):                       # hello.js:98-101
+        eng.addEntity("Alice", Alice, i)
+        eng.addEntity("Bob", Bob, i)
+    blob = hello_params_blob(eng.firstId("Alice"), eng.firstId("Bob"), count, ids)
+    eng.setClassParams("Alice", blob)
+    eng.setClassParams("Bob", blob)
+    for i in range(count):                       # hello.js:103-106
+        eng.schedService(0, "generate", None, "Alice", i)
+        eng.schedService(50, "generate", None, "Bob", i)
+    st = eng.run()
+    assert st["total_events"] == case["total_events"]
+    got = ([eng.getEntity("Alice", i).count for i in range(count)] +
+           [eng.getEntity("Bob", i).count for i in range(count)])
+    assert got == case["counts"]
+    assert float(eng.now).hex() == case["last_time_hex"]
+    eng.exit()
