@@ -566,6 +566,10 @@ struct DevCtx {
   // index) instead of being appended right away; SIMIAN_NONE = append directly
   WindowShared *stage_sh;
   uint32_t stage;
+  // fold the times of LOCALLY routed records into the LBTS candidate (window
+  // kernel: yes; constructors: no -- the calendar search finds those, and a
+  // candidate that a later window commits would move the window bounds)
+  bool local_min;
   // same-window self-sends (rx omitted, offset < minDelay allowed: entity.js:41)
   int npend;
   double pend_time[SEQ ? SIMIAN_SELF_MAX : 1];
@@ -573,7 +577,8 @@ struct DevCtx {
 
   __device__ __forceinline__ DevCtx(const DevCfg &c_, const WinState &W_, AppendCtx &ax_,
                                     ThreadAcc &ta_)
-      : c(c_), W(W_), ax(ax_), ta(ta_), stage_sh(nullptr), stage(SIMIAN_NONE), npend(0) {}
+      : c(c_), W(W_), ax(ax_), ta(ta_), stage_sh(nullptr), stage(SIMIAN_NONE), local_min(true),
+        npend(0) {}
 
   __device__ __forceinline__ double now() const { return now_; }
   __device__ __forceinline__ uint32_t self_id() const { return self_gid; }
@@ -591,8 +596,10 @@ struct DevCtx {
   __device__ __forceinline__ unsigned long long data() const { return data_; }
 
   __device__ __forceinline__ void put_local(const RecBits &r) {
-    unsigned long long tk = simian_time_key(r.time());
-    ta.min_key = tk < ta.min_key ? tk : ta.min_key;
+    if (local_min) {
+      unsigned long long tk = simian_time_key(r.time());
+      ta.min_key = tk < ta.min_key ? tk : ta.min_key;
+    }
     ta.appended++;
     if (!SEQ && stage != SIMIAN_NONE) { // K4 is done by the append phase of k_window
       slot_put(*stage_sh, stage, r);
@@ -738,6 +745,7 @@ __global__ void k_construct(const __grid_constant__ DevCfg c, int cls, uint32_t 
   for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < cl.n_local;
        j += gridDim.x * blockDim.x) {
     DevCtx<false> ctx(c, W, ax, ta);
+    ctx.local_min = false;
     int k;
     ctx.self_slot = cl.slot_base + j;
     ctx.self_gid = gid_of_slot(c, ctx.self_slot, k);
@@ -1172,8 +1180,10 @@ __device__ void setup_next_window(const DevCfg &c, const WinState &W, WinState *
     }
     nw.alloc_limit = ld_cg64(&a->free_tail);
 #ifdef SIMIAN_PROFILE_PHASES
+#ifndef SIMIAN_PROFILE_KEEP_FIRST
     if (a->windows == 1) // steady-state windows only: drop the t = 0 burst window
       for (int q = 0; q < 12; q++) a->phase_cycles[q] = 0;
+#endif
 #endif
     a->min_key = SIMIAN_KEY_NONE;
     a->ticket = 0;
@@ -1713,12 +1723,16 @@ __global__ void __launch_bounds__(NTHREADS) k_begin(const __grid_constant__ DevC
   __syncthreads();
   const double inf = __longlong_as_double(0x7FF0000000000000LL);
   unsigned long long far = c.acc->far_min[0];
+  // what entity constructors sent to other ranks waits in outbox 0 until the
+  // first window's exchange: only this rank's candidate covers it
+  const unsigned long long keep_min = c.acc->min_key;
   setup_next_window(c, w0, &c.win[0], c.start, far == SIMIAN_KEY_NONE ? inf : simian_key_time(far),
                     false);
   if (threadIdx.x == 0) {
     c.acc->windows = 0;
     c.acc->window_index = 0;
     c.win[0].parity = 0;
+    c.acc->min_key = keep_min;
   }
 }
 

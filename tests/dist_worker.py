@@ -33,10 +33,45 @@ CASES = {
 }
 
 
+LANL = dict(kind="lanl", n_ent=2100, s_ent=12.0, q_avg=2.0, p_receive=0.002, m_ent=24.0,
+            ops_ent=30.0, ops_sigma=0.2, cache_friendliness=0.5, end_time=8.0,
+            min_delay=0.5, time_bins=16, seed=4)
+HELLO = dict(kind="hello", count=300, end=200.0, min_delay=0.5, seed=3)
+CASES["lanl"] = LANL
+CASES["hello"] = HELLO
+
+
 def build(eng, c, world):
+    if c.get("kind") == "lanl":
+        from simian_b200.workloads import build_lanl
+        keys = ("n_ent", "s_ent", "q_avg", "p_receive", "m_ent", "ops_ent", "ops_sigma",
+                "cache_friendliness", "end_time", "min_delay", "time_bins")
+        build_lanl(eng, **{k: c[k] for k in keys})
+        return
+    if c.get("kind") == "hello":
+        from simian_b200.workloads import build_hello
+        build_hello(eng, c["count"])
+        return
     groups = c["groups"] or world
     build_phold(eng, c["n"], c["per_entity"], c["lookahead"], c["p_remote"], 1.0,
                 c["mode"], groups)
+
+
+def shape(c):
+    """-> (engine end time, minDelay, [(class, count)], oracle tie mode)"""
+    if c.get("kind") == "lanl":
+        from simian_b200.workloads import LANL_CLASS, lanl_engine_end
+        return (lanl_engine_end(c["end_time"], c["min_delay"]), c["min_delay"],
+                [(LANL_CLASS, c["n_ent"])], 1)
+    if c.get("kind") == "hello":
+        return c["end"], c["min_delay"], [("Alice", c["count"]), ("Bob", c["count"])], 1
+    return c["end"], c["min_delay"], [("Node", c["n"])], 0
+
+
+def read_all(h, classes):
+    cnt = np.concatenate([h.read_counts(k, n) for k, n in classes])
+    hsh = np.concatenate([h.read_trace_hashes(k, n) for k, n in classes])
+    return cnt, hsh
 
 
 def main():
@@ -58,28 +93,34 @@ def main():
     om.build()
     for name in a.cases.split(","):
         c = CASES[name]
+        end, min_delay, classes, tie_mode = shape(c)
         # single-process reference run of the same model
-        ref = om.Oracle("ref", 0.0, c["end"], c["min_delay"], size=1, seed=c["seed"])
+        ref = om.Oracle("ref", 0.0, end, min_delay, size=1, seed=c["seed"], tie_mode=tie_mode)
         build(ref, c, world)
         st_ref = ref.run()
-        cnt_ref = ref.read_counts("Node", c["n"])
-        h_ref = ref.read_trace_hashes("Node", c["n"])
-        assert st_ref["distinguishable_ties"] == 0
+        cnt_ref, h_ref = read_all(ref, classes)
+        if tie_mode == 0:
+            assert st_ref["distinguishable_ties"] == 0
         if a.engine == "oracle":
-            o = om.Oracle("dist", 0.0, c["end"], c["min_delay"], size=world,
-                          seed=c["seed"])
+            o = om.Oracle("dist", 0.0, end, min_delay, size=world, seed=c["seed"],
+                          tie_mode=tie_mode)
             build(o, c, world)
             eng = om.OracleRankEngine(o, rank, world)
             st = drive_windows(eng, rank, world)
-            cnt = o.read_counts("Node", c["n"])
-            h = o.read_trace_hashes("Node", c["n"])
-            mine = np.array([o.L.oracle_owner_rank(o.h, g) == rank
-                             for g in range(c["n"])])
+            cnt, h = read_all(o, classes)
+            gid0 = 0
+            mine = []
+            for k, n in classes:
+                mine += [o.L.oracle_owner_rank(o.h, gid0 + g) == rank for g in range(n)]
+                gid0 += n
+            mine = np.array(mine)
         else:
             from simian_b200 import capi
             from simian_b200.distributed import GpuRankEngine
-            opts = {"bucket_width": 1.0 / 32} if c["min_delay"] < 0.05 else {}
-            e = capi.Engine("dist", 0.0, c["end"], c["min_delay"], rank=rank,
+            opts = {"bucket_width": 1.0 / 32} if min_delay < 0.05 else {}
+            if c.get("kind") == "hello":
+                opts = {"bucket_width": 1.0}
+            e = capi.Engine("dist", 0.0, end, min_delay, rank=rank,
                             size=world, device=local, seed=c["seed"], **opts)
             build(e, c, world)
             if a.driver in ("p2p", "p2p_nccl"):
@@ -88,10 +129,9 @@ def main():
                                        allreduce="peer" if a.driver == "p2p" else "nccl")
             else:
                 st = drive_windows(GpuRankEngine(e, "cuda:%d" % local), rank, world)
-            cnt = e.read_counts("Node", c["n"])
-            h = e.read_trace_hashes("Node", c["n"])
-            base = e.base_rank("Node")
-            mine = (base + np.arange(c["n"])) % world == rank
+            cnt, h = read_all(e, classes)
+            mine = np.concatenate([(e.base_rank(k) + np.arange(n)) % world == rank
+                                   for k, n in classes])
             e.close()
         assert mine.sum() > 0
         np.testing.assert_array_equal(cnt[mine], cnt_ref[mine])

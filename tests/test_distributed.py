@@ -32,8 +32,9 @@ def _launch(nproc, *args, timeout=600):
 
 @pytest.mark.parametrize("world", [2, 3])
 def test_window_driver_over_gloo(world, oracle_mod):
-    out = _launch(world, "--engine", "oracle", "--backend", "gloo")
-    assert out.count("DIST-OK") == 3
+    out = _launch(world, "--engine", "oracle", "--backend", "gloo", "--cases",
+                  "ross,other_group,uniform_sparse,lanl,hello")
+    assert out.count("DIST-OK") == 5
 
 
 @pytest.mark.gpu
@@ -45,5 +46,6 @@ def test_cuda_engine_over_nccl_two_gpus():
     for w in sorted({2, world}):
         for driver in ("p2p", "p2p_nccl", "nccl"):
             out = _launch(w, "--engine", "cuda", "--backend", "nccl", "--driver",
-                          driver, "--cases", "ross,other_group,uniform_sparse,big")
-            assert out.count("DIST-OK") == 4, driver
+                          driver, "--cases",
+                          "ross,other_group,uniform_sparse,big,lanl,hello")
+            assert out.count("DIST-OK") == 6, driver
