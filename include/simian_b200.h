@@ -43,7 +43,8 @@ enum simian_status {
   SIMIAN_ERR_OUTBOX_FULL = 11,   /* cross-GPU staging buffer full: raise "outbox_events"  */
   SIMIAN_ERR_RING_SPAN = 12,     /* window spans the whole calendar ring: raise "bucket_width" */
   SIMIAN_ERR_CUDA = 13,
-  SIMIAN_ERR_NO_DEVICE = 14 /* no CUDA device: there is NO CPU fallback                   */
+  SIMIAN_ERR_NO_DEVICE = 14, /* no CUDA device: there is NO CPU fallback                  */
+  SIMIAN_ERR_STALLED = 15    /* a device-side wait (page install, peer flag) timed out     */
 };
 
 /* What Simian.run prints (simian.js:159-164) plus the parity quantities. */

@@ -208,6 +208,7 @@ const char *status_text(int code) {
     case SIMIAN_ERR_SELF_PENDING: return "too many same-window self-sends pending on one entity";
     case SIMIAN_ERR_OUTBOX_FULL: return "cross-GPU outbox full: raise option outbox_events";
     case SIMIAN_ERR_RING_SPAN: return "window spans too many calendar sub-buckets: raise option bucket_width";
+    case SIMIAN_ERR_STALLED: return "a device-side wait timed out (page install or peer exchange flag)";
     default: return "error";
   }
 }

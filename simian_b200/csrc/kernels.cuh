@@ -246,9 +246,14 @@ __device__ __noinline__ void cell_append_slow(const DevCfg &c, AppendCtx &ax,
       atomicExch(hp, ((unsigned long long)np << 32) | 1ull);
       return;
     }
+    uint32_t spins = 0;
 #pragma unroll 1
     while ((uint32_t)(ld_cg64(hp) >> 32) == p) { // wait for the installer
       if (ld_cg(&c.acc->error)) return;
+      if (++spins > (1u << 24)) { // seconds: never legitimately; fail, do not hang
+        set_error(c, SIMIAN_ERR_STALLED);
+        return;
+      }
       __nanosleep(40);
     }
     old = atomicAdd(hp, 1ull);
@@ -459,8 +464,13 @@ __global__ void k_pull(const __grid_constant__ DevCfg c, uint32_t win_ix, uint32
     const volatile unsigned long long *f =
         &c.xch[W.parity * (uint32_t)c.size + threadIdx.x].seq;
     const unsigned long long want = (unsigned long long)win_ix + 1ull;
+    uint32_t spins = 0;
     while (*f != want) {
       if (ld_cg(&c.acc->error)) break;
+      if (++spins > (1u << 27)) { // > 10 s: a peer died or never launched this window
+        set_error(c, SIMIAN_ERR_STALLED);
+        break;
+      }
       __nanosleep(100);
     }
     __threadfence_system();
@@ -1485,16 +1495,35 @@ __global__ void __launch_bounds__(NTHREADS, SIMIAN_MINBLOCKS)
 #pragma unroll
           for (int u = 0; u < EV_PER_THREAD; u++)
             if (cell[u] != SIMIAN_NONE) old[u] = atomicAdd(c.cell_state + cell[u], 1ull);
+          // Claims are serviced in two rounds so that no thread ever waits for a
+          // page while it still owes one: first every claim that landed in a
+          // page or must INSTALL one (never blocks); only then the claims that
+          // have to wait for another thread's install.  (Waiting first can
+          // deadlock: two threads holding crossed install/wait claims.)
+          uint32_t waiting = 0;
 #pragma unroll
           for (int u = 0; u < EV_PER_THREAD; u++)
             if (cell[u] != SIMIAN_NONE) {
-              const RecBits r = slot_get(sh, tid + u * NTHREADS);
-              if ((uint32_t)old[u] < (uint32_t)PAGE)
-                st_rec(c.pool + ((size_t)(uint32_t)(old[u] >> 32) * PAGE + (uint32_t)old[u]), r);
-              else
-                cell_append_slow(c, sh.ax, W.alloc_limit, c.cell_state + cell[u], old[u], r.q0, r.q1,
-                                 r.q2, r.q3);
+              if ((uint32_t)old[u] <= (uint32_t)PAGE) {
+                const RecBits r = slot_get(sh, tid + u * NTHREADS);
+                if ((uint32_t)old[u] < (uint32_t)PAGE)
+                  st_rec(c.pool + ((size_t)(uint32_t)(old[u] >> 32) * PAGE + (uint32_t)old[u]), r);
+                else
+                  cell_append_slow(c, sh.ax, W.alloc_limit, c.cell_state + cell[u], old[u], r.q0,
+                                   r.q1, r.q2, r.q3);
+              } else {
+                waiting |= 1u << u;
+              }
             }
+          if (waiting) { // rare
+#pragma unroll
+            for (int u = 0; u < EV_PER_THREAD; u++)
+              if (waiting & (1u << u)) {
+                const RecBits r = slot_get(sh, tid + u * NTHREADS);
+                cell_append_slow(c, sh.ax, W.alloc_limit, c.cell_state + cell[u], old[u], r.q0,
+                                 r.q1, r.q2, r.q3);
+              }
+          }
         }
         PHASE(5);
         // C, one thread per entity: fold the trace hash chain, publish the count

@@ -243,3 +243,26 @@ def test_engine_hello_matches_oracle(case, sequential, oracle_mod):
     if "counts" in case:  # the unmodified SimianPie engine
         assert list(ce) == case["counts"]
         assert se["total_events"] == case["total_events"]
+
+
+@pytest.mark.timeout(120)
+def test_contended_cells_many_page_installs(oracle_mod):
+    """integer delays: thousands of events per window land in the same few
+    calendar cells, pages fill and are installed while many claims are in
+    flight (the append phase holds up to four claims per thread).  Regression
+    for a deadlock between crossed install/wait claims; repeated because it was
+    timing dependent."""
+    from helpers import run_hello
+    from simian_b200 import capi
+    case = dict(name="hello_contended", count=3000, end=180.0, min_delay=0.5, seed=11)
+    so, co, ho = run_hello(
+        lambda: oracle_mod.Oracle(case["name"], 0.0, case["end"], case["min_delay"],
+                                  tie_mode=1, seed=case["seed"]), case)
+    for rep in range(4):
+        se, ce, he = run_hello(
+            lambda: capi.Engine(case["name"], 0.0, case["end"], case["min_delay"],
+                                seed=case["seed"], bucket_width=1.0), case)
+        assert se["error"] == 0
+        assert se["total_events"] == so["total_events"]
+        np.testing.assert_array_equal(ce, co)
+        np.testing.assert_array_equal(he, ho)

@@ -5,7 +5,7 @@ TAG=${1:-x}
 OUT=gpurun_out
 mkdir -p $OUT
 if [ -z "$2" ]; then
-  timeout 900 python -m pytest tests -m gpu -x -q > $OUT/pytest_$TAG.log 2>&1
+  timeout 300 python -m pytest tests -m gpu -x -q --timeout 120 > $OUT/pytest_$TAG.log 2>&1
   echo "pytest rc=$?"; tail -5 $OUT/pytest_$TAG.log
 fi
 timeout 600 python bench.py > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err
