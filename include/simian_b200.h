@@ -195,6 +195,10 @@ int simian_setup(simian_engine *e);
 /* blob == NULL: *written = blob size.  Otherwise fills the blob to publish. */
 int simian_ipc_export(simian_engine *e, void *blob, uint64_t blobBytes, uint64_t *written);
 int simian_ipc_import(simian_engine *e, int peerRank, const void *blob, uint64_t blobBytes);
+/* simian_window_process with the LBTS candidate computed by the last CTA of
+ * the same launch (no separate simian_window_local_min / publish_min launch);
+ * publish != 0: and written to the peers' exchange slots                     */
+int simian_window_process_lbts(simian_engine *e, int publish);
 /* waitForPeers != 0: first wait (on the device) until every rank has
  * published this window's LBTS candidate, i.e. finished its window           */
 int simian_window_pull(simian_engine *e, int waitForPeers);

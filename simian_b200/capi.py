@@ -78,6 +78,7 @@ SIGNATURES = {
     "simian_ipc_import": (_i, [_vp, _i, _vp, _u64]),
     "simian_window_pull": (_i, [_vp, _i]),
     "simian_window_publish_min": (_i, [_vp]),
+    "simian_window_process_lbts": (_i, [_vp, _i]),
     "simian_window_advance_async": (_i, [_vp, _i]),
     "simian_poll": (_i, [_vp, C.POINTER(_i)]),
     "simian_minvec_ptr": (_i, [_vp, C.POINTER(_vp)]),
@@ -252,6 +253,9 @@ class Engine:
 
     def window_pull(self, wait_for_peers=False):
         self._ck(self.L.simian_window_pull(self.h, int(wait_for_peers)))
+
+    def window_process_lbts(self, publish=True):
+        self._ck(self.L.simian_window_process_lbts(self.h, int(publish)))
 
     def window_publish_min(self):
         self._ck(self.L.simian_window_publish_min(self.h))

@@ -870,6 +870,14 @@ int simian_window_process(simian_engine *e) {
   return 0;
 }
 
+int simian_window_process_lbts(simian_engine *e, int publish) {
+  k_window<<<e->cfg.n_blocks, NTHREADS, e->smem_bytes, e->stream>>>(e->cfg, e->win_ix,
+                                                                  publish ? 3 : 2);
+  CK(cudaGetLastError());
+  e->launches++;
+  return 0;
+}
+
 int simian_window_outbox(simian_engine *e, uint32_t *hostCounts, void **devOutbox,
                          uint64_t *cap) {
   if (e->size == 1) {

@@ -1346,8 +1346,46 @@ __device__ void reduce_parts(const DevCfg &c, WindowShared &sh) {
   __syncthreads();
 }
 
+// size > 1: this rank's minLeft candidate (simian.js:143) -> minvec, and, with
+// `publish`, the send half of the allreduce(MIN) over peer memory: one thread
+// per peer writes the candidate into the peer's slot array -- data, fence, flag.
+// One CTA, all threads; the launch's results must be visible (ticket fence or
+// a kernel boundary).
+__device__ void lbts_candidate(const DevCfg &c, const WinState &W, WindowShared &sh, uint32_t win_ix,
+                               int publish) {
+  unsigned long long cand, far;
+  if (!W.done) reduce_parts(c, sh);
+  if (W.redist || W.done) {
+    cand = far = SIMIAN_KEY_NONE;
+  } else {
+    local_min_candidate(c, W, sh, cand, far);
+  }
+  const double inf = __longlong_as_double(0x7FF0000000000000LL);
+  const double m0 = cand == SIMIAN_KEY_NONE ? c.inf_time : simian_key_time(cand);
+  const double m1 = far == SIMIAN_KEY_NONE ? inf : simian_key_time(far);
+  if (threadIdx.x == 0) {
+    c.acc->minvec[0] = m0;
+    c.acc->minvec[1] = m1;
+    c.acc->ticket = 0;
+  }
+  if (publish && !W.done && threadIdx.x < (unsigned)c.size) {
+    MinSlot *dst = c.peer_xch[threadIdx.x];
+    if (dst) {
+      dst += W.parity * (uint32_t)c.size + (uint32_t)c.rank;
+      *(volatile double *)&dst->min_left = m0;
+      *(volatile double *)&dst->far_min = m1;
+      __threadfence_system();
+      *(volatile unsigned long long *)&dst->seq = (unsigned long long)win_ix + 1ull;
+    } else {
+      set_error(c, SIMIAN_ERR_BAD_ARGUMENT); // peers were never connected
+    }
+  }
+}
+
 // One lookahead window (or one redistribution pass) for entity block blockIdx.x.
-// fuse_advance != 0 (size == 1): the last CTA to finish computes window k+1.
+// fuse_advance: 1 (size == 1): the last CTA to finish computes window k+1;
+// 2 / 3 (size > 1): the last CTA computes this rank's LBTS candidate (3: and
+// publishes it to the peers' exchange slots); 0: neither.
 __global__ void __launch_bounds__(NTHREADS, SIMIAN_MINBLOCKS)
     k_window(const __grid_constant__ DevCfg c, uint32_t win_ix, int fuse_advance) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1659,6 +1697,10 @@ __global__ void __launch_bounds__(NTHREADS, SIMIAN_MINBLOCKS)
   __syncthreads();
   if (!sh.is_last) return;
   __threadfence();
+  if (fuse_advance >= 2) {
+    lbts_candidate(c, W, sh, win_ix, fuse_advance == 3);
+    return;
+  }
   reduce_parts(c, sh);
   WinState *Wn = &c.win[(win_ix + 1u) & 1u];
   if (W.redist) {
@@ -1674,40 +1716,11 @@ __global__ void __launch_bounds__(NTHREADS, SIMIAN_MINBLOCKS)
   PHASE(9);
 }
 
-// size > 1: local minLeft candidate after the exchange (simian.js:143)
 __global__ void __launch_bounds__(NTHREADS) k_local_min(const __grid_constant__ DevCfg c, uint32_t win_ix,
                                                         int publish) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   WindowShared &sh = *reinterpret_cast<WindowShared *>(smem_raw);
-  const WinState &W = c.win[win_ix & 1u];
-  unsigned long long cand, far;
-  if (!W.done) reduce_parts(c, sh); // the BlockParts of this window's k_window launch
-  if (W.redist || W.done) {
-    cand = far = SIMIAN_KEY_NONE;
-  } else {
-    local_min_candidate(c, W, sh, cand, far);
-  }
-  const double inf = __longlong_as_double(0x7FF0000000000000LL);
-  const double m0 = cand == SIMIAN_KEY_NONE ? c.inf_time : simian_key_time(cand);
-  const double m1 = far == SIMIAN_KEY_NONE ? inf : simian_key_time(far);
-  if (threadIdx.x == 0) {
-    c.acc->minvec[0] = m0;
-    c.acc->minvec[1] = m1;
-  }
-  // allreduce(MIN) over peer memory, send half: one thread per peer writes this
-  // rank's candidate into the peer's slot array -- data, fence, then the flag
-  if (publish && !W.done && threadIdx.x < (unsigned)c.size) {
-    MinSlot *dst = c.peer_xch[threadIdx.x];
-    if (dst) {
-      dst += W.parity * (uint32_t)c.size + (uint32_t)c.rank;
-      *(volatile double *)&dst->min_left = m0;
-      *(volatile double *)&dst->far_min = m1;
-      __threadfence_system();
-      *(volatile unsigned long long *)&dst->seq = (unsigned long long)win_ix + 1ull;
-    } else {
-      set_error(c, SIMIAN_ERR_BAD_ARGUMENT); // peers were never connected
-    }
-  }
+  lbts_candidate(c, c.win[win_ix & 1u], sh, win_ix, publish);
 }
 
 // size > 1: consume the allreduced {globalMinLeft, min far} (simian.js:144)

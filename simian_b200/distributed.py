@@ -103,16 +103,16 @@ def drive_windows_p2p(engine, rank, size, device, group=None, batch=8,
     exchange: no host round trip inside a batch of windows.  Per window:
       k_window           events below the bound; remote sends -> outbox[parity],
                          and into this rank's LBTS candidate       :122-134, entity.js:66
-      k_local_min        minLeft candidate                          :143
+        (its last CTA)   minLeft candidate                          :143
       all_reduce(MIN)    {minLeft, min far time}; orders the pull   :144 (mpi.cpp:380)
       k_pull             peers' outboxes -> local calendar, NVLink  :137-142
       k_advance          next window                                :119-120
     The host polls `done`/error once per batch; windows launched past the end
     are no-ops on every rank (the window sequence is global).
     allreduce="peer" (default): the MIN-allreduce itself runs over NVLink peer
-    memory -- k_local_min writes this rank's candidate into every peer's
-    exchange slots, k_pull waits for all of them, k_advance takes the minimum --
-    so a window is four kernel launches and no collective-library call;
+    memory -- the last CTA of k_window writes this rank's candidate into every
+    peer's exchange slots, k_pull waits for all of them, k_advance takes the
+    minimum -- so a window is three kernel launches and no collective-library call;
     allreduce="nccl": torch.distributed all_reduce as drawn above."""
     engine.set_stream(torch.cuda.current_stream(device).cuda_stream)
     connect_peers(engine, rank, size, group)
@@ -131,17 +131,17 @@ def drive_windows_p2p(engine, rank, size, device, group=None, batch=8,
     while True:
         for _ in range(batch):
             mark()
-            engine.window_process()
-            mark()
             if allreduce == "peer":
-                engine.window_publish_min()
+                engine.window_process_lbts(True)   # k_window + candidate + publish
+                mark()
                 mark()
                 mark()
                 engine.window_pull(True)
                 mark()
                 engine.window_advance_async(True)
             else:
-                engine.window_local_min()
+                engine.window_process_lbts(False)  # k_window + candidate
+                mark()
                 mark()
                 dist.all_reduce(mv, op=dist.ReduceOp.MIN, group=group)
                 mark()
