@@ -906,48 +906,47 @@ __device__ __forceinline__ uint32_t rank_event(const DevCfg &c, WindowShared &sh
   const uint32_t le = (uint32_t)a.y - slot0;
   const double tr = __longlong_as_double((long long)a.x);
   uint32_t rank = 0;
-  bool have_pred = false;
-  RecBits pred;
   const uint32_t first = sh.head[le];
   const ulonglong2 bh = sh.hi[i];
-  RecBits r;
-  r.q0 = a.x;
-  r.q1 = a.y;
-  r.q2 = bh.x;
-  r.q3 = bh.y;
+  // tie-break words of this event: (handler, src) and seq
+  const unsigned long long my2 = ((bh.x & 0xFFFFull) << 32) | (a.y >> 32);
+  const uint32_t myseq = (uint32_t)(bh.x >> 32);
+  // latest equal-time predecessor (for the tie statistics): its key and slot
+  uint32_t pj = LIST_END, pseq = 0;
+  unsigned long long p2 = 0;
 #pragma unroll 1
   for (uint32_t j = first; j != LIST_END; j = sh.nxt[j]) {
     if (j == i) continue;
-    const double to = __longlong_as_double((long long)sh.lo[j].x);
+    const ulonglong2 o = sh.lo[j];
+    const double to = __longlong_as_double((long long)o.x);
     if (to < tr) {
       rank++;
     } else if (to == tr) { // a true same-entity time tie: the defined order decides
-      const RecBits o = slot_get(sh, j);
-      unsigned long long a2 = ((unsigned long long)o.handler() << 32) | o.src();
-      unsigned long long b2 = ((unsigned long long)r.handler() << 32) | r.src();
+      const unsigned long long ox = sh.hi[j].x;
+      const unsigned long long o2 = ((ox & 0xFFFFull) << 32) | (o.y >> 32);
+      const uint32_t oseq = (uint32_t)(ox >> 32);
       // identical records (same key down to seq) are ordered by their slot: any
       // order of indistinguishable events commits the same thing
-      bool before = a2 != b2 ? a2 < b2 : (o.seq() != r.seq() ? o.seq() < r.seq() : j < i);
-      if (before) { // equal-time predecessor: keep the latest one
+      const bool before = o2 != my2 ? o2 < my2 : (oseq != myseq ? oseq < myseq : j < i);
+      if (before) {
         rank++;
-        if (!have_pred) {
-          pred = o;
-          have_pred = true;
-        } else {
-          unsigned long long p2 = ((unsigned long long)pred.handler() << 32) | pred.src();
-          if (p2 != a2 ? p2 < a2 : pred.seq() <= o.seq()) pred = o;
+        // keep the latest predecessor: (key, seq, slot) maximal
+        if (pj == LIST_END || (p2 != o2 ? p2 < o2 : (pseq != oseq ? pseq < oseq : pj < j))) {
+          pj = j;
+          p2 = o2;
+          pseq = oseq;
         }
       }
     }
   }
-  if (c.tie_check && have_pred) {
+  if (c.tie_check && pj != LIST_END) {
     ta.ties++;
-    if (pred.q1 >> 32 != r.q1 >> 32 || pred.handler() != r.handler() || pred.q3 != r.q3)
-      ta.dties++;
+    // distinguishable: (handler, src) or data differ -- what the handler sees
+    if (p2 != my2 || sh.hi[pj].y != bh.y) ta.dties++;
   }
   uint32_t t = first;
   for (uint32_t s = 0; s < rank; s++) t = sh.nxt[t];
-  sh.xs[t] = simian_trace_event(tr, r.handler(), r.src(), r.data());
+  sh.xs[t] = simian_trace_event(tr, (uint32_t)(bh.x & 0xFFFFull), (uint32_t)(a.y >> 32), bh.y);
   unsigned long long tk = simian_time_key(tr);
   ta.max_key = tk > ta.max_key ? tk : ta.max_key;
   ta.committed++;
@@ -1006,19 +1005,27 @@ __device__ __forceinline__ void collect_due(const DevCfg &c, WindowShared &sh, T
                                             uint32_t slot0, uint32_t npg, uint32_t e_lo,
                                             uint32_t e_hi, bool first) {
   const int tid = threadIdx.x, lane = tid & 31;
-  const WinState &W = sh.W;
-  const uint32_t lim = npg * PAGE;
+  const double w_hi = sh.W.hi, w_gmin = sh.W.gmin;
   constexpr int U = 4;
+  // thread -> (page, slot): the slot inside the page is fixed per thread, the
+  // page advances by NTHREADS / PAGE per step (PAGE divides NTHREADS or vice versa)
+  static_assert(NTHREADS % PAGE == 0 || PAGE % NTHREADS == 0, "page / CTA shape");
+  const uint32_t lim = npg * PAGE;
   for (uint32_t base = 0; base < lim; base += U * NTHREADS) {
     unsigned long long q0[U], q1[U];
     uint32_t ref[U];
     bool ok[U];
 #pragma unroll
     for (int u = 0; u < U; u++) {
-      uint32_t i = base + u * NTHREADS + tid;
-      uint32_t pg = i / PAGE, sl = i % PAGE;
-      ok[u] = i < lim && sl < (uint32_t)(sh.pg_cnt[pg < PGMAX ? pg : 0] & 0x7FFFu);
-      ref[u] = ok[u] ? sh.pg_id[pg] * PAGE + sl : 0;
+      const uint32_t i = base + u * NTHREADS + tid;
+      const uint32_t pg = i / PAGE, sl = i % PAGE;
+      ok[u] = false;
+      ref[u] = 0;
+      if (i < lim) {
+        const uint32_t cnt = (uint32_t)(sh.pg_cnt[pg] & 0x7FFFu);
+        ok[u] = sl < cnt;
+        ref[u] = sh.pg_id[pg] * PAGE + sl;
+      }
       if (ok[u]) ld_rec_head(c.pool + ref[u], q0[u], q1[u]);
     }
 #pragma unroll
@@ -1027,9 +1034,9 @@ __device__ __forceinline__ void collect_due(const DevCfg &c, WindowShared &sh, T
       uint32_t le = 0;
       if (ok[u]) {
         double t = __longlong_as_double((long long)q0[u]);
-        if (t < W.hi) {
+        if (t < w_hi) {
           le = (uint32_t)q1[u] - slot0;
-          due = t >= W.gmin && le >= e_lo && le < e_hi;
+          due = t >= w_gmin && le >= e_lo && le < e_hi;
         } else if (first) {
           unsigned long long tk = simian_time_key(t);
           ta.min_key = tk < ta.min_key ? tk : ta.min_key;
