@@ -31,8 +31,8 @@ sys.path.insert(0, ROOT)
 
 BYTES_PER_EVENT = 96  # 32 read + 32 write + 16 + 16 state
 # dram__bytes_read.sum + dram__bytes_write.sum of one steady-state k_window launch
-# (config 2, ~1.68 M committed events): profiles/r1_j_k_window_ncu_full.csv
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 89337600 + 59158272
+# (config 2, ~1.68 M committed events): profiles/r1_p_k_window_ncu_full.csv
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 89334272 + 58740736
 
 
 def load_peaks():
@@ -66,21 +66,33 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+
+    def mark(self):
+        """the timed region starts now (the sampler itself starts before the
+        warm-up: nvidia-smi needs ~100 ms to deliver its first sample, more than
+        a short timed region lasts)"""
+        self.t_mark = time.perf_counter()
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)  # one more sampling period
         self.proc.terminate()
         self.t.join(timeout=2)
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        t0 = getattr(self, "t_mark", 0.0)
+        rows = [r for t, r in self.rows if t >= t0]
+        window = "timed"
+        if not rows:  # timed region shorter than the sampling period
+            rows, window = [r for _, r in self.rows], "warmup+timed"
+        sm = [float(r[0]) for r in rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 6
+        reasons = sorted({names[i] for r in rows if len(r) >= 6
                           for i in range(4) if r[2 + i].lower().startswith("active")})
         return {"sm_mhz": statistics.median(sm) if sm else None,
                 "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm)}
+                "samples": len(sm), "window": window}
 
 
 def workload_for(n_gpus, scale):
@@ -240,12 +252,13 @@ def main():
         st.pop("_engine").close()
         return st
 
-    for _ in range(args.warmup):
-        one_step_resident()
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        one_step_resident()
+    barrier()
+    sampler.mark()
     dev_s, wall0, events, launches, windows = 0.0, time.perf_counter(), 0, 0, 0
     for _ in range(args.steps):
         st = one_step_resident()
@@ -288,8 +301,8 @@ def main():
             else:
                 from simian_b200.distributed import drive_windows_p2p
                 st = drive_windows_p2p(e, rank, world, torch.device("cuda", local_rank))
-            counts = e.read_counts("Node", n)       # D2H of the step's results
-            hashes = e.read_trace_hashes("Node", n)
+            counts = e.read_local("Node", 0)[0]     # D2H of the step's results
+            hashes = e.read_local("Node", 1)[0]
             e.close()
             return st, counts, hashes
         one_step_e2e()
@@ -347,7 +360,7 @@ def main():
                      "note": "achieved = committed events/s per GPU x 96 B over the whole "
                              "timed window loop (k_window is >99% of it); traffic = "
                              "dram read+write bytes of one steady-state k_window launch, "
-                             "ncu --set full, profiles/r1_j_k_window_ncu_full.csv"},
+                             "ncu --set full, profiles/r1_p_k_window_ncu_full.csv"},
     }
     if e2e is not None:
         line["e2e"] = e2e

@@ -226,6 +226,12 @@ int simian_read_counts(simian_engine *e, const char *className, uint32_t first,
                        uint32_t count, uint64_t *out);
 int simian_read_trace_hashes(simian_engine *e, const char *className,
                              uint32_t first, uint32_t count, uint64_t *out);
+/* The same for THIS rank's own instances only, compact and in local order:
+ * out[j] belongs to instance *firstNum + j * *stride.  which: 0 counts,
+ * 1 trace hashes.  out == NULL: size query (*nLocal).                        */
+int simian_read_local(simian_engine *e, const char *className, int which, uint64_t *out,
+                      uint64_t capacity, uint64_t *nLocal, uint32_t *firstNum,
+                      uint32_t *stride);
 /* getEntity(name, num) state read-back (simian.js:200-205)                  */
 int simian_read_state(simian_engine *e, const char *className, uint32_t first,
                       uint32_t count, void *out);

@@ -86,6 +86,8 @@ SIGNATURES = {
     "simian_read_counts": (_i, [_vp, _cp, _u32, _u32, _vp]),
     "simian_read_trace_hashes": (_i, [_vp, _cp, _u32, _u32, _vp]),
     "simian_read_state": (_i, [_vp, _cp, _u32, _u32, _vp]),
+    "simian_read_local": (_i, [_vp, _cp, _i, _vp, _u64, C.POINTER(_u64), C.POINTER(_u32),
+                               C.POINTER(_u32)]),
     "simian_debug_phase_cycles": (_i, [_vp, C.POINTER(_u64)]),
     "simian_trim_cache": (None, []),
 }
@@ -294,6 +296,17 @@ class Engine:
 
     def read_trace_hashes(self, name, n, first=0):
         return self._read(self.L.simian_read_trace_hashes, name, n, first)
+
+    def read_local(self, name, which):
+        """this rank's own instances: (values, first num, stride); which: 0
+        counts, 1 trace hashes"""
+        n, first, stride = _u64(), _u32(), _u32()
+        self._ck(self.L.simian_read_local(self.h, name.encode(), which, None, 0,
+                                          C.byref(n), C.byref(first), C.byref(stride)))
+        out = np.empty(n.value, dtype=np.uint64)
+        self._ck(self.L.simian_read_local(self.h, name.encode(), which, out.ctypes.data,
+                                          n.value, C.byref(n), C.byref(first), C.byref(stride)))
+        return out, first.value, stride.value
 
     def read_state(self, name, n, state_bytes, first=0):
         out = np.zeros(n * state_bytes, dtype=np.uint8)

@@ -70,6 +70,29 @@ void pinned_give(size_t bytes, void *p) {
   g_pinned_cache.emplace(bytes, p);
 }
 
+// CUDA-IPC mappings of peers' buffers, keyed by the 64 handle bytes: engines of
+// the same shape reuse the same device buffers (allocation cache), so their
+// handles repeat and cudaIpcOpenMemHandle (~ms each) is paid once per peer
+std::map<std::string, void *> g_ipc_cache;
+
+cudaError_t ipc_open_cached(void **out, const cudaIpcMemHandle_t &h) {
+  std::string key((const char *)&h, sizeof h);
+  {
+    std::lock_guard<std::mutex> g(g_alloc_cache_mu);
+    auto it = g_ipc_cache.find(key);
+    if (it != g_ipc_cache.end()) {
+      *out = it->second;
+      return cudaSuccess;
+    }
+  }
+  cudaError_t ce = cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess);
+  if (ce == cudaSuccess) {
+    std::lock_guard<std::mutex> g(g_alloc_cache_mu);
+    g_ipc_cache[key] = *out;
+  }
+  return ce;
+}
+
 size_t alloc_cache_limit() {
   const char *s = getenv("SIMIAN_B200_CACHE_GB");
   double gb = s ? atof(s) : 64.0;
@@ -154,6 +177,7 @@ struct simian_engine {
   std::vector<SchedOp> ops;
   uint32_t n_ids = 0, sched_seq = 0;
   uint64_t initial_events = 0;
+  uint64_t record_events = 0; // the part of initial_events that came as host records
   // state
   bool running = false, set_up = false, stepping = false;
   bool laid_out = false;            // HBM layout allocated + initialised (may precede set_up)
@@ -329,7 +353,10 @@ int setup_layout(simian_engine *e) {
   while (ring < e->ring) ring <<= 1;
   c.ring = ring;
   c.ring_mask = ring - 1;
-  uint64_t local_initial = e->initial_events / g + 1;
+  // events this rank will hold at the start: script loops (schedService /
+  // constructors) run on every rank and only owners keep their share; host
+  // records may already be the rank's own (all counted: an upper bound)
+  uint64_t local_initial = (e->initial_events - e->record_events) / g + e->record_events + 1;
   // default pool: twice the initial events + one (partial) page for every cell
   // of the ring, the upper bound on simultaneously open pages
   uint64_t pool_events = e->pool_events
@@ -354,7 +381,9 @@ int setup_layout(simian_engine *e) {
   if (dev_alloc(e, &c.bcount, c.n_blocks)) return e->err_code;
   if (dev_alloc(e, &e->d_digest, 2)) return e->err_code;
   if (e->size > 1) {
-    uint64_t cap = e->outbox_events ? e->outbox_events : 2 * local_initial / g + 65536;
+    // a window in which every local event sends one record to a uniformly chosen
+    // peer (the t = 0 burst of PHOLD at 100 % remote), with a factor 2 of slack
+    uint64_t cap = e->outbox_events ? e->outbox_events : 2 * local_initial / (g - 1) + 65536;
     c.outbox_cap = (uint32_t)cap;
     if (dev_alloc(e, &c.outbox, 2 * (size_t)e->size * cap)) return e->err_code;
     if (dev_alloc(e, &c.outbox_count, 2 * (size_t)e->size)) return e->err_code;
@@ -484,6 +513,8 @@ void simian_trim_cache(void) {
   g_alloc_cache_bytes = 0;
   for (auto &kv : g_pinned_cache) cudaFreeHost(kv.second);
   g_pinned_cache.clear();
+  for (auto &kv : g_ipc_cache) cudaIpcCloseMemHandle(kv.second);
+  g_ipc_cache.clear();
 }
 
 double simian_hash_name(const char *str) { // hash.js:21-26
@@ -530,8 +561,7 @@ void simian_destroy(simian_engine *e) {
   if (!e) return;
   cudaSetDevice(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
-  for (void *p : e->peer_map)
-    if (p) cudaIpcCloseMemHandle(p);
+  // peer mappings stay open in the process-wide cache (simian_trim_cache closes them)
   for (auto &a : e->allocs)
     if (!cache_give(e->device, a.second, a.first)) cudaFree(a.first);
   for (SchedOp &op : e->ops)
@@ -802,9 +832,9 @@ int simian_ipc_import(simian_engine *e, int peerRank, const void *blob, uint64_t
   if (b.rank != peerRank || b.size != e->size || b.cap != e->cfg.outbox_cap)
     return e->fail(SIMIAN_ERR_BAD_ARGUMENT, "ipc blob does not match this world");
   void *po = nullptr, *pc = nullptr, *px = nullptr;
-  CK(cudaIpcOpenMemHandle(&po, b.outbox, cudaIpcMemLazyEnablePeerAccess));
-  CK(cudaIpcOpenMemHandle(&pc, b.count, cudaIpcMemLazyEnablePeerAccess));
-  CK(cudaIpcOpenMemHandle(&px, b.xch, cudaIpcMemLazyEnablePeerAccess));
+  CK(ipc_open_cached(&po, b.outbox));
+  CK(ipc_open_cached(&pc, b.count));
+  CK(ipc_open_cached(&px, b.xch));
   e->peer_map[3 * peerRank] = po;
   e->peer_map[3 * peerRank + 1] = pc;
   e->peer_map[3 * peerRank + 2] = px;
@@ -986,6 +1016,37 @@ static int read_core(simian_engine *e, const char *className, uint32_t first, ui
   }
   pinned_give(pin_bytes, loc);
   // hand the scratch buffer straight back to the allocation cache
+  auto a = e->allocs.back();
+  e->allocs.pop_back();
+  if (!cache_give(e->device, a.second, a.first)) cudaFree(a.first);
+  return 0;
+}
+
+// this rank's own instances of a class, in local order (num = rank_off + j*size)
+int simian_read_local(simian_engine *e, const char *className, int which, uint64_t *out,
+                      uint64_t capacity, uint64_t *nLocal, uint32_t *firstNum, uint32_t *stride) {
+  auto it = e->class_ix.find(className);
+  if (it == e->class_ix.end()) return e->fail(SIMIAN_ERR_UNKNOWN_NAME, "unknown class");
+  if (!e->set_up) return e->fail(SIMIAN_ERR_BAD_ARGUMENT, "nothing has run yet");
+  HostClass &h = e->classes[it->second];
+  if (nLocal) *nLocal = h.n_local;
+  if (firstNum) *firstNum = h.rank_off;
+  if (stride) *stride = (uint32_t)e->size;
+  if (!out) return 0; // size query
+  if (capacity < h.n_local) return e->fail(SIMIAN_ERR_BAD_ARGUMENT, "buffer too small");
+  if (!h.n_local) return 0;
+  CK(cudaSetDevice(e->device));
+  unsigned long long *tmp = nullptr;
+  if (dev_alloc(e, &tmp, (size_t)h.n_local)) return e->err_code;
+  k_gather_core<<<592, 256, 0, e->stream>>>(e->cfg, h.slot_base, h.n_local, which, tmp);
+  CK(cudaGetLastError());
+  size_t bytes = sizeof(uint64_t) * (size_t)h.n_local;
+  uint64_t *loc = (uint64_t *)pinned_take(bytes);
+  if (!loc) return e->fail(SIMIAN_ERR_CUDA, "cudaMallocHost failed");
+  CK(cudaMemcpyAsync(loc, tmp, bytes, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  memcpy(out, loc, bytes);
+  pinned_give(bytes, loc);
   auto a = e->allocs.back();
   e->allocs.pop_back();
   if (!cache_give(e->device, a.second, a.first)) cudaFree(a.first);

@@ -52,9 +52,11 @@ CONFIGS = {
                          p_receive=1e-5, m_ent=1000.0, ops_ent=1000.0,
                          ops_sigma=0.1, cache_friendliness=0.5, end_time=100.0,
                          min_delay=1.0, time_bins=10),
+    # tiny windows: ~80 due events per entity block per window; one calendar row
+    # per window (bucket_width = minDelay) instead of eight
     "config5_phold_4m_small_lookahead": dict(
         n=1 << 22, per_entity=16, min_delay=0.01, lookahead=0.01, p_remote=0.1,
-        mode=PHOLD_ROSS_REMOTE, groups=1, end=2.0),
+        mode=PHOLD_ROSS_REMOTE, groups=1, end=2.0, options=dict(bucket_width=0.01)),
 }
 
 

@@ -132,6 +132,14 @@ def main():
             cnt, h = read_all(e, classes)
             mine = np.concatenate([(e.base_rank(k) + np.arange(n)) % world == rank
                                    for k, n in classes])
+            # the compact per-rank read-back returns the same values
+            off = 0
+            for k, n in classes:
+                loc, first, stride = e.read_local(k, 0)
+                np.testing.assert_array_equal(loc, cnt[off:off + n][first::stride])
+                loc, first, stride = e.read_local(k, 1)
+                np.testing.assert_array_equal(loc, h[off:off + n][first::stride])
+                off += n
             e.close()
         assert mine.sum() > 0
         np.testing.assert_array_equal(cnt[mine], cnt_ref[mine])

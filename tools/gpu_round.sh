@@ -8,6 +8,7 @@ if [ -z "$2" ]; then
   timeout 300 python -m pytest tests -m gpu -x -q --timeout 120 > $OUT/pytest_$TAG.log 2>&1
   echo "pytest rc=$?"; tail -5 $OUT/pytest_$TAG.log
 fi
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
 timeout 600 python bench.py > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err
 echo "bench rc=$?"; cat $OUT/bench_$TAG.json
 if [ -f simian_b200/libsimian_b200_prof.so ]; then

@@ -12,6 +12,7 @@ scale = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
 opts = dict(kv.split("=") for kv in sys.argv[3:])
 opts = {k: float(v) for k, v in opts.items()}
 c = dict(CONFIGS[name])
+opts = dict(c.pop("options", {}), **opts)
 if c.get("kind") == "lanl":
     from simian_b200.workloads import build_lanl, lanl_engine_end  # noqa: E402
     c.pop("kind")
