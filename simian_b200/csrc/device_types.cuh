@@ -160,6 +160,8 @@ struct DevCfg {
   const uint32_t *peer_count[SIMIAN_MAX_RANKS];
   // LBTS exchange slots: every rank WRITES its {minLeft, min far time, window
   // number} into slot [parity][its rank] of every peer's array (and its own)
+  unsigned long long run_nonce;          // same on every rank, new for every engine: flags of an
+                                         // earlier run over the same (cached) buffers never match
   MinSlot *xch;                          // [2][size], local
   MinSlot *peer_xch[SIMIAN_MAX_RANKS];   // peers' arrays (peer_xch[rank] == xch)
 };

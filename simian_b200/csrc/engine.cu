@@ -13,6 +13,7 @@
 #include <chrono>
 #include <map>
 #include <mutex>
+#include <random>
 #include <string>
 #include <vector>
 
@@ -199,7 +200,9 @@ struct simian_engine {
   uint32_t *h_counts = nullptr;
   std::chrono::steady_clock::time_point t_begin;
   size_t smem_bytes = sizeof(WindowShared);
-  void *peer_map[3 * SIMIAN_MAX_RANKS] = {}; // cudaIpcOpenMemHandle results
+  void *ipc_slab = nullptr; // outbox_count at +0, exchange slots at +4096
+  uint64_t salt = 0;
+  bool peer_seen[SIMIAN_MAX_RANKS] = {};
 
   int fail(int code, const std::string &m) {
     if (!err_code) {
@@ -386,8 +389,14 @@ int setup_layout(simian_engine *e) {
     uint64_t cap = e->outbox_events ? e->outbox_events : 2 * local_initial / (g - 1) + 65536;
     c.outbox_cap = (uint32_t)cap;
     if (dev_alloc(e, &c.outbox, 2 * (size_t)e->size * cap)) return e->err_code;
-    if (dev_alloc(e, &c.outbox_count, 2 * (size_t)e->size)) return e->err_code;
-    if (dev_alloc(e, &c.xch, 2 * (size_t)e->size)) return e->err_code;
+    // the two small peer-visible arrays live in ONE allocation of their own, large
+    // enough (2 MB) not to be carved out of a slab CUDA shares between small
+    // cudaMallocs: an IPC handle names a whole allocation
+    uint8_t *slab = nullptr;
+    if (dev_alloc(e, &slab, (size_t)2 << 20)) return e->err_code;
+    e->ipc_slab = slab;
+    c.outbox_count = (uint32_t *)slab;
+    c.xch = (MinSlot *)(slab + 4096);
     c.peer_xch[e->rank] = c.xch;
   }
   if (!e->h_acc) {
@@ -598,6 +607,12 @@ int simian_set_option(simian_engine *e, const char *key, double v) {
 }
 
 int simian_set_stream(simian_engine *e, void *s) {
+  // work already queued on the old stream (early layout + ingest of
+  // simian_sched_events) must be complete before anything runs on the new one
+  if (e->stream) {
+    cudaSetDevice(e->device);
+    cudaStreamSynchronize(e->stream);
+  }
   if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
   e->stream = (cudaStream_t)s;
   e->own_stream = false;
@@ -794,8 +809,9 @@ int simian_setup(simian_engine *e) {
 
 namespace {
 struct IpcBlob { // what one rank publishes to its peers
-  cudaIpcMemHandle_t outbox, count, xch;
+  cudaIpcMemHandle_t outbox, slab;
   uint64_t cap;
+  uint64_t salt; // random per engine; the run nonce is the sum over all ranks
   int32_t rank, size;
 };
 } // namespace
@@ -810,11 +826,19 @@ int simian_ipc_export(simian_engine *e, void *blob, uint64_t blobBytes, uint64_t
   IpcBlob b;
   memset(&b, 0, sizeof b);
   CK(cudaIpcGetMemHandle(&b.outbox, e->cfg.outbox));
-  CK(cudaIpcGetMemHandle(&b.count, e->cfg.outbox_count));
-  CK(cudaIpcGetMemHandle(&b.xch, e->cfg.xch));
+  CK(cudaIpcGetMemHandle(&b.slab, e->ipc_slab));
   // k_init has zeroed the exchange slots before any peer can write into them
   CK(cudaStreamSynchronize(e->stream));
   b.cap = e->cfg.outbox_cap;
+  if (!e->salt) {
+    std::random_device rd;
+    e->salt = (((uint64_t)rd() << 32) ^ (uint64_t)rd() ^
+               (uint64_t)std::chrono::steady_clock::now().time_since_epoch().count())
+              << 24; // the low 24 bits stay free for the window number
+    if (!e->salt) e->salt = 1ull << 24;
+    e->cfg.run_nonce += e->salt;
+  }
+  b.salt = e->salt;
   b.rank = e->rank;
   b.size = e->size;
   memcpy(blob, &b, sizeof b);
@@ -831,14 +855,15 @@ int simian_ipc_import(simian_engine *e, int peerRank, const void *blob, uint64_t
   memcpy(&b, blob, sizeof b);
   if (b.rank != peerRank || b.size != e->size || b.cap != e->cfg.outbox_cap)
     return e->fail(SIMIAN_ERR_BAD_ARGUMENT, "ipc blob does not match this world");
-  void *po = nullptr, *pc = nullptr, *px = nullptr;
+  void *po = nullptr, *ps = nullptr;
   CK(ipc_open_cached(&po, b.outbox));
-  CK(ipc_open_cached(&pc, b.count));
-  CK(ipc_open_cached(&px, b.xch));
-  e->peer_map[3 * peerRank] = po;
-  e->peer_map[3 * peerRank + 1] = pc;
-  e->peer_map[3 * peerRank + 2] = px;
-  e->cfg.peer_xch[peerRank] = (MinSlot *)px;
+  CK(ipc_open_cached(&ps, b.slab));
+  void *pc = ps;
+  e->cfg.peer_xch[peerRank] = (MinSlot *)((uint8_t *)ps + 4096);
+  if (!e->peer_seen[peerRank]) { // nonce = sum of every rank's salt (own one added at export)
+    e->cfg.run_nonce += b.salt;
+    e->peer_seen[peerRank] = true;
+  }
   e->cfg.peer_outbox[peerRank] = (const simian_event_t *)po;
   e->cfg.peer_count[peerRank] = (const uint32_t *)pc;
   return 0;

@@ -463,7 +463,7 @@ __global__ void k_pull(const __grid_constant__ DevCfg c, uint32_t win_ix, uint32
     // k_window: the outboxes are complete (the barrier MPI_Alltoall is, mpi.cpp:422)
     const volatile unsigned long long *f =
         &c.xch[W.parity * (uint32_t)c.size + threadIdx.x].seq;
-    const unsigned long long want = (unsigned long long)win_ix + 1ull;
+    const unsigned long long want = c.run_nonce + (unsigned long long)win_ix + 1ull;
     uint32_t spins = 0;
     while (*f != want) {
       if (ld_cg(&c.acc->error)) break;
@@ -1382,7 +1382,7 @@ __device__ void lbts_candidate(const DevCfg &c, const WinState &W, WindowShared 
       *(volatile double *)&dst->min_left = m0;
       *(volatile double *)&dst->far_min = m1;
       __threadfence_system();
-      *(volatile unsigned long long *)&dst->seq = (unsigned long long)win_ix + 1ull;
+      *(volatile unsigned long long *)&dst->seq = c.run_nonce + (unsigned long long)win_ix + 1ull;
     } else {
       set_error(c, SIMIAN_ERR_BAD_ARGUMENT); // peers were never connected
     }

@@ -154,6 +154,11 @@ def drive_windows_p2p(engine, rank, size, device, group=None, batch=8,
             break
         batch = min(2 * batch, max_batch)
     st = engine.run_end()
+    # This rank is done (poll synchronised its stream), but a peer may still be
+    # pulling the last window's records out of this rank's outbox: nobody may
+    # tear its engine down -- or build the next one over the same buffers --
+    # before every rank got here (MPI_Barrier at the end of run, simian.js:152).
+    dist.barrier(group=group)
     st["driver_windows"] = windows
     if profile:
         names = ["k_window", "k_local_min", "all_reduce", "k_pull", "k_advance"]
