@@ -757,6 +757,7 @@ int simian_sched_events(simian_engine *e, const simian_event_t *ev, uint64_t n) 
   op.d_recs = (simian_event_t *)cache_take(e->device, op.d_bytes);
   if (!op.d_recs) CK(cudaMalloc((void **)&op.d_recs, op.d_bytes));
   e->initial_events += n;
+  e->record_events += n;
   // (worth it for bulk inputs only: small calls just park their records)
   bool early = !e->classes.empty() && e->n_ids > 0 && e->err_code == 0 &&
                (n >= 65536 || e->laid_out);
