@@ -487,11 +487,19 @@ __global__ void k_pull(const __grid_constant__ DevCfg c, uint32_t win_ix, uint32
       uint32_t n = *(const volatile uint32_t *)(pc + box);
       n = n < c.outbox_cap ? n : c.outbox_cap;
       src += (size_t)box * c.outbox_cap;
-      for (uint32_t idx = sub * blockDim.x + threadIdx.x; idx < n;
-           idx += blocks_per_peer * blockDim.x) {
-        RecBits r = ld_rec(src + idx);
-        append_local(c, ax, W.tb_clean, W.far_row, W.alloc_limit, r);
-        napp++;
+      // four 32-byte NVLink reads in flight per thread, then the four appends
+      const uint32_t stride = blocks_per_peer * blockDim.x;
+      for (uint32_t idx = sub * blockDim.x + threadIdx.x; idx < n; idx += 4 * stride) {
+        RecBits r[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+          if (idx + u * stride < n) r[u] = ld_rec(src + idx + u * stride);
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+          if (idx + u * stride < n) {
+            append_local(c, ax, W.tb_clean, W.far_row, W.alloc_limit, r[u]);
+            napp++;
+          }
       }
     } else {
       set_error(c, SIMIAN_ERR_BAD_ARGUMENT); // peers were never connected
