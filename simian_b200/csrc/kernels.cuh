@@ -83,6 +83,13 @@ __device__ __forceinline__ RecBits ld_rec(const simian_event_t *p) {
                : "l"(p));
   return r;
 }
+// the record as two 128-bit loads (the __noinline__ twin of st_rec_2x16)
+__device__ __forceinline__ RecBits ld_rec_2x16(const simian_event_t *p) {
+  RecBits r;
+  asm volatile("ld.global.v2.u64 {%0,%1}, [%2];" : "=l"(r.q0), "=l"(r.q1) : "l"(p));
+  asm volatile("ld.global.v2.u64 {%0,%1}, [%2];" : "=l"(r.q2), "=l"(r.q3) : "l"((const char *)p + 16));
+  return r;
+}
 // first half only: {time, dst|src}
 __device__ __forceinline__ void ld_rec_head(const simian_event_t *p, unsigned long long &q0,
                                             unsigned long long &q1) {
@@ -516,15 +523,23 @@ __global__ void k_pull(const __grid_constant__ DevCfg c, uint32_t win_ix, uint32
 #define EV_PER_THREAD ((NREFS + NTHREADS - 1) / NTHREADS)
 static_assert(EV_PER_THREAD <= 4, "ranks are packed 8 bits each into one register");
 #define RSTACK_MAX 80 // entity sub-ranges a CTA can have pending
+#define NBINS 16      // histogram bins over the block's entities (burst partition)
 
 struct WindowShared {
   WinState W;
   AppendCtx ax;
   unsigned long long min_key, max_key, free_base, ring_base;
   uint32_t committed, emitted, dropped, ties, dties, appended;
-  uint32_t npg, nfree, total, is_last, found, stack_n, pass_lo, pass_hi;
+  uint32_t npg, nfree, total, is_last, found, stack_n, pass_lo, pass_hi, pass_pg_lo, pass_pg_hi;
   long long scan_j, t_last;
-  uint32_t rstack[2 * RSTACK_MAX]; // entity sub-ranges still to process (lo, hi)
+  // entity sub-ranges still to process: (lo, hi, first page-list index, end page-list index)
+  uint32_t rstack[4 * RSTACK_MAX];
+  // burst partition (a window whose due events overflow the slots): due records
+  // per 1/16th of the block's entities, the parts they are grouped into, and
+  // the scratch pages (listed behind the cells' pages in pg_id) of each part
+  uint32_t hist[NBINS], pfill[NBINS], pcnt[NBINS], plo[NBINS], phi[NBINS], ppage0[NBINS + 1];
+  uint32_t part_of_bin[NBINS];
+  uint32_t nparts, bin_shift;
   uint32_t head[EPB];              // per local entity: index of its first due event
   uint32_t pg_id[PGMAX];           // pages of this block's cells in the window rows
   uint16_t pg_cnt[PGMAX];
@@ -1010,15 +1025,15 @@ __device__ __forceinline__ void chain_entity(const DevCfg &c, WindowShared &sh, 
 // minimum time >= hi is tracked (K1).  Slots are claimed with one
 // shared-memory atomic per warp.
 __device__ __forceinline__ void collect_due(const DevCfg &c, WindowShared &sh, ThreadAcc &ta,
-                                            uint32_t slot0, uint32_t npg, uint32_t e_lo,
-                                            uint32_t e_hi, bool first) {
+                                            uint32_t slot0, uint32_t pg_lo, uint32_t pg_hi,
+                                            uint32_t e_lo, uint32_t e_hi, bool first) {
   const int tid = threadIdx.x, lane = tid & 31;
   const double w_hi = sh.W.hi, w_gmin = sh.W.gmin;
   constexpr int U = 4;
   // thread -> (page, slot): the slot inside the page is fixed per thread, the
   // page advances by NTHREADS / PAGE per step (PAGE divides NTHREADS or vice versa)
   static_assert(NTHREADS % PAGE == 0 || PAGE % NTHREADS == 0, "page / CTA shape");
-  const uint32_t lim = npg * PAGE;
+  const uint32_t lim = (pg_hi - pg_lo) * PAGE;
   for (uint32_t base = 0; base < lim; base += U * NTHREADS) {
     unsigned long long q0[U], q1[U];
     uint32_t ref[U];
@@ -1026,7 +1041,7 @@ __device__ __forceinline__ void collect_due(const DevCfg &c, WindowShared &sh, T
 #pragma unroll
     for (int u = 0; u < U; u++) {
       const uint32_t i = base + u * NTHREADS + tid;
-      const uint32_t pg = i / PAGE, sl = i % PAGE;
+      const uint32_t pg = pg_lo + i / PAGE, sl = i % PAGE;
       ok[u] = false;
       ref[u] = 0;
       if (i < lim) {
@@ -1064,12 +1079,125 @@ __device__ __forceinline__ void collect_due(const DevCfg &c, WindowShared &sh, T
             uint32_t prev = atomicExch(&sh.head[le], pos);
             sh.nxt[pos] = (uint16_t)prev;
             if (prev == LIST_END) cp_async16(&sh.core_s[le], &c.core[slot0 + le]);
+          } else if (first) {
+            // overflow (a burst): where in the block the records without a slot
+            // belong -- the partition step sizes its parts from this
+            atomicAdd(&sh.hist[le >> sh.bin_shift], 1u);
           }
         }
       }
     }
   }
   cp_async_wait_all();
+}
+
+// Burst partition.  The first pass found more due events than the CTA has
+// slots for (e.g. the 16 events per entity all scheduled at t = 0).  Instead
+// of re-scanning every page of the window once per entity sub-range, the due
+// records are copied ONCE into scratch pages grouped by entity sub-range
+// ("parts", sized from the histogram the overflowing pass built); each part is
+// then one ordinary pass over its own few pages, all of whose records are due.
+// The scratch pages come from the block's page stack / the free ring, are
+// listed behind the cells' pages in pg_id and are recycled with them at the end
+// of the launch.  Returns (CTA-uniform) false when the page list has no room:
+// the caller falls back to splitting the entity range and re-scanning.
+__device__ __noinline__ bool partition_burst(const DevCfg &c, WindowShared &sh, uint32_t slot0,
+                                             uint32_t npg_scan) {
+  const int tid = threadIdx.x;
+  const uint32_t shift = sh.bin_shift;
+  // the records that did get a slot in the overflowing pass
+  for (uint32_t i = tid; i < NREFS; i += NTHREADS)
+    atomicAdd(&sh.hist[((uint32_t)sh.lo[i].y - slot0) >> shift], 1u);
+  __syncthreads();
+  if (tid == 0) {
+    const uint32_t nb = ((c.epb - 1u) >> shift) + 1u; // bins in use
+    uint32_t q = 0, cur = 0, bin0 = 0, pages = sh.npg;
+    bool fits = true;
+    for (uint32_t bin = 0; bin <= nb; bin++) {
+      const uint32_t h = bin < nb ? sh.hist[bin] : 0u;
+      if (bin == nb || (cur != 0 && cur + h > (uint32_t)NREFS)) { // close part q
+        const uint32_t np = (cur + PAGE - 1) / PAGE;
+        if (pages + np > (uint32_t)PGMAX) {
+          fits = false;
+          break;
+        }
+        sh.pcnt[q] = cur;
+        sh.pfill[q] = 0;
+        sh.plo[q] = bin0 << shift;
+        sh.phi[q] = (bin << shift) < c.epb ? (bin << shift) : c.epb;
+        sh.ppage0[q] = pages;
+        for (uint32_t k = 0; k < np; k++)
+          sh.pg_cnt[pages + k] =
+              (uint16_t)((k + 1 < np ? (uint32_t)PAGE : cur - k * PAGE) | PG_FREE_FLAG);
+        pages += np;
+        q++;
+        bin0 = bin;
+        cur = 0;
+      }
+      if (bin < nb) {
+        sh.part_of_bin[bin] = q;
+        cur += h;
+      }
+    }
+    sh.ppage0[q] = pages;
+    sh.nparts = fits ? q : 0u;
+  }
+  __syncthreads();
+  const uint32_t nparts = sh.nparts;
+  if (nparts == 0) return false;
+  const uint32_t pg_end = sh.ppage0[nparts];
+  for (uint32_t i = npg_scan + tid; i < pg_end; i += NTHREADS)
+    sh.pg_id[i] = page_get(c, sh.ax, sh.W.alloc_limit); // SIMIAN_NONE: sticky error set
+  __syncthreads();
+  if (tid == 0) {
+    sh.npg = pg_end; // recycled with the cells' pages
+    sh.found = ld_cg(&c.acc->error);
+  }
+  __syncthreads();
+  if (sh.found) return true; // pool exhausted: nothing is pushed, the launch ends
+  // one pass over the window's pages: every due record -> its part's scratch pages
+  const double w_hi = sh.W.hi, w_gmin = sh.W.gmin;
+  constexpr int U = 4;
+  const uint32_t lim = npg_scan * PAGE;
+  for (uint32_t base = 0; base < lim; base += U * NTHREADS) {
+    RecBits r[U];
+    bool ok[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const uint32_t i = base + u * NTHREADS + tid;
+      const uint32_t pg = i / PAGE, sl = i % PAGE;
+      ok[u] = i < lim && sl < (uint32_t)(sh.pg_cnt[pg < PGMAX ? pg : 0] & 0x7FFFu);
+      if (ok[u]) r[u] = ld_rec_2x16(c.pool + ((size_t)sh.pg_id[pg] * PAGE + sl));
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      if (!ok[u]) continue;
+      const double t = r[u].time();
+      if (!(t < w_hi && t >= w_gmin)) continue;
+      const uint32_t q = sh.part_of_bin[(r[u].dst() - slot0) >> shift];
+      const uint32_t pos = atomicAdd(&sh.pfill[q], 1u);
+      if (pos >= sh.pcnt[q]) { // cannot happen: both passes see the same records
+        set_error(c, SIMIAN_ERR_WINDOW_OVERFLOW);
+        continue;
+      }
+      st_rec_2x16(c.pool + ((size_t)sh.pg_id[sh.ppage0[q] + pos / PAGE] * PAGE + pos % PAGE),
+                  r[u].q0, r[u].q1, r[u].q2, r[u].q3);
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (uint32_t q = nparts; q-- > 0;) { // lowest sub-range on top of the stack
+      if (sh.pcnt[q] == 0) continue;
+      uint32_t *st = &sh.rstack[4 * sh.stack_n];
+      st[0] = sh.plo[q];
+      st[1] = sh.phi[q];
+      st[2] = sh.ppage0[q];
+      st[3] = sh.ppage0[q + 1];
+      sh.stack_n++;
+    }
+  }
+  __syncthreads();
+  return true;
 }
 
 // walk one cell's page chain into the CTA's page list
@@ -1463,29 +1591,58 @@ __global__ void __launch_bounds__(NTHREADS, SIMIAN_MINBLOCKS)
     if (tid == 0) {
       sh.rstack[0] = 0;
       sh.rstack[1] = c.epb;
+      sh.rstack[2] = 0;
+      sh.rstack[3] = npg;
       sh.stack_n = 1;
+      // histogram bin = entity >> bin_shift: the smallest power of two that
+      // covers the block with NBINS bins
+      uint32_t sft = 0;
+      while (((c.epb - 1u) >> sft) >= (uint32_t)NBINS) sft++;
+      sh.bin_shift = sft;
     }
+    const uint32_t npg_scan = npg;
     bool first = true;
+    bool pushed = false; // CTA-uniform: some pass overflowed and pushed sub-ranges
 #pragma unroll 1
     for (;;) {
+#ifndef SIMIAN_KEEP_BARRIERS
+      // the common case is ONE pass over the whole block: nothing was pushed,
+      // so the stack need not be looked at again (saves two barriers per window)
+      if (!first && !pushed) break;
+#endif
       __syncthreads();
       if (sh.stack_n == 0) break;
       __syncthreads();
       if (tid == 0) {
         sh.stack_n--;
-        sh.pass_lo = sh.rstack[2 * sh.stack_n];
-        sh.pass_hi = sh.rstack[2 * sh.stack_n + 1];
+        sh.pass_lo = sh.rstack[4 * sh.stack_n];
+        sh.pass_hi = sh.rstack[4 * sh.stack_n + 1];
+        sh.pass_pg_lo = sh.rstack[4 * sh.stack_n + 2];
+        sh.pass_pg_hi = sh.rstack[4 * sh.stack_n + 3];
         sh.total = 0;
       }
+      if (first && tid < NBINS) sh.hist[tid] = 0;
       for (uint32_t i = tid; i < c.epb; i += NTHREADS) sh.head[i] = LIST_END;
       __syncthreads();
       const uint32_t e_lo = sh.pass_lo, e_hi = sh.pass_hi;
-      collect_due(c, sh, ta, slot0, npg, e_lo, e_hi, first);
+      const uint32_t pg_lo = sh.pass_pg_lo, pg_hi = sh.pass_pg_hi;
+      collect_due(c, sh, ta, slot0, pg_lo, pg_hi, e_lo, e_hi, first);
+      const bool was_first = first;
       first = false;
       __syncthreads();
       PHASE(2);
       const uint32_t m = sh.total;
-      if (m > NREFS) { // overflow: split the entity range and retry
+      if (m > NREFS) { // overflow (a burst)
+        pushed = true;
+#ifndef SIMIAN_NO_PARTITION
+        // first pass: copy the due records once into scratch pages grouped by
+        // entity sub-range; each group is then a pass over its own pages
+        if (was_first && partition_burst(c, sh, slot0, npg_scan)) {
+          npg = sh.npg; // the scratch pages are recycled with the others
+          continue;
+        }
+#endif
+        // otherwise split the entity range and re-scan the same pages
         if (e_hi - e_lo <= 1) {
           if (tid == 0) set_error(c, SIMIAN_ERR_ENTITY_BURST);
           break;
@@ -1497,9 +1654,11 @@ __global__ void __launch_bounds__(NTHREADS, SIMIAN_MINBLOCKS)
           if (parts > 16u) parts = 16u;
           if (sh.stack_n + parts > RSTACK_MAX) parts = 2;
           for (uint32_t q = parts; q-- > 0;) { // lowest sub-range on top of the stack
-            sh.rstack[2 * sh.stack_n] = e_lo + (uint32_t)((unsigned long long)span * q / parts);
-            sh.rstack[2 * sh.stack_n + 1] =
-                e_lo + (uint32_t)((unsigned long long)span * (q + 1) / parts);
+            uint32_t *st = &sh.rstack[4 * sh.stack_n];
+            st[0] = e_lo + (uint32_t)((unsigned long long)span * q / parts);
+            st[1] = e_lo + (uint32_t)((unsigned long long)span * (q + 1) / parts);
+            st[2] = pg_lo;
+            st[3] = pg_hi;
             sh.stack_n++;
           }
         }
@@ -1527,8 +1686,10 @@ __global__ void __launch_bounds__(NTHREADS, SIMIAN_MINBLOCKS)
           uint32_t i = tid + u * NTHREADS;
           if (i < m) run_event(c, sh, ta, slot0, i, (rkpack >> (8 * u)) & 255u);
         }
+#ifdef SIMIAN_KEEP_BARRIERS
         __syncthreads();
-        PHASE(4);
+#endif
+        PHASE(4); // (no barrier: phase B reads only the slots its own thread staged)
         // B (K4), one thread per EVENT: append the staged records; the claims
         // of all of a thread's events are in flight together
         {
