@@ -1079,11 +1079,14 @@ __device__ __forceinline__ void collect_due(const DevCfg &c, WindowShared &sh, T
             uint32_t prev = atomicExch(&sh.head[le], pos);
             sh.nxt[pos] = (uint16_t)prev;
             if (prev == LIST_END) cp_async16(&sh.core_s[le], &c.core[slot0 + le]);
-          } else if (first) {
+          }
+#ifndef SIMIAN_HIST_PASS
+          else if (first) {
             // overflow (a burst): where in the block the records without a slot
             // belong -- the partition step sizes its parts from this
             atomicAdd(&sh.hist[le >> sh.bin_shift], 1u);
           }
+#endif
         }
       }
     }
@@ -1101,13 +1104,43 @@ __device__ __forceinline__ void collect_due(const DevCfg &c, WindowShared &sh, T
 // listed behind the cells' pages in pg_id and are recycled with them at the end
 // of the launch.  Returns (CTA-uniform) false when the page list has no room:
 // the caller falls back to splitting the entity range and re-scanning.
-__device__ __noinline__ bool partition_burst(const DevCfg &c, WindowShared &sh, uint32_t slot0,
-                                             uint32_t npg_scan) {
+#ifdef SIMIAN_PART_INLINE
+#define PART_INLINE __forceinline__
+#else
+#define PART_INLINE __noinline__
+#endif
+__device__ PART_INLINE bool partition_burst(const DevCfg &c, WindowShared &sh, uint32_t slot0,
+                                            uint32_t npg_scan) {
   const int tid = threadIdx.x;
   const uint32_t shift = sh.bin_shift;
+#ifdef SIMIAN_HIST_PASS
+  // count pass: due records per histogram bin (times and destinations only)
+  {
+    const double w_hi = sh.W.hi, w_gmin = sh.W.gmin;
+    const uint32_t lim = npg_scan * PAGE;
+    for (uint32_t base = 0; base < lim; base += 4 * NTHREADS) {
+      unsigned long long q0[4], q1[4];
+      bool ok[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const uint32_t i = base + u * NTHREADS + tid;
+        const uint32_t pg = i / PAGE, sl = i % PAGE;
+        ok[u] = i < lim && sl < (uint32_t)(sh.pg_cnt[pg < PGMAX ? pg : 0] & 0x7FFFu);
+        if (ok[u]) ld_rec_head(c.pool + ((size_t)sh.pg_id[pg] * PAGE + sl), q0[u], q1[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        if (!ok[u]) continue;
+        const double t = __longlong_as_double((long long)q0[u]);
+        if (t < w_hi && t >= w_gmin) atomicAdd(&sh.hist[((uint32_t)q1[u] - slot0) >> shift], 1u);
+      }
+    }
+  }
+#else
   // the records that did get a slot in the overflowing pass
   for (uint32_t i = tid; i < NREFS; i += NTHREADS)
     atomicAdd(&sh.hist[((uint32_t)sh.lo[i].y - slot0) >> shift], 1u);
+#endif
   __syncthreads();
   if (tid == 0) {
     const uint32_t nb = ((c.epb - 1u) >> shift) + 1u; // bins in use
@@ -1525,6 +1558,200 @@ __device__ void lbts_candidate(const DevCfg &c, const WinState &W, WindowShared 
   }
 }
 
+// K3 + K4 + trace chain for the m due events one pass collected into the
+// shared-memory slots (entities [e_lo, e_hi) of the block).  CTA-uniform.
+__device__ __forceinline__ void process_pass(const DevCfg &c, WindowShared &sh, ThreadAcc &ta,
+                                             uint32_t slot0, uint32_t m, uint32_t e_lo,
+                                             uint32_t e_hi) {
+  const int tid = threadIdx.x;
+  const WinState &W = sh.W;
+  if (c.all_pure) {
+    // A1, one thread per EVENT: rank (kept in a register), tie check, trace word
+    uint32_t rkpack = 0; // EV_PER_THREAD ranks, 8 bits each
+#pragma unroll 1
+    for (int u = 0; u < EV_PER_THREAD; u++) {
+      uint32_t i = tid + u * NTHREADS;
+      if (i < m) {
+        uint32_t r = rank_event(c, sh, ta, slot0, i);
+        if (r > 255u) set_error(c, SIMIAN_ERR_ENTITY_BURST);
+        rkpack |= (r & 255u) << (8 * u);
+      }
+    }
+    __syncthreads();
+    PHASE(3);
+    // A2 (K3), one thread per EVENT: handler; the sent record is staged in
+    // the consumed record's slot
+#pragma unroll 1
+    for (int u = 0; u < EV_PER_THREAD; u++) {
+      uint32_t i = tid + u * NTHREADS;
+      if (i < m) run_event(c, sh, ta, slot0, i, (rkpack >> (8 * u)) & 255u);
+    }
+#ifdef SIMIAN_KEEP_BARRIERS
+    __syncthreads();
+#endif
+    PHASE(4); // (no barrier: phase B reads only the slots its own thread staged)
+    // B (K4), one thread per EVENT: append the staged records; the claims
+    // of all of a thread's events are in flight together
+    {
+      unsigned long long old[EV_PER_THREAD];
+      uint32_t cell[EV_PER_THREAD];
+#pragma unroll
+      for (int u = 0; u < EV_PER_THREAD; u++) {
+        uint32_t i = tid + u * NTHREADS;
+        cell[u] = SIMIAN_NONE;
+        if (i < m) {
+          ulonglong2 a = sh.lo[i];
+          if ((uint32_t)a.y != SIMIAN_NONE)
+            cell[u] = cell_of_local(c, sh.ax, W.tb_clean, W.far_row,
+                                    __longlong_as_double((long long)a.x), (uint32_t)a.y);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < EV_PER_THREAD; u++)
+        if (cell[u] != SIMIAN_NONE) old[u] = atomicAdd(c.cell_state + cell[u], 1ull);
+      // Claims are serviced in two rounds so that no thread ever waits for a
+      // page while it still owes one: first every claim that landed in a
+      // page or must INSTALL one (never blocks); only then the claims that
+      // have to wait for another thread's install.  (Waiting first can
+      // deadlock: two threads holding crossed install/wait claims.)
+      uint32_t waiting = 0;
+#pragma unroll
+      for (int u = 0; u < EV_PER_THREAD; u++)
+        if (cell[u] != SIMIAN_NONE) {
+          if ((uint32_t)old[u] <= (uint32_t)PAGE) {
+            const RecBits r = slot_get(sh, tid + u * NTHREADS);
+            if ((uint32_t)old[u] < (uint32_t)PAGE)
+              st_rec(c.pool + ((size_t)(uint32_t)(old[u] >> 32) * PAGE + (uint32_t)old[u]), r);
+            else
+              cell_append_slow(c, sh.ax, W.alloc_limit, c.cell_state + cell[u], old[u], r.q0,
+                               r.q1, r.q2, r.q3);
+          } else {
+            waiting |= 1u << u;
+          }
+        }
+      if (waiting) { // rare
+#pragma unroll
+        for (int u = 0; u < EV_PER_THREAD; u++)
+          if (waiting & (1u << u)) {
+            const RecBits r = slot_get(sh, tid + u * NTHREADS);
+            cell_append_slow(c, sh.ax, W.alloc_limit, c.cell_state + cell[u], old[u], r.q0,
+                             r.q1, r.q2, r.q3);
+          }
+      }
+    }
+    PHASE(5);
+    // C, one thread per entity: fold the trace hash chain, publish the count
+    for (uint32_t le = e_lo + tid; le < e_hi; le += NTHREADS) {
+      uint32_t f = sh.head[le];
+      if (f != LIST_END) chain_entity(c, sh, slot0 + le, le, f);
+    }
+  } else {
+    // K3 + K4: stateful handlers, one thread per entity.  A separate
+    // accumulator keeps `ta` of the thread-per-event path in registers
+    // (process_entity is not inlined).
+    ThreadAcc t2;
+    thread_acc_init(t2);
+    for (uint32_t le = e_lo + tid; le < e_hi; le += NTHREADS) {
+      uint32_t f = sh.head[le];
+      if (f != LIST_END) process_entity(c, sh, t2, slot0 + le, f);
+    }
+    ta.min_key = t2.min_key < ta.min_key ? t2.min_key : ta.min_key;
+    ta.max_key = t2.max_key > ta.max_key ? t2.max_key : ta.max_key;
+    ta.committed += t2.committed;
+    ta.emitted += t2.emitted;
+    ta.dropped += t2.dropped;
+    ta.ties += t2.ties;
+    ta.dties += t2.dties;
+    ta.appended += t2.appended;
+  }
+}
+
+// per-thread accumulators -> the CTA's accumulators in shared memory (K1)
+__device__ __forceinline__ void accumulate_block(WindowShared &sh, const ThreadAcc &ta) {
+  unsigned long long mn = warp_min_u64(ta.min_key), mx = warp_max_u64(ta.max_key);
+  uint32_t s0 = __reduce_add_sync(0xffffffffu, ta.committed);
+  uint32_t s1 = __reduce_add_sync(0xffffffffu, ta.emitted);
+  uint32_t s2 = __reduce_add_sync(0xffffffffu, ta.dropped);
+  uint32_t s3 = __reduce_add_sync(0xffffffffu, ta.ties);
+  uint32_t s4 = __reduce_add_sync(0xffffffffu, ta.dties);
+  uint32_t s5 = __reduce_add_sync(0xffffffffu, ta.appended);
+  if ((threadIdx.x & 31) == 0) {
+    if (mn != SIMIAN_KEY_NONE) atomicMin(&sh.min_key, mn);
+    if (mx) atomicMax(&sh.max_key, mx);
+    if (s0) atomicAdd(&sh.committed, s0);
+    if (s1) atomicAdd(&sh.emitted, s1);
+    if (s2) atomicAdd(&sh.dropped, s2);
+    if (s3) atomicAdd(&sh.ties, s3);
+    if (s4) atomicAdd(&sh.dties, s4);
+    if (s5) atomicAdd(&sh.appended, s5);
+  }
+}
+
+// The cold path of a window: the first pass found more due events than the CTA
+// has slots for (m0 > NREFS; bursts such as the 16 events per entity all
+// scheduled at t = 0).  The due records are partitioned into scratch pages by
+// entity sub-range (partition_burst) -- or, when the page list has no room,
+// the entity range is split and the same pages are re-scanned -- and the
+// sub-ranges are processed one pass each.  Kept out of line, with its own
+// accumulators, so that the common single-pass window pays nothing for it.
+__device__ __noinline__ void burst_passes(const DevCfg &c, WindowShared &sh, uint32_t slot0,
+                                          uint32_t npg_scan, uint32_t m0) {
+  const int tid = threadIdx.x;
+  ThreadAcc ta;
+  thread_acc_init(ta);
+  uint32_t m = m0, e_lo = 0, e_hi = c.epb, pg_lo = 0, pg_hi = npg_scan;
+  bool part_ok = false;
+#ifndef SIMIAN_NO_PARTITION
+  part_ok = partition_burst(c, sh, slot0, npg_scan);
+#endif
+#pragma unroll 1
+  for (;;) {
+    if (m > NREFS && !part_ok) { // split the entity range and re-scan the same pages
+      if (e_hi - e_lo <= 1) {
+        if (tid == 0) set_error(c, SIMIAN_ERR_ENTITY_BURST);
+        break;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        uint32_t parts = m / (NREFS * 3u / 4u) + 1u, span = e_hi - e_lo;
+        if (parts > span) parts = span;
+        if (parts > 16u) parts = 16u;
+        if (sh.stack_n + parts > RSTACK_MAX) parts = 2;
+        for (uint32_t q = parts; q-- > 0;) { // lowest sub-range on top of the stack
+          uint32_t *st = &sh.rstack[4 * sh.stack_n];
+          st[0] = e_lo + (uint32_t)((unsigned long long)span * q / parts);
+          st[1] = e_lo + (uint32_t)((unsigned long long)span * (q + 1) / parts);
+          st[2] = pg_lo;
+          st[3] = pg_hi;
+          sh.stack_n++;
+        }
+      }
+    } else if (m && m <= NREFS) {
+      process_pass(c, sh, ta, slot0, m, e_lo, e_hi);
+    }
+    part_ok = false; // only the first (whole-block) overflow is partitioned
+    __syncthreads();
+    if (sh.stack_n == 0) break;
+    __syncthreads();
+    if (tid == 0) {
+      sh.stack_n--;
+      sh.pass_lo = sh.rstack[4 * sh.stack_n];
+      sh.pass_hi = sh.rstack[4 * sh.stack_n + 1];
+      sh.pass_pg_lo = sh.rstack[4 * sh.stack_n + 2];
+      sh.pass_pg_hi = sh.rstack[4 * sh.stack_n + 3];
+      sh.total = 0;
+    }
+    for (uint32_t i = tid; i < c.epb; i += NTHREADS) sh.head[i] = LIST_END;
+    __syncthreads();
+    e_lo = sh.pass_lo, e_hi = sh.pass_hi;
+    pg_lo = sh.pass_pg_lo, pg_hi = sh.pass_pg_hi;
+    collect_due(c, sh, ta, slot0, pg_lo, pg_hi, e_lo, e_hi, false);
+    __syncthreads();
+    m = sh.total;
+  }
+  accumulate_block(sh, ta);
+}
+
 // One lookahead window (or one redistribution pass) for entity block blockIdx.x.
 // fuse_advance: 1 (size == 1): the last CTA to finish computes window k+1;
 // 2 / 3 (size > 1): the last CTA computes this rank's LBTS candidate (3: and
@@ -1533,7 +1760,7 @@ __global__ void __launch_bounds__(NTHREADS, SIMIAN_MINBLOCKS)
     k_window(const __grid_constant__ DevCfg c, uint32_t win_ix, int fuse_advance) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   WindowShared &sh = *reinterpret_cast<WindowShared *>(smem_raw);
-  const int tid = threadIdx.x, lane = tid & 31;
+  const int tid = threadIdx.x;
   const uint32_t b = blockIdx.x;
   const WinState *Wg = &c.win[win_ix & 1u];
   if (Wg->done) return; // simian.js:119: enqueued past the end of the run
@@ -1577,6 +1804,21 @@ __global__ void __launch_bounds__(NTHREADS, SIMIAN_MINBLOCKS)
       list_cell_pages(c, sh, (uint32_t)(hw >> 32), hc < PAGE ? hc : PAGE,
                       (tb == W.tb_hi) ? 0u : PG_FREE_FLAG);
     }
+    // set-up of the first (normally only) pass, under the same barrier
+    for (uint32_t i = tid; i < c.epb; i += NTHREADS) sh.head[i] = LIST_END;
+    if (tid >= NTHREADS - NBINS) sh.hist[tid - (NTHREADS - NBINS)] = 0;
+    if (tid == NTHREADS - 1) {
+      sh.total = 0;
+      sh.stack_n = 0;
+      sh.pass_lo = 0;
+      sh.pass_hi = c.epb;
+      sh.pass_pg_lo = 0; // (pass_pg_hi of the first pass = the number of listed pages)
+      // histogram bin = entity >> bin_shift: the smallest power of two that
+      // covers the block with NBINS bins
+      uint32_t sft = 0;
+      while (((c.epb - 1u) >> sft) >= (uint32_t)NBINS) sft++;
+      sh.bin_shift = sft;
+    }
     __syncthreads();
     PHASE(1);
     npg = sh.npg;
@@ -1584,188 +1826,22 @@ __global__ void __launch_bounds__(NTHREADS, SIMIAN_MINBLOCKS)
       if (tid == 0) set_error(c, SIMIAN_ERR_WINDOW_OVERFLOW);
       npg = 0;
     }
-    // ---- K2..K4 over entity sub-ranges; normally ONE pass over [0, EPB).  A
-    // sub-range whose due events overflow the shared-memory slots is split
-    // and retried (bursts such as the 16 events/entity at t = 0).
+    // ---- K2..K4: normally ONE pass over the whole block.  A window whose due
+    // events overflow the shared-memory slots (bursts such as the 16 events per
+    // entity at t = 0) takes the out-of-line multi-pass path.
     const uint32_t slot0 = b * c.epb;
-    if (tid == 0) {
-      sh.rstack[0] = 0;
-      sh.rstack[1] = c.epb;
-      sh.rstack[2] = 0;
-      sh.rstack[3] = npg;
-      sh.stack_n = 1;
-      // histogram bin = entity >> bin_shift: the smallest power of two that
-      // covers the block with NBINS bins
-      uint32_t sft = 0;
-      while (((c.epb - 1u) >> sft) >= (uint32_t)NBINS) sft++;
-      sh.bin_shift = sft;
+    collect_due(c, sh, ta, slot0, 0, npg, 0, c.epb, true);
+    __syncthreads();
+    PHASE(2);
+    const uint32_t m = sh.total;
+    if (m > NREFS) {
+      burst_passes(c, sh, slot0, npg, m);
+      npg = sh.npg; // scratch pages of the partition are recycled with the others
+      if (npg > PGMAX) npg = 0;
+    } else if (m) {
+      process_pass(c, sh, ta, slot0, m, 0, c.epb);
     }
-    const uint32_t npg_scan = npg;
-    bool first = true;
-    bool pushed = false; // CTA-uniform: some pass overflowed and pushed sub-ranges
-#pragma unroll 1
-    for (;;) {
-#ifndef SIMIAN_KEEP_BARRIERS
-      // the common case is ONE pass over the whole block: nothing was pushed,
-      // so the stack need not be looked at again (saves two barriers per window)
-      if (!first && !pushed) break;
-#endif
-      __syncthreads();
-      if (sh.stack_n == 0) break;
-      __syncthreads();
-      if (tid == 0) {
-        sh.stack_n--;
-        sh.pass_lo = sh.rstack[4 * sh.stack_n];
-        sh.pass_hi = sh.rstack[4 * sh.stack_n + 1];
-        sh.pass_pg_lo = sh.rstack[4 * sh.stack_n + 2];
-        sh.pass_pg_hi = sh.rstack[4 * sh.stack_n + 3];
-        sh.total = 0;
-      }
-      if (first && tid < NBINS) sh.hist[tid] = 0;
-      for (uint32_t i = tid; i < c.epb; i += NTHREADS) sh.head[i] = LIST_END;
-      __syncthreads();
-      const uint32_t e_lo = sh.pass_lo, e_hi = sh.pass_hi;
-      const uint32_t pg_lo = sh.pass_pg_lo, pg_hi = sh.pass_pg_hi;
-      collect_due(c, sh, ta, slot0, pg_lo, pg_hi, e_lo, e_hi, first);
-      const bool was_first = first;
-      first = false;
-      __syncthreads();
-      PHASE(2);
-      const uint32_t m = sh.total;
-      if (m > NREFS) { // overflow (a burst)
-        pushed = true;
-#ifndef SIMIAN_NO_PARTITION
-        // first pass: copy the due records once into scratch pages grouped by
-        // entity sub-range; each group is then a pass over its own pages
-        if (was_first && partition_burst(c, sh, slot0, npg_scan)) {
-          npg = sh.npg; // the scratch pages are recycled with the others
-          continue;
-        }
-#endif
-        // otherwise split the entity range and re-scan the same pages
-        if (e_hi - e_lo <= 1) {
-          if (tid == 0) set_error(c, SIMIAN_ERR_ENTITY_BURST);
-          break;
-        }
-        __syncthreads();
-        if (tid == 0) {
-          uint32_t parts = m / (NREFS * 3u / 4u) + 1u, span = e_hi - e_lo;
-          if (parts > span) parts = span;
-          if (parts > 16u) parts = 16u;
-          if (sh.stack_n + parts > RSTACK_MAX) parts = 2;
-          for (uint32_t q = parts; q-- > 0;) { // lowest sub-range on top of the stack
-            uint32_t *st = &sh.rstack[4 * sh.stack_n];
-            st[0] = e_lo + (uint32_t)((unsigned long long)span * q / parts);
-            st[1] = e_lo + (uint32_t)((unsigned long long)span * (q + 1) / parts);
-            st[2] = pg_lo;
-            st[3] = pg_hi;
-            sh.stack_n++;
-          }
-        }
-        continue;
-      }
-      if (m == 0) continue;
-      if (c.all_pure) {
-        // A1, one thread per EVENT: rank (kept in a register), tie check, trace word
-        uint32_t rkpack = 0; // EV_PER_THREAD ranks, 8 bits each
-#pragma unroll 1
-        for (int u = 0; u < EV_PER_THREAD; u++) {
-          uint32_t i = tid + u * NTHREADS;
-          if (i < m) {
-            uint32_t r = rank_event(c, sh, ta, slot0, i);
-            if (r > 255u) set_error(c, SIMIAN_ERR_ENTITY_BURST);
-            rkpack |= (r & 255u) << (8 * u);
-          }
-        }
-        __syncthreads();
-        PHASE(3);
-        // A2 (K3), one thread per EVENT: handler; the sent record is staged in
-        // the consumed record's slot
-#pragma unroll 1
-        for (int u = 0; u < EV_PER_THREAD; u++) {
-          uint32_t i = tid + u * NTHREADS;
-          if (i < m) run_event(c, sh, ta, slot0, i, (rkpack >> (8 * u)) & 255u);
-        }
-#ifdef SIMIAN_KEEP_BARRIERS
-        __syncthreads();
-#endif
-        PHASE(4); // (no barrier: phase B reads only the slots its own thread staged)
-        // B (K4), one thread per EVENT: append the staged records; the claims
-        // of all of a thread's events are in flight together
-        {
-          unsigned long long old[EV_PER_THREAD];
-          uint32_t cell[EV_PER_THREAD];
-#pragma unroll
-          for (int u = 0; u < EV_PER_THREAD; u++) {
-            uint32_t i = tid + u * NTHREADS;
-            cell[u] = SIMIAN_NONE;
-            if (i < m) {
-              ulonglong2 a = sh.lo[i];
-              if ((uint32_t)a.y != SIMIAN_NONE)
-                cell[u] = cell_of_local(c, sh.ax, W.tb_clean, W.far_row,
-                                        __longlong_as_double((long long)a.x), (uint32_t)a.y);
-            }
-          }
-#pragma unroll
-          for (int u = 0; u < EV_PER_THREAD; u++)
-            if (cell[u] != SIMIAN_NONE) old[u] = atomicAdd(c.cell_state + cell[u], 1ull);
-          // Claims are serviced in two rounds so that no thread ever waits for a
-          // page while it still owes one: first every claim that landed in a
-          // page or must INSTALL one (never blocks); only then the claims that
-          // have to wait for another thread's install.  (Waiting first can
-          // deadlock: two threads holding crossed install/wait claims.)
-          uint32_t waiting = 0;
-#pragma unroll
-          for (int u = 0; u < EV_PER_THREAD; u++)
-            if (cell[u] != SIMIAN_NONE) {
-              if ((uint32_t)old[u] <= (uint32_t)PAGE) {
-                const RecBits r = slot_get(sh, tid + u * NTHREADS);
-                if ((uint32_t)old[u] < (uint32_t)PAGE)
-                  st_rec(c.pool + ((size_t)(uint32_t)(old[u] >> 32) * PAGE + (uint32_t)old[u]), r);
-                else
-                  cell_append_slow(c, sh.ax, W.alloc_limit, c.cell_state + cell[u], old[u], r.q0,
-                                   r.q1, r.q2, r.q3);
-              } else {
-                waiting |= 1u << u;
-              }
-            }
-          if (waiting) { // rare
-#pragma unroll
-            for (int u = 0; u < EV_PER_THREAD; u++)
-              if (waiting & (1u << u)) {
-                const RecBits r = slot_get(sh, tid + u * NTHREADS);
-                cell_append_slow(c, sh.ax, W.alloc_limit, c.cell_state + cell[u], old[u], r.q0,
-                                 r.q1, r.q2, r.q3);
-              }
-          }
-        }
-        PHASE(5);
-        // C, one thread per entity: fold the trace hash chain, publish the count
-        for (uint32_t le = e_lo + tid; le < e_hi; le += NTHREADS) {
-          uint32_t f = sh.head[le];
-          if (f != LIST_END) chain_entity(c, sh, slot0 + le, le, f);
-        }
-      } else {
-        // K3 + K4: stateful handlers, one thread per entity.  A separate
-        // accumulator keeps `ta` of the thread-per-event path in registers
-        // (process_entity is not inlined).
-        ThreadAcc t2;
-        thread_acc_init(t2);
-        for (uint32_t le = e_lo + tid; le < e_hi; le += NTHREADS) {
-          uint32_t f = sh.head[le];
-          if (f != LIST_END) process_entity(c, sh, t2, slot0 + le, f);
-        }
-        ta.min_key = t2.min_key < ta.min_key ? t2.min_key : ta.min_key;
-        ta.max_key = t2.max_key > ta.max_key ? t2.max_key : ta.max_key;
-        ta.committed += t2.committed;
-        ta.emitted += t2.emitted;
-        ta.dropped += t2.dropped;
-        ta.ties += t2.ties;
-        ta.dties += t2.dties;
-        ta.appended += t2.appended;
-      }
-      PHASE(6);
-    }
+    PHASE(6);
   }
   __syncthreads();
   // ---- recycle: the pages of rows [tb_clean, tb_hi) go onto the block's own
@@ -1830,23 +1906,7 @@ __global__ void __launch_bounds__(NTHREADS, SIMIAN_MINBLOCKS)
   PHASE(7);
   // ---- K1: CTA reduction of the accumulators into this CTA's BlockPart
   {
-    unsigned long long mn = warp_min_u64(ta.min_key), mx = warp_max_u64(ta.max_key);
-    uint32_t s0 = __reduce_add_sync(0xffffffffu, ta.committed);
-    uint32_t s1 = __reduce_add_sync(0xffffffffu, ta.emitted);
-    uint32_t s2 = __reduce_add_sync(0xffffffffu, ta.dropped);
-    uint32_t s3 = __reduce_add_sync(0xffffffffu, ta.ties);
-    uint32_t s4 = __reduce_add_sync(0xffffffffu, ta.dties);
-    uint32_t s5 = __reduce_add_sync(0xffffffffu, ta.appended);
-    if (lane == 0) {
-      if (mn != SIMIAN_KEY_NONE) atomicMin(&sh.min_key, mn);
-      if (mx) atomicMax(&sh.max_key, mx);
-      if (s0) atomicAdd(&sh.committed, s0);
-      if (s1) atomicAdd(&sh.emitted, s1);
-      if (s2) atomicAdd(&sh.dropped, s2);
-      if (s3) atomicAdd(&sh.ties, s3);
-      if (s4) atomicAdd(&sh.dties, s4);
-      if (s5) atomicAdd(&sh.appended, s5);
-    }
+    accumulate_block(sh, ta);
   }
   __syncthreads();
   if (tid < 10) { // one thread per field: independent, result-less atomics

@@ -60,6 +60,35 @@ def test_engine_matches_oracle(case, sequential, oracle_mod):
     assert_parity(so, co, ho, se, ce, he)
 
 
+BURST_CASES = [
+    # 16 events per entity at t = 0, blocks of 200 entities: bins of 16 entities,
+    # parts of several bins, a ragged last block
+    (dict(name="burst_blocks_of_200", n=3001, per_entity=16, min_delay=0.1, lookahead=0.1,
+          p_remote=0.2, mode=1, end=2.0, seed=21), dict(block_entities=200)),
+    # a burst in a block of one bin per entity (block_entities <= 16)
+    (dict(name="burst_blocks_of_13", n=200, per_entity=100, min_delay=0.1, lookahead=0.1,
+          p_remote=0.5, mode=1, end=1.0, seed=22), dict(block_entities=13)),
+    # one part = one histogram bin that overflows again: the partition is followed
+    # by entity-range splits over the part's own pages
+    (dict(name="burst_part_overflows", n=1024, per_entity=40, min_delay=0.1, lookahead=0.1,
+          p_remote=0.1, mode=1, end=1.0, seed=23), dict()),
+    # a mid-run burst: wide windows (minDelay = 2 mean delays) keep every window
+    # above the slot count
+    (dict(name="burst_every_window", n=2048, per_entity=8, min_delay=2.0, lookahead=2.0,
+          p_remote=0.3, mode=1, end=12.0, seed=24), dict(bucket_width=1.0)),
+]
+
+
+@pytest.mark.parametrize("case,opts", BURST_CASES, ids=lambda c: c.get("name", "") if "n" in c else None)
+@pytest.mark.parametrize("sequential", [0, 1], ids=["per_event", "per_entity"])
+def test_burst_partition_matches_oracle(case, opts, sequential, oracle_mod):
+    """windows whose due events overflow the CTA's slots: the due records are
+    copied into scratch pages grouped by entity sub-range (partition_burst)"""
+    so, co, ho = run_oracle_phold(oracle_mod, case)
+    se, ce, he = run_engine_phold(case, force_sequential=sequential, **opts)
+    assert_parity(so, co, ho, se, ce, he)
+
+
 def test_sparse_windows_and_far_list(oracle_mod):
     """config-1 shape: minDelay << mean delay, so almost every event goes
     through the far-future list and the window jumps over idle time."""
