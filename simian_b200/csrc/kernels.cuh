@@ -522,6 +522,13 @@ __global__ void k_pull(const __grid_constant__ DevCfg c, uint32_t win_ix, uint32
 #define LIST_END 0xFFFFu
 #define EV_PER_THREAD ((NREFS + NTHREADS - 1) / NTHREADS)
 static_assert(EV_PER_THREAD <= 4, "ranks are packed 8 bits each into one register");
+#ifndef SIMIAN_UNROLL_A1
+#define SIMIAN_UNROLL_A1 1
+#endif
+#ifndef SIMIAN_UNROLL_A2
+#define SIMIAN_UNROLL_A2 1
+#endif
+constexpr int kUnrollA1 = SIMIAN_UNROLL_A1, kUnrollA2 = SIMIAN_UNROLL_A2;
 #define RSTACK_MAX 80 // entity sub-ranges a CTA can have pending
 #define NBINS 16      // histogram bins over the block's entities (burst partition)
 
@@ -530,7 +537,8 @@ struct WindowShared {
   AppendCtx ax;
   unsigned long long min_key, max_key, free_base, ring_base;
   uint32_t committed, emitted, dropped, ties, dties, appended;
-  uint32_t npg, nfree, total, is_last, found, stack_n, pass_lo, pass_hi, pass_pg_lo, pass_pg_hi;
+  uint32_t npg, nvalid, nfree, total, is_last, found, stack_n, pass_lo, pass_hi, pass_pg_lo,
+      pass_pg_hi;
   long long scan_j, t_last;
   // entity sub-ranges still to process: (lo, hi, first page-list index, end page-list index)
   uint32_t rstack[4 * RSTACK_MAX];
@@ -542,6 +550,7 @@ struct WindowShared {
   uint32_t nparts, bin_shift;
   uint32_t head[EPB];              // per local entity: index of its first due event
   uint32_t pg_id[PGMAX];           // pages of this block's cells in the window rows
+  uint32_t pg_off[PGMAX];          // records in the pages listed before this one
   uint16_t pg_cnt[PGMAX];
   uint16_t nxt[NREFS];          // next due event of the same entity
   unsigned long long xs[NREFS]; // trace words, stored in commit order along the entity list
@@ -1094,6 +1103,55 @@ __device__ __forceinline__ void collect_due(const DevCfg &c, WindowShared &sh, T
   cp_async_wait_all();
 }
 
+// K2, common case: the pages of the window's rows hold no more records than
+// the CTA has slots.  ALL of them are copied into the shared-memory slots in
+// one round trip (cp.async, no registers, every load of the CTA in flight at
+// once); slot = records in the pages listed before + index in the page.
+__device__ __forceinline__ void collect_all(const DevCfg &c, WindowShared &sh, uint32_t npg) {
+  const uint32_t lim = npg * PAGE;
+  for (uint32_t i = threadIdx.x; i < lim; i += NTHREADS) {
+    const uint32_t pg = i / PAGE, sl = i % PAGE;
+    if (sl < (uint32_t)(sh.pg_cnt[pg] & 0x7FFFu)) {
+      const simian_event_t *src = c.pool + ((size_t)sh.pg_id[pg] * PAGE + sl);
+      const uint32_t pos = sh.pg_off[pg] + sl;
+      cp_async16(&sh.lo[pos], src);
+      cp_async16(&sh.hi[pos], (const char *)src + 16);
+    }
+  }
+  cp_async_wait_all();
+}
+
+// ... then every thread classifies the records in its slots (the same slots it
+// handles in the later phases): due events are pushed onto their entity's list
+// and fetch the entity's {count, hash} (waited for after the rank phase); the
+// others only feed the LBTS minimum (K1).  Returns the mask of its due slots.
+__device__ __forceinline__ uint32_t link_due(const DevCfg &c, WindowShared &sh, ThreadAcc &ta,
+                                             uint32_t slot0, uint32_t nvalid) {
+  const double w_hi = sh.W.hi, w_gmin = sh.W.gmin;
+  uint32_t live = 0;
+#pragma unroll
+  for (int u = 0; u < EV_PER_THREAD; u++) {
+    const uint32_t i = threadIdx.x + u * NTHREADS;
+    if (i < nvalid) {
+      const ulonglong2 a = sh.lo[i];
+      const double t = __longlong_as_double((long long)a.x);
+      if (t < w_hi) {
+        if (t >= w_gmin) {
+          const uint32_t le = (uint32_t)a.y - slot0;
+          const uint32_t prev = atomicExch(&sh.head[le], i);
+          sh.nxt[i] = (uint16_t)prev;
+          if (prev == LIST_END) cp_async16(&sh.core_s[le], &c.core[slot0 + le]);
+          live |= 1u << u;
+        }
+      } else {
+        unsigned long long tk = simian_time_key(t);
+        ta.min_key = tk < ta.min_key ? tk : ta.min_key;
+      }
+    }
+  }
+  return live;
+}
+
 // Burst partition.  The first pass found more due events than the CTA has
 // slots for (e.g. the 16 events per entity all scheduled at t = 0).  Instead
 // of re-scanning every page of the window once per entity sub-range, the due
@@ -1240,9 +1298,11 @@ __device__ __forceinline__ void list_cell_pages(const DevCfg &c, WindowShared &s
 #pragma unroll 1
   while (p != SIMIAN_NONE) {
     uint32_t idx = atomicAdd(&sh.npg, 1u);
+    uint32_t off = atomicAdd(&sh.nvalid, cntp);
     if (idx < PGMAX) {
       sh.pg_id[idx] = p;
       sh.pg_cnt[idx] = (uint16_t)(cntp | flag);
+      sh.pg_off[idx] = off;
     }
     p = c.page_next[p];
     cntp = PAGE;
@@ -1560,31 +1620,33 @@ __device__ void lbts_candidate(const DevCfg &c, const WinState &W, WindowShared 
 
 // K3 + K4 + trace chain for the m due events one pass collected into the
 // shared-memory slots (entities [e_lo, e_hi) of the block).  CTA-uniform.
+// `live`: bit u = slot (threadIdx.x + u * NTHREADS) holds a due event of this thread.
 __device__ __forceinline__ void process_pass(const DevCfg &c, WindowShared &sh, ThreadAcc &ta,
-                                             uint32_t slot0, uint32_t m, uint32_t e_lo,
+                                             uint32_t slot0, uint32_t live, uint32_t e_lo,
                                              uint32_t e_hi) {
   const int tid = threadIdx.x;
   const WinState &W = sh.W;
   if (c.all_pure) {
     // A1, one thread per EVENT: rank (kept in a register), tie check, trace word
     uint32_t rkpack = 0; // EV_PER_THREAD ranks, 8 bits each
-#pragma unroll 1
+#pragma unroll kUnrollA1
     for (int u = 0; u < EV_PER_THREAD; u++) {
       uint32_t i = tid + u * NTHREADS;
-      if (i < m) {
+      if (live & (1u << u)) {
         uint32_t r = rank_event(c, sh, ta, slot0, i);
         if (r > 255u) set_error(c, SIMIAN_ERR_ENTITY_BURST);
         rkpack |= (r & 255u) << (8 * u);
       }
     }
+    cp_async_wait_all(); // the entities' {count, hash} (link_due)
     __syncthreads();
     PHASE(3);
     // A2 (K3), one thread per EVENT: handler; the sent record is staged in
     // the consumed record's slot
-#pragma unroll 1
+#pragma unroll kUnrollA2
     for (int u = 0; u < EV_PER_THREAD; u++) {
       uint32_t i = tid + u * NTHREADS;
-      if (i < m) run_event(c, sh, ta, slot0, i, (rkpack >> (8 * u)) & 255u);
+      if (live & (1u << u)) run_event(c, sh, ta, slot0, i, (rkpack >> (8 * u)) & 255u);
     }
 #ifdef SIMIAN_KEEP_BARRIERS
     __syncthreads();
@@ -1599,7 +1661,7 @@ __device__ __forceinline__ void process_pass(const DevCfg &c, WindowShared &sh, 
       for (int u = 0; u < EV_PER_THREAD; u++) {
         uint32_t i = tid + u * NTHREADS;
         cell[u] = SIMIAN_NONE;
-        if (i < m) {
+        if (live & (1u << u)) {
           ulonglong2 a = sh.lo[i];
           if ((uint32_t)a.y != SIMIAN_NONE)
             cell[u] = cell_of_local(c, sh.ax, W.tb_clean, W.far_row,
@@ -1646,6 +1708,8 @@ __device__ __forceinline__ void process_pass(const DevCfg &c, WindowShared &sh, 
       if (f != LIST_END) chain_entity(c, sh, slot0 + le, le, f);
     }
   } else {
+    cp_async_wait_all(); // the entities' {count, hash} (link_due)
+    __syncthreads();
     // K3 + K4: stateful handlers, one thread per entity.  A separate
     // accumulator keeps `ta` of the thread-per-event path in registers
     // (process_entity is not inlined).
@@ -1687,22 +1751,35 @@ __device__ __forceinline__ void accumulate_block(WindowShared &sh, const ThreadA
   }
 }
 
-// The cold path of a window: the first pass found more due events than the CTA
-// has slots for (m0 > NREFS; bursts such as the 16 events per entity all
-// scheduled at t = 0).  The due records are partitioned into scratch pages by
-// entity sub-range (partition_burst) -- or, when the page list has no room,
-// the entity range is split and the same pages are re-scanned -- and the
-// sub-ranges are processed one pass each.  Kept out of line, with its own
-// accumulators, so that the common single-pass window pays nothing for it.
-__device__ __noinline__ void burst_passes(const DevCfg &c, WindowShared &sh, uint32_t slot0,
-                                          uint32_t npg_scan, uint32_t m0) {
+// slots [0, m) are all live: this thread's mask
+__device__ __forceinline__ uint32_t live_below(uint32_t m) {
+  uint32_t live = 0;
+#pragma unroll
+  for (int u = 0; u < EV_PER_THREAD; u++)
+    if (threadIdx.x + u * NTHREADS < m) live |= 1u << u;
+  return live;
+}
+
+// The uncommon path of a window: the pages of its rows hold more records than
+// the CTA has slots.  A filtered scan gives slots to the DUE records only; when
+// even those overflow (bursts such as the 16 events per entity all scheduled at
+// t = 0) they are partitioned into scratch pages by entity sub-range
+// (partition_burst) -- or, when the page list has no room, the entity range is
+// split and the same pages are re-scanned -- and the sub-ranges are processed
+// one pass each.  Kept out of line, with its own accumulators, so that the
+// common single-pass window pays nothing for it.
+__device__ __noinline__ void filtered_passes(const DevCfg &c, WindowShared &sh, uint32_t slot0,
+                                             uint32_t npg_scan) {
   const int tid = threadIdx.x;
   ThreadAcc ta;
   thread_acc_init(ta);
+  collect_due(c, sh, ta, slot0, 0, npg_scan, 0, c.epb, true);
+  __syncthreads();
+  const uint32_t m0 = sh.total;
   uint32_t m = m0, e_lo = 0, e_hi = c.epb, pg_lo = 0, pg_hi = npg_scan;
   bool part_ok = false;
 #ifndef SIMIAN_NO_PARTITION
-  part_ok = partition_burst(c, sh, slot0, npg_scan);
+  if (m0 > NREFS) part_ok = partition_burst(c, sh, slot0, npg_scan);
 #endif
 #pragma unroll 1
   for (;;) {
@@ -1727,7 +1804,7 @@ __device__ __noinline__ void burst_passes(const DevCfg &c, WindowShared &sh, uin
         }
       }
     } else if (m && m <= NREFS) {
-      process_pass(c, sh, ta, slot0, m, e_lo, e_hi);
+      process_pass(c, sh, ta, slot0, live_below(m), e_lo, e_hi);
     }
     part_ok = false; // only the first (whole-block) overflow is partitioned
     __syncthreads();
@@ -1774,6 +1851,7 @@ __global__ void __launch_bounds__(NTHREADS, SIMIAN_MINBLOCKS)
     sh.max_key = 0;
     sh.committed = sh.emitted = sh.dropped = sh.ties = sh.dties = sh.appended = 0;
     sh.npg = 0;
+    sh.nvalid = 0;
     sh.nfree = 0;
     sh.is_last = 0;
     sh.ax.far_appends = sh.ax.page_allocs = sh.ax.pgc_take = 0;
@@ -1830,16 +1908,22 @@ __global__ void __launch_bounds__(NTHREADS, SIMIAN_MINBLOCKS)
     // events overflow the shared-memory slots (bursts such as the 16 events per
     // entity at t = 0) takes the out-of-line multi-pass path.
     const uint32_t slot0 = b * c.epb;
-    collect_due(c, sh, ta, slot0, 0, npg, 0, c.epb, true);
-    __syncthreads();
-    PHASE(2);
-    const uint32_t m = sh.total;
-    if (m > NREFS) {
-      burst_passes(c, sh, slot0, npg, m);
-      npg = sh.npg; // scratch pages of the partition are recycled with the others
+    const uint32_t nvalid = sh.nvalid;
+    if (nvalid == 0) {
+      // nothing in the window's rows for this block
+    } else if (nvalid <= NREFS) {
+      // all records of the window's pages fit the slots: one bulk copy, then
+      // every thread links the due ones among its slots
+      collect_all(c, sh, npg);
+      __syncthreads();
+      const uint32_t live = link_due(c, sh, ta, slot0, nvalid);
+      __syncthreads();
+      PHASE(2);
+      process_pass(c, sh, ta, slot0, live, 0, c.epb);
+    } else {
+      filtered_passes(c, sh, slot0, npg);
+      npg = sh.npg; // scratch pages of a partition are recycled with the others
       if (npg > PGMAX) npg = 0;
-    } else if (m) {
-      process_pass(c, sh, ta, slot0, m, 0, c.epb);
     }
     PHASE(6);
   }
