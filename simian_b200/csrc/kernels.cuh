@@ -946,6 +946,9 @@ __device__ __forceinline__ uint32_t rank_event(const DevCfg &c, WindowShared &sh
   // latest equal-time predecessor (for the tie statistics): its key and slot
   uint32_t pj = LIST_END, pseq = 0;
   unsigned long long p2 = 0;
+  // t = the rank-th node of the list: it trails the walk (rank so far <= nodes
+  // visited so far), one step forward for every event found to precede this one
+  uint32_t t = first;
 #pragma unroll 1
   for (uint32_t j = first; j != LIST_END; j = sh.nxt[j]) {
     if (j == i) continue;
@@ -953,6 +956,7 @@ __device__ __forceinline__ uint32_t rank_event(const DevCfg &c, WindowShared &sh
     const double to = __longlong_as_double((long long)o.x);
     if (to < tr) {
       rank++;
+      t = sh.nxt[t];
     } else if (to == tr) { // a true same-entity time tie: the defined order decides
       const unsigned long long ox = sh.hi[j].x;
       const unsigned long long o2 = ((ox & 0xFFFFull) << 32) | (o.y >> 32);
@@ -962,6 +966,7 @@ __device__ __forceinline__ uint32_t rank_event(const DevCfg &c, WindowShared &sh
       const bool before = o2 != my2 ? o2 < my2 : (oseq != myseq ? oseq < myseq : j < i);
       if (before) {
         rank++;
+        t = sh.nxt[t];
         // keep the latest predecessor: (key, seq, slot) maximal
         if (pj == LIST_END || (p2 != o2 ? p2 < o2 : (pseq != oseq ? pseq < oseq : pj < j))) {
           pj = j;
@@ -976,8 +981,6 @@ __device__ __forceinline__ uint32_t rank_event(const DevCfg &c, WindowShared &sh
     // distinguishable: (handler, src) or data differ -- what the handler sees
     if (p2 != my2 || sh.hi[pj].y != bh.y) ta.dties++;
   }
-  uint32_t t = first;
-  for (uint32_t s = 0; s < rank; s++) t = sh.nxt[t];
   sh.xs[t] = simian_trace_event(tr, (uint32_t)(bh.x & 0xFFFFull), (uint32_t)(a.y >> 32), bh.y);
   unsigned long long tk = simian_time_key(tr);
   ta.max_key = tk > ta.max_key ? tk : ta.max_key;
@@ -1671,6 +1674,13 @@ __device__ __forceinline__ void process_pass(const DevCfg &c, WindowShared &sh, 
 #pragma unroll
       for (int u = 0; u < EV_PER_THREAD; u++)
         if (cell[u] != SIMIAN_NONE) old[u] = atomicAdd(c.cell_state + cell[u], 1ull);
+      // C, one thread per entity, while the claims are in flight: fold the trace
+      // hash chain, publish the count (reads what phase A1 parked; A2 / B only
+      // touch the record slots)
+      for (uint32_t le = e_lo + tid; le < e_hi; le += NTHREADS) {
+        uint32_t f = sh.head[le];
+        if (f != LIST_END) chain_entity(c, sh, slot0 + le, le, f);
+      }
       // Claims are serviced in two rounds so that no thread ever waits for a
       // page while it still owes one: first every claim that landed in a
       // page or must INSTALL one (never blocks); only then the claims that
@@ -1702,11 +1712,6 @@ __device__ __forceinline__ void process_pass(const DevCfg &c, WindowShared &sh, 
       }
     }
     PHASE(5);
-    // C, one thread per entity: fold the trace hash chain, publish the count
-    for (uint32_t le = e_lo + tid; le < e_hi; le += NTHREADS) {
-      uint32_t f = sh.head[le];
-      if (f != LIST_END) chain_entity(c, sh, slot0 + le, le, f);
-    }
   } else {
     cp_async_wait_all(); // the entities' {count, hash} (link_due)
     __syncthreads();
