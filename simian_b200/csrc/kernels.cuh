@@ -522,13 +522,6 @@ __global__ void k_pull(const __grid_constant__ DevCfg c, uint32_t win_ix, uint32
 #define LIST_END 0xFFFFu
 #define EV_PER_THREAD ((NREFS + NTHREADS - 1) / NTHREADS)
 static_assert(EV_PER_THREAD <= 4, "ranks are packed 8 bits each into one register");
-#ifndef SIMIAN_UNROLL_A1
-#define SIMIAN_UNROLL_A1 1
-#endif
-#ifndef SIMIAN_UNROLL_A2
-#define SIMIAN_UNROLL_A2 1
-#endif
-constexpr int kUnrollA1 = SIMIAN_UNROLL_A1, kUnrollA2 = SIMIAN_UNROLL_A2;
 #define RSTACK_MAX 80 // entity sub-ranges a CTA can have pending
 #define NBINS 16      // histogram bins over the block's entities (burst partition)
 
@@ -1091,14 +1084,11 @@ __device__ __forceinline__ void collect_due(const DevCfg &c, WindowShared &sh, T
             uint32_t prev = atomicExch(&sh.head[le], pos);
             sh.nxt[pos] = (uint16_t)prev;
             if (prev == LIST_END) cp_async16(&sh.core_s[le], &c.core[slot0 + le]);
-          }
-#ifndef SIMIAN_HIST_PASS
-          else if (first) {
+          } else if (first) {
             // overflow (a burst): where in the block the records without a slot
             // belong -- the partition step sizes its parts from this
             atomicAdd(&sh.hist[le >> sh.bin_shift], 1u);
           }
-#endif
         }
       }
     }
@@ -1165,43 +1155,13 @@ __device__ __forceinline__ uint32_t link_due(const DevCfg &c, WindowShared &sh, 
 // listed behind the cells' pages in pg_id and are recycled with them at the end
 // of the launch.  Returns (CTA-uniform) false when the page list has no room:
 // the caller falls back to splitting the entity range and re-scanning.
-#ifdef SIMIAN_PART_INLINE
-#define PART_INLINE __forceinline__
-#else
-#define PART_INLINE __noinline__
-#endif
-__device__ PART_INLINE bool partition_burst(const DevCfg &c, WindowShared &sh, uint32_t slot0,
+__device__ __noinline__ bool partition_burst(const DevCfg &c, WindowShared &sh, uint32_t slot0,
                                             uint32_t npg_scan) {
   const int tid = threadIdx.x;
   const uint32_t shift = sh.bin_shift;
-#ifdef SIMIAN_HIST_PASS
-  // count pass: due records per histogram bin (times and destinations only)
-  {
-    const double w_hi = sh.W.hi, w_gmin = sh.W.gmin;
-    const uint32_t lim = npg_scan * PAGE;
-    for (uint32_t base = 0; base < lim; base += 4 * NTHREADS) {
-      unsigned long long q0[4], q1[4];
-      bool ok[4];
-#pragma unroll
-      for (int u = 0; u < 4; u++) {
-        const uint32_t i = base + u * NTHREADS + tid;
-        const uint32_t pg = i / PAGE, sl = i % PAGE;
-        ok[u] = i < lim && sl < (uint32_t)(sh.pg_cnt[pg < PGMAX ? pg : 0] & 0x7FFFu);
-        if (ok[u]) ld_rec_head(c.pool + ((size_t)sh.pg_id[pg] * PAGE + sl), q0[u], q1[u]);
-      }
-#pragma unroll
-      for (int u = 0; u < 4; u++) {
-        if (!ok[u]) continue;
-        const double t = __longlong_as_double((long long)q0[u]);
-        if (t < w_hi && t >= w_gmin) atomicAdd(&sh.hist[((uint32_t)q1[u] - slot0) >> shift], 1u);
-      }
-    }
-  }
-#else
   // the records that did get a slot in the overflowing pass
   for (uint32_t i = tid; i < NREFS; i += NTHREADS)
     atomicAdd(&sh.hist[((uint32_t)sh.lo[i].y - slot0) >> shift], 1u);
-#endif
   __syncthreads();
   if (tid == 0) {
     const uint32_t nb = ((c.epb - 1u) >> shift) + 1u; // bins in use
@@ -1632,7 +1592,7 @@ __device__ __forceinline__ void process_pass(const DevCfg &c, WindowShared &sh, 
   if (c.all_pure) {
     // A1, one thread per EVENT: rank (kept in a register), tie check, trace word
     uint32_t rkpack = 0; // EV_PER_THREAD ranks, 8 bits each
-#pragma unroll kUnrollA1
+#pragma unroll 1
     for (int u = 0; u < EV_PER_THREAD; u++) {
       uint32_t i = tid + u * NTHREADS;
       if (live & (1u << u)) {
@@ -1646,14 +1606,11 @@ __device__ __forceinline__ void process_pass(const DevCfg &c, WindowShared &sh, 
     PHASE(3);
     // A2 (K3), one thread per EVENT: handler; the sent record is staged in
     // the consumed record's slot
-#pragma unroll kUnrollA2
+#pragma unroll 1
     for (int u = 0; u < EV_PER_THREAD; u++) {
       uint32_t i = tid + u * NTHREADS;
       if (live & (1u << u)) run_event(c, sh, ta, slot0, i, (rkpack >> (8 * u)) & 255u);
     }
-#ifdef SIMIAN_KEEP_BARRIERS
-    __syncthreads();
-#endif
     PHASE(4); // (no barrier: phase B reads only the slots its own thread staged)
     // B (K4), one thread per EVENT: append the staged records; the claims
     // of all of a thread's events are in flight together
@@ -1783,9 +1740,7 @@ __device__ __noinline__ void filtered_passes(const DevCfg &c, WindowShared &sh, 
   const uint32_t m0 = sh.total;
   uint32_t m = m0, e_lo = 0, e_hi = c.epb, pg_lo = 0, pg_hi = npg_scan;
   bool part_ok = false;
-#ifndef SIMIAN_NO_PARTITION
   if (m0 > NREFS) part_ok = partition_burst(c, sh, slot0, npg_scan);
-#endif
 #pragma unroll 1
   for (;;) {
     if (m > NREFS && !part_ok) { // split the entity range and re-scan the same pages

@@ -11,8 +11,9 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 cfg = bench.workload_for(world, 1.0)
+opts = {k: float(v) for k, v in (kv.split("=") for kv in sys.argv[1:])}
 for rep in range(2):
-    e = capi.Engine("p", 0.0, cfg["end"], cfg["min_delay"], rank=rank, size=world, device=local, seed=1)
+    e = capi.Engine("p", 0.0, cfg["end"], cfg["min_delay"], rank=rank, size=world, device=local, seed=1, **opts)
     build_phold(e, cfg["n"], cfg["per_entity"], cfg["lookahead"], cfg["p_remote"], 1.0, cfg["mode"], cfg["groups"])
     st = drive_windows_p2p(e, rank, world, torch.device("cuda", local), profile=True,
                            allreduce=os.environ.get("SIMIAN_ALLREDUCE", "peer"))
