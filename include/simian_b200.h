@@ -126,6 +126,12 @@ int64_t simian_first_id(simian_engine *e, const char *className);
 /* getBaseRank(name) = hash(name) % size   simian.js:192-194, hash.js:21-26  */
 int simian_base_rank(simian_engine *e, const char *className);
 double simian_hash_name(const char *name);
+/* A model script that overrides Simian.getBaseRank (documented extension point,
+ * Docs/README.Simian:92-100, simian.js:192-194): instances of className live on
+ * rank (baseRank + num) % size.  Before the class's entities are added; the
+ * same value on every rank.  getOffsetRank keeps the reference form
+ * (simian.js:196-198), which the device-side routing implements.             */
+int simian_set_base_rank(simian_engine *e, const char *className, int baseRank);
 
 /* schedService(time, eventName, data, rx, rxId)             simian.js:170-190 */
 int simian_sched_service(simian_engine *e, double time, const char *serviceName,

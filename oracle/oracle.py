@@ -72,6 +72,7 @@ def lib():
             "oracle_add_entities": (i, [vp, cp, u32, u32]),
             "oracle_first_id": (i, [vp, cp]),
             "oracle_base_rank": (i, [vp, cp]),
+            "oracle_set_base_rank": (i, [vp, cp, i]),
             "oracle_intern_service": (i, [vp, cp]),
             "oracle_attach_service": (i, [vp, cp, cp, cp]),
             "oracle_sched_service": (i, [vp, d, cp, u64, cp, u32]),
@@ -160,6 +161,9 @@ class Oracle:
 
     def base_rank(self, name):
         return self.L.oracle_base_rank(self.h, name.encode())
+
+    def set_base_rank(self, name, base_rank):
+        self._ck(self.L.oracle_set_base_rank(self.h, name.encode(), int(base_rank)))
 
     def intern_service(self, name):
         return self.L.oracle_intern_service(self.h, name.encode())

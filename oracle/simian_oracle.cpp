@@ -149,6 +149,7 @@ struct ClassInfo {
   uint32_t count = 0;
   uint32_t state_bytes = 0;
   double name_hash = 0; /* hash.js */
+  int base_rank_override = -1; /* >= 0: the model script's own getBaseRank */
   std::vector<uint8_t> params;
   std::map<uint16_t, int> fn_of_service; /* service id -> builtin fn */
   std::vector<uint8_t> state;            /* count * state_bytes */
@@ -223,6 +224,7 @@ struct World {
   }
   /* getBaseRank: hash(name) % size  (simian.js:192-194) */
   int base_rank(const ClassInfo &c) const {
+    if (c.base_rank_override >= 0) return c.base_rank_override % size; /* user getBaseRank */
     return (int)fmod(c.name_hash, (double)size);
   }
   /* getOffsetRank: (baseRanks[name] + num) % size  (simian.js:196-198) */
@@ -491,6 +493,14 @@ int oracle_first_id(void *o, const char *className) {
   World *w = (World *)o;
   if (!w->class_ix.count(className)) return -1;
   return (int)w->classes[w->class_ix[className]].first_id;
+}
+
+/* a model script overriding Simian.getBaseRank (simian.js:192-194) */
+int oracle_set_base_rank(void *o, const char *className, int baseRank) {
+  World *w = (World *)o;
+  if (!w->class_ix.count(className) || baseRank < 0) return -1;
+  w->classes[w->class_ix[className]].base_rank_override = baseRank;
+  return 0;
 }
 
 int oracle_base_rank(void *o, const char *className) {

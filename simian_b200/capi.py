@@ -59,6 +59,7 @@ SIGNATURES = {
     "simian_intern_service": (_i, [_vp, _cp]),
     "simian_first_id": (C.c_int64, [_vp, _cp]),
     "simian_base_rank": (_i, [_vp, _cp]),
+    "simian_set_base_rank": (_i, [_vp, _cp, _i]),
     "simian_hash_name": (_d, [_cp]),
     "simian_sched_service": (_i, [_vp, _d, _cp, _u64, _cp, _u32]),
     "simian_sched_service_bulk": (_i, [_vp, _d, _cp, _u64, _cp, _u32, _u32, _u32]),
@@ -180,6 +181,9 @@ class Engine:
 
     def base_rank(self, name):
         return self.L.simian_base_rank(self.h, name.encode())
+
+    def set_base_rank(self, name, base_rank):
+        self._ck(self.L.simian_set_base_rank(self.h, name.encode(), int(base_rank)))
 
     def sched_service(self, time, service, data, rx, rx_id):
         self._ck(self.L.simian_sched_service(self.h, time, service.encode(),

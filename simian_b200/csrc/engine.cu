@@ -122,6 +122,7 @@ struct HostClass {
   std::string name;
   uint32_t first_id = 0, count = 0, state_bytes = 0;
   double name_hash = 0;
+  int base_rank_override = -1; // simian_set_base_rank: a user-defined getBaseRank
   std::vector<uint8_t> params;
   std::vector<uint8_t> init_state; // count * state_bytes when given
   bool has_init = false;
@@ -303,7 +304,9 @@ int setup_layout(simian_engine *e) {
   uint32_t g = (uint32_t)e->size, slot = 0;
   for (int k = 0; k < c.n_classes; k++) {
     HostClass &h = e->classes[k];
-    h.base_rank = (uint32_t)fmod(h.name_hash, (double)e->size); // simian.js:192-194
+    h.base_rank = h.base_rank_override >= 0
+                      ? (uint32_t)h.base_rank_override % (uint32_t)e->size
+                      : (uint32_t)fmod(h.name_hash, (double)e->size); // simian.js:192-194
     h.rank_off = ((uint32_t)e->rank + g - h.base_rank % g) % g;
     h.n_local = local_count(h.count, h.rank_off, g);
     h.slot_base = slot;
@@ -704,7 +707,20 @@ int64_t simian_first_id(simian_engine *e, const char *className) {
 int simian_base_rank(simian_engine *e, const char *className) {
   auto it = e->class_ix.find(className);
   if (it == e->class_ix.end()) return -1;
-  return (int)fmod(e->classes[it->second].name_hash, (double)e->size);
+  const HostClass &h = e->classes[it->second];
+  if (h.base_rank_override >= 0) return h.base_rank_override % e->size;
+  return (int)fmod(h.name_hash, (double)e->size);
+}
+
+int simian_set_base_rank(simian_engine *e, const char *className, int baseRank) {
+  auto it = e->class_ix.find(className);
+  if (it == e->class_ix.end()) return e->fail(SIMIAN_ERR_UNKNOWN_NAME, "unknown entity class");
+  if (baseRank < 0) return e->fail(SIMIAN_ERR_BAD_ARGUMENT, "base rank must be >= 0");
+  if (e->set_up || e->classes[it->second].count)
+    return e->fail(SIMIAN_ERR_RUNNING, "the base rank of a class is set before its entities are added");
+  teardown_layout(e);
+  e->classes[it->second].base_rank_override = baseRank;
+  return 0;
 }
 
 int simian_sched_service_bulk(simian_engine *e, double time, const char *serviceName,

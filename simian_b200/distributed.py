@@ -232,6 +232,46 @@ def drive_windows(eng, rank, size, group=None, max_windows=None):
     return st
 
 
+def drive_windows_loopback(ranks, max_windows=None):
+    """The same window loop for ALL ranks of a world inside ONE process (the
+    ranks' engines may share one GPU): the exchange and the min-reduction of
+    simian.js:136-145 are done with tensor copies instead of collectives.  Used
+    to test the multi-rank engine paths (outboxes, ingest, LBTS candidate,
+    advance) where a second GPU is not available.  `ranks`: RankEngine objects,
+    index = rank.  Returns the per-rank stats dicts."""
+    size = len(ranks)
+    for r in ranks:
+        r.begin()
+    windows = 0
+    while True:
+        for r in ranks:
+            r.process()                                     # simian.js:122-134
+        boxes = [r.outbox()[1] for r in ranks]              # [src][dst] -> records
+        for dst, r in enumerate(ranks):                     # :137-142
+            parts = [boxes[src][dst] for src in range(size) if src != dst]
+            n_in = sum(int(p.shape[0]) for p in parts)
+            inbox = r.new_inbox(n_in)
+            if n_in:
+                torch.cat(parts, out=inbox[:n_in])
+            r.ingest(inbox, n_in)
+        mvs = [r.local_min() for r in ranks]                # :143
+        g = torch.stack([m.to(mvs[0].device) for m in mvs]).min(dim=0).values
+        for m in mvs:                                       # :144
+            m.copy_(g)
+        windows += 1
+        dones = [r.advance() for r in ranks]                # :119
+        if all(dones):
+            break
+        if max_windows and windows >= max_windows:
+            break
+    out = []
+    for r in ranks:
+        st = r.end()
+        st["driver_windows"] = windows
+        out.append(st)
+    return out
+
+
 def run_distributed_phold(cfg, rank, world, local_rank, seed=1, driver="p2p",
                           **options):
     """One PHOLD step on `world` GPUs (one process each); returns this rank's

@@ -48,6 +48,10 @@ napi_value DefineClass(napi_env env, napi_callback_info info) {
   int rc = simian_define_class(e, str(env, a[1]).c_str(), (uint32_t)num(env, a[2]));
   return check(env, e, rc < 0 ? -rc : 0);
 }
+napi_value SetBaseRank(napi_env env, napi_callback_info info) {  // a script's own getBaseRank
+  ARGS(3); simian_engine *e = eng(env, a[0]);
+  return check(env, e, simian_set_base_rank(e, str(env, a[1]).c_str(), (int)num(env, a[2])));
+}
 napi_value SetClassParams(napi_env env, napi_callback_info info) {
   ARGS(3); simian_engine *e = eng(env, a[0]); void *p; size_t n;
   NAPI_OK(napi_get_buffer_info(env, a[2], &p, &n));
@@ -118,6 +122,7 @@ napi_value Init(napi_env env, napi_value exports) {
   napi_property_descriptor d[] = {
       {"create", 0, Create, 0, 0, 0, napi_default, 0}, {"destroy", 0, Destroy, 0, 0, 0, napi_default, 0},
       {"defineClass", 0, DefineClass, 0, 0, 0, napi_default, 0}, {"setClassParams", 0, SetClassParams, 0, 0, 0, napi_default, 0},
+      {"setBaseRank", 0, SetBaseRank, 0, 0, 0, napi_default, 0},
       {"addEntities", 0, AddEntities, 0, 0, 0, napi_default, 0}, {"attachService", 0, AttachService, 0, 0, 0, napi_default, 0},
       {"internService", 0, InternService, 0, 0, 0, napi_default, 0}, {"firstId", 0, FirstId, 0, 0, 0, napi_default, 0},
       {"schedService", 0, SchedService, 0, 0, 0, napi_default, 0}, {"schedServiceBulk", 0, SchedServiceBulk, 0, 0, 0, napi_default, 0},

@@ -68,6 +68,9 @@ class Simian {
         if (this._classes[name]) return;
         this._classes[name] = klass;
         native.defineClass(this._h, name, klass.stateBytes || 0);
+        // a subclass's own getBaseRank (simian.js:192-194) goes to the engine
+        if (this.getBaseRank !== Simian.prototype.getBaseRank)
+            native.setBaseRank(this._h, name, this.getBaseRank(name) % this.size);
         for (const key of Object.getOwnPropertyNames(klass.prototype)) {
             const f = klass.prototype[key];
             if (f instanceof DeviceFn) native.attachService(this._h, name, key, f.deviceFn);

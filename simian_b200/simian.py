@@ -14,6 +14,14 @@ SimianJS/entity.js (and their Python twin SimianPie/simian.py):
       .reqService(offset, eventName, data, rx, rxId)          entity.js:35-68
       .attachService(name, fun)                               entity.js:70-72
 
+Extension points kept: a subclass may override getBaseRank (simian.js:192-194,
+Docs/README.Simian:92-100) -- the value is handed to the engine
+(simian_set_base_rank); getOffsetRank keeps the reference form, which is what the
+device-side routing implements.  The per-rank log "<simName>.<rank>.out"
+(simian.js:83,225) and the run banner / statistics printed by rank 0
+(simian.js:104-113,159-165) are opt-in (`log=True`, `verbose=True`): a 16 M
+entity model would write 16 M lines.
+
 What changes: service handlers are not host closures but CUDA device functions
 compiled into libsimian_b200.so, bound BY NAME (`device_fn("phold_generate")`),
 and `data` is a fixed 8-byte payload (an int).  Process-oriented coroutines
@@ -80,6 +88,13 @@ class Entity(object):
         self.engine.attachService(type(self), name, fun, _class_name=self.name)
 
     @property
+    def state(self):
+        """the entity's user state (state_bytes of the class) read back from HBM:
+        what `engine.getEntity(name, num).<field>` reads in the reference"""
+        nb = type(self).state_bytes
+        return bytes(self.engine._h.read_state(self.name, 1, nb, first=self.num)) if nb else b""
+
+    @property
     def count(self):
         """committed events of this entity (read back from HBM)"""
         return int(self.engine._h.read_counts(self.name, 1, first=self.num)[0])
@@ -90,9 +105,11 @@ class Entity(object):
 
 
 class Simian(object):
+    version = "simian-b200 (SimianJS event-oriented service API on B200)"
+
     def __init__(self, simName, startTime=0.0, endTime=1e100, minDelay=1,
                  useMPI=False, rank=None, size=None, device=-1, seed=1,
-                 **options):
+                 log=False, verbose=False, **options):
         self.name = simName
         self.startTime = startTime
         self.endTime = endTime or 1e100          # simian.js:41
@@ -115,8 +132,24 @@ class Simian(object):
         self._added = {}     # class -> instances announced by addEntity, not yet in the engine
         self._pending = []   # host records injected before run
         self._seq = 0
-        self.out = None      # the per-rank log "<name>.<rank>.out" is opt-in
+        # One output file per rank (simian.js:83), opt-in: log=True, a path
+        # prefix, or an open file object
+        self.verbose = bool(verbose)
+        self._own_out = False
+        if log is True:
+            log = simName
+        if isinstance(log, str):
+            self.out = open("%s.%d.out" % (log, self.rank), "w")
+            self._own_out = True
+        else:
+            self.out = log or None
         self.stats = None
+        if type(self).getOffsetRank is not Simian.getOffsetRank:
+            raise SimianError(6, "getOffsetRank cannot be overridden: the device-side routing "
+                                 "implements (baseRank + num) % size; override getBaseRank")
+
+    def __str__(self):                           # simian.js:86-88
+        return self.version
 
     # ---- placement ------------------------------------------------------
     def getBaseRank(self, name):                 # simian.js:192-194
@@ -136,6 +169,9 @@ class Simian(object):
             return
         self._classes[name] = entityClass
         self._h.define_class(name, entityClass.state_bytes)
+        # a subclass's own getBaseRank (simian.js:192-194) goes to the engine
+        if type(self).getBaseRank is not Simian.getBaseRank:
+            self._h.set_base_rank(name, int(self.getBaseRank(name)) % self.size)
         for attr in dir(entityClass):
             fn = getattr(entityClass, attr, None)
             if isinstance(fn, DeviceFn):
@@ -165,7 +201,10 @@ class Simian(object):
         if num != first + cnt:
             raise SimianError(6, "instances of %s must be added as 0, 1, 2, ..." % name)
         self._added[name] = (first, cnt + 1)
-        if self.getOffsetRank(name, num) == self.rank:            # simian.js:223
+        computedRank = self.getOffsetRank(name, num)
+        if computedRank == self.rank:                             # simian.js:223
+            if self.out is not None:                              # simian.js:225
+                self.out.write("%s(%d) Running on rank %d\n" % (name, num, computedRank))
             ents[num] = entityClass(name, self.out, self, num, *theArgs)
 
     def _flush_entities(self):
@@ -185,6 +224,11 @@ class Simian(object):
         self._flush_entities()
         self._h.add_entities(name, first, count)
         self.entities.setdefault(name, _LazyEntities(self, name, entityClass))
+        if self.out is not None:                                  # simian.js:225
+            base = self.baseRanks[name]
+            self.out.writelines("%s(%d) Running on rank %d\n" % (name, num, self.rank)
+                                for num in range(first, first + count)
+                                if (base + num) % self.size == self.rank)
 
     def setClassParams(self, name, blob):
         self._h.set_class_params(name, bytes(blob))
@@ -224,6 +268,13 @@ class Simian(object):
     # ---- run ------------------------------------------------------------------
     def run(self):                                                # simian.js:99-168
         self._flush_entities()
+        if self.verbose and not self.rank:                        # simian.js:104-113
+            print(self)
+            print("===========================================")
+            print("----------SIMIAN-B200 PDES ENGINE----------")
+            print("===========================================")
+            print("GPU: ON")
+            print("MPI: ON" if self.useMPI else "MPI: OFF")
         self.running = True
         try:
             if self.size == 1:
@@ -236,9 +287,40 @@ class Simian(object):
         finally:
             self.running = False
         self.now = self.stats["last_time"]
+        if self.verbose:
+            for line in self.report_lines():
+                print(line)
         return self.stats
 
+    def report_lines(self):
+        """What rank 0 prints after a run (simian.js:151-165); [] on other ranks.
+        size > 1: the event counts are summed over the ranks (MPI allreduce SUM,
+        simian.js:153-154)."""
+        st = self.stats
+        total, synch = st["total_events"], st["synch_events"]
+        if self.size > 1:
+            import torch
+            import torch.distributed as dist
+            t = torch.tensor([total, synch], dtype=torch.int64)
+            if dist.get_backend() == "nccl":
+                t = t.cuda()
+            dist.all_reduce(t)
+            total, synch = int(t[0]), int(t[1])
+        if self.rank:
+            return []
+        sec = st["run_seconds"] or float("nan")
+        return ["SIMULATION FINISHED IN : %s (s)" % sec,
+                "SIMULATED EVENTS       : %d" % total,
+                "SYNCHRONIZATION EVENTS : %d" % synch,
+                "MODEL-EVENTS/SECOND    : %s" % (total / sec),
+                "TOTAL-EVENTS/SECOND    : %s" % ((total + synch) / sec),
+                "==========================================="]
+
     def exit(self):                                               # simian.js:90-97
+        if self.out is not None and self._own_out:
+            self.out.flush()
+            self.out.close()
+        self.out = None
         if self._h is not None:
             self._h.close()
             self._h = None

@@ -141,6 +141,52 @@ def lanl_states(raw, n_ent, m_ent):
     return st, lists
 
 
+def lanl_report(state, time_bins, out):
+    """The statistics table of the LANL PDES benchmark, in the reference's
+    on-disk format (OutputHandler, pdes_lanl_benchmarkV8.js:317-341).  The
+    reference fans the per-entity statistics in to entity 0 with n_ent events
+    at one timestamp (an N-way distinguishable tie, order = heap shape); here
+    the fan-in is done off the event path from the entity state read back from
+    HBM (simian_read_state), in entity-id order.  `state`: the struct array of
+    lanl_states(); `out`: a file-like object."""
+    n = len(state)
+    out.write("%10s %10s %10s %10s %10s %10s    '%s'\n" % (
+        "#EntityID", "#Sends", "#Receives", "Ops(Min", "Avg", "Max)", "Time Bin Sends"))
+    g_send = g_recv = g_ops = 0
+    g_mean, g_min, g_max = 0.0, float("inf"), 0.0
+    g_bins = np.zeros(time_bins, dtype=np.int64)
+    for i in range(n):
+        r = state[i]
+        sends, recvs = int(r["send_count"]), int(r["receive_count"])
+        bins = [int(x) for x in r["time_sends"][:time_bins]]
+        g_mean = (recvs * float(r["ops_mean"]) + g_mean * g_recv) / max(1, g_recv + recvs)
+        g_send += sends
+        g_recv += recvs
+        g_ops += int(r["ops_count"])
+        g_min = min(g_min, float(r["ops_min"]))
+        g_max = max(g_max, float(r["ops_max"]))
+        g_bins += np.array(bins, dtype=np.int64)
+        out.write("%10d %10d %10d %10d %10.5g %10d    %s\n" % (
+            i, sends, recvs, _js_int(r["ops_min"]), float(r["ops_mean"]), _js_int(r["ops_max"]),
+            "[" + ",".join(map(str, bins)) + "]"))
+    out.write("===================== LANL PDES BENCHMARK  Collected Stats from All Ranks "
+              "=======================\n")
+    out.write("%10s %10s %10s %10s %10s %10s %10s    '%s'\n" % (
+        "#Entities", "#Sends", "#Receives", "OpsCount", "Ops(Min", "Avg", "Max)", "Time Bin Sends"))
+    out.write("%10d %10d %10d %10d %10d %10.5g %10d    %s\n" % (
+        n, g_send, g_recv, g_ops, _js_int(g_min), g_mean, _js_int(g_max),
+        "[" + ",".join(str(int(x)) for x in g_bins) + "]"))
+    out.write("=" * 97 + "\n")
+    return dict(sends=g_send, receives=g_recv, ops_count=g_ops, ops_min=g_min,
+                ops_mean=g_mean, ops_max=g_max, time_sends=g_bins)
+
+
+def _js_int(x):
+    """sprintf.js %d of a double: truncation (parseInt); +/-inf and NaN print 0"""
+    x = float(x)
+    return int(x) if math.isfinite(x) else 0
+
+
 # ---- hello.js: two entity classes, data-carrying events, replies to tx/txId ----
 
 HELLO_SERVICES = ("generate", "square", "sqrt", "result")

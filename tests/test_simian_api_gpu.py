@@ -99,3 +99,81 @@ def test_hello_script_shape_matches_simianpie_golden():
     assert got == case["counts"]
     assert float(eng.now).hex() == case["last_time_hex"]
     eng.exit()
+
+
+def test_rank_log_run_banner_and_state_readback(tmp_path, capsys, oracle_mod):
+    """the per-rank log "<simName>.<rank>.out" (simian.js:83,225), what rank 0
+    prints around run (simian.js:104-113,159-165) and getEntity state read-back"""
+    import numpy as np
+    from simian_b200.simian import Entity, Simian
+    from simian_b200.workloads import (LANL_CLASS, LANL_STATE_DTYPE, build_lanl, lanl_engine_end,
+                                       lanl_report, lanl_state_bytes, lanl_states)
+
+    class Node(Entity):
+        pass
+
+    eng = Simian("LOGTEST", 0, 5, 0.5, log=str(tmp_path / "LOGTEST"), verbose=True)
+    for i in range(3):
+        eng.addEntity("Node", Node, i)
+    eng.addEntities("Other", Node, 0, 2)
+    from simian_b200.simian import device_fn
+    eng.attachService(Node, "tick", device_fn("noop"))
+    eng.schedService(1.0, "tick", None, "Node", 1)
+    eng.schedService(2.0, "tick", None, "Other", 0)
+    st = eng.run()
+    assert st["total_events"] == 2
+    eng.exit()
+    text = (tmp_path / "LOGTEST.0.out").read_text().splitlines()
+    assert text == ["Node(0) Running on rank 0", "Node(1) Running on rank 0",
+                    "Node(2) Running on rank 0", "Other(0) Running on rank 0",
+                    "Other(1) Running on rank 0"]
+    printed = capsys.readouterr().out.splitlines()
+    assert printed[1] == "===========================================" and "MPI: OFF" in printed
+    assert "SIMULATED EVENTS       : 2" in printed
+    assert any(l.startswith("SIMULATION FINISHED IN : ") for l in printed)
+    assert any(l.startswith("MODEL-EVENTS/SECOND    : ") for l in printed)
+
+    # LANL statistics table from the entity state read back from HBM
+    case = dict(n_ent=40, s_ent=10.0, q_avg=1.0, p_receive=0.05, m_ent=8.0, ops_ent=20.0,
+                ops_sigma=0.1, cache_friendliness=0.5, end_time=6.0, min_delay=0.5, time_bins=8)
+    from simian_b200 import capi
+    e = capi.Engine("lanl", 0.0, lanl_engine_end(6.0, 0.5), 0.5, seed=3)
+    build_lanl(e, **case)
+    s2 = e.run()
+    raw = e.read_state(LANL_CLASS, 40, lanl_state_bytes(40, 8.0))
+    state, _ = lanl_states(raw, 40, 8.0)
+    e.close()
+    import io
+    out = io.StringIO()
+    tot = lanl_report(state, 8, out)
+    assert len(out.getvalue().splitlines()) == 1 + 40 + 4
+    assert tot["sends"] == int(state["send_count"].sum()) > 0
+    assert tot["receives"] == int(state["receive_count"].sum())
+    assert s2["total_events"] > tot["sends"]
+
+
+def test_placement_extension_points():
+    """getBaseRank may be overridden (Docs/README.Simian:92-100); getOffsetRank
+    may not: the device routing implements the reference form"""
+    from simian_b200.simian import Entity, Simian, SimianError, device_fn
+
+    class Node(Entity):
+        tick = device_fn("noop")
+
+    class MySimian(Simian):
+        def getBaseRank(self, name):
+            return 7
+
+    eng = MySimian("place", 0, 5, 0.5)
+    eng.addEntity("Node", Node, 0)
+    assert eng.baseRanks["Node"] == 7 and eng._h.base_rank("Node") == 0   # 7 % size(1)
+    eng.schedService(1.0, "tick", None, "Node", 0)
+    assert eng.run()["total_events"] == 1
+    eng.exit()
+
+    class Bad(Simian):
+        def getOffsetRank(self, name, num):
+            return 0
+
+    with pytest.raises(SimianError):
+        Bad("bad", 0, 5, 0.5)
