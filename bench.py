@@ -285,6 +285,9 @@ def main():
     if not args.no_e2e:
         buf, ev = make_host_events(cfg, torch, np, capi, rank, world)
         n = cfg["n"]
+        n_mine = len(ev) // cfg["per_entity"]
+        # the step's results land in page-locked host buffers the caller owns
+        res = torch.empty((2, n_mine), dtype=torch.int64, pin_memory=True).numpy().view(np.uint64)
 
         def one_step_e2e():
             from simian_b200.workloads import phold_params_blob
@@ -301,8 +304,8 @@ def main():
             else:
                 from simian_b200.distributed import drive_windows_p2p
                 st = drive_windows_p2p(e, rank, world, torch.device("cuda", local_rank))
-            counts = e.read_local("Node", 0)[0]     # D2H of the step's results
-            hashes = e.read_local("Node", 1)[0]
+            counts = e.read_local("Node", 0, out=res[0])[0]   # D2H of the step's results
+            hashes = e.read_local("Node", 1, out=res[1])[0]
             e.close()
             return st, counts, hashes
         one_step_e2e()

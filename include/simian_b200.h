@@ -226,6 +226,9 @@ int simian_poll(simian_engine *e, int *done);
 int simian_set_stream(simian_engine *e, void *cudaStream);
 
 /* ---- results: what the parity tests compare ------------------------------ */
+/* `out` buffers in page-locked host memory (cudaHostAlloc / cudaHostRegister,
+ * torch pin_memory) are filled by one DMA; pageable ones through a pinned
+ * bounce buffer and a host copy.                                              */
 /* per-entity committed-event counts of className(first .. first+count-1);
  * entries of entities living on other ranks are left untouched              */
 int simian_read_counts(simian_engine *e, const char *className, uint32_t first,

@@ -301,13 +301,19 @@ class Engine:
     def read_trace_hashes(self, name, n, first=0):
         return self._read(self.L.simian_read_trace_hashes, name, n, first)
 
-    def read_local(self, name, which):
+    def read_local(self, name, which, out=None):
         """this rank's own instances: (values, first num, stride); which: 0
-        counts, 1 trace hashes"""
+        counts, 1 trace hashes.  `out`: a uint64 array to fill (page-locked host
+        memory is written by one DMA, without a bounce buffer)"""
         n, first, stride = _u64(), _u32(), _u32()
         self._ck(self.L.simian_read_local(self.h, name.encode(), which, None, 0,
                                           C.byref(n), C.byref(first), C.byref(stride)))
-        out = np.empty(n.value, dtype=np.uint64)
+        if out is None:
+            out = np.empty(n.value, dtype=np.uint64)
+        elif out.dtype != np.uint64 or out.size < n.value or not out.flags.c_contiguous:
+            raise ValueError("out: contiguous uint64 array of at least %d entries" % n.value)
+        else:
+            out = out[:n.value]
         self._ck(self.L.simian_read_local(self.h, name.encode(), which, out.ctypes.data,
                                           n.value, C.byref(n), C.byref(first), C.byref(stride)))
         return out, first.value, stride.value

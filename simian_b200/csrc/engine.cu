@@ -403,9 +403,12 @@ int setup_layout(simian_engine *e) {
     c.peer_xch[e->rank] = c.xch;
   }
   if (!e->h_acc) {
-    CK(cudaMallocHost((void **)&e->h_acc, sizeof(DevAcc)));
-    CK(cudaMallocHost((void **)&e->h_win, 2 * sizeof(WinState)));
-    CK(cudaMallocHost((void **)&e->h_counts, sizeof(uint32_t) * (size_t)e->size));
+    // pinned mirrors of the device flags, from the process-wide pinned pool (a
+    // cudaMallocHost / cudaFreeHost pair per engine costs about a millisecond)
+    e->h_acc = (DevAcc *)pinned_take(sizeof(DevAcc));
+    e->h_win = (WinState *)pinned_take(2 * sizeof(WinState));
+    e->h_counts = (uint32_t *)pinned_take(sizeof(uint32_t) * SIMIAN_MAX_RANKS);
+    if (!e->h_acc || !e->h_win || !e->h_counts) return e->fail(SIMIAN_ERR_CUDA, "cudaMallocHost failed");
     CK(cudaEventCreate(&e->ev0));
     CK(cudaEventCreate(&e->ev1));
   }
@@ -579,9 +582,9 @@ void simian_destroy(simian_engine *e) {
   for (SchedOp &op : e->ops)
     if (op.d_recs && !cache_give(e->device, op.d_bytes, op.d_recs)) cudaFree(op.d_recs);
   if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
-  if (e->h_acc) cudaFreeHost(e->h_acc);
-  if (e->h_win) cudaFreeHost(e->h_win);
-  if (e->h_counts) cudaFreeHost(e->h_counts);
+  if (e->h_acc) pinned_give(sizeof(DevAcc), e->h_acc);
+  if (e->h_win) pinned_give(2 * sizeof(WinState), e->h_win);
+  if (e->h_counts) pinned_give(sizeof(uint32_t) * SIMIAN_MAX_RANKS, e->h_counts);
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
   if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
@@ -1028,6 +1031,16 @@ int simian_run(simian_engine *e, simian_stats *out) {
   return rc ? rc : rc2;
 }
 
+// the caller's buffer is page-locked host memory: results are copied straight into it
+static bool is_pinned_host(const void *p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost;
+}
+
 static int read_core(simian_engine *e, const char *className, uint32_t first, uint32_t count,
                      uint64_t *out, int which) {
   auto it = e->class_ix.find(className);
@@ -1043,20 +1056,26 @@ static int read_core(simian_engine *e, const char *className, uint32_t first, ui
   k_gather_core<<<592, 256, 0, e->stream>>>(e->cfg, h.slot_base, h.n_local, which, tmp);
   CK(cudaGetLastError());
   uint32_t g = (uint32_t)e->size;
-  size_t pin_bytes = sizeof(uint64_t) * (size_t)h.n_local;
-  uint64_t *loc = (uint64_t *)pinned_take(pin_bytes);
-  if (!loc) return e->fail(SIMIAN_ERR_CUDA, "cudaMallocHost failed");
-  CK(cudaMemcpyAsync(loc, tmp, pin_bytes, cudaMemcpyDeviceToHost, e->stream));
-  CK(cudaStreamSynchronize(e->stream));
-  if (g == 1) { // local index == num
-    memcpy(out, loc + first, sizeof(uint64_t) * (size_t)count);
+  if (g == 1 && is_pinned_host(out)) { // local index == num: one DMA into the caller's buffer
+    CK(cudaMemcpyAsync(out, tmp + first, sizeof(uint64_t) * (size_t)count, cudaMemcpyDeviceToHost,
+                       e->stream));
+    CK(cudaStreamSynchronize(e->stream));
   } else {
-    for (uint32_t j = 0; j < h.n_local; j++) {
-      uint32_t num = j * g + h.rank_off;
-      if (num >= first && num < first + count) out[num - first] = loc[j];
+    size_t pin_bytes = sizeof(uint64_t) * (size_t)h.n_local;
+    uint64_t *loc = (uint64_t *)pinned_take(pin_bytes);
+    if (!loc) return e->fail(SIMIAN_ERR_CUDA, "cudaMallocHost failed");
+    CK(cudaMemcpyAsync(loc, tmp, pin_bytes, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    if (g == 1) {
+      memcpy(out, loc + first, sizeof(uint64_t) * (size_t)count);
+    } else {
+      for (uint32_t j = 0; j < h.n_local; j++) {
+        uint32_t num = j * g + h.rank_off;
+        if (num >= first && num < first + count) out[num - first] = loc[j];
+      }
     }
+    pinned_give(pin_bytes, loc);
   }
-  pinned_give(pin_bytes, loc);
   // hand the scratch buffer straight back to the allocation cache
   auto a = e->allocs.back();
   e->allocs.pop_back();
@@ -1083,12 +1102,17 @@ int simian_read_local(simian_engine *e, const char *className, int which, uint64
   k_gather_core<<<592, 256, 0, e->stream>>>(e->cfg, h.slot_base, h.n_local, which, tmp);
   CK(cudaGetLastError());
   size_t bytes = sizeof(uint64_t) * (size_t)h.n_local;
-  uint64_t *loc = (uint64_t *)pinned_take(bytes);
-  if (!loc) return e->fail(SIMIAN_ERR_CUDA, "cudaMallocHost failed");
-  CK(cudaMemcpyAsync(loc, tmp, bytes, cudaMemcpyDeviceToHost, e->stream));
-  CK(cudaStreamSynchronize(e->stream));
-  memcpy(out, loc, bytes);
-  pinned_give(bytes, loc);
+  if (is_pinned_host(out)) { // one DMA into the caller's page-locked buffer
+    CK(cudaMemcpyAsync(out, tmp, bytes, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+  } else {
+    uint64_t *loc = (uint64_t *)pinned_take(bytes);
+    if (!loc) return e->fail(SIMIAN_ERR_CUDA, "cudaMallocHost failed");
+    CK(cudaMemcpyAsync(loc, tmp, bytes, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    memcpy(out, loc, bytes);
+    pinned_give(bytes, loc);
+  }
   auto a = e->allocs.back();
   e->allocs.pop_back();
   if (!cache_give(e->device, a.second, a.first)) cudaFree(a.first);

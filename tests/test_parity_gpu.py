@@ -295,3 +295,29 @@ def test_contended_cells_many_page_installs(oracle_mod):
         assert se["total_events"] == so["total_events"]
         np.testing.assert_array_equal(ce, co)
         np.testing.assert_array_equal(he, ho)
+
+
+def test_read_back_into_pinned_and_pageable_buffers(oracle_mod):
+    """results go straight into a caller's page-locked buffer (one DMA) or
+    through the bounce buffer: same values"""
+    import torch
+    from simian_b200 import capi
+    from simian_b200.workloads import build_phold
+    case = CASES[1]
+    e = capi.Engine("rb", 0.0, case["end"], case["min_delay"], seed=case["seed"])
+    build_phold(e, case["n"], case["per_entity"], case["lookahead"], case["p_remote"], 1.0,
+                case["mode"], 1)
+    e.run()
+    n = case["n"]
+    pinned = torch.empty((2, n + 5), dtype=torch.int64, pin_memory=True).numpy().view(np.uint64)
+    c0, first, stride = e.read_local("Node", 0)
+    c1, _, _ = e.read_local("Node", 0, out=pinned[0])
+    h0, _, _ = e.read_local("Node", 1)
+    h1, _, _ = e.read_local("Node", 1, out=pinned[1])
+    assert (first, stride, len(c1)) == (0, 1, n)
+    np.testing.assert_array_equal(c0, c1)
+    np.testing.assert_array_equal(h0, h1)
+    np.testing.assert_array_equal(c0, e.read_counts("Node", n))
+    with pytest.raises(ValueError):
+        e.read_local("Node", 0, out=np.zeros(3, dtype=np.uint64))
+    e.close()
