@@ -180,6 +180,12 @@ struct AppendCtx { // per-CTA, in shared memory
 
 // head word of an empty cell: no page, "full" so the first append installs one
 #define CELL_EMPTY (((unsigned long long)SIMIAN_NONE << 32) | (unsigned long long)PAGE)
+// Bit 31 of the head word's count half (and of a page_next entry): the page has
+// an OLDER page behind it.  Cells of one page -- almost all of them -- are then
+// listed without reading page_next at all; claims on a chained cell miss the
+// `count < PAGE` fast path and are serviced by cell_append_slow.
+#define CELL_OLDER 0x80000000u
+#define CELL_COUNT(lo32) ((uint32_t)(lo32) & 0x7FFFFFFFu)
 
 __device__ __forceinline__ void append_ctx_init(AppendCtx &ax) {
   if (threadIdx.x == 0) ax.far_appends = ax.page_allocs = ax.pgc_take = ax.pgc_have = 0;
@@ -238,19 +244,21 @@ __device__ __noinline__ void cell_append_slow(const DevCfg &c, AppendCtx &ax,
                                               unsigned long long q2, unsigned long long q3) {
 #pragma unroll 1
   for (;;) {
-    uint32_t p = (uint32_t)(old >> 32), i = (uint32_t)old;
-    if (i < (uint32_t)PAGE) {
+    const uint32_t p = (uint32_t)(old >> 32), i = CELL_COUNT(old);
+    if (i < (uint32_t)PAGE) { // (a chained cell: the fast path does not take these)
       st_rec_2x16(c.pool + ((size_t)p * PAGE + i), q0, q1, q2, q3);
       return;
     }
     if (i == (uint32_t)PAGE) { // first overflow: install the next page
       uint32_t np = page_get(c, ax, alloc_limit);
       if (np == SIMIAN_NONE) return; // sticky error set
-      c.page_next[np] = p;
+      // the link carries the old head's own "older page" bit
+      c.page_next[np] = p == SIMIAN_NONE ? SIMIAN_NONE : (p | ((uint32_t)old & CELL_OLDER));
       st_rec_2x16(c.pool + (size_t)np * PAGE, q0, q1, q2, q3); // slot 0 is ours
       // no fence: appenders of this launch only write into the page; chains
       // and records are read after a launch boundary or after the ticket fence
-      atomicExch(hp, ((unsigned long long)np << 32) | 1ull);
+      atomicExch(hp, ((unsigned long long)np << 32) |
+                         (unsigned long long)(p == SIMIAN_NONE ? 0u : CELL_OLDER) | 1ull);
       return;
     }
     uint32_t spins = 0;
@@ -1254,12 +1262,15 @@ __device__ __noinline__ bool partition_burst(const DevCfg &c, WindowShared &sh, 
   return true;
 }
 
-// walk one cell's page chain into the CTA's page list
+// walk one cell's page chain into the CTA's page list.  `lo32`: the count half
+// of the cell's head word (records in the head page, CELL_OLDER)
 __device__ __forceinline__ void list_cell_pages(const DevCfg &c, WindowShared &sh, uint32_t head,
-                                                uint32_t head_cnt, uint32_t flag) {
-  uint32_t p = head, cntp = head_cnt;
+                                                uint32_t lo32, uint32_t flag) {
+  uint32_t p = head, cntp = CELL_COUNT(lo32), older = lo32 & CELL_OLDER;
+  if (cntp > (uint32_t)PAGE) cntp = PAGE;
+  if (p == SIMIAN_NONE) return;
 #pragma unroll 1
-  while (p != SIMIAN_NONE) {
+  for (;;) {
     uint32_t idx = atomicAdd(&sh.npg, 1u);
     uint32_t off = atomicAdd(&sh.nvalid, cntp);
     if (idx < PGMAX) {
@@ -1267,8 +1278,12 @@ __device__ __forceinline__ void list_cell_pages(const DevCfg &c, WindowShared &s
       sh.pg_cnt[idx] = (uint16_t)(cntp | flag);
       sh.pg_off[idx] = off;
     }
-    p = c.page_next[p];
-    cntp = PAGE;
+    if (!older) break; // the common case: no link is read
+    const uint32_t raw = c.page_next[p];
+    if (raw == SIMIAN_NONE) break;
+    p = raw & 0x7FFFFFFFu;
+    older = raw & CELL_OLDER;
+    cntp = PAGE; // older pages are always full
   }
 }
 
@@ -1326,7 +1341,7 @@ __device__ void local_min_candidate(const DevCfg &c, const WinState &W, WindowSh
     uint32_t row = (uint32_t)(jf & (long long)c.ring_mask) * c.n_blocks;
     for (uint32_t b = tid; b < c.n_blocks; b += NTHREADS) {
       unsigned long long hw = ld_cg64(&c.cell_state[row + b]);
-      uint32_t p = (uint32_t)(hw >> 32), f = (uint32_t)hw;
+      uint32_t p = (uint32_t)(hw >> 32), f = CELL_COUNT(hw), older = (uint32_t)hw & CELL_OLDER;
       while (p != SIMIAN_NONE) {
         f = f < PAGE ? f : PAGE;
         for (uint32_t s = 0; s < f; s++) {
@@ -1335,7 +1350,11 @@ __device__ void local_min_candidate(const DevCfg &c, const WinState &W, WindowSh
           unsigned long long kk = simian_time_key(__longlong_as_double((long long)q0));
           mn = kk < mn ? kk : mn;
         }
-        p = ld_cg(&c.page_next[p]);
+        if (!older) break;
+        const uint32_t raw = ld_cg(&c.page_next[p]);
+        if (raw == SIMIAN_NONE) break;
+        p = raw & 0x7FFFFFFFu;
+        older = raw & CELL_OLDER;
         f = PAGE;
       }
     }
@@ -1429,11 +1448,14 @@ __device__ void setup_next_window(const DevCfg &c, const WinState &W, WinState *
 
 // free a whole cell (pages -> ring, head cleared); one thread
 __device__ __forceinline__ void free_cell(const DevCfg &c, uint32_t cell) {
-  uint32_t p = (uint32_t)(c.cell_state[cell] >> 32);
+  const unsigned long long hw = c.cell_state[cell];
+  uint32_t p = (uint32_t)(hw >> 32), older = (uint32_t)hw & CELL_OLDER;
   while (p != SIMIAN_NONE) {
-    uint32_t nx = c.page_next[p];
+    const uint32_t raw = older ? c.page_next[p] : SIMIAN_NONE;
     page_free(c, p);
-    p = nx;
+    if (raw == SIMIAN_NONE) break;
+    p = raw & 0x7FFFFFFFu;
+    older = raw & CELL_OLDER;
   }
   c.cell_state[cell] = CELL_EMPTY;
 }
@@ -1458,8 +1480,7 @@ __device__ void redistribute_block(const DevCfg &c, WindowShared &sh, uint32_t b
   __syncthreads();
   if (tid == 0) {
     unsigned long long hw = c.cell_state[far_cell];
-    uint32_t hc = (uint32_t)hw;
-    list_cell_pages(c, sh, (uint32_t)(hw >> 32), hc < PAGE ? hc : PAGE, PG_FREE_FLAG);
+    list_cell_pages(c, sh, (uint32_t)(hw >> 32), (uint32_t)hw, PG_FREE_FLAG);
   }
   __syncthreads();
   uint32_t npg = sh.npg;
@@ -1647,7 +1668,7 @@ __device__ __forceinline__ void process_pass(const DevCfg &c, WindowShared &sh, 
 #pragma unroll
       for (int u = 0; u < EV_PER_THREAD; u++)
         if (cell[u] != SIMIAN_NONE) {
-          if ((uint32_t)old[u] <= (uint32_t)PAGE) {
+          if (CELL_COUNT(old[u]) <= (uint32_t)PAGE) { // lands in a page, or installs one
             const RecBits r = slot_get(sh, tid + u * NTHREADS);
             if ((uint32_t)old[u] < (uint32_t)PAGE)
               st_rec(c.pool + ((size_t)(uint32_t)(old[u] >> 32) * PAGE + (uint32_t)old[u]), r);
@@ -1838,8 +1859,7 @@ __global__ void __launch_bounds__(NTHREADS, SIMIAN_MINBLOCKS)
       // row tb_hi may be appended to during this launch: use the snapshot; rows
       // fully below the bound are recycled after this window
       unsigned long long hw = (tb == W.tb_hi) ? c.snap[b] : c.cell_state[cell];
-      uint32_t hc = (uint32_t)hw;
-      list_cell_pages(c, sh, (uint32_t)(hw >> 32), hc < PAGE ? hc : PAGE,
+      list_cell_pages(c, sh, (uint32_t)(hw >> 32), (uint32_t)hw,
                       (tb == W.tb_hi) ? 0u : PG_FREE_FLAG);
     }
     // set-up of the first (normally only) pass, under the same barrier
