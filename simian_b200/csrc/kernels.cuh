@@ -538,7 +538,7 @@ struct WindowShared {
   AppendCtx ax;
   unsigned long long min_key, max_key, free_base, ring_base;
   uint32_t committed, emitted, dropped, ties, dties, appended;
-  uint32_t npg, nvalid, nfree, total, is_last, found, stack_n, pass_lo, pass_hi, pass_pg_lo,
+  uint32_t npg, nvalid, nfree, free_pos, total, is_last, found, stack_n, pass_lo, pass_hi, pass_pg_lo,
       pass_pg_hi;
   long long scan_j, t_last;
   // entity sub-ranges still to process: (lo, hi, first page-list index, end page-list index)
@@ -1203,6 +1203,7 @@ __device__ __noinline__ bool partition_burst(const DevCfg &c, WindowShared &sh, 
     }
     sh.ppage0[q] = pages;
     sh.nparts = fits ? q : 0u;
+    if (fits) sh.nfree += pages - sh.npg; // the scratch pages are recycled with the others
   }
   __syncthreads();
   const uint32_t nparts = sh.nparts;
@@ -1277,6 +1278,7 @@ __device__ __forceinline__ void list_cell_pages(const DevCfg &c, WindowShared &s
       sh.pg_id[idx] = p;
       sh.pg_cnt[idx] = (uint16_t)(cntp | flag);
       sh.pg_off[idx] = off;
+      if (flag) atomicAdd(&sh.nfree, 1u); // recycled after this window
     }
     if (!older) break; // the common case: no link is read
     const uint32_t raw = c.page_next[p];
@@ -1834,6 +1836,7 @@ __global__ void __launch_bounds__(NTHREADS, SIMIAN_MINBLOCKS)
     sh.npg = 0;
     sh.nvalid = 0;
     sh.nfree = 0;
+    sh.free_pos = 0;
     sh.is_last = 0;
     sh.ax.far_appends = sh.ax.page_allocs = sh.ax.pgc_take = 0;
     sh.ax.pgc_have = c.bcount[b];
@@ -1909,35 +1912,33 @@ __global__ void __launch_bounds__(NTHREADS, SIMIAN_MINBLOCKS)
   }
   __syncthreads();
   // ---- recycle: the pages of rows [tb_clean, tb_hi) go onto the block's own
-  // page stack (what does not fit: to the global ring), heads are cleared
+  // page stack (what does not fit: to the global ring), heads are cleared.  The
+  // stack lives in HBM (bcache[b]); the entries below the ones popped in this
+  // launch stay where they are, the recycled pages are written above them.
   {
     const uint32_t have = sh.ax.pgc_have;
     const uint32_t rem = have - (sh.ax.pgc_take < have ? sh.ax.pgc_take : have);
-    uint32_t mine = 0;
-    if (!W.redist)
-      for (uint32_t i = tid; i < npg; i += NTHREADS)
-        if (sh.pg_cnt[i] & PG_FREE_FLAG) mine++;
-    uint32_t pos = 0;
-    if (mine) pos = atomicAdd(&sh.nfree, mine);
-    __syncthreads();
-    const uint32_t nfree = sh.nfree;
-    const uint32_t room = SIMIAN_BC - rem;             // free pages the stack still takes
+    const uint32_t nfree = W.redist ? 0u : sh.nfree;       // counted while the pages were listed
+    const uint32_t room = SIMIAN_BC - rem;                 // free pages the stack still takes
     const uint32_t over = nfree > room ? nfree - room : 0; // the rest goes to the ring
     uint32_t cnt = rem + (nfree - over);                   // stack height after recycling
     // low stack: take pages from the ring for the next window (one atomic)
     const uint32_t need = (cnt < SIMIAN_BC_LOW) ? SIMIAN_BC_FILL - cnt : 0u;
-    if (tid == 0) {
-      if (over) sh.free_base = atomicAdd(&c.acc->free_tail, (unsigned long long)over);
-      if (need) sh.ring_base = atomicAdd(&c.acc->alloc_head, (unsigned long long)need);
+    if (over || need) {
+      if (tid == 0) {
+        if (over) sh.free_base = atomicAdd(&c.acc->free_tail, (unsigned long long)over);
+        if (need) sh.ring_base = atomicAdd(&c.acc->alloc_head, (unsigned long long)need);
+      }
+      __syncthreads();
     }
-    if (over || need) __syncthreads();
     if (!W.redist) {
+      uint32_t *stack = c.bcache + (size_t)b * SIMIAN_BC;
       for (uint32_t i = tid; i < npg; i += NTHREADS)
         if (sh.pg_cnt[i] & PG_FREE_FLAG) {
-          uint32_t k = pos++;
+          const uint32_t k = atomicAdd(&sh.free_pos, 1u);
           if (k < nfree - over)
-            sh.ax.pgc[rem + k] = sh.pg_id[i];
-          else
+            stack[rem + k] = sh.pg_id[i];
+          else if (k < nfree)
             c.free_ring[(sh.free_base + (k - (nfree - over))) % c.n_pages] = sh.pg_id[i];
         }
       if (tid < ncell - 1) {
@@ -1957,13 +1958,12 @@ __global__ void __launch_bounds__(NTHREADS, SIMIAN_MINBLOCKS)
       // ring slots beyond alloc_limit are not valid yet: take only what is
       unsigned long long lim = W.alloc_limit, base = sh.ring_base;
       uint32_t okn = base >= lim ? 0u : (lim - base < need ? (uint32_t)(lim - base) : need);
-      if ((uint32_t)tid < okn) sh.ax.pgc[cnt + tid] = c.free_ring[(base + tid) % c.n_pages];
+      if ((uint32_t)tid < okn)
+        c.bcache[(size_t)b * SIMIAN_BC + cnt + tid] = c.free_ring[(base + tid) % c.n_pages];
       if (tid == 0 && okn < need)
         atomicAdd(&c.acc->leaked_pages, (unsigned long long)(need - okn));
       cnt += okn;
     }
-    __syncthreads();
-    if (tid < (int)cnt) c.bcache[(size_t)b * SIMIAN_BC + tid] = sh.ax.pgc[tid];
     if (tid == 0) c.bcount[b] = cnt;
   }
 
