@@ -172,6 +172,7 @@ struct simian_engine {
   uint64_t pool_events = 0, outbox_events = 0;
   int launch_batch = 16, tie_check = 1, force_sequential = 0;
   uint32_t epb_override = 0; // option "block_entities"
+  int pdl = 1;               // option "pdl": window launches overlap the previous one's drain
   // model
   std::vector<HostClass> classes;
   std::map<std::string, int> class_ix;
@@ -608,6 +609,7 @@ int simian_set_option(simian_engine *e, const char *key, double v) {
   else if (k == "tie_check") e->tie_check = v != 0;
   else if (k == "force_sequential") e->force_sequential = v != 0;
   else if (k == "block_entities") e->epb_override = (uint32_t)v;
+  else if (k == "pdl") e->pdl = v != 0;
   else return e->fail(SIMIAN_ERR_BAD_ARGUMENT, "unknown option " + k);
   return 0;
 }
@@ -1013,7 +1015,24 @@ int simian_run(simian_engine *e, simian_stats *out) {
   int batch = e->launch_batch;
   for (;;) {
     for (int i = 0; i < batch; i++) {
-      k_window<<<e->cfg.n_blocks, NTHREADS, e->smem_bytes, e->stream>>>(e->cfg, e->win_ix, 1);
+      if (e->pdl) {
+        // programmatic dependent launch: the CTAs of window k+1 become resident
+        // while the last wave of window k drains (they wait inside the kernel)
+        cudaLaunchConfig_t lc;
+        memset(&lc, 0, sizeof lc);
+        lc.gridDim = dim3(e->cfg.n_blocks);
+        lc.blockDim = dim3(NTHREADS);
+        lc.dynamicSmemBytes = e->smem_bytes;
+        lc.stream = e->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        lc.attrs = at;
+        lc.numAttrs = 1;
+        CK(cudaLaunchKernelEx(&lc, k_window, e->cfg, e->win_ix, 1));
+      } else {
+        k_window<<<e->cfg.n_blocks, NTHREADS, e->smem_bytes, e->stream>>>(e->cfg, e->win_ix, 1);
+      }
       e->win_ix++;
       e->launches++;
     }

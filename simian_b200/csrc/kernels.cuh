@@ -1822,6 +1822,12 @@ __global__ void __launch_bounds__(NTHREADS, SIMIAN_MINBLOCKS)
   WindowShared &sh = *reinterpret_cast<WindowShared *>(smem_raw);
   const int tid = threadIdx.x;
   const uint32_t b = blockIdx.x;
+  // Programmatic dependent launch: every resident CTA of the previous window
+  // has started, so this grid's CTAs may take the SM slots that launch's last
+  // wave frees -- and wait here until it has completed and its writes are
+  // visible.  (Both calls are no-ops for an ordinary launch.)
+  cudaTriggerProgrammaticLaunchCompletion();
+  cudaGridDependencySynchronize();
   const WinState *Wg = &c.win[win_ix & 1u];
   if (Wg->done) return; // simian.js:119: enqueued past the end of the run
   if (tid == 0) sh.found = ld_cg(&c.acc->error);
