@@ -31,8 +31,8 @@ sys.path.insert(0, ROOT)
 
 BYTES_PER_EVENT = 96  # 32 read + 32 write + 16 + 16 state
 # dram__bytes_read.sum + dram__bytes_write.sum of one steady-state k_window launch
-# (config 2, ~1.68 M committed events): profiles/r1_q_k_window_ncu_full.csv
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 81539072 + 45740288
+# (config 2, ~1.68 M committed events): profiles/r1_s_k_window_ncu_full.csv
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 79651328 + 45706496
 
 
 def load_peaks():
@@ -228,6 +228,9 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
+        # NCCL_DEBUG=VERSION prints a banner on stdout, where the ONE JSON line goes
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     cfg = workload_for(world, args.scale)
     peak, peak_kind = load_peaks()
@@ -363,7 +366,7 @@ def main():
                      "note": "achieved = committed events/s per GPU x 96 B over the whole "
                              "timed window loop (k_window is >99% of it); traffic = "
                              "dram read+write bytes of one steady-state k_window launch, "
-                             "ncu --set full, profiles/r1_q_k_window_ncu_full.csv"},
+                             "ncu --set full, profiles/r1_s_k_window_ncu_full.csv"},
     }
     if e2e is not None:
         line["e2e"] = e2e
