@@ -226,11 +226,19 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback")
     torch.cuda.set_device(local_rank)
     dist = None
+    # stdout carries ONE JSON line: whatever libraries print there while the
+    # benchmark runs (NCCL's version banner at its first collective) goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(line), flush=True)
+
     if world > 1:
         import torch.distributed as dist
-        # NCCL_DEBUG=VERSION prints a banner on stdout, where the ONE JSON line goes
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     cfg = workload_for(world, args.scale)
     peak, peak_kind = load_peaks()
@@ -374,7 +382,7 @@ def main():
         cb = cpu_baseline_sample(cfg)
         cb.pop("events"), cb.pop("seconds")
         line["cpu_baseline"] = cb
-    print(json.dumps(line), flush=True)
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
