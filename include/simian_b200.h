@@ -92,7 +92,11 @@ const char *simian_last_error(simian_engine *e);
  *   "outbox_events"   per-peer cross-GPU staging capacity in records
  *   "launch_batch"    window kernels enqueued between host polls
  *   "tie_check"       1: count same-entity time ties (default 1)
- *   "force_sequential" 1: always run handlers one thread per entity (testing)  */
+ *   "force_sequential" 1: always run handlers one thread per entity (testing)
+ *   "block_entities"  entities per entity block = per CTA of the window kernel (default and max 512)
+ *   "pdl"             1: window kernels are launched as programmatic dependents of
+ *                     each other, the next window's CTAs become resident while the
+ *                     previous one drains (default 1; size == 1)                  */
 int simian_set_option(simian_engine *e, const char *key, double value);
 
 /* Entity classes.  An entity class = the `name` of addEntity plus the JS class
