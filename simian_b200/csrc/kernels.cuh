@@ -944,9 +944,9 @@ __device__ __forceinline__ uint32_t rank_event(const DevCfg &c, WindowShared &sh
   // tie-break words of this event: (handler, src) and seq
   const unsigned long long my2 = ((bh.x & 0xFFFFull) << 32) | (a.y >> 32);
   const uint32_t myseq = (uint32_t)(bh.x >> 32);
-  // latest equal-time predecessor (for the tie statistics): its key and slot
-  uint32_t pj = LIST_END, pseq = 0;
-  unsigned long long p2 = 0;
+  // tie statistics: is there an equal-time event before this one, and does
+  // any of those differ from it in what the handler sees
+  bool has_pred = false, any_diff = false;
   // t = the rank-th node of the list: it trails the walk (rank so far <= nodes
   // visited so far), one step forward for every event found to precede this one
   uint32_t t = first;
@@ -959,28 +959,46 @@ __device__ __forceinline__ uint32_t rank_event(const DevCfg &c, WindowShared &sh
       rank++;
       t = sh.nxt[t];
     } else if (to == tr) { // a true same-entity time tie: the defined order decides
-      const unsigned long long ox = sh.hi[j].x;
-      const unsigned long long o2 = ((ox & 0xFFFFull) << 32) | (o.y >> 32);
-      const uint32_t oseq = (uint32_t)(ox >> 32);
+      const ulonglong2 oh = sh.hi[j];
+      const unsigned long long o2 = ((oh.x & 0xFFFFull) << 32) | (o.y >> 32);
+      const uint32_t oseq = (uint32_t)(oh.x >> 32);
       // identical records (same key down to seq) are ordered by their slot: any
       // order of indistinguishable events commits the same thing
       const bool before = o2 != my2 ? o2 < my2 : (oseq != myseq ? oseq < myseq : j < i);
       if (before) {
         rank++;
         t = sh.nxt[t];
+        has_pred = true;
+        any_diff |= (o2 != my2) | (oh.y != bh.y);
+      }
+    }
+  }
+  if (c.tie_check && has_pred) {
+    ta.ties++;
+    // distinguishable tie: the LATEST equal-time predecessor differs in (handler,
+    // src) or data.  When every equal-time predecessor is indistinguishable from
+    // this event (bursts of identical schedService calls) the answer is no;
+    // otherwise the latest one is looked for (rare: models with real ties).
+    if (any_diff) {
+      uint32_t pj = LIST_END, pseq = 0;
+      unsigned long long p2 = 0;
+#pragma unroll 1
+      for (uint32_t j = first; j != LIST_END; j = sh.nxt[j]) {
+        if (j == i || __longlong_as_double((long long)sh.lo[j].x) != tr) continue;
+        const unsigned long long ox = sh.hi[j].x;
+        const unsigned long long o2 = ((ox & 0xFFFFull) << 32) | (sh.lo[j].y >> 32);
+        const uint32_t oseq = (uint32_t)(ox >> 32);
+        const bool before = o2 != my2 ? o2 < my2 : (oseq != myseq ? oseq < myseq : j < i);
         // keep the latest predecessor: (key, seq, slot) maximal
-        if (pj == LIST_END || (p2 != o2 ? p2 < o2 : (pseq != oseq ? pseq < oseq : pj < j))) {
+        if (before &&
+            (pj == LIST_END || (p2 != o2 ? p2 < o2 : (pseq != oseq ? pseq < oseq : pj < j)))) {
           pj = j;
           p2 = o2;
           pseq = oseq;
         }
       }
+      if (p2 != my2 || sh.hi[pj].y != bh.y) ta.dties++;
     }
-  }
-  if (c.tie_check && pj != LIST_END) {
-    ta.ties++;
-    // distinguishable: (handler, src) or data differ -- what the handler sees
-    if (p2 != my2 || sh.hi[pj].y != bh.y) ta.dties++;
   }
   sh.xs[t] = simian_trace_event(tr, (uint32_t)(bh.x & 0xFFFFull), (uint32_t)(a.y >> 32), bh.y);
   unsigned long long tk = simian_time_key(tr);
