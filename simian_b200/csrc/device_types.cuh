@@ -5,7 +5,7 @@
 //   SimianJS/simian.js:53-59  entities{} / eventList[] / eventQueue
 // with
 //   * a paged CALENDAR in HBM: cell (time sub-bucket, entity block) -> chain of
-//     2-KB pages of 32-byte POD event records (one DRAM sector per record);
+//     4-KB pages of 32-byte POD event records (one DRAM sector per record);
 //   * per-entity core state {commit count, trace hash} (16 B) + per-class user
 //     state, indexed by local slot;
 //   * a double-buffered device-resident window descriptor (the LBTS state of

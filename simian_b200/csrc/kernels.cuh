@@ -3,13 +3,18 @@
 // One lookahead window of the reference (SimianJS/simian.js:119-148) is ONE
 // launch of k_window:
 //   K2  coalesced dequeue of every event below the window bound from the
-//       block's calendar cells                       (eventQ.pop, eventQ.js:53-92)
+//       block's calendar cells: the records of the window's pages are copied
+//       into shared-memory slots with cp.async in one round trip and the due
+//       ones linked per entity                      (eventQ.pop, eventQ.js:53-92)
 //   K3  handlers of all entities in parallel, each entity's events in
 //       (time, handler, src, seq) order               (simian.js:124-133)
 //   K4  emit: lock-free paged append of 32-B records into the destination
 //       cell, or into the per-peer outbox             (entity.js:47-67, eventQ.push)
 //   K1  LBTS: block min-reduction of leftover + emitted times, one atomicMin
 //       per CTA, last CTA computes the next window    (simian.js:120,143-147)
+// The common window is a straight line of phases (collect_all, link_due,
+// process_pass); windows whose records overflow the CTA's 1024 slots (bursts)
+// go through ONE out-of-line function (filtered_passes / partition_burst).
 // Compiled with -fmad=false: include/simian_spec.h must see no FMA contraction.
 #pragma once
 #include "device_types.cuh"
