@@ -73,6 +73,8 @@ const char *simian_version(void);
 
 /* new Simian(simName, startTime, endTime, minDelay, useMPI)   simian.js:36-84
  * rank/size play MPI.rank()/MPI.size() (simian.js:73-75): one engine per GPU.
+ * size <= 16 (SIMIAN_MAX_RANKS: the GPUs of one NVLink domain; the peer tables
+ * of the device-driven exchange are that long) -- larger worlds are refused.
  * device < 0 selects cuda device `rank % deviceCount`.  Returns NULL on failure
  * (simian_last_error(NULL) tells why; in particular when no GPU is present). */
 simian_engine *simian_create(const char *simName, double startTime,
@@ -87,7 +89,7 @@ const char *simian_last_error(simian_engine *e);
 /* Engine tunables, all optional, before the first run:
  *   "seed"            engine seed of the shared counter-based RNG (default 1)
  *   "bucket_width"    calendar sub-bucket width in simulated time (default minDelay/8)
- *   "ring_buckets"    calendar ring length, power of two (default 2048)
+ *   "ring_buckets"    calendar ring length, power of two (default 1024)
  *   "pool_events"     event pool capacity in records (default 2x initial + one page per calendar cell)
  *   "outbox_events"   per-peer cross-GPU staging capacity in records
  *   "launch_batch"    window kernels enqueued between host polls
@@ -205,6 +207,11 @@ int simian_setup(simian_engine *e);
 /* blob == NULL: *written = blob size.  Otherwise fills the blob to publish. */
 int simian_ipc_export(simian_engine *e, void *blob, uint64_t blobBytes, uint64_t *written);
 int simian_ipc_import(simian_engine *e, int peerRank, const void *blob, uint64_t blobBytes);
+
+/* The same connection for ranks that live in ONE process (every rank's engine on
+ * one device: the multi-rank paths of a one-GPU test run): peer buffers are
+ * wired by plain device pointers, no CUDA IPC.  Call on every ordered pair.   */
+int simian_connect_local(simian_engine *e, int peerRank, simian_engine *peer);
 /* simian_window_process with the LBTS candidate computed by the last CTA of
  * the same launch (no separate simian_window_local_min / publish_min launch);
  * publish != 0: and written to the peers' exchange slots                     */

@@ -77,6 +77,7 @@ SIGNATURES = {
     "simian_setup": (_i, [_vp]),
     "simian_ipc_export": (_i, [_vp, _vp, _u64, C.POINTER(_u64)]),
     "simian_ipc_import": (_i, [_vp, _i, _vp, _u64]),
+    "simian_connect_local": (_i, [_vp, _i, _vp]),
     "simian_window_pull": (_i, [_vp, _i]),
     "simian_window_publish_min": (_i, [_vp]),
     "simian_window_process_lbts": (_i, [_vp, _i]),
@@ -256,6 +257,10 @@ class Engine:
     def ipc_import(self, peer_rank, blob):
         buf = C.create_string_buffer(bytes(blob), len(blob))
         self._ck(self.L.simian_ipc_import(self.h, peer_rank, buf, len(blob)))
+
+    def connect_local(self, peer_rank, peer):
+        """wire a peer engine of the SAME process by plain device pointers"""
+        self._ck(self.L.simian_connect_local(self.h, peer_rank, peer.h))
 
     def window_pull(self, wait_for_peers=False):
         self._ck(self.L.simian_window_pull(self.h, int(wait_for_peers)))

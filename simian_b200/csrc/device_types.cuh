@@ -4,10 +4,8 @@
 //   SimianJS/eventQ.js        one binary heap of boxed event objects per rank
 //   SimianJS/simian.js:53-59  entities{} / eventList[] / eventQueue
 // with
-//   * a paged CALENDAR in HBM: cell (entity group, time sub-bucket) -> chain of
-//     512-byte pages of 32-byte POD event records (one DRAM sector per record);
-//     an entity GROUP is 64 consecutive local entities, owned by ONE WARP of
-//     the window kernel;
+//   * a paged CALENDAR in HBM: cell (time sub-bucket, entity block) -> chain of
+//     4-KB pages of 32-byte POD event records (one DRAM sector per record);
 //   * per-entity core state {commit count, trace hash} (16 B) + per-class user
 //     state, indexed by local slot;
 //   * a double-buffered device-resident window descriptor (the LBTS state of
@@ -18,34 +16,29 @@
 #include "../../include/simian_models.h"
 #include "../../include/simian_spec.h"
 
-#ifndef SIMIAN_GE_SHIFT
-#define SIMIAN_GE_SHIFT 6 // log2(entities per group)
+#ifndef SIMIAN_EPB
+#define SIMIAN_EPB 512 // max entities per block (one CTA owns one block)
 #endif
-#define SIMIAN_GE (1u << SIMIAN_GE_SHIFT) // entities per group (one warp owns one group)
-static_assert(SIMIAN_GE == 64, "a lane of the owning warp handles entities lane and lane + 32");
-#ifndef SIMIAN_WPC
-#define SIMIAN_WPC 4 // default warps (= entity groups) per CTA of the window kernel
+#ifndef SIMIAN_THREADS
+#define SIMIAN_THREADS 256 // threads per CTA of the window kernel
 #endif
-#define SIMIAN_WPC_MAX 8
-#define SIMIAN_THREADS (32 * SIMIAN_WPC_MAX) // max threads per CTA of the window kernel
 #ifndef SIMIAN_PAGE
-#define SIMIAN_PAGE 16 // records per page (512 B)
+#define SIMIAN_PAGE 128 // records per page (4 KB)
 #endif
-#ifndef SIMIAN_NSLOT
-#define SIMIAN_NSLOT 144 // records a warp holds on chip per pass
+#ifndef SIMIAN_REFS
+#define SIMIAN_REFS (4 * SIMIAN_THREADS) // due events a CTA holds on chip per pass
 #endif
 #ifndef SIMIAN_PGMAX
-#define SIMIAN_PGMAX 96 // pages a warp lists on chip; longer lists are walked in chunks
+#define SIMIAN_PGMAX (SIMIAN_EPB + SIMIAN_EPB / 4) // pages a CTA can list per window
 #endif
 #ifndef SIMIAN_BC
-#define SIMIAN_BC 32 // free pages an entity group keeps for itself (group page cache)
+#define SIMIAN_BC 64 // free pages an entity block keeps for itself (block page cache)
 #endif
-#define SIMIAN_BC_ROW (SIMIAN_BC + 4) // words per cache row in HBM: pages, then the count
-#define SIMIAN_BC_FILL 16 // refill target / initial fill of a group page cache
-#define SIMIAN_BC_LOW 4   // refill from the global ring below this
+#define SIMIAN_BC_FILL 32 // refill target / initial fill of a block page cache
+#define SIMIAN_BC_LOW 8   // refill from the global ring below this
 
 #ifndef SIMIAN_MINBLOCKS
-#define SIMIAN_MINBLOCKS 3 // __launch_bounds__(256, 3): 80 registers; 6 CTAs of 4 warps per SM
+#define SIMIAN_MINBLOCKS 3 // __launch_bounds__ min CTAs/SM of the window kernel
 #endif
 
 #define SIMIAN_MAX_RANKS 16 // GPUs of one box (peer memory over NVLink)
@@ -55,15 +48,6 @@ static_assert(SIMIAN_GE == 64, "a lane of the owning warp handles entities lane 
 #define SIMIAN_NONE 0xFFFFFFFFu
 #define SIMIAN_KEY_NONE 0xFFFFFFFFFFFFFFFFull
 #define SIMIAN_SELF_MAX 8 // same-window self-sends pending per entity
-// Time word of a record slot nobody has written in the page's current life.
-// FREE-PAGE INVARIANT: every record slot of a free page holds a time below the
-// lower bound of every window that can ever read the page again (-inf after
-// k_init and after a far-row page is released; otherwise the time of a record
-// a past window consumed).  A reader may therefore copy a page beyond the
-// records that were complete when the launch began: what it finds there is
-// either such a dead record or one being appended right now (time >= the
-// window's upper bound) -- never a due one.
-#define SIMIAN_TIME_DEAD 0xFFF0000000000000ull
 
 struct __align__(16) EntityCore {
   uint64_t count; // committed events                (numEvents, per entity)
@@ -81,7 +65,7 @@ struct DevClass {
   uint32_t params_bytes;
   uint8_t *state;     // n_local * state_bytes
   const void *params; // model parameters (device copy)
-  uint8_t fn_of_service[SIMIAN_MAX_SERVICES]; // service id -> device function id
+  uint8_t fn_of_service[SIMIAN_MAX_SERVICES]; // service id -> builtin fn
 };
 
 // LBTS / window descriptor (simian.js:118-120,143-147), device resident.
@@ -97,7 +81,6 @@ struct WinState {
   uint32_t parity;        // window index & 1: which outbox this window fills
   unsigned long long alloc_limit; // pages allocatable in this launch
 };
-static_assert(sizeof(WinState) == 72, "copied into shared memory as nine 8-byte words");
 
 // Global accumulators (atomics), reset by the advance step.
 struct DevAcc {
@@ -112,7 +95,7 @@ struct DevAcc {
   unsigned int ticket;
   unsigned int error; // sticky, first error wins
   unsigned int window_index;
-  unsigned int loop_arrive; // persistent window loop: CTAs that finished the current window
+  unsigned int pad_;
   double minvec[2]; // {local minLeft candidate, local far min} for allreduce
   unsigned long long phase_cycles[12]; // SIMIAN_PROFILE_PHASES builds only
 };
@@ -141,34 +124,32 @@ struct DevCfg {
   int n_classes, tie_check;
   int all_pure, pad2_; // every attached handler is stateless: thread-per-event path
   DevClass cls[SIMIAN_MAX_CLASSES];
-  // entities: core[] is padded to whole groups
+  // entities
   EntityCore *core;
-  uint32_t n_slots, n_groups;
+  uint32_t n_slots, n_blocks;
+  // entities per block, <= SIMIAN_EPB: chosen at setup so that the grid of the
+  // window kernel fills whole waves of resident CTAs (epb_inv = ceil(2^64/epb))
+  uint32_t epb, pad3_;
+  unsigned long long epb_inv;
   // calendar
   double inv_w;
   uint32_t ring, ring_mask;
-  uint32_t rows, pad3_; // ring + 2: head words per group (the last two are the far-future rows)
-  // cell head word = (head page << 32) | older-page bit << 31 | records claimed
-  // in the head page; [n_groups][rows]: the sub-buckets of one group are
-  // contiguous, so the warp that owns the group lists a window's cells from a
-  // few sectors
+  // cell head word = (head page << 32) | records claimed in the head page;
+  // [(ring+2) * n_blocks], row-major by sub-bucket slot; the last two rows are
+  // the far-future rows
   unsigned long long *cell_state;
   simian_event_t *pool;
-  uint32_t *page_next; // older page of the same cell (always full); NONE while the page
-                       // is free or has no older page
+  uint32_t *page_next; // older page of the same cell (always full)
   uint32_t *free_ring;
   uint32_t n_pages, n_ids;
-  // one bit per ring row: some group has (had) a page in that row since the row
-  // was last recycled; the sparse-case LBTS search reads ring/32 words instead of
-  // every head word
-  uint32_t *row_bits; // [ring / 32]
-  WinState *win;      // [2]
+  unsigned long long *snap; // [n_blocks] head words of row tb_hi at window start
+  WinState *win;                  // [2]
   DevAcc *acc;
   BlockPart *part; // [SIMIAN_PART_SLOTS]
-  // group page caches: pages an entity group recycled and will reuse, so that
-  // steady-state windows never touch the global free ring.  Row g =
-  // {SIMIAN_BC page ids (a stack), count, 3 pad words}: one 144-byte bulk copy
-  uint32_t *bcache; // [n_groups][SIMIAN_BC_ROW]
+  // block page caches: pages an entity block recycled and will reuse, so that
+  // steady-state windows never touch the global free ring
+  uint32_t *bcache; // [n_blocks][SIMIAN_BC]
+  uint32_t *bcount; // [n_blocks]
   // cross-GPU staging (size > 1), double buffered by window parity: the
   // records window k sends stay readable by the peers until window k+2
   simian_event_t *outbox; // [2][size][outbox_cap]

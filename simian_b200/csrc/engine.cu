@@ -171,7 +171,7 @@ struct simian_engine {
   uint32_t ring = 1024;
   uint64_t pool_events = 0, outbox_events = 0;
   int launch_batch = 16, tie_check = 1, force_sequential = 0;
-  int wpc = SIMIAN_WPC;       // option "block_entities" / 64: entity groups (warps) per CTA
+  uint32_t epb_override = 0; // option "block_entities"
   int pdl = 1;               // option "pdl": window launches overlap the previous one's drain
   // model
   std::vector<HostClass> classes;
@@ -201,8 +201,7 @@ struct simian_engine {
   WinState *h_win = nullptr;
   uint32_t *h_counts = nullptr;
   std::chrono::steady_clock::time_point t_begin;
-  size_t smem_bytes = WINDOW_SMEM_BYTES(SIMIAN_WPC);
-  uint32_t grid = 1; // CTAs of the window kernel
+  size_t smem_bytes = sizeof(WindowShared);
   void *ipc_slab = nullptr; // outbox_count at +0, exchange slots at +4096
   uint64_t salt = 0;
   bool peer_seen[SIMIAN_MAX_RANKS] = {};
@@ -261,11 +260,9 @@ int dev_alloc(simian_engine *e, T **p, size_t n) {
   return 0;
 }
 
-constexpr int AUX_THREADS = 256; // one-CTA kernels of the LBTS step
-
 // The parameter blob of a class must be what its attached device function
 // reads (the reference throws inside the handler on a bad model; here a bad
-// blob would index past HBM buffers).
+// blob would index past HBM buffers).  No blob at all: the device copy is zeros.
 int check_class_params(simian_engine *e, const HostClass &h, int fn) {
   size_t need = 0;
   switch (fn) {
@@ -280,7 +277,7 @@ int check_class_params(simian_engine *e, const HostClass &h, int fn) {
     case SIMIAN_FN_HELLO_RESULT: need = sizeof(simian_hello_params_t); break;
     default: return 0;
   }
-  if (h.params.empty()) return 0; // none given: the device copy is zero-filled (see setup_layout)
+  if (h.params.empty()) return 0;
   if (h.params.size() < need)
     return e->fail(SIMIAN_ERR_BAD_ARGUMENT,
                    "class " + h.name + ": parameter blob smaller than its device function reads");
@@ -290,8 +287,7 @@ int check_class_params(simian_engine *e, const HostClass &h, int fn) {
     if (p.n_entities == 0 || (uint64_t)p.first_id + p.n_entities > e->n_ids)
       return e->fail(SIMIAN_ERR_BAD_ARGUMENT, "phold: first_id + n_entities exceeds the entities added");
     if (p.mode == SIMIAN_PHOLD_OTHER_GROUP && (p.groups < 2 || p.n_entities < p.groups))
-      return e->fail(SIMIAN_ERR_BAD_ARGUMENT,
-                     "phold OTHER_GROUP needs 2 <= groups <= n_entities");
+      return e->fail(SIMIAN_ERR_BAD_ARGUMENT, "phold OTHER_GROUP needs 2 <= groups <= n_entities");
   }
   return 0;
 }
@@ -321,9 +317,10 @@ void teardown_layout(simian_engine *e) {
 int setup_layout(simian_engine *e) {
   if (e->laid_out) return 0;
   DevCfg &c = e->cfg;
-  e->smem_bytes = WINDOW_SMEM_BYTES(e->wpc);
   CK(cudaFuncSetAttribute(k_window, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                          (int)WINDOW_SMEM_BYTES(SIMIAN_WPC_MAX)));
+                          (int)e->smem_bytes));
+  CK(cudaFuncSetAttribute(k_local_min, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          (int)e->smem_bytes));
   memset(&c, 0, sizeof c);
   c.start = e->start;
   c.end = e->end;
@@ -389,53 +386,47 @@ int setup_layout(simian_engine *e) {
     d.params = dp;
   }
   c.n_slots = slot;
-  // entity groups of 64 local slots, one warp each; wpc groups per CTA
-  c.n_groups = (slot + GE - 1) / GE;
-  if (c.n_groups == 0) c.n_groups = 1;
-  e->grid = (c.n_groups + (uint32_t)e->wpc - 1) / (uint32_t)e->wpc;
+  // Entities per block (option "block_entities", <= SIMIAN_EPB).  Shrinking the
+  // block so that the grid fills whole waves of resident CTAs was measured on
+  // config 2 (480 instead of 512: 4.92 instead of 4.61 waves) and gained nothing:
+  // CTAs do not run in lock-step waves, and smaller blocks pay more per-CTA overhead.
+  c.epb = e->epb_override ? e->epb_override : EPB;
+  if (c.epb > EPB || c.epb < 1) return e->fail(SIMIAN_ERR_BAD_ARGUMENT, "bad block_entities");
+  c.epb_inv = ~0ull / c.epb + 1ull; // ceil(2^64 / epb): x / epb == umul64hi(x, epb_inv) for x < 2^32
+  c.n_blocks = (slot + c.epb - 1) / c.epb;
+  if (c.n_blocks == 0) c.n_blocks = 1;
   double w = e->bucket_width > 0 ? e->bucket_width : e->min_delay / 8.0;
   c.inv_w = 1.0 / w;
   uint32_t ring = 256;
   while (ring < e->ring) ring <<= 1;
   c.ring = ring;
   c.ring_mask = ring - 1;
-  c.rows = ring + 2;
-  if ((uint64_t)c.n_groups * c.rows >= 0xFFFFFFFFull)
-    return e->fail(SIMIAN_ERR_BAD_ARGUMENT, "too many calendar cells: lower ring_buckets");
   // events this rank will hold at the start: script loops (schedService /
   // constructors) run on every rank and only owners keep their share; host
   // records may already be the rank's own (all counted: an upper bound)
   uint64_t local_initial = (e->initial_events - e->record_events) / g + e->record_events + 1;
-  // Default pool.  A group's pending records occupy one open (partial) page per
-  // non-empty cell plus their full pages.  The safe bound is one page for every
-  // cell + the full pages; it is the default while it stays below 16 GB (pages are
-  // only touched when used: a large pool costs address space, not time).  Beyond
-  // that the default is six times the initial records (config 2 and 3 use four
-  // times) or 16 GB, whichever is larger.  "pool_events"
-  // overrides; SIMIAN_ERR_POOL_EXHAUSTED is loud.
-  const uint64_t full_pages = 2 * local_initial / PAGE + (uint64_t)SIMIAN_BC * c.n_groups + 1024ull;
-  const uint64_t safe_pages = (uint64_t)c.rows * c.n_groups + full_pages;
-  const uint64_t cap16 = (16ull << 30) / (PAGE * sizeof(simian_event_t));
-  uint64_t n_pages = safe_pages;
-  if (n_pages > cap16) {
-    const uint64_t heur = 6 * local_initial / PAGE + 64ull * c.n_groups + 1024ull;
-    n_pages = heur > cap16 ? heur : cap16;
-    if (n_pages > safe_pages) n_pages = safe_pages;
-  }
-  if (e->pool_events) n_pages = (e->pool_events + PAGE - 1) / PAGE;
-  if (n_pages > 0x7FFFFFFFull) n_pages = 0x7FFFFFFFull; // bit 31 of a page link is a flag
+  // default pool: twice the initial events + one (partial) page for every cell
+  // of the ring, the upper bound on simultaneously open pages
+  uint64_t pool_events = e->pool_events
+                             ? e->pool_events
+                             : 2 * local_initial +
+                                   (uint64_t)PAGE * ((uint64_t)(ring + 2) * c.n_blocks + 1024ull +
+                                                     (uint64_t)SIMIAN_BC * c.n_blocks);
+  uint64_t n_pages = (pool_events + PAGE - 1) / PAGE;
+  if (n_pages > 0xFFFFFFFFull / PAGE) n_pages = 0xFFFFFFFFull / PAGE;
   c.n_pages = (uint32_t)n_pages;
-  size_t n_cells = (size_t)c.rows * c.n_groups;
-  if (dev_alloc(e, &c.core, (size_t)c.n_groups * GE)) return e->err_code;
+  size_t n_cells = (size_t)(ring + 2) * c.n_blocks;
+  if (dev_alloc(e, &c.core, c.n_slots)) return e->err_code;
   if (dev_alloc(e, &c.cell_state, n_cells)) return e->err_code;
   if (dev_alloc(e, &c.pool, (size_t)c.n_pages * PAGE)) return e->err_code;
   if (dev_alloc(e, &c.page_next, c.n_pages)) return e->err_code;
   if (dev_alloc(e, &c.free_ring, c.n_pages)) return e->err_code;
-  if (dev_alloc(e, &c.row_bits, ring / 32)) return e->err_code;
+  if (dev_alloc(e, &c.snap, c.n_blocks)) return e->err_code;
   if (dev_alloc(e, &c.win, 2)) return e->err_code;
   if (dev_alloc(e, &c.acc, 1)) return e->err_code;
   if (dev_alloc(e, &c.part, SIMIAN_PART_SLOTS)) return e->err_code;
-  if (dev_alloc(e, &c.bcache, (size_t)c.n_groups * SIMIAN_BC_ROW)) return e->err_code;
+  if (dev_alloc(e, &c.bcache, (size_t)c.n_blocks * SIMIAN_BC)) return e->err_code;
+  if (dev_alloc(e, &c.bcount, c.n_blocks)) return e->err_code;
   if (dev_alloc(e, &e->d_digest, 2)) return e->err_code;
   if (e->size > 1) {
     // a window in which every local event sends one record to a uniformly chosen
@@ -463,7 +454,7 @@ int setup_layout(simian_engine *e) {
     CK(cudaEventCreate(&e->ev0));
     CK(cudaEventCreate(&e->ev1));
   }
-  k_init<<<1184, 256, 0, e->stream>>>(c, (unsigned long long)n_cells);
+  k_init<<<296, 256, 0, e->stream>>>(c, (uint32_t)n_cells);
   CK(cudaGetLastError());
   e->laid_out = true;
   e->laid_out_initial = e->initial_events;
@@ -509,7 +500,7 @@ int setup(simian_engine *e) {
     }
   }
   e->ops.clear();
-  k_begin<<<1, AUX_THREADS, 0, e->stream>>>(c);
+  k_begin<<<1, NTHREADS, 0, e->stream>>>(c);
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(e->stream));
   e->win_ix = 0;
@@ -592,20 +583,20 @@ double simian_hash_name(const char *str) { // hash.js:21-26
 
 simian_engine *simian_create(const char *simName, double startTime, double endTime,
                              double minDelay, int rank, int size, int device) {
+  if (size < 1 || rank < 0 || rank >= size) {
+    g_create_error = "bad rank/size";
+    return nullptr;
+  }
+  if (size > SIMIAN_MAX_RANKS) { // peer tables of the engine (the GPUs of one NVLink domain)
+    g_create_error = "size exceeds SIMIAN_MAX_RANKS (16): one engine per GPU of one box";
+    return nullptr;
+  }
   int ndev = 0;
   cudaError_t ce = cudaGetDeviceCount(&ndev);
   if (ce != cudaSuccess || ndev == 0) {
     g_create_error = std::string("no CUDA device (") +
                      (ce == cudaSuccess ? "device count 0" : cudaGetErrorString(ce)) +
                      "): simian-b200 has no CPU fallback";
-    return nullptr;
-  }
-  if (size < 1 || rank < 0 || rank >= size) {
-    g_create_error = "bad rank/size";
-    return nullptr;
-  }
-  if (size > SIMIAN_MAX_RANKS) { // peer tables of the engine (GPUs of one NVLink domain)
-    g_create_error = "size exceeds SIMIAN_MAX_RANKS (16): one engine per GPU of one box";
     return nullptr;
   }
   simian_engine *e = new simian_engine();
@@ -662,10 +653,7 @@ int simian_set_option(simian_engine *e, const char *key, double v) {
   else if (k == "launch_batch") e->launch_batch = v < 1 ? 1 : (int)v;
   else if (k == "tie_check") e->tie_check = v != 0;
   else if (k == "force_sequential") e->force_sequential = v != 0;
-  else if (k == "block_entities") { // entities per CTA of the window kernel: 64 per warp
-    int w = (int)((v + GE - 1) / GE);
-    e->wpc = w < 1 ? 1 : (w > SIMIAN_WPC_MAX ? SIMIAN_WPC_MAX : w);
-  }
+  else if (k == "block_entities") e->epb_override = (uint32_t)v;
   else if (k == "pdl") e->pdl = v != 0;
   else return e->fail(SIMIAN_ERR_BAD_ARGUMENT, "unknown option " + k);
   return 0;
@@ -843,21 +831,31 @@ int simian_sched_events(simian_engine *e, const simian_event_t *ev, uint64_t n) 
   if (!e->copy_stream) CK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
   const uint64_t chunk = 1ull << 20; // records (32 MB)
   std::vector<cudaEvent_t> evs;
-  for (uint64_t off = 0; off < n; off += chunk) {
+  cudaError_t ce = cudaSuccess;
+  const char *what = "";
+#define TRY(call) if (ce == cudaSuccess) { ce = (call); what = #call; }
+  for (uint64_t off = 0; off < n && ce == cudaSuccess && !e->err_code; off += chunk) {
     uint64_t m = n - off < chunk ? n - off : chunk;
-    CK(cudaMemcpyAsync(op.d_recs + off, ev + off, m * sizeof(simian_event_t),
-                       cudaMemcpyHostToDevice, e->copy_stream));
+    TRY(cudaMemcpyAsync(op.d_recs + off, ev + off, m * sizeof(simian_event_t),
+                        cudaMemcpyHostToDevice, e->copy_stream));
     if (early) {
-      cudaEvent_t done;
-      CK(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
-      CK(cudaEventRecord(done, e->copy_stream));
-      CK(cudaStreamWaitEvent(e->stream, done, 0));
-      evs.push_back(done);
-      if (ingest_records(e, op.d_recs + off, m, e->stream)) return e->err_code;
+      cudaEvent_t done = nullptr;
+      TRY(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+      if (done) evs.push_back(done);
+      TRY(cudaEventRecord(done, e->copy_stream));
+      TRY(cudaStreamWaitEvent(e->stream, done, 0));
+      if (ce == cudaSuccess) ingest_records(e, op.d_recs + off, m, e->stream);
     }
   }
-  CK(cudaStreamSynchronize(e->copy_stream)); // the host buffer is only borrowed
+  TRY(cudaStreamSynchronize(e->copy_stream)); // the host buffer is only borrowed
+#undef TRY
   for (cudaEvent_t d : evs) cudaEventDestroy(d);
+  if (ce != cudaSuccess || e->err_code) { // nothing leaks on a failed call
+    cudaStreamSynchronize(e->stream);
+    if (!cache_give(e->device, op.d_bytes, op.d_recs)) cudaFree(op.d_recs);
+    if (ce != cudaSuccess) return e->fail(SIMIAN_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(ce));
+    return e->err_code;
+  }
   op.ingested = early;
   e->ops.push_back(op);
   return 0;
@@ -887,6 +885,17 @@ int simian_setup(simian_engine *e) {
 }
 
 namespace {
+// this engine's share of the run nonce (the nonce is the sum over all ranks)
+void ensure_salt(simian_engine *e) {
+  if (e->salt) return;
+  std::random_device rd;
+  e->salt = (((uint64_t)rd() << 32) ^ (uint64_t)rd() ^
+             (uint64_t)std::chrono::steady_clock::now().time_since_epoch().count())
+            << 24; // the low 24 bits stay free for the window number
+  if (!e->salt) e->salt = 1ull << 24;
+  e->cfg.run_nonce += e->salt;
+}
+
 struct IpcBlob { // what one rank publishes to its peers
   cudaIpcMemHandle_t outbox, slab;
   uint64_t cap;
@@ -909,14 +918,7 @@ int simian_ipc_export(simian_engine *e, void *blob, uint64_t blobBytes, uint64_t
   // k_init has zeroed the exchange slots before any peer can write into them
   CK(cudaStreamSynchronize(e->stream));
   b.cap = e->cfg.outbox_cap;
-  if (!e->salt) {
-    std::random_device rd;
-    e->salt = (((uint64_t)rd() << 32) ^ (uint64_t)rd() ^
-               (uint64_t)std::chrono::steady_clock::now().time_since_epoch().count())
-              << 24; // the low 24 bits stay free for the window number
-    if (!e->salt) e->salt = 1ull << 24;
-    e->cfg.run_nonce += e->salt;
-  }
+  ensure_salt(e);
   b.salt = e->salt;
   b.rank = e->rank;
   b.size = e->size;
@@ -948,8 +950,33 @@ int simian_ipc_import(simian_engine *e, int peerRank, const void *blob, uint64_t
   return 0;
 }
 
+// Peer connection inside ONE process (all ranks of a world on one device, or on
+// devices with peer access enabled by the caller): the same wiring as
+// simian_ipc_export / simian_ipc_import, with plain device pointers.
+int simian_connect_local(simian_engine *e, int peerRank, simian_engine *peer) {
+  if (!peer || peerRank < 0 || peerRank >= e->size || peerRank >= SIMIAN_MAX_RANKS ||
+      peerRank == e->rank || peer->rank != peerRank || peer->size != e->size)
+    return e->fail(SIMIAN_ERR_BAD_ARGUMENT, "bad local peer");
+  int rc = simian_setup(e);
+  if (rc) return rc;
+  if (simian_setup(peer)) return e->fail(SIMIAN_ERR_BAD_ARGUMENT, "peer engine failed to set up");
+  if (peer->cfg.outbox_cap != e->cfg.outbox_cap)
+    return e->fail(SIMIAN_ERR_BAD_ARGUMENT, "peer outbox does not match this world");
+  CK(cudaStreamSynchronize(e->stream)); // k_init has zeroed the exchange slots
+  ensure_salt(e);
+  ensure_salt(peer);
+  if (!e->peer_seen[peerRank]) {
+    e->cfg.run_nonce += peer->salt;
+    e->peer_seen[peerRank] = true;
+  }
+  e->cfg.peer_xch[peerRank] = peer->cfg.xch;
+  e->cfg.peer_outbox[peerRank] = peer->cfg.outbox;
+  e->cfg.peer_count[peerRank] = peer->cfg.outbox_count;
+  return 0;
+}
+
 int simian_window_publish_min(simian_engine *e) {
-  k_local_min<<<1, AUX_THREADS, 0, e->stream>>>(e->cfg, e->win_ix, 1);
+  k_local_min<<<1, NTHREADS, e->smem_bytes, e->stream>>>(e->cfg, e->win_ix, 1);
   CK(cudaGetLastError());
   e->launches++;
   return 0;
@@ -971,7 +998,7 @@ int simian_minvec_ptr(simian_engine *e, void **devMinVec) {
 }
 
 int simian_window_advance_async(simian_engine *e, int minFromPeers) {
-  k_advance<<<1, AUX_THREADS, 0, e->stream>>>(e->cfg, e->win_ix, minFromPeers);
+  k_advance<<<1, NTHREADS, 0, e->stream>>>(e->cfg, e->win_ix, minFromPeers);
   CK(cudaGetLastError());
   e->launches++;
   e->win_ix++;
@@ -997,15 +1024,16 @@ int simian_run_begin(simian_engine *e) {
 }
 
 int simian_window_process(simian_engine *e) {
-  k_window<<<e->grid, 32 * e->wpc, e->smem_bytes, e->stream>>>(e->cfg, e->win_ix, e->size == 1);
+  k_window<<<e->cfg.n_blocks, NTHREADS, e->smem_bytes, e->stream>>>(e->cfg, e->win_ix,
+                                                                  e->size == 1);
   CK(cudaGetLastError());
   e->launches++;
   return 0;
 }
 
 int simian_window_process_lbts(simian_engine *e, int publish) {
-  k_window<<<e->grid, 32 * e->wpc, e->smem_bytes, e->stream>>>(e->cfg, e->win_ix,
-                                                               publish ? 3 : 2);
+  k_window<<<e->cfg.n_blocks, NTHREADS, e->smem_bytes, e->stream>>>(e->cfg, e->win_ix,
+                                                                  publish ? 3 : 2);
   CK(cudaGetLastError());
   e->launches++;
   return 0;
@@ -1038,7 +1066,7 @@ int simian_window_ingest(simian_engine *e, const void *devRecords, uint64_t n) {
 }
 
 int simian_window_local_min(simian_engine *e, void **devMinVec) {
-  k_local_min<<<1, AUX_THREADS, 0, e->stream>>>(e->cfg, e->win_ix, 0);
+  k_local_min<<<1, NTHREADS, e->smem_bytes, e->stream>>>(e->cfg, e->win_ix, 0);
   CK(cudaGetLastError());
   e->launches++;
   if (devMinVec) *devMinVec = (void *)e->cfg.acc->minvec;
@@ -1046,7 +1074,7 @@ int simian_window_local_min(simian_engine *e, void **devMinVec) {
 }
 
 int simian_window_advance(simian_engine *e, int *done) {
-  k_advance<<<1, AUX_THREADS, 0, e->stream>>>(e->cfg, e->win_ix, 0);
+  k_advance<<<1, NTHREADS, 0, e->stream>>>(e->cfg, e->win_ix, 0);
   CK(cudaGetLastError());
   e->launches++;
   e->win_ix++;
@@ -1075,8 +1103,8 @@ int simian_run(simian_engine *e, simian_stats *out) {
         // programmatic dependent launch: the CTAs of window k+1 become resident
         // while the last wave of window k drains (they wait inside the kernel)
         cudaLaunchConfig_t lc = {};
-        lc.gridDim = dim3(e->grid);
-        lc.blockDim = dim3(32 * e->wpc);
+        lc.gridDim = dim3(e->cfg.n_blocks);
+        lc.blockDim = dim3(NTHREADS);
         lc.dynamicSmemBytes = e->smem_bytes;
         lc.stream = e->stream;
         cudaLaunchAttribute at[1];
@@ -1086,7 +1114,7 @@ int simian_run(simian_engine *e, simian_stats *out) {
         lc.numAttrs = 1;
         CK(cudaLaunchKernelEx(&lc, k_window, e->cfg, e->win_ix, 1));
       } else {
-        k_window<<<e->grid, 32 * e->wpc, e->smem_bytes, e->stream>>>(e->cfg, e->win_ix, 1);
+        k_window<<<e->cfg.n_blocks, NTHREADS, e->smem_bytes, e->stream>>>(e->cfg, e->win_ix, 1);
       }
       e->win_ix++;
       e->launches++;

@@ -1,52 +1,39 @@
 // kernels.cuh -- hand-written sm_100a kernels of the simian-b200 window loop.
 //
 // One lookahead window of the reference (SimianJS/simian.js:119-148) is ONE
-// launch of k_window.  An entity GROUP (64 consecutive local entities) is owned
-// by ONE WARP; the warps of a CTA never wait for each other between the first
-// and the last instruction of a window (no block barrier on the hot path):
-//   K2  dequeue: the pages of the group's calendar cells in the window's rows
-//       are bulk-copied into the warp's shared-memory slots (cp.async.bulk +
-//       mbarrier, one copy per page)                 (eventQ.pop, eventQ.js:53-92)
-//   K3  the due records are counting-sorted by entity inside the warp
-//       (histogram + scan -> contiguous per-entity segments), ranked under
-//       (time, handler, src, seq) and their handlers run, one lane per event
-//                                                     (simian.js:124-133)
+// launch of k_window:
+//   K2  coalesced dequeue of every event below the window bound from the
+//       block's calendar cells: the records of the window's pages are copied
+//       into shared-memory slots with cp.async in one round trip and the due
+//       ones linked per entity                      (eventQ.pop, eventQ.js:53-92)
+//   K3  handlers of all entities in parallel, each entity's events in
+//       (time, handler, src, seq) order               (simian.js:124-133)
 //   K4  emit: lock-free paged append of 32-B records into the destination
 //       cell, or into the per-peer outbox             (entity.js:47-67, eventQ.push)
-//   K1  LBTS: warp min-reduction of leftover + emitted times, one result-less
-//       atomic per CTA, last CTA computes the next window (simian.js:120,143-147)
-// Windows whose records overflow the warp's slots (bursts) are processed in
-// several passes over entity sub-ranges (slow_passes).
+//   K1  LBTS: block min-reduction of leftover + emitted times, one atomicMin
+//       per CTA, last CTA computes the next window    (simian.js:120,143-147)
+// The common window is a straight line of phases (collect_all, link_due,
+// process_pass); windows whose records overflow the CTA's 1024 slots (bursts)
+// go through ONE out-of-line function (filtered_passes / partition_burst).
 // Compiled with -fmad=false: include/simian_spec.h must see no FMA contraction.
 #pragma once
 #include "device_types.cuh"
 
-#define GE SIMIAN_GE
-#define GE_SHIFT SIMIAN_GE_SHIFT
+#define EPB SIMIAN_EPB
+#define NTHREADS SIMIAN_THREADS
 #define PAGE SIMIAN_PAGE
-#define NSLOT SIMIAN_NSLOT
+#define NREFS SIMIAN_REFS
 #define PGMAX SIMIAN_PGMAX
-#define NROUND ((NSLOT + 31) / 32)
-#define FULL 0xffffffffu
-static_assert(NSLOT <= 255, "slot indices and arrival counts are kept in bytes");
-static_assert(NROUND <= 8, "per-lane ranks / slots are packed 8 bits each into 64 bits");
-static_assert(PAGE <= 31 && (PAGE & (PAGE - 1)) == 0, "page record count: 5 bits of pg_cnt");
-static_assert(SIMIAN_MAX_CELLS <= 96, "ring span");
-
-// page-list entry flags (pg_cnt)
-#define PG_COUNT(x) ((uint32_t)(x) & 31u)
-#define PG_LINKED 0x4000u // the page's page_next entry is set (reset it when the page is freed)
 #define PG_FREE_FLAG 0x8000u
 
 // per-phase SM-cycle accounting of k_window (diagnostic builds only)
 #ifdef SIMIAN_PROFILE_PHASES
 #define PHASE(k)                                                                 \
   do {                                                                           \
-    __syncwarp();                                                                \
-    if ((threadIdx.x & 31) == 0) {                                               \
+    if (threadIdx.x == 0) {                                                      \
       long long _t = clock64();                                                  \
-      atomicAdd(&c.acc->phase_cycles[k], (unsigned long long)(_t - ws.t_last));  \
-      ws.t_last = _t;                                                            \
+      atomicAdd(&c.acc->phase_cycles[k], (unsigned long long)(_t - sh.t_last));  \
+      sh.t_last = _t;                                                            \
     }                                                                            \
   } while (0)
 #else
@@ -113,6 +100,14 @@ __device__ __forceinline__ void ld_rec_head(const simian_event_t *p, unsigned lo
                                             unsigned long long &q1) {
   asm volatile("ld.global.v2.u64 {%0,%1}, [%2];" : "=l"(q0), "=l"(q1) : "l"(p));
 }
+// 16 bytes global -> shared without passing through registers (LDGSTS)
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *src) {
+  uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.wait_all;" ::: "memory");
+}
 // L2-coherent loads (bypass L1) for data other CTAs wrote in this launch
 __device__ __forceinline__ uint32_t ld_cg(const uint32_t *p) {
   uint32_t v;
@@ -123,51 +118,6 @@ __device__ __forceinline__ unsigned long long ld_cg64(const unsigned long long *
   unsigned long long v;
   asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(v) : "l"(p));
   return v;
-}
-
-// ---- bulk asynchronous copies (TMA unit, no tensor map) + mbarrier ---------
-// global -> shared, 16-byte granules, completion counted in bytes on an
-// mbarrier in shared memory (SASS: UBLKCP + SYNCS).
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) {
-  return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t arrivals) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(arrivals)
-               : "memory");
-  // make the initialised barrier visible to the async proxy (the copy engine)
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-// one arrival that also announces `bytes` of bulk-copy traffic still to land
-__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
-               "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, uint32_t bytes,
-                                         unsigned long long *bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
-          "r"(smem_u32(smem_dst)),
-      "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
-      : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(unsigned long long *bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-      "selp.u32 %0, 1, 0, p;\n"
-      "}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
 }
 
 __device__ __forceinline__ long long tb_of(const DevCfg &c, double t) {
@@ -223,49 +173,27 @@ __device__ __forceinline__ uint32_t gid_of_slot(const DevCfg &c, uint32_t slot, 
   return cl.first_id + (c.size == 1 ? j : j * (uint32_t)c.size + cl.rank_off);
 }
 
-// 64-bit min / max over the warp with redux.sync on the two halves
-__device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v) {
-  uint32_t hi = (uint32_t)(v >> 32), lo = (uint32_t)v;
-  uint32_t mh = __reduce_min_sync(FULL, hi);
-  uint32_t ml = __reduce_min_sync(FULL, hi == mh ? lo : 0xFFFFFFFFu);
-  return ((unsigned long long)mh << 32) | ml;
-}
-__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v) {
-  uint32_t hi = (uint32_t)(v >> 32), lo = (uint32_t)v;
-  uint32_t mh = __reduce_max_sync(FULL, hi);
-  uint32_t ml = __reduce_max_sync(FULL, hi == mh ? lo : 0u);
-  return ((unsigned long long)mh << 32) | ml;
-}
-
 // ------------------------------------------------------ paged cell append --
 
-// In shared memory: one per WARP in k_window (the group's page cache, bulk
-// copied from bcache[g]), one per CTA in the other appending kernels (no cache).
-struct __align__(16) AppendCtx {
-  // [0, SIMIAN_BC): the group's free pages, a stack popped from the top with a
-  // shared-memory atomic; [SIMIAN_BC]: the stack height as stored in HBM
-  uint32_t pgc[SIMIAN_BC_ROW];
+struct AppendCtx { // per-CTA, in shared memory
   uint32_t far_appends, page_allocs;
+  // the entity block's own free pages (k_window only; pgc_have == 0 elsewhere):
+  // a stack, popped from the top with a shared-memory atomic
   uint32_t pgc_take, pgc_have;
+  uint32_t pgc[SIMIAN_BC];
 };
 
 // head word of an empty cell: no page, "full" so the first append installs one
 #define CELL_EMPTY (((unsigned long long)SIMIAN_NONE << 32) | (unsigned long long)PAGE)
 // Bit 31 of the head word's count half (and of a page_next entry): the page has
-// an OLDER page behind it.
+// an OLDER page behind it.  Cells of one page -- almost all of them -- are then
+// listed without reading page_next at all; claims on a chained cell miss the
+// `count < PAGE` fast path and are serviced by cell_append_slow.
 #define CELL_OLDER 0x80000000u
 #define CELL_COUNT(lo32) ((uint32_t)(lo32) & 0x7FFFFFFFu)
 
 __device__ __forceinline__ void append_ctx_init(AppendCtx &ax) {
   if (threadIdx.x == 0) ax.far_appends = ax.page_allocs = ax.pgc_take = ax.pgc_have = 0;
-}
-
-// Free-page invariant for a page whose contents are unknown (never used since
-// the pool was allocated, or a far-row page whose records lie in the future).
-__device__ __forceinline__ void scrub_page(const DevCfg &c, uint32_t p) {
-  unsigned long long *w = reinterpret_cast<unsigned long long *>(c.pool + (size_t)p * PAGE);
-#pragma unroll 4
-  for (uint32_t s = 0; s < (uint32_t)PAGE; s++) w[4 * s] = SIMIAN_TIME_DEAD;
 }
 
 // Pop a page from the free ring.  Pages pushed during a launch become
@@ -274,7 +202,7 @@ __device__ __forceinline__ void scrub_page(const DevCfg &c, uint32_t p) {
 __device__ __forceinline__ uint32_t page_get(const DevCfg &c, AppendCtx &ax,
                                              unsigned long long alloc_limit) {
   atomicAdd(&ax.page_allocs, 1u);
-  if (ax.pgc_have) { // group cache first: a shared-memory atomic, no L2 round trip
+  if (ax.pgc_have) { // block cache first: a shared-memory atomic, no L2 round trip
     uint32_t k = atomicAdd(&ax.pgc_take, 1u);
     if (k < ax.pgc_have) return ax.pgc[ax.pgc_have - 1u - k];
   }
@@ -283,17 +211,10 @@ __device__ __forceinline__ uint32_t page_get(const DevCfg &c, AppendCtx &ax,
     set_error(c, SIMIAN_ERR_POOL_EXHAUSTED);
     return SIMIAN_NONE;
   }
-  const uint32_t p = c.free_ring[i % c.n_pages];
-  if (i < c.n_pages) { // first lap of the ring: a page nobody has used yet
-    scrub_page(c, p);
-    __threadfence(); // dead times are visible before the page is linked into a cell
-  }
-  return p;
+  return c.free_ring[i % c.n_pages];
 }
 
-// Return a page to the ring.  `linked`: its page_next entry was set.
-__device__ __forceinline__ void page_free(const DevCfg &c, uint32_t p, bool linked) {
-  if (linked) c.page_next[p] = SIMIAN_NONE;
+__device__ __forceinline__ void page_free(const DevCfg &c, uint32_t p) {
   unsigned long long pos = atomicAdd(&c.acc->free_tail, 1ull);
   c.free_ring[pos % c.n_pages] = p;
 }
@@ -310,7 +231,7 @@ __device__ __forceinline__ void append_ctx_flush(const DevCfg &c, AppendCtx &ax)
 
 // sum a per-thread count of appended records into acc->appended (one atomic per warp)
 __device__ __forceinline__ void appended_flush(const DevCfg &c, uint32_t n) {
-  n = __reduce_add_sync(FULL, n);
+  for (int o = 16; o; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
   if ((threadIdx.x & 31) == 0 && n) atomicAdd(&c.acc->appended, (unsigned long long)n);
 }
 
@@ -329,30 +250,18 @@ __device__ __noinline__ void cell_append_slow(const DevCfg &c, AppendCtx &ax,
 #pragma unroll 1
   for (;;) {
     const uint32_t p = (uint32_t)(old >> 32), i = CELL_COUNT(old);
-    if (i < (uint32_t)PAGE) {
+    if (i < (uint32_t)PAGE) { // (a chained cell: the fast path does not take these)
       st_rec_2x16(c.pool + ((size_t)p * PAGE + i), q0, q1, q2, q3);
       return;
     }
     if (i == (uint32_t)PAGE) { // first overflow: install the next page
       uint32_t np = page_get(c, ax, alloc_limit);
       if (np == SIMIAN_NONE) return; // sticky error set
-      if (p != SIMIAN_NONE) {
-        // the link carries the old head's own "older page" bit.  A reader that
-        // sees the new head word before this store (no fence here) finds NONE
-        // -- page_next of a free page -- and re-reads (list_walk).
-        c.page_next[np] = p | ((uint32_t)old & CELL_OLDER);
-      } else {
-        // the cell's first page: mark its ring row as occupied (LBTS search)
-        const uint32_t row = (uint32_t)((unsigned long long)(hp - c.cell_state) % c.rows);
-        if (row < c.ring) {
-          uint32_t *w = c.row_bits + (row >> 5);
-          const uint32_t bit = 1u << (row & 31u);
-          if (!(ld_cg(w) & bit)) atomicOr(w, bit);
-        }
-      }
+      // the link carries the old head's own "older page" bit
+      c.page_next[np] = p == SIMIAN_NONE ? SIMIAN_NONE : (p | ((uint32_t)old & CELL_OLDER));
       st_rec_2x16(c.pool + (size_t)np * PAGE, q0, q1, q2, q3); // slot 0 is ours
-      // no fence: appenders of this launch only write into the page; records
-      // are read after a launch boundary or after the ticket fence
+      // no fence: appenders of this launch only write into the page; chains
+      // and records are read after a launch boundary or after the ticket fence
       atomicExch(hp, ((unsigned long long)np << 32) |
                          (unsigned long long)(p == SIMIAN_NONE ? 0u : CELL_OLDER) | 1ull);
       return;
@@ -372,35 +281,30 @@ __device__ __noinline__ void cell_append_slow(const DevCfg &c, AppendCtx &ax,
 }
 
 __device__ __forceinline__ void cell_append(const DevCfg &c, AppendCtx &ax,
-                                            unsigned long long alloc_limit,
-                                            unsigned long long *hp, const RecBits &r) {
+                                            unsigned long long alloc_limit, uint32_t cell,
+                                            const RecBits &r) {
+  unsigned long long *hp = c.cell_state + cell;
   unsigned long long old = atomicAdd(hp, 1ull);
-  if (CELL_COUNT(old) < (uint32_t)PAGE)
-    st_rec_2x16(c.pool + ((size_t)(uint32_t)(old >> 32) * PAGE + CELL_COUNT(old)), r.q0, r.q1,
-                r.q2, r.q3);
+  if ((uint32_t)old < (uint32_t)PAGE)
+    st_rec(c.pool + ((size_t)(uint32_t)(old >> 32) * PAGE + (uint32_t)old), r);
   else
     cell_append_slow(c, ax, alloc_limit, hp, old, r.q0, r.q1, r.q2, r.q3);
 }
 
-// calendar cell (index into cell_state) of a record whose dst is a LOCAL SLOT;
-// SIMIAN_NONE: error set
+// calendar cell of a record whose dst is a LOCAL SLOT (SIMIAN_NONE: error set)
 __device__ __forceinline__ uint32_t cell_of_local(const DevCfg &c, AppendCtx &ax,
                                                   long long tb_clean, uint32_t far_row,
                                                   double time, uint32_t dst_slot) {
-  const uint32_t g = dst_slot >> GE_SHIFT;
-  if (g >= c.n_groups) { // an id the model made up (reference: throws at dispatch)
-    set_error(c, SIMIAN_ERR_UNKNOWN_NAME);
-    return SIMIAN_NONE;
-  }
+  uint32_t b = (uint32_t)__umul64hi((unsigned long long)dst_slot, c.epb_inv); // dst_slot / epb
   long long tb = tb_of(c, time);
   if (tb < tb_clean) {
     set_error(c, SIMIAN_ERR_OUT_OF_ORDER);
     return SIMIAN_NONE;
   }
-  if (tb - tb_clean < (long long)c.ring) return g * c.rows + (uint32_t)(tb & (long long)c.ring_mask);
+  if (tb - tb_clean < (long long)c.ring) return (uint32_t)(tb & (long long)c.ring_mask) * c.n_blocks + b;
   atomicMin(&c.acc->far_min[far_row], simian_time_key(time));
   atomicAdd(&ax.far_appends, 1u);
-  return g * c.rows + c.ring + far_row;
+  return (c.ring + far_row) * c.n_blocks + b;
 }
 
 // route a record whose dst is a LOCAL SLOT into the calendar or the far row
@@ -408,12 +312,12 @@ __device__ __forceinline__ void append_local(const DevCfg &c, AppendCtx &ax, lon
                                              uint32_t far_row, unsigned long long alloc_limit,
                                              const RecBits &r) {
   uint32_t cell = cell_of_local(c, ax, tb_clean, far_row, r.time(), r.dst());
-  if (cell != SIMIAN_NONE) cell_append(c, ax, alloc_limit, c.cell_state + cell, r);
+  if (cell != SIMIAN_NONE) cell_append(c, ax, alloc_limit, cell, r);
 }
 
 // ------------------------------------------------------------ init / load --
 
-__global__ void k_init(const __grid_constant__ DevCfg c, unsigned long long n_cells) {
+__global__ void k_init(const __grid_constant__ DevCfg c, uint32_t n_cells) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t j = i; j < c.n_pages; j += stride) {
@@ -421,6 +325,7 @@ __global__ void k_init(const __grid_constant__ DevCfg c, unsigned long long n_ce
     c.page_next[j] = SIMIAN_NONE;
   }
   for (size_t j = i; j < n_cells; j += stride) c.cell_state[j] = CELL_EMPTY;
+  for (size_t j = i; j < c.n_blocks; j += stride) c.snap[j] = CELL_EMPTY;
   for (size_t j = i; j < SIMIAN_PART_SLOTS; j += stride) {
     BlockPart z;
     z.min_key = SIMIAN_KEY_NONE;
@@ -429,37 +334,25 @@ __global__ void k_init(const __grid_constant__ DevCfg c, unsigned long long n_ce
         z.page_allocs = 0;
     c.part[j] = z;
   }
-  // group page caches start with SIMIAN_BC_FILL pages each when the pool allows
+  // block page caches start with SIMIAN_BC_FILL pages each when the pool allows
   const uint32_t fill =
-      ((unsigned long long)c.n_groups * SIMIAN_BC_FILL * 2ull <= c.n_pages) ? SIMIAN_BC_FILL : 0u;
-  for (size_t j = i; j < (size_t)c.n_groups * SIMIAN_BC_ROW; j += stride) {
-    uint32_t g = (uint32_t)(j / SIMIAN_BC_ROW), k = (uint32_t)(j % SIMIAN_BC_ROW);
-    c.bcache[j] = k < fill ? g * fill + k : (k == SIMIAN_BC ? fill : SIMIAN_NONE);
+      ((unsigned long long)c.n_blocks * SIMIAN_BC_FILL * 2ull <= c.n_pages) ? SIMIAN_BC_FILL : 0u;
+  for (size_t j = i; j < (size_t)c.n_blocks * SIMIAN_BC; j += stride) {
+    uint32_t bb = (uint32_t)(j / SIMIAN_BC), k = (uint32_t)(j % SIMIAN_BC);
+    c.bcache[j] = k < fill ? bb * fill + k : SIMIAN_NONE;
+    if (k == 0) c.bcount[bb] = fill;
   }
-  // Free-page invariant: pages the caches start with get dead time words here;
-  // every other page is scrubbed when it leaves the ring for the first time
-  // (page_get, cache refill), so an engine pays for the pages it uses, not for
-  // the pool it reserved.
-  {
-    RecBits dead;
-    dead.q0 = SIMIAN_TIME_DEAD;
-    dead.q1 = 0xFFFFFFFFFFFFFFFFull;
-    dead.q2 = dead.q3 = 0;
-    const size_t nrec = (size_t)c.n_groups * fill * PAGE;
-    for (size_t j = i; j < nrec; j += stride) st_rec(c.pool + j, dead);
-  }
-  for (size_t j = i; j < (size_t)c.n_groups * GE; j += stride) {
+  for (size_t j = i; j < c.n_slots; j += stride) {
     EntityCore z;
     z.count = 0;
     z.hash = 0;
     c.core[j] = z;
   }
-  for (size_t j = i; j < c.ring / 32; j += stride) c.row_bits[j] = 0;
   if (i == 0) {
     DevAcc *a = c.acc;
     a->min_key = SIMIAN_KEY_NONE;
     a->far_min[0] = a->far_min[1] = SIMIAN_KEY_NONE;
-    a->alloc_head = (unsigned long long)c.n_groups * fill; // ring slots [0, alloc_head) went to the caches
+    a->alloc_head = (unsigned long long)c.n_blocks * fill; // ring slots [0, alloc_head) went to the caches
     a->free_tail = c.n_pages;
     a->committed = a->emitted = a->dropped = a->ties = a->dist_ties = 0;
     a->max_key = 0;
@@ -468,7 +361,6 @@ __global__ void k_init(const __grid_constant__ DevCfg c, unsigned long long n_ce
     a->ticket = 0;
     a->error = 0;
     a->window_index = 0;
-    a->loop_arrive = 0;
     a->minvec[0] = a->minvec[1] = 0;
     for (int q = 0; q < 12; q++) a->phase_cycles[q] = 0;
     WinState w;
@@ -567,7 +459,10 @@ __global__ void k_ingest(const __grid_constant__ DevCfg c, const simian_event_t 
   }
   appended_flush(c, napp);
   if (track_min) {
-    mn = warp_min_u64(mn);
+    for (int o = 16; o; o >>= 1) {
+      unsigned long long x = __shfl_xor_sync(0xffffffffu, mn, o);
+      mn = x < mn ? x : mn;
+    }
     if ((threadIdx.x & 31) == 0 && mn != SIMIAN_KEY_NONE) atomicMin(&smin, mn);
     __syncthreads();
     if (threadIdx.x == 0 && smin != SIMIAN_KEY_NONE) atomicMin(&c.acc->min_key, smin);
@@ -625,7 +520,7 @@ __global__ void k_pull(const __grid_constant__ DevCfg c, uint32_t win_ix, uint32
 #pragma unroll
         for (int u = 0; u < 4; u++)
           if (idx + u * stride < n) {
-            if (r[u].dst() >= c.n_slots) {
+            if (r[u].dst() >= c.n_slots) { // a slot this rank does not have
               set_error(c, SIMIAN_ERR_UNKNOWN_NAME);
               continue;
             }
@@ -642,44 +537,57 @@ __global__ void k_pull(const __grid_constant__ DevCfg c, uint32_t win_ix, uint32
 }
 
 // ---------------------------------------------------------- window kernel --
-// (k_construct, which needs the handler context, is defined after DevCtx)
+// (k_construct, which needs the handler context, is defined after it below)
 
-// everything one warp (= one entity group) keeps on chip for a window
-struct __align__(32) WarpShared {
-  simian_event_t slots[NSLOT];  // the window's records; the pure path overwrites slot s
-                                // with the record event s emits (staged, then appended)
-  EntityCore core_s[GE];        // {commit count, trace hash} of the group's entities
-  AppendCtx ax;                 // the group's page cache + append counters
-  unsigned long long xs[NSLOT]; // trace words in commit order, entity after entity
+#define LIST_END 0xFFFFu
+#define EV_PER_THREAD ((NREFS + NTHREADS - 1) / NTHREADS)
+static_assert(EV_PER_THREAD <= 4, "ranks are packed 8 bits each into one register");
+#define RSTACK_MAX 80 // entity sub-ranges a CTA can have pending
+#define NBINS 16      // histogram bins over the block's entities (burst partition)
+
+struct WindowShared {
   WinState W;
-  unsigned long long mbar;      // completion barrier of the bulk copies
-  long long t_last;
-  // the warp's results of this window (K1), updated by lane 0 after warp-level
-  // reductions: no lane keeps accumulators in registers across the phases
-  unsigned long long acc_min, acc_max;
-  uint32_t acc_committed, acc_emitted, acc_dropped, acc_ties, acc_dties, acc_appended;
-  uint32_t cnt[GE];             // due events per entity
-  uint32_t pg_id[PGMAX];        // pages of the group's cells in the window rows (one chunk)
-  uint32_t npg, total;
-  uint16_t pg_cnt[PGMAX];       // records in the page | PG_LINKED | PG_FREE_FLAG
-  uint16_t pg_off[PGMAX];       // records in the pages listed before this one
-  uint16_t base[GE];            // first sorted position of each entity's events
-  uint16_t ent[NSLOT];          // per slot: entity | arrival index << 8 (0xFFFF: not due)
-  uint8_t ord[NSLOT];           // slots grouped by entity (arrival order inside an entity)
-  uint8_t srt[NSLOT];           // slots in commit order: entity after entity, key order inside
+  AppendCtx ax;
+  unsigned long long min_key, max_key, free_base, ring_base;
+  uint32_t committed, emitted, dropped, ties, dties, appended;
+  uint32_t npg, nvalid, nfree, free_pos, total, is_last, found, stack_n, pass_lo, pass_hi, pass_pg_lo,
+      pass_pg_hi;
+  long long scan_j, t_last;
+  // entity sub-ranges still to process: (lo, hi, first page-list index, end page-list index)
+  uint32_t rstack[4 * RSTACK_MAX];
+  // burst partition (a window whose due events overflow the slots): due records
+  // per 1/16th of the block's entities, the parts they are grouped into, and
+  // the scratch pages (listed behind the cells' pages in pg_id) of each part
+  uint32_t hist[NBINS], pfill[NBINS], pcnt[NBINS], plo[NBINS], phi[NBINS], ppage0[NBINS + 1];
+  uint32_t part_of_bin[NBINS];
+  uint32_t nparts, bin_shift;
+  uint32_t head[EPB];              // per local entity: index of its first due event
+  uint32_t pg_id[PGMAX];           // pages of this block's cells in the window rows
+  uint32_t pg_off[PGMAX];          // records in the pages listed before this one
+  uint16_t pg_cnt[PGMAX];
+  uint16_t nxt[NREFS];          // next due event of the same entity
+  unsigned long long xs[NREFS]; // trace words, stored in commit order along the entity list
+  EntityCore core_s[EPB];       // {commit count, trace hash} of the entities with due events
+  // due events: the 32-byte records themselves, as two 16-byte halves (no bank
+  // conflicts).  The thread-per-event path overwrites slot i with the record
+  // event i emits (staged, then appended).
+  ulonglong2 lo[NREFS]; // {time, dst | src << 32}
+  ulonglong2 hi[NREFS]; // {handler | flags << 16 | seq << 32, data}
 };
 
-struct CtaShared { // per CTA: result accumulators + scratch of the advance step
-  unsigned long long min_key, max_key;
-  uint32_t committed, emitted, dropped, ties, dties, appended, far_appends, page_allocs;
-  uint32_t is_last, found;
-  long long scan_j;
-  unsigned long long red[10];
-  WinState nw;
-};
-
-// dynamic shared memory of k_window for wpc warps per CTA
-#define WINDOW_SMEM_BYTES(wpc) (sizeof(CtaShared) + (size_t)(wpc) * sizeof(WarpShared))
+__device__ __forceinline__ RecBits slot_get(const WindowShared &sh, uint32_t i) {
+  ulonglong2 a = sh.lo[i], b = sh.hi[i];
+  RecBits r;
+  r.q0 = a.x;
+  r.q1 = a.y;
+  r.q2 = b.x;
+  r.q3 = b.y;
+  return r;
+}
+__device__ __forceinline__ void slot_put(WindowShared &sh, uint32_t i, const RecBits &r) {
+  sh.lo[i] = make_ulonglong2(r.q0, r.q1);
+  sh.hi[i] = make_ulonglong2(r.q2, r.q3);
+}
 
 // per-thread accumulators of the handler phase
 struct ThreadAcc {
@@ -693,36 +601,6 @@ __device__ __forceinline__ void thread_acc_init(ThreadAcc &ta) {
   ta.committed = ta.emitted = ta.dropped = ta.ties = ta.dties = ta.appended = 0;
 }
 
-// fold warp-level results into the warp's accumulators (call with all lanes;
-// the values are warp-uniform or reduced here; lane 0 writes)
-__device__ __forceinline__ void wacc_min(WarpShared &ws, unsigned long long lane_min) {
-  const unsigned long long mn = warp_min_u64(lane_min);
-  if ((threadIdx.x & 31u) == 0 && mn < ws.acc_min) ws.acc_min = mn;
-}
-__device__ __forceinline__ void wacc_max(WarpShared &ws, unsigned long long lane_max) {
-  const unsigned long long mx = warp_max_u64(lane_max);
-  if ((threadIdx.x & 31u) == 0 && mx > ws.acc_max) ws.acc_max = mx;
-}
-// per-lane ThreadAcc of the per-entity path -> the warp's accumulators
-__device__ __forceinline__ void wacc_thread(WarpShared &ws, const ThreadAcc &ta) {
-  wacc_min(ws, ta.min_key);
-  wacc_max(ws, ta.max_key);
-  uint32_t s0 = __reduce_add_sync(FULL, ta.committed);
-  uint32_t s1 = __reduce_add_sync(FULL, ta.emitted);
-  uint32_t s2 = __reduce_add_sync(FULL, ta.dropped);
-  uint32_t s3 = __reduce_add_sync(FULL, ta.ties);
-  uint32_t s4 = __reduce_add_sync(FULL, ta.dties);
-  uint32_t s5 = __reduce_add_sync(FULL, ta.appended);
-  if ((threadIdx.x & 31u) == 0) {
-    ws.acc_committed += s0;
-    ws.acc_emitted += s1;
-    ws.acc_dropped += s2;
-    ws.acc_ties += s3;
-    ws.acc_dties += s4;
-    ws.acc_appended += s5;
-  }
-}
-
 // what a handler reaches through `self` on the device (see simian_models.h)
 // SEQ: one thread per entity (stateful handlers, same-window self-sends);
 // !SEQ: one thread per event (pure handlers).
@@ -731,10 +609,7 @@ struct DevCtx {
   const DevCfg &c;
   const WinState &W; // window bound / recycle frontier / far row in force
   AppendCtx &ax;
-  // what the handler did, read by the caller afterwards (kept here, by value,
-  // so that no per-thread accumulator struct has its address taken)
-  unsigned long long acc_min; // min time key of what it sent (LBTS candidate)
-  uint32_t acc_emitted, acc_dropped, acc_appended;
+  ThreadAcc &ta;
   const DevClass *cl;
   uint32_t self_gid, self_slot;
   unsigned long long commit_idx, key;
@@ -742,9 +617,10 @@ struct DevCtx {
   double now_;
   uint32_t handler_, src_;
   unsigned long long data_;
-  // !SEQ: where the first locally routed record is staged (a shared-memory
-  // slot) instead of being appended right away; null = append directly
-  simian_event_t *stage;
+  // !SEQ: where the first locally routed record is staged (shared-memory slot
+  // index) instead of being appended right away; SIMIAN_NONE = append directly
+  WindowShared *stage_sh;
+  uint32_t stage;
   // fold the times of LOCALLY routed records into the LBTS candidate (window
   // kernel: yes; constructors: no -- the calendar search finds those, and a
   // candidate that a later window commits would move the window bounds)
@@ -754,9 +630,10 @@ struct DevCtx {
   double pend_time[SEQ ? SIMIAN_SELF_MAX : 1];
   unsigned long long pend_q2[SEQ ? SIMIAN_SELF_MAX : 1], pend_data[SEQ ? SIMIAN_SELF_MAX : 1];
 
-  __device__ __forceinline__ DevCtx(const DevCfg &c_, const WinState &W_, AppendCtx &ax_)
-      : c(c_), W(W_), ax(ax_), acc_min(SIMIAN_KEY_NONE), acc_emitted(0), acc_dropped(0),
-        acc_appended(0), stage(nullptr), local_min(true), npend(0) {}
+  __device__ __forceinline__ DevCtx(const DevCfg &c_, const WinState &W_, AppendCtx &ax_,
+                                    ThreadAcc &ta_)
+      : c(c_), W(W_), ax(ax_), ta(ta_), stage_sh(nullptr), stage(SIMIAN_NONE), local_min(true),
+        npend(0) {}
 
   __device__ __forceinline__ double now() const { return now_; }
   __device__ __forceinline__ uint32_t self_id() const { return self_gid; }
@@ -776,14 +653,12 @@ struct DevCtx {
   __device__ __forceinline__ void put_local(const RecBits &r) {
     if (local_min) {
       unsigned long long tk = simian_time_key(r.time());
-      acc_min = tk < acc_min ? tk : acc_min;
+      ta.min_key = tk < ta.min_key ? tk : ta.min_key;
     }
-    acc_appended++;
-    if (!SEQ && stage) { // K4 is done by the append phase of k_window
-      ulonglong2 *d = reinterpret_cast<ulonglong2 *>(stage);
-      d[0] = make_ulonglong2(r.q0, r.q1);
-      d[1] = make_ulonglong2(r.q2, r.q3);
-      stage = nullptr;
+    ta.appended++;
+    if (!SEQ && stage != SIMIAN_NONE) { // K4 is done by the append phase of k_window
+      slot_put(*stage_sh, stage, r);
+      stage = SIMIAN_NONE;
     } else {
       append_local(c, ax, W.tb_clean, W.far_row, W.alloc_limit, r);
     }
@@ -799,11 +674,11 @@ struct DevCtx {
     }
     double time = now_ + offset; // entity.js:47
     if (time > c.end) {          // entity.js:48
-      acc_dropped++;
+      ta.dropped++;
       return;
     }
     uint32_t seq = simian_emit_seq(commit_idx, k);
-    acc_emitted++;
+    ta.emitted++;
     if (rx == SIMIAN_NULL_ENTITY) { // entity.js:50-51
       if (time < now_) {
         set_error(c, SIMIAN_ERR_OUT_OF_ORDER); // simian.js:124-125 at pop time
@@ -837,7 +712,7 @@ struct DevCtx {
       // the receiver has not seen it when the LBTS candidates are reduced:
       // the sender's candidate covers it (simian.js:143-144)
       unsigned long long tk = simian_time_key(time);
-      acc_min = tk < acc_min ? tk : acc_min;
+      ta.min_key = tk < ta.min_key ? tk : ta.min_key;
       // warp-aggregated claim: one atomic per (warp, destination rank)
       const uint32_t box = W.parity * (uint32_t)c.size + (uint32_t)rank;
       unsigned act = __activemask();
@@ -850,10 +725,7 @@ struct DevCtx {
         set_error(c, SIMIAN_ERR_OUTBOX_FULL);
         return;
       }
-      if (SEQ) // (inside the __noinline__ per-entity function: see st_rec_2x16)
-        st_rec_2x16(c.outbox + ((size_t)box * c.outbox_cap + i), r.q0, r.q1, r.q2, r.q3);
-      else
-        st_rec(c.outbox + ((size_t)box * c.outbox_cap + i), r);
+      st_rec(c.outbox + ((size_t)box * c.outbox_cap + i), r);
     }
   }
 };
@@ -931,7 +803,7 @@ __global__ void k_construct(const __grid_constant__ DevCfg c, int cls, uint32_t 
   thread_acc_init(ta);
   for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < cl.n_local;
        j += gridDim.x * blockDim.x) {
-    DevCtx<false> ctx(c, W, ax);
+    DevCtx<false> ctx(c, W, ax, ta);
     ctx.local_min = false;
     int k;
     ctx.self_slot = cl.slot_base + j;
@@ -945,10 +817,6 @@ __global__ void k_construct(const __grid_constant__ DevCfg c, int cls, uint32_t 
     ctx.src_ = SIMIAN_NULL_ENTITY;
     ctx.data_ = 0;
     run_handler(ctx, fn);
-    ta.emitted += ctx.acc_emitted;
-    ta.dropped += ctx.acc_dropped;
-    ta.appended += ctx.acc_appended;
-    ta.min_key = ctx.acc_min < ta.min_key ? ctx.acc_min : ta.min_key;
   }
   if (ta.emitted) atomicAdd(&c.acc->emitted, (unsigned long long)ta.emitted);
   if (ta.dropped) atomicAdd(&c.acc->dropped, (unsigned long long)ta.dropped);
@@ -957,75 +825,71 @@ __global__ void k_construct(const __grid_constant__ DevCfg c, int cls, uint32_t 
   append_ctx_flush(c, ax);
 }
 
-__device__ __forceinline__ ulonglong2 slot_lo(const WarpShared &ws, uint32_t s) {
-  return reinterpret_cast<const ulonglong2 *>(&ws.slots[s])[0]; // {time, dst | src << 32}
-}
-__device__ __forceinline__ ulonglong2 slot_hi(const WarpShared &ws, uint32_t s) {
-  return reinterpret_cast<const ulonglong2 *>(&ws.slots[s])[1]; // {handler | flags | seq, data}
+// key order (time, handler, src, seq), then the slot index so that identical
+// records are all taken, in a fixed order: a < b
+__device__ __forceinline__ bool key_lt(unsigned long long a1, unsigned long long a2, uint32_t a3,
+                                       uint32_t a4, unsigned long long b1,
+                                       unsigned long long b2, uint32_t b3, uint32_t b4) {
+  if (a1 != b1) return a1 < b1;
+  if (a2 != b2) return a2 < b2;
+  if (a3 != b3) return a3 < b3;
+  return a4 < b4;
 }
 
-// All due events of one entity, in commit order (simian.js:122-134 restricted
-// to one entity; entities never interact inside a window because cross-entity
-// sends carry offset >= minDelay, entity.js:41).  Its calendar events are
-// srt[b .. b+n) (sorted by the rank phase); same-window self-sends are merged
-// in by time.  One thread.
-// `carry` (a hot entity whose window is cut into time slices, split passes):
-// the same-window self-sends still pending and the tie state travel from slice
-// to slice through ws.xs (unused by this path); a pending self-send is
-// committed in the slice its time bin belongs to (bin < bin_hi).
-__device__ __forceinline__ uint32_t time_bin(const WinState &W, double t) {
-  const double x = (t - W.gmin) * (64.0 / (W.hi - W.gmin));
-  return x < 63.0 ? (uint32_t)x : 63u;
-}
-#define CARRY_NPEND 0
-#define CARRY_TIME 1
-#define CARRY_Q2 (1 + SIMIAN_SELF_MAX)
-#define CARRY_DATA (1 + 2 * SIMIAN_SELF_MAX)
-#define CARRY_LAST (1 + 3 * SIMIAN_SELF_MAX) // have_last, last_time, last_q, last_data
-static_assert(CARRY_LAST + 4 <= NSLOT, "carry area lives in ws.xs");
-
-__device__ __noinline__ void process_entity(const DevCfg &c, WarpShared &ws, ThreadAcc &ta,
-                                            uint32_t slot, uint32_t le, uint32_t b, uint32_t n,
-                                            bool carry, uint32_t bin_hi) {
+// All due events of one entity, in order (simian.js:122-134 restricted to one
+// entity; entities never interact inside a window because cross-entity sends
+// carry offset >= minDelay, entity.js:41).  The records are in shared memory.
+__device__ __noinline__ void process_entity(const DevCfg &c, WindowShared &sh, ThreadAcc &ta,
+                                            uint32_t slot, uint32_t first) {
+  uint32_t n = 0;
+  for (uint32_t j = first; j != LIST_END; j = sh.nxt[j]) n++;
   int k;
-  DevCtx<true> ctx(c, ws.W, ws.ax);
+  DevCtx<true> ctx(c, sh.W, sh.ax, ta);
   ctx.self_slot = slot;
   ctx.self_gid = gid_of_slot(c, slot, k);
   ctx.cl = &c.cls[k];
-  EntityCore st = ws.core_s[le];
-  bool have_last = false;
+  EntityCore st = sh.core_s[slot - blockIdx.x * c.epb];
+  unsigned long long p1 = 0, p2 = 0;
+  uint32_t p3 = 0, p4 = 0;
+  bool have_prev = false, have_last = false;
   double last_time = 0;
   unsigned long long last_q = 0, last_data = 0;
-  if (carry) {
-    ctx.npend = (int)ws.xs[CARRY_NPEND];
-    for (int j = 0; j < ctx.npend; j++) {
-      ctx.pend_time[j] = __longlong_as_double((long long)ws.xs[CARRY_TIME + j]);
-      ctx.pend_q2[j] = ws.xs[CARRY_Q2 + j];
-      ctx.pend_data[j] = ws.xs[CARRY_DATA + j];
-    }
-    have_last = ws.xs[CARRY_LAST] != 0;
-    last_time = __longlong_as_double((long long)ws.xs[CARRY_LAST + 1]);
-    last_q = ws.xs[CARRY_LAST + 2];
-    last_data = ws.xs[CARRY_LAST + 3];
-  }
   uint32_t taken = 0;
 #pragma unroll 1
   for (;;) {
-    const bool have_g = taken < n;
-    const uint32_t gs = have_g ? ws.srt[b + taken] : 0u;
-    // earliest pending same-window self-send (of this time slice)
+    // next event of the static group: min key strictly above the previous one
+    bool have_g = false;
+    uint32_t gj = 0;
+    unsigned long long g1 = 0, g2 = 0;
+    uint32_t g3 = 0;
+    if (taken < n) {
+#pragma unroll 1
+      for (uint32_t j = first; j != LIST_END; j = sh.nxt[j]) {
+        const RecBits r = slot_get(sh, j);
+        unsigned long long k1 = simian_time_key(r.time());
+        unsigned long long k2 = ((unsigned long long)r.handler() << 32) | r.src();
+        uint32_t k3 = r.seq();
+        if (have_prev && !key_lt(p1, p2, p3, p4, k1, k2, k3, j)) continue;
+        if (!have_g || key_lt(k1, k2, k3, j, g1, g2, g3, gj)) {
+          gj = j;
+          g1 = k1;
+          g2 = k2;
+          g3 = k3;
+          have_g = true;
+        }
+      }
+    }
+    // earliest pending same-window self-send
     int pj = -1;
-    for (int j = 0; j < ctx.npend; j++) {
-      if (carry && time_bin(ws.W, ctx.pend_time[j]) >= bin_hi) continue;
+    for (int j = 0; j < ctx.npend; j++)
       if (pj < 0 || ctx.pend_time[j] < ctx.pend_time[pj] ||
           (ctx.pend_time[j] == ctx.pend_time[pj] && ctx.pend_q2[j] < ctx.pend_q2[pj]))
         pj = j;
-    }
     double time;
     uint32_t handler, src;
     unsigned long long data;
     if (pj >= 0 &&
-        (!have_g || ctx.pend_time[pj] < __longlong_as_double((long long)slot_lo(ws, gs).x))) {
+        (!have_g || ctx.pend_time[pj] < __longlong_as_double((long long)sh.lo[gj].x))) {
       time = ctx.pend_time[pj];
       handler = (uint32_t)(ctx.pend_q2[pj] & 0xFFFFu);
       src = ctx.self_gid;
@@ -1035,11 +899,16 @@ __device__ __noinline__ void process_entity(const DevCfg &c, WarpShared &ws, Thr
       ctx.pend_q2[pj] = ctx.pend_q2[ctx.npend];
       ctx.pend_data[pj] = ctx.pend_data[ctx.npend];
     } else if (have_g) {
-      const ulonglong2 a = slot_lo(ws, gs), bh = slot_hi(ws, gs);
-      time = __longlong_as_double((long long)a.x);
-      handler = (uint32_t)(bh.x & 0xFFFFull);
-      src = (uint32_t)(a.y >> 32);
-      data = bh.y;
+      const RecBits g = slot_get(sh, gj);
+      time = g.time();
+      handler = g.handler();
+      src = g.src();
+      data = g.data();
+      p1 = g1;
+      p2 = g2;
+      p3 = g3;
+      p4 = gj;
+      have_prev = true;
       taken++;
     } else
       break;
@@ -1072,721 +941,386 @@ __device__ __noinline__ void process_entity(const DevCfg &c, WarpShared &ws, Thr
     run_handler(ctx, fn); // simian.js:129-131
   }
   c.core[slot] = st;
-  ta.emitted += ctx.acc_emitted;
-  ta.dropped += ctx.acc_dropped;
-  ta.appended += ctx.acc_appended;
-  ta.min_key = ctx.acc_min < ta.min_key ? ctx.acc_min : ta.min_key;
-  if (carry) {
-    ws.core_s[le] = st;
-    ws.xs[CARRY_NPEND] = (unsigned long long)ctx.npend;
-    for (int j = 0; j < ctx.npend; j++) {
-      ws.xs[CARRY_TIME + j] = (unsigned long long)__double_as_longlong(ctx.pend_time[j]);
-      ws.xs[CARRY_Q2 + j] = ctx.pend_q2[j];
-      ws.xs[CARRY_DATA + j] = ctx.pend_data[j];
-    }
-    ws.xs[CARRY_LAST] = have_last ? 1ull : 0ull;
-    ws.xs[CARRY_LAST + 1] = (unsigned long long)__double_as_longlong(last_time);
-    ws.xs[CARRY_LAST + 2] = last_q;
-    ws.xs[CARRY_LAST + 3] = last_data;
-  }
 }
 
-// Rank phase, one lane per EVENT: the event in slot s sits at position p of the
-// entity-grouped order; its rank inside its entity's segment under (time,
-// handler, src, seq) gives its commit position q = base + rank (srt[q] = s).
-// STATS (thread-per-event path): tie statistics against its predecessor,
-// and the order-independent part of the trace hash parked at xs[q] so that the
-// chain phase reads the words in commit order.  Returns the rank.
-template <bool STATS>
-__device__ __forceinline__ uint32_t rank_event(const DevCfg &c, WarpShared &ws, uint32_t slot0,
-                                               uint32_t p, uint32_t s, bool &tie, bool &dtie) {
-  const ulonglong2 a = slot_lo(ws, s);
-  const ulonglong2 bh = slot_hi(ws, s);
+// ---- thread-per-event path (pure handlers) --------------------------------
+// Phase A1, one thread per EVENT: rank of the event inside its entity's list
+// under (time, handler, src, seq), tie check against its predecessor, and the
+// order-independent part of the trace hash, which is parked on the rank-th
+// node of the entity's list so that the chain phase reads it in commit order.
+// Returns the rank.
+__device__ __forceinline__ uint32_t rank_event(const DevCfg &c, WindowShared &sh, ThreadAcc &ta,
+                                               uint32_t slot0, uint32_t i) {
+  const ulonglong2 a = sh.lo[i];
   const uint32_t le = (uint32_t)a.y - slot0;
-  const uint32_t n = ws.cnt[le], b = ws.base[le];
   const double tr = __longlong_as_double((long long)a.x);
+  uint32_t rank = 0;
+  const uint32_t first = sh.head[le];
+  const ulonglong2 bh = sh.hi[i];
   // tie-break words of this event: (handler, src) and seq
   const unsigned long long my2 = ((bh.x & 0xFFFFull) << 32) | (a.y >> 32);
   const uint32_t myseq = (uint32_t)(bh.x >> 32);
-  uint32_t rank = 0;
   // tie statistics: is there an equal-time event before this one, and does
   // any of those differ from it in what the handler sees
   bool has_pred = false, any_diff = false;
-  if (n > 1) {
+  // t = the rank-th node of the list: it trails the walk (rank so far <= nodes
+  // visited so far), one step forward for every event found to precede this one
+  uint32_t t = first;
 #pragma unroll 1
-    for (uint32_t j = b; j < b + n; j++) {
-      if (j == p) continue;
-      const uint32_t s2 = ws.ord[j];
-      const ulonglong2 o = slot_lo(ws, s2);
-      const double to = __longlong_as_double((long long)o.x);
-      if (to < tr) {
+  for (uint32_t j = first; j != LIST_END; j = sh.nxt[j]) {
+    if (j == i) continue;
+    const ulonglong2 o = sh.lo[j];
+    const double to = __longlong_as_double((long long)o.x);
+    if (to < tr) {
+      rank++;
+      t = sh.nxt[t];
+    } else if (to == tr) { // a true same-entity time tie: the defined order decides
+      const ulonglong2 oh = sh.hi[j];
+      const unsigned long long o2 = ((oh.x & 0xFFFFull) << 32) | (o.y >> 32);
+      const uint32_t oseq = (uint32_t)(oh.x >> 32);
+      // identical records (same key down to seq) are ordered by their slot: any
+      // order of indistinguishable events commits the same thing
+      const bool before = o2 != my2 ? o2 < my2 : (oseq != myseq ? oseq < myseq : j < i);
+      if (before) {
         rank++;
-      } else if (to == tr) { // a true same-entity time tie: the defined order decides
-        const ulonglong2 oh = slot_hi(ws, s2);
-        const unsigned long long o2 = ((oh.x & 0xFFFFull) << 32) | (o.y >> 32);
-        const uint32_t oseq = (uint32_t)(oh.x >> 32);
-        // identical records (same key down to seq) are ordered by their slot: any
-        // order of indistinguishable events commits the same thing
-        const bool before = o2 != my2 ? o2 < my2 : (oseq != myseq ? oseq < myseq : s2 < s);
-        if (before) {
-          rank++;
-          has_pred = true;
-          any_diff |= (o2 != my2) | (oh.y != bh.y);
-        }
+        t = sh.nxt[t];
+        has_pred = true;
+        any_diff |= (o2 != my2) | (oh.y != bh.y);
       }
     }
   }
-  ws.srt[b + rank] = (uint8_t)s;
-  if (STATS) {
-    if (c.tie_check && has_pred) {
-      tie = true;
-      // distinguishable tie: the LATEST equal-time predecessor differs in (handler,
-      // src) or data.  When every equal-time predecessor is indistinguishable from
-      // this event (bursts of identical schedService calls) the answer is no;
-      // otherwise the latest one is looked for (rare: models with real ties).
-      if (any_diff) {
-        uint32_t ps = SIMIAN_NONE, pseq = 0;
-        unsigned long long p2 = 0, pdata = 0;
+  if (c.tie_check && has_pred) {
+    ta.ties++;
+    // distinguishable tie: the LATEST equal-time predecessor differs in (handler,
+    // src) or data.  When every equal-time predecessor is indistinguishable from
+    // this event (bursts of identical schedService calls) the answer is no;
+    // otherwise the latest one is looked for (rare: models with real ties).
+    if (any_diff) {
+      uint32_t pj = LIST_END, pseq = 0;
+      unsigned long long p2 = 0;
 #pragma unroll 1
-        for (uint32_t j = b; j < b + n; j++) {
-          if (j == p) continue;
-          const uint32_t s2 = ws.ord[j];
-          const ulonglong2 o = slot_lo(ws, s2);
-          if (__longlong_as_double((long long)o.x) != tr) continue;
-          const ulonglong2 oh = slot_hi(ws, s2);
-          const unsigned long long o2 = ((oh.x & 0xFFFFull) << 32) | (o.y >> 32);
-          const uint32_t oseq = (uint32_t)(oh.x >> 32);
-          const bool before = o2 != my2 ? o2 < my2 : (oseq != myseq ? oseq < myseq : s2 < s);
-          // keep the latest predecessor: (key, seq, slot) maximal
-          if (before &&
-              (ps == SIMIAN_NONE || (p2 != o2 ? p2 < o2 : (pseq != oseq ? pseq < oseq : ps < s2)))) {
-            ps = s2;
-            p2 = o2;
-            pseq = oseq;
-            pdata = oh.y;
-          }
+      for (uint32_t j = first; j != LIST_END; j = sh.nxt[j]) {
+        if (j == i || __longlong_as_double((long long)sh.lo[j].x) != tr) continue;
+        const unsigned long long ox = sh.hi[j].x;
+        const unsigned long long o2 = ((ox & 0xFFFFull) << 32) | (sh.lo[j].y >> 32);
+        const uint32_t oseq = (uint32_t)(ox >> 32);
+        const bool before = o2 != my2 ? o2 < my2 : (oseq != myseq ? oseq < myseq : j < i);
+        // keep the latest predecessor: (key, seq, slot) maximal
+        if (before &&
+            (pj == LIST_END || (p2 != o2 ? p2 < o2 : (pseq != oseq ? pseq < oseq : pj < j)))) {
+          pj = j;
+          p2 = o2;
+          pseq = oseq;
         }
-        if (p2 != my2 || pdata != bh.y) dtie = true;
       }
+      if (p2 != my2 || sh.hi[pj].y != bh.y) ta.dties++;
     }
-    ws.xs[b + rank] =
-        simian_trace_event(tr, (uint32_t)(bh.x & 0xFFFFull), (uint32_t)(a.y >> 32), bh.y);
   }
+  sh.xs[t] = simian_trace_event(tr, (uint32_t)(bh.x & 0xFFFFull), (uint32_t)(a.y >> 32), bh.y);
+  unsigned long long tk = simian_time_key(tr);
+  ta.max_key = tk > ta.max_key ? tk : ta.max_key;
+  ta.committed++;
   return rank;
 }
 
-// Handler phase, one lane per EVENT (pure handlers): the handler itself
-// (simian.js:129-131): RNG, log, destination.  Commit index = the entity's
-// committed count + rank.  The record it sends to a local entity replaces the
-// consumed one in slot s.
-// `ecnt` += emitted | dropped << 8 | appended << 16; `mn` = min time key sent.
-__device__ __forceinline__ void run_event(const DevCfg &c, WarpShared &ws, uint32_t slot0,
-                                          uint32_t s, uint32_t rank, uint32_t &ecnt,
-                                          unsigned long long &mn) {
-  const ulonglong2 a = slot_lo(ws, s), bh = slot_hi(ws, s);
-  const uint32_t slot = (uint32_t)a.y;
+// Phase A2, one thread per EVENT: the handler itself (simian.js:129-131): RNG,
+// log, destination.  Commit index = the entity's committed count + rank.  The
+// record it sends to a local entity replaces the consumed one in slot i.
+__device__ __forceinline__ void run_event(const DevCfg &c, WindowShared &sh, ThreadAcc &ta,
+                                          uint32_t slot0, uint32_t i, uint32_t rank) {
+  const RecBits r = slot_get(sh, i);
+  const uint32_t slot = r.dst();
   int k;
-  DevCtx<false> ctx(c, ws.W, ws.ax);
-  ctx.stage = &ws.slots[s];
+  DevCtx<false> ctx(c, sh.W, sh.ax, ta);
+  ctx.stage_sh = &sh;
+  ctx.stage = i;
   ctx.self_slot = slot;
   ctx.self_gid = gid_of_slot(c, slot, k);
   ctx.cl = &c.cls[k];
-  ctx.commit_idx = ws.core_s[slot - slot0].count + rank;
+  ctx.commit_idx = sh.core_s[slot - slot0].count + rank;
   ctx.key = simian_rng_key(c.seed, ctx.self_gid, ctx.commit_idx);
   ctx.n_emit = 0;
-  ctx.now_ = __longlong_as_double((long long)a.x); // simian.js:126
-  ctx.handler_ = (uint32_t)(bh.x & 0xFFFFull);
-  ctx.src_ = (uint32_t)(a.y >> 32);
-  ctx.data_ = bh.y;
-  const uint32_t h = ctx.handler_;
+  ctx.now_ = r.time(); // simian.js:126
+  ctx.handler_ = r.handler();
+  ctx.src_ = r.src();
+  ctx.data_ = r.data();
+  uint32_t h = r.handler();
   run_pure_handler(ctx, h < SIMIAN_MAX_SERVICES ? ctx.cl->fn_of_service[h] : 0);
-  if (ctx.stage) // nothing staged: mark the slot
-    reinterpret_cast<unsigned long long *>(&ws.slots[s])[1] = 0xFFFFFFFFFFFFFFFFull;
-  ecnt += ctx.acc_emitted | (ctx.acc_dropped << 8) | (ctx.acc_appended << 16);
-  mn = ctx.acc_min < mn ? ctx.acc_min : mn;
+  if (ctx.stage != SIMIAN_NONE) sh.lo[i].y = 0xFFFFFFFFFFFFFFFFull; // nothing staged
 }
 
-// K3 + K4 + trace chain for the records in slots [0, nvalid): classification
-// (due / leftover), counting sort by entity, rank, handlers, appends, chain.
-// Entities [e_lo, e_hi) of the group are committed (every due record in the
-// slots belongs to one of them).  `first`: leftover times feed the LBTS minimum.
-// `carry`: one time slice of a hot entity (split passes): the entity's state in
-// shared memory is kept current for the next slice; bin_hi bounds the slice.
-// Warp-uniform.  Results go to the warp's accumulators (ws.acc_*).
-__device__ __forceinline__ void warp_pass(const DevCfg &c, WarpShared &ws, uint32_t slot0,
-                                          uint32_t nvalid, uint32_t e_lo, uint32_t e_hi,
-                                          bool first, bool carry = false, uint32_t bin_hi = 64u) {
-  const uint32_t lane = threadIdx.x & 31u;
-  ws.cnt[lane] = 0;
-  ws.cnt[lane + 32] = 0;
-  __syncwarp();
-  // ---- classify: due records join their entity's histogram bin (the value the
-  // shared-memory atomic returns is the record's arrival index inside the bin)
-  {
-    const double w_hi = ws.W.hi, w_gmin = ws.W.gmin;
-    unsigned long long mn = SIMIAN_KEY_NONE, mx = 0;
-    for (uint32_t s = lane; s < nvalid; s += 32) {
-      const ulonglong2 a = slot_lo(ws, s);
-      const double t = __longlong_as_double((long long)a.x);
-      uint32_t e = 0xFFFFu;
-      if (t < w_hi) {
-        if (t >= w_gmin) {
-          const uint32_t le = (uint32_t)a.y - slot0;
-          if (le < GE) {
-            e = le | (atomicAdd(&ws.cnt[le], 1u) << 8);
-            const unsigned long long tk = simian_time_key(t);
-            mx = tk > mx ? tk : mx;
-          } else {
-            set_error(c, SIMIAN_ERR_UNKNOWN_NAME); // a record in another group's cell
-          }
-        }
-      } else {
-        const unsigned long long tk = simian_time_key(t);
-        mn = tk < mn ? tk : mn;
-      }
-      ws.ent[s] = (uint16_t)e;
-    }
-    if (first) wacc_min(ws, mn); // leftovers: K1
-    if (c.all_pure) wacc_max(ws, mx); // (the per-entity path tracks what it commits)
-  }
-  __syncwarp();
-  // ---- exclusive scan of the 64 bins (two per lane, packed 16 + 16 bits)
-  uint32_t m;
-  {
-    const uint32_t c0 = ws.cnt[lane], c1 = ws.cnt[lane + 32];
-    uint32_t x = c0 | (c1 << 16);
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      uint32_t y = __shfl_up_sync(FULL, x, o);
-      if (lane >= (uint32_t)o) x += y;
-    }
-    const uint32_t tot = __shfl_sync(FULL, x, 31);
-    const uint32_t tot0 = tot & 0xFFFFu;
-    m = tot0 + (tot >> 16);
-    ws.base[lane] = (uint16_t)((x & 0xFFFFu) - c0);
-    ws.base[lane + 32] = (uint16_t)(tot0 + (x >> 16) - c1);
-  }
-  __syncwarp();
-  if (m == 0 && !(carry && !c.all_pure)) return;
-  // ---- place: slots grouped by entity
-  for (uint32_t s = lane; s < nvalid; s += 32) {
-    const uint32_t e = ws.ent[s];
-    if (e != 0xFFFFu) ws.ord[ws.base[e & (GE - 1u)] + (e >> 8)] = (uint8_t)s;
-  }
-  __syncwarp();
-  PHASE(3);
-  const uint32_t nr = (m + 31u) >> 5;
-  if (c.all_pure) {
-    // ---- rank, one lane per EVENT; the rank is parked in ent[slot]
-    {
-      uint32_t nt = 0, nd = 0;
+// Phase C, one thread per entity: fold the trace words, already in commit
+// order along the list, and publish the new commit count.
+__device__ __forceinline__ void chain_entity(const DevCfg &c, WindowShared &sh, uint32_t slot,
+                                             uint32_t le, uint32_t first) {
+  EntityCore st = sh.core_s[le];
+  uint32_t n = 0;
 #pragma unroll 1
-      for (uint32_t v = 0; v < nr; v++) {
-        const uint32_t p = lane + 32u * v;
-        bool tie = false, dtie = false;
-        if (p < m) {
-          const uint32_t s = ws.ord[p];
-          ws.ent[s] = (uint16_t)rank_event<true>(c, ws, slot0, p, s, tie, dtie);
-        }
-        if (c.tie_check) {
-          nt += (uint32_t)__popc(__ballot_sync(FULL, tie));
-          nd += (uint32_t)__popc(__ballot_sync(FULL, dtie));
-        }
-      }
-      if (lane == 0) {
-        ws.acc_committed += m;
-        ws.acc_ties += nt;
-        ws.acc_dties += nd;
-      }
-    }
-    __syncwarp();
-    PHASE(4);
-    // ---- handlers (K3), one lane per EVENT; the sent record is staged in the
-    // consumed record's slot
-    {
-      uint32_t ecnt = 0;
-      unsigned long long mn = SIMIAN_KEY_NONE;
-#pragma unroll 1
-      for (uint32_t v = 0; v < nr; v++) {
-        const uint32_t p = lane + 32u * v;
-        if (p < m) {
-          const uint32_t s = ws.ord[p];
-          run_event(c, ws, slot0, s, ws.ent[s], ecnt, mn);
-        }
-      }
-      wacc_min(ws, mn);
-      const uint32_t s1 = __reduce_add_sync(FULL, ecnt & 255u);
-      const uint32_t s2 = __reduce_add_sync(FULL, (ecnt >> 8) & 255u);
-      const uint32_t s5 = __reduce_add_sync(FULL, ecnt >> 16);
-      if (lane == 0) {
-        ws.acc_emitted += s1;
-        ws.acc_dropped += s2;
-        ws.acc_appended += s5;
-      }
-    }
-    PHASE(5); // (no barrier: the append phase reads only the slots its own lane staged)
-    // ---- append (K4), one lane per EVENT; the claims of all of a lane's
-    // events are in flight together
-    {
-      const WinState &W = ws.W;
-      unsigned long long old[NROUND];
-      uint32_t cell[NROUND];
-      uint32_t spack[(NROUND + 3) / 4]; // the slot of each round, 8 bits each
-#pragma unroll
-      for (int q = 0; q < (NROUND + 3) / 4; q++) spack[q] = 0;
-#pragma unroll
-      for (int v = 0; v < NROUND; v++) {
-        cell[v] = SIMIAN_NONE;
-        if ((uint32_t)v < nr && lane + 32u * v < m) {
-          const uint32_t s = ws.ord[lane + 32u * v];
-          spack[v / 4] |= s << (8 * (v % 4));
-          const ulonglong2 a = slot_lo(ws, s);
-          if ((uint32_t)a.y != SIMIAN_NONE)
-            cell[v] = cell_of_local(c, ws.ax, W.tb_clean, W.far_row,
-                                    __longlong_as_double((long long)a.x), (uint32_t)a.y);
-        }
-      }
-#pragma unroll
-      for (int v = 0; v < NROUND; v++)
-        if (cell[v] != SIMIAN_NONE) old[v] = atomicAdd(c.cell_state + cell[v], 1ull);
-      // ---- chain, one lane per entity, while the claims are in flight: fold
-      // the trace words (in commit order at xs[base ..]) and publish the count
-      {
-        if (carry) __syncwarp(); // the handlers have read the entity's old count
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-          const uint32_t le = lane + 32u * h;
-          const uint32_t n = ws.cnt[le];
-          if (le >= e_lo && le < e_hi && n) {
-            const uint32_t b = ws.base[le];
-            EntityCore st = ws.core_s[le];
-#pragma unroll 1
-            for (uint32_t j = 0; j < n; j++) st.hash = simian_trace_chain(st.hash, ws.xs[b + j]);
-            st.count += n;
-            c.core[slot0 + le] = st;
-            if (carry) ws.core_s[le] = st;
-          }
-        }
-      }
-      // Claims are serviced in two rounds so that no lane ever waits for a
-      // page while it still owes one: first every claim that landed in a
-      // page or must INSTALL one (never blocks); only then the claims that
-      // have to wait for another thread's install.  (Waiting first can
-      // deadlock: two threads holding crossed install/wait claims.)
-      uint32_t waiting = 0;
-#pragma unroll
-      for (int v = 0; v < NROUND; v++)
-        if (cell[v] != SIMIAN_NONE) {
-          const uint32_t idx = CELL_COUNT(old[v]);
-          if (idx <= (uint32_t)PAGE) { // lands in a page, or installs one
-            const uint32_t s = (spack[v / 4] >> (8 * (v % 4))) & 255u;
-            const ulonglong2 a = slot_lo(ws, s), bh = slot_hi(ws, s);
-            if (idx < (uint32_t)PAGE) {
-              RecBits r;
-              r.q0 = a.x, r.q1 = a.y, r.q2 = bh.x, r.q3 = bh.y;
-              st_rec(c.pool + ((size_t)(uint32_t)(old[v] >> 32) * PAGE + idx), r);
-            } else {
-              cell_append_slow(c, ws.ax, W.alloc_limit, c.cell_state + cell[v], old[v], a.x, a.y,
-                               bh.x, bh.y);
-            }
-          } else {
-            waiting |= 1u << v;
-          }
-        }
-      __syncwarp(); // every install of this warp is done before any of its lanes waits
-      if (waiting) { // rare
-#pragma unroll
-        for (int v = 0; v < NROUND; v++)
-          if (waiting & (1u << v)) {
-            const uint32_t s = (spack[v / 4] >> (8 * (v % 4))) & 255u;
-            const ulonglong2 a = slot_lo(ws, s), bh = slot_hi(ws, s);
-            cell_append_slow(c, ws.ax, W.alloc_limit, c.cell_state + cell[v], old[v], a.x, a.y,
-                             bh.x, bh.y);
-          }
-      }
-    }
-    __syncwarp();
-    PHASE(6);
-  } else {
-    // ---- stateful handlers: sort each entity's events (rank), then one lane
-    // per entity commits them in order, same-window self-sends merged in
-#pragma unroll 1
-    for (uint32_t v = 0; v < nr; v++) {
-      const uint32_t p = lane + 32u * v;
-      bool t0 = false, t1 = false;
-      if (p < m) rank_event<false>(c, ws, slot0, p, ws.ord[p], t0, t1);
-    }
-    __syncwarp();
-    // (process_entity is not inlined: its accumulators live in local memory)
-    ThreadAcc t2;
-    thread_acc_init(t2);
-    // (a time slice of a hot entity runs even without calendar events: pending
-    // self-sends may fall into it)
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-      const uint32_t le = lane + 32u * h;
-      const uint32_t n = ws.cnt[le];
-      if (le >= e_lo && le < e_hi && (n || carry))
-        process_entity(c, ws, t2, slot0 + le, le, ws.base[le], n, carry, bin_hi);
-    }
-    __syncwarp();
-    wacc_thread(ws, t2);
+  for (uint32_t j = first; j != LIST_END; j = sh.nxt[j]) {
+    st.hash = simian_trace_chain(st.hash, sh.xs[j]);
+    n++;
   }
+  st.count += n;
+  c.core[slot] = st;
 }
 
-// ---- page listing ------------------------------------------------------------
-// A lane owns one calendar cell of the window (row tb_lo + lane) and walks its
-// page chain through a cursor it keeps in registers; the pages go into the
-// warp's page list, at most PGMAX per chunk.
-
-struct Cursor {
-  uint32_t page; // SIMIAN_NONE: exhausted
-  uint32_t cnt;  // records in it | CELL_OLDER
-};
-
-__device__ __forceinline__ Cursor cursor_of_head(unsigned long long hw) {
-  Cursor k;
-  k.page = (uint32_t)(hw >> 32);
-  uint32_t n = CELL_COUNT(hw);
-  k.cnt = (n < (uint32_t)PAGE ? n : (uint32_t)PAGE) | ((uint32_t)hw & CELL_OLDER);
-  return k;
-}
-
-// page_next of a page known to have an older page.  The installer publishes the
-// cell's new head word without a fence after writing the link, so a reader in
-// the same launch may still see NONE (the value of a free page): re-read.
-__device__ __forceinline__ uint32_t link_of(const DevCfg &c, uint32_t p) {
-  uint32_t raw = ld_cg(&c.page_next[p]);
-  uint32_t spins = 0;
-  while (raw == SIMIAN_NONE) {
-    if (++spins > (1u << 22)) {
-      set_error(c, SIMIAN_ERR_STALLED);
-      break;
-    }
-    __nanosleep(20);
-    raw = ld_cg(&c.page_next[p]);
-  }
-  return raw;
-}
-
-// Lists the next chunk of pages.  Returns true when every cursor is exhausted
-// (the list is complete); ws.npg / pg_* hold the chunk, nvalid its records.
-__device__ __forceinline__ bool list_chunk(const DevCfg &c, WarpShared &ws, Cursor &cur,
-                                           uint32_t free_flag, uint32_t &npg_out,
-                                           uint32_t &nvalid_out) {
-  const uint32_t lane = threadIdx.x & 31u;
-  if (lane == 0) ws.npg = 0;
-  __syncwarp();
-#pragma unroll 1
-  while (cur.page != SIMIAN_NONE) {
-    const uint32_t idx = atomicAdd(&ws.npg, 1u);
-    if (idx >= (uint32_t)PGMAX) break; // resume here in the next chunk
-    const uint32_t older = cur.cnt & CELL_OLDER;
-    ws.pg_id[idx] = cur.page;
-    ws.pg_cnt[idx] = (uint16_t)(CELL_COUNT(cur.cnt) | (older ? PG_LINKED : 0u) | free_flag);
-    if (!older) {
-      cur.page = SIMIAN_NONE;
-      break;
-    }
-    const uint32_t raw = link_of(c, cur.page);
-    if (raw == SIMIAN_NONE) { // error set
-      cur.page = SIMIAN_NONE;
-      break;
-    }
-    cur.page = raw & 0x7FFFFFFFu;
-    cur.cnt = (uint32_t)PAGE | (raw & CELL_OLDER); // older pages are always full
-  }
-  __syncwarp();
-  uint32_t npg = ws.npg;
-  npg = npg < (uint32_t)PGMAX ? npg : (uint32_t)PGMAX;
-  // record offsets: exclusive prefix of the page counts
-  uint32_t carry = 0;
-  for (uint32_t i0 = 0; i0 < npg; i0 += 32) {
-    const uint32_t i = i0 + lane;
-    const uint32_t n = i < npg ? PG_COUNT(ws.pg_cnt[i]) : 0u;
-    uint32_t x = n;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      uint32_t y = __shfl_up_sync(FULL, x, o);
-      if (lane >= (uint32_t)o) x += y;
-    }
-    if (i < npg) ws.pg_off[i] = (uint16_t)(carry + x - n);
-    carry += __shfl_sync(FULL, x, 31);
-  }
-  __syncwarp();
-  npg_out = npg;
-  nvalid_out = carry;
-  return __ballot_sync(FULL, cur.page != SIMIAN_NONE) == 0u;
-}
-
-// One scan over the pages of the current chunk (slow path).  Every due record
-// has a KEY in [0, 64): its local entity (BYTIME == false), or, for the records
-// of entity `ent` only, its time bin inside the window (BYTIME == true).
-// COLLECT == false: histogram of the keys (ws.cnt) (+ the leftover minimum);
-// COLLECT == true: the due records with key in [e_lo, e_hi) are copied into the
-// slots (ws.total counts them).
-template <bool COLLECT, bool BYTIME>
-__device__ __forceinline__ void scan_chunk(const DevCfg &c, WarpShared &ws,
-                                           unsigned long long &left_min, uint32_t slot0,
-                                           uint32_t npg, uint32_t e_lo, uint32_t e_hi,
-                                           uint32_t ent) {
-  const uint32_t lane = threadIdx.x & 31u;
-  const double w_hi = ws.W.hi, w_gmin = ws.W.gmin;
+// K2: ONE coalesced pass over the block's pages.  Every record whose time is
+// inside [gmin, hi) and whose entity is inside [e_lo, e_hi) is copied into a
+// shared-memory slot (cp.async, no registers) and pushed onto its entity's
+// list (eventQ.pop for all of them at once, eventQ.js:53-92); the first event
+// of an entity also fetches the entity's {count, hash}.  On the first pass the
+// minimum time >= hi is tracked (K1).  Slots are claimed with one
+// shared-memory atomic per warp.
+__device__ __forceinline__ void collect_due(const DevCfg &c, WindowShared &sh, ThreadAcc &ta,
+                                            uint32_t slot0, uint32_t pg_lo, uint32_t pg_hi,
+                                            uint32_t e_lo, uint32_t e_hi, bool first) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  const double w_hi = sh.W.hi, w_gmin = sh.W.gmin;
   constexpr int U = 4;
-  const uint32_t lim = npg * PAGE;
-  for (uint32_t base = 0; base < lim; base += U * 32) {
+  // thread -> (page, slot): the slot inside the page is fixed per thread, the
+  // page advances by NTHREADS / PAGE per step (PAGE divides NTHREADS or vice versa)
+  static_assert(NTHREADS % PAGE == 0 || PAGE % NTHREADS == 0, "page / CTA shape");
+  const uint32_t lim = (pg_hi - pg_lo) * PAGE;
+  for (uint32_t base = 0; base < lim; base += U * NTHREADS) {
     unsigned long long q0[U], q1[U];
-    const simian_event_t *src[U];
+    uint32_t ref[U];
     bool ok[U];
 #pragma unroll
     for (int u = 0; u < U; u++) {
-      const uint32_t i = base + u * 32 + lane;
-      const uint32_t pg = i / PAGE, sl = i % PAGE;
-      ok[u] = i < lim && sl < PG_COUNT(ws.pg_cnt[pg < (uint32_t)PGMAX ? pg : 0]);
-      src[u] = c.pool + ((size_t)ws.pg_id[pg < (uint32_t)PGMAX ? pg : 0] * PAGE + sl);
-      if (ok[u]) ld_rec_head(src[u], q0[u], q1[u]);
+      const uint32_t i = base + u * NTHREADS + tid;
+      const uint32_t pg = pg_lo + i / PAGE, sl = i % PAGE;
+      ok[u] = false;
+      ref[u] = 0;
+      if (i < lim) {
+        const uint32_t cnt = (uint32_t)(sh.pg_cnt[pg] & 0x7FFFu);
+        ok[u] = sl < cnt;
+        ref[u] = sh.pg_id[pg] * PAGE + sl;
+      }
+      if (ok[u]) ld_rec_head(c.pool + ref[u], q0[u], q1[u]);
     }
 #pragma unroll
     for (int u = 0; u < U; u++) {
       bool due = false;
       uint32_t le = 0;
       if (ok[u]) {
-        const double t = __longlong_as_double((long long)q0[u]);
+        double t = __longlong_as_double((long long)q0[u]);
         if (t < w_hi) {
           le = (uint32_t)q1[u] - slot0;
-          due = t >= w_gmin;
-          if (due && le >= GE) {
-            set_error(c, SIMIAN_ERR_UNKNOWN_NAME);
-            due = false;
-          }
-          if (BYTIME) {
-            due = due && le == ent;
-            if (due) le = time_bin(ws.W, t); // the key
-          }
-          if (COLLECT) due = due && le >= e_lo && le < e_hi;
-        } else if (!COLLECT && !BYTIME) {
+          due = t >= w_gmin && le >= e_lo && le < e_hi;
+        } else if (first) {
           unsigned long long tk = simian_time_key(t);
-          left_min = tk < left_min ? tk : left_min;
+          ta.min_key = tk < ta.min_key ? tk : ta.min_key;
         }
       }
-      if (!COLLECT) {
-        if (due) atomicAdd(&ws.cnt[le], 1u);
-      } else {
-        const unsigned mk = __ballot_sync(FULL, due);
-        if (mk) {
-          const uint32_t p0 = ws.total; // warp-uniform: updated by lane 0 below
-          if (due) {
-            const uint32_t pos = p0 + __popc(mk & ((1u << lane) - 1u));
-            if (pos < (uint32_t)NSLOT) {
-              unsigned long long q2, q3;
-              ld_rec_head((const simian_event_t *)((const char *)src[u] + 16), q2, q3);
-              ulonglong2 *d = reinterpret_cast<ulonglong2 *>(&ws.slots[pos]);
-              d[0] = make_ulonglong2(q0[u], q1[u]);
-              d[1] = make_ulonglong2(q2, q3);
-            } else {
-              set_error(c, SIMIAN_ERR_WINDOW_OVERFLOW); // cannot happen: ranges are sized from the histogram
-            }
+      unsigned m = __ballot_sync(0xffffffffu, due);
+      if (m) {
+        uint32_t p0 = 0;
+        int leader = __ffs(m) - 1;
+        if (lane == leader) p0 = atomicAdd(&sh.total, (uint32_t)__popc(m));
+        p0 = __shfl_sync(0xffffffffu, p0, leader);
+        if (due) {
+          uint32_t pos = p0 + __popc(m & ((1u << lane) - 1u));
+          if (pos < NREFS) {
+            sh.lo[pos] = make_ulonglong2(q0[u], q1[u]);
+            cp_async16(&sh.hi[pos], (const char *)(c.pool + ref[u]) + 16);
+            uint32_t prev = atomicExch(&sh.head[le], pos);
+            sh.nxt[pos] = (uint16_t)prev;
+            if (prev == LIST_END) cp_async16(&sh.core_s[le], &c.core[slot0 + le]);
+          } else if (first) {
+            // overflow (a burst): where in the block the records without a slot
+            // belong -- the partition step sizes its parts from this
+            atomicAdd(&sh.hist[le >> sh.bin_shift], 1u);
           }
-          __syncwarp();
-          if (lane == 0) ws.total = p0 + __popc(mk);
-          __syncwarp();
         }
       }
     }
   }
+  cp_async_wait_all();
 }
 
-// The uncommon path of a window: the pages of its rows hold more records than
-// the warp has slots (bursts such as the 16 events per entity all scheduled at
-// t = 0), or more pages than the list holds.  A first scan builds the histogram
-// of due records per entity; the group's entities are then cut into ranges of
-// at most NSLOT due records, and each range is one filtered scan + one ordinary
-// pass.  Page lists longer than PGMAX are re-walked chunk by chunk in every scan.
-// Kept out of line so that the common single-pass window pays nothing for it.
-// BYTIME: the same for ONE entity (`ent`) with more due events than slots: its
-// window is cut into time slices along a 64-bin time histogram, each slice one
-// pass; the entity's state and pending self-sends carry over (warp_pass carry).
-template <bool BYTIME>
-__device__ __noinline__ void slow_passes(const DevCfg &c, WarpShared &ws, uint32_t slot0,
-                                         unsigned long long hw, uint32_t free_flag, bool complete,
-                                         uint32_t npg0, uint32_t ent) {
-  const uint32_t lane = threadIdx.x & 31u;
-  unsigned long long left_min = SIMIAN_KEY_NONE;
-  ws.cnt[lane] = 0;
-  ws.cnt[lane + 32] = 0;
-  __syncwarp();
-  // ---- scan 1: histogram (the first chunk is already listed)
-  {
-    uint32_t npg = npg0, nv;
-    Cursor cur;
-    cur.page = SIMIAN_NONE;
-    cur.cnt = 0;
-    bool done = complete;
-    if (!complete) { // re-walk from the heads: the cursors of the first listing are gone
-      cur = cursor_of_head(hw);
-      done = list_chunk(c, ws, cur, free_flag, npg, nv);
-    }
-#pragma unroll 1
-    for (;;) {
-      scan_chunk<false, BYTIME>(c, ws, left_min, slot0, npg, 0, GE, ent);
-      if (done) break;
-      done = list_chunk(c, ws, cur, free_flag, npg, nv);
+// K2, common case: the pages of the window's rows hold no more records than
+// the CTA has slots.  ALL of them are copied into the shared-memory slots in
+// one round trip (cp.async, no registers, every load of the CTA in flight at
+// once); slot = records in the pages listed before + index in the page.
+__device__ __forceinline__ void collect_all(const DevCfg &c, WindowShared &sh, uint32_t npg) {
+  const uint32_t lim = npg * PAGE;
+  for (uint32_t i = threadIdx.x; i < lim; i += NTHREADS) {
+    const uint32_t pg = i / PAGE, sl = i % PAGE;
+    if (sl < (uint32_t)(sh.pg_cnt[pg] & 0x7FFFu)) {
+      const simian_event_t *src = c.pool + ((size_t)sh.pg_id[pg] * PAGE + sl);
+      const uint32_t pos = sh.pg_off[pg] + sl;
+      cp_async16(&sh.lo[pos], src);
+      cp_async16(&sh.hi[pos], (const char *)src + 16);
     }
   }
-  __syncwarp();
-  if (!BYTIME) wacc_min(ws, left_min); // leftovers: K1
-  // exclusive prefix of the histogram, kept in registers (warp_pass reuses ws.cnt)
-  const uint32_t h0 = ws.cnt[lane], h1 = ws.cnt[lane + 32];
-  uint32_t x = h0, y = h1;
+  cp_async_wait_all();
+}
+
+// ... then every thread classifies the records in its slots (the same slots it
+// handles in the later phases): due events are pushed onto their entity's list
+// and fetch the entity's {count, hash} (waited for after the rank phase); the
+// others only feed the LBTS minimum (K1).  Returns the mask of its due slots.
+__device__ __forceinline__ uint32_t link_due(const DevCfg &c, WindowShared &sh, ThreadAcc &ta,
+                                             uint32_t slot0, uint32_t nvalid) {
+  const double w_hi = sh.W.hi, w_gmin = sh.W.gmin;
+  uint32_t live = 0;
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    uint32_t a = __shfl_up_sync(FULL, x, o), b = __shfl_up_sync(FULL, y, o);
-    if (lane >= (uint32_t)o) x += a, y += b;
-  }
-  const uint32_t t0 = __shfl_sync(FULL, x, 31);
-  const uint32_t in0 = x, in1 = t0 + y; // inclusive prefix at entities lane, lane + 32
-  const uint32_t total_due = __shfl_sync(FULL, in1, 31);
-  if (total_due == 0) return;
-  if (BYTIME) { // nothing pending, no tie state yet
-    if (lane == 0) ws.xs[CARRY_NPEND] = 0, ws.xs[CARRY_LAST] = 0;
-    __syncwarp();
-  }
-  uint32_t e_lo = 0;
-#pragma unroll 1
-  while (e_lo < GE) {
-    // inclusive prefix just before e_lo
-    const uint32_t before =
-        e_lo == 0 ? 0u
-                  : (e_lo <= 32 ? __shfl_sync(FULL, in0, (e_lo - 1u) & 31u)
-                                : __shfl_sync(FULL, in1, (e_lo - 33u) & 31u));
-    // entities e >= e_lo whose inclusive prefix still fits: a prefix of [e_lo, GE)
-    const unsigned f0 = __ballot_sync(FULL, lane >= e_lo && in0 - before <= (uint32_t)NSLOT);
-    const unsigned f1 = __ballot_sync(FULL, lane + 32u >= e_lo && in1 - before <= (uint32_t)NSLOT);
-    const uint32_t fit = (uint32_t)__popc(f0) + (uint32_t)__popc(f1);
-    uint32_t e_hi = e_lo + fit;
-    if (fit == 0) { // one entity with more due events than the warp has slots
-      if (BYTIME) { // ... inside 1/64 of the window: give up
-        if (lane == 0) set_error(c, SIMIAN_ERR_ENTITY_BURST);
-        break;
+  for (int u = 0; u < EV_PER_THREAD; u++) {
+    const uint32_t i = threadIdx.x + u * NTHREADS;
+    if (i < nvalid) {
+      const ulonglong2 a = sh.lo[i];
+      const double t = __longlong_as_double((long long)a.x);
+      if (t < w_hi) {
+        if (t >= w_gmin) {
+          const uint32_t le = (uint32_t)a.y - slot0;
+          const uint32_t prev = atomicExch(&sh.head[le], i);
+          sh.nxt[i] = (uint16_t)prev;
+          if (prev == LIST_END) cp_async16(&sh.core_s[le], &c.core[slot0 + le]);
+          live |= 1u << u;
+        }
+      } else {
+        unsigned long long tk = simian_time_key(t);
+        ta.min_key = tk < ta.min_key ? tk : ta.min_key;
       }
-      slow_passes<true>(c, ws, slot0, hw, free_flag, complete, npg0, e_lo);
-      e_lo++;
-      continue;
     }
-    const uint32_t upto = e_hi <= 32 ? __shfl_sync(FULL, in0, (e_hi - 1u) & 31u)
-                                     : __shfl_sync(FULL, in1, (e_hi - 33u) & 31u);
-    if (upto != before || (BYTIME && !c.all_pure)) {
-      // ---- scan 2: the due records of [e_lo, e_hi) -> slots
-      if (lane == 0) ws.total = 0;
-      __syncwarp();
-      uint32_t npg = npg0, nv;
-      Cursor cur;
-      cur.page = SIMIAN_NONE;
-      cur.cnt = 0;
-      bool done = complete;
-      if (!complete) {
-        cur = cursor_of_head(hw);
-        done = list_chunk(c, ws, cur, free_flag, npg, nv);
-      }
-#pragma unroll 1
-      for (;;) {
-        scan_chunk<true, BYTIME>(c, ws, left_min, slot0, npg, e_lo, e_hi, ent);
-        if (done) break;
-        done = list_chunk(c, ws, cur, free_flag, npg, nv);
-      }
-      __syncwarp();
-      uint32_t m = ws.total;
-      m = m < (uint32_t)NSLOT ? m : (uint32_t)NSLOT;
-      if (BYTIME)
-        warp_pass(c, ws, slot0, m, ent, ent + 1u, false, true, e_hi);
-      else
-        warp_pass(c, ws, slot0, m, e_lo, e_hi, false);
-    }
-    e_lo = e_hi;
   }
+  return live;
 }
 
-// free a whole cell (pages -> ring, head cleared); one thread.  `scrub`: the
-// records may lie in the future (far rows): restore the free-page invariant.
-__device__ __forceinline__ void free_cell(const DevCfg &c, unsigned long long *hp, bool scrub) {
-  const unsigned long long hw = *hp;
-  uint32_t p = (uint32_t)(hw >> 32), older = (uint32_t)hw & CELL_OLDER;
-  while (p != SIMIAN_NONE) {
-    const uint32_t raw = older ? c.page_next[p] : SIMIAN_NONE;
-    if (scrub) scrub_page(c, p);
-    page_free(c, p, older != 0);
+// Burst partition.  The first pass found more due events than the CTA has
+// slots for (e.g. the 16 events per entity all scheduled at t = 0).  Instead
+// of re-scanning every page of the window once per entity sub-range, the due
+// records are copied ONCE into scratch pages grouped by entity sub-range
+// ("parts", sized from the histogram the overflowing pass built); each part is
+// then one ordinary pass over its own few pages, all of whose records are due.
+// The scratch pages come from the block's page stack / the free ring, are
+// listed behind the cells' pages in pg_id and are recycled with them at the end
+// of the launch.  Returns (CTA-uniform) false when the page list has no room:
+// the caller falls back to splitting the entity range and re-scanning.
+__device__ __noinline__ bool partition_burst(const DevCfg &c, WindowShared &sh, uint32_t slot0,
+                                            uint32_t npg_scan) {
+  const int tid = threadIdx.x;
+  const uint32_t shift = sh.bin_shift;
+  // the records that did get a slot in the overflowing pass
+  for (uint32_t i = tid; i < NREFS; i += NTHREADS)
+    atomicAdd(&sh.hist[((uint32_t)sh.lo[i].y - slot0) >> shift], 1u);
+  __syncthreads();
+  if (tid == 0) {
+    const uint32_t nb = ((c.epb - 1u) >> shift) + 1u; // bins in use
+    uint32_t q = 0, cur = 0, bin0 = 0, pages = sh.npg;
+    bool fits = true;
+    for (uint32_t bin = 0; bin <= nb; bin++) {
+      const uint32_t h = bin < nb ? sh.hist[bin] : 0u;
+      if (bin == nb || (cur != 0 && cur + h > (uint32_t)NREFS)) { // close part q
+        const uint32_t np = (cur + PAGE - 1) / PAGE;
+        if (pages + np > (uint32_t)PGMAX) {
+          fits = false;
+          break;
+        }
+        sh.pcnt[q] = cur;
+        sh.pfill[q] = 0;
+        sh.plo[q] = bin0 << shift;
+        sh.phi[q] = (bin << shift) < c.epb ? (bin << shift) : c.epb;
+        sh.ppage0[q] = pages;
+        for (uint32_t k = 0; k < np; k++)
+          sh.pg_cnt[pages + k] =
+              (uint16_t)((k + 1 < np ? (uint32_t)PAGE : cur - k * PAGE) | PG_FREE_FLAG);
+        pages += np;
+        q++;
+        bin0 = bin;
+        cur = 0;
+      }
+      if (bin < nb) {
+        sh.part_of_bin[bin] = q;
+        cur += h;
+      }
+    }
+    sh.ppage0[q] = pages;
+    sh.nparts = fits ? q : 0u;
+    if (fits) sh.nfree += pages - sh.npg; // the scratch pages are recycled with the others
+  }
+  __syncthreads();
+  const uint32_t nparts = sh.nparts;
+  if (nparts == 0) return false;
+  const uint32_t pg_end = sh.ppage0[nparts];
+  for (uint32_t i = npg_scan + tid; i < pg_end; i += NTHREADS)
+    sh.pg_id[i] = page_get(c, sh.ax, sh.W.alloc_limit); // SIMIAN_NONE: sticky error set
+  __syncthreads();
+  if (tid == 0) {
+    sh.npg = pg_end; // recycled with the cells' pages
+    sh.found = ld_cg(&c.acc->error);
+  }
+  __syncthreads();
+  if (sh.found) return true; // pool exhausted: nothing is pushed, the launch ends
+  // one pass over the window's pages: every due record -> its part's scratch pages
+  const double w_hi = sh.W.hi, w_gmin = sh.W.gmin;
+  constexpr int U = 4;
+  const uint32_t lim = npg_scan * PAGE;
+  for (uint32_t base = 0; base < lim; base += U * NTHREADS) {
+    RecBits r[U];
+    bool ok[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const uint32_t i = base + u * NTHREADS + tid;
+      const uint32_t pg = i / PAGE, sl = i % PAGE;
+      ok[u] = i < lim && sl < (uint32_t)(sh.pg_cnt[pg < PGMAX ? pg : 0] & 0x7FFFu);
+      if (ok[u]) r[u] = ld_rec_2x16(c.pool + ((size_t)sh.pg_id[pg] * PAGE + sl));
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      if (!ok[u]) continue;
+      const double t = r[u].time();
+      if (!(t < w_hi && t >= w_gmin)) continue;
+      const uint32_t q = sh.part_of_bin[(r[u].dst() - slot0) >> shift];
+      const uint32_t pos = atomicAdd(&sh.pfill[q], 1u);
+      if (pos >= sh.pcnt[q]) { // cannot happen: both passes see the same records
+        set_error(c, SIMIAN_ERR_WINDOW_OVERFLOW);
+        continue;
+      }
+      st_rec_2x16(c.pool + ((size_t)sh.pg_id[sh.ppage0[q] + pos / PAGE] * PAGE + pos % PAGE),
+                  r[u].q0, r[u].q1, r[u].q2, r[u].q3);
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (uint32_t q = nparts; q-- > 0;) { // lowest sub-range on top of the stack
+      if (sh.pcnt[q] == 0) continue;
+      uint32_t *st = &sh.rstack[4 * sh.stack_n];
+      st[0] = sh.plo[q];
+      st[1] = sh.phi[q];
+      st[2] = sh.ppage0[q];
+      st[3] = sh.ppage0[q + 1];
+      sh.stack_n++;
+    }
+  }
+  __syncthreads();
+  return true;
+}
+
+// walk one cell's page chain into the CTA's page list.  `lo32`: the count half
+// of the cell's head word (records in the head page, CELL_OLDER)
+__device__ __forceinline__ void list_cell_pages(const DevCfg &c, WindowShared &sh, uint32_t head,
+                                                uint32_t lo32, uint32_t flag) {
+  uint32_t p = head, cntp = CELL_COUNT(lo32), older = lo32 & CELL_OLDER;
+  if (cntp > (uint32_t)PAGE) cntp = PAGE;
+  if (p == SIMIAN_NONE) return;
+#pragma unroll 1
+  for (;;) {
+    uint32_t idx = atomicAdd(&sh.npg, 1u);
+    uint32_t off = atomicAdd(&sh.nvalid, cntp);
+    if (idx < PGMAX) {
+      sh.pg_id[idx] = p;
+      sh.pg_cnt[idx] = (uint16_t)(cntp | flag);
+      sh.pg_off[idx] = off;
+      if (flag) atomicAdd(&sh.nfree, 1u); // recycled after this window
+    }
+    if (!older) break; // the common case: no link is read
+    const uint32_t raw = c.page_next[p];
     if (raw == SIMIAN_NONE) break;
     p = raw & 0x7FFFFFFFu;
     older = raw & CELL_OLDER;
+    cntp = PAGE; // older pages are always full
   }
-  *hp = CELL_EMPTY;
-}
-
-// Push the pages of the current chunk that are marked free onto the group's
-// page stack in HBM (what does not fit: to the global ring).  `height`: the
-// stack height, warp-uniform, updated.
-__device__ __forceinline__ void recycle_chunk(const DevCfg &c, WarpShared &ws, uint32_t *stack,
-                                              uint32_t npg, uint32_t &height) {
-  const uint32_t lane = threadIdx.x & 31u;
-  for (uint32_t i0 = 0; i0 < npg; i0 += 32) {
-    const uint32_t i = i0 + lane;
-    const uint32_t pc = i < npg ? ws.pg_cnt[i] : 0u;
-    const bool f = (pc & PG_FREE_FLAG) != 0;
-    const unsigned mk = __ballot_sync(FULL, f);
-    const uint32_t room = (uint32_t)SIMIAN_BC - height;
-    if (f) {
-      const uint32_t k = __popc(mk & ((1u << lane) - 1u));
-      const uint32_t pid = ws.pg_id[i];
-      if (k < room) {
-        if (pc & PG_LINKED) c.page_next[pid] = SIMIAN_NONE;
-        stack[height + k] = pid;
-      } else {
-        page_free(c, pid, (pc & PG_LINKED) != 0);
-      }
-    }
-    const uint32_t n = (uint32_t)__popc(mk);
-    height += n < room ? n : room;
-  }
-}
-
-// Far-row redistribution for group g (own cells only: no cross-warp traffic).
-__device__ __noinline__ void redistribute_group(const DevCfg &c, WarpShared &ws, uint32_t g) {
-  const WinState &W = ws.W;
-  const uint32_t lane = threadIdx.x & 31u;
-  unsigned long long *cells = c.cell_state + (size_t)g * c.rows;
-  // 1. recycle rows [tb_clean, tb_clean_new): only dead records remain there
-  long long nrec = W.tb_clean_new - W.tb_clean;
-  if (nrec > (long long)c.ring) nrec = c.ring;
-  for (long long i = lane; i < nrec; i += 32) {
-    long long tb = W.tb_clean + i;
-    free_cell(c, cells + (uint32_t)(tb & (long long)c.ring_mask), false);
-  }
-  __syncwarp();
-  // 2. move the far row: into the calendar when within the new horizon, else
-  //    into the other far row
-  unsigned long long *far_cell = cells + c.ring + W.far_row;
-  const uint32_t other = W.far_row ^ 1u;
-  const unsigned long long hw = *far_cell;
-  Cursor cur;
-  cur.page = SIMIAN_NONE;
-  cur.cnt = 0;
-  if (lane == 0) cur = cursor_of_head(hw);
-  bool done;
-#pragma unroll 1
-  do {
-    uint32_t npg, nv;
-    done = list_chunk(c, ws, cur, 0u, npg, nv);
-    for (uint32_t i = lane; i < npg * PAGE; i += 32) {
-      const uint32_t pg = i / PAGE, s = i % PAGE;
-      if (s >= PG_COUNT(ws.pg_cnt[pg])) continue;
-      RecBits r = ld_rec_2x16(c.pool + ((size_t)ws.pg_id[pg] * PAGE + s));
-      append_local(c, ws.ax, W.tb_clean_new, other, W.alloc_limit, r);
-    }
-    __syncwarp();
-  } while (!done);
-  // 3. release the far row's pages; their records lie in the future: scrub
-  if (lane == 0) free_cell(c, far_cell, true);
-  __syncwarp();
 }
 
 // ------- LBTS candidate + next-window set-up (one CTA, all threads) --------
@@ -1795,10 +1329,10 @@ __device__ __noinline__ void redistribute_group(const DevCfg &c, WarpShared &ws,
 // acc->min_key already holds leftovers of row tb_hi + everything appended since
 // the last advance; rows above tb_hi are searched only when that candidate does
 // not already lie in row tb_hi (sparse case: the window jumped over idle time).
-__device__ void local_min_candidate(const DevCfg &c, const WinState &W, CtaShared &sh,
+__device__ void local_min_candidate(const DevCfg &c, const WinState &W, WindowShared &sh,
                                     unsigned long long &cand_out,
                                     unsigned long long &far_out) {
-  const uint32_t tid = threadIdx.x, nt = blockDim.x;
+  const int tid = threadIdx.x;
   DevAcc *a = c.acc;
   unsigned long long far = ld_cg64(&a->far_min[W.far_row]);
   unsigned long long cand = ld_cg64(&a->min_key);
@@ -1811,35 +1345,38 @@ __device__ void local_min_candidate(const DevCfg &c, const WinState &W, CtaShare
     long long tc = tb_of(c, simian_key_time(cand));
     jmax = tc < jmax ? tc : jmax;
   }
-  const long long j0 = W.tb_hi + 1;
-  // first occupied sub-bucket row in [j0, jmax]: one bit per ring row
+  long long j0 = W.tb_hi + 1;
+  // first non-empty sub-bucket row in [j0, jmax], (row, block) pairs in row-major order
   if (tid == 0) sh.scan_j = 0x7FFFFFFFFFFFFFFFLL;
   __syncthreads();
   if (j0 <= jmax) {
-    long long nrows = jmax - j0 + 1;
-    if (nrows > (long long)c.ring) nrows = c.ring;
-    long long best = 0x7FFFFFFFFFFFFFFFLL;
-    for (long long k = tid; k < nrows; k += nt) {
-      const long long j = j0 + k;
-      const uint32_t row = (uint32_t)(j & (long long)c.ring_mask);
-      if ((ld_cg(&c.row_bits[row >> 5]) >> (row & 31u)) & 1u) {
-        best = j;
-        break; // this thread's rows are visited in increasing order
+    unsigned long long total = (unsigned long long)(jmax - j0 + 1) * c.n_blocks;
+    for (unsigned long long base = 0; base < total; base += (unsigned long long)NTHREADS * 8) {
+#pragma unroll 1
+      for (int u = 0; u < 8; u++) {
+        unsigned long long i = base + (unsigned long long)u * NTHREADS + tid;
+        if (i < total) {
+          long long j = j0 + (long long)(i / c.n_blocks);
+          uint32_t b = (uint32_t)(i % c.n_blocks);
+          if ((uint32_t)(ld_cg64(&c.cell_state[(uint32_t)(j & (long long)c.ring_mask) *
+                                                   c.n_blocks + b]) >> 32) != SIMIAN_NONE)
+            atomicMin((unsigned long long *)&sh.scan_j, (unsigned long long)j);
+        }
       }
+      __syncthreads();
+      if (sh.scan_j != 0x7FFFFFFFFFFFFFFFLL) break;
     }
-    if (best != 0x7FFFFFFFFFFFFFFFLL)
-      atomicMin((unsigned long long *)&sh.scan_j, (unsigned long long)best);
   }
   __syncthreads();
-  const long long jf = sh.scan_j;
+  long long jf = sh.scan_j;
   __syncthreads();
   if (jf != 0x7FFFFFFFFFFFFFFFLL) {
     if (tid == 0) sh.min_key = SIMIAN_KEY_NONE;
     __syncthreads();
     unsigned long long mn = SIMIAN_KEY_NONE;
-    const uint32_t row = (uint32_t)(jf & (long long)c.ring_mask);
-    for (uint32_t g = tid; g < c.n_groups; g += nt) {
-      unsigned long long hw = ld_cg64(&c.cell_state[(size_t)g * c.rows + row]);
+    uint32_t row = (uint32_t)(jf & (long long)c.ring_mask) * c.n_blocks;
+    for (uint32_t b = tid; b < c.n_blocks; b += NTHREADS) {
+      unsigned long long hw = ld_cg64(&c.cell_state[row + b]);
       uint32_t p = (uint32_t)(hw >> 32), f = CELL_COUNT(hw), older = (uint32_t)hw & CELL_OLDER;
       while (p != SIMIAN_NONE) {
         f = f < PAGE ? f : PAGE;
@@ -1869,9 +1406,10 @@ __device__ void local_min_candidate(const DevCfg &c, const WinState &W, CtaShare
 
 // Write window k+1 given globalMinLeft (simian.js:119-120,144-147).
 __device__ void setup_next_window(const DevCfg &c, const WinState &W, WinState *Wn, double gmin,
-                                  double far_min_time, bool after_redist, WinState &nw) {
-  const uint32_t tid = threadIdx.x, nt = blockDim.x;
+                                  double far_min_time, bool after_redist) {
+  const int tid = threadIdx.x;
   DevAcc *a = c.acc;
+  __shared__ WinState nw;
   if (tid == 0) {
     nw = W;
     nw.redist = 0;
@@ -1901,7 +1439,7 @@ __device__ void setup_next_window(const DevCfg &c, const WinState &W, WinState *
         nw.redist = 1;
         nw.tb_clean_new = nw.tb_lo;
       }
-      if (nw.tb_hi - nw.tb_lo + 1 > 32)
+      if (nw.tb_hi - nw.tb_lo + 1 > SIMIAN_MAX_CELLS)
         atomicCAS(&a->error, 0u, (unsigned int)SIMIAN_ERR_RING_SPAN);
     }
     nw.alloc_limit = ld_cg64(&a->free_tail);
@@ -1917,23 +1455,20 @@ __device__ void setup_next_window(const DevCfg &c, const WinState &W, WinState *
     nw.parity = a->window_index & 1u;
   }
   __syncthreads();
-  // Occupancy bits of recycled rows are cleared while nothing can append to the
-  // ring rows they alias: after a window, rows [old tb_clean, tb_hi) (recycled by
-  // it); before a redistribution pass, the rows it is going to recycle (the pass
-  // then appends into rows up to a ring above its NEW frontier, whose bits must
-  // survive -- so nothing is cleared after it).
-  {
-    long long lo = W.tb_clean, n = after_redist ? 0 : nw.tb_clean - lo;
-    if (nw.redist) {
-      if (n == 0) lo = nw.tb_clean;
-      n = nw.tb_clean_new - lo;
-    }
-    if (n >= (long long)c.ring) {
-      for (uint32_t k = tid; k < c.ring / 32; k += nt) c.row_bits[k] = 0;
-    } else {
-      for (long long k = tid; k < n; k += nt) {
-        const uint32_t row = (uint32_t)((lo + k) & (long long)c.ring_mask);
-        atomicAnd(&c.row_bits[row >> 5], ~(1u << (row & 31u)));
+  // snapshot the heads of row tb_hi: appends of the next launch may target it
+  if (!nw.done) {
+    uint32_t row = (uint32_t)(nw.tb_hi & (long long)c.ring_mask) * c.n_blocks;
+    for (uint32_t b0 = 0; b0 < c.n_blocks; b0 += 8 * blockDim.x) { // 8 loads in flight per thread
+      unsigned long long v[8];
+#pragma unroll
+      for (int q = 0; q < 8; q++) {
+        uint32_t b = b0 + q * blockDim.x + tid;
+        if (b < c.n_blocks) v[q] = ld_cg64(&c.cell_state[row + b]);
+      }
+#pragma unroll
+      for (int q = 0; q < 8; q++) {
+        uint32_t b = b0 + q * blockDim.x + tid;
+        if (b < c.n_blocks) c.snap[b] = v[q];
       }
     }
   }
@@ -1947,60 +1482,121 @@ __device__ void setup_next_window(const DevCfg &c, const WinState &W, WinState *
   }
 }
 
+// free a whole cell (pages -> ring, head cleared); one thread
+__device__ __forceinline__ void free_cell(const DevCfg &c, uint32_t cell) {
+  const unsigned long long hw = c.cell_state[cell];
+  uint32_t p = (uint32_t)(hw >> 32), older = (uint32_t)hw & CELL_OLDER;
+  while (p != SIMIAN_NONE) {
+    const uint32_t raw = older ? c.page_next[p] : SIMIAN_NONE;
+    page_free(c, p);
+    if (raw == SIMIAN_NONE) break;
+    p = raw & 0x7FFFFFFFu;
+    older = raw & CELL_OLDER;
+  }
+  c.cell_state[cell] = CELL_EMPTY;
+}
+
+// Far-row redistribution for block b (own cells only: no cross-CTA traffic).
+__device__ void redistribute_block(const DevCfg &c, WindowShared &sh, uint32_t b) {
+  const WinState &W = sh.W;
+  const int tid = threadIdx.x;
+  // 1. recycle rows [tb_clean, tb_clean_new): only dead records remain there
+  long long nrec = W.tb_clean_new - W.tb_clean;
+  if (nrec > (long long)c.ring) nrec = c.ring;
+  for (long long i = tid; i < nrec; i += NTHREADS) {
+    long long tb = W.tb_clean + i;
+    free_cell(c, (uint32_t)(tb & (long long)c.ring_mask) * c.n_blocks + b);
+  }
+  __syncthreads();
+  // 2. move the far row: into the calendar when within the new horizon, else
+  //    into the other far row
+  uint32_t far_cell = (c.ring + W.far_row) * c.n_blocks + b;
+  uint32_t other = W.far_row ^ 1u;
+  if (tid == 0) sh.npg = 0;
+  __syncthreads();
+  if (tid == 0) {
+    unsigned long long hw = c.cell_state[far_cell];
+    list_cell_pages(c, sh, (uint32_t)(hw >> 32), (uint32_t)hw, PG_FREE_FLAG);
+  }
+  __syncthreads();
+  uint32_t npg = sh.npg;
+  if (npg > PGMAX) {
+    if (tid == 0) set_error(c, SIMIAN_ERR_WINDOW_OVERFLOW);
+    npg = PGMAX;
+  }
+  for (uint32_t i = tid; i < npg * PAGE; i += NTHREADS) {
+    uint32_t pg = i / PAGE, s = i % PAGE;
+    if (s >= (uint32_t)(sh.pg_cnt[pg] & 0x7FFFu)) continue;
+    RecBits r = ld_rec(c.pool + ((size_t)sh.pg_id[pg] * PAGE + s));
+    append_local(c, sh.ax, W.tb_clean_new, other, W.alloc_limit, r);
+  }
+  __syncthreads();
+  for (uint32_t i = tid; i < npg; i += NTHREADS) page_free(c, sh.pg_id[i]);
+  if (tid == 0) c.cell_state[far_cell] = CELL_EMPTY;
+}
+
+// 64-bit min / max over the warp with redux.sync on the two halves
+__device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v) {
+  uint32_t hi = (uint32_t)(v >> 32), lo = (uint32_t)v;
+  uint32_t mh = __reduce_min_sync(0xffffffffu, hi);
+  uint32_t ml = __reduce_min_sync(0xffffffffu, hi == mh ? lo : 0xFFFFFFFFu);
+  return ((unsigned long long)mh << 32) | ml;
+}
+__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v) {
+  uint32_t hi = (uint32_t)(v >> 32), lo = (uint32_t)v;
+  uint32_t mh = __reduce_max_sync(0xffffffffu, hi);
+  uint32_t ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+  return ((unsigned long long)mh << 32) | ml;
+}
+
 // Sum the launch's results into the global accumulators (one CTA, all threads;
 // runs after the ticket fence, so every CTA's contribution is visible).  The
 // CTAs add into SIMIAN_PART_SLOTS accumulator slots (block index mod slots), so
 // this is ONE round trip, not a loop over the blocks; the slots are cleared
 // for the next launch.
-__device__ void reduce_parts(const DevCfg &c, CtaShared &sh) {
-  const uint32_t tid = threadIdx.x, nt = blockDim.x;
-  if (tid < 10) sh.red[tid] = tid == 0 ? SIMIAN_KEY_NONE : 0ull;
+__device__ void reduce_parts(const DevCfg &c, WindowShared &sh) {
+  const int tid = threadIdx.x;
+  __shared__ unsigned long long red[10];
+  if (tid < 10) red[tid] = tid == 0 ? SIMIAN_KEY_NONE : 0ull;
   __syncthreads();
-  {
-    unsigned long long mn = SIMIAN_KEY_NONE, mx = 0;
+  if (tid < SIMIAN_PART_SLOTS) {
+    BlockPart *p = &c.part[tid];
+    unsigned long long mn = ld_cg64(&p->min_key), mx = ld_cg64(&p->max_key);
     uint32_t v[8];
+    const uint32_t *w = &p->committed;
 #pragma unroll
-    for (int q = 0; q < 8; q++) v[q] = 0;
-    for (uint32_t s = tid; s < SIMIAN_PART_SLOTS; s += nt) {
-      BlockPart *p = &c.part[s];
-      unsigned long long a = ld_cg64(&p->min_key), b = ld_cg64(&p->max_key);
-      mn = a < mn ? a : mn;
-      mx = b > mx ? b : mx;
-      const uint32_t *w = &p->committed;
+    for (int q = 0; q < 8; q++) v[q] = ld_cg(w + q);
+    p->min_key = SIMIAN_KEY_NONE;
+    p->max_key = 0;
 #pragma unroll
-      for (int q = 0; q < 8; q++) v[q] += ld_cg(w + q);
-      p->min_key = SIMIAN_KEY_NONE;
-      p->max_key = 0;
-#pragma unroll
-      for (int q = 0; q < 8; q++) (&p->committed)[q] = 0;
-    }
+    for (int q = 0; q < 8; q++) (&p->committed)[q] = 0;
     mn = warp_min_u64(mn);
     mx = warp_max_u64(mx);
 #pragma unroll
-    for (int q = 0; q < 8; q++) v[q] = __reduce_add_sync(FULL, v[q]);
+    for (int q = 0; q < 8; q++) v[q] = __reduce_add_sync(0xffffffffu, v[q]);
     if ((tid & 31) == 0) {
-      if (mn != SIMIAN_KEY_NONE) atomicMin(&sh.red[0], mn);
-      if (mx) atomicMax(&sh.red[1], mx);
+      if (mn != SIMIAN_KEY_NONE) atomicMin(&red[0], mn);
+      if (mx) atomicMax(&red[1], mx);
 #pragma unroll
       for (int q = 0; q < 8; q++)
-        if (v[q]) atomicAdd(&sh.red[2 + q], (unsigned long long)v[q]);
+        if (v[q]) atomicAdd(&red[2 + q], (unsigned long long)v[q]);
     }
   }
   __syncthreads();
   if (tid == 0) {
     DevAcc *a = c.acc;
     unsigned long long m0 = ld_cg64(&a->min_key); // ingested / scheduled since the last advance
-    a->min_key = sh.red[0] < m0 ? sh.red[0] : m0;
+    a->min_key = red[0] < m0 ? red[0] : m0;
     unsigned long long m1 = ld_cg64(&a->max_key);
-    a->max_key = sh.red[1] > m1 ? sh.red[1] : m1;
-    a->committed += sh.red[2];
-    a->emitted += sh.red[3];
-    a->dropped += sh.red[4];
-    a->ties += sh.red[5];
-    a->dist_ties += sh.red[6];
-    a->appended += sh.red[7];
-    a->far_appends += sh.red[8];
-    a->page_allocs += sh.red[9];
+    a->max_key = red[1] > m1 ? red[1] : m1;
+    a->committed += red[2];
+    a->emitted += red[3];
+    a->dropped += red[4];
+    a->ties += red[5];
+    a->dist_ties += red[6];
+    a->appended += red[7];
+    a->far_appends += red[8];
+    a->page_allocs += red[9];
     __threadfence();
   }
   __syncthreads();
@@ -2011,7 +1607,7 @@ __device__ void reduce_parts(const DevCfg &c, CtaShared &sh) {
 // per peer writes the candidate into the peer's slot array -- data, fence, flag.
 // One CTA, all threads; the launch's results must be visible (ticket fence or
 // a kernel boundary).
-__device__ void lbts_candidate(const DevCfg &c, const WinState &W, CtaShared &sh, uint32_t win_ix,
+__device__ void lbts_candidate(const DevCfg &c, const WinState &W, WindowShared &sh, uint32_t win_ix,
                                int publish) {
   unsigned long long cand, far;
   if (!W.done) reduce_parts(c, sh);
@@ -2042,234 +1638,224 @@ __device__ void lbts_candidate(const DevCfg &c, const WinState &W, CtaShared &sh
   }
 }
 
-// One lookahead window (or one redistribution pass) for entity group g, by the
-// calling WARP.  Adds the warp's results into the CTA accumulators.
-__device__ __forceinline__ void window_warp(const DevCfg &c, const WinState *Wg, WarpShared &ws,
-                                            CtaShared &sh, uint32_t g, uint32_t mbar_parity) {
-  const uint32_t lane = threadIdx.x & 31u;
-  const uint32_t slot0 = g << GE_SHIFT;
-  // ---- bulk copies that do not depend on the window: the group's entity
-  // states and its page cache row (arrival 1 of 2 on the warp's barrier)
-  if (lane == 0) {
-    mbar_arrive_expect_tx(&ws.mbar, (uint32_t)(GE * sizeof(EntityCore) + SIMIAN_BC_ROW * 4));
-    bulk_g2s(ws.core_s, c.core + slot0, (uint32_t)(GE * sizeof(EntityCore)), &ws.mbar);
-    bulk_g2s(ws.ax.pgc, c.bcache + (size_t)g * SIMIAN_BC_ROW, SIMIAN_BC_ROW * 4, &ws.mbar);
-#ifdef SIMIAN_PROFILE_PHASES
-    ws.t_last = clock64();
-#endif
-    ws.acc_min = SIMIAN_KEY_NONE;
-    ws.acc_max = 0;
-    ws.acc_committed = ws.acc_emitted = ws.acc_dropped = 0;
-    ws.acc_ties = ws.acc_dties = ws.acc_appended = 0;
-  }
-  // the window descriptor: nine 8-byte words
-  if (lane < 9)
-    reinterpret_cast<unsigned long long *>(&ws.W)[lane] =
-        reinterpret_cast<const unsigned long long *>(Wg)[lane];
-  __syncwarp();
-  const WinState &W = ws.W;
-  unsigned long long *cells = c.cell_state + (size_t)g * c.rows;
-  PHASE(0);
-
-  if (W.redist) {
-    if (lane == 0) {
-      mbar_arrive(&ws.mbar);
-      ws.ax.far_appends = ws.ax.page_allocs = ws.ax.pgc_take = ws.ax.pgc_have = 0;
+// K3 + K4 + trace chain for the m due events one pass collected into the
+// shared-memory slots (entities [e_lo, e_hi) of the block).  CTA-uniform.
+// `live`: bit u = slot (threadIdx.x + u * NTHREADS) holds a due event of this thread.
+__device__ __forceinline__ void process_pass(const DevCfg &c, WindowShared &sh, ThreadAcc &ta,
+                                             uint32_t slot0, uint32_t live, uint32_t e_lo,
+                                             uint32_t e_hi) {
+  const int tid = threadIdx.x;
+  const WinState &W = sh.W;
+  if (c.all_pure) {
+    // A1, one thread per EVENT: rank (kept in a register), tie check, trace word
+    uint32_t rkpack = 0; // EV_PER_THREAD ranks, 8 bits each
+#pragma unroll 1
+    for (int u = 0; u < EV_PER_THREAD; u++) {
+      uint32_t i = tid + u * NTHREADS;
+      if (live & (1u << u)) {
+        uint32_t r = rank_event(c, sh, ta, slot0, i);
+        if (r > 255u) set_error(c, SIMIAN_ERR_ENTITY_BURST);
+        rkpack |= (r & 255u) << (8 * u);
+      }
     }
-    __syncwarp();
-    uint32_t spins = 0;
-    while (!mbar_try_wait(&ws.mbar, mbar_parity))
-      if (++spins > (1u << 24)) {
-        set_error(c, SIMIAN_ERR_STALLED);
+    cp_async_wait_all(); // the entities' {count, hash} (link_due)
+    __syncthreads();
+    PHASE(3);
+    // A2 (K3), one thread per EVENT: handler; the sent record is staged in
+    // the consumed record's slot
+#pragma unroll 1
+    for (int u = 0; u < EV_PER_THREAD; u++) {
+      uint32_t i = tid + u * NTHREADS;
+      if (live & (1u << u)) run_event(c, sh, ta, slot0, i, (rkpack >> (8 * u)) & 255u);
+    }
+    PHASE(4); // (no barrier: phase B reads only the slots its own thread staged)
+    // B (K4), one thread per EVENT: append the staged records; the claims
+    // of all of a thread's events are in flight together
+    {
+      unsigned long long old[EV_PER_THREAD];
+      uint32_t cell[EV_PER_THREAD];
+#pragma unroll
+      for (int u = 0; u < EV_PER_THREAD; u++) {
+        uint32_t i = tid + u * NTHREADS;
+        cell[u] = SIMIAN_NONE;
+        if (live & (1u << u)) {
+          ulonglong2 a = sh.lo[i];
+          if ((uint32_t)a.y != SIMIAN_NONE)
+            cell[u] = cell_of_local(c, sh.ax, W.tb_clean, W.far_row,
+                                    __longlong_as_double((long long)a.x), (uint32_t)a.y);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < EV_PER_THREAD; u++)
+        if (cell[u] != SIMIAN_NONE) old[u] = atomicAdd(c.cell_state + cell[u], 1ull);
+      // C, one thread per entity, while the claims are in flight: fold the trace
+      // hash chain, publish the count (reads what phase A1 parked; A2 / B only
+      // touch the record slots)
+      for (uint32_t le = e_lo + tid; le < e_hi; le += NTHREADS) {
+        uint32_t f = sh.head[le];
+        if (f != LIST_END) chain_entity(c, sh, slot0 + le, le, f);
+      }
+      // Claims are serviced in two rounds so that no thread ever waits for a
+      // page while it still owes one: first every claim that landed in a
+      // page or must INSTALL one (never blocks); only then the claims that
+      // have to wait for another thread's install.  (Waiting first can
+      // deadlock: two threads holding crossed install/wait claims.)
+      uint32_t waiting = 0;
+#pragma unroll
+      for (int u = 0; u < EV_PER_THREAD; u++)
+        if (cell[u] != SIMIAN_NONE) {
+          if (CELL_COUNT(old[u]) <= (uint32_t)PAGE) { // lands in a page, or installs one
+            const RecBits r = slot_get(sh, tid + u * NTHREADS);
+            if ((uint32_t)old[u] < (uint32_t)PAGE)
+              st_rec(c.pool + ((size_t)(uint32_t)(old[u] >> 32) * PAGE + (uint32_t)old[u]), r);
+            else
+              cell_append_slow(c, sh.ax, W.alloc_limit, c.cell_state + cell[u], old[u], r.q0,
+                               r.q1, r.q2, r.q3);
+          } else {
+            waiting |= 1u << u;
+          }
+        }
+      if (waiting) { // rare
+#pragma unroll
+        for (int u = 0; u < EV_PER_THREAD; u++)
+          if (waiting & (1u << u)) {
+            const RecBits r = slot_get(sh, tid + u * NTHREADS);
+            cell_append_slow(c, sh.ax, W.alloc_limit, c.cell_state + cell[u], old[u], r.q0,
+                             r.q1, r.q2, r.q3);
+          }
+      }
+    }
+    PHASE(5);
+  } else {
+    cp_async_wait_all(); // the entities' {count, hash} (link_due)
+    __syncthreads();
+    // K3 + K4: stateful handlers, one thread per entity.  A separate
+    // accumulator keeps `ta` of the thread-per-event path in registers
+    // (process_entity is not inlined).
+    ThreadAcc t2;
+    thread_acc_init(t2);
+    for (uint32_t le = e_lo + tid; le < e_hi; le += NTHREADS) {
+      uint32_t f = sh.head[le];
+      if (f != LIST_END) process_entity(c, sh, t2, slot0 + le, f);
+    }
+    ta.min_key = t2.min_key < ta.min_key ? t2.min_key : ta.min_key;
+    ta.max_key = t2.max_key > ta.max_key ? t2.max_key : ta.max_key;
+    ta.committed += t2.committed;
+    ta.emitted += t2.emitted;
+    ta.dropped += t2.dropped;
+    ta.ties += t2.ties;
+    ta.dties += t2.dties;
+    ta.appended += t2.appended;
+  }
+}
+
+// per-thread accumulators -> the CTA's accumulators in shared memory (K1)
+__device__ __forceinline__ void accumulate_block(WindowShared &sh, const ThreadAcc &ta) {
+  unsigned long long mn = warp_min_u64(ta.min_key), mx = warp_max_u64(ta.max_key);
+  uint32_t s0 = __reduce_add_sync(0xffffffffu, ta.committed);
+  uint32_t s1 = __reduce_add_sync(0xffffffffu, ta.emitted);
+  uint32_t s2 = __reduce_add_sync(0xffffffffu, ta.dropped);
+  uint32_t s3 = __reduce_add_sync(0xffffffffu, ta.ties);
+  uint32_t s4 = __reduce_add_sync(0xffffffffu, ta.dties);
+  uint32_t s5 = __reduce_add_sync(0xffffffffu, ta.appended);
+  if ((threadIdx.x & 31) == 0) {
+    if (mn != SIMIAN_KEY_NONE) atomicMin(&sh.min_key, mn);
+    if (mx) atomicMax(&sh.max_key, mx);
+    if (s0) atomicAdd(&sh.committed, s0);
+    if (s1) atomicAdd(&sh.emitted, s1);
+    if (s2) atomicAdd(&sh.dropped, s2);
+    if (s3) atomicAdd(&sh.ties, s3);
+    if (s4) atomicAdd(&sh.dties, s4);
+    if (s5) atomicAdd(&sh.appended, s5);
+  }
+}
+
+// slots [0, m) are all live: this thread's mask
+__device__ __forceinline__ uint32_t live_below(uint32_t m) {
+  uint32_t live = 0;
+#pragma unroll
+  for (int u = 0; u < EV_PER_THREAD; u++)
+    if (threadIdx.x + u * NTHREADS < m) live |= 1u << u;
+  return live;
+}
+
+// The uncommon path of a window: the pages of its rows hold more records than
+// the CTA has slots.  A filtered scan gives slots to the DUE records only; when
+// even those overflow (bursts such as the 16 events per entity all scheduled at
+// t = 0) they are partitioned into scratch pages by entity sub-range
+// (partition_burst) -- or, when the page list has no room, the entity range is
+// split and the same pages are re-scanned -- and the sub-ranges are processed
+// one pass each.  Kept out of line, with its own accumulators, so that the
+// common single-pass window pays nothing for it.
+__device__ __noinline__ void filtered_passes(const DevCfg &c, WindowShared &sh, uint32_t slot0,
+                                             uint32_t npg_scan) {
+  const int tid = threadIdx.x;
+  ThreadAcc ta;
+  thread_acc_init(ta);
+  collect_due(c, sh, ta, slot0, 0, npg_scan, 0, c.epb, true);
+  __syncthreads();
+  const uint32_t m0 = sh.total;
+  uint32_t m = m0, e_lo = 0, e_hi = c.epb, pg_lo = 0, pg_hi = npg_scan;
+  bool part_ok = false;
+  if (m0 > NREFS) part_ok = partition_burst(c, sh, slot0, npg_scan);
+#pragma unroll 1
+  for (;;) {
+    if (m > NREFS && !part_ok) { // split the entity range and re-scan the same pages
+      if (e_hi - e_lo <= 1) {
+        if (tid == 0) set_error(c, SIMIAN_ERR_ENTITY_BURST);
         break;
       }
-    // (the page cache is not used by a redistribution pass: pages come from the ring)
-    redistribute_group(c, ws, g);
-  } else {
-    // ---- K2a: this lane's cell of the window: row tb_lo + lane.  Row tb_hi may
-    // be appended to during this launch (see SIMIAN_TIME_DEAD); the rows below
-    // it are recycled after this window.
-    const int ncell = (int)(W.tb_hi - W.tb_lo + 1);
-    unsigned long long hw = CELL_EMPTY;
-    uint32_t free_flag = 0;
-    if ((int)lane < ncell) {
-      const long long tb = W.tb_lo + lane;
-      hw = ld_cg64(cells + (uint32_t)(tb & (long long)c.ring_mask));
-      free_flag = tb == W.tb_hi ? 0u : PG_FREE_FLAG;
-    }
-    Cursor cur = cursor_of_head(hw);
-    uint32_t npg, nvalid;
-    const bool complete = list_chunk(c, ws, cur, free_flag, npg, nvalid);
-    PHASE(1);
-    const bool fast = complete && nvalid <= (uint32_t)NSLOT;
-    // ---- K2: one bulk copy per listed page into the slots (arrival 2 of 2)
-    if (lane == 0) {
-      if (fast && nvalid)
-        mbar_arrive_expect_tx(&ws.mbar, nvalid * 32u);
-      else
-        mbar_arrive(&ws.mbar);
-    }
-    __syncwarp();
-    if (fast)
-      for (uint32_t i = lane; i < npg; i += 32) {
-        const uint32_t n = PG_COUNT(ws.pg_cnt[i]);
-        if (n)
-          bulk_g2s(&ws.slots[ws.pg_off[i]], c.pool + (size_t)ws.pg_id[i] * PAGE, n * 32u,
-                   &ws.mbar);
-      }
-    {
-      uint32_t spins = 0;
-      while (!mbar_try_wait(&ws.mbar, mbar_parity))
-        if (++spins > (1u << 24)) { // never legitimately: fail, do not hang
-          set_error(c, SIMIAN_ERR_STALLED);
-          break;
+      __syncthreads();
+      if (tid == 0) {
+        uint32_t parts = m / (NREFS * 3u / 4u) + 1u, span = e_hi - e_lo;
+        if (parts > span) parts = span;
+        if (parts > 16u) parts = 16u;
+        if (sh.stack_n + parts > RSTACK_MAX) parts = 2;
+        for (uint32_t q = parts; q-- > 0;) { // lowest sub-range on top of the stack
+          uint32_t *st = &sh.rstack[4 * sh.stack_n];
+          st[0] = e_lo + (uint32_t)((unsigned long long)span * q / parts);
+          st[1] = e_lo + (uint32_t)((unsigned long long)span * (q + 1) / parts);
+          st[2] = pg_lo;
+          st[3] = pg_hi;
+          sh.stack_n++;
         }
-    }
-    if (lane == 0) {
-      ws.ax.far_appends = ws.ax.page_allocs = ws.ax.pgc_take = 0;
-      ws.ax.pgc_have = ws.ax.pgc[SIMIAN_BC];
-    }
-    __syncwarp();
-    PHASE(2);
-    if (nvalid == 0 && complete) {
-      // nothing in the window's rows for this group
-    } else if (fast) {
-      warp_pass(c, ws, slot0, nvalid, 0, GE, true);
-    } else {
-      slow_passes<false>(c, ws, slot0, hw, free_flag, complete, npg, 0u);
-    }
-    __syncwarp();
-    // ---- recycle: the pages of rows [tb_lo, tb_hi) go onto the group's own
-    // page stack in HBM (what does not fit: to the global ring), heads are
-    // cleared.  The entries below the ones popped in this launch stay where they
-    // are, the recycled pages are written above them.
-    {
-      uint32_t *stack = c.bcache + (size_t)g * SIMIAN_BC_ROW;
-      const uint32_t have = ws.ax.pgc_have, take = ws.ax.pgc_take;
-      uint32_t height = have - (take < have ? take : have);
-      if (complete) {
-        // (a slow window whose list was complete still holds it: npg of the first listing)
-        recycle_chunk(c, ws, stack, npg, height);
-      } else {
-        Cursor k2 = cursor_of_head(hw);
-        bool done;
-#pragma unroll 1
-        do {
-          uint32_t n2, nv2;
-          done = list_chunk(c, ws, k2, free_flag, n2, nv2);
-          recycle_chunk(c, ws, stack, n2, height);
-        } while (!done);
       }
-      if ((int)lane < ncell - 1) {
-        const long long tb = W.tb_lo + lane;
-        cells[(uint32_t)(tb & (long long)c.ring_mask)] = CELL_EMPTY;
-      }
-      // rows the window jumped over (dead records only)
-      long long nskip = W.tb_lo - W.tb_clean;
-      if (nskip > (long long)c.ring) nskip = c.ring;
-      for (long long i = lane; i < nskip; i += 32) {
-        const long long tb = W.tb_clean + i;
-        free_cell(c, cells + (uint32_t)(tb & (long long)c.ring_mask), false);
-      }
-      // low stack: take pages from the ring for the next window (one atomic)
-      if (height < (uint32_t)SIMIAN_BC_LOW) {
-        const uint32_t need = (uint32_t)SIMIAN_BC_FILL - height;
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(&c.acc->alloc_head, (unsigned long long)need);
-        base = __shfl_sync(FULL, base, 0);
-        // ring slots beyond alloc_limit are not valid yet: take only what is
-        const unsigned long long lim = W.alloc_limit;
-        const uint32_t okn =
-            base >= lim ? 0u : (lim - base < need ? (uint32_t)(lim - base) : need);
-        if (lane < okn) {
-          const uint32_t p = c.free_ring[(base + lane) % c.n_pages];
-          if (base + lane < c.n_pages) scrub_page(c, p); // first lap of the ring
-          stack[height + lane] = p;
-        }
-        if (lane == 0 && okn < need)
-          atomicAdd(&c.acc->leaked_pages, (unsigned long long)(need - okn));
-        height += okn;
-      }
-      if (lane == 0) stack[SIMIAN_BC] = height;
+    } else if (m && m <= NREFS) {
+      process_pass(c, sh, ta, slot0, live_below(m), e_lo, e_hi);
     }
-    PHASE(7);
+    part_ok = false; // only the first (whole-block) overflow is partitioned
+    __syncthreads();
+    if (sh.stack_n == 0) break;
+    __syncthreads();
+    if (tid == 0) {
+      sh.stack_n--;
+      sh.pass_lo = sh.rstack[4 * sh.stack_n];
+      sh.pass_hi = sh.rstack[4 * sh.stack_n + 1];
+      sh.pass_pg_lo = sh.rstack[4 * sh.stack_n + 2];
+      sh.pass_pg_hi = sh.rstack[4 * sh.stack_n + 3];
+      sh.total = 0;
+    }
+    for (uint32_t i = tid; i < c.epb; i += NTHREADS) sh.head[i] = LIST_END;
+    __syncthreads();
+    e_lo = sh.pass_lo, e_hi = sh.pass_hi;
+    pg_lo = sh.pass_pg_lo, pg_hi = sh.pass_pg_hi;
+    collect_due(c, sh, ta, slot0, pg_lo, pg_hi, e_lo, e_hi, false);
+    __syncthreads();
+    m = sh.total;
   }
-
-  // ---- K1: the warp's results -> the CTA's accumulators
-  __syncwarp();
-  if (lane == 0) {
-    if (ws.acc_min != SIMIAN_KEY_NONE) atomicMin(&sh.min_key, ws.acc_min);
-    if (ws.acc_max) atomicMax(&sh.max_key, ws.acc_max);
-    if (ws.acc_committed) atomicAdd(&sh.committed, ws.acc_committed);
-    if (ws.acc_emitted) atomicAdd(&sh.emitted, ws.acc_emitted);
-    if (ws.acc_dropped) atomicAdd(&sh.dropped, ws.acc_dropped);
-    if (ws.acc_ties) atomicAdd(&sh.ties, ws.acc_ties);
-    if (ws.acc_dties) atomicAdd(&sh.dties, ws.acc_dties);
-    if (ws.acc_appended) atomicAdd(&sh.appended, ws.acc_appended);
-    if (ws.ax.far_appends) atomicAdd(&sh.far_appends, ws.ax.far_appends);
-    if (ws.ax.page_allocs) atomicAdd(&sh.page_allocs, ws.ax.page_allocs);
-  }
-  PHASE(8);
+  accumulate_block(sh, ta);
 }
 
-__device__ __forceinline__ void cta_acc_reset(CtaShared &sh) {
-  sh.min_key = SIMIAN_KEY_NONE;
-  sh.max_key = 0;
-  sh.committed = sh.emitted = sh.dropped = sh.ties = sh.dties = sh.appended = 0;
-  sh.far_appends = sh.page_allocs = 0;
-  sh.is_last = 0;
-}
-
-// the CTA's accumulators -> its BlockPart slot: one thread per field,
-// independent, result-less atomics
-__device__ __forceinline__ void cta_acc_flush(const DevCfg &c, CtaShared &sh, uint32_t tid) {
-  if (tid < 10) {
-    BlockPart *p = &c.part[blockIdx.x % SIMIAN_PART_SLOTS];
-    switch (tid) {
-      case 0: if (sh.min_key != SIMIAN_KEY_NONE) atomicMin(&p->min_key, sh.min_key); break;
-      case 1: if (sh.max_key) atomicMax(&p->max_key, sh.max_key); break;
-      case 2: if (sh.committed) atomicAdd(&p->committed, sh.committed); break;
-      case 3: if (sh.emitted) atomicAdd(&p->emitted, sh.emitted); break;
-      case 4: if (sh.dropped) atomicAdd(&p->dropped, sh.dropped); break;
-      case 5: if (sh.ties) atomicAdd(&p->ties, sh.ties); break;
-      case 6: if (sh.dties) atomicAdd(&p->dties, sh.dties); break;
-      case 7: if (sh.appended) atomicAdd(&p->appended, sh.appended); break;
-      case 8: if (sh.far_appends) atomicAdd(&p->far_appends, sh.far_appends); break;
-      default: if (sh.page_allocs) atomicAdd(&p->page_allocs, sh.page_allocs); break;
-    }
-  }
-}
-
-// the step after the last CTA of a window: this rank's next window (size == 1)
-__device__ void advance_single(const DevCfg &c, const WinState &W, CtaShared &sh, uint32_t win_ix) {
-  reduce_parts(c, sh);
-  WinState *Wn = &c.win[(win_ix + 1u) & 1u];
-  if (W.redist) {
-    setup_next_window(c, W, Wn, W.gmin, 0.0, true, sh.nw);
-  } else {
-    unsigned long long cand, far;
-    local_min_candidate(c, W, sh, cand, far);
-    double gmin = cand == SIMIAN_KEY_NONE ? c.inf_time : simian_key_time(cand); // simian.js:147
-    double farT = far == SIMIAN_KEY_NONE ? __longlong_as_double(0x7FF0000000000000LL)
-                                         : simian_key_time(far);
-    setup_next_window(c, W, Wn, gmin, farT, false, sh.nw);
-  }
-}
-
-// One lookahead window (or one redistribution pass): warp w of CTA b owns
-// entity group b * wpc + w (wpc = blockDim.x / 32).
+// One lookahead window (or one redistribution pass) for entity block blockIdx.x.
 // fuse_advance: 1 (size == 1): the last CTA to finish computes window k+1;
 // 2 / 3 (size > 1): the last CTA computes this rank's LBTS candidate (3: and
 // publishes it to the peers' exchange slots); 0: neither.
-__global__ void __launch_bounds__(SIMIAN_THREADS, SIMIAN_MINBLOCKS)
+__global__ void __launch_bounds__(NTHREADS, SIMIAN_MINBLOCKS)
     k_window(const __grid_constant__ DevCfg c, uint32_t win_ix, int fuse_advance) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, wpc = blockDim.x >> 5;
-  WarpShared &ws = reinterpret_cast<WarpShared *>(smem_raw)[warp];
-  CtaShared &sh = *reinterpret_cast<CtaShared *>(smem_raw + (size_t)wpc * sizeof(WarpShared));
-  // the warp's copy barrier: two arrivals per window (state + cache, records)
-  if (lane == 0) mbar_init(&ws.mbar, 2u);
-  if (tid == 0) cta_acc_reset(sh);
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  WindowShared &sh = *reinterpret_cast<WindowShared *>(smem_raw);
+  const int tid = threadIdx.x;
+  const uint32_t b = blockIdx.x;
   // Programmatic dependent launch: every resident CTA of the previous window
   // has started, so this grid's CTAs may take the SM slots that launch's last
   // wave frees -- and wait here until it has completed and its writes are
@@ -2279,12 +1865,170 @@ __global__ void __launch_bounds__(SIMIAN_THREADS, SIMIAN_MINBLOCKS)
   const WinState *Wg = &c.win[win_ix & 1u];
   if (Wg->done) return; // simian.js:119: enqueued past the end of the run
   if (tid == 0) sh.found = ld_cg(&c.acc->error);
+  // the block's own free pages (written by this block's CTA of the previous launch)
+  if (tid < SIMIAN_BC) sh.ax.pgc[tid] = c.bcache[(size_t)b * SIMIAN_BC + tid];
+  if (tid == 0) {
+    sh.t_last = clock64();
+    sh.W = *Wg;
+    sh.min_key = SIMIAN_KEY_NONE;
+    sh.max_key = 0;
+    sh.committed = sh.emitted = sh.dropped = sh.ties = sh.dties = sh.appended = 0;
+    sh.npg = 0;
+    sh.nvalid = 0;
+    sh.nfree = 0;
+    sh.free_pos = 0;
+    sh.is_last = 0;
+    sh.ax.far_appends = sh.ax.page_allocs = sh.ax.pgc_take = 0;
+    sh.ax.pgc_have = c.bcount[b];
+  }
   __syncthreads();
   if (sh.found) return; // sticky error: CTA-uniform exit
-  const uint32_t g = blockIdx.x * wpc + warp;
-  if (g < c.n_groups) window_warp(c, Wg, ws, sh, g, 0u);
+  const WinState &W = sh.W;
+  PHASE(0);
+
+  ThreadAcc ta;
+  thread_acc_init(ta);
+  uint32_t npg = 0;
+  int ncell = 0;
+
+  if (W.redist) {
+    redistribute_block(c, sh, b);
+  } else {
+    // ---- K2a: list the pages of this block's cells in rows [tb_lo, tb_hi]
+    ncell = (int)(W.tb_hi - W.tb_lo + 1);
+    if (tid < ncell) {
+      long long tb = W.tb_lo + tid;
+      uint32_t cell = (uint32_t)(tb & (long long)c.ring_mask) * c.n_blocks + b;
+      // row tb_hi may be appended to during this launch: use the snapshot; rows
+      // fully below the bound are recycled after this window
+      unsigned long long hw = (tb == W.tb_hi) ? c.snap[b] : c.cell_state[cell];
+      list_cell_pages(c, sh, (uint32_t)(hw >> 32), (uint32_t)hw,
+                      (tb == W.tb_hi) ? 0u : PG_FREE_FLAG);
+    }
+    // set-up of the first (normally only) pass, under the same barrier
+    for (uint32_t i = tid; i < c.epb; i += NTHREADS) sh.head[i] = LIST_END;
+    if (tid >= NTHREADS - NBINS) sh.hist[tid - (NTHREADS - NBINS)] = 0;
+    if (tid == NTHREADS - 1) {
+      sh.total = 0;
+      sh.stack_n = 0;
+      sh.pass_lo = 0;
+      sh.pass_hi = c.epb;
+      sh.pass_pg_lo = 0; // (pass_pg_hi of the first pass = the number of listed pages)
+      // histogram bin = entity >> bin_shift: the smallest power of two that
+      // covers the block with NBINS bins
+      uint32_t sft = 0;
+      while (((c.epb - 1u) >> sft) >= (uint32_t)NBINS) sft++;
+      sh.bin_shift = sft;
+    }
+    __syncthreads();
+    PHASE(1);
+    npg = sh.npg;
+    if (npg > PGMAX) {
+      if (tid == 0) set_error(c, SIMIAN_ERR_WINDOW_OVERFLOW);
+      npg = 0;
+    }
+    // ---- K2..K4: normally ONE pass over the whole block.  A window whose due
+    // events overflow the shared-memory slots (bursts such as the 16 events per
+    // entity at t = 0) takes the out-of-line multi-pass path.
+    const uint32_t slot0 = b * c.epb;
+    const uint32_t nvalid = sh.nvalid;
+    if (nvalid == 0) {
+      // nothing in the window's rows for this block
+    } else if (nvalid <= NREFS) {
+      // all records of the window's pages fit the slots: one bulk copy, then
+      // every thread links the due ones among its slots
+      collect_all(c, sh, npg);
+      __syncthreads();
+      const uint32_t live = link_due(c, sh, ta, slot0, nvalid);
+      __syncthreads();
+      PHASE(2);
+      process_pass(c, sh, ta, slot0, live, 0, c.epb);
+    } else {
+      filtered_passes(c, sh, slot0, npg);
+      npg = sh.npg; // scratch pages of a partition are recycled with the others
+      if (npg > PGMAX) npg = 0;
+    }
+    PHASE(6);
+  }
   __syncthreads();
-  cta_acc_flush(c, sh, tid);
+  // ---- recycle: the pages of rows [tb_clean, tb_hi) go onto the block's own
+  // page stack (what does not fit: to the global ring), heads are cleared.  The
+  // stack lives in HBM (bcache[b]); the entries below the ones popped in this
+  // launch stay where they are, the recycled pages are written above them.
+  {
+    const uint32_t have = sh.ax.pgc_have;
+    const uint32_t rem = have - (sh.ax.pgc_take < have ? sh.ax.pgc_take : have);
+    const uint32_t nfree = W.redist ? 0u : sh.nfree;       // counted while the pages were listed
+    const uint32_t room = SIMIAN_BC - rem;                 // free pages the stack still takes
+    const uint32_t over = nfree > room ? nfree - room : 0; // the rest goes to the ring
+    uint32_t cnt = rem + (nfree - over);                   // stack height after recycling
+    // low stack: take pages from the ring for the next window (one atomic)
+    const uint32_t need = (cnt < SIMIAN_BC_LOW) ? SIMIAN_BC_FILL - cnt : 0u;
+    if (over || need) {
+      if (tid == 0) {
+        if (over) sh.free_base = atomicAdd(&c.acc->free_tail, (unsigned long long)over);
+        if (need) sh.ring_base = atomicAdd(&c.acc->alloc_head, (unsigned long long)need);
+      }
+      __syncthreads();
+    }
+    if (!W.redist) {
+      uint32_t *stack = c.bcache + (size_t)b * SIMIAN_BC;
+      for (uint32_t i = tid; i < npg; i += NTHREADS)
+        if (sh.pg_cnt[i] & PG_FREE_FLAG) {
+          const uint32_t k = atomicAdd(&sh.free_pos, 1u);
+          if (k < nfree - over)
+            stack[rem + k] = sh.pg_id[i];
+          else if (k < nfree)
+            c.free_ring[(sh.free_base + (k - (nfree - over))) % c.n_pages] = sh.pg_id[i];
+        }
+      if (tid < ncell - 1) {
+        long long tb = W.tb_lo + tid;
+        c.cell_state[(uint32_t)(tb & (long long)c.ring_mask) * c.n_blocks + b] = CELL_EMPTY;
+      }
+      // rows the window jumped over (dead records only)
+      long long nskip = W.tb_lo - W.tb_clean;
+      if (nskip > (long long)c.ring) nskip = c.ring;
+      for (long long i = tid; i < nskip; i += NTHREADS) {
+        long long tb = W.tb_clean + i;
+        if (tb >= W.tb_lo) break;
+        free_cell(c, (uint32_t)(tb & (long long)c.ring_mask) * c.n_blocks + b);
+      }
+    }
+    if (need) {
+      // ring slots beyond alloc_limit are not valid yet: take only what is
+      unsigned long long lim = W.alloc_limit, base = sh.ring_base;
+      uint32_t okn = base >= lim ? 0u : (lim - base < need ? (uint32_t)(lim - base) : need);
+      if ((uint32_t)tid < okn)
+        c.bcache[(size_t)b * SIMIAN_BC + cnt + tid] = c.free_ring[(base + tid) % c.n_pages];
+      if (tid == 0 && okn < need)
+        atomicAdd(&c.acc->leaked_pages, (unsigned long long)(need - okn));
+      cnt += okn;
+    }
+    if (tid == 0) c.bcount[b] = cnt;
+  }
+
+  PHASE(7);
+  // ---- K1: CTA reduction of the accumulators into this CTA's BlockPart
+  {
+    accumulate_block(sh, ta);
+  }
+  __syncthreads();
+  if (tid < 10) { // one thread per field: independent, result-less atomics
+    BlockPart *p = &c.part[b % SIMIAN_PART_SLOTS];
+    switch (tid) {
+      case 0: if (sh.min_key != SIMIAN_KEY_NONE) atomicMin(&p->min_key, sh.min_key); break;
+      case 1: if (sh.max_key) atomicMax(&p->max_key, sh.max_key); break;
+      case 2: if (sh.committed) atomicAdd(&p->committed, sh.committed); break;
+      case 3: if (sh.emitted) atomicAdd(&p->emitted, sh.emitted); break;
+      case 4: if (sh.dropped) atomicAdd(&p->dropped, sh.dropped); break;
+      case 5: if (sh.ties) atomicAdd(&p->ties, sh.ties); break;
+      case 6: if (sh.dties) atomicAdd(&p->dties, sh.dties); break;
+      case 7: if (sh.appended) atomicAdd(&p->appended, sh.appended); break;
+      case 8: if (sh.ax.far_appends) atomicAdd(&p->far_appends, sh.ax.far_appends); break;
+      default: if (sh.ax.page_allocs) atomicAdd(&p->page_allocs, sh.ax.page_allocs); break;
+    }
+  }
+  PHASE(8);
   if (!fuse_advance) return;
   // ---- last CTA computes the next window (simian.js:147)
   __threadfence();
@@ -2293,25 +2037,35 @@ __global__ void __launch_bounds__(SIMIAN_THREADS, SIMIAN_MINBLOCKS)
   __syncthreads();
   if (!sh.is_last) return;
   __threadfence();
-  const WinState W = *Wg;
   if (fuse_advance >= 2) {
     lbts_candidate(c, W, sh, win_ix, fuse_advance == 3);
     return;
   }
-  advance_single(c, W, sh, win_ix);
+  reduce_parts(c, sh);
+  WinState *Wn = &c.win[(win_ix + 1u) & 1u];
+  if (W.redist) {
+    setup_next_window(c, W, Wn, W.gmin, 0.0, true);
+  } else {
+    unsigned long long cand, far;
+    local_min_candidate(c, W, sh, cand, far);
+    double gmin = cand == SIMIAN_KEY_NONE ? c.inf_time : simian_key_time(cand); // simian.js:147
+    double farT = far == SIMIAN_KEY_NONE ? __longlong_as_double(0x7FF0000000000000LL)
+                                         : simian_key_time(far);
+    setup_next_window(c, W, Wn, gmin, farT, false);
+  }
+  PHASE(9);
 }
 
-__global__ void __launch_bounds__(SIMIAN_THREADS) k_local_min(const __grid_constant__ DevCfg c, uint32_t win_ix,
-                                                            int publish) {
-  __shared__ CtaShared sh;
-  const WinState W = c.win[win_ix & 1u];
-  lbts_candidate(c, W, sh, win_ix, publish);
+__global__ void __launch_bounds__(NTHREADS) k_local_min(const __grid_constant__ DevCfg c, uint32_t win_ix,
+                                                        int publish) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  WindowShared &sh = *reinterpret_cast<WindowShared *>(smem_raw);
+  lbts_candidate(c, c.win[win_ix & 1u], sh, win_ix, publish);
 }
 
 // size > 1: consume the allreduced {globalMinLeft, min far} (simian.js:144)
-__global__ void __launch_bounds__(SIMIAN_THREADS) k_advance(const __grid_constant__ DevCfg c, uint32_t win_ix,
-                                                          int from_xch) {
-  __shared__ WinState nw;
+__global__ void __launch_bounds__(NTHREADS) k_advance(const __grid_constant__ DevCfg c, uint32_t win_ix,
+                                                      int from_xch) {
   const WinState W = c.win[win_ix & 1u];
   WinState *Wn = &c.win[(win_ix + 1u) & 1u];
   if (W.done) {
@@ -2330,9 +2084,9 @@ __global__ void __launch_bounds__(SIMIAN_THREADS) k_advance(const __grid_constan
     }
   }
   if (W.redist)
-    setup_next_window(c, W, Wn, W.gmin, 0.0, true, nw);
+    setup_next_window(c, W, Wn, W.gmin, 0.0, true);
   else
-    setup_next_window(c, W, Wn, g0, g1, false, nw);
+    setup_next_window(c, W, Wn, g0, g1, false);
   // The outbox the NEXT window fills was sent two windows ago; every peer has
   // read it (its pull precedes the allreduce this advance follows).  The one
   // just sent may still be being read: it is left alone.
@@ -2341,9 +2095,9 @@ __global__ void __launch_bounds__(SIMIAN_THREADS) k_advance(const __grid_constan
 }
 
 // first window: gmin = startTime even when the queue is empty (simian.js:118)
-__global__ void __launch_bounds__(SIMIAN_THREADS) k_begin(const __grid_constant__ DevCfg c) {
+__global__ void __launch_bounds__(NTHREADS) k_begin(const __grid_constant__ DevCfg c) {
   WinState W = c.win[0];
-  __shared__ WinState w0, nw;
+  __shared__ WinState w0;
   if (threadIdx.x == 0) {
     w0 = W;
     w0.tb_hi = w0.tb_clean; // nothing recycled yet
@@ -2355,7 +2109,7 @@ __global__ void __launch_bounds__(SIMIAN_THREADS) k_begin(const __grid_constant_
   // first window's exchange: only this rank's candidate covers it
   const unsigned long long keep_min = c.acc->min_key;
   setup_next_window(c, w0, &c.win[0], c.start, far == SIMIAN_KEY_NONE ? inf : simian_key_time(far),
-                    false, nw);
+                    false);
   if (threadIdx.x == 0) {
     c.acc->windows = 0;
     c.acc->window_index = 0;
@@ -2375,6 +2129,7 @@ __global__ void k_gather_core(const __grid_constant__ DevCfg c, uint32_t slot_ba
     out[j] = which ? st.hash : st.count;
   }
 }
+
 
 // digest = sum of simian_digest_term over local entities; state checksum
 __global__ void k_digest(const __grid_constant__ DevCfg c, unsigned long long *out /* [2] */) {

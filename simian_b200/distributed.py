@@ -272,6 +272,49 @@ def drive_windows_loopback(ranks, max_windows=None):
     return out
 
 
+def drive_windows_p2p_loopback(engines, device, batch=8, max_batch=64):
+    """drive_windows_p2p for ALL ranks of a world inside ONE process on ONE
+    device: the same three kernels per rank and window -- k_window (fused LBTS
+    candidate, published into every peer's exchange slots), k_pull (flags, then
+    the peers' outboxes -> calendar), k_advance (minimum over the slots) -- with
+    the peers wired by plain device pointers (simian_connect_local) instead of
+    CUDA IPC.  Everything runs on ONE stream, phase by phase over the ranks, so
+    every flag a k_pull waits for was written by a kernel that has already
+    completed: no kernel ever waits for a kernel that has not run.  This is how
+    the device-driven exchange is covered by a one-GPU test run."""
+    size = len(engines)
+    stream = torch.cuda.current_stream(device).cuda_stream
+    for e in engines:
+        e.set_stream(stream)
+    for r, e in enumerate(engines):
+        for p, pe in enumerate(engines):
+            if p != r:
+                e.connect_local(p, pe)
+    for e in engines:
+        e.run_begin()
+    windows = 0
+    while True:
+        for _ in range(batch):
+            for e in engines:
+                e.window_process_lbts(True)    # k_window + candidate + publish
+            for e in engines:
+                e.window_pull(True)            # all flags are already there
+            for e in engines:
+                e.window_advance_async(True)
+            windows += 1
+        dones = [e.poll() for e in engines]
+        if all(dones):
+            break
+        assert not any(dones), "the window sequence is global: ranks end together"
+        batch = min(2 * batch, max_batch)
+    out = []
+    for e in engines:
+        st = e.run_end()
+        st["driver_windows"] = windows
+        out.append(st)
+    return out
+
+
 def run_distributed_phold(cfg, rank, world, local_rank, seed=1, driver="p2p",
                           **options):
     """One PHOLD step on `world` GPUs (one process each); returns this rank's

@@ -59,6 +59,16 @@ def test_no_cpu_fallback(built):
     assert ei.value.code == 14 and "no CPU fallback" in str(ei.value)
 
 
+def test_world_larger_than_the_peer_tables_is_refused(built):
+    """size > SIMIAN_MAX_RANKS (16) would overrun the engine's peer tables
+    (include/simian_b200.h documents the limit): refused at create, GPU or not"""
+    with pytest.raises(built.SimianError) as ei:
+        built.Engine("x", 0.0, 1.0, 0.1, rank=0, size=17)
+    assert "SIMIAN_MAX_RANKS" in str(ei.value)
+    with pytest.raises(built.SimianError):
+        built.Engine("x", 0.0, 1.0, 0.1, rank=3, size=2)
+
+
 def test_hash_name_matches_hash_js(built):
     assert built.lib().simian_hash_name(b"Node") == 6385183179.0
 

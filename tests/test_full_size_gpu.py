@@ -1,7 +1,10 @@
 """-m gpu: BASELINE config 2 at its FULL size (2^20 entities x 16 events, 1.7e8
-committed events), where the oracle would take minutes: size-independent
-properties instead of a record-by-record comparison.
+committed events): the full run against the oracle (its ranks on the host's
+threads: seconds), and size-independent properties.
 
+  * the oracle itself: per-entity committed counts and order-sensitive trace
+    hashes of all 2^20 entities, digest, window count, emitted / dropped / tie
+    counts, f64 final time -- bit for bit;
   * a checksum of checksums: the digest the device reduces equals the sum of
     simian_digest_term over the per-entity counts and trace hashes read back,
     recomputed here (include/simian_spec.h, transcribed to numpy);
@@ -67,6 +70,32 @@ def test_digest_is_the_checksum_of_the_per_entity_checksums(full):
     assert st["total_events"] > 1.6e8
     assert int(counts.sum()) == st["total_events"]
     assert digest_of(counts, hashes) == st["digest"]
+
+
+def test_full_size_against_the_oracle(full, oracle_mod):
+    """config 2 at BASELINE's own size against the CPU restatement of the
+    reference algorithm (one rank per host thread, proven equal to the
+    sequential oracle in test_oracle.py): every entity, bit for bit"""
+    import os
+    cfg, (st, counts, hashes) = full
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    cores = max(1, min(cores, 32))
+    o = oracle_mod.Oracle("full", 0.0, cfg["end"], cfg["min_delay"], size=cores, seed=1,
+                          threads=cores)
+    build_phold(o, cfg["n"], cfg["per_entity"], cfg["lookahead"], cfg["p_remote"], 1.0,
+                cfg["mode"], cfg["groups"])
+    so = o.run()
+    co, ho = o.read_counts("Node", cfg["n"]), o.read_trace_hashes("Node", cfg["n"])
+    o.close()
+    assert so["distinguishable_ties"] == 0 and st["distinguishable_ties"] == 0
+    for k in ("total_events", "windows", "digest", "emitted", "dropped_past_end", "ties"):
+        assert st[k] == so[k], k
+    assert float(st["last_time"]).hex() == float(so["last_time"]).hex()
+    np.testing.assert_array_equal(counts, co)
+    np.testing.assert_array_equal(hashes, ho)
 
 
 def test_event_conservation(full):

@@ -97,6 +97,43 @@ def test_cuda_ranks_share_one_gpu(name, world, oracle_mod):
     _check(world, stats, results, owners, ref)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 3, 4, 8])
+@pytest.mark.parametrize("name", ["ross", "other_group", "uniform_sparse", "lanl", "hello"])
+def test_device_driven_exchange_all_ranks_on_one_gpu(name, world, oracle_mod):
+    """The data plane the multi-GPU numbers come from -- k_window(fuse = 3: LBTS
+    candidate published into the peers' exchange slots) -> k_pull (flags, then
+    the peers' outboxes) -> k_advance(minimum over the slots) -- with every rank
+    of a 2/3/4/8-rank world on ONE device (drive_windows_p2p_loopback: peers wired
+    by device pointers, one stream).  Bit-exact per-entity counts and trace hashes
+    against a single-rank oracle run."""
+    import torch
+    from simian_b200 import capi
+    from simian_b200.distributed import drive_windows_p2p_loopback
+    c = CASES[name]
+    end, min_delay, classes, tie_mode = shape(c)
+    ref = _reference(oracle_mod, c, world)
+    opts = {"bucket_width": 1.0 / 32} if min_delay < 0.05 else {}
+    if c.get("kind") == "hello":
+        opts = {"bucket_width": 1.0}
+    engines = []
+    for rank in range(world):
+        e = capi.Engine("p2p", 0.0, end, min_delay, rank=rank, size=world, device=0,
+                        seed=c["seed"], **opts)
+        build(e, c, world)
+        engines.append(e)
+    stats = drive_windows_p2p_loopback(engines, torch.device("cuda", 0))
+    results, owners = [], []
+    for rank, e in enumerate(engines):
+        assert stats[rank]["error"] == 0
+        results.append(read_all(e, classes))
+        owners.append(np.concatenate([(e.base_rank(k) + np.arange(n)) % world == rank
+                                      for k, n in classes]))
+    for e in engines:
+        e.close()
+    _check(world, stats, results, owners, ref)
+
+
 # ---- a model script's own getBaseRank (simian.js:192-194) ------------------------
 
 def _owners_with_base(classes, bases, world):

@@ -119,6 +119,43 @@ def test_empty_run_and_end_time_zero_events(oracle_mod):
     assert o.run()["windows"] == 1
 
 
+def test_bad_model_parameters_are_errors_not_memory_faults():
+    """a parameter blob shorter than the attached device function reads, an
+    out-of-range destination the handler computes, PHOLD groups < 2: the
+    reference throws inside the handler; here they are engine errors"""
+    from simian_b200 import capi
+    from simian_b200.workloads import phold_params_blob
+    e = capi.Engine("short", 0.0, 1.0, 0.1)
+    e.define_class("Node", 0)
+    e.add_entities("Node", 0, 64)
+    e.attach_service("Node", "generate", "phold_generate")
+    e.set_class_params("Node", phold_params_blob(0, 64, 0.1, 1.0, 0.1, 1, 1)[:16])
+    e.sched_service_bulk(0.0, "generate", 0, "Node", 0, 64, 1)
+    with pytest.raises(capi.SimianError) as ei:
+        e.run()
+    assert ei.value.code == 6
+    # destinations beyond the entities that exist: n_entities overstated
+    e = capi.Engine("range", 0.0, 1.0, 0.1)
+    e.define_class("Node", 0)
+    e.add_entities("Node", 0, 64)
+    e.attach_service("Node", "generate", "phold_generate")
+    e.set_class_params("Node", phold_params_blob(0, 1 << 20, 0.1, 1.0, 0.1, 0, 1))
+    e.sched_service_bulk(0.0, "generate", 0, "Node", 0, 64, 1)
+    with pytest.raises(capi.SimianError) as ei:
+        e.run()
+    assert ei.value.code == 6
+    # OTHER_GROUP with one group: a modulo by zero in the handler
+    e = capi.Engine("groups", 0.0, 1.0, 0.1)
+    e.define_class("Node", 0)
+    e.add_entities("Node", 0, 64)
+    e.attach_service("Node", "generate", "phold_generate")
+    e.set_class_params("Node", phold_params_blob(0, 64, 0.5, 1.0, 0.1, 2, 1))
+    e.sched_service_bulk(0.0, "generate", 0, "Node", 0, 64, 1)
+    with pytest.raises(capi.SimianError) as ei:
+        e.run()
+    assert ei.value.code == 6
+
+
 def test_lookahead_violation_is_an_error():
     """entity.js:41-45: rx given and offset < minDelay must throw"""
     from simian_b200 import capi

@@ -13,7 +13,7 @@ for rep in range(2):
     ph = e.debug_phase_cycles()
     e.close()
 tot = sum(ph) or 1
-names = ["0 W + state/cache copies issued", "1 list pages", "2 bulk copy of the pages (wait)", "3 classify + counting sort", "4 rank", "5 handlers", "6 append + chain", "7 recycle", "8 warp reduce", "9 -"]
+names = ["0 init", "1 list pages", "2 scan", "3 A1 rank", "4 A2 handler", "5 B append", "6 C chain", "7 recycle", "8 reduce", "9 advance"]
 print("events %d windows %d dev %.2f ms" % (st["total_events"], st["windows"], st["device_seconds"] * 1e3))
 for n, v in zip(names, ph):
     print("%-16s %6.2f%% %14d" % (n, 100.0 * v / tot, v))

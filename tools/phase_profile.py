@@ -20,7 +20,9 @@ for rep in range(2):
     ph = e.debug_phase_cycles()
     e.close()
 tot = sum(ph) or 1
-names = ["0 W + state/cache copies issued", "1 list pages", "2 bulk copy of the pages (wait)", "3 classify + counting sort", "4 rank", "5 handlers", "6 append + chain", "7 recycle", "8 warp reduce", "9 -"]
+names = ["0 init/W/page cache", "1 list pages", "2 scan -> smem slots", "3 A1 rank",
+         "4 A2 handler+stage", "5 B append", "6 C chain", "7 recycle", "8 reduce/part",
+         "9 advance(last CTA)"]
 print("events %d dev %.2f ms  ev/s %.3e  launches %d" % (
     st["total_events"], st["device_seconds"] * 1e3,
     st["total_events"] / st["device_seconds"], st["kernel_launches"]))
