@@ -412,6 +412,19 @@ int setup_layout(simian_engine *e) {
                              : 2 * local_initial +
                                    (uint64_t)PAGE * ((uint64_t)(ring + 2) * c.n_blocks + 1024ull +
                                                      (uint64_t)SIMIAN_BC * c.n_blocks);
+  // The safe default (one page per cell) grows with entities x ring: 9.5 GB for
+  // 2^20 entities, 152 GB for 2^24.  Beyond 16 GB the default becomes ten times the
+  // initial records (measured need of the PHOLD configs: ~7.5x)
+  // or 16 GB, whichever is larger; SIMIAN_ERR_POOL_EXHAUSTED is loud, "pool_events"
+  // overrides.
+  if (!e->pool_events) {
+    const uint64_t cap16 = (16ull << 30) / sizeof(simian_event_t);
+    if (pool_events > cap16) {
+      uint64_t heur = 10 * local_initial + (uint64_t)PAGE * (2ull * SIMIAN_BC * c.n_blocks + 1024ull);
+      if (heur < cap16) heur = cap16;
+      if (heur < pool_events) pool_events = heur;
+    }
+  }
   uint64_t n_pages = (pool_events + PAGE - 1) / PAGE;
   if (n_pages > 0xFFFFFFFFull / PAGE) n_pages = 0xFFFFFFFFull / PAGE;
   c.n_pages = (uint32_t)n_pages;

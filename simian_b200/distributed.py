@@ -315,22 +315,32 @@ def drive_windows_p2p_loopback(engines, device, batch=8, max_batch=64):
     return out
 
 
-def run_distributed_phold(cfg, rank, world, local_rank, seed=1, driver="p2p",
-                          **options):
-    """One PHOLD step on `world` GPUs (one process each); returns this rank's
-    stats.  cfg: a dict of simian_b200.workloads.CONFIGS shape.  driver: "p2p"
+def run_distributed_model(build, name, end, min_delay, rank, world, local_rank, seed=1,
+                          driver="p2p", profile=False, **options):
+    """One run of a model on `world` GPUs (one process each); returns this
+    rank's stats with the engine under "_engine".  build(engine): the model script
+    (addEntity / attachService / schedService loops).  driver: "p2p"
     (device-driven pull over NVLink) or "nccl" (host-driven alltoallv)."""
     from . import capi
-    from .workloads import build_phold
     device = torch.device("cuda", local_rank)
-    options = dict(options)
-    e = capi.Engine("phold", 0.0, cfg["end"], cfg["min_delay"], rank=rank,
-                    size=world, device=local_rank, seed=seed, **options)
-    build_phold(e, cfg["n"], cfg["per_entity"], cfg["lookahead"], cfg["p_remote"],
-                cfg.get("lam", 1.0), cfg["mode"], cfg["groups"])
+    e = capi.Engine(name, 0.0, end, min_delay, rank=rank, size=world, device=local_rank,
+                    seed=seed, **options)
+    build(e)
     if driver == "p2p":
-        st = drive_windows_p2p(e, rank, world, device)
+        st = drive_windows_p2p(e, rank, world, device, profile=profile)
     else:
         st = drive_windows(GpuRankEngine(e, device), rank, world)
     st["_engine"] = e
     return st
+
+
+def run_distributed_phold(cfg, rank, world, local_rank, seed=1, driver="p2p",
+                          **options):
+    """One PHOLD step on `world` GPUs (one process each); returns this rank's
+    stats.  cfg: a dict of simian_b200.workloads.CONFIGS shape."""
+    from .workloads import build_phold
+    return run_distributed_model(
+        lambda e: build_phold(e, cfg["n"], cfg["per_entity"], cfg["lookahead"],
+                              cfg["p_remote"], cfg.get("lam", 1.0), cfg["mode"], cfg["groups"]),
+        "phold", cfg["end"], cfg["min_delay"], rank, world, local_rank, seed=seed,
+        driver=driver, **options)
