@@ -96,6 +96,11 @@ const char *simian_last_error(simian_engine *e);
  *   "tie_check"       1: count same-entity time ties (default 1)
  *   "force_sequential" 1: always run handlers one thread per entity (testing)
  *   "block_entities"  entities per entity block = per CTA of the window kernel (default and max 512)
+ *   "persistent_loop" 1: when every entity block's CTA is resident at once (small and
+ *                     medium models, size == 1) the whole window loop runs inside
+ *                     cooperative launches of one kernel, a grid barrier per window
+ *                     instead of a kernel launch; 0 (default): one launch per window
+ *                     (measured equal: DESIGN.md section 7)
  *   "pdl"             1: window kernels are launched as programmatic dependents of
  *                     each other, the next window's CTAs become resident while the
  *                     previous one drains (default 1; size == 1)                  */

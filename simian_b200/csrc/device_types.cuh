@@ -95,7 +95,7 @@ struct DevAcc {
   unsigned int ticket;
   unsigned int error; // sticky, first error wins
   unsigned int window_index;
-  unsigned int pad_;
+  unsigned int loop_seq; // k_window_loop: windows completed in the current launch sequence
   double minvec[2]; // {local minLeft candidate, local far min} for allreduce
   unsigned long long phase_cycles[12]; // SIMIAN_PROFILE_PHASES builds only
 };

@@ -22,6 +22,12 @@
 
 extern "C" void simian_trim_cache(void);
 
+// window_loop.cu: the persistent window loop, compiled in its own translation unit
+int simian_loop_blocks_per_sm(size_t smem_bytes);
+cudaError_t simian_loop_launch(const DevCfg &cfg, uint32_t win_ix, uint32_t max_windows,
+                               size_t smem_bytes, cudaStream_t stream);
+size_t simian_loop_smem_bytes();
+
 namespace {
 
 std::string g_create_error;
@@ -173,6 +179,12 @@ struct simian_engine {
   int launch_batch = 16, tie_check = 1, force_sequential = 0;
   uint32_t epb_override = 0; // option "block_entities"
   int pdl = 1;               // option "pdl": window launches overlap the previous one's drain
+  // option "persistent_loop": the window loop inside one cooperative launch when
+  // every block's CTA is resident at once.  Off by default: measured (B200, r2_h) a
+  // window of a small model costs ~18.5 us with either driver -- it is bound by its
+  // chain of dependent memory round trips, not by the launch (PDL hides that)
+  int loop = 0;
+  bool loop_ok = false;      // every entity block's CTA is resident at once (set at layout)
   // model
   std::vector<HostClass> classes;
   std::map<std::string, int> class_ix;
@@ -467,6 +479,15 @@ int setup_layout(simian_engine *e) {
     CK(cudaEventCreate(&e->ev0));
     CK(cudaEventCreate(&e->ev1));
   }
+  // persistent window loop: only when every block's CTA fits on the GPU at once
+  e->loop_ok = false;
+  if (e->loop && e->size == 1) {
+    int sms = 0, coop = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->device);
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, e->device);
+    const int per_sm = simian_loop_blocks_per_sm(simian_loop_smem_bytes());
+    e->loop_ok = coop && per_sm > 0 && (uint64_t)c.n_blocks <= (uint64_t)per_sm * (uint64_t)sms;
+  }
   k_init<<<296, 256, 0, e->stream>>>(c, (uint32_t)n_cells);
   CK(cudaGetLastError());
   e->laid_out = true;
@@ -668,6 +689,7 @@ int simian_set_option(simian_engine *e, const char *key, double v) {
   else if (k == "force_sequential") e->force_sequential = v != 0;
   else if (k == "block_entities") e->epb_override = (uint32_t)v;
   else if (k == "pdl") e->pdl = v != 0;
+  else if (k == "persistent_loop") e->loop = v != 0;
   else return e->fail(SIMIAN_ERR_BAD_ARGUMENT, "unknown option " + k);
   return 0;
 }
@@ -1110,6 +1132,25 @@ int simian_run(simian_engine *e, simian_stats *out) {
   int rc = simian_run_begin(e);
   if (rc) return rc;
   int batch = e->launch_batch;
+  if (e->loop_ok) {
+    // the whole window loop inside cooperative launches of k_window_loop (window_loop.cu): a grid
+    // barrier per window instead of a kernel launch (models whose blocks are all
+    // resident at once; tiny windows are launch-latency bound otherwise)
+    for (;;) {
+      CK(simian_loop_launch(e->cfg, e->win_ix, 1u << 16, simian_loop_smem_bytes(), e->stream));
+      e->launches++;
+      rc = poll(e);
+      if (rc) break;
+      if (e->h_acc->window_index == e->win_ix) { // the launch made no progress
+        rc = e->fail(SIMIAN_ERR_CUDA, "window kernel did not advance");
+        break;
+      }
+      e->win_ix = e->h_acc->window_index;
+      if (e->h_win[e->win_ix & 1u].done) break;
+    }
+    int rc2 = simian_run_end(e, out);
+    return rc ? rc : rc2;
+  }
   for (;;) {
     for (int i = 0; i < batch; i++) {
       if (e->pdl) {

@@ -108,6 +108,47 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *src) {
 __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.wait_all;" ::: "memory");
 }
+
+// ---- bulk asynchronous copies (TMA unit, no tensor map) + mbarrier ---------
+// global -> shared, 16-byte granules, completion counted in bytes on an
+// mbarrier in shared memory (SASS: UBLKCP + SYNCS).
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t arrivals) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(arrivals)
+               : "memory");
+  // make the initialised barrier visible to the async proxy (the copy engine)
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+// one arrival that also announces `bytes` of bulk-copy traffic still to land
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, uint32_t bytes,
+                                         unsigned long long *bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(smem_u32(smem_dst)),
+      "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long *bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // L2-coherent loads (bypass L1) for data other CTAs wrote in this launch
 __device__ __forceinline__ uint32_t ld_cg(const uint32_t *p) {
   uint32_t v;
@@ -361,6 +402,7 @@ __global__ void k_init(const __grid_constant__ DevCfg c, uint32_t n_cells) {
     a->ticket = 0;
     a->error = 0;
     a->window_index = 0;
+    a->loop_seq = 0;
     a->minvec[0] = a->minvec[1] = 0;
     for (int q = 0; q < 12; q++) a->phase_cycles[q] = 0;
     WinState w;
@@ -545,7 +587,29 @@ static_assert(EV_PER_THREAD <= 4, "ranks are packed 8 bits each into one registe
 #define RSTACK_MAX 80 // entity sub-ranges a CTA can have pending
 #define NBINS 16      // histogram bins over the block's entities (burst partition)
 
-struct WindowShared {
+// K2 page copy: 16-byte cp.async per half record (default), or -- build with
+// -DSIMIAN_USE_BULK_SCAN -- one cp.async.bulk per page completing on an mbarrier
+// (UBLKCP + SYNCS in SASS).  Measured on config 2 (tools/ab_run.py, median of 5,
+// twice): steady windows 13.22 ms against 13.25 ms, the t = 0 burst window 1.85 ms
+// against 1.75 ms (whole records in shared memory cost the 16-way tie ranking
+// two-way bank conflicts): 15.07 ms against 15.00 ms per step.  Not faster: the
+// kernel is not bound by the copy (profiles/README.md, r2_e), so the default stays.
+#ifdef SIMIAN_USE_BULK_SCAN
+#define SIMIAN_BULK_SCAN 1
+#endif
+struct __align__(32) SlotRec {
+  ulonglong2 lo; // {time, dst | src << 32}
+  ulonglong2 hi; // {handler | flags << 16 | seq << 32, data}
+};
+#ifdef SIMIAN_BULK_SCAN
+#define SLOT_LO(sh, i) ((sh).rec[i].lo)
+#define SLOT_HI(sh, i) ((sh).rec[i].hi)
+#else
+#define SLOT_LO(sh, i) ((sh).lo[i])
+#define SLOT_HI(sh, i) ((sh).hi[i])
+#endif
+
+struct __align__(32) WindowShared {
   WinState W;
   AppendCtx ax;
   unsigned long long min_key, max_key, free_base, ring_base;
@@ -568,15 +632,21 @@ struct WindowShared {
   uint16_t nxt[NREFS];          // next due event of the same entity
   unsigned long long xs[NREFS]; // trace words, stored in commit order along the entity list
   EntityCore core_s[EPB];       // {commit count, trace hash} of the entities with due events
-  // due events: the 32-byte records themselves, as two 16-byte halves (no bank
-  // conflicts).  The thread-per-event path overwrites slot i with the record
-  // event i emits (staged, then appended).
+  // due events: the 32-byte records themselves.  The thread-per-event path
+  // overwrites slot i with the record event i emits (staged, then appended).
+#ifdef SIMIAN_BULK_SCAN
+  // whole records, so that a page is ONE bulk copy (cp.async.bulk) into the slots
+  SlotRec rec[NREFS];
+  unsigned long long mbar; // completion barrier of the bulk copies
+#else
+  // as two 16-byte halves (no bank conflicts); filled with 16-byte cp.async
   ulonglong2 lo[NREFS]; // {time, dst | src << 32}
   ulonglong2 hi[NREFS]; // {handler | flags << 16 | seq << 32, data}
+#endif
 };
 
 __device__ __forceinline__ RecBits slot_get(const WindowShared &sh, uint32_t i) {
-  ulonglong2 a = sh.lo[i], b = sh.hi[i];
+  ulonglong2 a = SLOT_LO(sh, i), b = SLOT_HI(sh, i);
   RecBits r;
   r.q0 = a.x;
   r.q1 = a.y;
@@ -585,8 +655,8 @@ __device__ __forceinline__ RecBits slot_get(const WindowShared &sh, uint32_t i) 
   return r;
 }
 __device__ __forceinline__ void slot_put(WindowShared &sh, uint32_t i, const RecBits &r) {
-  sh.lo[i] = make_ulonglong2(r.q0, r.q1);
-  sh.hi[i] = make_ulonglong2(r.q2, r.q3);
+  SLOT_LO(sh, i) = make_ulonglong2(r.q0, r.q1);
+  SLOT_HI(sh, i) = make_ulonglong2(r.q2, r.q3);
 }
 
 // per-thread accumulators of the handler phase
@@ -889,7 +959,7 @@ __device__ __noinline__ void process_entity(const DevCfg &c, WindowShared &sh, T
     uint32_t handler, src;
     unsigned long long data;
     if (pj >= 0 &&
-        (!have_g || ctx.pend_time[pj] < __longlong_as_double((long long)sh.lo[gj].x))) {
+        (!have_g || ctx.pend_time[pj] < __longlong_as_double((long long)SLOT_LO(sh, gj).x))) {
       time = ctx.pend_time[pj];
       handler = (uint32_t)(ctx.pend_q2[pj] & 0xFFFFu);
       src = ctx.self_gid;
@@ -951,12 +1021,12 @@ __device__ __noinline__ void process_entity(const DevCfg &c, WindowShared &sh, T
 // Returns the rank.
 __device__ __forceinline__ uint32_t rank_event(const DevCfg &c, WindowShared &sh, ThreadAcc &ta,
                                                uint32_t slot0, uint32_t i) {
-  const ulonglong2 a = sh.lo[i];
+  const ulonglong2 a = SLOT_LO(sh, i);
   const uint32_t le = (uint32_t)a.y - slot0;
   const double tr = __longlong_as_double((long long)a.x);
   uint32_t rank = 0;
   const uint32_t first = sh.head[le];
-  const ulonglong2 bh = sh.hi[i];
+  const ulonglong2 bh = SLOT_HI(sh, i);
   // tie-break words of this event: (handler, src) and seq
   const unsigned long long my2 = ((bh.x & 0xFFFFull) << 32) | (a.y >> 32);
   const uint32_t myseq = (uint32_t)(bh.x >> 32);
@@ -969,13 +1039,13 @@ __device__ __forceinline__ uint32_t rank_event(const DevCfg &c, WindowShared &sh
 #pragma unroll 1
   for (uint32_t j = first; j != LIST_END; j = sh.nxt[j]) {
     if (j == i) continue;
-    const ulonglong2 o = sh.lo[j];
+    const ulonglong2 o = SLOT_LO(sh, j);
     const double to = __longlong_as_double((long long)o.x);
     if (to < tr) {
       rank++;
       t = sh.nxt[t];
     } else if (to == tr) { // a true same-entity time tie: the defined order decides
-      const ulonglong2 oh = sh.hi[j];
+      const ulonglong2 oh = SLOT_HI(sh, j);
       const unsigned long long o2 = ((oh.x & 0xFFFFull) << 32) | (o.y >> 32);
       const uint32_t oseq = (uint32_t)(oh.x >> 32);
       // identical records (same key down to seq) are ordered by their slot: any
@@ -1000,9 +1070,9 @@ __device__ __forceinline__ uint32_t rank_event(const DevCfg &c, WindowShared &sh
       unsigned long long p2 = 0;
 #pragma unroll 1
       for (uint32_t j = first; j != LIST_END; j = sh.nxt[j]) {
-        if (j == i || __longlong_as_double((long long)sh.lo[j].x) != tr) continue;
-        const unsigned long long ox = sh.hi[j].x;
-        const unsigned long long o2 = ((ox & 0xFFFFull) << 32) | (sh.lo[j].y >> 32);
+        if (j == i || __longlong_as_double((long long)SLOT_LO(sh, j).x) != tr) continue;
+        const unsigned long long ox = SLOT_HI(sh, j).x;
+        const unsigned long long o2 = ((ox & 0xFFFFull) << 32) | (SLOT_LO(sh, j).y >> 32);
         const uint32_t oseq = (uint32_t)(ox >> 32);
         const bool before = o2 != my2 ? o2 < my2 : (oseq != myseq ? oseq < myseq : j < i);
         // keep the latest predecessor: (key, seq, slot) maximal
@@ -1013,7 +1083,7 @@ __device__ __forceinline__ uint32_t rank_event(const DevCfg &c, WindowShared &sh
           pseq = oseq;
         }
       }
-      if (p2 != my2 || sh.hi[pj].y != bh.y) ta.dties++;
+      if (p2 != my2 || SLOT_HI(sh, pj).y != bh.y) ta.dties++;
     }
   }
   sh.xs[t] = simian_trace_event(tr, (uint32_t)(bh.x & 0xFFFFull), (uint32_t)(a.y >> 32), bh.y);
@@ -1046,7 +1116,7 @@ __device__ __forceinline__ void run_event(const DevCfg &c, WindowShared &sh, Thr
   ctx.data_ = r.data();
   uint32_t h = r.handler();
   run_pure_handler(ctx, h < SIMIAN_MAX_SERVICES ? ctx.cl->fn_of_service[h] : 0);
-  if (ctx.stage != SIMIAN_NONE) sh.lo[i].y = 0xFFFFFFFFFFFFFFFFull; // nothing staged
+  if (ctx.stage != SIMIAN_NONE) SLOT_LO(sh, i).y = 0xFFFFFFFFFFFFFFFFull; // nothing staged
 }
 
 // Phase C, one thread per entity: fold the trace words, already in commit
@@ -1121,8 +1191,8 @@ __device__ __forceinline__ void collect_due(const DevCfg &c, WindowShared &sh, T
         if (due) {
           uint32_t pos = p0 + __popc(m & ((1u << lane) - 1u));
           if (pos < NREFS) {
-            sh.lo[pos] = make_ulonglong2(q0[u], q1[u]);
-            cp_async16(&sh.hi[pos], (const char *)(c.pool + ref[u]) + 16);
+            SLOT_LO(sh, pos) = make_ulonglong2(q0[u], q1[u]);
+            cp_async16(&SLOT_HI(sh, pos), (const char *)(c.pool + ref[u]) + 16);
             uint32_t prev = atomicExch(&sh.head[le], pos);
             sh.nxt[pos] = (uint16_t)prev;
             if (prev == LIST_END) cp_async16(&sh.core_s[le], &c.core[slot0 + le]);
@@ -1142,19 +1212,41 @@ __device__ __forceinline__ void collect_due(const DevCfg &c, WindowShared &sh, T
 // the CTA has slots.  ALL of them are copied into the shared-memory slots in
 // one round trip (cp.async, no registers, every load of the CTA in flight at
 // once); slot = records in the pages listed before + index in the page.
-__device__ __forceinline__ void collect_all(const DevCfg &c, WindowShared &sh, uint32_t npg) {
+#ifdef SIMIAN_BULK_SCAN
+// ONE bulk copy per listed page (its records are contiguous: <= 4 KB), issued by
+// one thread each; the bytes land on the CTA's mbarrier, which every thread then
+// waits on itself -- no block barrier between the copy and the classification.
+__device__ __forceinline__ void collect_all(const DevCfg &c, WindowShared &sh, uint32_t npg,
+                                            uint32_t nvalid) {
+  if (threadIdx.x == 0) mbar_arrive_expect_tx(&sh.mbar, nvalid * 32u);
+  for (uint32_t i = threadIdx.x; i < npg; i += NTHREADS) {
+    const uint32_t n = (uint32_t)(sh.pg_cnt[i] & 0x7FFFu);
+    if (n)
+      bulk_g2s(&sh.rec[sh.pg_off[i]], c.pool + (size_t)sh.pg_id[i] * PAGE, n * 32u, &sh.mbar);
+  }
+  uint32_t spins = 0;
+  while (!mbar_try_wait(&sh.mbar, 0u))
+    if (++spins > (1u << 24)) { // never legitimately: fail, do not hang
+      set_error(c, SIMIAN_ERR_STALLED);
+      break;
+    }
+}
+#else
+__device__ __forceinline__ void collect_all(const DevCfg &c, WindowShared &sh, uint32_t npg,
+                                            uint32_t /*nvalid*/) {
   const uint32_t lim = npg * PAGE;
   for (uint32_t i = threadIdx.x; i < lim; i += NTHREADS) {
     const uint32_t pg = i / PAGE, sl = i % PAGE;
     if (sl < (uint32_t)(sh.pg_cnt[pg] & 0x7FFFu)) {
       const simian_event_t *src = c.pool + ((size_t)sh.pg_id[pg] * PAGE + sl);
       const uint32_t pos = sh.pg_off[pg] + sl;
-      cp_async16(&sh.lo[pos], src);
-      cp_async16(&sh.hi[pos], (const char *)src + 16);
+      cp_async16(&SLOT_LO(sh, pos), src);
+      cp_async16(&SLOT_HI(sh, pos), (const char *)src + 16);
     }
   }
   cp_async_wait_all();
 }
+#endif
 
 // ... then every thread classifies the records in its slots (the same slots it
 // handles in the later phases): due events are pushed onto their entity's list
@@ -1168,7 +1260,7 @@ __device__ __forceinline__ uint32_t link_due(const DevCfg &c, WindowShared &sh, 
   for (int u = 0; u < EV_PER_THREAD; u++) {
     const uint32_t i = threadIdx.x + u * NTHREADS;
     if (i < nvalid) {
-      const ulonglong2 a = sh.lo[i];
+      const ulonglong2 a = SLOT_LO(sh, i);
       const double t = __longlong_as_double((long long)a.x);
       if (t < w_hi) {
         if (t >= w_gmin) {
@@ -1203,7 +1295,7 @@ __device__ __noinline__ bool partition_burst(const DevCfg &c, WindowShared &sh, 
   const uint32_t shift = sh.bin_shift;
   // the records that did get a slot in the overflowing pass
   for (uint32_t i = tid; i < NREFS; i += NTHREADS)
-    atomicAdd(&sh.hist[((uint32_t)sh.lo[i].y - slot0) >> shift], 1u);
+    atomicAdd(&sh.hist[((uint32_t)SLOT_LO(sh, i).y - slot0) >> shift], 1u);
   __syncthreads();
   if (tid == 0) {
     const uint32_t nb = ((c.epb - 1u) >> shift) + 1u; // bins in use
@@ -1679,7 +1771,7 @@ __device__ __forceinline__ void process_pass(const DevCfg &c, WindowShared &sh, 
         uint32_t i = tid + u * NTHREADS;
         cell[u] = SIMIAN_NONE;
         if (live & (1u << u)) {
-          ulonglong2 a = sh.lo[i];
+          ulonglong2 a = SLOT_LO(sh, i);
           if ((uint32_t)a.y != SIMIAN_NONE)
             cell[u] = cell_of_local(c, sh.ax, W.tb_clean, W.far_row,
                                     __longlong_as_double((long long)a.x), (uint32_t)a.y);
@@ -1846,30 +1938,24 @@ __device__ __noinline__ void filtered_passes(const DevCfg &c, WindowShared &sh, 
   accumulate_block(sh, ta);
 }
 
-// One lookahead window (or one redistribution pass) for entity block blockIdx.x.
-// fuse_advance: 1 (size == 1): the last CTA to finish computes window k+1;
-// 2 / 3 (size > 1): the last CTA computes this rank's LBTS candidate (3: and
-// publishes it to the peers' exchange slots); 0: neither.
-__global__ void __launch_bounds__(NTHREADS, SIMIAN_MINBLOCKS)
-    k_window(const __grid_constant__ DevCfg c, uint32_t win_ix, int fuse_advance) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  WindowShared &sh = *reinterpret_cast<WindowShared *>(smem_raw);
+// Per-window set-up of a CTA: sticky error flag, the block's own free pages
+// (written by this block's CTA of the previous window), accumulators, window
+// descriptor.  All threads; ends with a block barrier.  Returns the error flag.
+__device__ __forceinline__ uint32_t window_cta_begin(const DevCfg &c, WindowShared &sh,
+                                                     const WinState *Wg, uint32_t b) {
   const int tid = threadIdx.x;
-  const uint32_t b = blockIdx.x;
-  // Programmatic dependent launch: every resident CTA of the previous window
-  // has started, so this grid's CTAs may take the SM slots that launch's last
-  // wave frees -- and wait here until it has completed and its writes are
-  // visible.  (Both calls are no-ops for an ordinary launch.)
-  cudaTriggerProgrammaticLaunchCompletion();
-  cudaGridDependencySynchronize();
-  const WinState *Wg = &c.win[win_ix & 1u];
-  if (Wg->done) return; // simian.js:119: enqueued past the end of the run
   if (tid == 0) sh.found = ld_cg(&c.acc->error);
-  // the block's own free pages (written by this block's CTA of the previous launch)
-  if (tid < SIMIAN_BC) sh.ax.pgc[tid] = c.bcache[(size_t)b * SIMIAN_BC + tid];
+  if (tid < SIMIAN_BC) sh.ax.pgc[tid] = ld_cg(&c.bcache[(size_t)b * SIMIAN_BC + tid]);
   if (tid == 0) {
+#ifdef SIMIAN_BULK_SCAN
+    mbar_init(&sh.mbar, 1u);
+#endif
     sh.t_last = clock64();
-    sh.W = *Wg;
+    { // L2-coherent copy: in the loop the descriptor was written by another CTA of this launch
+      const unsigned long long *src = reinterpret_cast<const unsigned long long *>(Wg);
+      unsigned long long *dst = reinterpret_cast<unsigned long long *>(&sh.W);
+      for (int q = 0; q < (int)(sizeof(WinState) / 8); q++) dst[q] = ld_cg64(src + q);
+    }
     sh.min_key = SIMIAN_KEY_NONE;
     sh.max_key = 0;
     sh.committed = sh.emitted = sh.dropped = sh.ties = sh.dties = sh.appended = 0;
@@ -1879,10 +1965,17 @@ __global__ void __launch_bounds__(NTHREADS, SIMIAN_MINBLOCKS)
     sh.free_pos = 0;
     sh.is_last = 0;
     sh.ax.far_appends = sh.ax.page_allocs = sh.ax.pgc_take = 0;
-    sh.ax.pgc_have = c.bcount[b];
+    sh.ax.pgc_have = ld_cg(&c.bcount[b]);
   }
   __syncthreads();
-  if (sh.found) return; // sticky error: CTA-uniform exit
+  return sh.found;
+}
+
+// One lookahead window (or one redistribution pass) for entity block b: K2a
+// list -> K2 dequeue -> K3 handlers -> K4 emit -> recycle -> the CTA's results
+// into its BlockPart slot.  All threads of the CTA.
+__device__ __forceinline__ void window_cta_body(const DevCfg &c, WindowShared &sh, uint32_t b) {
+  const int tid = threadIdx.x;
   const WinState &W = sh.W;
   PHASE(0);
 
@@ -1937,8 +2030,10 @@ __global__ void __launch_bounds__(NTHREADS, SIMIAN_MINBLOCKS)
     } else if (nvalid <= NREFS) {
       // all records of the window's pages fit the slots: one bulk copy, then
       // every thread links the due ones among its slots
-      collect_all(c, sh, npg);
-      __syncthreads();
+      collect_all(c, sh, npg, nvalid);
+#ifndef SIMIAN_BULK_SCAN
+      __syncthreads(); // (bulk copies: every thread has waited on the mbarrier itself)
+#endif
       const uint32_t live = link_due(c, sh, ta, slot0, nvalid);
       __syncthreads();
       PHASE(2);
@@ -2029,6 +2124,29 @@ __global__ void __launch_bounds__(NTHREADS, SIMIAN_MINBLOCKS)
     }
   }
   PHASE(8);
+}
+
+// One lookahead window (or one redistribution pass) for entity block blockIdx.x.
+// fuse_advance: 1 (size == 1): the last CTA to finish computes window k+1;
+// 2 / 3 (size > 1): the last CTA computes this rank's LBTS candidate (3: and
+// publishes it to the peers' exchange slots); 0: neither.
+__global__ void __launch_bounds__(NTHREADS, SIMIAN_MINBLOCKS)
+    k_window(const __grid_constant__ DevCfg c, uint32_t win_ix, int fuse_advance) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  WindowShared &sh = *reinterpret_cast<WindowShared *>(smem_raw);
+  const int tid = threadIdx.x;
+  const uint32_t b = blockIdx.x;
+  // Programmatic dependent launch: every resident CTA of the previous window
+  // has started, so this grid's CTAs may take the SM slots that launch's last
+  // wave frees -- and wait here until it has completed and its writes are
+  // visible.  (Both calls are no-ops for an ordinary launch.)
+  cudaTriggerProgrammaticLaunchCompletion();
+  cudaGridDependencySynchronize();
+  const WinState *Wg = &c.win[win_ix & 1u];
+  if (Wg->done) return; // simian.js:119: enqueued past the end of the run
+  if (window_cta_begin(c, sh, Wg, b)) return; // sticky error: CTA-uniform exit
+  const WinState &W = sh.W;
+  window_cta_body(c, sh, b);
   if (!fuse_advance) return;
   // ---- last CTA computes the next window (simian.js:147)
   __threadfence();
@@ -2056,9 +2174,76 @@ __global__ void __launch_bounds__(NTHREADS, SIMIAN_MINBLOCKS)
   PHASE(9);
 }
 
+#ifdef SIMIAN_LOOP_TU
+// The window loop of simian.js:118-149 INSIDE one launch, for models whose entity
+// blocks are all resident at once (gridDim.x = n_blocks <= the CTAs the GPU holds;
+// launched cooperatively): a window costs a grid barrier instead of a kernel
+// launch.  After each window the last CTA to arrive computes the next window and
+// releases the others (acc->loop_seq = windows done so far); the __threadfence()
+// every thread then executes also invalidates the SM's L1 (CCTL.IVALL in SASS), so
+// what other CTAs wrote in the previous window is read from L2.  size == 1 only.
+// Runs at most max_windows windows; the host polls in between.
+// Compiled in its own translation unit (window_loop.cu): inside k_window's the
+// loop costs the per-window kernel registers (config 2: 15.0 -> 16.6 ms per step).
+__global__ void __launch_bounds__(NTHREADS, SIMIAN_MINBLOCKS)
+    k_window_loop(const __grid_constant__ DevCfg c, uint32_t win_ix0, uint32_t max_windows) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  WindowShared &sh = *reinterpret_cast<WindowShared *>(smem_raw);
+  const int tid = threadIdx.x;
+  const uint32_t b = blockIdx.x;
+#pragma unroll 1
+  for (uint32_t w = 0; w < max_windows; w++) {
+    const uint32_t win_ix = win_ix0 + w;
+    const WinState *Wg = &c.win[win_ix & 1u];
+    // (the descriptor was written by another CTA of this launch: read through L2)
+    if (ld_cg(&Wg->done)) return; // simian.js:119
+    if (window_cta_begin(c, sh, Wg, b)) return; // sticky error: CTA-uniform exit
+    window_cta_body(c, sh, b);
+    // ---- grid barrier; the last CTA to arrive computes the next window
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) sh.is_last = (atomicAdd(&c.acc->ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (sh.is_last) {
+      __threadfence();
+      reduce_parts(c, sh);
+      const WinState &W = sh.W;
+      WinState *Wn = &c.win[(win_ix + 1u) & 1u];
+      if (W.redist) {
+        setup_next_window(c, W, Wn, W.gmin, 0.0, true);
+      } else {
+        unsigned long long cand, far;
+        local_min_candidate(c, W, sh, cand, far);
+        double gmin = cand == SIMIAN_KEY_NONE ? c.inf_time : simian_key_time(cand); // simian.js:147
+        double farT = far == SIMIAN_KEY_NONE ? __longlong_as_double(0x7FF0000000000000LL)
+                                             : simian_key_time(far);
+        setup_next_window(c, W, Wn, gmin, farT, false);
+      }
+      __syncthreads();
+      if (tid == 0) {
+        __threadfence();
+        atomicExch(&c.acc->loop_seq, win_ix + 1u); // release the other CTAs
+      }
+    } else if (tid == 0) {
+      uint32_t spins = 0;
+      while (ld_cg(&c.acc->loop_seq) != win_ix + 1u) {
+        if (ld_cg(&c.acc->error)) break;
+        if (++spins > (1u << 26)) { // seconds: a CTA of this grid never became resident
+          set_error(c, SIMIAN_ERR_STALLED);
+          break;
+        }
+        __nanosleep(20);
+      }
+    }
+    __syncthreads();
+    __threadfence(); // (also drops the SM's L1 lines: the next window reads L2)
+  }
+}
+#endif
+
 __global__ void __launch_bounds__(NTHREADS) k_local_min(const __grid_constant__ DevCfg c, uint32_t win_ix,
                                                         int publish) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   WindowShared &sh = *reinterpret_cast<WindowShared *>(smem_raw);
   lbts_candidate(c, c.win[win_ix & 1u], sh, win_ix, publish);
 }

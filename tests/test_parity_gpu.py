@@ -52,12 +52,17 @@ CASES = [
 
 @pytest.mark.parametrize("case", CASES, ids=lambda c: c["name"])
 @pytest.mark.parametrize("sequential", [0, 1], ids=["per_event", "per_entity"])
-def test_engine_matches_oracle(case, sequential, oracle_mod):
+@pytest.mark.parametrize("loop", [1, 0], ids=["persistent_loop", "launch_per_window"])
+def test_engine_matches_oracle(case, sequential, loop, oracle_mod):
     """both handler mappings: one thread per event (pure handlers) and one
-    thread per entity (the general path)"""
+    thread per entity (the general path); both window drivers: the loop inside
+    one cooperative launch (k_window_loop, the default for models this small)
+    and one launch of k_window per window"""
     so, co, ho = run_oracle_phold(oracle_mod, case)
-    se, ce, he = run_engine_phold(case, force_sequential=sequential)
+    se, ce, he = run_engine_phold(case, force_sequential=sequential, persistent_loop=loop)
     assert_parity(so, co, ho, se, ce, he)
+    if loop:  # the whole run in a handful of launches
+        assert se["kernel_launches"] <= 4
 
 
 BURST_CASES = [
@@ -96,9 +101,10 @@ def test_sparse_windows_and_far_list(oracle_mod):
                 lookahead=1e-3, p_remote=0.0, mode=0, end=4.0, seed=9)
     so, co, ho = run_oracle_phold(oracle_mod, case)
     # default bucket width (minDelay/4) -> horizon 0.5: far list exercised
-    se, ce, he = run_engine_phold(case, ring_buckets=256)
-    assert_parity(so, co, ho, se, ce, he)
-    assert se["far_appends"] > 0 and se["redistributions"] > 0
+    for loop in (1, 0):
+        se, ce, he = run_engine_phold(case, ring_buckets=256, persistent_loop=loop)
+        assert_parity(so, co, ho, se, ce, he)
+        assert se["far_appends"] > 0 and se["redistributions"] > 0
     # tuned bucket width
     se, ce, he = run_engine_phold(case, bucket_width=1.0 / 32)
     assert_parity(so, co, ho, se, ce, he)
