@@ -332,6 +332,9 @@ def main():
                     help="scale the entity count (parity/debug only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--pull", default="all", choices=["deferred", "all"],
+                    help="N > 1: cross-GPU pull overlapped with the next window (two-ended "
+                         "outboxes) or everything between two windows")
     ap.add_argument("--no-extra", action="store_true",
                     help="skip the extra_configs (configs 1, 4, 5, scale anchor)")
     args = ap.parse_args()
@@ -382,6 +385,8 @@ def main():
             e.close()
             return st
         from simian_b200.distributed import run_distributed_model
+        if args.pull == "deferred":
+            opts["deferred_pull"] = 1
         st = run_distributed_model(lambda e: build_model(e, c), "bench", end, min_delay, rank,
                                    world, local_rank, profile=profile, **opts)
         st.pop("_engine").close()
@@ -496,7 +501,8 @@ def main():
         def one_step_e2e():
             from simian_b200.workloads import phold_params_blob
             e = capi.Engine("bench_e2e", 0.0, cfg["end"], cfg["min_delay"], seed=1,
-                            rank=rank, size=world, device=local_rank)
+                            rank=rank, size=world, device=local_rank,
+                            deferred_pull=int(world > 1 and args.pull == "deferred"))
             e.define_class("Node", 0)
             e.add_entities("Node", 0, n)
             e.attach_service("Node", "generate", "phold_generate")
@@ -598,6 +604,10 @@ def main():
                    "end_time": cfg["end"], "events_per_step": events // args.steps,
                    "windows_per_step": windows // args.steps,
                    "l2_policy": "inputs_larger_than_l2 (event pool >= 512 MB per GPU)",
+                   "exchange": None if world == 1 else (
+                       "device-driven pull over NVLink peer memory, far records pulled while "
+                       "the next window runs (two-ended outboxes)" if args.pull == "deferred"
+                       else "device-driven pull over NVLink peer memory between two windows"),
                    "parity": {"digest": "%016x" % m["digest"], "total_events": m["last_events"],
                               "distinguishable_ties": m["dist_ties"],
                               "single_gpu_run_of_the_same_model": single,

@@ -96,6 +96,7 @@ const char *simian_last_error(simian_engine *e);
  *   "tie_check"       1: count same-entity time ties (default 1)
  *   "force_sequential" 1: always run handlers one thread per entity (testing)
  *   "block_entities"  entities per entity block = per CTA of the window kernel (default and max 512)
+ *   "deferred_pull"   1: two-ended cross-GPU outboxes, see simian_window_pull (default 0)
  *   "persistent_loop" 1: when every entity block's CTA is resident at once (small and
  *                     medium models, size == 1) the whole window loop runs inside
  *                     cooperative launches of one kernel, a grid barrier per window
@@ -224,6 +225,13 @@ int simian_window_process_lbts(simian_engine *e, int publish);
 /* waitForPeers != 0: first wait (on the device) until every rank has
  * published this window's LBTS candidate, i.e. finished its window           */
 int simian_window_pull(simian_engine *e, int waitForPeers);
+/* Deferred pull (option "deferred_pull" = 1 before setup; device-driven exchange
+ * only).  Senders stage a record that cannot be due in the receiver's next window
+ * (time >= the sending window's bound + 2 minDelay) from the BACK of the outbox;
+ * simian_window_pull then takes the front end (plus, after a jump over idle time,
+ * the far records below the next bound) before the advance step, and the first
+ * CTAs of the next simian_window_process_lbts launch pull the rest over NVLink
+ * beside that window's entity blocks: same calls, same three launches per window. */
 /* simian_window_local_min + allreduce(MIN), send half: the candidate is also
  * written into every peer's exchange slots over NVLink (mpi.cpp:364-390
  * without a collective library or the host)                                  */

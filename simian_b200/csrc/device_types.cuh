@@ -42,6 +42,7 @@
 #endif
 
 #define SIMIAN_MAX_RANKS 16 // GPUs of one box (peer memory over NVLink)
+#define SIMIAN_FAR_COUNT_OFF 64 // uint32 offset of the far-end counters behind outbox_count
 #define SIMIAN_MAX_CLASSES 8
 #define SIMIAN_MAX_SERVICES 32
 #define SIMIAN_MAX_CELLS 96 // sub-buckets one window may span
@@ -154,7 +155,10 @@ struct DevCfg {
   // records window k sends stay readable by the peers until window k+2
   simian_event_t *outbox; // [2][size][outbox_cap]
   uint32_t *outbox_count; // [2][size]
-  uint32_t outbox_cap, pad1_;
+  uint32_t outbox_cap;
+  // two-ended outboxes (deferred pull): far records are staged from the back of a
+  // box, counted in outbox_count[SIMIAN_FAR_COUNT_OFF + ...]
+  uint32_t split_outbox;
   // the peers' outboxes, mapped over NVLink (CUDA IPC); null = not connected
   const simian_event_t *peer_outbox[SIMIAN_MAX_RANKS];
   const uint32_t *peer_count[SIMIAN_MAX_RANKS];

@@ -184,6 +184,7 @@ struct simian_engine {
   // window of a small model costs ~18.5 us with either driver -- it is bound by its
   // chain of dependent memory round trips, not by the launch (PDL hides that)
   int loop = 0;
+  int deferred_pull = 0; // option "deferred_pull": two-ended outboxes (size > 1, device-driven exchange)
   bool loop_ok = false;      // every entity block's CTA is resident at once (set at layout)
   // model
   std::vector<HostClass> classes;
@@ -231,7 +232,9 @@ struct simian_engine {
   do {                                                                                 \
     cudaError_t _e = (call);                                                           \
     if (_e != cudaSuccess)                                                             \
-      return e->fail(SIMIAN_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e)); \
+      return e->fail(SIMIAN_ERR_CUDA, std::string(#call) + " (engine.cu:" +              \
+                                          std::to_string(__LINE__) + "): " +                   \
+                                          cudaGetErrorString(_e));                             \
   } while (0)
 
 namespace {
@@ -458,6 +461,7 @@ int setup_layout(simian_engine *e) {
     // peer (the t = 0 burst of PHOLD at 100 % remote), with a factor 2 of slack
     uint64_t cap = e->outbox_events ? e->outbox_events : 2 * local_initial / (g - 1) + 65536;
     c.outbox_cap = (uint32_t)cap;
+    c.split_outbox = e->deferred_pull ? 1u : 0u;
     if (dev_alloc(e, &c.outbox, 2 * (size_t)e->size * cap)) return e->err_code;
     // the two small peer-visible arrays live in ONE allocation of their own, large
     // enough (2 MB) not to be carved out of a slab CUDA shares between small
@@ -690,6 +694,7 @@ int simian_set_option(simian_engine *e, const char *key, double v) {
   else if (k == "block_entities") e->epb_override = (uint32_t)v;
   else if (k == "pdl") e->pdl = v != 0;
   else if (k == "persistent_loop") e->loop = v != 0;
+  else if (k == "deferred_pull") e->deferred_pull = v != 0;
   else return e->fail(SIMIAN_ERR_BAD_ARGUMENT, "unknown option " + k);
   return 0;
 }
@@ -1020,7 +1025,9 @@ int simian_window_publish_min(simian_engine *e) {
 int simian_window_pull(simian_engine *e, int waitForPeers) {
   if (e->size < 2) return 0;
   const uint32_t bpp = 148; // blocks per peer
-  k_pull<<<(e->size - 1) * bpp, 256, 0, e->stream>>>(e->cfg, e->win_ix, bpp, waitForPeers);
+  // with two-ended outboxes: the part that must be in before the next window
+  k_pull<<<(e->size - 1) * bpp, 256, 0, e->stream>>>(e->cfg, e->win_ix, bpp, waitForPeers,
+                                                      e->cfg.split_outbox ? 1 : 0);
   CK(cudaGetLastError());
   e->launches++;
   return 0;
@@ -1060,15 +1067,25 @@ int simian_run_begin(simian_engine *e) {
 
 int simian_window_process(simian_engine *e) {
   k_window<<<e->cfg.n_blocks, NTHREADS, e->smem_bytes, e->stream>>>(e->cfg, e->win_ix,
-                                                                  e->size == 1);
+                                                                  e->size == 1, 0u);
   CK(cudaGetLastError());
   e->launches++;
   return 0;
 }
 
 int simian_window_process_lbts(simian_engine *e, int publish) {
-  k_window<<<e->cfg.n_blocks, NTHREADS, e->smem_bytes, e->stream>>>(e->cfg, e->win_ix,
-                                                                  publish ? 3 : 2);
+  // deferred pull: the far records of the previous window are pulled by the first
+  // CTAs of this launch, beside the entity blocks (k_window, pull_blocks)
+  uint32_t pull_blocks = 0;
+  if (e->cfg.split_outbox && e->size > 1) {
+    const char *env = getenv("SIMIAN_B200_PULL_CTAS"); // total pull CTAs per launch (tuning)
+    uint32_t total = env ? (uint32_t)atoi(env) : 48u;
+    uint32_t bpp = total / (uint32_t)(e->size - 1);
+    if (bpp < 4u) bpp = 4u;
+    pull_blocks = bpp * (uint32_t)(e->size - 1);
+  }
+  k_window<<<e->cfg.n_blocks + pull_blocks, NTHREADS, e->smem_bytes, e->stream>>>(
+      e->cfg, e->win_ix, publish ? 3 : 2, pull_blocks);
   CK(cudaGetLastError());
   e->launches++;
   return 0;
@@ -1079,6 +1096,9 @@ int simian_window_outbox(simian_engine *e, uint32_t *hostCounts, void **devOutbo
   if (e->size == 1) {
     hostCounts[0] = 0;
   } else {
+    if (e->cfg.split_outbox)
+      return e->fail(SIMIAN_ERR_BAD_ARGUMENT,
+                     "deferred_pull engines are driven by the device-driven exchange only");
     CK(cudaMemcpyAsync(e->h_counts, e->cfg.outbox_count + (size_t)(e->win_ix & 1u) * e->size,
                        sizeof(uint32_t) * (size_t)e->size, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
@@ -1166,9 +1186,9 @@ int simian_run(simian_engine *e, simian_stats *out) {
         at[0].val.programmaticStreamSerializationAllowed = 1;
         lc.attrs = at;
         lc.numAttrs = 1;
-        CK(cudaLaunchKernelEx(&lc, k_window, e->cfg, e->win_ix, 1));
+        CK(cudaLaunchKernelEx(&lc, k_window, e->cfg, e->win_ix, 1, 0u));
       } else {
-        k_window<<<e->cfg.n_blocks, NTHREADS, e->smem_bytes, e->stream>>>(e->cfg, e->win_ix, 1);
+        k_window<<<e->cfg.n_blocks, NTHREADS, e->smem_bytes, e->stream>>>(e->cfg, e->win_ix, 1, 0u);
       }
       e->win_ix++;
       e->launches++;

@@ -214,6 +214,20 @@ __device__ __forceinline__ uint32_t gid_of_slot(const DevCfg &c, uint32_t slot, 
   return cl.first_id + (c.size == 1 ? j : j * (uint32_t)c.size + cl.rank_off);
 }
 
+// 64-bit min / max over the warp with redux.sync on the two halves
+__device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v) {
+  uint32_t hi = (uint32_t)(v >> 32), lo = (uint32_t)v;
+  uint32_t mh = __reduce_min_sync(0xffffffffu, hi);
+  uint32_t ml = __reduce_min_sync(0xffffffffu, hi == mh ? lo : 0xFFFFFFFFu);
+  return ((unsigned long long)mh << 32) | ml;
+}
+__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v) {
+  uint32_t hi = (uint32_t)(v >> 32), lo = (uint32_t)v;
+  uint32_t mh = __reduce_max_sync(0xffffffffu, hi);
+  uint32_t ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+  return ((unsigned long long)mh << 32) | ml;
+}
+
 // ------------------------------------------------------ paged cell append --
 
 struct AppendCtx { // per-CTA, in shared memory
@@ -421,7 +435,7 @@ __global__ void k_init(const __grid_constant__ DevCfg c, uint32_t n_cells) {
     c.win[1] = w;
   }
   for (size_t j = i; j < 2 * (size_t)c.size; j += stride) {
-    if (c.outbox_count) c.outbox_count[j] = 0;
+    if (c.outbox_count) c.outbox_count[j] = c.outbox_count[SIMIAN_FAR_COUNT_OFF + j] = 0;
     if (c.xch) {
       MinSlot z;
       z.min_left = z.far_min = 0;
@@ -512,17 +526,120 @@ __global__ void k_ingest(const __grid_constant__ DevCfg c, const simian_event_t 
   append_ctx_flush(c, ax);
 }
 
+// The record loop of the cross-GPU pull for one CTA: peer number q (of size - 1),
+// CTA `sub` of blocks_per_peer.  W: the window the records were sent in; a_*: the
+// recycle frontier / far row / page limit the appends obey.  See k_pull for `mode`.
+__device__ __forceinline__ void pull_records(const DevCfg &c, const WinState &W,
+                                             long long a_tb_clean, uint32_t a_far_row,
+                                             unsigned long long a_alloc_limit, AppendCtx &ax,
+                                             uint32_t q,
+                                             uint32_t sub, uint32_t blocks_per_peer, int mode,
+                                             double hi_next, uint32_t &napp,
+                                             unsigned long long &mn) {
+  const double thr = W.hi + 2.0 * c.min_delay; // the senders' near / far threshold
+  const uint32_t p = ((uint32_t)c.rank + 1u + q) % (uint32_t)c.size; // never c.rank
+  const uint32_t box = W.parity * (uint32_t)c.size + (uint32_t)c.rank;
+  const uint32_t *pc = c.peer_count[p];
+  const simian_event_t *src = c.peer_outbox[p];
+  if (!pc || !src) {
+    set_error(c, SIMIAN_ERR_BAD_ARGUMENT); // peers were never connected
+    return;
+  }
+  uint32_t n_near = *(const volatile uint32_t *)(pc + box);
+  uint32_t n_far = *(const volatile uint32_t *)(pc + SIMIAN_FAR_COUNT_OFF + box);
+  n_near = n_near < c.outbox_cap ? n_near : c.outbox_cap;
+  n_far = n_far < c.outbox_cap - n_near ? n_far : c.outbox_cap - n_near;
+  src += (size_t)box * c.outbox_cap;
+  const uint32_t stride = blocks_per_peer * blockDim.x;
+  // which ends this launch reads: [0, n_near) and / or the n_far records at the back
+  const bool do_near = mode != 2;
+  const bool do_far = mode == 2 || (mode == 1 && hi_next > thr);
+  for (int end = 0; end < 2; end++) {
+    if (end == 0 ? !do_near : !do_far) continue;
+    const uint32_t n = end == 0 ? n_near : n_far;
+    const simian_event_t *base = end == 0 ? src : src + (c.outbox_cap - n);
+    // four 32-byte NVLink reads in flight per thread, then the four cell claims in
+    // flight together, then the four stores
+    for (uint32_t idx = sub * blockDim.x + threadIdx.x; idx < n; idx += 4 * stride) {
+      RecBits r[4];
+      uint32_t cell[4];
+      unsigned long long old[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+        if (idx + u * stride < n) r[u] = ld_rec(base + idx + u * stride);
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        cell[u] = SIMIAN_NONE;
+        if (idx + u * stride < n) {
+          if (r[u].dst() >= c.n_slots) { // a slot this rank does not have
+            set_error(c, SIMIAN_ERR_UNKNOWN_NAME);
+            continue;
+          }
+          if (end == 1) { // far records: below the next bound now, the rest later
+            const bool below = r[u].time() < hi_next;
+            if (mode == 1 ? !below : below) continue;
+          }
+          if (mode == 2) {
+            unsigned long long k = simian_time_key(r[u].time());
+            mn = k < mn ? k : mn;
+          }
+          cell[u] = cell_of_local(c, ax, a_tb_clean, a_far_row, r[u].time(), r[u].dst());
+          if (cell[u] != SIMIAN_NONE) napp++;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+        if (cell[u] != SIMIAN_NONE) old[u] = atomicAdd(c.cell_state + cell[u], 1ull);
+      // (as in the append phase of k_window: every claim that lands in a page or
+      // installs one first, the claims that wait for another thread's install last)
+      uint32_t waiting = 0;
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+        if (cell[u] != SIMIAN_NONE) {
+          if (CELL_COUNT(old[u]) <= (uint32_t)PAGE) {
+            if ((uint32_t)old[u] < (uint32_t)PAGE)
+              st_rec(c.pool + ((size_t)(uint32_t)(old[u] >> 32) * PAGE + (uint32_t)old[u]), r[u]);
+            else
+              cell_append_slow(c, ax, a_alloc_limit, c.cell_state + cell[u], old[u], r[u].q0,
+                               r[u].q1, r[u].q2, r[u].q3);
+          } else {
+            waiting |= 1u << u;
+          }
+        }
+      if (waiting) {
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+          if (waiting & (1u << u))
+            cell_append_slow(c, ax, a_alloc_limit, c.cell_state + cell[u], old[u], r[u].q0,
+                             r[u].q1, r[u].q2, r[u].q3);
+      }
+    }
+  }
+}
+
 // Cross-GPU exchange, receiver side (simian.js:138-142): the records the peers
 // staged for this rank in window win_ix are read straight out of THEIR
 // outboxes over NVLink (coalesced 32-byte records) and appended to the local
 // calendar -- alltoallv and ingest in one kernel, counts never visit the host.
 // Runs after the window's allreduce, which orders it behind every peer's
 // k_window.  gridDim.x = (size - 1) * blocks_per_peer.
+// mode 0: everything the peers staged (front end of the boxes).
+// Deferred pull (two-ended boxes, DevCfg::split_outbox):
+// mode 1 (before the advance step): the front end -- what may be due in the next
+//   window; and, when the next window turns out to reach beyond the senders'
+//   near / far threshold (a jump over idle time), the far records below its bound.
+// mode 2 (after the advance step, while the next window runs -- normally by the
+//   first CTAs of that window's own k_window launch, see there): the back end --
+//   far records at or above the next window's bound; their times go into the
+//   LBTS candidate of that window.
 __global__ void k_pull(const __grid_constant__ DevCfg c, uint32_t win_ix, uint32_t blocks_per_peer,
-                       int wait_flags) {
+                       int wait_flags, int mode) {
   __shared__ AppendCtx ax;
+  __shared__ double s_hi_next;
+  __shared__ unsigned long long smin;
   append_ctx_init(ax);
   const WinState &W = c.win[win_ix & 1u];
+  if (threadIdx.x == 0) smin = SIMIAN_KEY_NONE;
   if (wait_flags && !W.done && threadIdx.x < (unsigned)c.size) {
     // every rank has published window win_ix's candidate, i.e. finished its
     // k_window: the outboxes are complete (the barrier MPI_Alltoall is, mpi.cpp:422)
@@ -541,40 +658,38 @@ __global__ void k_pull(const __grid_constant__ DevCfg c, uint32_t win_ix, uint32
     __threadfence_system();
   }
   __syncthreads();
-  uint32_t napp = 0;
-  if (!W.done) {
-    const uint32_t q = blockIdx.x / blocks_per_peer, sub = blockIdx.x % blocks_per_peer;
-    const uint32_t p = ((uint32_t)c.rank + 1u + q) % (uint32_t)c.size; // never c.rank
-    const uint32_t box = W.parity * (uint32_t)c.size + (uint32_t)c.rank;
-    const uint32_t *pc = c.peer_count[p];
-    const simian_event_t *src = c.peer_outbox[p];
-    if (pc && src) {
-      uint32_t n = *(const volatile uint32_t *)(pc + box);
-      n = n < c.outbox_cap ? n : c.outbox_cap;
-      src += (size_t)box * c.outbox_cap;
-      // four 32-byte NVLink reads in flight per thread, then the four appends
-      const uint32_t stride = blocks_per_peer * blockDim.x;
-      for (uint32_t idx = sub * blockDim.x + threadIdx.x; idx < n; idx += 4 * stride) {
-        RecBits r[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++)
-          if (idx + u * stride < n) r[u] = ld_rec(src + idx + u * stride);
-#pragma unroll
-        for (int u = 0; u < 4; u++)
-          if (idx + u * stride < n) {
-            if (r[u].dst() >= c.n_slots) { // a slot this rank does not have
-              set_error(c, SIMIAN_ERR_UNKNOWN_NAME);
-              continue;
-            }
-            append_local(c, ax, W.tb_clean, W.far_row, W.alloc_limit, r[u]);
-            napp++;
-          }
+  // the next window's bound: mode 1 computes it the way k_advance will (minimum
+  // over the exchange slots, simian.js:144-147); mode 2 reads what k_advance wrote
+  if (threadIdx.x == 0) {
+    double hn = __longlong_as_double(0x7FF0000000000000LL);
+    if (mode == 1 && !W.done) {
+      double g0 = hn;
+      for (int p = 0; p < c.size; p++) {
+        double a = *(const volatile double *)&c.xch[W.parity * (uint32_t)c.size + p].min_left;
+        g0 = a < g0 ? a : g0;
       }
-    } else {
-      set_error(c, SIMIAN_ERR_BAD_ARGUMENT); // peers were never connected
+      hn = (W.redist ? W.gmin : g0) + c.min_delay;
+    } else if (mode == 2) {
+      hn = c.win[(win_ix + 1u) & 1u].hi;
     }
+    s_hi_next = hn;
   }
+  __syncthreads();
+  const double hi_next = s_hi_next;
+  // appends of mode 2 run beside the NEXT window: its recycle frontier and limits
+  const WinState &Wa = mode == 2 ? c.win[(win_ix + 1u) & 1u] : W;
+  uint32_t napp = 0;
+  unsigned long long mn = SIMIAN_KEY_NONE;
+  if (!W.done)
+    pull_records(c, W, Wa.tb_clean, Wa.far_row, Wa.alloc_limit, ax, blockIdx.x / blocks_per_peer,
+                 blockIdx.x % blocks_per_peer, blocks_per_peer, mode, hi_next, napp, mn);
   appended_flush(c, napp);
+  if (mode == 2) { // pending records the next window's LBTS step must see
+    mn = warp_min_u64(mn);
+    if ((threadIdx.x & 31) == 0 && mn != SIMIAN_KEY_NONE) atomicMin(&smin, mn);
+    __syncthreads();
+    if (threadIdx.x == 0 && smin != SIMIAN_KEY_NONE) atomicMin(&c.acc->min_key, smin);
+  }
   append_ctx_flush(c, ax);
 }
 
@@ -695,6 +810,7 @@ struct DevCtx {
   // kernel: yes; constructors: no -- the calendar search finds those, and a
   // candidate that a later window commits would move the window bounds)
   bool local_min;
+  bool split_ok; // remote records may be classified near / far (not in constructors)
   // same-window self-sends (rx omitted, offset < minDelay allowed: entity.js:41)
   int npend;
   double pend_time[SEQ ? SIMIAN_SELF_MAX : 1];
@@ -703,7 +819,7 @@ struct DevCtx {
   __device__ __forceinline__ DevCtx(const DevCfg &c_, const WinState &W_, AppendCtx &ax_,
                                     ThreadAcc &ta_)
       : c(c_), W(W_), ax(ax_), ta(ta_), stage_sh(nullptr), stage(SIMIAN_NONE), local_min(true),
-        npend(0) {}
+        split_ok(true), npend(0) {}
 
   __device__ __forceinline__ double now() const { return now_; }
   __device__ __forceinline__ uint32_t self_id() const { return self_gid; }
@@ -785,17 +901,33 @@ struct DevCtx {
       ta.min_key = tk < ta.min_key ? tk : ta.min_key;
       // warp-aggregated claim: one atomic per (warp, destination rank)
       const uint32_t box = W.parity * (uint32_t)c.size + (uint32_t)rank;
+      // Two-ended outbox (c.split_outbox, the deferred pull): records that cannot
+      // be due in the receiver's next window -- time >= this window's bound + 2
+      // minDelay -- are staged from the BACK of the box and pulled while that next
+      // window runs; the others from the front, pulled before it.
+      const uint32_t far = (c.split_outbox && split_ok &&
+                            time >= W.hi + 2.0 * c.min_delay) ? 1u : 0u;
+      const int key = rank * 2 + (int)far;
       unsigned act = __activemask();
-      unsigned peers = __match_any_sync(act, rank);
+      unsigned peers = __match_any_sync(act, key);
       int leader = __ffs(peers) - 1, ln = threadIdx.x & 31;
       uint32_t i = 0;
-      if (ln == leader) i = atomicAdd(&c.outbox_count[box], (uint32_t)__popc(peers));
+      if (ln == leader)
+        i = atomicAdd(&c.outbox_count[far * SIMIAN_FAR_COUNT_OFF + box], (uint32_t)__popc(peers));
       i = __shfl_sync(peers, i, leader) + __popc(peers & ((1u << ln) - 1u));
-      if (i >= c.outbox_cap) {
+      // (the two ends meet: the other end's count is only a lower bound here, the
+      // receiver checks the sum again)
+      if (i >= c.outbox_cap ||
+          i + ld_cg(&c.outbox_count[(far ^ 1u) * SIMIAN_FAR_COUNT_OFF + box]) >= c.outbox_cap) {
         set_error(c, SIMIAN_ERR_OUTBOX_FULL);
         return;
       }
-      st_rec(c.outbox + ((size_t)box * c.outbox_cap + i), r);
+      simian_event_t *dst_rec =
+          c.outbox + ((size_t)box * c.outbox_cap + (far ? c.outbox_cap - 1u - i : i));
+      if (SEQ) // (inside the __noinline__ per-entity function: see st_rec_2x16)
+        st_rec_2x16(dst_rec, r.q0, r.q1, r.q2, r.q3);
+      else
+        st_rec(dst_rec, r);
     }
   }
 };
@@ -875,6 +1007,7 @@ __global__ void k_construct(const __grid_constant__ DevCfg c, int cls, uint32_t 
        j += gridDim.x * blockDim.x) {
     DevCtx<false> ctx(c, W, ax, ta);
     ctx.local_min = false;
+    ctx.split_ok = false; // no window is open: everything is pulled before the first one
     int k;
     ctx.self_slot = cl.slot_base + j;
     ctx.self_gid = gid_of_slot(c, ctx.self_slot, k);
@@ -918,7 +1051,7 @@ __device__ __noinline__ void process_entity(const DevCfg &c, WindowShared &sh, T
   ctx.self_slot = slot;
   ctx.self_gid = gid_of_slot(c, slot, k);
   ctx.cl = &c.cls[k];
-  EntityCore st = sh.core_s[slot - blockIdx.x * c.epb];
+  EntityCore st = sh.core_s[slot % c.epb]; // (local entity: slot - block * epb)
   unsigned long long p1 = 0, p2 = 0;
   uint32_t p3 = 0, p4 = 0;
   bool have_prev = false, have_last = false;
@@ -1627,20 +1760,6 @@ __device__ void redistribute_block(const DevCfg &c, WindowShared &sh, uint32_t b
   if (tid == 0) c.cell_state[far_cell] = CELL_EMPTY;
 }
 
-// 64-bit min / max over the warp with redux.sync on the two halves
-__device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v) {
-  uint32_t hi = (uint32_t)(v >> 32), lo = (uint32_t)v;
-  uint32_t mh = __reduce_min_sync(0xffffffffu, hi);
-  uint32_t ml = __reduce_min_sync(0xffffffffu, hi == mh ? lo : 0xFFFFFFFFu);
-  return ((unsigned long long)mh << 32) | ml;
-}
-__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v) {
-  uint32_t hi = (uint32_t)(v >> 32), lo = (uint32_t)v;
-  uint32_t mh = __reduce_max_sync(0xffffffffu, hi);
-  uint32_t ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
-  return ((unsigned long long)mh << 32) | ml;
-}
-
 // Sum the launch's results into the global accumulators (one CTA, all threads;
 // runs after the ticket fence, so every CTA's contribution is visible).  The
 // CTAs add into SIMIAN_PART_SLOTS accumulator slots (block index mod slots), so
@@ -2130,12 +2249,19 @@ __device__ __forceinline__ void window_cta_body(const DevCfg &c, WindowShared &s
 // fuse_advance: 1 (size == 1): the last CTA to finish computes window k+1;
 // 2 / 3 (size > 1): the last CTA computes this rank's LBTS candidate (3: and
 // publishes it to the peers' exchange slots); 0: neither.
+// pull_blocks > 0 (size > 1, two-ended outboxes): the FIRST pull_blocks CTAs of the
+// grid are not entity blocks -- they read the far end of the peers' outboxes of
+// the PREVIOUS window over NVLink and append the records to the calendar while
+// the other CTAs run this window (those records lie at or above this window's
+// bound); their times join the LBTS candidate like everything else a CTA reports.
 __global__ void __launch_bounds__(NTHREADS, SIMIAN_MINBLOCKS)
-    k_window(const __grid_constant__ DevCfg c, uint32_t win_ix, int fuse_advance) {
+    k_window(const __grid_constant__ DevCfg c, uint32_t win_ix, int fuse_advance,
+             uint32_t pull_blocks) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   WindowShared &sh = *reinterpret_cast<WindowShared *>(smem_raw);
   const int tid = threadIdx.x;
-  const uint32_t b = blockIdx.x;
+  const bool puller = blockIdx.x < pull_blocks;
+  const uint32_t b = puller ? 0u : blockIdx.x - pull_blocks;
   // Programmatic dependent launch: every resident CTA of the previous window
   // has started, so this grid's CTAs may take the SM slots that launch's last
   // wave frees -- and wait here until it has completed and its writes are
@@ -2144,9 +2270,53 @@ __global__ void __launch_bounds__(NTHREADS, SIMIAN_MINBLOCKS)
   cudaGridDependencySynchronize();
   const WinState *Wg = &c.win[win_ix & 1u];
   if (Wg->done) return; // simian.js:119: enqueued past the end of the run
-  if (window_cta_begin(c, sh, Wg, b)) return; // sticky error: CTA-uniform exit
+  if (puller) {
+    // (no entity block: only the accumulators and the window descriptor)
+    if (tid == 0) {
+      sh.found = ld_cg(&c.acc->error);
+      sh.W = *Wg;
+      sh.min_key = SIMIAN_KEY_NONE;
+      sh.max_key = 0;
+      sh.committed = sh.emitted = sh.dropped = sh.ties = sh.dties = sh.appended = 0;
+      sh.is_last = 0;
+      sh.ax.far_appends = sh.ax.page_allocs = sh.ax.pgc_take = sh.ax.pgc_have = 0;
+    }
+    __syncthreads();
+    if (sh.found) return;
+    if (win_ix > 0) {
+      const WinState &Wp = c.win[(win_ix - 1u) & 1u]; // the window the records were sent in
+      const uint32_t bpp = pull_blocks / (uint32_t)(c.size - 1);
+      uint32_t napp = 0;
+      unsigned long long mn = SIMIAN_KEY_NONE;
+      // Beside a redistribution pass the appends keep the OLD recycle frontier (the
+      // rows the pass frees are then never aliased by a row appended to) and go to
+      // the far row the pass itself fills, not the one it drains.
+      pull_records(c, Wp, sh.W.tb_clean, sh.W.redist ? sh.W.far_row ^ 1u : sh.W.far_row,
+                   sh.W.alloc_limit, sh.ax, blockIdx.x / bpp, blockIdx.x % bpp, bpp, 2, sh.W.hi,
+                   napp, mn);
+      napp = __reduce_add_sync(0xffffffffu, napp);
+      mn = warp_min_u64(mn);
+      if ((tid & 31) == 0) {
+        if (napp) atomicAdd(&sh.appended, napp);
+        if (mn != SIMIAN_KEY_NONE) atomicMin(&sh.min_key, mn);
+      }
+    }
+    __syncthreads();
+    if (tid < 10) { // the CTA's results -> its BlockPart slot (as window_cta_body does)
+      BlockPart *p = &c.part[blockIdx.x % SIMIAN_PART_SLOTS];
+      switch (tid) {
+        case 0: if (sh.min_key != SIMIAN_KEY_NONE) atomicMin(&p->min_key, sh.min_key); break;
+        case 7: if (sh.appended) atomicAdd(&p->appended, sh.appended); break;
+        case 8: if (sh.ax.far_appends) atomicAdd(&p->far_appends, sh.ax.far_appends); break;
+        case 9: if (sh.ax.page_allocs) atomicAdd(&p->page_allocs, sh.ax.page_allocs); break;
+        default: break;
+      }
+    }
+  } else {
+    if (window_cta_begin(c, sh, Wg, b)) return; // sticky error: CTA-uniform exit
+    window_cta_body(c, sh, b);
+  }
   const WinState &W = sh.W;
-  window_cta_body(c, sh, b);
   if (!fuse_advance) return;
   // ---- last CTA computes the next window (simian.js:147)
   __threadfence();
@@ -2275,8 +2445,10 @@ __global__ void __launch_bounds__(NTHREADS) k_advance(const __grid_constant__ De
   // The outbox the NEXT window fills was sent two windows ago; every peer has
   // read it (its pull precedes the allreduce this advance follows).  The one
   // just sent may still be being read: it is left alone.
-  if (threadIdx.x < c.size && c.outbox_count)
-    c.outbox_count[((W.parity ^ 1u) * (uint32_t)c.size) + threadIdx.x] = 0;
+  if (threadIdx.x < c.size && c.outbox_count) {
+    const uint32_t j = ((W.parity ^ 1u) * (uint32_t)c.size) + threadIdx.x;
+    c.outbox_count[j] = c.outbox_count[SIMIAN_FAR_COUNT_OFF + j] = 0;
+  }
 }
 
 // first window: gmin = startTime even when the queue is empty (simian.js:118)

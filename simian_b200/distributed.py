@@ -113,7 +113,11 @@ def drive_windows_p2p(engine, rank, size, device, group=None, batch=8,
     memory -- the last CTA of k_window writes this rank's candidate into every
     peer's exchange slots, k_pull waits for all of them, k_advance takes the
     minimum -- so a window is three kernel launches and no collective-library call;
-    allreduce="nccl": torch.distributed all_reduce as drawn above."""
+    allreduce="nccl": torch.distributed all_reduce as drawn above.
+    Engines created with option deferred_pull = 1 stage the records that cannot be
+    due in the receiver's next window from the back of their outboxes; k_pull then
+    takes only the front end, and the first CTAs of the NEXT k_window launch pull
+    the rest over NVLink beside that window's entity blocks (same three launches)."""
     engine.set_stream(torch.cuda.current_stream(device).cuda_stream)
     connect_peers(engine, rank, size, group)
     engine.run_begin()

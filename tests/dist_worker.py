@@ -79,7 +79,7 @@ def main():
     ap.add_argument("--engine", default="oracle")
     ap.add_argument("--backend", default="gloo")
     ap.add_argument("--cases", default="ross,other_group,uniform_sparse")
-    ap.add_argument("--driver", default="p2p", choices=["p2p", "p2p_nccl", "nccl"],
+    ap.add_argument("--driver", default="p2p", choices=["p2p", "p2p_deferred", "p2p_nccl", "nccl"],
                     help="cuda engine: device-driven pull over NVLink, or the "
                          "host-driven NCCL alltoallv")
     a = ap.parse_args()
@@ -120,13 +120,15 @@ def main():
             opts = {"bucket_width": 1.0 / 32} if min_delay < 0.05 else {}
             if c.get("kind") == "hello":
                 opts = {"bucket_width": 1.0}
+            if a.driver == "p2p_deferred":
+                opts["deferred_pull"] = 1
             e = capi.Engine("dist", 0.0, end, min_delay, rank=rank,
                             size=world, device=local, seed=c["seed"], **opts)
             build(e, c, world)
-            if a.driver in ("p2p", "p2p_nccl"):
+            if a.driver in ("p2p", "p2p_deferred", "p2p_nccl"):
                 from simian_b200.distributed import drive_windows_p2p
                 st = drive_windows_p2p(e, rank, world, torch.device("cuda", local),
-                                       allreduce="peer" if a.driver == "p2p" else "nccl")
+                                       allreduce="nccl" if a.driver == "p2p_nccl" else "peer")
             else:
                 st = drive_windows(GpuRankEngine(e, "cuda:%d" % local), rank, world)
             cnt, h = read_all(e, classes)

@@ -44,7 +44,7 @@ def test_cuda_engine_over_nccl_two_gpus():
         pytest.skip("needs >= 2 GPUs (run under gpurun --gpus 2)")
     world = min(torch.cuda.device_count(), 8)
     for w in sorted({2, world}):
-        for driver in ("p2p", "p2p_nccl", "nccl"):
+        for driver in ("p2p", "p2p_deferred", "p2p_nccl", "nccl"):
             out = _launch(w, "--engine", "cuda", "--backend", "nccl", "--driver",
                           driver, "--cases",
                           "ross,other_group,uniform_sparse,big,lanl,hello")

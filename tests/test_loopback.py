@@ -98,15 +98,19 @@ def test_cuda_ranks_share_one_gpu(name, world, oracle_mod):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("deferred", [0, 1], ids=["pull_all", "deferred_pull"])
 @pytest.mark.parametrize("world", [2, 3, 4, 8])
 @pytest.mark.parametrize("name", ["ross", "other_group", "uniform_sparse", "lanl", "hello"])
-def test_device_driven_exchange_all_ranks_on_one_gpu(name, world, oracle_mod):
+def test_device_driven_exchange_all_ranks_on_one_gpu(name, world, deferred, oracle_mod):
     """The data plane the multi-GPU numbers come from -- k_window(fuse = 3: LBTS
     candidate published into the peers' exchange slots) -> k_pull (flags, then
     the peers' outboxes) -> k_advance(minimum over the slots) -- with every rank
     of a 2/3/4/8-rank world on ONE device (drive_windows_p2p_loopback: peers wired
     by device pointers, one stream).  Bit-exact per-entity counts and trace hashes
-    against a single-rank oracle run."""
+    against a single-rank oracle run.  deferred_pull: two-ended outboxes -- the
+    near end pulled by k_pull before the advance step, the far end by the first
+    CTAs of the next k_window launch (uniform_sparse and hello jump over idle
+    time, so the near pull also takes far records below the next bound)."""
     import torch
     from simian_b200 import capi
     from simian_b200.distributed import drive_windows_p2p_loopback
@@ -119,7 +123,7 @@ def test_device_driven_exchange_all_ranks_on_one_gpu(name, world, oracle_mod):
     engines = []
     for rank in range(world):
         e = capi.Engine("p2p", 0.0, end, min_delay, rank=rank, size=world, device=0,
-                        seed=c["seed"], **opts)
+                        seed=c["seed"], deferred_pull=deferred, **opts)
         build(e, c, world)
         engines.append(e)
     stats = drive_windows_p2p_loopback(engines, torch.device("cuda", 0))
