@@ -215,6 +215,37 @@ SIMIAN_HD double simian_lanl_gauss(Ctx &ctx, uint32_t &di, double mu, double sig
   return ((x1 * w) * sigma) + mu;
 }
 
+/* The receive handler's randomly weighted subset sum (:304-307):
+ *   value = sum over i < na, j < nj of list[i] * uniform()
+ * Term k = i * nj + j uses draw di0 + k.  The ORDER OF THE ADDITIONS is part of the
+ * specification (f64 addition does not associate) and is chosen so that 32 lanes
+ * can share one sum: 32 partial sums, partial l adding the terms k = l, l + 32,
+ * l + 64, ... in increasing k, then the butterfly p[l] += p[l ^ o] for
+ * o = 16, 8, 4, 2, 1 (every p[l] ends with the same bits; value = p[0]).       */
+template <class Ctx>
+SIMIAN_HD double simian_lanl_weighted_sum(Ctx &ctx, const double *list, uint32_t na,
+                                          uint32_t nj, uint32_t di0) {
+  double p[32], q[32];
+  for (int l = 0; l < 32; l++) p[l] = 0.0;
+  const uint32_t total = na * nj;
+  for (uint32_t k = 0; k < total; k++)
+    p[k & 31u] += list[k / nj] * simian_u01(ctx.draw(di0 + k));
+  for (int o = 16; o; o >>= 1) {
+    for (int l = 0; l < 32; l++) q[l] = p[l] + p[l ^ o];
+    for (int l = 0; l < 32; l++) p[l] = q[l];
+  }
+  return p[0];
+}
+
+/* An engine may take the sum over (a warp per sum, after the entity's events of
+ * the window): it then returns true and adds the value to *sink itself, later,
+ * in commit order.  Default: not taken over.                                     */
+template <class Ctx>
+SIMIAN_HD bool simian_defer_weighted_sum(Ctx &, const double *, uint32_t, uint32_t,
+                                         uint32_t, double *) {
+  return false;
+}
+
 /* ReceiveHandler (:290-309): randomly weighted subset sum over the list */
 template <class Ctx>
 SIMIAN_HD void simian_lanl_receive(Ctx &ctx) {
@@ -233,13 +264,10 @@ SIMIAN_HD void simian_lanl_receive(Ctx &ctx) {
   if (r_ops < st->ops_min) st->ops_min = r_ops;
   st->ops_mean = (st->ops_mean * (double)(st->receive_count - 1) + r_ops) / (double)st->receive_count;
   uint32_t na = (uint32_t)r_active, nj = (uint32_t)r_ops_per_element;
-  double value = 0;
-  for (uint32_t i = 0; i < na; i++) { /* :304-307 */
-    double li = list[i];
-    for (uint32_t j = 0; j < nj; j++) value += li * simian_u01(ctx.draw(di++));
-    st->ops_count += nj;
-  }
-  st->value_sink += value;
+  /* :304-307, in the defined order of simian_lanl_weighted_sum */
+  if (!simian_defer_weighted_sum(ctx, list, na, nj, di, &st->value_sink))
+    st->value_sink += simian_lanl_weighted_sum(ctx, list, na, nj, di);
+  st->ops_count += (uint64_t)na * nj;
 }
 
 /* FinishHandler (:311-315): the stats fan-in is done off-path */

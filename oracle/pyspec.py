@@ -227,13 +227,21 @@ def lanl_receive(p, st, ctx):
         st.ops_min = r_ops
     st.ops_mean = (st.ops_mean * float(st.receive_count - 1) + r_ops) / float(st.receive_count)
     na, nj = int(r_active), int(r_ops_per_element)
-    value = 0.0
-    for i in range(na):
-        li = st.list[i]
-        for _ in range(nj):
-            value += li * u01(ctx.draw(di.next()))
-        st.ops_count += nj
-    st.value_sink += value
+    st.value_sink += lanl_weighted_sum(ctx, st.list, na, nj, di.i)
+    st.ops_count += na * nj
+
+
+def lanl_weighted_sum(ctx, lst, na, nj, di0):
+    """simian_lanl_weighted_sum (include/simian_models.h): 32 partial sums in
+    increasing term order, then the butterfly p[l] += p[l ^ o], o = 16 .. 1"""
+    p = [0.0] * 32
+    for k in range(na * nj):
+        p[k & 31] += lst[k // nj] * u01(ctx.draw(di0 + k))
+    o = 16
+    while o:
+        p = [p[l] + p[l ^ o] for l in range(32)]
+        o >>= 1
+    return p[0]
 
 
 def lanl_construct(p, st, ctx):

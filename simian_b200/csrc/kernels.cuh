@@ -811,6 +811,12 @@ struct DevCtx {
   // candidate that a later window commits would move the window bounds)
   bool local_min;
   bool split_ok; // remote records may be classified near / far (not in constructors)
+  // SEQ: where a handler may park a deferred warp-wide sum (simian_defer_weighted_sum):
+  // the shared-memory slot of the calendar event being committed (NONE: a pending
+  // self-send, or not inside the window kernel) and the entity's count at window start
+  WindowShared *job_sh;
+  uint32_t job_slot;
+  unsigned long long job_count0;
   // same-window self-sends (rx omitted, offset < minDelay allowed: entity.js:41)
   int npend;
   double pend_time[SEQ ? SIMIAN_SELF_MAX : 1];
@@ -819,7 +825,7 @@ struct DevCtx {
   __device__ __forceinline__ DevCtx(const DevCfg &c_, const WinState &W_, AppendCtx &ax_,
                                     ThreadAcc &ta_)
       : c(c_), W(W_), ax(ax_), ta(ta_), stage_sh(nullptr), stage(SIMIAN_NONE), local_min(true),
-        split_ok(true), npend(0) {}
+        split_ok(true), job_sh(nullptr), job_slot(SIMIAN_NONE), job_count0(0), npend(0) {}
 
   __device__ __forceinline__ double now() const { return now_; }
   __device__ __forceinline__ uint32_t self_id() const { return self_gid; }
@@ -1039,6 +1045,51 @@ __device__ __forceinline__ bool key_lt(unsigned long long a1, unsigned long long
   return a4 < b4;
 }
 
+// ---- deferred warp-wide sums (the LANL receive handler's weighted subset sum) ----
+// The per-entity path runs one thread per entity; a handler's long sum would make
+// one lane work while 31 wait.  simian_defer_weighted_sum parks the sum as a JOB on
+// the consumed event's shared-memory slot -- xs[slot] = na | nj << 20 | di0 << 40 |
+// commit delta << 46 | sink offset << 56, the record's data word = the list
+// pointer -- and after the entities' events of the pass a WARP computes each job in
+// the order simian_lanl_weighted_sum defines and adds it to the sink, an entity's
+// jobs in commit order.  (Every event of an entity in a pass has a commit delta
+// below NREFS = 1024, so a model's jobs are either all parked or all computed in
+// line: the additions into the sink keep their commit order.)
+#define JOB_NA(x) ((uint32_t)(x) & 0xFFFFFu)
+#define JOB_NJ(x) ((uint32_t)((x) >> 20) & 0xFFFFFu)
+#define JOB_DI0(x) ((uint32_t)((x) >> 40) & 0x3Fu)
+#define JOB_DELTA(x) ((uint32_t)((x) >> 46) & 0x3FFu)
+#define JOB_SINK_OFF(x) ((int)(signed char)((x) >> 56))
+static_assert(NREFS <= 1024, "commit delta of a parked job: 10 bits");
+
+__device__ __forceinline__ bool simian_defer_weighted_sum(DevCtx<true> &ctx, const double *list,
+                                                          uint32_t na, uint32_t nj, uint32_t di0,
+                                                          double *sink) {
+  if (!ctx.job_sh || ctx.job_slot == SIMIAN_NONE) return false;
+  const unsigned long long delta = ctx.commit_idx - ctx.job_count0;
+  const long long off = sink - list; // in doubles
+  if (na == 0 || na >= (1u << 20) || nj >= (1u << 20) || di0 >= 64u || delta >= 1024ull ||
+      off < -128 || off > 127 || (unsigned long long)na * nj >= (1ull << 32))
+    return false;
+  WindowShared &sh = *ctx.job_sh;
+  SLOT_HI(sh, ctx.job_slot).y = (unsigned long long)list; // (the event's data has been read)
+  sh.xs[ctx.job_slot] = (unsigned long long)na | ((unsigned long long)nj << 20) |
+                        ((unsigned long long)di0 << 40) | (delta << 46) |
+                        ((unsigned long long)(unsigned char)(signed char)off << 56);
+  return true;
+}
+
+// one job, all 32 lanes: partial sums by lane, then the butterfly (the defined order)
+__device__ __forceinline__ double warp_weighted_sum(unsigned long long key, const double *list,
+                                                    uint32_t na, uint32_t nj, uint32_t di0) {
+  const uint32_t lane = threadIdx.x & 31u, total = na * nj;
+  double p = 0.0;
+  for (uint32_t k = lane; k < total; k += 32u)
+    p += list[k / nj] * simian_u01(simian_rng_draw(key, di0 + k));
+  for (int o = 16; o; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+  return p;
+}
+
 // All due events of one entity, in order (simian.js:122-134 restricted to one
 // entity; entities never interact inside a window because cross-entity sends
 // carry offset >= minDelay, entity.js:41).  The records are in shared memory.
@@ -1052,6 +1103,8 @@ __device__ __noinline__ void process_entity(const DevCfg &c, WindowShared &sh, T
   ctx.self_gid = gid_of_slot(c, slot, k);
   ctx.cl = &c.cls[k];
   EntityCore st = sh.core_s[slot % c.epb]; // (local entity: slot - block * epb)
+  ctx.job_sh = &sh;
+  ctx.job_count0 = st.count;
   unsigned long long p1 = 0, p2 = 0;
   uint32_t p3 = 0, p4 = 0;
   bool have_prev = false, have_last = false;
@@ -1101,7 +1154,9 @@ __device__ __noinline__ void process_entity(const DevCfg &c, WindowShared &sh, T
       ctx.pend_time[pj] = ctx.pend_time[ctx.npend];
       ctx.pend_q2[pj] = ctx.pend_q2[ctx.npend];
       ctx.pend_data[pj] = ctx.pend_data[ctx.npend];
+      ctx.job_slot = SIMIAN_NONE; // no slot to park a deferred sum on
     } else if (have_g) {
+      ctx.job_slot = gj;
       const RecBits g = slot_get(sh, gj);
       time = g.time();
       handler = g.handler();
@@ -1939,6 +1994,10 @@ __device__ __forceinline__ void process_pass(const DevCfg &c, WindowShared &sh, 
     PHASE(5);
   } else {
     cp_async_wait_all(); // the entities' {count, hash} (link_due)
+    // no deferred sum is parked on any slot yet (xs is otherwise unused on this path)
+#pragma unroll
+    for (int u = 0; u < EV_PER_THREAD; u++)
+      if (live & (1u << u)) sh.xs[tid + u * NTHREADS] = 0ull;
     __syncthreads();
     // K3 + K4: stateful handlers, one thread per entity.  A separate
     // accumulator keeps `ta` of the thread-per-event path in registers
@@ -1948,6 +2007,38 @@ __device__ __forceinline__ void process_pass(const DevCfg &c, WindowShared &sh, 
     for (uint32_t le = e_lo + tid; le < e_hi; le += NTHREADS) {
       uint32_t f = sh.head[le];
       if (f != LIST_END) process_entity(c, sh, t2, slot0 + le, f);
+    }
+    // ---- the sums the handlers deferred (simian_defer_weighted_sum): one WARP per
+    // entity, the entity's jobs in commit order, each in the defined order
+    __syncthreads();
+    for (uint32_t le = e_lo + (uint32_t)(tid >> 5); le < e_hi; le += NTHREADS / 32) {
+      const uint32_t first = sh.head[le];
+      if (first == LIST_END) continue;
+      int last = -1;
+#pragma unroll 1
+      for (;;) {
+        // the next job of this entity (warp-uniform walk of its short list)
+        uint32_t bj = LIST_END, bd = 1024u;
+        for (uint32_t j = first; j != LIST_END; j = sh.nxt[j]) {
+          const unsigned long long x = sh.xs[j];
+          if (x) {
+            const uint32_t d = JOB_DELTA(x);
+            if ((int)d > last && d < bd) bd = d, bj = j;
+          }
+        }
+        if (bj == LIST_END) break;
+        last = (int)bd;
+        const unsigned long long x = sh.xs[bj];
+        const double *list = (const double *)SLOT_HI(sh, bj).y;
+        int k;
+        const uint32_t gid = gid_of_slot(c, slot0 + le, k);
+        const unsigned long long key = simian_rng_key(c.seed, gid, sh.core_s[le].count + bd);
+        const double v = warp_weighted_sum(key, list, JOB_NA(x), JOB_NJ(x), JOB_DI0(x));
+        if ((tid & 31) == 0) {
+          double *sink = const_cast<double *>(list) + JOB_SINK_OFF(x);
+          *sink += v;
+        }
+      }
     }
     ta.min_key = t2.min_key < ta.min_key ? t2.min_key : ta.min_key;
     ta.max_key = t2.max_key > ta.max_key ? t2.max_key : ta.max_key;
