@@ -129,6 +129,12 @@ int simian_add_entities(simian_engine *e, const char *className,
 int simian_attach_service(simian_engine *e, const char *className,
                           const char *serviceName, const char *deviceFnName);
 
+/* id of a device function in the library's handler registry
+ * (include/simian_handlers.def; a model author's own handlers are compiled in
+ * with make HANDLERS=...), 0 when no handler of that name is registered.  Needs
+ * no engine and no GPU.                                                       */
+int simian_device_function_id(const char *deviceFnName);
+
 /* interned id of a service name (the `name` field of an event)              */
 int simian_intern_service(simian_engine *e, const char *serviceName);
 

@@ -39,17 +39,18 @@ enum simian_builtin_fn {
   SIMIAN_FN_HELLO_SQUARE = 8,   /* "hello_square"   */
   SIMIAN_FN_HELLO_SQRT = 9,     /* "hello_sqrt"     */
   SIMIAN_FN_HELLO_RESULT = 10,  /* "hello_result"   */
-  SIMIAN_FN__END
+  SIMIAN_FN__END,
+  SIMIAN_FN_USER = 32 /* first id of handlers a model author registers (simian_handlers.def) */
 };
+
+typedef struct simian_no_params { uint32_t unused_; } simian_no_params_t;
 
 /* A handler is PURE when it neither touches state() nor sends to itself with
  * rx omitted below the window bound: its effect depends only on (self id,
  * commit index, now, handler, src, data).  The engine then runs it with one
- * thread per EVENT instead of one thread per entity.                         */
-SIMIAN_HD int simian_fn_is_pure(int fn) {
-  return fn == SIMIAN_FN_PHOLD_GENERATE || fn == SIMIAN_FN_COUNT_ONLY ||
-         (fn >= SIMIAN_FN_HELLO_GENERATE && fn <= SIMIAN_FN_HELLO_RESULT);
-}
+ * thread per EVENT instead of one thread per entity.  (Table: simian_handlers.def;
+ * the function itself is defined at the end of this header.)                    */
+SIMIAN_HD int simian_fn_is_pure(int fn);
 
 /* -------------------------------------------------------------- PHOLD ---- */
 
@@ -340,5 +341,42 @@ SIMIAN_HD void simian_hello_sqrt(Ctx &ctx) { /* hello.js:86-88 */
 }
 template <class Ctx>
 SIMIAN_HD void simian_hello_result(Ctx &) {} /* hello.js:54-59: logs only */
+
+/* ------------------------------------------------ the handler registry ---- */
+#ifdef SIMIAN_USER_HANDLERS_H
+#include SIMIAN_USER_HANDLERS_H /* a model author's handlers (make HANDLERS=...) */
+#endif
+
+SIMIAN_HD int simian_fn_is_pure(int fn) {
+  switch (fn) {
+#define SIMIAN_HANDLER(id, name, func, pure, ptype) \
+  case id:                                          \
+    return pure;
+#include "simian_handlers.def"
+#undef SIMIAN_HANDLER
+    default:
+      return 0;
+  }
+}
+
+/* name -> id (0: not registered); bytes of the parameter struct the handler reads */
+static inline int simian_fn_by_name(const char *n) {
+#define SIMIAN_HANDLER(id, name, func, pure, ptype) \
+  if (!strcmp(n, name)) return id;
+#include "simian_handlers.def"
+#undef SIMIAN_HANDLER
+  return SIMIAN_FN_NONE;
+}
+static inline size_t simian_fn_params_bytes(int fn) {
+  switch (fn) {
+#define SIMIAN_HANDLER(id, name, func, pure, ptype) \
+  case id:                                          \
+    return sizeof(ptype);
+#include "simian_handlers.def"
+#undef SIMIAN_HANDLER
+    default:
+      return 0;
+  }
+}
 
 #endif /* SIMIAN_MODELS_H */

@@ -12,7 +12,10 @@ import subprocess
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "_build", "libsimian_oracle.so")
+# SIMIAN_ORACLE_LIB: a variant built with a model author's handlers
+# (make -C oracle HANDLERS=... NAME=...), see include/simian_handlers.def
+LIB_PATH = os.environ.get("SIMIAN_ORACLE_LIB") or os.path.join(HERE, "_build",
+                                                               "libsimian_oracle.so")
 
 
 class OracleStats(C.Structure):
@@ -44,10 +47,12 @@ assert EVENT_DTYPE.itemsize == 32
 
 def build(force=False):
     """Compile the oracle with the recipe in oracle/Makefile."""
+    if os.environ.get("SIMIAN_ORACLE_LIB"):
+        return LIB_PATH
     if force or not os.path.exists(LIB_PATH) or any(
             os.path.getmtime(os.path.join(HERE, p)) > os.path.getmtime(LIB_PATH)
             for p in ("simian_oracle.cpp", "../include/simian_spec.h",
-                      "../include/simian_models.h")):
+                      "../include/simian_models.h", "../include/simian_handlers.def")):
         subprocess.check_call(["make", "-s", "-C", HERE])
     return LIB_PATH
 

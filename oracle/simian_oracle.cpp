@@ -339,34 +339,13 @@ void dispatch(World *w, Rank *r, const simian_event_t &ev) {
   ctx.key = simian_rng_key(w->seed, gid, idx);
   ctx.n_emit = 0;
   ctx.cls = &c;
-  switch (it->second) {
-    case SIMIAN_FN_PHOLD_GENERATE:
-      simian_phold_generate(ctx);
-      break;
-    case SIMIAN_FN_COUNT_ONLY:
-      simian_noop(ctx);
-      break;
-    case SIMIAN_FN_LANL_SEND:
-      simian_lanl_send(ctx);
-      break;
-    case SIMIAN_FN_LANL_RECEIVE:
-      simian_lanl_receive(ctx);
-      break;
-    case SIMIAN_FN_LANL_FINISH:
-      simian_lanl_finish(ctx);
-      break;
-    case SIMIAN_FN_HELLO_GENERATE:
-      simian_hello_generate(ctx);
-      break;
-    case SIMIAN_FN_HELLO_SQUARE:
-      simian_hello_square(ctx);
-      break;
-    case SIMIAN_FN_HELLO_SQRT:
-      simian_hello_sqrt(ctx);
-      break;
-    case SIMIAN_FN_HELLO_RESULT:
-      simian_hello_result(ctx);
-      break;
+  switch (it->second) { // generated from include/simian_handlers.def
+#define SIMIAN_HANDLER(id, name, func, pure, ptype) \
+  case id:                                          \
+    func(ctx);                                      \
+    break;
+#include "../include/simian_handlers.def"
+#undef SIMIAN_HANDLER
     default:
       if (!r->error) {
         r->error = ORACLE_ERR_UNKNOWN;
@@ -375,19 +354,7 @@ void dispatch(World *w, Rank *r, const simian_event_t &ev) {
   }
 }
 
-int fn_by_name(const char *n) {
-  if (!strcmp(n, "phold_generate")) return SIMIAN_FN_PHOLD_GENERATE;
-  if (!strcmp(n, "noop")) return SIMIAN_FN_COUNT_ONLY;
-  if (!strcmp(n, "lanl_send")) return SIMIAN_FN_LANL_SEND;
-  if (!strcmp(n, "lanl_receive")) return SIMIAN_FN_LANL_RECEIVE;
-  if (!strcmp(n, "lanl_finish")) return SIMIAN_FN_LANL_FINISH;
-  if (!strcmp(n, "lanl_construct")) return SIMIAN_FN_LANL_CONSTRUCT;
-  if (!strcmp(n, "hello_generate")) return SIMIAN_FN_HELLO_GENERATE;
-  if (!strcmp(n, "hello_square")) return SIMIAN_FN_HELLO_SQUARE;
-  if (!strcmp(n, "hello_sqrt")) return SIMIAN_FN_HELLO_SQRT;
-  if (!strcmp(n, "hello_result")) return SIMIAN_FN_HELLO_RESULT;
-  return SIMIAN_FN_NONE;
-}
+int fn_by_name(const char *n) { return simian_fn_by_name(n); }
 
 }  // namespace
 

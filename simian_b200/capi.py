@@ -91,6 +91,7 @@ SIGNATURES = {
     "simian_read_local": (_i, [_vp, _cp, _i, _vp, _u64, C.POINTER(_u64), C.POINTER(_u32),
                                C.POINTER(_u32)]),
     "simian_debug_phase_cycles": (_i, [_vp, C.POINTER(_u64)]),
+    "simian_device_function_id": (_i, [_cp]),
     "simian_trim_cache": (None, []),
 }
 

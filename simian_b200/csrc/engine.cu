@@ -151,19 +151,7 @@ struct SchedOp { // a recorded schedService call, replayed on the device at run
   bool ingested = false; // kind 1: already in the calendar (early layout)
 };
 
-int builtin_fn_by_name(const char *n) {
-  if (!strcmp(n, "phold_generate")) return SIMIAN_FN_PHOLD_GENERATE;
-  if (!strcmp(n, "noop")) return SIMIAN_FN_COUNT_ONLY;
-  if (!strcmp(n, "lanl_send")) return SIMIAN_FN_LANL_SEND;
-  if (!strcmp(n, "lanl_receive")) return SIMIAN_FN_LANL_RECEIVE;
-  if (!strcmp(n, "lanl_finish")) return SIMIAN_FN_LANL_FINISH;
-  if (!strcmp(n, "lanl_construct")) return SIMIAN_FN_LANL_CONSTRUCT;
-  if (!strcmp(n, "hello_generate")) return SIMIAN_FN_HELLO_GENERATE;
-  if (!strcmp(n, "hello_square")) return SIMIAN_FN_HELLO_SQUARE;
-  if (!strcmp(n, "hello_sqrt")) return SIMIAN_FN_HELLO_SQRT;
-  if (!strcmp(n, "hello_result")) return SIMIAN_FN_HELLO_RESULT;
-  return SIMIAN_FN_NONE;
-}
+int builtin_fn_by_name(const char *n) { return simian_fn_by_name(n); } // simian_handlers.def
 
 } // namespace
 
@@ -279,19 +267,8 @@ int dev_alloc(simian_engine *e, T **p, size_t n) {
 // reads (the reference throws inside the handler on a bad model; here a bad
 // blob would index past HBM buffers).  No blob at all: the device copy is zeros.
 int check_class_params(simian_engine *e, const HostClass &h, int fn) {
-  size_t need = 0;
-  switch (fn) {
-    case SIMIAN_FN_PHOLD_GENERATE: need = sizeof(simian_phold_params_t); break;
-    case SIMIAN_FN_LANL_SEND:
-    case SIMIAN_FN_LANL_RECEIVE:
-    case SIMIAN_FN_LANL_FINISH:
-    case SIMIAN_FN_LANL_CONSTRUCT: need = sizeof(simian_lanl_params_t); break;
-    case SIMIAN_FN_HELLO_GENERATE:
-    case SIMIAN_FN_HELLO_SQUARE:
-    case SIMIAN_FN_HELLO_SQRT:
-    case SIMIAN_FN_HELLO_RESULT: need = sizeof(simian_hello_params_t); break;
-    default: return 0;
-  }
+  const size_t need = simian_fn_params_bytes(fn); // the struct the handler reads (registry)
+  if (need <= sizeof(simian_no_params_t)) return 0;
   if (h.params.empty()) return 0;
   if (h.params.size() < need)
     return e->fail(SIMIAN_ERR_BAD_ARGUMENT,
@@ -787,6 +764,10 @@ int simian_attach_service(simian_engine *e, const char *className, const char *s
   if (sid < 0) return -sid;
   e->classes[ci].fn_of_service[sid] = (uint8_t)fn;
   return 0;
+}
+
+int simian_device_function_id(const char *deviceFnName) {
+  return deviceFnName ? builtin_fn_by_name(deviceFnName) : 0;
 }
 
 int64_t simian_first_id(simian_engine *e, const char *className) {

@@ -938,57 +938,32 @@ struct DevCtx {
   }
 };
 
-// the pure handlers only (thread-per-event path: simian_fn_is_pure)
+// Dispatch: generated from include/simian_handlers.def (attachService binds a
+// service name to one of these by name; simian.js:129-131 calls it).
+// The pure handlers only (thread-per-event path: simian_fn_is_pure).
 __device__ __forceinline__ void run_pure_handler(DevCtx<false> &ctx, uint32_t fn) {
-  if (fn == SIMIAN_FN_PHOLD_GENERATE)
-    simian_phold_generate(ctx);
-  else if (fn == SIMIAN_FN_COUNT_ONLY)
-    simian_noop(ctx);
-  else if (fn == SIMIAN_FN_HELLO_GENERATE)
-    simian_hello_generate(ctx);
-  else if (fn == SIMIAN_FN_HELLO_SQUARE)
-    simian_hello_square(ctx);
-  else if (fn == SIMIAN_FN_HELLO_SQRT)
-    simian_hello_sqrt(ctx);
-  else if (fn == SIMIAN_FN_HELLO_RESULT)
-    simian_hello_result(ctx);
-  else
-    set_error(ctx.c, SIMIAN_ERR_UNKNOWN_NAME);
+  switch (fn) {
+#define SIMIAN_HANDLER(id, name, func, pure, ptype) \
+  case id:                                          \
+    if constexpr (pure) func(ctx);                  \
+    else set_error(ctx.c, SIMIAN_ERR_UNKNOWN_NAME); \
+    break;
+#include "../../include/simian_handlers.def"
+#undef SIMIAN_HANDLER
+    default:
+      set_error(ctx.c, SIMIAN_ERR_UNKNOWN_NAME);
+  }
 }
 
 template <bool SEQ>
 __device__ __forceinline__ void run_handler(DevCtx<SEQ> &ctx, uint32_t fn) {
   switch (fn) {
-    case SIMIAN_FN_PHOLD_GENERATE:
-      simian_phold_generate(ctx);
-      break;
-    case SIMIAN_FN_COUNT_ONLY:
-      simian_noop(ctx);
-      break;
-    case SIMIAN_FN_LANL_SEND:
-      simian_lanl_send(ctx);
-      break;
-    case SIMIAN_FN_LANL_RECEIVE:
-      simian_lanl_receive(ctx);
-      break;
-    case SIMIAN_FN_LANL_FINISH:
-      simian_lanl_finish(ctx);
-      break;
-    case SIMIAN_FN_LANL_CONSTRUCT:
-      simian_lanl_construct(ctx);
-      break;
-    case SIMIAN_FN_HELLO_GENERATE:
-      simian_hello_generate(ctx);
-      break;
-    case SIMIAN_FN_HELLO_SQUARE:
-      simian_hello_square(ctx);
-      break;
-    case SIMIAN_FN_HELLO_SQRT:
-      simian_hello_sqrt(ctx);
-      break;
-    case SIMIAN_FN_HELLO_RESULT:
-      simian_hello_result(ctx);
-      break;
+#define SIMIAN_HANDLER(id, name, func, pure, ptype) \
+  case id:                                          \
+    func(ctx);                                      \
+    break;
+#include "../../include/simian_handlers.def"
+#undef SIMIAN_HANDLER
     default:
       set_error(ctx.c, SIMIAN_ERR_UNKNOWN_NAME);
   }
@@ -1084,8 +1059,15 @@ __device__ __forceinline__ double warp_weighted_sum(unsigned long long key, cons
                                                     uint32_t na, uint32_t nj, uint32_t di0) {
   const uint32_t lane = threadIdx.x & 31u, total = na * nj;
   double p = 0.0;
-  for (uint32_t k = lane; k < total; k += 32u)
-    p += list[k / nj] * simian_u01(simian_rng_draw(key, di0 + k));
+  // list index i = k / nj, advanced incrementally (k grows by 32 per step)
+  const uint32_t qi = 32u / nj, ri = 32u % nj;
+  uint32_t i = lane / nj, j = lane % nj;
+  for (uint32_t k = lane; k < total; k += 32u) {
+    p += list[i] * simian_u01(simian_rng_draw(key, di0 + k));
+    i += qi;
+    j += ri;
+    if (j >= nj) j -= nj, i++;
+  }
   for (int o = 16; o; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
   return p;
 }
