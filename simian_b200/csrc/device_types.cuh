@@ -17,8 +17,9 @@
 #include "../../include/simian_spec.h"
 
 #ifndef SIMIAN_EPB
-#define SIMIAN_EPB 512 // max entities per block (one CTA owns one block)
+#define SIMIAN_EPB 512 // entities per block by default (one CTA owns one block)
 #endif
+#define SIMIAN_EPB_MAX 1024 // option "block_entities": models with few due events per window
 #ifndef SIMIAN_THREADS
 #define SIMIAN_THREADS 256 // threads per CTA of the window kernel
 #endif
@@ -29,7 +30,7 @@
 #define SIMIAN_REFS (4 * SIMIAN_THREADS) // due events a CTA holds on chip per pass
 #endif
 #ifndef SIMIAN_PGMAX
-#define SIMIAN_PGMAX (SIMIAN_EPB + SIMIAN_EPB / 4) // pages a CTA can list per window
+#define SIMIAN_PGMAX 640 // pages a CTA can list per window
 #endif
 #ifndef SIMIAN_BC
 #define SIMIAN_BC 64 // free pages an entity block keeps for itself (block page cache)

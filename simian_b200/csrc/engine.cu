@@ -26,7 +26,7 @@ extern "C" void simian_trim_cache(void);
 int simian_loop_blocks_per_sm(size_t smem_bytes);
 cudaError_t simian_loop_launch(const DevCfg &cfg, uint32_t win_ix, uint32_t max_windows,
                                size_t smem_bytes, cudaStream_t stream);
-size_t simian_loop_smem_bytes();
+size_t simian_loop_smem_bytes(uint32_t epb);
 
 namespace {
 
@@ -202,7 +202,7 @@ struct simian_engine {
   WinState *h_win = nullptr;
   uint32_t *h_counts = nullptr;
   std::chrono::steady_clock::time_point t_begin;
-  size_t smem_bytes = sizeof(WindowShared);
+  size_t smem_bytes = WINDOW_SMEM_BYTES(SIMIAN_EPB);
   void *ipc_slab = nullptr; // outbox_count at +0, exchange slots at +4096
   uint64_t salt = 0;
   bool peer_seen[SIMIAN_MAX_RANKS] = {};
@@ -310,9 +310,9 @@ int setup_layout(simian_engine *e) {
   if (e->laid_out) return 0;
   DevCfg &c = e->cfg;
   CK(cudaFuncSetAttribute(k_window, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                          (int)e->smem_bytes));
+                          (int)WINDOW_SMEM_BYTES(SIMIAN_EPB_MAX)));
   CK(cudaFuncSetAttribute(k_local_min, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                          (int)e->smem_bytes));
+                          (int)WINDOW_SMEM_BYTES(SIMIAN_EPB_MAX)));
   memset(&c, 0, sizeof c);
   c.start = e->start;
   c.end = e->end;
@@ -383,7 +383,9 @@ int setup_layout(simian_engine *e) {
   // config 2 (480 instead of 512: 4.92 instead of 4.61 waves) and gained nothing:
   // CTAs do not run in lock-step waves, and smaller blocks pay more per-CTA overhead.
   c.epb = e->epb_override ? e->epb_override : EPB;
-  if (c.epb > EPB || c.epb < 1) return e->fail(SIMIAN_ERR_BAD_ARGUMENT, "bad block_entities");
+  if (c.epb > SIMIAN_EPB_MAX || c.epb < 1)
+    return e->fail(SIMIAN_ERR_BAD_ARGUMENT, "bad block_entities");
+  e->smem_bytes = WINDOW_SMEM_BYTES(c.epb);
   c.epb_inv = ~0ull / c.epb + 1ull; // ceil(2^64 / epb): x / epb == umul64hi(x, epb_inv) for x < 2^32
   c.n_blocks = (slot + c.epb - 1) / c.epb;
   if (c.n_blocks == 0) c.n_blocks = 1;
@@ -466,7 +468,7 @@ int setup_layout(simian_engine *e) {
     int sms = 0, coop = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->device);
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, e->device);
-    const int per_sm = simian_loop_blocks_per_sm(simian_loop_smem_bytes());
+    const int per_sm = simian_loop_blocks_per_sm(simian_loop_smem_bytes(e->cfg.epb));
     e->loop_ok = coop && per_sm > 0 && (uint64_t)c.n_blocks <= (uint64_t)per_sm * (uint64_t)sms;
   }
   k_init<<<296, 256, 0, e->stream>>>(c, (uint32_t)n_cells);
@@ -1138,7 +1140,7 @@ int simian_run(simian_engine *e, simian_stats *out) {
     // barrier per window instead of a kernel launch (models whose blocks are all
     // resident at once; tiny windows are launch-latency bound otherwise)
     for (;;) {
-      CK(simian_loop_launch(e->cfg, e->win_ix, 1u << 16, simian_loop_smem_bytes(), e->stream));
+      CK(simian_loop_launch(e->cfg, e->win_ix, 1u << 16, simian_loop_smem_bytes(e->cfg.epb), e->stream));
       e->launches++;
       rc = poll(e);
       if (rc) break;

@@ -724,6 +724,12 @@ struct __align__(32) SlotRec {
 #define SLOT_HI(sh, i) ((sh).hi[i])
 #endif
 
+// {commit count, trace hash} of the block's entities with due events: c.epb entries
+// behind the WindowShared struct (the block size is a run-time option)
+#define SH_CORE(sh) \
+  (reinterpret_cast<EntityCore *>(reinterpret_cast<unsigned char *>(&(sh)) + sizeof(WindowShared)))
+#define WINDOW_SMEM_BYTES(epb) (sizeof(WindowShared) + (size_t)(epb) * sizeof(EntityCore))
+
 struct __align__(32) WindowShared {
   WinState W;
   AppendCtx ax;
@@ -740,13 +746,14 @@ struct __align__(32) WindowShared {
   uint32_t hist[NBINS], pfill[NBINS], pcnt[NBINS], plo[NBINS], phi[NBINS], ppage0[NBINS + 1];
   uint32_t part_of_bin[NBINS];
   uint32_t nparts, bin_shift;
-  uint32_t head[EPB];              // per local entity: index of its first due event
+  uint32_t head[SIMIAN_EPB_MAX];   // per local entity: index of its first due event
   uint32_t pg_id[PGMAX];           // pages of this block's cells in the window rows
   uint32_t pg_off[PGMAX];          // records in the pages listed before this one
   uint16_t pg_cnt[PGMAX];
   uint16_t nxt[NREFS];          // next due event of the same entity
   unsigned long long xs[NREFS]; // trace words, stored in commit order along the entity list
-  EntityCore core_s[EPB];       // {commit count, trace hash} of the entities with due events
+  // (the entities' {commit count, trace hash}, 16 bytes x entities per block, follow
+  // the struct in dynamic shared memory: SH_CORE)
   // due events: the 32-byte records themselves.  The thread-per-event path
   // overwrites slot i with the record event i emits (staged, then appended).
 #ifdef SIMIAN_BULK_SCAN
@@ -1084,7 +1091,7 @@ __device__ __noinline__ void process_entity(const DevCfg &c, WindowShared &sh, T
   ctx.self_slot = slot;
   ctx.self_gid = gid_of_slot(c, slot, k);
   ctx.cl = &c.cls[k];
-  EntityCore st = sh.core_s[slot % c.epb]; // (local entity: slot - block * epb)
+  EntityCore st = SH_CORE(sh)[slot % c.epb]; // (local entity: slot - block * epb)
   ctx.job_sh = &sh;
   ctx.job_count0 = st.count;
   unsigned long long p1 = 0, p2 = 0;
@@ -1277,7 +1284,7 @@ __device__ __forceinline__ void run_event(const DevCfg &c, WindowShared &sh, Thr
   ctx.self_slot = slot;
   ctx.self_gid = gid_of_slot(c, slot, k);
   ctx.cl = &c.cls[k];
-  ctx.commit_idx = sh.core_s[slot - slot0].count + rank;
+  ctx.commit_idx = SH_CORE(sh)[slot - slot0].count + rank;
   ctx.key = simian_rng_key(c.seed, ctx.self_gid, ctx.commit_idx);
   ctx.n_emit = 0;
   ctx.now_ = r.time(); // simian.js:126
@@ -1293,7 +1300,7 @@ __device__ __forceinline__ void run_event(const DevCfg &c, WindowShared &sh, Thr
 // order along the list, and publish the new commit count.
 __device__ __forceinline__ void chain_entity(const DevCfg &c, WindowShared &sh, uint32_t slot,
                                              uint32_t le, uint32_t first) {
-  EntityCore st = sh.core_s[le];
+  EntityCore st = SH_CORE(sh)[le];
   uint32_t n = 0;
 #pragma unroll 1
   for (uint32_t j = first; j != LIST_END; j = sh.nxt[j]) {
@@ -1365,7 +1372,7 @@ __device__ __forceinline__ void collect_due(const DevCfg &c, WindowShared &sh, T
             cp_async16(&SLOT_HI(sh, pos), (const char *)(c.pool + ref[u]) + 16);
             uint32_t prev = atomicExch(&sh.head[le], pos);
             sh.nxt[pos] = (uint16_t)prev;
-            if (prev == LIST_END) cp_async16(&sh.core_s[le], &c.core[slot0 + le]);
+            if (prev == LIST_END) cp_async16(&SH_CORE(sh)[le], &c.core[slot0 + le]);
           } else if (first) {
             // overflow (a burst): where in the block the records without a slot
             // belong -- the partition step sizes its parts from this
@@ -1437,7 +1444,7 @@ __device__ __forceinline__ uint32_t link_due(const DevCfg &c, WindowShared &sh, 
           const uint32_t le = (uint32_t)a.y - slot0;
           const uint32_t prev = atomicExch(&sh.head[le], i);
           sh.nxt[i] = (uint16_t)prev;
-          if (prev == LIST_END) cp_async16(&sh.core_s[le], &c.core[slot0 + le]);
+          if (prev == LIST_END) cp_async16(&SH_CORE(sh)[le], &c.core[slot0 + le]);
           live |= 1u << u;
         }
       } else {
@@ -2014,7 +2021,7 @@ __device__ __forceinline__ void process_pass(const DevCfg &c, WindowShared &sh, 
         const double *list = (const double *)SLOT_HI(sh, bj).y;
         int k;
         const uint32_t gid = gid_of_slot(c, slot0 + le, k);
-        const unsigned long long key = simian_rng_key(c.seed, gid, sh.core_s[le].count + bd);
+        const unsigned long long key = simian_rng_key(c.seed, gid, SH_CORE(sh)[le].count + bd);
         const double v = warp_weighted_sum(key, list, JOB_NA(x), JOB_NJ(x), JOB_DI0(x));
         if ((tid & 31) == 0) {
           double *sink = const_cast<double *>(list) + JOB_SINK_OFF(x);

@@ -34,4 +34,6 @@ cudaError_t simian_loop_launch(const DevCfg &cfg, uint32_t win_ix, uint32_t max_
                                      stream);
 }
 
-size_t simian_loop_smem_bytes() { return sizeof(simian_loop_tu::WindowShared); }
+size_t simian_loop_smem_bytes(uint32_t epb) {
+  return sizeof(simian_loop_tu::WindowShared) + (size_t)epb * sizeof(EntityCore);
+}
