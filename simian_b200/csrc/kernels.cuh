@@ -1066,7 +1066,10 @@ __device__ __forceinline__ double warp_weighted_sum(unsigned long long key, cons
                                                     uint32_t na, uint32_t nj, uint32_t di0) {
   const uint32_t lane = threadIdx.x & 31u, total = na * nj;
   double p = 0.0;
-  // list index i = k / nj, advanced incrementally (k grows by 32 per step)
+  // list index i = k / nj, advanced incrementally (k grows by 32 per step).  The
+  // loop is bound by its arithmetic (a splitmix64 draw + u64 -> f64 per term), not
+  // by the list loads: loading eight elements ahead made it slower (747 -> 899 ms
+  // per config-4 run).
   const uint32_t qi = 32u / nj, ri = 32u % nj;
   uint32_t i = lane / nj, j = lane % nj;
   for (uint32_t k = lane; k < total; k += 32u) {
@@ -2000,6 +2003,7 @@ __device__ __forceinline__ void process_pass(const DevCfg &c, WindowShared &sh, 
     // ---- the sums the handlers deferred (simian_defer_weighted_sum): one WARP per
     // entity, the entity's jobs in commit order, each in the defined order
     __syncthreads();
+    PHASE(4);
     for (uint32_t le = e_lo + (uint32_t)(tid >> 5); le < e_hi; le += NTHREADS / 32) {
       const uint32_t first = sh.head[le];
       if (first == LIST_END) continue;
@@ -2029,6 +2033,8 @@ __device__ __forceinline__ void process_pass(const DevCfg &c, WindowShared &sh, 
         }
       }
     }
+    __syncthreads();
+    PHASE(5);
     ta.min_key = t2.min_key < ta.min_key ? t2.min_key : ta.min_key;
     ta.max_key = t2.max_key > ta.max_key ? t2.max_key : ta.max_key;
     ta.committed += t2.committed;

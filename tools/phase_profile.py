@@ -12,10 +12,20 @@ from simian_b200 import capi  # noqa: E402
 from simian_b200.workloads import CONFIGS, build_phold  # noqa: E402
 
 c = dict(CONFIGS[sys.argv[1] if len(sys.argv) > 1 else "config2_phold_1m"])
+scale = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
+opts = c.pop("options", {})
 for rep in range(2):
-    e = capi.Engine("p", 0.0, c["end"], c["min_delay"], seed=1)
-    build_phold(e, c["n"], c["per_entity"], c["lookahead"], c["p_remote"], 1.0,
-                c["mode"], c["groups"])
+    if c.get("kind") == "lanl":
+        from simian_b200.workloads import build_lanl, lanl_engine_end
+        k = {x: c[x] for x in c if x != "kind"}
+        k["n_ent"] = max(64, int(k["n_ent"] * scale))
+        e = capi.Engine("p", 0.0, lanl_engine_end(k["end_time"], k["min_delay"]), k["min_delay"],
+                        seed=1, **opts)
+        build_lanl(e, **k)
+    else:
+        e = capi.Engine("p", 0.0, c["end"], c["min_delay"], seed=1, **opts)
+        build_phold(e, max(1, int(c["n"] * scale)), c["per_entity"], c["lookahead"],
+                    c["p_remote"], 1.0, c["mode"], c["groups"])
     st = e.run()
     ph = e.debug_phase_cycles()
     e.close()
