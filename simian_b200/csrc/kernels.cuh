@@ -673,9 +673,16 @@ __global__ void k_pull(const __grid_constant__ DevCfg c, uint32_t win_ix, uint32
   append_ctx_init(ax);
   const WinState &W = c.win[win_ix & 1u];
   if (threadIdx.x == 0) smin = SIMIAN_KEY_NONE;
-  if (wait_flags && !W.done && threadIdx.x < (unsigned)c.size) {
-    // every rank has published window win_ix's candidate, i.e. finished its
-    // k_window: the outboxes are complete (the barrier MPI_Alltoall is, mpi.cpp:422)
+  // The CTAs of peer p wait for p's flag only (mode 0): records of the ranks that
+  // finished their window early are pulled while the late ones are still running.
+  // Every peer has CTAs here, so when the kernel ends all flags have been seen
+  // (k_advance reads every slot).  The deferred modes need every candidate at once.
+  const uint32_t my_peer =
+      ((uint32_t)c.rank + 1u + blockIdx.x / blocks_per_peer) % (uint32_t)c.size;
+  if (wait_flags && !W.done &&
+      (mode == 0 ? threadIdx.x == my_peer : threadIdx.x < (unsigned)c.size)) {
+    // a rank that has published window win_ix's candidate has finished its
+    // k_window: its outboxes are complete (the barrier MPI_Alltoall is, mpi.cpp:422)
     const volatile unsigned long long *f =
         &c.xch[W.parity * (uint32_t)c.size + threadIdx.x].seq;
     const unsigned long long want = c.run_nonce + (unsigned long long)win_ix + 1ull;
