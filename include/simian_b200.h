@@ -276,7 +276,11 @@ int simian_read_state(simian_engine *e, const char *className, uint32_t first,
                       uint32_t count, void *out);
 
 /* Engines of the same shape reuse the HBM of destroyed ones (process-wide
- * cache, SIMIAN_B200_CACHE_GB, default 64); this returns it all to CUDA.     */
+ * cache, SIMIAN_B200_CACHE_GB, default 64); this returns it all to CUDA and
+ * closes the cached CUDA-IPC mappings of peers' buffers: call it only while no
+ * multi-rank engine of this process is between run_begin and run_end.  (When an
+ * allocation fails the library drops its cached allocations by itself, never
+ * the mappings.)                                                             */
 void simian_trim_cache(void);
 
 /* diagnostic only: summed SM cycles spent in each phase of the window kernel

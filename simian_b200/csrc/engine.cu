@@ -245,6 +245,19 @@ const char *status_text(int code) {
   }
 }
 
+void trim_alloc_cache() { // cached device allocations only
+  std::lock_guard<std::mutex> g(g_alloc_cache_mu);
+  int cur = 0;
+  cudaGetDevice(&cur);
+  for (auto &kv : g_alloc_cache) {
+    cudaSetDevice(kv.first.device);
+    cudaFree(kv.second);
+  }
+  cudaSetDevice(cur);
+  g_alloc_cache.clear();
+  g_alloc_cache_bytes = 0;
+}
+
 template <class T>
 int dev_alloc(simian_engine *e, T **p, size_t n) {
   size_t bytes = (n ? n : 1) * sizeof(T);
@@ -252,9 +265,11 @@ int dev_alloc(simian_engine *e, T **p, size_t n) {
   void *q = cache_take(e->device, bytes);
   if (!q) {
     cudaError_t ce = cudaMalloc(&q, bytes);
-    if (ce != cudaSuccess) { // make room: drop the cache and retry once
+    if (ce != cudaSuccess) { // make room: drop the cached ALLOCATIONS and retry once
+      // (not the CUDA-IPC mappings of peers' buffers: live engines of this process
+      // may still be running kernels that read through them)
       cudaGetLastError();
-      simian_trim_cache();
+      trim_alloc_cache();
       CK(cudaMalloc(&q, bytes));
     }
   }
@@ -1007,7 +1022,9 @@ int simian_window_publish_min(simian_engine *e) {
 
 int simian_window_pull(simian_engine *e, int waitForPeers) {
   if (e->size < 2) return 0;
-  const uint32_t bpp = 148; // blocks per peer
+  uint32_t bpp = 148; // blocks per peer
+  if (const char *env = getenv("SIMIAN_B200_PULL_BPP")) bpp = (uint32_t)atoi(env); // (tuning)
+  if (bpp < 1) bpp = 1;
   // with two-ended outboxes: the part that must be in before the next window
   k_pull<<<(e->size - 1) * bpp, 256, 0, e->stream>>>(e->cfg, e->win_ix, bpp, waitForPeers,
                                                       e->cfg.split_outbox ? 1 : 0);

@@ -287,6 +287,15 @@ class Simian(object):
         finally:
             self.running = False
         self.now = self.stats["last_time"]
+        if self.stats.get("distinguishable_ties"):
+            # equal-time events of one entity that differ in what the handler sees
+            # commit in the engine's order (time, handler, src, seq); the reference
+            # engines use heap shape (SimianJS) / FIFO (SimianPie) there, so
+            # per-entity traces can differ from theirs on such models
+            import warnings
+            warnings.warn("%d distinguishable same-entity time ties: their commit order is the "
+                          "engine's (time, handler, src, seq), not the reference heap's"
+                          % self.stats["distinguishable_ties"], RuntimeWarning, stacklevel=2)
         if self.verbose:
             for line in self.report_lines():
                 print(line)
