@@ -94,6 +94,19 @@ def test_burst_partition_matches_oracle(case, opts, sequential, oracle_mod):
     assert_parity(so, co, ho, se, ce, he)
 
 
+@pytest.mark.parametrize("sequential", [0, 1], ids=["per_event", "per_entity"])
+@pytest.mark.parametrize("epb", [1024, 777, 64])
+def test_entity_block_size_is_a_run_time_option(epb, sequential, oracle_mod):
+    """block_entities up to 1024 (sparse windows: more due events per CTA): the
+    per-block entity states are a run-time sized tail of the CTA's shared memory"""
+    case = dict(name="blocks", n=5000, per_entity=3, min_delay=0.02, lookahead=0.02,
+                p_remote=0.3, mode=1, end=1.5, seed=31)
+    so, co, ho = run_oracle_phold(oracle_mod, case)
+    se, ce, he = run_engine_phold(case, force_sequential=sequential, block_entities=epb,
+                                  bucket_width=0.01)
+    assert_parity(so, co, ho, se, ce, he)
+
+
 def test_sparse_windows_and_far_list(oracle_mod):
     """config-1 shape: minDelay << mean delay, so almost every event goes
     through the far-future list and the window jumps over idle time."""
