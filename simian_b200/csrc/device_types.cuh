@@ -169,4 +169,10 @@ struct DevCfg {
                                          // earlier run over the same (cached) buffers never match
   MinSlot *xch;                          // [2][size], local
   MinSlot *peer_xch[SIMIAN_MAX_RANKS];   // peers' arrays (peer_xch[rank] == xch)
+  // split window (option "split_handlers", pure handlers only): k_window_stage ranks a
+  // block's due events and parks them here -- {time, dst | src << 32, handler |
+  // commit index << 16, data}, compacted -- and k_emit runs their handlers and appends
+  // what they send at its own (higher) occupancy.  null: one kernel does both.
+  simian_event_t *stage; // [n_blocks][SIMIAN_REFS]
+  uint32_t *stage_n;     // [n_blocks] records parked by the block in this window
 };

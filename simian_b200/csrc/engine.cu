@@ -20,6 +20,10 @@
 #include "../../include/simian_b200.h"
 #include "kernels.cuh"
 
+#ifndef SIMIAN_SPLIT_DEFAULT
+#define SIMIAN_SPLIT_DEFAULT 1 // option "split_handlers" when the model does not say
+#endif
+
 extern "C" void simian_trim_cache(void);
 
 // window_loop.cu: the persistent window loop, compiled in its own translation unit
@@ -173,6 +177,11 @@ struct simian_engine {
   // chain of dependent memory round trips, not by the launch (PDL hides that)
   int loop = 0;
   int deferred_pull = 0; // option "deferred_pull": two-ended outboxes (size > 1, device-driven exchange)
+  // option "split_handlers": a window is two launches -- k_window_stage (dequeue, rank,
+  // trace chain, recycle) and k_emit (handlers + appends at a higher occupancy).  Pure
+  // handlers only; -1 = the default for the model (see setup_layout)
+  int split = -1;
+  bool split_on = false; // in force for this layout
   bool loop_ok = false;      // every entity block's CTA is resident at once (set at layout)
   // model
   std::vector<HostClass> classes;
@@ -328,6 +337,8 @@ int setup_layout(simian_engine *e) {
                           (int)WINDOW_SMEM_BYTES(SIMIAN_EPB_MAX)));
   CK(cudaFuncSetAttribute(k_local_min, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           (int)WINDOW_SMEM_BYTES(SIMIAN_EPB_MAX)));
+  CK(cudaFuncSetAttribute(k_window_stage, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          (int)WINDOW_SMEM_BYTES(SIMIAN_EPB_MAX)));
   memset(&c, 0, sizeof c);
   c.start = e->start;
   c.end = e->end;
@@ -450,6 +461,17 @@ int setup_layout(simian_engine *e) {
   if (dev_alloc(e, &c.bcache, (size_t)c.n_blocks * SIMIAN_BC)) return e->err_code;
   if (dev_alloc(e, &c.bcount, c.n_blocks)) return e->err_code;
   if (dev_alloc(e, &e->d_digest, 2)) return e->err_code;
+  // split window: only models of pure handlers, not beside the deferred pull (its
+  // pull CTAs ride in k_window) or the persistent loop
+  e->split_on = c.all_pure && !e->deferred_pull && !e->loop &&
+                (e->split < 0 ? SIMIAN_SPLIT_DEFAULT != 0 : e->split != 0);
+  c.stage = nullptr;
+  c.stage_n = nullptr;
+  if (e->split_on) {
+    if (dev_alloc(e, &c.stage, (size_t)c.n_blocks * NREFS)) return e->err_code;
+    if (dev_alloc(e, &c.stage_n, c.n_blocks)) return e->err_code;
+    CK(cudaMemsetAsync(c.stage_n, 0, sizeof(uint32_t) * (size_t)c.n_blocks, e->stream));
+  }
   if (e->size > 1) {
     // a window in which every local event sends one record to a uniformly chosen
     // peer (the t = 0 burst of PHOLD at 100 % remote), with a factor 2 of slack
@@ -689,6 +711,7 @@ int simian_set_option(simian_engine *e, const char *key, double v) {
   else if (k == "pdl") e->pdl = v != 0;
   else if (k == "persistent_loop") e->loop = v != 0;
   else if (k == "deferred_pull") e->deferred_pull = v != 0;
+  else if (k == "split_handlers") e->split = v != 0;
   else return e->fail(SIMIAN_ERR_BAD_ARGUMENT, "unknown option " + k);
   return 0;
 }
@@ -1065,12 +1088,37 @@ int simian_run_begin(simian_engine *e) {
   return 0;
 }
 
-int simian_window_process(simian_engine *e) {
-  k_window<<<e->cfg.n_blocks, NTHREADS, e->smem_bytes, e->stream>>>(e->cfg, e->win_ix,
-                                                                  e->size == 1, 0u);
-  CK(cudaGetLastError());
+// One window's launch(es).  fuse: what the last CTA does (k_window); pull_blocks: CTAs
+// of the deferred pull riding in front of the entity blocks.  With programmatic
+// dependent launch the CTAs of a launch become resident while the last wave of the
+// one before drains (they wait inside the kernel).
+static int launch_window(simian_engine *e, int fuse, uint32_t pull_blocks, bool pdl) {
+  cudaLaunchConfig_t lc = {};
+  lc.blockDim = dim3(NTHREADS);
+  lc.stream = e->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  lc.attrs = at;
+  lc.numAttrs = pdl ? 1 : 0;
+  if (e->split_on && pull_blocks == 0) {
+    lc.gridDim = dim3(e->cfg.n_blocks);
+    lc.dynamicSmemBytes = e->smem_bytes;
+    CK(cudaLaunchKernelEx(&lc, k_window_stage, e->cfg, e->win_ix));
+    lc.dynamicSmemBytes = 0;
+    CK(cudaLaunchKernelEx(&lc, k_emit, e->cfg, e->win_ix, fuse));
+    e->launches += 2;
+    return 0;
+  }
+  lc.gridDim = dim3(e->cfg.n_blocks + pull_blocks);
+  lc.dynamicSmemBytes = e->smem_bytes;
+  CK(cudaLaunchKernelEx(&lc, k_window, e->cfg, e->win_ix, fuse, pull_blocks));
   e->launches++;
   return 0;
+}
+
+int simian_window_process(simian_engine *e) {
+  return launch_window(e, e->size == 1, 0u, false);
 }
 
 int simian_window_process_lbts(simian_engine *e, int publish) {
@@ -1084,11 +1132,7 @@ int simian_window_process_lbts(simian_engine *e, int publish) {
     if (bpp < 4u) bpp = 4u;
     pull_blocks = bpp * (uint32_t)(e->size - 1);
   }
-  k_window<<<e->cfg.n_blocks + pull_blocks, NTHREADS, e->smem_bytes, e->stream>>>(
-      e->cfg, e->win_ix, publish ? 3 : 2, pull_blocks);
-  CK(cudaGetLastError());
-  e->launches++;
-  return 0;
+  return launch_window(e, publish ? 3 : 2, pull_blocks, false);
 }
 
 int simian_window_outbox(simian_engine *e, uint32_t *hostCounts, void **devOutbox,
@@ -1173,26 +1217,10 @@ int simian_run(simian_engine *e, simian_stats *out) {
   }
   for (;;) {
     for (int i = 0; i < batch; i++) {
-      if (e->pdl) {
-        // programmatic dependent launch: the CTAs of window k+1 become resident
-        // while the last wave of window k drains (they wait inside the kernel)
-        cudaLaunchConfig_t lc = {};
-        lc.gridDim = dim3(e->cfg.n_blocks);
-        lc.blockDim = dim3(NTHREADS);
-        lc.dynamicSmemBytes = e->smem_bytes;
-        lc.stream = e->stream;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        at[0].val.programmaticStreamSerializationAllowed = 1;
-        lc.attrs = at;
-        lc.numAttrs = 1;
-        CK(cudaLaunchKernelEx(&lc, k_window, e->cfg, e->win_ix, 1, 0u));
-      } else {
-        k_window<<<e->cfg.n_blocks, NTHREADS, e->smem_bytes, e->stream>>>(e->cfg, e->win_ix, 1, 0u);
-      }
+      if ((rc = launch_window(e, 1, 0u, e->pdl != 0))) break;
       e->win_ix++;
-      e->launches++;
     }
+    if (rc) break;
     CK(cudaGetLastError());
     rc = poll(e);
     if (rc) break;

@@ -71,15 +71,25 @@ __device__ __forceinline__ void st_rec(simian_event_t *p, const RecBits &r) {
                "l"(r.q2), "l"(r.q3)
                : "memory");
 }
-// Same record as two 128-bit stores.  Used inside __noinline__ functions: ptxas
-// 12.9 turns the 256-bit form into a single 64-bit store there (seen in SASS:
-// LDL.64 + STG.E.64), silently dropping 24 of the 32 bytes.
+// Same record as two 128-bit stores.  Used wherever the store may end up inside a
+// function that is NOT inlined into a kernel body (__noinline__ functions and
+// everything they inline): ptxas 12.9 can turn the 256-bit form into a single
+// 64-bit store there (seen in SASS: STG.E.64 for a st.global.v4.u64 of the PTX),
+// silently dropping 24 of the 32 bytes -- and whether it does depends on unrelated
+// code (round 2: adding a second kernel that shares the functions broke 25 sites
+// that had compiled correctly).  Hence the WIDE template flag below: 256-bit stores
+// only on call chains that are force-inlined into a __global__ function.
 __device__ __forceinline__ void st_rec_2x16(simian_event_t *p, unsigned long long q0,
                                             unsigned long long q1, unsigned long long q2,
                                             unsigned long long q3) {
   asm volatile("st.global.v2.u64 [%0], {%1,%2};" ::"l"(p), "l"(q0), "l"(q1) : "memory");
   asm volatile("st.global.v2.u64 [%0], {%1,%2};" ::"l"((char *)p + 16), "l"(q2), "l"(q3)
                : "memory");
+}
+template <bool WIDE>
+__device__ __forceinline__ void st_rec_sel(simian_event_t *p, const RecBits &r) {
+  if constexpr (WIDE) st_rec(p, r);
+  else st_rec_2x16(p, r.q0, r.q1, r.q2, r.q3);
 }
 __device__ __forceinline__ RecBits ld_rec(const simian_event_t *p) {
   RecBits r;
@@ -335,13 +345,14 @@ __device__ __noinline__ void cell_append_slow(const DevCfg &c, AppendCtx &ax,
   }
 }
 
+template <bool WIDE = false>
 __device__ __forceinline__ void cell_append(const DevCfg &c, AppendCtx &ax,
                                             unsigned long long alloc_limit, uint32_t cell,
                                             const RecBits &r) {
   unsigned long long *hp = c.cell_state + cell;
   unsigned long long old = atomicAdd(hp, 1ull);
   if ((uint32_t)old < (uint32_t)PAGE)
-    st_rec(c.pool + ((size_t)(uint32_t)(old >> 32) * PAGE + (uint32_t)old), r);
+    st_rec_sel<WIDE>(c.pool + ((size_t)(uint32_t)(old >> 32) * PAGE + (uint32_t)old), r);
   else
     cell_append_slow(c, ax, alloc_limit, hp, old, r.q0, r.q1, r.q2, r.q3);
 }
@@ -363,11 +374,12 @@ __device__ __forceinline__ uint32_t cell_of_local(const DevCfg &c, AppendCtx &ax
 }
 
 // route a record whose dst is a LOCAL SLOT into the calendar or the far row
+template <bool WIDE = false>
 __device__ __forceinline__ void append_local(const DevCfg &c, AppendCtx &ax, long long tb_clean,
                                              uint32_t far_row, unsigned long long alloc_limit,
                                              const RecBits &r) {
   uint32_t cell = cell_of_local(c, ax, tb_clean, far_row, r.time(), r.dst());
-  if (cell != SIMIAN_NONE) cell_append(c, ax, alloc_limit, cell, r);
+  if (cell != SIMIAN_NONE) cell_append<WIDE>(c, ax, alloc_limit, cell, r);
 }
 
 // ------------------------------------------------------------ init / load --
@@ -466,7 +478,7 @@ __global__ void k_sched_bulk(const __grid_constant__ DevCfg c, double time, uint
     if (rank != c.rank) continue; // only the owner pushes (simian.js:177)
     RecBits r = make_rec(time, slot, SIMIAN_NULL_ENTITY, handler, SIMIAN_EVF_SCHED,
                          seq_base + (uint32_t)idx, data);
-    append_local(c, ax, W.tb_clean, W.far_row, W.alloc_limit, r);
+    append_local<true>(c, ax, W.tb_clean, W.far_row, W.alloc_limit, r);
     napp++;
   }
   appended_flush(c, napp);
@@ -510,7 +522,7 @@ __global__ void k_ingest(const __grid_constant__ DevCfg c, const simian_event_t 
     }
     unsigned long long k = simian_time_key(r.time());
     mn = k < mn ? k : mn;
-    append_local(c, ax, W.tb_clean, W.far_row, W.alloc_limit, r);
+    append_local<true>(c, ax, W.tb_clean, W.far_row, W.alloc_limit, r);
     napp++;
   }
   appended_flush(c, napp);
@@ -583,7 +595,7 @@ __device__ __forceinline__ void pull_records(const DevCfg &c, const WinState &W,
             unsigned long long k = simian_time_key(r[u].time());
             mn = k < mn ? k : mn;
           }
-          append_local(c, ax, a_tb_clean, a_far_row, a_alloc_limit, r[u]);
+          append_local<true>(c, ax, a_tb_clean, a_far_row, a_alloc_limit, r[u]);
           napp++;
         }
     }
@@ -836,7 +848,9 @@ __device__ __forceinline__ void thread_acc_init(ThreadAcc &ta) {
 // what a handler reaches through `self` on the device (see simian_models.h)
 // SEQ: one thread per entity (stateful handlers, same-window self-sends);
 // !SEQ: one thread per event (pure handlers).
-template <bool SEQ>
+// WIDE: records are written with one 256-bit store (only where the context lives in
+// code that is force-inlined into a kernel body -- see st_rec_2x16).
+template <bool SEQ, bool WIDE = false>
 struct DevCtx {
   const DevCfg &c;
   const WinState &W; // window bound / recycle frontier / far row in force
@@ -899,7 +913,7 @@ struct DevCtx {
       slot_put(*stage_sh, stage, r);
       stage = SIMIAN_NONE;
     } else {
-      append_local(c, ax, W.tb_clean, W.far_row, W.alloc_limit, r);
+      append_local<WIDE>(c, ax, W.tb_clean, W.far_row, W.alloc_limit, r);
     }
   }
 
@@ -977,10 +991,7 @@ struct DevCtx {
       }
       simian_event_t *dst_rec =
           c.outbox + ((size_t)box * c.outbox_cap + (far ? c.outbox_cap - 1u - i : i));
-      if (SEQ) // (inside the __noinline__ per-entity function: see st_rec_2x16)
-        st_rec_2x16(dst_rec, r.q0, r.q1, r.q2, r.q3);
-      else
-        st_rec(dst_rec, r);
+      st_rec_sel<WIDE>(dst_rec, r);
     }
   }
 };
@@ -988,7 +999,8 @@ struct DevCtx {
 // Dispatch: generated from include/simian_handlers.def (attachService binds a
 // service name to one of these by name; simian.js:129-131 calls it).
 // The pure handlers only (thread-per-event path: simian_fn_is_pure).
-__device__ __forceinline__ void run_pure_handler(DevCtx<false> &ctx, uint32_t fn) {
+template <class Ctx>
+__device__ __forceinline__ void run_pure_handler(Ctx &ctx, uint32_t fn) {
   switch (fn) {
 #define SIMIAN_HANDLER(id, name, func, pure, ptype) \
   case id:                                          \
@@ -1002,8 +1014,8 @@ __device__ __forceinline__ void run_pure_handler(DevCtx<false> &ctx, uint32_t fn
   }
 }
 
-template <bool SEQ>
-__device__ __forceinline__ void run_handler(DevCtx<SEQ> &ctx, uint32_t fn) {
+template <class Ctx>
+__device__ __forceinline__ void run_handler(Ctx &ctx, uint32_t fn) {
   switch (fn) {
 #define SIMIAN_HANDLER(id, name, func, pure, ptype) \
   case id:                                          \
@@ -1033,7 +1045,7 @@ __global__ void k_construct(const __grid_constant__ DevCfg c, int cls, uint32_t 
   thread_acc_init(ta);
   for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < cl.n_local;
        j += gridDim.x * blockDim.x) {
-    DevCtx<false> ctx(c, W, ax, ta);
+    DevCtx<false, true> ctx(c, W, ax, ta);
     ctx.local_min = false;
     ctx.split_ok = false; // no window is open: everything is pulled before the first one
     int k;
@@ -1316,12 +1328,13 @@ __device__ __forceinline__ uint32_t rank_event(const DevCfg &c, WindowShared &sh
 // Phase A2, one thread per EVENT: the handler itself (simian.js:129-131): RNG,
 // log, destination.  Commit index = the entity's committed count + rank.  The
 // record it sends to a local entity replaces the consumed one in slot i.
+template <bool WIDE>
 __device__ __forceinline__ void run_event(const DevCfg &c, WindowShared &sh, ThreadAcc &ta,
                                           uint32_t slot0, uint32_t i, uint32_t rank) {
   const RecBits r = slot_get(sh, i);
   const uint32_t slot = r.dst();
   int k;
-  DevCtx<false> ctx(c, sh.W, sh.ax, ta);
+  DevCtx<false, WIDE> ctx(c, sh.W, sh.ax, ta);
   ctx.stage_sh = &sh;
   ctx.stage = i;
   ctx.self_slot = slot;
@@ -1641,7 +1654,8 @@ __device__ __forceinline__ void list_cell_pages(const DevCfg &c, WindowShared &s
 // acc->min_key already holds leftovers of row tb_hi + everything appended since
 // the last advance; rows above tb_hi are searched only when that candidate does
 // not already lie in row tb_hi (sparse case: the window jumped over idle time).
-__device__ void local_min_candidate(const DevCfg &c, const WinState &W, WindowShared &sh,
+template <class SH>
+__device__ void local_min_candidate(const DevCfg &c, const WinState &W, SH &sh,
                                     unsigned long long &cand_out,
                                     unsigned long long &far_out) {
   const int tid = threadIdx.x;
@@ -1852,7 +1866,8 @@ __device__ void redistribute_block(const DevCfg &c, WindowShared &sh, uint32_t b
 // CTAs add into SIMIAN_PART_SLOTS accumulator slots (block index mod slots), so
 // this is ONE round trip, not a loop over the blocks; the slots are cleared
 // for the next launch.
-__device__ void reduce_parts(const DevCfg &c, WindowShared &sh) {
+template <class SH>
+__device__ void reduce_parts(const DevCfg &c, SH &sh) {
   const int tid = threadIdx.x;
   __shared__ unsigned long long red[10];
   if (tid < 10) red[tid] = tid == 0 ? SIMIAN_KEY_NONE : 0ull;
@@ -1905,7 +1920,8 @@ __device__ void reduce_parts(const DevCfg &c, WindowShared &sh) {
 // per peer writes the candidate into the peer's slot array -- data, fence, flag.
 // One CTA, all threads; the launch's results must be visible (ticket fence or
 // a kernel boundary).
-__device__ void lbts_candidate(const DevCfg &c, const WinState &W, WindowShared &sh, uint32_t win_ix,
+template <class SH>
+__device__ void lbts_candidate(const DevCfg &c, const WinState &W, SH &sh, uint32_t win_ix,
                                int publish) {
   unsigned long long cand, far;
   if (!W.done) reduce_parts(c, sh);
@@ -1939,6 +1955,11 @@ __device__ void lbts_candidate(const DevCfg &c, const WinState &W, WindowShared 
 // K3 + K4 + trace chain for the m due events one pass collected into the
 // shared-memory slots (entities [e_lo, e_hi) of the block).  CTA-uniform.
 // `live`: bit u = slot (threadIdx.x + u * NTHREADS) holds a due event of this thread.
+// STAGE (split window, k_window_stage): after the rank phase the events are parked
+// in HBM for k_emit -- compacted, each with its commit index -- instead of running
+// their handlers here; the trace chain follows at once.
+// WIDE: the pass is inlined into a kernel body (256-bit record stores allowed).
+template <bool STAGE, bool WIDE>
 __device__ __forceinline__ void process_pass(const DevCfg &c, WindowShared &sh, ThreadAcc &ta,
                                              uint32_t slot0, uint32_t live, uint32_t e_lo,
                                              uint32_t e_hi) {
@@ -1959,12 +1980,39 @@ __device__ __forceinline__ void process_pass(const DevCfg &c, WindowShared &sh, 
     cp_async_wait_all(); // the entities' {count, hash} (link_due)
     __syncthreads();
     PHASE(3);
+    if constexpr (STAGE) {
+      simian_event_t *out = c.stage + (size_t)blockIdx.x * NREFS;
+      const uint32_t lane = (uint32_t)tid & 31u;
+#pragma unroll
+      for (int u = 0; u < EV_PER_THREAD; u++) {
+        const bool lv = (live >> u) & 1u;
+        const unsigned m = __ballot_sync(0xffffffffu, lv);
+        if (!m) continue; // (warp-uniform)
+        uint32_t p0 = 0;
+        if (lane == 0) p0 = atomicAdd(&sh.total, (uint32_t)__popc(m));
+        p0 = __shfl_sync(0xffffffffu, p0, 0);
+        if (lv) {
+          RecBits r = slot_get(sh, tid + u * NTHREADS);
+          const unsigned long long ci =
+              SH_CORE(sh)[r.dst() - slot0].count + ((rkpack >> (8 * u)) & 255u);
+          if (ci >> 48) set_error(c, SIMIAN_ERR_ENTITY_BURST); // (2.8e14 commits of one entity)
+          r.q2 = (r.q2 & 0xFFFFull) | (ci << 16);
+          st_rec(out + p0 + __popc(m & ((1u << lane) - 1u)), r);
+        }
+      }
+      PHASE(4);
+      for (uint32_t le = e_lo + tid; le < e_hi; le += NTHREADS) {
+        uint32_t f = sh.head[le];
+        if (f != LIST_END) chain_entity(c, sh, slot0 + le, le, f);
+      }
+      PHASE(5);
+    } else {
     // A2 (K3), one thread per EVENT: handler; the sent record is staged in
     // the consumed record's slot
 #pragma unroll 1
     for (int u = 0; u < EV_PER_THREAD; u++) {
       uint32_t i = tid + u * NTHREADS;
-      if (live & (1u << u)) run_event(c, sh, ta, slot0, i, (rkpack >> (8 * u)) & 255u);
+      if (live & (1u << u)) run_event<WIDE>(c, sh, ta, slot0, i, (rkpack >> (8 * u)) & 255u);
     }
     PHASE(4); // (no barrier: phase B reads only the slots its own thread staged)
     // B (K4), one thread per EVENT: append the staged records; the claims
@@ -2005,7 +2053,8 @@ __device__ __forceinline__ void process_pass(const DevCfg &c, WindowShared &sh, 
           if (CELL_COUNT(old[u]) <= (uint32_t)PAGE) { // lands in a page, or installs one
             const RecBits r = slot_get(sh, tid + u * NTHREADS);
             if ((uint32_t)old[u] < (uint32_t)PAGE)
-              st_rec(c.pool + ((size_t)(uint32_t)(old[u] >> 32) * PAGE + (uint32_t)old[u]), r);
+              st_rec_sel<WIDE>(
+                  c.pool + ((size_t)(uint32_t)(old[u] >> 32) * PAGE + (uint32_t)old[u]), r);
             else
               cell_append_slow(c, sh.ax, W.alloc_limit, c.cell_state + cell[u], old[u], r.q0,
                                r.q1, r.q2, r.q3);
@@ -2024,6 +2073,7 @@ __device__ __forceinline__ void process_pass(const DevCfg &c, WindowShared &sh, 
       }
     }
     PHASE(5);
+    } // (!STAGE)
   } else {
     cp_async_wait_all(); // the entities' {count, hash} (link_due)
     // no deferred sum is parked on any slot yet (xs is otherwise unused on this path)
@@ -2087,7 +2137,8 @@ __device__ __forceinline__ void process_pass(const DevCfg &c, WindowShared &sh, 
 }
 
 // per-thread accumulators -> the CTA's accumulators in shared memory (K1)
-__device__ __forceinline__ void accumulate_block(WindowShared &sh, const ThreadAcc &ta) {
+template <class SH>
+__device__ __forceinline__ void accumulate_block(SH &sh, const ThreadAcc &ta) {
   unsigned long long mn = warp_min_u64(ta.min_key), mx = warp_max_u64(ta.max_key);
   uint32_t s0 = __reduce_add_sync(0xffffffffu, ta.committed);
   uint32_t s1 = __reduce_add_sync(0xffffffffu, ta.emitted);
@@ -2158,7 +2209,7 @@ __device__ __noinline__ void filtered_passes(const DevCfg &c, WindowShared &sh, 
         }
       }
     } else if (m && m <= NREFS) {
-      process_pass(c, sh, ta, slot0, live_below(m), e_lo, e_hi);
+      process_pass<false, false>(c, sh, ta, slot0, live_below(m), e_lo, e_hi);
     }
     part_ok = false; // only the first (whole-block) overflow is partitioned
     __syncthreads();
@@ -2219,10 +2270,12 @@ __device__ __forceinline__ uint32_t window_cta_begin(const DevCfg &c, WindowShar
 // One lookahead window (or one redistribution pass) for entity block b: K2a
 // list -> K2 dequeue -> K3 handlers -> K4 emit -> recycle -> the CTA's results
 // into its BlockPart slot.  All threads of the CTA.
+template <bool SPLIT>
 __device__ __forceinline__ void window_cta_body(const DevCfg &c, WindowShared &sh, uint32_t b) {
   const int tid = threadIdx.x;
   const WinState &W = sh.W;
   PHASE(0);
+  bool staged = false; // SPLIT: this window's events were parked for k_emit
 
   ThreadAcc ta;
   thread_acc_init(ta);
@@ -2282,7 +2335,8 @@ __device__ __forceinline__ void window_cta_body(const DevCfg &c, WindowShared &s
       const uint32_t live = link_due(c, sh, ta, slot0, nvalid);
       __syncthreads();
       PHASE(2);
-      process_pass(c, sh, ta, slot0, live, 0, c.epb);
+      process_pass<SPLIT, true>(c, sh, ta, slot0, live, 0, c.epb);
+      staged = SPLIT && c.all_pure;
     } else {
       filtered_passes(c, sh, slot0, npg);
       npg = sh.npg; // scratch pages of a partition are recycled with the others
@@ -2291,6 +2345,7 @@ __device__ __forceinline__ void window_cta_body(const DevCfg &c, WindowShared &s
     PHASE(6);
   }
   __syncthreads();
+  if (SPLIT && tid == 0) c.stage_n[b] = staged ? sh.total : 0u;
   // ---- recycle: the pages of rows [tb_clean, tb_hi) go onto the block's own
   // page stack (what does not fit: to the global ring), heads are cleared.  The
   // stack lives in HBM (bcache[b]); the entries below the ones popped in this
@@ -2371,6 +2426,41 @@ __device__ __forceinline__ void window_cta_body(const DevCfg &c, WindowShared &s
   PHASE(8);
 }
 
+// End of a window launch: the last CTA to finish does the LBTS step
+// (simian.js:143-147).  fuse_advance: 1 (size == 1): it computes window k+1;
+// 2 / 3 (size > 1): this rank's LBTS candidate (3: and publishes it to the peers'
+// exchange slots); 0: nothing.  All threads of every CTA of the launch.
+template <class SH>
+__device__ __forceinline__ void window_tail(const DevCfg &c, SH &sh, uint32_t win_ix,
+                                            int fuse_advance) {
+  const int tid = threadIdx.x;
+  const WinState &W = sh.W;
+  if (!fuse_advance) return;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) sh.is_last = (atomicAdd(&c.acc->ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!sh.is_last) return;
+  __threadfence();
+  if (fuse_advance >= 2) {
+    lbts_candidate(c, W, sh, win_ix, fuse_advance == 3);
+    return;
+  }
+  reduce_parts(c, sh);
+  WinState *Wn = &c.win[(win_ix + 1u) & 1u];
+  if (W.redist) {
+    setup_next_window(c, W, Wn, W.gmin, 0.0, true);
+  } else {
+    unsigned long long cand, far;
+    local_min_candidate(c, W, sh, cand, far);
+    double gmin = cand == SIMIAN_KEY_NONE ? c.inf_time : simian_key_time(cand); // simian.js:147
+    double farT = far == SIMIAN_KEY_NONE ? __longlong_as_double(0x7FF0000000000000LL)
+                                         : simian_key_time(far);
+    setup_next_window(c, W, Wn, gmin, farT, false);
+  }
+  PHASE(9);
+}
+
 // One lookahead window (or one redistribution pass) for entity block blockIdx.x.
 // fuse_advance: 1 (size == 1): the last CTA to finish computes window k+1;
 // 2 / 3 (size > 1): the last CTA computes this rank's LBTS candidate (3: and
@@ -2440,35 +2530,114 @@ __global__ void __launch_bounds__(NTHREADS, SIMIAN_MINBLOCKS)
     }
   } else {
     if (window_cta_begin(c, sh, Wg, b)) return; // sticky error: CTA-uniform exit
-    window_cta_body(c, sh, b);
+    window_cta_body<false>(c, sh, b);
   }
-  const WinState &W = sh.W;
-  if (!fuse_advance) return;
-  // ---- last CTA computes the next window (simian.js:147)
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) sh.is_last = (atomicAdd(&c.acc->ticket, 1u) == gridDim.x - 1);
-  __syncthreads();
-  if (!sh.is_last) return;
-  __threadfence();
-  if (fuse_advance >= 2) {
-    lbts_candidate(c, W, sh, win_ix, fuse_advance == 3);
-    return;
-  }
-  reduce_parts(c, sh);
-  WinState *Wn = &c.win[(win_ix + 1u) & 1u];
-  if (W.redist) {
-    setup_next_window(c, W, Wn, W.gmin, 0.0, true);
-  } else {
-    unsigned long long cand, far;
-    local_min_candidate(c, W, sh, cand, far);
-    double gmin = cand == SIMIAN_KEY_NONE ? c.inf_time : simian_key_time(cand); // simian.js:147
-    double farT = far == SIMIAN_KEY_NONE ? __longlong_as_double(0x7FF0000000000000LL)
-                                         : simian_key_time(far);
-    setup_next_window(c, W, Wn, gmin, farT, false);
-  }
-  PHASE(9);
+  window_tail(c, sh, win_ix, fuse_advance);
 }
+
+#ifndef SIMIAN_LOOP_TU
+// ---- the split window (option "split_handlers"; pure handlers) ---------------
+// k_window_stage: K2a list -> K2 dequeue -> A1 rank -> park the ranked events in
+// HBM (c.stage) -> C trace chain -> recycle.  No handler runs here (except on the
+// out-of-line burst path, which keeps the one-kernel form), so the CTA's chain of
+// dependent round trips ends earlier; the LBTS step belongs to k_emit.
+__global__ void __launch_bounds__(NTHREADS, SIMIAN_MINBLOCKS)
+    k_window_stage(const __grid_constant__ DevCfg c, uint32_t win_ix) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  WindowShared &sh = *reinterpret_cast<WindowShared *>(smem_raw);
+  cudaTriggerProgrammaticLaunchCompletion();
+  cudaGridDependencySynchronize();
+  const WinState *Wg = &c.win[win_ix & 1u];
+  if (Wg->done) return; // simian.js:119
+  if (window_cta_begin(c, sh, Wg, blockIdx.x)) return; // sticky error
+  window_cta_body<true>(c, sh, blockIdx.x);
+}
+
+#ifndef SIMIAN_EMIT_MINBLOCKS
+#define SIMIAN_EMIT_MINBLOCKS 5
+#endif
+struct __align__(16) EmitShared {
+  WinState W;
+  AppendCtx ax;
+  unsigned long long min_key, max_key;
+  uint32_t committed, emitted, dropped, ties, dties, appended;
+  uint32_t found, is_last, n;
+  long long scan_j, t_last;
+};
+
+// k_emit: K3 + K4 of the split window, one thread per parked event: the handler
+// (simian.js:129-131) with the commit index k_window_stage gave the event, every
+// record it sends appended straight to the destination cell (or the peer's
+// outbox).  Needs no lists and little shared memory: five CTAs per SM instead of
+// three hide the latency of the claims and of the f64 arithmetic.  The last CTA
+// does the LBTS step (fuse_advance as in k_window).
+__global__ void __launch_bounds__(NTHREADS, SIMIAN_EMIT_MINBLOCKS)
+    k_emit(const __grid_constant__ DevCfg c, uint32_t win_ix, int fuse_advance) {
+  __shared__ EmitShared sh;
+  const int tid = threadIdx.x;
+  const uint32_t b = blockIdx.x;
+  cudaTriggerProgrammaticLaunchCompletion();
+  cudaGridDependencySynchronize();
+  const WinState *Wg = &c.win[win_ix & 1u];
+  if (Wg->done) return;
+  if (tid == 0) {
+    sh.found = ld_cg(&c.acc->error);
+    sh.W = *Wg;
+    sh.n = c.stage_n[b];
+    sh.min_key = SIMIAN_KEY_NONE;
+    sh.max_key = 0;
+    sh.committed = sh.emitted = sh.dropped = sh.ties = sh.dties = sh.appended = 0;
+    sh.is_last = 0;
+    sh.ax.far_appends = sh.ax.page_allocs = sh.ax.pgc_take = 0;
+    sh.ax.pgc_have = c.bcount[b];
+    sh.t_last = clock64();
+  }
+  if (tid < SIMIAN_BC) sh.ax.pgc[tid] = c.bcache[(size_t)b * SIMIAN_BC + tid];
+  __syncthreads();
+  if (sh.found) return; // sticky error: CTA-uniform exit, the window does not advance
+  const uint32_t n = sh.n < (uint32_t)NREFS ? sh.n : (uint32_t)NREFS;
+  ThreadAcc ta;
+  thread_acc_init(ta);
+  const simian_event_t *in = c.stage + (size_t)b * NREFS;
+#pragma unroll 1
+  for (uint32_t i = tid; i < n; i += NTHREADS) {
+    const RecBits r = ld_rec(in + i);
+    int k;
+    DevCtx<false, true> ctx(c, sh.W, sh.ax, ta);
+    ctx.self_slot = r.dst();
+    ctx.self_gid = gid_of_slot(c, ctx.self_slot, k);
+    ctx.cl = &c.cls[k];
+    ctx.commit_idx = r.q2 >> 16;
+    ctx.key = simian_rng_key(c.seed, ctx.self_gid, ctx.commit_idx);
+    ctx.n_emit = 0;
+    ctx.now_ = r.time(); // simian.js:126
+    ctx.handler_ = r.handler();
+    ctx.src_ = r.src();
+    ctx.data_ = r.data();
+    const uint32_t h = r.handler();
+    run_pure_handler(ctx, h < SIMIAN_MAX_SERVICES ? ctx.cl->fn_of_service[h] : 0);
+  }
+  accumulate_block(sh, ta);
+  __syncthreads();
+  if (tid == 0 && sh.ax.pgc_take) { // pages popped from the block's stack
+    const uint32_t have = sh.ax.pgc_have;
+    c.bcount[b] = have - (sh.ax.pgc_take < have ? sh.ax.pgc_take : have);
+  }
+  if (tid < 10) { // one thread per field: independent, result-less atomics
+    BlockPart *p = &c.part[b % SIMIAN_PART_SLOTS];
+    switch (tid) {
+      case 0: if (sh.min_key != SIMIAN_KEY_NONE) atomicMin(&p->min_key, sh.min_key); break;
+      case 3: if (sh.emitted) atomicAdd(&p->emitted, sh.emitted); break;
+      case 4: if (sh.dropped) atomicAdd(&p->dropped, sh.dropped); break;
+      case 7: if (sh.appended) atomicAdd(&p->appended, sh.appended); break;
+      case 8: if (sh.ax.far_appends) atomicAdd(&p->far_appends, sh.ax.far_appends); break;
+      case 9: if (sh.ax.page_allocs) atomicAdd(&p->page_allocs, sh.ax.page_allocs); break;
+      default: break;
+    }
+  }
+  window_tail(c, sh, win_ix, fuse_advance);
+}
+#endif
 
 #ifdef SIMIAN_LOOP_TU
 // The window loop of simian.js:118-149 INSIDE one launch, for models whose entity
@@ -2494,7 +2663,7 @@ __global__ void __launch_bounds__(NTHREADS, SIMIAN_MINBLOCKS)
     // (the descriptor was written by another CTA of this launch: read through L2)
     if (ld_cg(&Wg->done)) return; // simian.js:119
     if (window_cta_begin(c, sh, Wg, b)) return; // sticky error: CTA-uniform exit
-    window_cta_body(c, sh, b);
+    window_cta_body<false>(c, sh, b);
     // ---- grid barrier; the last CTA to arrive computes the next window
     __threadfence();
     __syncthreads();
