@@ -104,7 +104,14 @@ const char *simian_last_error(simian_engine *e);
  *                     (measured equal: DESIGN.md section 7)
  *   "pdl"             1: window kernels are launched as programmatic dependents of
  *                     each other, the next window's CTAs become resident while the
- *                     previous one drains (default 1; size == 1)                  */
+ *                     previous one drains (default 1; size == 1)
+ *   "split_handlers"  1: models of pure handlers run a window as three launches --
+ *                     k_window_stage (dequeue, rank, park the events with their commit
+ *                     indices, trace chain, recycle; 48 registers), k_window_rest
+ *                     (bursts and redistribution passes in the one-kernel form) and
+ *                     k_emit (handlers + appends, a persistent grid of warps) -- instead
+ *                     of one; same results bit for bit.  Default 0: measured equal to
+ *                     the one-kernel window on config 2         */
 int simian_set_option(simian_engine *e, const char *key, double value);
 
 /* Entity classes.  An entity class = the `name` of addEntity plus the JS class

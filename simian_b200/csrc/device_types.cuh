@@ -42,6 +42,10 @@
 #define SIMIAN_MINBLOCKS 3 // __launch_bounds__ min CTAs/SM of the window kernel
 #endif
 
+#ifndef SIMIAN_STAGE_MINBLOCKS
+#define SIMIAN_STAGE_MINBLOCKS 3 // min CTAs/SM of k_window_stage (the split window)
+#endif
+
 #define SIMIAN_MAX_RANKS 16 // GPUs of one box (peer memory over NVLink)
 #define SIMIAN_FAR_COUNT_OFF 64 // uint32 offset of the far-end counters behind outbox_count
 #define SIMIAN_MAX_CLASSES 8

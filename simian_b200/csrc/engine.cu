@@ -21,7 +21,7 @@
 #include "kernels.cuh"
 
 #ifndef SIMIAN_SPLIT_DEFAULT
-#define SIMIAN_SPLIT_DEFAULT 1 // option "split_handlers" when the model does not say
+#define SIMIAN_SPLIT_DEFAULT 0 // option "split_handlers" when the model does not say
 #endif
 
 extern "C" void simian_trim_cache(void);
@@ -182,6 +182,8 @@ struct simian_engine {
   // handlers only; -1 = the default for the model (see setup_layout)
   int split = -1;
   bool split_on = false; // in force for this layout
+  uint32_t rest_ctas = 444; // grid of k_window_rest: the CTAs resident at once
+  uint32_t emit_ctas = 740; // grid of k_emit: the CTAs resident at once
   bool loop_ok = false;      // every entity block's CTA is resident at once (set at layout)
   // model
   std::vector<HostClass> classes;
@@ -339,6 +341,8 @@ int setup_layout(simian_engine *e) {
                           (int)WINDOW_SMEM_BYTES(SIMIAN_EPB_MAX)));
   CK(cudaFuncSetAttribute(k_window_stage, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           (int)WINDOW_SMEM_BYTES(SIMIAN_EPB_MAX)));
+  CK(cudaFuncSetAttribute(k_window_rest, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          (int)WINDOW_SMEM_BYTES(SIMIAN_EPB_MAX)));
   memset(&c, 0, sizeof c);
   c.start = e->start;
   c.end = e->end;
@@ -468,6 +472,21 @@ int setup_layout(simian_engine *e) {
   c.stage = nullptr;
   c.stage_n = nullptr;
   if (e->split_on) {
+    int sms = 0, per_sm = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->device);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_window_rest, NTHREADS,
+                                                      e->smem_bytes) != cudaSuccess || per_sm < 1) {
+      cudaGetLastError();
+      per_sm = 1;
+    }
+    e->rest_ctas = (uint32_t)(per_sm * (sms > 0 ? sms : 148));
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_emit, NTHREADS, 0) != cudaSuccess ||
+        per_sm < 1) {
+      cudaGetLastError();
+      per_sm = 1;
+    }
+    e->emit_ctas = (uint32_t)(per_sm * (sms > 0 ? sms : 148));
+    if (const char *env = getenv("SIMIAN_B200_EMIT_CTAS")) e->emit_ctas = (uint32_t)atoi(env); // (tuning)
     if (dev_alloc(e, &c.stage, (size_t)c.n_blocks * NREFS)) return e->err_code;
     if (dev_alloc(e, &c.stage_n, c.n_blocks)) return e->err_code;
     CK(cudaMemsetAsync(c.stage_n, 0, sizeof(uint32_t) * (size_t)c.n_blocks, e->stream));
@@ -1105,9 +1124,16 @@ static int launch_window(simian_engine *e, int fuse, uint32_t pull_blocks, bool 
     lc.gridDim = dim3(e->cfg.n_blocks);
     lc.dynamicSmemBytes = e->smem_bytes;
     CK(cudaLaunchKernelEx(&lc, k_window_stage, e->cfg, e->win_ix));
+    // the blocks k_window_stage left alone (bursts, redistribution passes): a grid of
+    // resident CTAs looping over the blocks; nothing to do in a steady window
+    lc.gridDim = dim3(e->cfg.n_blocks < e->rest_ctas ? e->cfg.n_blocks : e->rest_ctas);
+    CK(cudaLaunchKernelEx(&lc, k_window_rest, e->cfg, e->win_ix));
+    // k_emit: a persistent grid of warps striding over the blocks' chunks
+    const uint32_t want = (e->cfg.n_blocks * EMIT_CHUNKS_PER_BLOCK + EMIT_WARPS - 1) / EMIT_WARPS;
+    lc.gridDim = dim3(want < e->emit_ctas ? want : e->emit_ctas);
     lc.dynamicSmemBytes = 0;
     CK(cudaLaunchKernelEx(&lc, k_emit, e->cfg, e->win_ix, fuse));
-    e->launches += 2;
+    e->launches += 3;
     return 0;
   }
   lc.gridDim = dim3(e->cfg.n_blocks + pull_blocks);

@@ -246,6 +246,11 @@ struct AppendCtx { // per-CTA, in shared memory
   // a stack, popped from the top with a shared-memory atomic
   uint32_t pgc_take, pgc_have;
   uint32_t pgc[SIMIAN_BC];
+  // k_emit: the page stack of an entity block popped IN PLACE (HBM) with an atomic on
+  // its height -- several warps of several CTAs may work for the same block there;
+  // null elsewhere
+  uint32_t *gstack_count;
+  const uint32_t *gstack;
 };
 
 // head word of an empty cell: no page, "full" so the first append installs one
@@ -258,7 +263,11 @@ struct AppendCtx { // per-CTA, in shared memory
 #define CELL_COUNT(lo32) ((uint32_t)(lo32) & 0x7FFFFFFFu)
 
 __device__ __forceinline__ void append_ctx_init(AppendCtx &ax) {
-  if (threadIdx.x == 0) ax.far_appends = ax.page_allocs = ax.pgc_take = ax.pgc_have = 0;
+  if (threadIdx.x == 0) {
+    ax.far_appends = ax.page_allocs = ax.pgc_take = ax.pgc_have = 0;
+    ax.gstack_count = nullptr;
+    ax.gstack = nullptr;
+  }
 }
 
 // Pop a page from the free ring.  Pages pushed during a launch become
@@ -270,6 +279,11 @@ __device__ __forceinline__ uint32_t page_get(const DevCfg &c, AppendCtx &ax,
   if (ax.pgc_have) { // block cache first: a shared-memory atomic, no L2 round trip
     uint32_t k = atomicAdd(&ax.pgc_take, 1u);
     if (k < ax.pgc_have) return ax.pgc[ax.pgc_have - 1u - k];
+  }
+  if (ax.gstack_count) { // the block's stack in HBM: one atomic on its height
+    const int old = atomicSub((int *)ax.gstack_count, 1);
+    if (old > 0) return ld_cg(&ax.gstack[old - 1]);
+    atomicAdd((int *)ax.gstack_count, 1); // empty: undo, take from the ring
   }
   unsigned long long i = atomicAdd(&c.acc->alloc_head, 1ull);
   if (i >= alloc_limit) {
@@ -749,6 +763,9 @@ __global__ void k_pull(const __grid_constant__ DevCfg c, uint32_t win_ix, uint32
 // (k_construct, which needs the handler context, is defined after it below)
 
 #define LIST_END 0xFFFFu
+// stage_n[b] of a block whose window the split kernels leave to k_window_rest (a
+// burst that overflows the slots, or a redistribution pass)
+#define STAGE_REST 0xFFFFFFFFu
 #define EV_PER_THREAD ((NREFS + NTHREADS - 1) / NTHREADS)
 static_assert(EV_PER_THREAD <= 4, "ranks are packed 8 bits each into one register");
 #define RSTACK_MAX 80 // entity sub-ranges a CTA can have pending
@@ -819,7 +836,8 @@ struct __align__(32) WindowShared {
 #endif
 };
 
-__device__ __forceinline__ RecBits slot_get(const WindowShared &sh, uint32_t i) {
+template <class SH>
+__device__ __forceinline__ RecBits slot_get(const SH &sh, uint32_t i) {
   ulonglong2 a = SLOT_LO(sh, i), b = SLOT_HI(sh, i);
   RecBits r;
   r.q0 = a.x;
@@ -828,7 +846,8 @@ __device__ __forceinline__ RecBits slot_get(const WindowShared &sh, uint32_t i) 
   r.q3 = b.y;
   return r;
 }
-__device__ __forceinline__ void slot_put(WindowShared &sh, uint32_t i, const RecBits &r) {
+template <class SH>
+__device__ __forceinline__ void slot_put(SH &sh, uint32_t i, const RecBits &r) {
   SLOT_LO(sh, i) = make_ulonglong2(r.q0, r.q1);
   SLOT_HI(sh, i) = make_ulonglong2(r.q2, r.q3);
 }
@@ -863,10 +882,9 @@ struct DevCtx {
   double now_;
   uint32_t handler_, src_;
   unsigned long long data_;
-  // !SEQ: where the first locally routed record is staged (shared-memory slot
-  // index) instead of being appended right away; SIMIAN_NONE = append directly
-  WindowShared *stage_sh;
-  uint32_t stage;
+  // !SEQ: where the first locally routed record is staged (the two halves of a
+  // shared-memory slot) instead of being appended right away; null = append directly
+  ulonglong2 *stage_lo, *stage_hi;
   // fold the times of LOCALLY routed records into the LBTS candidate (window
   // kernel: yes; constructors: no -- the calendar search finds those, and a
   // candidate that a later window commits would move the window bounds)
@@ -885,7 +903,7 @@ struct DevCtx {
 
   __device__ __forceinline__ DevCtx(const DevCfg &c_, const WinState &W_, AppendCtx &ax_,
                                     ThreadAcc &ta_)
-      : c(c_), W(W_), ax(ax_), ta(ta_), stage_sh(nullptr), stage(SIMIAN_NONE), local_min(true),
+      : c(c_), W(W_), ax(ax_), ta(ta_), stage_lo(nullptr), stage_hi(nullptr), local_min(true),
         split_ok(true), job_sh(nullptr), job_slot(SIMIAN_NONE), job_count0(0), npend(0) {}
 
   __device__ __forceinline__ double now() const { return now_; }
@@ -909,9 +927,10 @@ struct DevCtx {
       ta.min_key = tk < ta.min_key ? tk : ta.min_key;
     }
     ta.appended++;
-    if (!SEQ && stage != SIMIAN_NONE) { // K4 is done by the append phase of k_window
-      slot_put(*stage_sh, stage, r);
-      stage = SIMIAN_NONE;
+    if (!SEQ && stage_lo) { // K4 is done by the append phase of k_window / k_emit
+      *stage_lo = make_ulonglong2(r.q0, r.q1);
+      *stage_hi = make_ulonglong2(r.q2, r.q3);
+      stage_lo = nullptr;
     } else {
       append_local<WIDE>(c, ax, W.tb_clean, W.far_row, W.alloc_limit, r);
     }
@@ -1335,8 +1354,8 @@ __device__ __forceinline__ void run_event(const DevCfg &c, WindowShared &sh, Thr
   const uint32_t slot = r.dst();
   int k;
   DevCtx<false, WIDE> ctx(c, sh.W, sh.ax, ta);
-  ctx.stage_sh = &sh;
-  ctx.stage = i;
+  ctx.stage_lo = &SLOT_LO(sh, i);
+  ctx.stage_hi = &SLOT_HI(sh, i);
   ctx.self_slot = slot;
   ctx.self_gid = gid_of_slot(c, slot, k);
   ctx.cl = &c.cls[k];
@@ -1349,7 +1368,7 @@ __device__ __forceinline__ void run_event(const DevCfg &c, WindowShared &sh, Thr
   ctx.data_ = r.data();
   uint32_t h = r.handler();
   run_pure_handler(ctx, h < SIMIAN_MAX_SERVICES ? ctx.cl->fn_of_service[h] : 0);
-  if (ctx.stage != SIMIAN_NONE) SLOT_LO(sh, i).y = 0xFFFFFFFFFFFFFFFFull; // nothing staged
+  if (ctx.stage_lo) SLOT_LO(sh, i).y = 0xFFFFFFFFFFFFFFFFull; // nothing staged
 }
 
 // Phase C, one thread per entity: fold the trace words, already in commit
@@ -1952,6 +1971,63 @@ __device__ void lbts_candidate(const DevCfg &c, const WinState &W, SH &sh, uint3
   }
 }
 
+// Phase B (K4), one thread per EVENT: append the records the handlers staged in the
+// shared-memory slots (slot i = threadIdx.x + u * NTHREADS for bit u of `live`; a
+// slot whose dst is NONE staged nothing).  The claims of all of a thread's events
+// are in flight together; `between` runs while they are.
+template <bool WIDE, int NEV, class SH, class F>
+__device__ __forceinline__ void append_staged(const DevCfg &c, SH &sh, AppendCtx &ax,
+                                              const WinState &W, uint32_t live, uint32_t base,
+                                              uint32_t stride, F between) {
+  unsigned long long old[NEV];
+  uint32_t cell[NEV];
+#pragma unroll
+  for (int u = 0; u < NEV; u++) {
+    uint32_t i = base + u * stride;
+    cell[u] = SIMIAN_NONE;
+    if (live & (1u << u)) {
+      ulonglong2 a = SLOT_LO(sh, i);
+      if ((uint32_t)a.y != SIMIAN_NONE)
+        cell[u] = cell_of_local(c, ax, W.tb_clean, W.far_row,
+                                __longlong_as_double((long long)a.x), (uint32_t)a.y);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < NEV; u++)
+    if (cell[u] != SIMIAN_NONE) old[u] = atomicAdd(c.cell_state + cell[u], 1ull);
+  between();
+  // Claims are serviced in two rounds so that no thread ever waits for a
+  // page while it still owes one: first every claim that landed in a
+  // page or must INSTALL one (never blocks); only then the claims that
+  // have to wait for another thread's install.  (Waiting first can
+  // deadlock: two threads holding crossed install/wait claims.)
+  uint32_t waiting = 0;
+#pragma unroll
+  for (int u = 0; u < NEV; u++)
+    if (cell[u] != SIMIAN_NONE) {
+      if (CELL_COUNT(old[u]) <= (uint32_t)PAGE) { // lands in a page, or installs one
+        const RecBits r = slot_get(sh, base + u * stride);
+        if ((uint32_t)old[u] < (uint32_t)PAGE)
+          st_rec_sel<WIDE>(
+              c.pool + ((size_t)(uint32_t)(old[u] >> 32) * PAGE + (uint32_t)old[u]), r);
+        else
+          cell_append_slow(c, ax, W.alloc_limit, c.cell_state + cell[u], old[u], r.q0, r.q1,
+                           r.q2, r.q3);
+      } else {
+        waiting |= 1u << u;
+      }
+    }
+  if (waiting) { // rare
+#pragma unroll
+    for (int u = 0; u < NEV; u++)
+      if (waiting & (1u << u)) {
+        const RecBits r = slot_get(sh, base + u * stride);
+        cell_append_slow(c, ax, W.alloc_limit, c.cell_state + cell[u], old[u], r.q0, r.q1,
+                         r.q2, r.q3);
+      }
+  }
+}
+
 // K3 + K4 + trace chain for the m due events one pass collected into the
 // shared-memory slots (entities [e_lo, e_hi) of the block).  CTA-uniform.
 // `live`: bit u = slot (threadIdx.x + u * NTHREADS) holds a due event of this thread.
@@ -2015,66 +2091,18 @@ __device__ __forceinline__ void process_pass(const DevCfg &c, WindowShared &sh, 
       if (live & (1u << u)) run_event<WIDE>(c, sh, ta, slot0, i, (rkpack >> (8 * u)) & 255u);
     }
     PHASE(4); // (no barrier: phase B reads only the slots its own thread staged)
-    // B (K4), one thread per EVENT: append the staged records; the claims
-    // of all of a thread's events are in flight together
-    {
-      unsigned long long old[EV_PER_THREAD];
-      uint32_t cell[EV_PER_THREAD];
-#pragma unroll
-      for (int u = 0; u < EV_PER_THREAD; u++) {
-        uint32_t i = tid + u * NTHREADS;
-        cell[u] = SIMIAN_NONE;
-        if (live & (1u << u)) {
-          ulonglong2 a = SLOT_LO(sh, i);
-          if ((uint32_t)a.y != SIMIAN_NONE)
-            cell[u] = cell_of_local(c, sh.ax, W.tb_clean, W.far_row,
-                                    __longlong_as_double((long long)a.x), (uint32_t)a.y);
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < EV_PER_THREAD; u++)
-        if (cell[u] != SIMIAN_NONE) old[u] = atomicAdd(c.cell_state + cell[u], 1ull);
-      // C, one thread per entity, while the claims are in flight: fold the trace
-      // hash chain, publish the count (reads what phase A1 parked; A2 / B only
-      // touch the record slots)
+    // B (K4) with C (trace chain) folded while the claims are in flight
+    append_staged<WIDE, EV_PER_THREAD>(c, sh, sh.ax, W, live, (uint32_t)tid, (uint32_t)NTHREADS, [&]() {
+      // C, one thread per entity: fold the trace hash chain, publish the count
+      // (reads what phase A1 parked; A2 / B only touch the record slots)
       for (uint32_t le = e_lo + tid; le < e_hi; le += NTHREADS) {
         uint32_t f = sh.head[le];
         if (f != LIST_END) chain_entity(c, sh, slot0 + le, le, f);
       }
-      // Claims are serviced in two rounds so that no thread ever waits for a
-      // page while it still owes one: first every claim that landed in a
-      // page or must INSTALL one (never blocks); only then the claims that
-      // have to wait for another thread's install.  (Waiting first can
-      // deadlock: two threads holding crossed install/wait claims.)
-      uint32_t waiting = 0;
-#pragma unroll
-      for (int u = 0; u < EV_PER_THREAD; u++)
-        if (cell[u] != SIMIAN_NONE) {
-          if (CELL_COUNT(old[u]) <= (uint32_t)PAGE) { // lands in a page, or installs one
-            const RecBits r = slot_get(sh, tid + u * NTHREADS);
-            if ((uint32_t)old[u] < (uint32_t)PAGE)
-              st_rec_sel<WIDE>(
-                  c.pool + ((size_t)(uint32_t)(old[u] >> 32) * PAGE + (uint32_t)old[u]), r);
-            else
-              cell_append_slow(c, sh.ax, W.alloc_limit, c.cell_state + cell[u], old[u], r.q0,
-                               r.q1, r.q2, r.q3);
-          } else {
-            waiting |= 1u << u;
-          }
-        }
-      if (waiting) { // rare
-#pragma unroll
-        for (int u = 0; u < EV_PER_THREAD; u++)
-          if (waiting & (1u << u)) {
-            const RecBits r = slot_get(sh, tid + u * NTHREADS);
-            cell_append_slow(c, sh.ax, W.alloc_limit, c.cell_state + cell[u], old[u], r.q0,
-                             r.q1, r.q2, r.q3);
-          }
-      }
-    }
+    });
     PHASE(5);
     } // (!STAGE)
-  } else {
+  } else if constexpr (!STAGE) { // (the split window is for models of pure handlers only)
     cp_async_wait_all(); // the entities' {count, hash} (link_due)
     // no deferred sum is parked on any slot yet (xs is otherwise unused on this path)
 #pragma unroll
@@ -2262,6 +2290,8 @@ __device__ __forceinline__ uint32_t window_cta_begin(const DevCfg &c, WindowShar
     sh.is_last = 0;
     sh.ax.far_appends = sh.ax.page_allocs = sh.ax.pgc_take = 0;
     sh.ax.pgc_have = ld_cg(&c.bcount[b]);
+    sh.ax.gstack_count = nullptr;
+    sh.ax.gstack = nullptr;
   }
   __syncthreads();
   return sh.found;
@@ -2283,7 +2313,12 @@ __device__ __forceinline__ void window_cta_body(const DevCfg &c, WindowShared &s
   int ncell = 0;
 
   if (W.redist) {
-    redistribute_block(c, sh, b);
+    if constexpr (SPLIT) { // left to k_window_rest
+      if (tid == 0) c.stage_n[b] = STAGE_REST;
+      return;
+    } else {
+      redistribute_block(c, sh, b);
+    }
   } else {
     // ---- K2a: list the pages of this block's cells in rows [tb_lo, tb_hi]
     ncell = (int)(W.tb_hi - W.tb_lo + 1);
@@ -2336,11 +2371,16 @@ __device__ __forceinline__ void window_cta_body(const DevCfg &c, WindowShared &s
       __syncthreads();
       PHASE(2);
       process_pass<SPLIT, true>(c, sh, ta, slot0, live, 0, c.epb);
-      staged = SPLIT && c.all_pure;
+      staged = SPLIT;
     } else {
-      filtered_passes(c, sh, slot0, npg);
-      npg = sh.npg; // scratch pages of a partition are recycled with the others
-      if (npg > PGMAX) npg = 0;
+      if constexpr (SPLIT) { // a burst: left to k_window_rest (nothing was touched yet)
+        if (tid == 0) c.stage_n[b] = STAGE_REST;
+        return;
+      } else {
+        filtered_passes(c, sh, slot0, npg);
+        npg = sh.npg; // scratch pages of a partition are recycled with the others
+        if (npg > PGMAX) npg = 0;
+      }
     }
     PHASE(6);
   }
@@ -2496,6 +2536,8 @@ __global__ void __launch_bounds__(NTHREADS, SIMIAN_MINBLOCKS)
       sh.committed = sh.emitted = sh.dropped = sh.ties = sh.dties = sh.appended = 0;
       sh.is_last = 0;
       sh.ax.far_appends = sh.ax.page_allocs = sh.ax.pgc_take = sh.ax.pgc_have = 0;
+      sh.ax.gstack_count = nullptr;
+      sh.ax.gstack = nullptr;
     }
     __syncthreads();
     if (sh.found) return;
@@ -2536,12 +2578,20 @@ __global__ void __launch_bounds__(NTHREADS, SIMIAN_MINBLOCKS)
 }
 
 #ifndef SIMIAN_LOOP_TU
-// ---- the split window (option "split_handlers"; pure handlers) ---------------
-// k_window_stage: K2a list -> K2 dequeue -> A1 rank -> park the ranked events in
-// HBM (c.stage) -> C trace chain -> recycle.  No handler runs here (except on the
-// out-of-line burst path, which keeps the one-kernel form), so the CTA's chain of
-// dependent round trips ends earlier; the LBTS step belongs to k_emit.
-__global__ void __launch_bounds__(NTHREADS, SIMIAN_MINBLOCKS)
+// ---- the split window (option "split_handlers"; models of pure handlers) -------
+// One window = three launches, chained by programmatic dependent launch:
+//   k_window_stage  K2a list -> K2 dequeue -> A1 rank -> park the ranked events in HBM
+//                   (c.stage: {time, dst | src << 32, handler | commit index << 16, data},
+//                   compacted) -> C trace chain -> recycle.  The common window only:
+//                   no handler, no burst path, no redistribution in its call graph, so
+//                   it needs 60 registers instead of the 102 the one-kernel window wants.
+//   k_window_rest   the one-kernel window (window_cta_body<false>) for the blocks
+//                   k_window_stage flagged (STAGE_REST): bursts that overflow the slots,
+//                   redistribution passes.  A few CTAs looping over the blocks; they
+//                   find nothing to do in a steady window.
+//   k_emit          K3 + K4: the handlers of the parked events, their records appended;
+//                   then the LBTS step (last CTA).
+__global__ void __launch_bounds__(NTHREADS, SIMIAN_STAGE_MINBLOCKS)
     k_window_stage(const __grid_constant__ DevCfg c, uint32_t win_ix) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   WindowShared &sh = *reinterpret_cast<WindowShared *>(smem_raw);
@@ -2553,85 +2603,167 @@ __global__ void __launch_bounds__(NTHREADS, SIMIAN_MINBLOCKS)
   window_cta_body<true>(c, sh, blockIdx.x);
 }
 
-#ifndef SIMIAN_EMIT_MINBLOCKS
-#define SIMIAN_EMIT_MINBLOCKS 5
-#endif
-struct __align__(16) EmitShared {
-  WinState W;
-  AppendCtx ax;
-  unsigned long long min_key, max_key;
-  uint32_t committed, emitted, dropped, ties, dties, appended;
-  uint32_t found, is_last, n;
-  long long scan_j, t_last;
-};
-
-// k_emit: K3 + K4 of the split window, one thread per parked event: the handler
-// (simian.js:129-131) with the commit index k_window_stage gave the event, every
-// record it sends appended straight to the destination cell (or the peer's
-// outbox).  Needs no lists and little shared memory: five CTAs per SM instead of
-// three hide the latency of the claims and of the f64 arithmetic.  The last CTA
-// does the LBTS step (fuse_advance as in k_window).
-__global__ void __launch_bounds__(NTHREADS, SIMIAN_EMIT_MINBLOCKS)
-    k_emit(const __grid_constant__ DevCfg c, uint32_t win_ix, int fuse_advance) {
-  __shared__ EmitShared sh;
-  const int tid = threadIdx.x;
-  const uint32_t b = blockIdx.x;
+__global__ void __launch_bounds__(NTHREADS, SIMIAN_MINBLOCKS)
+    k_window_rest(const __grid_constant__ DevCfg c, uint32_t win_ix) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  WindowShared &sh = *reinterpret_cast<WindowShared *>(smem_raw);
   cudaTriggerProgrammaticLaunchCompletion();
   cudaGridDependencySynchronize();
   const WinState *Wg = &c.win[win_ix & 1u];
   if (Wg->done) return;
-  if (tid == 0) {
-    sh.found = ld_cg(&c.acc->error);
-    sh.W = *Wg;
-    sh.n = c.stage_n[b];
+#pragma unroll 1
+  for (uint32_t b = blockIdx.x; b < c.n_blocks; b += gridDim.x) {
+    if (c.stage_n[b] != STAGE_REST) continue; // (CTA-uniform)
+    __syncthreads();                          // every thread has read the flag
+    if (threadIdx.x == 0) c.stage_n[b] = 0u;  // nothing parked: k_emit skips the block
+    if (window_cta_begin(c, sh, Wg, b)) return; // sticky error
+    window_cta_body<false>(c, sh, b);
+    __syncthreads(); // the shared struct is reused by the next block
+  }
+}
+
+#ifndef SIMIAN_EMIT_MINBLOCKS
+#define SIMIAN_EMIT_MINBLOCKS 5
+#endif
+#define EMIT_WARPS (NTHREADS / 32)
+#ifndef EMIT_EV
+#define EMIT_EV 2                     // events per lane and chunk
+#endif
+#define EMIT_CHUNK (32 * EMIT_EV)     // parked events a warp takes at a time
+#define EMIT_CHUNKS_PER_BLOCK (NREFS / EMIT_CHUNK)
+struct __align__(32) EmitShared {
+  WinState W;
+  unsigned long long min_key, max_key;
+  uint32_t committed, emitted, dropped, ties, dties, appended;
+  uint32_t found, is_last, far_appends, page_allocs;
+  long long scan_j, t_last;
+  AppendCtx ax[EMIT_WARPS]; // per warp: the page stack of the block it works for
+  // a warp's chunk of parked events; a handler's first local record replaces the
+  // event it consumed (staged, then appended: append_staged)
+#ifdef SIMIAN_BULK_SCAN
+  SlotRec rec[EMIT_WARPS * EMIT_CHUNK];
+#else
+  ulonglong2 lo[EMIT_WARPS * EMIT_CHUNK];
+  ulonglong2 hi[EMIT_WARPS * EMIT_CHUNK];
+#endif
+};
+
+// k_emit: K3 + K4 of the split window.  A persistent grid of WARPS: every warp takes
+// chunks of 64 parked events (static stride over all blocks' chunks), fetches them
+// into its own shared-memory slots with cp.async, runs the handlers (simian.js:129-131)
+// with the commit indices k_window_stage gave the events -- two per lane -- stages
+// what they send in the consumed slots and appends it with both cell claims in
+// flight.  No block barrier between the CTA's set-up and its end; a page a claim has
+// to install comes from the source block's stack in HBM (an atomic on its height).
+// The last CTA does the LBTS step (fuse_advance as in k_window).
+__global__ void __launch_bounds__(NTHREADS, SIMIAN_EMIT_MINBLOCKS)
+    k_emit(const __grid_constant__ DevCfg c, uint32_t win_ix, int fuse_advance) {
+  __shared__ EmitShared sh;
+  const int tid = threadIdx.x;
+  const uint32_t lane = (uint32_t)tid & 31u, warp = (uint32_t)tid >> 5;
+  cudaTriggerProgrammaticLaunchCompletion();
+  cudaGridDependencySynchronize();
+  const WinState *Wg = &c.win[win_ix & 1u];
+  if (Wg->done) return;
+  // the CTA's set-up, one independent load per thread
+  if (tid < (int)(sizeof(WinState) / 8))
+    reinterpret_cast<unsigned long long *>(&sh.W)[tid] =
+        reinterpret_cast<const unsigned long long *>(Wg)[tid];
+  if (tid == 32) sh.found = ld_cg(&c.acc->error);
+  if (tid == 33) {
     sh.min_key = SIMIAN_KEY_NONE;
     sh.max_key = 0;
     sh.committed = sh.emitted = sh.dropped = sh.ties = sh.dties = sh.appended = 0;
     sh.is_last = 0;
-    sh.ax.far_appends = sh.ax.page_allocs = sh.ax.pgc_take = 0;
-    sh.ax.pgc_have = c.bcount[b];
+    sh.far_appends = sh.page_allocs = 0;
     sh.t_last = clock64();
   }
-  if (tid < SIMIAN_BC) sh.ax.pgc[tid] = c.bcache[(size_t)b * SIMIAN_BC + tid];
+  if (lane == 0) {
+    AppendCtx &a = sh.ax[warp];
+    a.far_appends = a.page_allocs = a.pgc_take = a.pgc_have = 0;
+    a.gstack_count = nullptr;
+    a.gstack = nullptr;
+  }
   __syncthreads();
   if (sh.found) return; // sticky error: CTA-uniform exit, the window does not advance
-  const uint32_t n = sh.n < (uint32_t)NREFS ? sh.n : (uint32_t)NREFS;
   ThreadAcc ta;
   thread_acc_init(ta);
-  const simian_event_t *in = c.stage + (size_t)b * NREFS;
+  AppendCtx &ax = sh.ax[warp];
+  const uint32_t slot_base = warp * EMIT_CHUNK + lane;
+  const uint32_t n_chunks = c.n_blocks * EMIT_CHUNKS_PER_BLOCK;
+  const uint32_t total_warps = gridDim.x * EMIT_WARPS;
+  if (!sh.W.redist) {
 #pragma unroll 1
-  for (uint32_t i = tid; i < n; i += NTHREADS) {
-    const RecBits r = ld_rec(in + i);
-    int k;
-    DevCtx<false, true> ctx(c, sh.W, sh.ax, ta);
-    ctx.self_slot = r.dst();
-    ctx.self_gid = gid_of_slot(c, ctx.self_slot, k);
-    ctx.cl = &c.cls[k];
-    ctx.commit_idx = r.q2 >> 16;
-    ctx.key = simian_rng_key(c.seed, ctx.self_gid, ctx.commit_idx);
-    ctx.n_emit = 0;
-    ctx.now_ = r.time(); // simian.js:126
-    ctx.handler_ = r.handler();
-    ctx.src_ = r.src();
-    ctx.data_ = r.data();
-    const uint32_t h = r.handler();
-    run_pure_handler(ctx, h < SIMIAN_MAX_SERVICES ? ctx.cl->fn_of_service[h] : 0);
+    for (uint32_t ch = blockIdx.x * EMIT_WARPS + warp; ch < n_chunks; ch += total_warps) {
+      const uint32_t b = ch / EMIT_CHUNKS_PER_BLOCK;
+      const uint32_t off = (ch % EMIT_CHUNKS_PER_BLOCK) * EMIT_CHUNK;
+      uint32_t n = c.stage_n[b];
+      n = n <= (uint32_t)NREFS ? n : 0u; // (STAGE_REST never survives k_window_rest)
+      if (off >= n) continue;            // (warp-uniform)
+      const simian_event_t *in = c.stage + (size_t)b * NREFS + off;
+      const uint32_t m = n - off < (uint32_t)EMIT_CHUNK ? n - off : (uint32_t)EMIT_CHUNK;
+      uint32_t live = 0;
+#pragma unroll
+      for (int u = 0; u < EMIT_EV; u++) {
+        const uint32_t j = lane + 32u * u;
+        if (j < m) {
+          cp_async16(&SLOT_LO(sh, slot_base + 32u * u), in + j);
+          cp_async16(&SLOT_HI(sh, slot_base + 32u * u), (const char *)(in + j) + 16);
+          live |= 1u << u;
+        }
+      }
+      if (lane == 0) { // the source block's page stack serves this chunk's installs
+        ax.gstack_count = c.bcount + b;
+        ax.gstack = c.bcache + (size_t)b * SIMIAN_BC;
+      }
+      cp_async_wait_all(); // (a lane reads only the slots it fetched itself)
+      __syncwarp();
+#ifdef SIMIAN_EMIT_UNROLL
+#pragma unroll
+#else
+#pragma unroll 1
+#endif
+      for (int u = 0; u < EMIT_EV; u++) {
+        if (!(live & (1u << u))) continue;
+        const uint32_t i = slot_base + 32u * u;
+        const RecBits r = slot_get(sh, i);
+        int k;
+        DevCtx<false, true> ctx(c, sh.W, ax, ta);
+        ctx.stage_lo = &SLOT_LO(sh, i);
+        ctx.stage_hi = &SLOT_HI(sh, i);
+        ctx.self_slot = r.dst();
+        ctx.self_gid = gid_of_slot(c, ctx.self_slot, k);
+        ctx.cl = &c.cls[k];
+        ctx.commit_idx = r.q2 >> 16;
+        ctx.key = simian_rng_key(c.seed, ctx.self_gid, ctx.commit_idx);
+        ctx.n_emit = 0;
+        ctx.now_ = r.time(); // simian.js:126
+        ctx.handler_ = r.handler();
+        ctx.src_ = r.src();
+        ctx.data_ = r.data();
+        const uint32_t h = r.handler();
+        run_pure_handler(ctx, h < SIMIAN_MAX_SERVICES ? ctx.cl->fn_of_service[h] : 0);
+        if (ctx.stage_lo) SLOT_LO(sh, i).y = 0xFFFFFFFFFFFFFFFFull; // nothing staged
+      }
+      append_staged<true, EMIT_EV>(c, sh, ax, sh.W, live, slot_base, 32u, []() {});
+      __syncwarp(); // the slots and the stack pointers are reused by the next chunk
+    }
   }
   accumulate_block(sh, ta);
-  __syncthreads();
-  if (tid == 0 && sh.ax.pgc_take) { // pages popped from the block's stack
-    const uint32_t have = sh.ax.pgc_have;
-    c.bcount[b] = have - (sh.ax.pgc_take < have ? sh.ax.pgc_take : have);
+  if (lane == 0) {
+    if (ax.far_appends) atomicAdd(&sh.far_appends, ax.far_appends);
+    if (ax.page_allocs) atomicAdd(&sh.page_allocs, ax.page_allocs);
   }
+  __syncthreads();
   if (tid < 10) { // one thread per field: independent, result-less atomics
-    BlockPart *p = &c.part[b % SIMIAN_PART_SLOTS];
+    BlockPart *p = &c.part[blockIdx.x % SIMIAN_PART_SLOTS];
     switch (tid) {
       case 0: if (sh.min_key != SIMIAN_KEY_NONE) atomicMin(&p->min_key, sh.min_key); break;
       case 3: if (sh.emitted) atomicAdd(&p->emitted, sh.emitted); break;
       case 4: if (sh.dropped) atomicAdd(&p->dropped, sh.dropped); break;
       case 7: if (sh.appended) atomicAdd(&p->appended, sh.appended); break;
-      case 8: if (sh.ax.far_appends) atomicAdd(&p->far_appends, sh.ax.far_appends); break;
-      case 9: if (sh.ax.page_allocs) atomicAdd(&p->page_allocs, sh.ax.page_allocs); break;
+      case 8: if (sh.far_appends) atomicAdd(&p->far_appends, sh.far_appends); break;
+      case 9: if (sh.page_allocs) atomicAdd(&p->page_allocs, sh.page_allocs); break;
       default: break;
     }
   }

@@ -377,3 +377,24 @@ def test_read_back_into_pinned_and_pageable_buffers(oracle_mod):
     with pytest.raises(ValueError):
         e.read_local("Node", 0, out=np.zeros(3, dtype=np.uint64))
     e.close()
+
+
+SPLIT_CASES = [(c, {}) for c in CASES if c["name"] in
+               ("multi_block_ross", "ragged_last_block", "other_group", "small_lookahead",
+                "burst_64_per_entity", "lambda_half")] + BURST_CASES + [
+    # config-1 shape: far list, redistribution passes (left to k_window_rest)
+    (dict(name="sparse_far_list", n=200, per_entity=1, min_delay=1e-3, lookahead=1e-3,
+          p_remote=0.0, mode=0, end=4.0, seed=9), dict(ring_buckets=256)),
+]
+
+
+@pytest.mark.parametrize("case,opts", SPLIT_CASES, ids=lambda c: c.get("name", "") if "n" in c else None)
+def test_split_window_matches_oracle(case, opts, oracle_mod):
+    """option split_handlers: a window is k_window_stage (dequeue, rank, park the
+    events with their commit indices, trace chain, recycle) -> k_window_rest
+    (bursts / redistribution passes, the one-kernel form) -> k_emit (handlers +
+    appends, persistent warps).  Same bits as the one-kernel window."""
+    so, co, ho = run_oracle_phold(oracle_mod, case)
+    se, ce, he = run_engine_phold(case, split_handlers=1, persistent_loop=0, **opts)
+    assert_parity(so, co, ho, se, ce, he)
+    assert se["kernel_launches"] >= 3 * se["windows"]

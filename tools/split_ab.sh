@@ -12,7 +12,7 @@ fi
 for o in "split_handlers=0" "split_handlers=1"; do
   echo "== $o"; timeout 300 python tools/ab_run.py config2_phold_1m 5 $o
 done
-for v in emit4; do
+for v in emit4 emit6; do
   if [ -f simian_b200/libsimian_b200_$v.so ]; then
     echo "== $v split_handlers=1"
     SIMIAN_B200_LIB=$PWD/simian_b200/libsimian_b200_$v.so timeout 300 python tools/ab_run.py config2_phold_1m 5 split_handlers=1
