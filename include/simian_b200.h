@@ -44,7 +44,8 @@ enum simian_status {
   SIMIAN_ERR_RING_SPAN = 12,     /* window spans the whole calendar ring: raise "bucket_width" */
   SIMIAN_ERR_CUDA = 13,
   SIMIAN_ERR_NO_DEVICE = 14, /* no CUDA device: there is NO CPU fallback                  */
-  SIMIAN_ERR_STALLED = 15    /* a device-side wait (page install, peer flag) timed out     */
+  SIMIAN_ERR_STALLED = 15,   /* a device-side wait (page install, peer flag) timed out     */
+  SIMIAN_ERR_PAYLOAD = 16    /* payload word missing / too long / not available on this path */
 };
 
 /* What Simian.run prints (simian.js:159-164) plus the parity quantities. */
@@ -105,6 +106,10 @@ const char *simian_last_error(simian_engine *e);
  *   "pdl"             1: window kernels are launched as programmatic dependents of
  *                     each other, the next window's CTAs become resident while the
  *                     previous one drains (default 1; size == 1)
+ *   "payloads"        1: handlers may send events whose `data` is longer than 8 bytes
+ *                     (req_service_blob / payload(k) of the handler context; the words
+ *                     travel as continuation records, include/simian_spec.h).  Default 0:
+ *                     the window kernel then never looks at a record's flags
  *   "split_handlers"  1: models of pure handlers run a window as three launches --
  *                     k_window_stage (dequeue, rank, park the events with their commit
  *                     indices, trace chain, recycle; 48 registers), k_window_rest

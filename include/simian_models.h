@@ -39,6 +39,9 @@ enum simian_builtin_fn {
   SIMIAN_FN_HELLO_SQUARE = 8,   /* "hello_square"   */
   SIMIAN_FN_HELLO_SQRT = 9,     /* "hello_sqrt"     */
   SIMIAN_FN_HELLO_RESULT = 10,  /* "hello_result"   */
+  SIMIAN_FN_BLOB_SEND = 11,     /* "blob_send"      */
+  SIMIAN_FN_BLOB_RECV = 12,     /* "blob_recv"      */
+  SIMIAN_FN_BLOB_ACK = 13,      /* "blob_ack"       */
   SIMIAN_FN__END,
   SIMIAN_FN_USER = 32 /* first id of handlers a model author registers (simian_handlers.def) */
 };
@@ -113,8 +116,13 @@ SIMIAN_HD void simian_noop(Ctx &) {}
  * place of masala.random (each handler invocation draws draw(0), draw(1), ...
  * of its own committed event; the reference re-seeds the global stream from
  * the event payload at handler entry, :260,:291 -- same idea).  Deviations,
- * all stated in DESIGN.md: p_send == 0 and p_list == 0 only (Math.pow is not
- * portable; r_min is passed in as a parameter); the weighted sum `value` is
+ * all stated in DESIGN.md: the geometric source / list-size distributions
+ * (p_send, invert, p_list: :209-221) use simian_powi, a defined sequence of
+ * multiplications, instead of Math.pow (r_min, :196, is passed in as a
+ * parameter); every entity's list has room for the largest one (entity 0's), an
+ * entity uses its own list_size of it; an entity whose `ops` is 0 (deep in the
+ * geometric tail) does no list work on a receive (JS: NaN loop bounds; the
+ * Python twin divides by zero there); the weighted sum `value` is
  * stored in the entity state instead of being discarded (:308) so the compute
  * loop is observable; the statistics fan-in to entity 0 (:311-342, an N-way
  * distinguishable time tie) is done off-path by reading entity
@@ -132,11 +140,12 @@ typedef struct simian_lanl_params {
   double end_time;  /* the MODEL's endTime (:115); engine end = max(end,2)+3*minDelay (:349) */
   double min_delay; /* :116 */
   double r_min;     /* pow(1-p_receive, n_ent)  (:196), computed by the host */
+  double p_send, p_list; /* :103,107: 0 = uniform */
   uint32_t time_bins; /* :112, <= SIMIAN_LANL_TIME_BINS */
   uint16_t svc_send, svc_receive; /* interned ids of "SendHandler" / "ReceiveHandler" */
   uint16_t svc_finish, pad0_;
-  uint32_t pad1_;
-} simian_lanl_params_t; /* 104 bytes */
+  uint32_t invert; /* :104 */
+} simian_lanl_params_t; /* 120 bytes */
 
 /* per-entity state (:202-252); the list of list_size doubles follows it */
 typedef struct simian_lanl_state {
@@ -256,10 +265,13 @@ SIMIAN_HD void simian_lanl_receive(Ctx &ctx) {
   uint32_t di = 0;
   double r_ops = simian_floor(simian_lanl_gauss(ctx, di, st->ops, st->ops * p->ops_sigma));
   if (!(r_ops > 1.0)) r_ops = 1.0;                                       /* max(1, ..) */
-  double r_active = simian_floor((double)st->active_elements * (r_ops / st->ops));
-  if (r_active > (double)st->list_size) r_active = (double)st->list_size; /* :295 */
-  if (!(r_active > 1.0)) r_active = 1.0;                                  /* :296 */
-  double r_ops_per_element = simian_floor(r_ops / r_active);              /* :297 */
+  double r_active = 1.0, r_ops_per_element = 0.0;
+  if (st->ops > 0.0) {
+    r_active = simian_floor((double)st->active_elements * (r_ops / st->ops));
+    if (r_active > (double)st->list_size) r_active = (double)st->list_size; /* :295 */
+    if (!(r_active > 1.0)) r_active = 1.0;                                  /* :296 */
+    r_ops_per_element = simian_floor(r_ops / r_active);                     /* :297 */
+  } /* ops == 0 (p_list tail): no list work, see the note at the top */
   st->receive_count++;
   if (r_ops > st->ops_max) st->ops_max = r_ops;
   if (r_ops < st->ops_min) st->ops_min = r_ops;
@@ -275,18 +287,29 @@ SIMIAN_HD void simian_lanl_receive(Ctx &ctx) {
 template <class Ctx>
 SIMIAN_HD void simian_lanl_finish(Ctx &) {}
 
-/* constructor PDES_LANL_Node (:203-257), p_send == 0 and p_list == 0 */
+/* `num` of the entity a handler runs for (class-local index) */
+template <class Ctx>
+SIMIAN_HD uint32_t simian_lanl_num(Ctx &ctx, const simian_lanl_params_t *p) {
+  return ctx.self_id() - p->first_id;
+}
+
+/* constructor PDES_LANL_Node (:203-257) */
 template <class Ctx>
 SIMIAN_HD void simian_lanl_construct(Ctx &ctx) {
   const simian_lanl_params_t *p = (const simian_lanl_params_t *)ctx.params();
   simian_lanl_state_t *st = (simian_lanl_state_t *)ctx.state();
   double *list = (double *)(st + 1);
   uint32_t di = 0;
+  const uint32_t num = simian_lanl_num(ctx, p);
   double prob = 1.0 / (double)p->n_ent;                                    /* :208 */
+  if (p->p_send != 0)                                                      /* :209-212 */
+    prob = p->p_send * simian_powi(1.0 - p->p_send, p->invert ? (uint64_t)(p->n_ent - num) : num);
   double target_global_sends = (double)p->n_ent * p->s_ent;                /* :198 */
   double target_sends = simian_floor(prob * target_global_sends);          /* :213 */
   st->local_intersend_delay =
       (target_sends > 0) ? p->end_time / target_sends : 10 * p->end_time;  /* :214-216 */
+  prob = 1.0 / (double)p->n_ent;                                           /* :219 */
+  if (p->p_list != 0) prob = p->p_list * simian_powi(1.0 - p->p_list, num); /* :220 */
   st->list_size = (uint32_t)simian_floor(prob * (double)p->n_ent * p->m_ent);   /* :221 */
   st->ops = simian_floor(prob * (double)p->n_ent * p->ops_ent);                 /* :222 */
   st->active_elements = (uint32_t)simian_floor(p->cache_friendliness * (double)st->list_size);
@@ -341,6 +364,45 @@ SIMIAN_HD void simian_hello_sqrt(Ctx &ctx) { /* hello.js:86-88 */
 }
 template <class Ctx>
 SIMIAN_HD void simian_hello_result(Ctx &) {} /* hello.js:54-59: logs only */
+
+/* ------------------------------------- payloads beyond 8 bytes ("blobs") ---- */
+/* entity.js:52-60: `data` of an event is any JS object.  Here: any number of 64-bit
+ * words (<= SIMIAN_BLOB_MAX_WORDS), sent with ctx.req_service_blob and read with
+ * ctx.payload_words() / ctx.payload(k) (simian_spec.h: continuation records).  The
+ * test model: every entity keeps sending a random-length vector of random words to
+ * a random entity ("recv"), which folds the words in order and acknowledges the
+ * fold to the sender ("ack": the sender's trace hash then covers every word).
+ * draw 0 = target, 1 = length, 2 = delay to the receiver, 3 = own delay, 4.. words. */
+#define SIMIAN_BLOB_MODEL_MAX_WORDS 24
+typedef struct simian_blob_params {
+  uint32_t first_id, n_entities;
+  double lookahead;
+  uint32_t max_words, pad_;
+  uint16_t svc_send, svc_recv, svc_ack, pad2_;
+} simian_blob_params_t; /* 32 bytes */
+
+template <class Ctx>
+SIMIAN_HD void simian_blob_send(Ctx &ctx) {
+  const simian_blob_params_t *p = (const simian_blob_params_t *)ctx.params();
+  uint32_t target = (uint32_t)(simian_u01(ctx.draw(0)) * (double)p->n_entities);
+  uint32_t mw = p->max_words < SIMIAN_BLOB_MODEL_MAX_WORDS ? p->max_words : SIMIAN_BLOB_MODEL_MAX_WORDS;
+  uint32_t nw = (uint32_t)(ctx.draw(1) % (uint64_t)(mw + 1u)); /* 0 .. max_words */
+  /* (the words are produced on demand: no staging array in the handler) */
+  ctx.req_service_blob_fn(simian_exponential(ctx.draw(2), 1.0) + p->lookahead, p->svc_recv, nw,
+                          p->first_id + target, [&ctx](uint32_t k) { return ctx.draw(4 + k); });
+  ctx.req_service(simian_exponential(ctx.draw(3), 1.0) + p->lookahead, p->svc_send, 0ull,
+                  SIMIAN_NULL_ENTITY);
+}
+template <class Ctx>
+SIMIAN_HD void simian_blob_recv(Ctx &ctx) {
+  const simian_blob_params_t *p = (const simian_blob_params_t *)ctx.params();
+  uint32_t nw = ctx.payload_words();
+  uint64_t fold = simian_mix64((uint64_t)nw + 1ull);
+  for (uint32_t k = 0; k < nw; k++) fold = simian_mix64(fold ^ ctx.payload(k));
+  ctx.req_service(p->lookahead, p->svc_ack, fold, ctx.src());
+}
+template <class Ctx>
+SIMIAN_HD void simian_blob_ack(Ctx &) {} /* commits: the trace hash covers the fold */
 
 /* ------------------------------------------------ the handler registry ---- */
 #ifdef SIMIAN_USER_HANDLERS_H

@@ -43,6 +43,16 @@ extern "C" {
 
 /* flags */
 #define SIMIAN_EVF_SCHED 0x0001u /* injected by schedService (tx = null)      */
+/* Payloads larger than the 8-byte `data` word (entity.js:52-60: `data` is any
+ * object).  The event itself is the HEADER: flags & BLOB, data = number of 64-bit
+ * payload words.  Word k travels as a CONTINUATION record -- same time, dst, src,
+ * handler and seq as its header, flags = CONT | k, data = the word -- through the
+ * calendar, the outboxes and the exchange like any record, but is never committed:
+ * it is what the header's handler reads with payload(k).  (src, seq) names the
+ * header: seq = simian_emit_seq(commit index of the sender, emission number).   */
+#define SIMIAN_EVF_BLOB 0x0002u
+#define SIMIAN_EVF_CONT 0x8000u          /* | word index, 15 bits */
+#define SIMIAN_BLOB_MAX_WORDS 0x7FFFu
 
 /* 32 bytes = exactly one DRAM sector; a scattered append costs one sector.  */
 typedef struct
@@ -172,6 +182,20 @@ SIMIAN_HD double simian_log(double x) {
 }
 
 /* exponential(lambda) = -ln(uniform())/lambda   (phold-noop-noMPI.js:28)    */
+/* b^n for an integer exponent, as a FIXED sequence of f64 multiplications (square
+ * and multiply, low bit first): Math.pow / ** of the reference scripts
+ * (pdes_lanl_benchmarkV8.js:211-212,220) is libm and not reproducible bit for bit
+ * across platforms; this is -- on host, device and in oracle/pyspec.py.          */
+SIMIAN_HD double simian_powi(double b, uint64_t n) {
+  double r = 1.0;
+  while (n) {
+    if (n & 1ull) r = r * b;
+    b = b * b;
+    n >>= 1;
+  }
+  return r;
+}
+
 SIMIAN_HD double simian_exponential(uint64_t draw, double lambda) {
   double e = -simian_log(simian_u01_open(draw));
   return (lambda == 1.0) ? e : e / lambda; /* x/1.0 == x: same bits */

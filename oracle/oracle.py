@@ -111,6 +111,7 @@ def lib():
             "oracle_spec_u01": (d, [u64]),
             "oracle_spec_u01_open": (d, [u64]),
             "oracle_spec_exponential": (d, [u64, d]),
+            "oracle_spec_powi": (d, [d, u64]),
             "oracle_spec_trace_step": (u64, [u64, d, u32, u32, u64]),
             "oracle_spec_digest_term": (u64, [u32, u64, u64]),
         }

@@ -103,6 +103,17 @@ LANL_CASES = [
          p_receive=0.05, m_ent=64.0, ops_ent=100.0, ops_sigma=0.3,
          cache_friendliness=0.25, end_time=12.0, min_delay=0.5, time_bins=8,
          seed=9),
+    # geometric source and list-size distributions (pdes_lanl_benchmarkV8.js:209-221):
+    # entity 0 sends most and owns the longest list; every entity keeps ops >= 1
+    dict(name="lanl_geometric_send_list", n_ent=36, s_ent=18.0, q_avg=2.0,
+         p_receive=0.03, p_send=0.06, p_list=0.05, invert=False, m_ent=48.0,
+         ops_ent=120.0, ops_sigma=0.2, cache_friendliness=0.5, end_time=14.0,
+         min_delay=0.5, time_bins=7, seed=13),
+    # inverted source distribution: the high ids send most, the low ids receive most
+    dict(name="lanl_geometric_inverted", n_ent=30, s_ent=25.0, q_avg=1.0,
+         p_receive=0.08, p_send=0.1, p_list=0.04, invert=True, m_ent=32.0,
+         ops_ent=90.0, ops_sigma=0.1, cache_friendliness=0.75, end_time=10.0,
+         min_delay=1.0, time_bins=10, seed=17),
 ]
 LANL_SERVICES = {"SendHandler": 0, "ReceiveHandler": 1, "FinishHandler": 2}
 
@@ -114,7 +125,9 @@ def run_lanl_case(Simian, case):
     P = pyspec.LanlParams(n, case["s_ent"], case["q_avg"], case["p_receive"],
                           case["m_ent"], case["ops_ent"], case["ops_sigma"],
                           case["cache_friendliness"], case["end_time"],
-                          case["min_delay"], case["time_bins"])
+                          case["min_delay"], case["time_bins"],
+                          case.get("p_send", 0.0), case.get("p_list", 0.0),
+                          case.get("invert", False))
     eng = Simian("pin_" + case["name"], 0.0,
                  max(case["end_time"], 2) + 3 * case["min_delay"],
                  case["min_delay"], False, silent=True)
@@ -281,6 +294,80 @@ def run_hello_case(Simian, case):
     return out
 
 
+BLOB_CASES = [
+    dict(name="blobs_40", n=40, end=12.0, min_delay=0.25, lookahead=0.25, max_words=9, seed=3),
+    dict(name="blobs_long_payloads", n=25, end=8.0, min_delay=0.5, lookahead=0.5,
+         max_words=24, seed=8),
+]
+BLOB_SVC = {"send": 0, "recv": 1, "ack": 2}
+
+
+def run_blob_case(Simian, case):
+    """Events whose `data` is a LIST (entity.js:52-60: any object) on the unmodified
+    SimianPie engine; handlers = transcription of simian_blob_* (simian_models.h).
+    The commit bookkeeping hashes the 8-byte data word the engine's header record
+    carries: the number of payload words ("recv"), the fold ("ack"), 0 ("send")."""
+    n = case["n"]
+    eng = Simian("pin_" + case["name"], 0.0, case["end"], case["min_delay"], False,
+                 silent=True)
+    stats = {"ties": 0, "dist_ties": 0}
+
+    class Node(eng.Entity):
+        def __init__(self, baseInfo, *args):
+            super(Node, self).__init__(baseInfo)
+            self.count = 0
+            self.hash = 0
+            self.last = None
+
+        def _commit(self, service, word, txId):
+            now = self.engine.now
+            src = pyspec.NULL_ENTITY if txId is None else txId
+            h = BLOB_SVC[service]
+            cur = (now, h, src, word)
+            if self.last is not None and self.last[0] == now:
+                stats["ties"] += 1
+                if self.last != cur:
+                    stats["dist_ties"] += 1
+            self.last = cur
+            idx = self.count
+            self.hash = pyspec.trace_step(self.hash, now, h, src, word)
+            self.count = idx + 1
+            return idx
+
+        def send(self, data, tx, txId):
+            idx = self._commit("send", 0, txId)
+            target, words, d_recv, d_self = pyspec.blob_send(
+                case["seed"], self.num, idx, n, case["max_words"], case["lookahead"])
+            self.reqService(d_recv, "recv", words, "Node", target)
+            self.reqService(d_self, "send", None)
+
+        def recv(self, data, tx, txId):
+            self._commit("recv", len(data), txId)
+            self.reqService(case["lookahead"], "ack", pyspec.blob_fold(data), tx, txId)
+
+        def ack(self, data, tx, txId):
+            self._commit("ack", data, txId)
+
+    for i in range(n):
+        eng.addEntity("Node", Node, i)
+    for i in range(n):
+        eng.schedService(0, "send", None, "Node", i)
+    eng.run()
+    ents = [eng.getEntity("Node", i) for i in range(n)]
+    counts = [e.count for e in ents]
+    hashes = [e.hash for e in ents]
+    digest = 0
+    for i in range(n):
+        digest = (digest + pyspec.digest_term(i, counts[i], hashes[i])) & pyspec.M64
+    out = dict(case)
+    out.update(total_events=sum(counts), last_time_hex=float(eng.now).hex(),
+               digest="%016x" % digest, counts=counts,
+               hashes=["%016x" % h for h in hashes], ties=stats["ties"],
+               distinguishable_ties=stats["dist_ties"])
+    eng.exit()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reference", default="/root/reference")
@@ -344,6 +431,22 @@ def main():
                    "reference_engine": "SimianPie/simian.py (unmodified)",
                    "cases": hres}, f, separators=(",", ":"))
     print("wrote", hpath, os.path.getsize(hpath), "bytes")
+    # payloads beyond 8 bytes (events whose data is a list)
+    with tempfile.TemporaryDirectory() as tmp:
+        os.chdir(tmp)
+        try:
+            bres = [run_blob_case(Simian, c) for c in BLOB_CASES]
+        finally:
+            os.chdir(cwd)
+    for r in bres:
+        assert r["distinguishable_ties"] == 0, r["name"]
+        print(r["name"], "events", r["total_events"], "digest", r["digest"], "ties", r["ties"])
+    bpath = os.path.join(os.path.dirname(out_path), "blob_simianpie.json")
+    with open(bpath, "w") as f:
+        json.dump({"generator": "oracle/pin_simianpie.py",
+                   "reference_engine": "SimianPie/simian.py (unmodified)",
+                   "cases": bres}, f, separators=(",", ":"))
+    print("wrote", bpath, os.path.getsize(bpath), "bytes")
 
 
 if __name__ == "__main__":

@@ -140,10 +140,23 @@ def sceil(x):
     return -sfloor(-x)
 
 
+def powi(b, n):
+    """simian_powi: b**n as a fixed sequence of f64 multiplications"""
+    r = 1.0
+    while n:
+        if n & 1:
+            r = r * b
+        b = b * b
+        n >>= 1
+    return r
+
+
 class LanlParams:
     def __init__(self, n_ent, s_ent, q_avg, p_receive, m_ent, ops_ent, ops_sigma,
-                 cache_friendliness, end_time, min_delay, time_bins):
+                 cache_friendliness, end_time, min_delay, time_bins,
+                 p_send=0.0, p_list=0.0, invert=False):
         import math
+        self.p_send, self.p_list, self.invert = p_send, p_list, invert
         self.n_ent, self.s_ent, self.q_avg, self.p_receive = n_ent, s_ent, q_avg, p_receive
         self.m_ent, self.ops_ent, self.ops_sigma = m_ent, ops_ent, ops_sigma
         self.cache_friendliness, self.end_time, self.min_delay = cache_friendliness, end_time, min_delay
@@ -214,12 +227,14 @@ def lanl_receive(p, st, ctx):
     r_ops = sfloor(lanl_gauss(ctx, di, st.ops, st.ops * p.ops_sigma))
     if not (r_ops > 1.0):
         r_ops = 1.0
-    r_active = sfloor(float(st.active_elements) * (r_ops / st.ops))
-    if r_active > float(st.list_size):
-        r_active = float(st.list_size)
-    if not (r_active > 1.0):
-        r_active = 1.0
-    r_ops_per_element = sfloor(r_ops / r_active)
+    r_active, r_ops_per_element = 1.0, 0.0
+    if st.ops > 0.0:  # ops == 0 (p_list tail): no list work (simian_models.h)
+        r_active = sfloor(float(st.active_elements) * (r_ops / st.ops))
+        if r_active > float(st.list_size):
+            r_active = float(st.list_size)
+        if not (r_active > 1.0):
+            r_active = 1.0
+        r_ops_per_element = sfloor(r_ops / r_active)
     st.receive_count += 1
     if r_ops > st.ops_max:
         st.ops_max = r_ops
@@ -246,10 +261,16 @@ def lanl_weighted_sum(ctx, lst, na, nj, di0):
 
 def lanl_construct(p, st, ctx):
     di = _Di()
+    num = st.num
     prob = 1.0 / float(p.n_ent)
+    if p.p_send != 0:
+        prob = p.p_send * powi(1.0 - p.p_send, (p.n_ent - num) if p.invert else num)
     target_global_sends = float(p.n_ent) * p.s_ent
     target_sends = sfloor(prob * target_global_sends)
     st.local_intersend_delay = (p.end_time / target_sends) if target_sends > 0 else 10 * p.end_time
+    prob = 1.0 / float(p.n_ent)
+    if p.p_list != 0:
+        prob = p.p_list * powi(1.0 - p.p_list, num)
     st.list_size = int(sfloor(prob * float(p.n_ent) * p.m_ent))
     st.ops = sfloor(prob * float(p.n_ent) * p.ops_ent)
     st.active_elements = int(sfloor(p.cache_friendliness * float(st.list_size)))
@@ -276,3 +297,26 @@ def hello_generate(seed, gid, commit_idx, count):
     target_id = int(u01(rng_draw(key, 1)) * float(count))
     data = u01(rng_draw(key, 2)) * 100.0
     return target, target_id, data
+
+
+# ---- payloads beyond 8 bytes: transcription of simian_blob_* (simian_models.h) --
+
+BLOB_MODEL_MAX_WORDS = 24
+
+
+def blob_send(seed, gid, commit_idx, n_entities, max_words, lookahead):
+    """-> (target, words, delay to the receiver, own delay)"""
+    key = rng_key(seed, gid, commit_idx)
+    target = int(u01(rng_draw(key, 0)) * float(n_entities))
+    mw = min(max_words, BLOB_MODEL_MAX_WORDS)
+    nw = rng_draw(key, 1) % (mw + 1)
+    words = [rng_draw(key, 4 + k) for k in range(nw)]
+    return (target, words, exponential(rng_draw(key, 2), 1.0) + lookahead,
+            exponential(rng_draw(key, 3), 1.0) + lookahead)
+
+
+def blob_fold(words):
+    fold = mix64((len(words) + 1) & M64)
+    for w in words:
+        fold = mix64(fold ^ w)
+    return fold

@@ -41,6 +41,7 @@
 #include <atomic>
 #include <chrono>
 #include <map>
+#include <mutex>
 #include <thread>
 #include <string>
 #include <vector>
@@ -199,6 +200,11 @@ struct World {
   uint64_t windows = 0, ties = 0, dist_ties = 0, emitted = 0, dropped = 0;
   double last_time = 0, run_seconds = 0;
   int threads = 1; /* ranks stepped concurrently by oracle_run (1 = sequential) */
+  /* payload words of the events in flight, keyed (src << 32 | seq); shared by the
+   * ranks of this process (one rank per PROCESS -- the gloo form -- has no such
+   * table: payloads are not supported there) */
+  std::map<uint64_t, std::vector<uint64_t>> blobs;
+  std::mutex blob_mu;
 
   /* fold the per-rank statistics into the world's (after a window / at the end) */
   void gather_rank_stats() {
@@ -264,8 +270,45 @@ struct HostCtx {
   uint32_t src() const { return ev ? ev->src : SIMIAN_NULL_ENTITY; }
   uint64_t data() const { return ev ? ev->data : 0; }
 
+  /* payloads beyond 8 bytes (entity.js:52-60: `data` is any object): the event
+   * carries the number of words, the words stay in a table of the world keyed by
+   * (src, seq) -- the names the engine's continuation records carry too */
+  uint32_t payload_words() const {
+    return (ev && (ev->flags & SIMIAN_EVF_BLOB)) ? (uint32_t)ev->data : 0u;
+  }
+  uint64_t payload(uint32_t k) {
+    if (k < payload_words()) {
+      std::lock_guard<std::mutex> g(w->blob_mu);
+      auto it = w->blobs.find(((uint64_t)ev->src << 32) | ev->seq);
+      if (it != w->blobs.end() && k < it->second.size()) return it->second[k];
+    }
+    if (!r->error) {
+      r->error = ORACLE_ERR_UNKNOWN;
+      r->errmsg = "payload word missing";
+    }
+    return 0;
+  }
+  void req_service_blob(double offset, uint16_t service, const uint64_t *words, uint32_t nwords,
+                        uint32_t rx) {
+    req_service_blob_fn(offset, service, nwords, rx, [words](uint32_t k) { return words[k]; });
+  }
+  template <class F>
+  void req_service_blob_fn(double offset, uint16_t service, uint32_t nwords, uint32_t rx, F word) {
+    const uint32_t seq = simian_emit_seq(commit_idx, n_emit);
+    {
+      std::vector<uint64_t> v(nwords);
+      for (uint32_t k = 0; k < nwords; k++) v[k] = word(k);
+      std::lock_guard<std::mutex> g(w->blob_mu);
+      w->blobs[((uint64_t)self << 32) | seq] = std::move(v);
+    }
+    send_(offset, service, (uint64_t)nwords, rx, SIMIAN_EVF_BLOB);
+  }
+
   /* Entity.reqService  (entity.js:35-68) */
   void req_service(double offset, uint16_t service, uint64_t data, uint32_t rx) {
+    send_(offset, service, data, rx, 0);
+  }
+  void send_(double offset, uint16_t service, uint64_t data, uint32_t rx, uint16_t flags) {
     uint32_t k = n_emit++;
     if ((rx != SIMIAN_NULL_ENTITY) && (offset < w->minDelay)) { /* :41 */
       if (!r->error) {
@@ -286,7 +329,7 @@ struct HostCtx {
     e.dst = rx;
     e.src = self;
     e.handler = service;
-    e.flags = 0;
+    e.flags = flags;
     e.seq = simian_emit_seq(commit_idx, k);
     e.data = data;
     r->emitted++;
@@ -865,6 +908,7 @@ uint64_t oracle_spec_rng_draw(uint64_t k, uint32_t i) {
 }
 double oracle_spec_u01(uint64_t x) { return simian_u01(x); }
 double oracle_spec_u01_open(uint64_t x) { return simian_u01_open(x); }
+double oracle_spec_powi(double b, uint64_t n) { return simian_powi(b, n); }
 double oracle_spec_exponential(uint64_t d, double l) {
   return simian_exponential(d, l);
 }

@@ -128,7 +128,8 @@ struct DevCfg {
   uint64_t seed;
   int rank, size;
   int n_classes, tie_check;
-  int all_pure, pad2_; // every attached handler is stateless: thread-per-event path
+  int all_pure; // every attached handler is stateless: thread-per-event path
+  int blobs;    // option "payloads": events may carry continuation records (SIMIAN_EVF_CONT)
   DevClass cls[SIMIAN_MAX_CLASSES];
   // entities
   EntityCore *core;

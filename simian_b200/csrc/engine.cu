@@ -181,6 +181,7 @@ struct simian_engine {
   // trace chain, recycle) and k_emit (handlers + appends at a higher occupancy).  Pure
   // handlers only; -1 = the default for the model (see setup_layout)
   int split = -1;
+  int payloads = 0; // option "payloads": handlers may send / read payload words (continuation records)
   bool split_on = false; // in force for this layout
   uint32_t rest_ctas = 444; // grid of k_window_rest: the CTAs resident at once
   uint32_t emit_ctas = 740; // grid of k_emit: the CTAs resident at once
@@ -252,6 +253,7 @@ const char *status_text(int code) {
     case SIMIAN_ERR_OUTBOX_FULL: return "cross-GPU outbox full: raise option outbox_events";
     case SIMIAN_ERR_RING_SPAN: return "window spans too many calendar sub-buckets: raise option bucket_width";
     case SIMIAN_ERR_STALLED: return "a device-side wait timed out (page install or peer exchange flag)";
+    case SIMIAN_ERR_PAYLOAD: return "event payload: word missing, too long, or not available on this path";
     default: return "error";
   }
 }
@@ -336,6 +338,8 @@ int setup_layout(simian_engine *e) {
   if (e->laid_out) return 0;
   DevCfg &c = e->cfg;
   CK(cudaFuncSetAttribute(k_window, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          (int)WINDOW_SMEM_BYTES(SIMIAN_EPB_MAX)));
+  CK(cudaFuncSetAttribute(k_window_blobs, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           (int)WINDOW_SMEM_BYTES(SIMIAN_EPB_MAX)));
   CK(cudaFuncSetAttribute(k_local_min, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           (int)WINDOW_SMEM_BYTES(SIMIAN_EPB_MAX)));
@@ -467,7 +471,8 @@ int setup_layout(simian_engine *e) {
   if (dev_alloc(e, &e->d_digest, 2)) return e->err_code;
   // split window: only models of pure handlers, not beside the deferred pull (its
   // pull CTAs ride in k_window) or the persistent loop
-  e->split_on = c.all_pure && !e->deferred_pull && !e->loop &&
+  c.blobs = e->payloads ? 1 : 0;
+  e->split_on = c.all_pure && !e->deferred_pull && !e->loop && !e->payloads &&
                 (e->split < 0 ? SIMIAN_SPLIT_DEFAULT != 0 : e->split != 0);
   c.stage = nullptr;
   c.stage_n = nullptr;
@@ -520,7 +525,7 @@ int setup_layout(simian_engine *e) {
   }
   // persistent window loop: only when every block's CTA fits on the GPU at once
   e->loop_ok = false;
-  if (e->loop && e->size == 1) {
+  if (e->loop && e->size == 1 && !e->payloads) {
     int sms = 0, coop = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->device);
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, e->device);
@@ -731,6 +736,7 @@ int simian_set_option(simian_engine *e, const char *key, double v) {
   else if (k == "persistent_loop") e->loop = v != 0;
   else if (k == "deferred_pull") e->deferred_pull = v != 0;
   else if (k == "split_handlers") e->split = v != 0;
+  else if (k == "payloads") e->payloads = v != 0;
   else return e->fail(SIMIAN_ERR_BAD_ARGUMENT, "unknown option " + k);
   return 0;
 }
@@ -1138,7 +1144,10 @@ static int launch_window(simian_engine *e, int fuse, uint32_t pull_blocks, bool 
   }
   lc.gridDim = dim3(e->cfg.n_blocks + pull_blocks);
   lc.dynamicSmemBytes = e->smem_bytes;
-  CK(cudaLaunchKernelEx(&lc, k_window, e->cfg, e->win_ix, fuse, pull_blocks));
+  if (e->cfg.blobs) // (its own instantiation: the ordinary kernel never looks at record flags)
+    CK(cudaLaunchKernelEx(&lc, k_window_blobs, e->cfg, e->win_ix, fuse, pull_blocks));
+  else
+    CK(cudaLaunchKernelEx(&lc, k_window, e->cfg, e->win_ix, fuse, pull_blocks));
   e->launches++;
   return 0;
 }

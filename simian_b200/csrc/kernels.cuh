@@ -110,6 +110,10 @@ __device__ __forceinline__ void ld_rec_head(const simian_event_t *p, unsigned lo
                                             unsigned long long &q1) {
   asm volatile("ld.global.v2.u64 {%0,%1}, [%2];" : "=l"(q0), "=l"(q1) : "l"(p));
 }
+// the flags half-word of a record in the pool
+__device__ __forceinline__ uint32_t ld_rec_flags(const simian_event_t *p) {
+  return (uint32_t)*reinterpret_cast<const unsigned short *>(reinterpret_cast<const char *>(p) + 18);
+}
 // 16 bytes global -> shared without passing through registers (LDGSTS)
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *src) {
   uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
@@ -537,7 +541,7 @@ __global__ void k_ingest(const __grid_constant__ DevCfg c, const simian_event_t 
     unsigned long long k = simian_time_key(r.time());
     mn = k < mn ? k : mn;
     append_local<true>(c, ax, W.tb_clean, W.far_row, W.alloc_limit, r);
-    napp++;
+    if (!(r.flags() & SIMIAN_EVF_CONT)) napp++; // (payload words are never committed)
   }
   appended_flush(c, napp);
   if (track_min) {
@@ -610,7 +614,7 @@ __device__ __forceinline__ void pull_records(const DevCfg &c, const WinState &W,
             mn = k < mn ? k : mn;
           }
           append_local<true>(c, ax, a_tb_clean, a_far_row, a_alloc_limit, r[u]);
-          napp++;
+          if (!(r[u].flags() & SIMIAN_EVF_CONT)) napp++; // (payload words are never committed)
         }
     }
   }
@@ -815,6 +819,9 @@ struct __align__(32) WindowShared {
   uint32_t hist[NBINS], pfill[NBINS], pcnt[NBINS], plo[NBINS], phi[NBINS], ppage0[NBINS + 1];
   uint32_t part_of_bin[NBINS];
   uint32_t nparts, bin_shift;
+  // due continuation records of the block (payload words, SIMIAN_EVF_CONT): one list
+  // through nxt[], searched by payload(k); they are in no entity's list
+  uint32_t cont_head, pad_cont_;
   uint32_t head[SIMIAN_EPB_MAX];   // per local entity: index of its first due event
   uint32_t pg_id[PGMAX];           // pages of this block's cells in the window rows
   uint32_t pg_off[PGMAX];          // records in the pages listed before this one
@@ -882,6 +889,10 @@ struct DevCtx {
   double now_;
   uint32_t handler_, src_;
   unsigned long long data_;
+  // payload of the event being committed (SIMIAN_EVF_BLOB): its flags and seq, and
+  // the CTA's slots, where the continuation records of the window are listed
+  uint32_t flags_, seq_;
+  const WindowShared *pl_sh;
   // !SEQ: where the first locally routed record is staged (the two halves of a
   // shared-memory slot) instead of being appended right away; null = append directly
   ulonglong2 *stage_lo, *stage_hi;
@@ -903,8 +914,9 @@ struct DevCtx {
 
   __device__ __forceinline__ DevCtx(const DevCfg &c_, const WinState &W_, AppendCtx &ax_,
                                     ThreadAcc &ta_)
-      : c(c_), W(W_), ax(ax_), ta(ta_), stage_lo(nullptr), stage_hi(nullptr), local_min(true),
-        split_ok(true), job_sh(nullptr), job_slot(SIMIAN_NONE), job_count0(0), npend(0) {}
+      : c(c_), W(W_), ax(ax_), ta(ta_), flags_(0), seq_(0), pl_sh(nullptr), stage_lo(nullptr),
+        stage_hi(nullptr), local_min(true), split_ok(true), job_sh(nullptr),
+        job_slot(SIMIAN_NONE), job_count0(0), npend(0) {}
 
   __device__ __forceinline__ double now() const { return now_; }
   __device__ __forceinline__ uint32_t self_id() const { return self_gid; }
@@ -936,10 +948,95 @@ struct DevCtx {
     }
   }
 
+  // ---- payloads beyond the 8-byte data word (entity.js:52-60) ----
+  __device__ __forceinline__ uint32_t payload_words() const {
+    return (flags_ & SIMIAN_EVF_BLOB) ? (uint32_t)data_ : 0u;
+  }
+  // word k of the payload of the event being committed: its continuation record is
+  // due in the same window and sits in the CTA's slots
+  __device__ __forceinline__ unsigned long long payload(uint32_t k) {
+    if (pl_sh && k < payload_words()) {
+      const unsigned long long want1 = (unsigned long long)self_slot | ((unsigned long long)src_ << 32);
+      const unsigned long long want2 = (unsigned long long)(handler_ & 0xFFFFu) |
+                                       ((unsigned long long)(SIMIAN_EVF_CONT | k) << 16) |
+                                       ((unsigned long long)seq_ << 32);
+      const unsigned long long t = (unsigned long long)__double_as_longlong(now_);
+      for (uint32_t j = pl_sh->cont_head; j != LIST_END; j = pl_sh->nxt[j]) {
+        const ulonglong2 a = SLOT_LO(*pl_sh, j);
+        if (a.x != t || a.y != want1) continue;
+        const ulonglong2 b = SLOT_HI(*pl_sh, j);
+        if (b.x == want2) return b.y;
+      }
+    }
+    set_error(c, SIMIAN_ERR_PAYLOAD);
+    return 0ull;
+  }
+
+  // a record for another rank: staged for the per-window exchange (entity.js:66)
+  __device__ __forceinline__ void put_remote(int rank, double time, const RecBits &r) {
+    // warp-aggregated claim: one atomic per (warp, destination rank)
+    const uint32_t box = W.parity * (uint32_t)c.size + (uint32_t)rank;
+    // Two-ended outbox (c.split_outbox, the deferred pull): records that cannot
+    // be due in the receiver's next window -- time >= this window's bound + 2
+    // minDelay -- are staged from the BACK of the box and pulled while that next
+    // window runs; the others from the front, pulled before it.
+    const uint32_t far = (c.split_outbox && split_ok &&
+                          time >= W.hi + 2.0 * c.min_delay) ? 1u : 0u;
+    const int key = rank * 2 + (int)far;
+    unsigned act = __activemask();
+    unsigned peers = __match_any_sync(act, key);
+    int leader = __ffs(peers) - 1, ln = threadIdx.x & 31;
+    uint32_t i = 0;
+    if (ln == leader)
+      i = atomicAdd(&c.outbox_count[far * SIMIAN_FAR_COUNT_OFF + box], (uint32_t)__popc(peers));
+    i = __shfl_sync(peers, i, leader) + __popc(peers & ((1u << ln) - 1u));
+    // (the two ends meet: the other end's count is only a lower bound here, the
+    // receiver checks the sum again)
+    if (i >= c.outbox_cap ||
+        i + ld_cg(&c.outbox_count[(far ^ 1u) * SIMIAN_FAR_COUNT_OFF + box]) >= c.outbox_cap) {
+      set_error(c, SIMIAN_ERR_OUTBOX_FULL);
+      return;
+    }
+    simian_event_t *dst_rec =
+        c.outbox + ((size_t)box * c.outbox_cap + (far ? c.outbox_cap - 1u - i : i));
+    st_rec_sel<WIDE>(dst_rec, r);
+  }
+
   // Entity.reqService (entity.js:35-68)
+  struct NoWords {
+    __device__ __forceinline__ unsigned long long operator()(uint32_t) const { return 0ull; }
+  };
+  struct WordsAt {
+    const unsigned long long *p;
+    __device__ __forceinline__ unsigned long long operator()(uint32_t k) const { return p[k]; }
+  };
   __device__ __forceinline__ void req_service(double offset, uint16_t service,
                                               unsigned long long data, uint32_t rx) {
+    send_<false>(offset, service, data, rx, NoWords(), 0u);
+  }
+  // ... with `data` = nwords 64-bit words (any JS object of the reference, flattened)
+  __device__ __forceinline__ void req_service_blob(double offset, uint16_t service,
+                                                   const uint64_t *words_, uint32_t nwords,
+                                                   uint32_t rx) {
+    WordsAt src{reinterpret_cast<const unsigned long long *>(words_)};
+    req_service_blob_fn(offset, service, nwords, rx, src);
+  }
+  // ... the words produced on demand: word(k) -> uint64 (no staging array)
+  template <class F>
+  __device__ __forceinline__ void req_service_blob_fn(double offset, uint16_t service,
+                                                      uint32_t nwords, uint32_t rx, F word) {
+    if (!c.blobs || nwords > SIMIAN_BLOB_MAX_WORDS) { // option "payloads" not set
+      set_error(c, SIMIAN_ERR_PAYLOAD);
+      return;
+    }
+    send_<true>(offset, service, (unsigned long long)nwords, rx, word, nwords);
+  }
+
+  template <bool BLOB, class F>
+  __device__ __forceinline__ void send_(double offset, uint16_t service, unsigned long long data,
+                                        uint32_t rx, F words, uint32_t nwords) {
     uint32_t k = n_emit++;
+    const uint32_t fl = BLOB ? SIMIAN_EVF_BLOB : 0u;
     if (rx != SIMIAN_NULL_ENTITY && offset < c.min_delay) { // entity.js:41-45
       set_error(c, SIMIAN_ERR_LOOKAHEAD);
       return;
@@ -957,6 +1054,10 @@ struct DevCtx {
         return;
       }
       if (time < W.hi) { // lands inside this window: stays with the entity
+        if (BLOB) { // (a pending self-send carries no payload)
+          set_error(c, SIMIAN_ERR_PAYLOAD);
+          return;
+        }
         if (!SEQ || npend >= SIMIAN_SELF_MAX) {
           set_error(c, SIMIAN_ERR_SELF_PENDING);
           return;
@@ -967,7 +1068,12 @@ struct DevCtx {
         npend++;
         return;
       }
-      put_local(make_rec(time, self_slot, self_gid, service, 0, seq, data));
+      put_local(make_rec(time, self_slot, self_gid, service, fl, seq, data));
+      if (BLOB)
+        for (uint32_t w = 0; w < nwords; w++) // the payload words: never committed, not counted
+          append_local<WIDE>(c, ax, W.tb_clean, W.far_row, W.alloc_limit,
+                             make_rec(time, self_slot, self_gid, service, SIMIAN_EVF_CONT | w, seq,
+                                      words(w)));
       return;
     }
     if (rx >= c.n_ids) { // the reference throws at dispatch (simian.js:128)
@@ -977,40 +1083,24 @@ struct DevCtx {
     int rank;
     uint32_t slot;
     route_gid(c, rx, rank, slot); // getOffsetRank, entity.js:62
-    RecBits r = make_rec(time, slot, self_gid, service, 0, seq, data);
+    RecBits r = make_rec(time, slot, self_gid, service, fl, seq, data);
     if (rank == c.rank) { // entity.js:64
       put_local(r);
+      if (BLOB)
+        for (uint32_t w = 0; w < nwords; w++)
+          append_local<WIDE>(c, ax, W.tb_clean, W.far_row, W.alloc_limit,
+                             make_rec(time, slot, self_gid, service, SIMIAN_EVF_CONT | w, seq,
+                                      words(w)));
     } else { // entity.js:66: staged for the per-window exchange
       // the receiver has not seen it when the LBTS candidates are reduced:
       // the sender's candidate covers it (simian.js:143-144)
       unsigned long long tk = simian_time_key(time);
       ta.min_key = tk < ta.min_key ? tk : ta.min_key;
-      // warp-aggregated claim: one atomic per (warp, destination rank)
-      const uint32_t box = W.parity * (uint32_t)c.size + (uint32_t)rank;
-      // Two-ended outbox (c.split_outbox, the deferred pull): records that cannot
-      // be due in the receiver's next window -- time >= this window's bound + 2
-      // minDelay -- are staged from the BACK of the box and pulled while that next
-      // window runs; the others from the front, pulled before it.
-      const uint32_t far = (c.split_outbox && split_ok &&
-                            time >= W.hi + 2.0 * c.min_delay) ? 1u : 0u;
-      const int key = rank * 2 + (int)far;
-      unsigned act = __activemask();
-      unsigned peers = __match_any_sync(act, key);
-      int leader = __ffs(peers) - 1, ln = threadIdx.x & 31;
-      uint32_t i = 0;
-      if (ln == leader)
-        i = atomicAdd(&c.outbox_count[far * SIMIAN_FAR_COUNT_OFF + box], (uint32_t)__popc(peers));
-      i = __shfl_sync(peers, i, leader) + __popc(peers & ((1u << ln) - 1u));
-      // (the two ends meet: the other end's count is only a lower bound here, the
-      // receiver checks the sum again)
-      if (i >= c.outbox_cap ||
-          i + ld_cg(&c.outbox_count[(far ^ 1u) * SIMIAN_FAR_COUNT_OFF + box]) >= c.outbox_cap) {
-        set_error(c, SIMIAN_ERR_OUTBOX_FULL);
-        return;
-      }
-      simian_event_t *dst_rec =
-          c.outbox + ((size_t)box * c.outbox_cap + (far ? c.outbox_cap - 1u - i : i));
-      st_rec_sel<WIDE>(dst_rec, r);
+      put_remote(rank, time, r);
+      if (BLOB)
+        for (uint32_t w = 0; w < nwords; w++)
+          put_remote(rank, time,
+                     make_rec(time, slot, self_gid, service, SIMIAN_EVF_CONT | w, seq, words(w)));
     }
   }
 };
@@ -1205,7 +1295,7 @@ __device__ __noinline__ void process_entity(const DevCfg &c, WindowShared &sh, T
           (ctx.pend_time[j] == ctx.pend_time[pj] && ctx.pend_q2[j] < ctx.pend_q2[pj]))
         pj = j;
     double time;
-    uint32_t handler, src;
+    uint32_t handler, src, ev_flags = 0, ev_seq = 0;
     unsigned long long data;
     if (pj >= 0 &&
         (!have_g || ctx.pend_time[pj] < __longlong_as_double((long long)SLOT_LO(sh, gj).x))) {
@@ -1221,6 +1311,8 @@ __device__ __noinline__ void process_entity(const DevCfg &c, WindowShared &sh, T
     } else if (have_g) {
       ctx.job_slot = gj;
       const RecBits g = slot_get(sh, gj);
+      ev_flags = g.flags();
+      ev_seq = g.seq();
       time = g.time();
       handler = g.handler();
       src = g.src();
@@ -1258,6 +1350,9 @@ __device__ __noinline__ void process_entity(const DevCfg &c, WindowShared &sh, T
     ctx.handler_ = handler;
     ctx.src_ = src;
     ctx.data_ = data;
+    ctx.flags_ = ev_flags;
+    ctx.seq_ = ev_seq;
+    ctx.pl_sh = &sh;
     uint32_t fn = handler < SIMIAN_MAX_SERVICES ? ctx.cl->fn_of_service[handler] : 0;
     run_handler(ctx, fn); // simian.js:129-131
   }
@@ -1366,6 +1461,9 @@ __device__ __forceinline__ void run_event(const DevCfg &c, WindowShared &sh, Thr
   ctx.handler_ = r.handler();
   ctx.src_ = r.src();
   ctx.data_ = r.data();
+  ctx.flags_ = r.flags();
+  ctx.seq_ = r.seq();
+  ctx.pl_sh = &sh;
   uint32_t h = r.handler();
   run_pure_handler(ctx, h < SIMIAN_MAX_SERVICES ? ctx.cl->fn_of_service[h] : 0);
   if (ctx.stage_lo) SLOT_LO(sh, i).y = 0xFFFFFFFFFFFFFFFFull; // nothing staged
@@ -1393,6 +1491,7 @@ __device__ __forceinline__ void chain_entity(const DevCfg &c, WindowShared &sh, 
 // of an entity also fetches the entity's {count, hash}.  On the first pass the
 // minimum time >= hi is tracked (K1).  Slots are claimed with one
 // shared-memory atomic per warp.
+template <bool BLOBS>
 __device__ __forceinline__ void collect_due(const DevCfg &c, WindowShared &sh, ThreadAcc &ta,
                                             uint32_t slot0, uint32_t pg_lo, uint32_t pg_hi,
                                             uint32_t e_lo, uint32_t e_hi, bool first) {
@@ -1445,9 +1544,14 @@ __device__ __forceinline__ void collect_due(const DevCfg &c, WindowShared &sh, T
           if (pos < NREFS) {
             SLOT_LO(sh, pos) = make_ulonglong2(q0[u], q1[u]);
             cp_async16(&SLOT_HI(sh, pos), (const char *)(c.pool + ref[u]) + 16);
-            uint32_t prev = atomicExch(&sh.head[le], pos);
-            sh.nxt[pos] = (uint16_t)prev;
-            if (prev == LIST_END) cp_async16(&SH_CORE(sh)[le], &c.core[slot0 + le]);
+            if (BLOBS && (ld_rec_flags(c.pool + ref[u]) & SIMIAN_EVF_CONT)) {
+              // a payload word: listed for payload(k), in no entity's list
+              sh.nxt[pos] = (uint16_t)atomicExch(&sh.cont_head, pos);
+            } else {
+              uint32_t prev = atomicExch(&sh.head[le], pos);
+              sh.nxt[pos] = (uint16_t)prev;
+              if (prev == LIST_END) cp_async16(&SH_CORE(sh)[le], &c.core[slot0 + le]);
+            }
           } else if (first) {
             // overflow (a burst): where in the block the records without a slot
             // belong -- the partition step sizes its parts from this
@@ -1504,6 +1608,10 @@ __device__ __forceinline__ void collect_all(const DevCfg &c, WindowShared &sh, u
 // handles in the later phases): due events are pushed onto their entity's list
 // and fetch the entity's {count, hash} (waited for after the rank phase); the
 // others only feed the LBTS minimum (K1).  Returns the mask of its due slots.
+// BLOBS (option "payloads", its own instantiation of the window kernel so that the
+// ordinary one never looks at a record's flags): continuation records are listed for
+// payload(k) instead of being linked as events.
+template <bool BLOBS>
 __device__ __forceinline__ uint32_t link_due(const DevCfg &c, WindowShared &sh, ThreadAcc &ta,
                                              uint32_t slot0, uint32_t nvalid) {
   const double w_hi = sh.W.hi, w_gmin = sh.W.gmin;
@@ -1516,11 +1624,16 @@ __device__ __forceinline__ uint32_t link_due(const DevCfg &c, WindowShared &sh, 
       const double t = __longlong_as_double((long long)a.x);
       if (t < w_hi) {
         if (t >= w_gmin) {
-          const uint32_t le = (uint32_t)a.y - slot0;
-          const uint32_t prev = atomicExch(&sh.head[le], i);
-          sh.nxt[i] = (uint16_t)prev;
-          if (prev == LIST_END) cp_async16(&SH_CORE(sh)[le], &c.core[slot0 + le]);
-          live |= 1u << u;
+          if (BLOBS && ((uint32_t)(SLOT_HI(sh, i).x >> 16) & SIMIAN_EVF_CONT)) {
+            // a payload word: listed for payload(k), in no entity's list, not an event
+            sh.nxt[i] = (uint16_t)atomicExch(&sh.cont_head, i);
+          } else {
+            const uint32_t le = (uint32_t)a.y - slot0;
+            const uint32_t prev = atomicExch(&sh.head[le], i);
+            sh.nxt[i] = (uint16_t)prev;
+            if (prev == LIST_END) cp_async16(&SH_CORE(sh)[le], &c.core[slot0 + le]);
+            live |= 1u << u;
+          }
         }
       } else {
         unsigned long long tk = simian_time_key(t);
@@ -2203,12 +2316,13 @@ __device__ __forceinline__ uint32_t live_below(uint32_t m) {
 // split and the same pages are re-scanned -- and the sub-ranges are processed
 // one pass each.  Kept out of line, with its own accumulators, so that the
 // common single-pass window pays nothing for it.
+template <bool BLOBS>
 __device__ __noinline__ void filtered_passes(const DevCfg &c, WindowShared &sh, uint32_t slot0,
                                              uint32_t npg_scan) {
   const int tid = threadIdx.x;
   ThreadAcc ta;
   thread_acc_init(ta);
-  collect_due(c, sh, ta, slot0, 0, npg_scan, 0, c.epb, true);
+  collect_due<BLOBS>(c, sh, ta, slot0, 0, npg_scan, 0, c.epb, true);
   __syncthreads();
   const uint32_t m0 = sh.total;
   uint32_t m = m0, e_lo = 0, e_hi = c.epb, pg_lo = 0, pg_hi = npg_scan;
@@ -2237,7 +2351,15 @@ __device__ __noinline__ void filtered_passes(const DevCfg &c, WindowShared &sh, 
         }
       }
     } else if (m && m <= NREFS) {
-      process_pass<false, false>(c, sh, ta, slot0, live_below(m), e_lo, e_hi);
+      uint32_t lv = live_below(m);
+      if (BLOBS) { // payload words hold slots but are not events
+#pragma unroll
+        for (int u = 0; u < EV_PER_THREAD; u++)
+          if ((lv & (1u << u)) &&
+              ((uint32_t)(SLOT_HI(sh, tid + u * NTHREADS).x >> 16) & SIMIAN_EVF_CONT))
+            lv &= ~(1u << u);
+      }
+      process_pass<false, false>(c, sh, ta, slot0, lv, e_lo, e_hi);
     }
     part_ok = false; // only the first (whole-block) overflow is partitioned
     __syncthreads();
@@ -2250,12 +2372,13 @@ __device__ __noinline__ void filtered_passes(const DevCfg &c, WindowShared &sh, 
       sh.pass_pg_lo = sh.rstack[4 * sh.stack_n + 2];
       sh.pass_pg_hi = sh.rstack[4 * sh.stack_n + 3];
       sh.total = 0;
+      sh.cont_head = LIST_END;
     }
     for (uint32_t i = tid; i < c.epb; i += NTHREADS) sh.head[i] = LIST_END;
     __syncthreads();
     e_lo = sh.pass_lo, e_hi = sh.pass_hi;
     pg_lo = sh.pass_pg_lo, pg_hi = sh.pass_pg_hi;
-    collect_due(c, sh, ta, slot0, pg_lo, pg_hi, e_lo, e_hi, false);
+    collect_due<BLOBS>(c, sh, ta, slot0, pg_lo, pg_hi, e_lo, e_hi, false);
     __syncthreads();
     m = sh.total;
   }
@@ -2300,7 +2423,7 @@ __device__ __forceinline__ uint32_t window_cta_begin(const DevCfg &c, WindowShar
 // One lookahead window (or one redistribution pass) for entity block b: K2a
 // list -> K2 dequeue -> K3 handlers -> K4 emit -> recycle -> the CTA's results
 // into its BlockPart slot.  All threads of the CTA.
-template <bool SPLIT>
+template <bool SPLIT, bool BLOBS = false>
 __device__ __forceinline__ void window_cta_body(const DevCfg &c, WindowShared &sh, uint32_t b) {
   const int tid = threadIdx.x;
   const WinState &W = sh.W;
@@ -2336,6 +2459,7 @@ __device__ __forceinline__ void window_cta_body(const DevCfg &c, WindowShared &s
     if (tid >= NTHREADS - NBINS) sh.hist[tid - (NTHREADS - NBINS)] = 0;
     if (tid == NTHREADS - 1) {
       sh.total = 0;
+      sh.cont_head = LIST_END;
       sh.stack_n = 0;
       sh.pass_lo = 0;
       sh.pass_hi = c.epb;
@@ -2367,7 +2491,7 @@ __device__ __forceinline__ void window_cta_body(const DevCfg &c, WindowShared &s
 #ifndef SIMIAN_BULK_SCAN
       __syncthreads(); // (bulk copies: every thread has waited on the mbarrier itself)
 #endif
-      const uint32_t live = link_due(c, sh, ta, slot0, nvalid);
+      const uint32_t live = link_due<BLOBS>(c, sh, ta, slot0, nvalid);
       __syncthreads();
       PHASE(2);
       process_pass<SPLIT, true>(c, sh, ta, slot0, live, 0, c.epb);
@@ -2377,7 +2501,7 @@ __device__ __forceinline__ void window_cta_body(const DevCfg &c, WindowShared &s
         if (tid == 0) c.stage_n[b] = STAGE_REST;
         return;
       } else {
-        filtered_passes(c, sh, slot0, npg);
+        filtered_passes<BLOBS>(c, sh, slot0, npg);
         npg = sh.npg; // scratch pages of a partition are recycled with the others
         if (npg > PGMAX) npg = 0;
       }
@@ -2510,9 +2634,10 @@ __device__ __forceinline__ void window_tail(const DevCfg &c, SH &sh, uint32_t wi
 // the PREVIOUS window over NVLink and append the records to the calendar while
 // the other CTAs run this window (those records lie at or above this window's
 // bound); their times join the LBTS candidate like everything else a CTA reports.
+template <bool BLOBS>
 __global__ void __launch_bounds__(NTHREADS, SIMIAN_MINBLOCKS)
-    k_window(const __grid_constant__ DevCfg c, uint32_t win_ix, int fuse_advance,
-             uint32_t pull_blocks) {
+    k_window_t(const __grid_constant__ DevCfg c, uint32_t win_ix, int fuse_advance,
+               uint32_t pull_blocks) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   WindowShared &sh = *reinterpret_cast<WindowShared *>(smem_raw);
   const int tid = threadIdx.x;
@@ -2572,10 +2697,14 @@ __global__ void __launch_bounds__(NTHREADS, SIMIAN_MINBLOCKS)
     }
   } else {
     if (window_cta_begin(c, sh, Wg, b)) return; // sticky error: CTA-uniform exit
-    window_cta_body<false>(c, sh, b);
+    window_cta_body<false, BLOBS>(c, sh, b);
   }
   window_tail(c, sh, win_ix, fuse_advance);
 }
+// the two instantiations: the ordinary window kernel and the one for models whose
+// events carry payload words (option "payloads")
+#define k_window k_window_t<false>
+#define k_window_blobs k_window_t<true>
 
 #ifndef SIMIAN_LOOP_TU
 // ---- the split window (option "split_handlers"; models of pure handlers) -------

@@ -82,14 +82,17 @@ LANL_STATE_DTYPE = np.dtype([
 assert LANL_STATE_DTYPE.itemsize == 168
 
 
-def lanl_list_size(n_ent, m_ent):
-    """this.list_size (pdes_lanl_benchmarkV8.js:221), p_list == 0; evaluated in
-    the same order as the handler: (prob * n_ent) * m_ent in f64."""
-    return int(math.floor((1.0 / n_ent) * n_ent * m_ent))
+def lanl_list_size(n_ent, m_ent, p_list=0.0):
+    """The LARGEST this.list_size (pdes_lanl_benchmarkV8.js:219-221): every
+    entity's state has room for it.  p_list == 0: the uniform size; otherwise
+    entity 0's (prob = p_list * (1-p_list)**0).  Evaluated in the same order as
+    the handler: (prob * n_ent) * m_ent in f64."""
+    prob = (1.0 / n_ent) if p_list == 0 else p_list
+    return int(math.floor(prob * n_ent * m_ent))
 
 
-def lanl_state_bytes(n_ent, m_ent):
-    return LANL_STATE_DTYPE.itemsize + 8 * lanl_list_size(n_ent, m_ent)
+def lanl_state_bytes(n_ent, m_ent, p_list=0.0):
+    return LANL_STATE_DTYPE.itemsize + 8 * lanl_list_size(n_ent, m_ent, p_list)
 
 
 def lanl_engine_end(end_time, min_delay):
@@ -99,26 +102,29 @@ def lanl_engine_end(end_time, min_delay):
 
 def lanl_params_blob(first_id, n_ent, s_ent, q_avg, p_receive, m_ent, ops_ent,
                      ops_sigma, cache_friendliness, end_time, min_delay,
-                     time_bins, svc_send, svc_receive, svc_finish):
-    """Pack simian_lanl_params_t (include/simian_models.h), 104 bytes."""
+                     time_bins, svc_send, svc_receive, svc_finish,
+                     p_send=0.0, p_list=0.0, invert=False):
+    """Pack simian_lanl_params_t (include/simian_models.h), 120 bytes."""
     r_min = math.pow(1.0 - p_receive, n_ent)  # :196
-    blob = struct.pack("<II10dIHHHHI", first_id, n_ent, s_ent, q_avg, p_receive,
+    blob = struct.pack("<II12dIHHHHI", first_id, n_ent, s_ent, q_avg, p_receive,
                        m_ent, ops_ent, ops_sigma, cache_friendliness, end_time,
-                       min_delay, r_min, time_bins, svc_send, svc_receive,
-                       svc_finish, 0, 0)
-    assert len(blob) == 104
+                       min_delay, r_min, p_send, p_list, time_bins, svc_send,
+                       svc_receive, svc_finish, 0, 1 if invert else 0)
+    assert len(blob) == 120
     return blob
 
 
 def build_lanl(eng, n_ent, s_ent=100.0, q_avg=1.0, p_receive=0.0, m_ent=1000.0,
                ops_ent=1000.0, ops_sigma=0.1, cache_friendliness=0.5,
-               end_time=100.0, min_delay=1.0, time_bins=10):
+               end_time=100.0, min_delay=1.0, time_bins=10, p_send=0.0,
+               p_list=0.0, invert=False):
     """The "MAIN" of pdes_lanl_benchmarkV8.js:346-356: one addEntity loop whose
     constructors schedule FinishHandler and run the first SendHandler.  The
     engine must have been created with end = lanl_engine_end(end_time,
-    min_delay).  p_send == 0 and p_list == 0 (see simian_models.h)."""
+    min_delay).  p_send / invert / p_list: the geometric source and list-size
+    distributions (:209-221); every entity's state has room for the largest list."""
     assert time_bins <= LANL_TIME_BINS
-    eng.define_class(LANL_CLASS, lanl_state_bytes(n_ent, m_ent))
+    eng.define_class(LANL_CLASS, lanl_state_bytes(n_ent, m_ent, p_list))
     eng.add_entities(LANL_CLASS, 0, n_ent)
     eng.attach_service(LANL_CLASS, "SendHandler", "lanl_send")
     eng.attach_service(LANL_CLASS, "ReceiveHandler", "lanl_receive")
@@ -128,16 +134,19 @@ def build_lanl(eng, n_ent, s_ent=100.0, q_avg=1.0, p_receive=0.0, m_ent=1000.0,
     eng.set_class_params(LANL_CLASS, lanl_params_blob(
         eng.first_id(LANL_CLASS), n_ent, s_ent, q_avg, p_receive, m_ent,
         ops_ent, ops_sigma, cache_friendliness, end_time, min_delay, time_bins,
-        *ids))
-    # each constructor sends FinishHandler + up to ceil(q_target) timers + 1 request
+        *ids, p_send=p_send, p_list=p_list, invert=invert))
+    # each constructor sends FinishHandler + up to ceil(q_target) timers + 1 request;
+    # with a geometric source distribution the busiest entity's q_target is
+    # q_avg * n_ent * p_send (the sum over the entities stays about q_avg * n_ent)
     per = 3 + int(math.ceil(q_avg))
-    eng.construct_entities(LANL_CLASS, "lanl_construct", n_ent * per)
+    extra = int(math.ceil(q_avg * n_ent * p_send)) if p_send else 0
+    eng.construct_entities(LANL_CLASS, "lanl_construct", n_ent * per + extra)
     return eng
 
 
-def lanl_states(raw, n_ent, m_ent):
-    """split simian_read_state bytes into (struct array, lists[n, list_size])"""
-    sb = lanl_state_bytes(n_ent, m_ent)
+def lanl_states(raw, n_ent, m_ent, p_list=0.0):
+    """split simian_read_state bytes into (struct array, lists[n, max list_size])"""
+    sb = lanl_state_bytes(n_ent, m_ent, p_list)
     a = np.frombuffer(bytes(raw), dtype=np.uint8).reshape(n_ent, sb)
     st = a[:, :168].copy().view(LANL_STATE_DTYPE).reshape(n_ent)
     lists = a[:, 168:].copy().view("<f8").reshape(n_ent, -1)
@@ -220,4 +229,32 @@ def build_hello(eng, count, t_alice=0.0, t_bob=50.0):
     eng.set_class_params("Bob", blob)
     eng.sched_service_bulk(t_alice, "generate", 0, "Alice", 0, count, 1)
     eng.sched_service_bulk(t_bob, "generate", 0, "Bob", 0, count, 1)
+    return eng
+
+
+# ---- payloads beyond 8 bytes (entity.js:52-60: `data` is any object) ------------
+
+BLOB_SERVICES = ("send", "recv", "ack")
+
+
+def blob_params_blob(first_id, n, lookahead, max_words, ids):
+    """Pack simian_blob_params_t (include/simian_models.h), 32 bytes."""
+    blob = struct.pack("<IIdIIHHHH", first_id, n, lookahead, max_words, 0, *ids, 0)
+    assert len(blob) == 32
+    return blob
+
+
+def build_blobs(eng, n, lookahead, max_words):
+    """The payload test model: every entity keeps sending a random-length vector of
+    64-bit words to a random entity, which folds it and acknowledges the fold.
+    CUDA engines need option payloads=1."""
+    ids = [eng.intern_service(s) for s in BLOB_SERVICES]
+    eng.define_class("Node", 0)
+    eng.add_entities("Node", 0, n)
+    eng.attach_service("Node", "send", "blob_send")
+    eng.attach_service("Node", "recv", "blob_recv")
+    eng.attach_service("Node", "ack", "blob_ack")
+    eng.set_class_params("Node", blob_params_blob(eng.first_id("Node"), n, lookahead,
+                                                   max_words, ids))
+    eng.sched_service_bulk(0.0, "send", 0, "Node", 0, n, 1)
     return eng

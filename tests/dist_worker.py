@@ -37,8 +37,20 @@ LANL = dict(kind="lanl", n_ent=2100, s_ent=12.0, q_avg=2.0, p_receive=0.002, m_e
             ops_ent=30.0, ops_sigma=0.2, cache_friendliness=0.5, end_time=8.0,
             min_delay=0.5, time_bins=16, seed=4)
 HELLO = dict(kind="hello", count=300, end=200.0, min_delay=0.5, seed=3)
+# payloads beyond 8 bytes: headers + continuation records through the outboxes
+BLOBS = dict(kind="blobs", n=1500, end=6.0, min_delay=0.25, lookahead=0.25, max_words=12, seed=9)
 CASES["lanl"] = LANL
 CASES["hello"] = HELLO
+CASES["blobs"] = BLOBS
+
+
+def engine_options(c):
+    """CUDA engine options a case needs"""
+    if c.get("kind") == "hello":
+        return {"bucket_width": 1.0}
+    if c.get("kind") == "blobs":
+        return {"payloads": 1}
+    return {"bucket_width": 1.0 / 32} if c.get("min_delay", 1.0) < 0.05 else {}
 
 
 def build(eng, c, world):
@@ -51,6 +63,10 @@ def build(eng, c, world):
     if c.get("kind") == "hello":
         from simian_b200.workloads import build_hello
         build_hello(eng, c["count"])
+        return
+    if c.get("kind") == "blobs":
+        from simian_b200.workloads import build_blobs
+        build_blobs(eng, c["n"], c["lookahead"], c["max_words"])
         return
     groups = c["groups"] or world
     build_phold(eng, c["n"], c["per_entity"], c["lookahead"], c["p_remote"], 1.0,
@@ -65,6 +81,8 @@ def shape(c):
                 [(LANL_CLASS, c["n_ent"])], 1)
     if c.get("kind") == "hello":
         return c["end"], c["min_delay"], [("Alice", c["count"]), ("Bob", c["count"])], 1
+    if c.get("kind") == "blobs":
+        return c["end"], c["min_delay"], [("Node", c["n"])], 0
     return c["end"], c["min_delay"], [("Node", c["n"])], 0
 
 

@@ -55,9 +55,14 @@ LANL_KEYS = ("n_ent", "s_ent", "q_avg", "p_receive", "m_ent", "ops_ent",
              "time_bins")
 
 
+LANL_OPT_KEYS = ("p_send", "p_list", "invert")
+
+
 def build_lanl_case(eng, case):
     from simian_b200.workloads import build_lanl
-    build_lanl(eng, **{k: case[k] for k in LANL_KEYS})
+    kw = {k: case[k] for k in LANL_KEYS}
+    kw.update({k: case[k] for k in LANL_OPT_KEYS if k in case})
+    build_lanl(eng, **kw)
     return eng
 
 
@@ -66,8 +71,9 @@ def read_lanl(handle, case):
     from simian_b200.workloads import (LANL_CLASS, lanl_state_bytes,
                                        lanl_states)
     n = case["n_ent"]
-    raw = handle.read_state(LANL_CLASS, n, lanl_state_bytes(n, case["m_ent"]))
-    st, lists = lanl_states(raw, n, case["m_ent"])
+    pl = case.get("p_list", 0.0)
+    raw = handle.read_state(LANL_CLASS, n, lanl_state_bytes(n, case["m_ent"], pl))
+    st, lists = lanl_states(raw, n, case["m_ent"], pl)
     return (handle.read_counts(LANL_CLASS, n),
             handle.read_trace_hashes(LANL_CLASS, n), st, lists)
 
@@ -126,3 +132,25 @@ def run_hello(handle_factory, case):
     hashes = np.concatenate([h.read_trace_hashes("Alice", n), h.read_trace_hashes("Bob", n)])
     h.close()
     return st, counts, hashes
+
+
+# ---- payloads beyond 8 bytes ("blobs" model) -------------------------------------
+
+def run_blobs(handle, case):
+    """-> (stats, counts, hashes)"""
+    from simian_b200.workloads import build_blobs
+    build_blobs(handle, case["n"], case["lookahead"], case["max_words"])
+    st = handle.run()
+    out = (st, handle.read_counts("Node", case["n"]), handle.read_trace_hashes("Node", case["n"]))
+    handle.close()
+    return out
+
+
+def assert_blob_golden(case, st, counts, hashes):
+    """against tests/golden/blob_simianpie.json (unmodified SimianPie engine, events
+    whose data is a Python list)"""
+    assert st["total_events"] == case["total_events"]
+    assert list(counts) == case["counts"]
+    assert ["%016x" % x for x in hashes] == case["hashes"]
+    assert "%016x" % st["digest"] == case["digest"]
+    assert float(st["last_time"]).hex() == case["last_time_hex"]

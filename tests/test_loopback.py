@@ -7,7 +7,7 @@ are placement invariant)."""
 import numpy as np
 import pytest
 
-from dist_worker import CASES, build, read_all, shape
+from dist_worker import CASES, build, engine_options, read_all, shape
 from simian_b200.distributed import drive_windows_loopback
 
 
@@ -70,16 +70,14 @@ def test_loopback_driver_with_oracle_ranks(name, world, oracle_mod):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("world", [2, 3])
-@pytest.mark.parametrize("name", ["ross", "other_group", "uniform_sparse", "lanl", "hello"])
+@pytest.mark.parametrize("name", ["ross", "other_group", "uniform_sparse", "lanl", "hello", "blobs"])
 def test_cuda_ranks_share_one_gpu(name, world, oracle_mod):
     from simian_b200 import capi
     from simian_b200.distributed import GpuRankEngine
     c = CASES[name]
     end, min_delay, classes, tie_mode = shape(c)
     ref = _reference(oracle_mod, c, world)
-    opts = {"bucket_width": 1.0 / 32} if min_delay < 0.05 else {}
-    if c.get("kind") == "hello":
-        opts = {"bucket_width": 1.0}
+    opts = engine_options(c)
     engines = []
     for rank in range(world):
         e = capi.Engine("dist", 0.0, end, min_delay, rank=rank, size=world, device=0,
@@ -100,7 +98,7 @@ def test_cuda_ranks_share_one_gpu(name, world, oracle_mod):
 @pytest.mark.gpu
 @pytest.mark.parametrize("deferred", [0, 1], ids=["pull_all", "deferred_pull"])
 @pytest.mark.parametrize("world", [2, 3, 4, 8])
-@pytest.mark.parametrize("name", ["ross", "other_group", "uniform_sparse", "lanl", "hello"])
+@pytest.mark.parametrize("name", ["ross", "other_group", "uniform_sparse", "lanl", "hello", "blobs"])
 def test_device_driven_exchange_all_ranks_on_one_gpu(name, world, deferred, oracle_mod):
     """The data plane the multi-GPU numbers come from -- k_window(fuse = 3: LBTS
     candidate published into the peers' exchange slots) -> k_pull (flags, then
@@ -117,9 +115,7 @@ def test_device_driven_exchange_all_ranks_on_one_gpu(name, world, deferred, orac
     c = CASES[name]
     end, min_delay, classes, tie_mode = shape(c)
     ref = _reference(oracle_mod, c, world)
-    opts = {"bucket_width": 1.0 / 32} if min_delay < 0.05 else {}
-    if c.get("kind") == "hello":
-        opts = {"bucket_width": 1.0}
+    opts = engine_options(c)
     engines = []
     for rank in range(world):
         e = capi.Engine("p2p", 0.0, end, min_delay, rank=rank, size=world, device=0,

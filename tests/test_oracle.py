@@ -118,6 +118,22 @@ def test_spec_bit_exact_vs_pyspec(oracle_mod):
         assert L.oracle_spec_digest_term(e, c, x) == pyspec.digest_term(e, c, x)
 
 
+def test_integer_power_is_bit_exact_and_close_to_libm(oracle_mod):
+    """simian_powi (the geometric distributions of the LANL benchmark,
+    pdes_lanl_benchmarkV8.js:211-212,220): same bits on host and in pyspec, and
+    within a few ulp-per-multiplication of math.pow"""
+    from oracle import pyspec
+    L = oracle_mod.lib()
+    rnd = random.Random(5)
+    assert L.oracle_spec_powi(0.37, 0) == 1.0
+    for _ in range(5000):
+        b, n = rnd.random(), rnd.randrange(0, 5000)
+        v = L.oracle_spec_powi(b, n)
+        assert v == pyspec.powi(b, n)
+        ref = math.pow(b, n)
+        assert abs(v - ref) <= 1e-12 * ref + 5e-324
+
+
 def test_portable_log_is_accurate(oracle_mod):
     L = oracle_mod.lib()
     rnd = random.Random(3)
@@ -277,6 +293,25 @@ def test_oracle_lanl_literal_js_heap_same_counts_and_state(oracle_mod, case):
     assert (h0 != h1).sum() <= 2 * case["distinguishable_ties"]
 
 
+def test_oracle_lanl_geometric_tail_runs_and_is_rank_invariant(oracle_mod):
+    """p_list steep enough that entities deep in the tail have no list and
+    ops == 0: a receive there does no list work (include/simian_models.h); the
+    result does not depend on the number of ranks"""
+    from helpers import run_oracle_lanl
+    case = dict(name="tail", n_ent=300, s_ent=12.0, q_avg=1.0, p_receive=0.0,
+                p_send=0.01, p_list=0.06, invert=True, m_ent=30.0, ops_ent=60.0,
+                ops_sigma=0.1, cache_friendliness=0.5, end_time=5.0, min_delay=0.5,
+                time_bins=10, seed=12)
+    ref = run_oracle_lanl(oracle_mod, case, size=1)
+    st = ref[3]
+    assert (st["list_size"] == 0).sum() > 100 and st["list_size"][0] == 540
+    assert int(st["receive_count"][st["ops"] == 0].sum()) > 0   # the guarded path ran
+    assert float(st["value_sink"][st["ops"] == 0].sum()) == 0.0
+    out = run_oracle_lanl(oracle_mod, case, size=3)
+    assert out[0]["digest"] == ref[0]["digest"]
+    assert out[0]["state_checksum"] == ref[0]["state_checksum"]
+
+
 def test_oracle_lanl_multi_rank_equals_single_rank(oracle_mod):
     from helpers import run_oracle_lanl
     case = lanl_golden_cases()[1]
@@ -350,3 +385,35 @@ def test_oracle_hello_matches_simianpie(oracle_mod, case):
             for i, dep in enumerate(case["order_dependent"]):
                 if not dep:
                     assert hx[i] == case["hashes"][i]
+
+
+# ---- payloads beyond 8 bytes (entity.js:52-60) ------------------------------------
+
+BLOB_GOLD = os.path.join(os.path.dirname(__file__), "golden", "blob_simianpie.json")
+
+
+def blob_golden_cases():
+    with open(BLOB_GOLD) as f:
+        return json.load(f)["cases"]
+
+
+@pytest.mark.parametrize("case", blob_golden_cases(), ids=lambda c: c["name"])
+def test_oracle_payloads_match_simianpie_goldens(oracle_mod, case):
+    """events whose data is a list of words: same counts, trace hashes (they cover
+    the fold of every payload the receivers acknowledged), digest, final time as the
+    unmodified SimianPie engine"""
+    from helpers import assert_blob_golden, run_blobs
+    o = oracle_mod.Oracle(case["name"], 0.0, case["end"], case["min_delay"], seed=case["seed"])
+    assert_blob_golden(case, *run_blobs(o, case))
+
+
+def test_oracle_payloads_are_rank_invariant(oracle_mod):
+    from helpers import run_blobs
+    case = dict(name="b", n=300, end=6.0, min_delay=0.25, lookahead=0.25, max_words=12, seed=5)
+    ref = run_blobs(oracle_mod.Oracle("b", 0.0, case["end"], case["min_delay"], seed=5), case)
+    for size in (2, 3):
+        out = run_blobs(oracle_mod.Oracle("b", 0.0, case["end"], case["min_delay"], size=size,
+                                          seed=5, threads=size), case)
+        assert out[0]["digest"] == ref[0]["digest"]
+        np.testing.assert_array_equal(out[1], ref[1])
+        np.testing.assert_array_equal(out[2], ref[2])

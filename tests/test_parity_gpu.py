@@ -221,6 +221,18 @@ LANL_CASES = [
          p_receive=0.0, m_ent=16.0, ops_ent=16.0, ops_sigma=0.5,
          cache_friendliness=0.75, end_time=4.0, min_delay=0.25, time_bins=8,
          seed=8),
+    # geometric source and list-size distributions (pdes_lanl_benchmarkV8.js:209-221),
+    # several blocks; every entity keeps a list and ops >= 1
+    dict(name="lanl_geometric_mild", n_ent=1400, s_ent=10.0, q_avg=1.0,
+         p_receive=0.001, p_send=0.002, p_list=0.003, invert=False, m_ent=40.0,
+         ops_ent=100.0, ops_sigma=0.2, cache_friendliness=0.5, end_time=6.0,
+         min_delay=0.5, time_bins=8, seed=10),
+    # a steep list-size distribution: the entities deep in the tail own no list and
+    # have ops == 0 (no list work on a receive); inverted source distribution
+    dict(name="lanl_geometric_steep_tail", n_ent=700, s_ent=12.0, q_avg=1.0,
+         p_receive=0.0, p_send=0.004, p_list=0.05, invert=True, m_ent=30.0,
+         ops_ent=60.0, ops_sigma=0.1, cache_friendliness=0.5, end_time=5.0,
+         min_delay=0.5, time_bins=10, seed=12),
 ]
 
 
@@ -398,3 +410,60 @@ def test_split_window_matches_oracle(case, opts, oracle_mod):
     se, ce, he = run_engine_phold(case, split_handlers=1, persistent_loop=0, **opts)
     assert_parity(so, co, ho, se, ce, he)
     assert se["kernel_launches"] >= 3 * se["windows"]
+
+
+# ---- payloads beyond 8 bytes (entity.js:52-60: `data` is any object) ----------------
+
+BLOB_GOLD = os.path.join(os.path.dirname(__file__), "golden", "blob_simianpie.json")
+
+
+def blob_golden_cases():
+    with open(BLOB_GOLD) as f:
+        return json.load(f)["cases"]
+
+
+@pytest.mark.parametrize("case", blob_golden_cases(), ids=lambda c: c["name"])
+def test_engine_payloads_match_simianpie_goldens(case):
+    """events whose data is a list of words (SimianPie: a Python list): header +
+    continuation records through the calendar; the acknowledged fold of every payload
+    is covered by the senders' trace hashes"""
+    from helpers import assert_blob_golden, run_blobs
+    from simian_b200 import capi
+    e = capi.Engine(case["name"], 0.0, case["end"], case["min_delay"], seed=case["seed"],
+                    payloads=1)
+    assert_blob_golden(case, *run_blobs(e, case))
+
+
+BLOB_CASES = [
+    (dict(name="blobs_multi_block", n=3000, end=5.0, min_delay=0.25, lookahead=0.25,
+          max_words=12, seed=21), dict()),
+    # wide windows and small entity blocks: the due records (events + payload words)
+    # overflow the CTA's slots in every window -- filtered scans, burst partition
+    (dict(name="blobs_overflowing_windows", n=1200, end=9.0, min_delay=1.5, lookahead=1.5,
+          max_words=24, seed=22), dict(bucket_width=0.5)),
+    (dict(name="blobs_small_blocks", n=900, end=6.0, min_delay=0.5, lookahead=0.5,
+          max_words=7, seed=23), dict(block_entities=48)),
+]
+
+
+@pytest.mark.parametrize("case,opts", BLOB_CASES, ids=lambda c: c.get("name", "") if "n" in c else None)
+def test_engine_payloads_match_oracle(case, opts, oracle_mod):
+    from helpers import assert_parity, run_blobs
+    from simian_b200 import capi
+    so, co, ho = run_blobs(oracle_mod.Oracle(case["name"], 0.0, case["end"], case["min_delay"],
+                                             seed=case["seed"]), case)
+    se, ce, he = run_blobs(capi.Engine(case["name"], 0.0, case["end"], case["min_delay"],
+                                       seed=case["seed"], payloads=1, **opts), case)
+    assert_parity(so, co, ho, se, ce, he)
+
+
+def test_payloads_need_the_option(oracle_mod):
+    """without option payloads = 1 a handler that sends a payload is a loud error"""
+    from helpers import run_blobs
+    from simian_b200 import capi
+    case = dict(name="b", n=64, end=2.0, min_delay=0.25, lookahead=0.25, max_words=4, seed=1)
+    e = capi.Engine("b", 0.0, case["end"], case["min_delay"], seed=1)
+    with pytest.raises(capi.SimianError) as ei:
+        run_blobs(e, case)
+    assert ei.value.code == 16
+    e.close()
