@@ -20,6 +20,12 @@
  *                    uint32_t rx)       self.reqService(...)  entity.js:35-68
  *        rx == SIMIAN_NULL_ENTITY  <=>  rx omitted (send to self, no lookahead
  *        check, entity.js:41,50-51)
+ *   payloads beyond the 8-byte word (entity.js:52-60: `data` is any object):
+ *   void req_service_blob(double offset, uint16_t service, const uint64_t *words,
+ *                         uint32_t nwords, uint32_t rx)
+ *   void req_service_blob_fn(offset, service, nwords, rx, word)   word(k) -> uint64_t
+ *   uint32_t payload_words()            words the event being executed carries
+ *   uint64_t payload(uint32_t k)        word k of them
  */
 #ifndef SIMIAN_MODELS_H
 #define SIMIAN_MODELS_H

@@ -181,6 +181,9 @@ struct simian_engine {
   // trace chain, recycle) and k_emit (handlers + appends at a higher occupancy).  Pure
   // handlers only; -1 = the default for the model (see setup_layout)
   int split = -1;
+  // option "pdl_exchange": the three launches of a device-driven multi-GPU window
+  // (k_window -> k_pull -> k_advance) are programmatic dependents of each other
+  int pdl_exchange = 0;
   int payloads = 0; // option "payloads": handlers may send / read payload words (continuation records)
   bool split_on = false; // in force for this layout
   uint32_t rest_ctas = 444; // grid of k_window_rest: the CTAs resident at once
@@ -737,6 +740,7 @@ int simian_set_option(simian_engine *e, const char *key, double v) {
   else if (k == "deferred_pull") e->deferred_pull = v != 0;
   else if (k == "split_handlers") e->split = v != 0;
   else if (k == "payloads") e->payloads = v != 0;
+  else if (k == "pdl_exchange") e->pdl_exchange = v != 0;
   else return e->fail(SIMIAN_ERR_BAD_ARGUMENT, "unknown option " + k);
   return 0;
 }
@@ -1074,8 +1078,19 @@ int simian_window_pull(simian_engine *e, int waitForPeers) {
   if (const char *env = getenv("SIMIAN_B200_PULL_BPP")) bpp = (uint32_t)atoi(env); // (tuning)
   if (bpp < 1) bpp = 1;
   // with two-ended outboxes: the part that must be in before the next window
-  k_pull<<<(e->size - 1) * bpp, 256, 0, e->stream>>>(e->cfg, e->win_ix, bpp, waitForPeers,
-                                                      e->cfg.split_outbox ? 1 : 0);
+  {
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3((e->size - 1) * bpp);
+    lc.blockDim = dim3(256);
+    lc.stream = e->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = at;
+    lc.numAttrs = e->pdl_exchange ? 1 : 0;
+    CK(cudaLaunchKernelEx(&lc, k_pull, e->cfg, e->win_ix, bpp, waitForPeers,
+                          e->cfg.split_outbox ? 1 : 0));
+  }
   CK(cudaGetLastError());
   e->launches++;
   return 0;
@@ -1088,7 +1103,18 @@ int simian_minvec_ptr(simian_engine *e, void **devMinVec) {
 }
 
 int simian_window_advance_async(simian_engine *e, int minFromPeers) {
-  k_advance<<<1, NTHREADS, 0, e->stream>>>(e->cfg, e->win_ix, minFromPeers);
+  {
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3(1);
+    lc.blockDim = dim3(NTHREADS);
+    lc.stream = e->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = at;
+    lc.numAttrs = e->pdl_exchange ? 1 : 0;
+    CK(cudaLaunchKernelEx(&lc, k_advance, e->cfg, e->win_ix, minFromPeers));
+  }
   CK(cudaGetLastError());
   e->launches++;
   e->win_ix++;
@@ -1167,7 +1193,7 @@ int simian_window_process_lbts(simian_engine *e, int publish) {
     if (bpp < 4u) bpp = 4u;
     pull_blocks = bpp * (uint32_t)(e->size - 1);
   }
-  return launch_window(e, publish ? 3 : 2, pull_blocks, false);
+  return launch_window(e, publish ? 3 : 2, pull_blocks, e->pdl_exchange != 0);
 }
 
 int simian_window_outbox(simian_engine *e, uint32_t *hostCounts, void **devOutbox,

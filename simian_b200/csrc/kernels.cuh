@@ -700,6 +700,9 @@ __global__ void k_pull(const __grid_constant__ DevCfg c, uint32_t win_ix, uint32
   __shared__ AppendCtx ax;
   __shared__ double s_hi_next;
   __shared__ unsigned long long smin;
+  // (programmatic dependent launch, option "pdl_exchange": no-ops otherwise)
+  cudaTriggerProgrammaticLaunchCompletion();
+  cudaGridDependencySynchronize();
   append_ctx_init(ax);
   const WinState &W = c.win[win_ix & 1u];
   if (threadIdx.x == 0) smin = SIMIAN_KEY_NONE;
@@ -2977,6 +2980,8 @@ __global__ void __launch_bounds__(NTHREADS) k_local_min(const __grid_constant__ 
 // size > 1: consume the allreduced {globalMinLeft, min far} (simian.js:144)
 __global__ void __launch_bounds__(NTHREADS) k_advance(const __grid_constant__ DevCfg c, uint32_t win_ix,
                                                       int from_xch) {
+  cudaTriggerProgrammaticLaunchCompletion();
+  cudaGridDependencySynchronize();
   const WinState W = c.win[win_ix & 1u];
   WinState *Wn = &c.win[(win_ix + 1u) & 1u];
   if (W.done) {

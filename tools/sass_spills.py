@@ -3,7 +3,9 @@
 attributes LDL/STL instructions of the kernel's main body to source lines; also
 prints the opcode histogram that goes into profiles/ (UBLKCP / SYNCS = bulk copies
 + mbarrier, LDGSTS = cp.async, ATOMS / ATOMG / RED, BAR).
-usage: python tools/sass_spills.py [lib.so] [--all-functions]"""
+usage: python tools/sass_spills.py [lib.so] [--all-functions] [--kernel=<mangled prefix>]
+(default kernel: the ordinary window kernel k_window_t<false>; e.g. --kernel=_Z14k_window_stage,
+--kernel=_Z6k_emit)"""
 import collections
 import os
 import re
@@ -18,10 +20,13 @@ allf = "--all-functions" in sys.argv
 tmp = tempfile.mkdtemp()
 subprocess.check_call(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp,
                       stdout=subprocess.DEVNULL)
-cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
+kern = next((a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--kernel=")),
+            "_Z10k_window_tILb0E")
+cubin = sorted(f for f in os.listdir(tmp) if f.endswith(".cubin") and "window_loop" not in f)[0]
 txt = subprocess.run(["nvdisasm", "--print-line-info", os.path.join(tmp, cubin)],
                      capture_output=True, text=True).stdout.split("\n")
-start = next(i for i, l in enumerate(txt) if l.startswith(".text._Z8k_window"))
+start = next(i for i, l in enumerate(txt)
+             if l.startswith(".text." + kern) or l.startswith(".text._Z8k_window"))
 end = next((i for i in range(start + 1, len(txt)) if txt[i].startswith("//-------") and ".text." in txt[i]),
            len(txt))
 cur, fn = None, None
