@@ -102,6 +102,9 @@ struct DevAcc {
   unsigned int error; // sticky, first error wins
   unsigned int window_index;
   unsigned int loop_seq; // k_window_loop: windows completed in the current launch sequence
+  unsigned int pad_jobs_;
+  // split sums: descriptors written to c.jobs by window k (k & 1); k_sums(k) clears the other
+  unsigned long long job_total[2];
   double minvec[2]; // {local minLeft candidate, local far min} for allreduce
   unsigned long long phase_cycles[12]; // SIMIAN_PROFILE_PHASES builds only
 };
@@ -180,4 +183,13 @@ struct DevCfg {
   // what they send at its own (higher) occupancy.  null: one kernel does both.
   simian_event_t *stage; // [n_blocks][SIMIAN_REFS]
   uint32_t *stage_n;     // [n_blocks] records parked by the block in this window
+  // deferred sums in a kernel of their own (option "split_sums", stateful handlers):
+  // k_window writes the jobs its handlers parked (simian_defer_weighted_sum) as 32-byte
+  // descriptors -- {list pointer, rng key, na | nj << 20 | di0 << 40 | sink offset << 56,
+  // run length (first job of an entity's run) or 0} -- and k_sums computes them at its
+  // own, higher occupancy.  null: the window kernel computes them itself.
+  simian_event_t *jobs; // [job_cap]: ONE array for all blocks (k_sums balances over it);
+                        // a CTA reserves the range of a pass with one atomic on acc->job_total
+  uint32_t *job_n;      // (unused)
+  uint32_t job_cap, pad4_;
 };

@@ -20,6 +20,9 @@
 #include "../../include/simian_b200.h"
 #include "kernels.cuh"
 
+#ifndef SIMIAN_SPLIT_SUMS_DEFAULT
+#define SIMIAN_SPLIT_SUMS_DEFAULT 1 // option "split_sums" when the model does not say
+#endif
 #ifndef SIMIAN_SPLIT_DEFAULT
 #define SIMIAN_SPLIT_DEFAULT 0 // option "split_handlers" when the model does not say
 #endif
@@ -184,6 +187,12 @@ struct simian_engine {
   // option "pdl_exchange": the three launches of a device-driven multi-GPU window
   // (k_window -> k_pull -> k_advance) are programmatic dependents of each other
   int pdl_exchange = 0;
+  // option "split_sums": the sums stateful handlers defer (simian_defer_weighted_sum, the
+  // LANL receive handler) are computed by k_sums after the window kernel instead of
+  // inside it; -1 = the default for the model
+  int split_sums = -1;
+  uint64_t job_cap = 0; // option "sum_jobs": descriptors per window (0: four per entity)
+  uint32_t sums_ctas = 888; // grid of k_sums: the CTAs resident at once
   int payloads = 0; // option "payloads": handlers may send / read payload words (continuation records)
   bool split_on = false; // in force for this layout
   uint32_t rest_ctas = 444; // grid of k_window_rest: the CTAs resident at once
@@ -499,6 +508,27 @@ int setup_layout(simian_engine *e) {
     if (dev_alloc(e, &c.stage_n, c.n_blocks)) return e->err_code;
     CK(cudaMemsetAsync(c.stage_n, 0, sizeof(uint32_t) * (size_t)c.n_blocks, e->stream));
   }
+  c.jobs = nullptr;
+  c.job_n = nullptr;
+  c.job_cap = 0;
+  if (!c.all_pure && !e->loop &&
+      (e->split_sums < 0 ? SIMIAN_SPLIT_SUMS_DEFAULT != 0 : e->split_sums != 0)) {
+    // descriptors of one window, all blocks together: by default four per entity (the
+    // LANL benchmark parks about one per entity and window), at least 1 M
+    uint64_t cap = e->job_cap ? e->job_cap : 4ull * c.n_slots;
+    if (!e->job_cap && cap < (1ull << 20)) cap = 1ull << 20;
+    if (cap > 0xFFFFFFF0ull) cap = 0xFFFFFFF0ull;
+    c.job_cap = (uint32_t)cap;
+    if (dev_alloc(e, &c.jobs, (size_t)c.job_cap)) return e->err_code;
+    int sms = 0, per_sm = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->device);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sums, NTHREADS, 0) != cudaSuccess ||
+        per_sm < 1) {
+      cudaGetLastError();
+      per_sm = 1;
+    }
+    e->sums_ctas = (uint32_t)(per_sm * (sms > 0 ? sms : 148));
+  }
   if (e->size > 1) {
     // a window in which every local event sends one record to a uniformly chosen
     // peer (the t = 0 burst of PHOLD at 100 % remote), with a factor 2 of slack
@@ -741,6 +771,8 @@ int simian_set_option(simian_engine *e, const char *key, double v) {
   else if (k == "split_handlers") e->split = v != 0;
   else if (k == "payloads") e->payloads = v != 0;
   else if (k == "pdl_exchange") e->pdl_exchange = v != 0;
+  else if (k == "split_sums") e->split_sums = v != 0;
+  else if (k == "sum_jobs") e->job_cap = v < 1 ? 1 : (uint64_t)v;
   else return e->fail(SIMIAN_ERR_BAD_ARGUMENT, "unknown option " + k);
   return 0;
 }
@@ -1175,6 +1207,12 @@ static int launch_window(simian_engine *e, int fuse, uint32_t pull_blocks, bool 
   else
     CK(cudaLaunchKernelEx(&lc, k_window, e->cfg, e->win_ix, fuse, pull_blocks));
   e->launches++;
+  if (e->cfg.jobs) { // the sums the window's handlers deferred
+    lc.gridDim = dim3(e->sums_ctas);
+    lc.dynamicSmemBytes = 0;
+    CK(cudaLaunchKernelEx(&lc, k_sums, e->cfg, e->win_ix));
+    e->launches++;
+  }
   return 0;
 }
 

@@ -447,6 +447,7 @@ __global__ void k_init(const __grid_constant__ DevCfg c, uint32_t n_cells) {
     a->error = 0;
     a->window_index = 0;
     a->loop_seq = 0;
+    a->job_total[0] = a->job_total[1] = 0;
     a->minvec[0] = a->minvec[1] = 0;
     for (int q = 0; q < 12; q++) a->phase_cycles[q] = 0;
     WinState w;
@@ -824,7 +825,10 @@ struct __align__(32) WindowShared {
   uint32_t nparts, bin_shift;
   // due continuation records of the block (payload words, SIMIAN_EVF_CONT): one list
   // through nxt[], searched by payload(k); they are in no entity's list
-  uint32_t cont_head, pad_cont_;
+  uint32_t cont_head;
+  // split sums: jobs the handlers of this pass parked, the range of c.jobs reserved for
+  // them (SIMIAN_NONE: no room, computed here) and the descriptors written so far
+  uint32_t pass_jobs, job_base, job_count;
   uint32_t head[SIMIAN_EPB_MAX];   // per local entity: index of its first due event
   uint32_t pg_id[PGMAX];           // pages of this block's cells in the window rows
   uint32_t pg_off[PGMAX];          // records in the pages listed before this one
@@ -1222,9 +1226,13 @@ __device__ __forceinline__ bool simian_defer_weighted_sum(DevCtx<true> &ctx, con
   sh.xs[ctx.job_slot] = (unsigned long long)na | ((unsigned long long)nj << 20) |
                         ((unsigned long long)di0 << 40) | (delta << 46) |
                         ((unsigned long long)(unsigned char)(signed char)off << 56);
+  if (ctx.c.jobs) atomicAdd(&sh.pass_jobs, 1u);
   return true;
 }
 
+#ifndef SIMIAN_WSUM_UNROLL
+#define SIMIAN_WSUM_UNROLL 1
+#endif
 // one job, all 32 lanes: partial sums by lane, then the butterfly (the defined order)
 __device__ __forceinline__ double warp_weighted_sum(unsigned long long key, const double *list,
                                                     uint32_t na, uint32_t nj, uint32_t di0) {
@@ -1236,6 +1244,8 @@ __device__ __forceinline__ double warp_weighted_sum(unsigned long long key, cons
   // per config-4 run).
   const uint32_t qi = 32u / nj, ri = 32u % nj;
   uint32_t i = lane / nj, j = lane % nj;
+  constexpr int wsum_unroll = SIMIAN_WSUM_UNROLL;
+#pragma unroll wsum_unroll
   for (uint32_t k = lane; k < total; k += 32u) {
     p += list[i] * simian_u01(simian_rng_draw(key, di0 + k));
     i += qi;
@@ -2144,6 +2154,11 @@ __device__ __forceinline__ void append_staged(const DevCfg &c, SH &sh, AppendCtx
   }
 }
 
+// the entity block a first slot belongs to
+__device__ __forceinline__ uint32_t blockIdx_of_block(const DevCfg &c, uint32_t slot0) {
+  return (uint32_t)__umul64hi((unsigned long long)slot0, c.epb_inv);
+}
+
 // K3 + K4 + trace chain for the m due events one pass collected into the
 // shared-memory slots (entities [e_lo, e_hi) of the block).  CTA-uniform.
 // `live`: bit u = slot (threadIdx.x + u * NTHREADS) holds a due event of this thread.
@@ -2224,6 +2239,7 @@ __device__ __forceinline__ void process_pass(const DevCfg &c, WindowShared &sh, 
 #pragma unroll
     for (int u = 0; u < EV_PER_THREAD; u++)
       if (live & (1u << u)) sh.xs[tid + u * NTHREADS] = 0ull;
+    if (tid == 0) sh.pass_jobs = sh.job_count = 0;
     __syncthreads();
     // K3 + K4: stateful handlers, one thread per entity.  A separate
     // accumulator keeps `ta` of the thread-per-event path in registers
@@ -2238,10 +2254,38 @@ __device__ __forceinline__ void process_pass(const DevCfg &c, WindowShared &sh, 
     // entity, the entity's jobs in commit order, each in the defined order
     __syncthreads();
     PHASE(4);
+    if (c.jobs) { // split sums: one range of the global job array for this pass
+      if (tid == 0) {
+        sh.job_base = SIMIAN_NONE;
+        const uint32_t n = sh.pass_jobs;
+        if (n) {
+          unsigned long long *tot = &c.acc->job_total[W.parity & 1u];
+          const unsigned long long base = atomicAdd(tot, (unsigned long long)n);
+          if (base + n <= (unsigned long long)c.job_cap)
+            sh.job_base = (uint32_t)base;
+          else // no room: give the range back, the sums of this pass are computed here
+            atomicAdd(tot, 0ull - (unsigned long long)n);
+        }
+      }
+      __syncthreads();
+    }
     for (uint32_t le = e_lo + (uint32_t)(tid >> 5); le < e_hi; le += NTHREADS / 32) {
       const uint32_t first = sh.head[le];
       if (first == LIST_END) continue;
+      // split sums: the entity's jobs become one RUN of descriptors in the block's
+      // segment of c.jobs, computed by k_sums; when the segment is full the warp
+      // computes them here as without the option
+      uint32_t run_base = SIMIAN_NONE, run_len = 0;
+      if (c.jobs && sh.job_base != SIMIAN_NONE) {
+        for (uint32_t j = first; j != LIST_END; j = sh.nxt[j])
+          if (sh.xs[j]) run_len++;
+        if (run_len == 0) continue;
+        uint32_t base = 0;
+        if ((tid & 31) == 0) base = atomicAdd(&sh.job_count, run_len);
+        run_base = sh.job_base + __shfl_sync(0xffffffffu, base, 0);
+      }
       int last = -1;
+      uint32_t emitted_jobs = 0;
 #pragma unroll 1
       for (;;) {
         // the next job of this entity (warp-uniform walk of its short list)
@@ -2260,6 +2304,15 @@ __device__ __forceinline__ void process_pass(const DevCfg &c, WindowShared &sh, 
         int k;
         const uint32_t gid = gid_of_slot(c, slot0 + le, k);
         const unsigned long long key = simian_rng_key(c.seed, gid, SH_CORE(sh)[le].count + bd);
+        if (run_base != SIMIAN_NONE) {
+          if ((tid & 31) == 0)
+            st_rec_2x16(c.jobs + ((size_t)run_base + emitted_jobs),
+                        (unsigned long long)list, key,
+                        x & ~(0x3FFull << 46), // (na, nj, di0, sink offset; the commit delta is spent)
+                        emitted_jobs == 0 ? (unsigned long long)run_len : 0ull);
+          emitted_jobs++;
+          continue;
+        }
         const double v = warp_weighted_sum(key, list, JOB_NA(x), JOB_NJ(x), JOB_DI0(x));
         if ((tid & 31) == 0) {
           double *sink = const_cast<double *>(list) + JOB_SINK_OFF(x);
@@ -2414,6 +2467,8 @@ __device__ __forceinline__ uint32_t window_cta_begin(const DevCfg &c, WindowShar
     sh.nfree = 0;
     sh.free_pos = 0;
     sh.is_last = 0;
+    sh.job_count = sh.pass_jobs = 0;
+    sh.job_base = SIMIAN_NONE;
     sh.ax.far_appends = sh.ax.page_allocs = sh.ax.pgc_take = 0;
     sh.ax.pgc_have = ld_cg(&c.bcount[b]);
     sh.ax.gstack_count = nullptr;
@@ -2900,6 +2955,92 @@ __global__ void __launch_bounds__(NTHREADS, SIMIAN_EMIT_MINBLOCKS)
     }
   }
   window_tail(c, sh, win_ix, fuse_advance);
+}
+
+// k_sums (option "split_sums"): the weighted subset sums the stateful handlers of a
+// window deferred (the LANL receive handler, pdes_lanl_benchmarkV8.js:304-307), one
+// WARP per run of an entity's jobs, each sum in the order simian_lanl_weighted_sum
+// defines, the runs' values added to the entity's sink in commit order.  The list
+// elements a sum reads are contiguous (list[0 .. na)): the warp fetches them into its
+// own 4 KB of shared memory with cp.async -- every load of the job in flight at once --
+// instead of one dependent HBM round trip per 32 terms (inside k_window, whose shared
+// memory is full, 67 % of the stall samples of the sum are that load), 512 elements
+// at a time; then the terms are pure arithmetic on 40 registers.
+#ifndef SIMIAN_SUMS_MINBLOCKS
+#define SIMIAN_SUMS_MINBLOCKS 4
+#endif
+#define SUMS_CHUNK 512 // list elements a warp stages at a time
+#ifndef SIMIAN_SUMS_UNROLL
+#define SIMIAN_SUMS_UNROLL 4
+#endif
+
+// one job, all 32 lanes, the defined order (simian_lanl_weighted_sum): lane l adds the
+// terms k = l, l + 32, ... in increasing k; the list comes through `buf` in chunks
+__device__ __forceinline__ double warp_weighted_sum_staged(unsigned long long key,
+                                                           const double *list, uint32_t na,
+                                                           uint32_t nj, uint32_t di0,
+                                                           double *buf) {
+  const uint32_t lane = threadIdx.x & 31u;
+  double p = 0.0;
+  if (na * nj != 0u) {
+    const uint32_t qi = 32u / nj, ri = 32u % nj;
+#pragma unroll 1
+    for (uint32_t i0 = 0; i0 < na; i0 += SUMS_CHUNK) {
+      const uint32_t cnt = na - i0 < (uint32_t)SUMS_CHUNK ? na - i0 : (uint32_t)SUMS_CHUNK;
+      for (uint32_t q = lane; q < cnt; q += 32u) { // (lists are 8-byte aligned only)
+        uint32_t d = (uint32_t)__cvta_generic_to_shared(buf + q);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(list + i0 + q)
+                     : "memory");
+      }
+      cp_async_wait_all();
+      __syncwarp();
+      const uint32_t k_lo = i0 * nj, k_hi = (i0 + cnt) * nj;
+      uint32_t k = k_lo + ((lane - k_lo) & 31u); // first k >= k_lo with k = lane (mod 32)
+      uint32_t i = k / nj - i0, j = k % nj;
+      constexpr int sums_unroll = SIMIAN_SUMS_UNROLL;
+#pragma unroll sums_unroll
+      for (; k < k_hi; k += 32u) {
+        p += buf[i] * simian_u01(simian_rng_draw(key, di0 + k));
+        i += qi;
+        j += ri;
+        if (j >= nj) j -= nj, i++;
+      }
+      __syncwarp(); // the chunk is overwritten next
+    }
+  }
+  for (int o = 16; o; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+  return p;
+}
+__global__ void __launch_bounds__(NTHREADS, SIMIAN_SUMS_MINBLOCKS)
+    k_sums(const __grid_constant__ DevCfg c, uint32_t win_ix) {
+  __shared__ double sbuf[NTHREADS / 32][SUMS_CHUNK];
+  cudaTriggerProgrammaticLaunchCompletion();
+  cudaGridDependencySynchronize();
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  // the descriptors window win_ix wrote; the counter of the other parity is cleared for
+  // window win_ix + 1 (its last reader, k_sums(win_ix - 1), is long done) -- also when
+  // this launch was enqueued past the end of the run: such a launch then finds zero
+  unsigned long long total = c.acc->job_total[win_ix & 1u];
+  if (blockIdx.x == 0 && threadIdx.x == 0) c.acc->job_total[(win_ix + 1u) & 1u] = 0ull;
+  if (total > c.job_cap) total = c.job_cap;
+  const uint32_t n = (uint32_t)total;
+  // a persistent grid of warps over ALL jobs: an entity block that is a hot spot of the
+  // model (geometric destinations) spreads over the whole GPU
+  for (uint32_t j0 = blockIdx.x * (NTHREADS / 32) + warp; j0 < n; j0 += gridDim.x * (NTHREADS / 32)) {
+    const RecBits h = ld_rec_2x16(c.jobs + j0);
+    const uint32_t run = (uint32_t)h.q3;
+    if (run == 0) continue; // inside another warp's run
+    for (uint32_t r = 0; r < run && j0 + r < n; r++) {
+      const RecBits d = r == 0 ? h : ld_rec_2x16(c.jobs + j0 + r);
+      const double *list = (const double *)d.q0;
+      const double v = warp_weighted_sum_staged(d.q1, list, JOB_NA(d.q2), JOB_NJ(d.q2),
+                                                JOB_DI0(d.q2), sbuf[warp]);
+      if (lane == 0) {
+        double *sink = const_cast<double *>(list) + JOB_SINK_OFF(d.q2);
+        *sink += v;
+      }
+    }
+  }
 }
 #endif
 

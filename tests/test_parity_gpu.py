@@ -196,10 +196,11 @@ def lanl_golden_cases():
         return json.load(f)["cases"]
 
 
+@pytest.mark.parametrize("split_sums", [0, 1], ids=["sums_in_window", "k_sums"])
 @pytest.mark.parametrize("case", lanl_golden_cases(), ids=lambda c: c["name"])
-def test_engine_lanl_matches_simianpie_goldens(case):
+def test_engine_lanl_matches_simianpie_goldens(case, split_sums):
     from helpers import assert_lanl_golden, run_engine_lanl
-    out = run_engine_lanl(case)
+    out = run_engine_lanl(case, split_sums=split_sums)
     assert out[0]["error"] == 0
     assert_lanl_golden(case, *out)
 
@@ -236,13 +237,20 @@ LANL_CASES = [
 ]
 
 
+# the deferred weighted sums: computed by the window kernel itself, by k_sums (option
+# split_sums: one global job array, a persistent grid of warps), and by both when the
+# job array is too small for some passes (sum_jobs = 96: those passes fall back)
+SUM_MODES = [dict(split_sums=0), dict(split_sums=1), dict(split_sums=1, sum_jobs=96)]
+
+
+@pytest.mark.parametrize("sums", SUM_MODES, ids=["sums_in_window", "k_sums", "k_sums_overflowing"])
 @pytest.mark.parametrize("case", LANL_CASES, ids=lambda c: c["name"])
-def test_engine_lanl_matches_oracle(case, oracle_mod):
+def test_engine_lanl_matches_oracle(case, sums, oracle_mod):
     """bit-exact counts, trace hashes (engine tie order = oracle tie_mode 1),
     the whole per-entity state incl. the f64 lists, window and emit counts"""
     from helpers import run_engine_lanl, run_oracle_lanl
     so, co, ho, sto, lo = run_oracle_lanl(oracle_mod, case, tie_mode=1)
-    se, ce, he, ste, le = run_engine_lanl(case)
+    se, ce, he, ste, le = run_engine_lanl(case, **sums)
     assert se["error"] == 0
     assert se["total_events"] == so["total_events"]
     np.testing.assert_array_equal(ce, co)
