@@ -110,6 +110,14 @@ const char *simian_last_error(simian_engine *e);
  *                     (req_service_blob / payload(k) of the handler context; the words
  *                     travel as continuation records, include/simian_spec.h).  Default 0:
  *                     the window kernel then never looks at a record's flags
+ *   "split_sums"      models with stateful handlers: the sums a handler defers
+ *                     (simian_defer_weighted_sum, the LANL receive handler) are computed by
+ *                     k_sums behind the window kernel -- one global job array, a persistent
+ *                     grid of warps -- instead of inside it (default 1; "sum_jobs" = the
+ *                     array's capacity per window, default four per entity; passes that
+ *                     find no room compute their sums in place)
+ *   "pdl_exchange"    1: the launches of a device-driven multi-GPU window are programmatic
+ *                     dependents of each other (default 0: measured equal)
  *   "split_handlers"  1: models of pure handlers run a window as three launches --
  *                     k_window_stage (dequeue, rank, park the events with their commit
  *                     indices, trace chain, recycle; 48 registers), k_window_rest
