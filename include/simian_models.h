@@ -48,6 +48,7 @@ enum simian_builtin_fn {
   SIMIAN_FN_BLOB_SEND = 11,     /* "blob_send"      */
   SIMIAN_FN_BLOB_RECV = 12,     /* "blob_recv"      */
   SIMIAN_FN_BLOB_ACK = 13,      /* "blob_ack"       */
+  SIMIAN_FN_LANL_OUTPUT = 14,   /* "lanl_output"    */
   SIMIAN_FN__END,
   SIMIAN_FN_USER = 32 /* first id of handlers a model author registers (simian_handlers.def) */
 };
@@ -131,8 +132,13 @@ SIMIAN_HD void simian_noop(Ctx &) {}
  * Python twin divides by zero there); the weighted sum `value` is
  * stored in the entity state instead of being discarded (:308) so the compute
  * loop is observable; the statistics fan-in to entity 0 (:311-342, an N-way
- * distinguishable time tie) is done off-path by reading entity
- * state, FinishHandler only commits.                                         */
+ * distinguishable time tie) is by default done off-path by reading
+ * entity state (FinishHandler only commits); with stats_on_path FinishHandler
+ * sends the reference's message -- 7 + time_bins words, a payload (simian_spec.h)
+ * -- to OutputHandler of entity 0, which accumulates the global statistics in
+ * its state (the on-disk table is still written by the host from that state).
+ * All n_ent messages are due at entity 0 in ONE window: models of a few dozen
+ * entities (an entity's due records must fit a CTA's slots).                   */
 
 #define SIMIAN_LANL_TIME_BINS 16
 #define SIMIAN_CTOR_COMMIT 0xFFFFFFFFFFFFFFFFull /* commit index of a constructor call */
@@ -149,8 +155,10 @@ typedef struct simian_lanl_params {
   double p_send, p_list; /* :103,107: 0 = uniform */
   uint32_t time_bins; /* :112, <= SIMIAN_LANL_TIME_BINS */
   uint16_t svc_send, svc_receive; /* interned ids of "SendHandler" / "ReceiveHandler" */
-  uint16_t svc_finish, pad0_;
-  uint32_t invert; /* :104 */
+  uint16_t svc_finish;
+  uint16_t svc_output;    /* "OutputHandler" (stats_on_path) */
+  uint16_t invert;        /* :104 */
+  uint16_t stats_on_path; /* FinishHandler sends the statistics message to entity 0 (:311-315) */
 } simian_lanl_params_t; /* 120 bytes */
 
 /* per-entity state (:202-252); the list of list_size doubles follows it */
@@ -161,7 +169,12 @@ typedef struct simian_lanl_state {
   uint64_t send_count, receive_count, ops_count;          /* :233-235 */
   uint32_t list_size, active_elements;                    /* :221,223 */
   uint32_t time_sends[SIMIAN_LANL_TIME_BINS];             /* :239-240 */
-} simian_lanl_state_t; /* 168 bytes */
+  /* the global statistics entity 0 collects in OutputHandler (:241-251, :321-330);
+   * present in every entity's state, used by entity 0 only (stats_on_path) */
+  uint64_t stats_received, gsend_count, greceive_count, gops_count;
+  double gops_max, gops_min, gops_mean;
+  uint32_t gtime_sends[SIMIAN_LANL_TIME_BINS];
+} simian_lanl_state_t; /* 288 bytes */
 
 SIMIAN_HD double simian_floor(double x) { /* Math.floor for |x| < 2^52 */
   double t = (double)(long long)x;
@@ -289,9 +302,50 @@ SIMIAN_HD void simian_lanl_receive(Ctx &ctx) {
   st->ops_count += (uint64_t)na * nj;
 }
 
-/* FinishHandler (:311-315): the stats fan-in is done off-path */
+/* FinishHandler (:311-315): msg = [num, send_count, receive_count, ops_min, ops_mean,
+ * ops_max, time_sends[0 .. time_bins), opsCount] to OutputHandler of entity 0 */
 template <class Ctx>
-SIMIAN_HD void simian_lanl_finish(Ctx &) {}
+SIMIAN_HD void simian_lanl_finish(Ctx &ctx) {
+  const simian_lanl_params_t *p = (const simian_lanl_params_t *)ctx.params();
+  if (!p->stats_on_path) return; /* the fan-in is done off the event path */
+  const simian_lanl_state_t *st = (const simian_lanl_state_t *)ctx.state();
+  const uint32_t bins = p->time_bins < SIMIAN_LANL_TIME_BINS ? p->time_bins : SIMIAN_LANL_TIME_BINS;
+  const uint32_t num = ctx.self_id() - p->first_id;
+  ctx.req_service_blob_fn(p->min_delay, p->svc_output, 7u + bins, p->first_id + 0u,
+                          [st, num, bins](uint32_t k) -> uint64_t {
+                            if (k == 0) return (uint64_t)num;
+                            if (k == 1) return st->send_count;
+                            if (k == 2) return st->receive_count;
+                            if (k == 3) return simian_f64_bits(st->ops_min);
+                            if (k == 4) return simian_f64_bits(st->ops_mean);
+                            if (k == 5) return simian_f64_bits(st->ops_max);
+                            if (k < 6u + bins) return (uint64_t)st->time_sends[k - 6u];
+                            return st->ops_count;
+                          });
+}
+
+/* OutputHandler (:317-342), the accumulation of the global statistics (:321-330);
+ * the table itself is written by the host from entity 0's state */
+template <class Ctx>
+SIMIAN_HD void simian_lanl_output(Ctx &ctx) {
+  const simian_lanl_params_t *p = (const simian_lanl_params_t *)ctx.params();
+  simian_lanl_state_t *st = (simian_lanl_state_t *)ctx.state();
+  const uint32_t bins = p->time_bins < SIMIAN_LANL_TIME_BINS ? p->time_bins : SIMIAN_LANL_TIME_BINS;
+  if (ctx.payload_words() != 7u + bins) return; /* (not a statistics message) */
+  const uint64_t sends = ctx.payload(1), recvs = ctx.payload(2);
+  const double ops_min = simian_bits_f64(ctx.payload(3)), ops_mean = simian_bits_f64(ctx.payload(4)),
+               ops_max = simian_bits_f64(ctx.payload(5));
+  st->stats_received++;
+  double den = (double)(st->greceive_count + recvs);
+  if (!(den > 1.0)) den = 1.0; /* max(1, .) */
+  st->gops_mean = ((double)recvs * ops_mean + st->gops_mean * (double)st->greceive_count) / den; /* :322 */
+  st->gsend_count += sends;
+  st->greceive_count += recvs;
+  st->gops_count += ctx.payload(6u + bins);
+  if (ops_min < st->gops_min) st->gops_min = ops_min;
+  if (ops_max > st->gops_max) st->gops_max = ops_max;
+  for (uint32_t i = 0; i < bins; i++) st->gtime_sends[i] += (uint32_t)ctx.payload(6u + i);
+}
 
 /* `num` of the entity a handler runs for (class-local index) */
 template <class Ctx>
@@ -329,6 +383,11 @@ SIMIAN_HD void simian_lanl_construct(Ctx &ctx) {
   st->ops_mean = 0.0;
   st->value_sink = 0.0;
   for (uint32_t i = 0; i < SIMIAN_LANL_TIME_BINS; i++) st->time_sends[i] = 0;
+  st->stats_received = st->gsend_count = st->greceive_count = st->gops_count = 0; /* :241-251 */
+  st->gops_max = 0;
+  st->gops_min = 1e100;
+  st->gops_mean = 0.0;
+  for (uint32_t i = 0; i < SIMIAN_LANL_TIME_BINS; i++) st->gtime_sends[i] = 0;
   /* :255 FinishUp at end of time, :256 first SendHandler call */
   ctx.req_service(p->end_time - ctx.now(), p->svc_finish, 0ull, SIMIAN_NULL_ENTITY);
   simian_lanl_send_body(ctx, di);

@@ -114,8 +114,18 @@ LANL_CASES = [
          p_receive=0.08, p_send=0.1, p_list=0.04, invert=True, m_ent=32.0,
          ops_ent=90.0, ops_sigma=0.1, cache_friendliness=0.75, end_time=10.0,
          min_delay=1.0, time_bins=10, seed=17),
+    # the statistics fan-in ON the event path (pdes_lanl_benchmarkV8.js:311-342):
+    # FinishHandler sends its message (a list) to OutputHandler of entity 0 -- n_ent
+    # events at one instant at one entity, each with a payload of 7 + time_bins words
+    dict(name="lanl_stats_on_path", n_ent=44, s_ent=16.0, q_avg=2.0, p_receive=0.04,
+         m_ent=40.0, ops_ent=80.0, ops_sigma=0.2, cache_friendliness=0.5, end_time=9.0,
+         min_delay=0.5, time_bins=9, stats_on_path=True, seed=21),
+    dict(name="lanl_stats_on_path_geometric", n_ent=32, s_ent=20.0, q_avg=1.0,
+         p_receive=0.06, p_send=0.07, p_list=0.05, invert=False, m_ent=36.0,
+         ops_ent=110.0, ops_sigma=0.1, cache_friendliness=0.5, end_time=8.0,
+         min_delay=1.0, time_bins=6, stats_on_path=True, seed=23),
 ]
-LANL_SERVICES = {"SendHandler": 0, "ReceiveHandler": 1, "FinishHandler": 2}
+LANL_SERVICES = {"SendHandler": 0, "ReceiveHandler": 1, "FinishHandler": 2, "OutputHandler": 3}
 
 
 def run_lanl_case(Simian, case):
@@ -127,7 +137,7 @@ def run_lanl_case(Simian, case):
                           case["cache_friendliness"], case["end_time"],
                           case["min_delay"], case["time_bins"],
                           case.get("p_send", 0.0), case.get("p_list", 0.0),
-                          case.get("invert", False))
+                          case.get("invert", False), case.get("stats_on_path", False))
     eng = Simian("pin_" + case["name"], 0.0,
                  max(case["end_time"], 2) + 3 * case["min_delay"],
                  case["min_delay"], False, silent=True)
@@ -179,6 +189,14 @@ def run_lanl_case(Simian, case):
 
         def FinishHandler(self, data, tx, txId):
             self._commit("FinishHandler", data, txId)
+            if P.stats_on_path:                                  # :311-315
+                self.reqService(case["min_delay"], "OutputHandler",
+                                pyspec.lanl_finish_msg(P, self), "PDES_LANL_Node", 0)
+
+        def OutputHandler(self, msg, tx, txId):                  # :317-342
+            # (the header record's data word = the number of payload words)
+            self._commit("OutputHandler", len(msg), txId)
+            pyspec.lanl_output(P, self, msg)
 
     for i in range(n):
         eng.addEntity("PDES_LANL_Node", PDES_LANL_Node, i)
@@ -207,6 +225,13 @@ def run_lanl_case(Simian, case):
             ops_mean=[float(e.ops_mean).hex() for e in ents],
             value_sink=[float(e.value_sink).hex() for e in ents],
             list_head=[[float(x).hex() for x in e.list[:4]] for e in ents]))
+    if P.stats_on_path:  # what entity 0 collected (:321-330)
+        e0 = ents[0]
+        out["global_stats"] = dict(
+            stats_received=e0.stats_received, gsend_count=e0.gsend_count,
+            greceive_count=e0.greceive_count, gops_count=e0.gops_count,
+            gops_max=float(e0.gops_max).hex(), gops_min=float(e0.gops_min).hex(),
+            gops_mean=float(e0.gops_mean).hex(), gtime_sends=list(e0.gtime_sends))
     eng.exit()
     return out
 

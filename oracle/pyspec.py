@@ -154,9 +154,10 @@ def powi(b, n):
 class LanlParams:
     def __init__(self, n_ent, s_ent, q_avg, p_receive, m_ent, ops_ent, ops_sigma,
                  cache_friendliness, end_time, min_delay, time_bins,
-                 p_send=0.0, p_list=0.0, invert=False):
+                 p_send=0.0, p_list=0.0, invert=False, stats_on_path=False):
         import math
         self.p_send, self.p_list, self.invert = p_send, p_list, invert
+        self.stats_on_path = stats_on_path
         self.n_ent, self.s_ent, self.q_avg, self.p_receive = n_ent, s_ent, q_avg, p_receive
         self.m_ent, self.ops_ent, self.ops_sigma = m_ent, ops_ent, ops_sigma
         self.cache_friendliness, self.end_time, self.min_delay = cache_friendliness, end_time, min_delay
@@ -284,6 +285,11 @@ def lanl_construct(p, st, ctx):
     st.ops_mean = 0.0
     st.value_sink = 0.0
     st.time_sends = [0] * LANL_TIME_BINS
+    st.stats_received = st.gsend_count = st.greceive_count = st.gops_count = 0
+    st.gops_max = 0.0
+    st.gops_min = 1e100
+    st.gops_mean = 0.0
+    st.gtime_sends = [0] * LANL_TIME_BINS
     ctx.req_service(p.end_time - ctx.now, "FinishHandler", 0, None)
     lanl_send_body(p, st, ctx, di)
 
@@ -320,3 +326,36 @@ def blob_fold(words):
     for w in words:
         fold = mix64(fold ^ w)
     return fold
+
+
+def lanl_finish_msg(p, st):
+    """simian_lanl_finish: the statistics message as its 64-bit words
+    [num, send_count, receive_count, ops_min, ops_mean, ops_max, time_sends.., opsCount]"""
+    bins = min(p.time_bins, LANL_TIME_BINS)
+    return ([st.num, st.send_count, st.receive_count, f64_bits(st.ops_min),
+             f64_bits(st.ops_mean), f64_bits(st.ops_max)] +
+            [int(x) for x in st.time_sends[:bins]] + [st.ops_count])
+
+
+def lanl_output(p, st, words):
+    """simian_lanl_output: the accumulation of OutputHandler
+    (pdes_lanl_benchmarkV8.js:321-330) on entity 0"""
+    bins = min(p.time_bins, LANL_TIME_BINS)
+    if len(words) != 7 + bins:
+        return
+    sends, recvs = words[1], words[2]
+    ops_min, ops_mean, ops_max = bits_f64(words[3]), bits_f64(words[4]), bits_f64(words[5])
+    st.stats_received += 1
+    den = float(st.greceive_count + recvs)
+    if not (den > 1.0):
+        den = 1.0
+    st.gops_mean = (float(recvs) * ops_mean + st.gops_mean * float(st.greceive_count)) / den
+    st.gsend_count += sends
+    st.greceive_count += recvs
+    st.gops_count += words[6 + bins]
+    if ops_min < st.gops_min:
+        st.gops_min = ops_min
+    if ops_max > st.gops_max:
+        st.gops_max = ops_max
+    for i in range(bins):
+        st.gtime_sends[i] += words[6 + i]

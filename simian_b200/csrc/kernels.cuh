@@ -775,7 +775,7 @@ __global__ void k_pull(const __grid_constant__ DevCfg c, uint32_t win_ix, uint32
 // burst that overflows the slots, or a redistribution pass)
 #define STAGE_REST 0xFFFFFFFFu
 #define EV_PER_THREAD ((NREFS + NTHREADS - 1) / NTHREADS)
-static_assert(EV_PER_THREAD <= 4, "ranks are packed 8 bits each into one register");
+static_assert(EV_PER_THREAD <= 8, "ranks are packed 8 bits each into one 64-bit register");
 #define RSTACK_MAX 80 // entity sub-ranges a CTA can have pending
 #define NBINS 16      // histogram bins over the block's entities (burst partition)
 
@@ -1199,7 +1199,7 @@ __device__ __forceinline__ bool key_lt(unsigned long long a1, unsigned long long
 // The per-entity path runs one thread per entity; a handler's long sum would make
 // one lane work while 31 wait.  simian_defer_weighted_sum parks the sum as a JOB on
 // the consumed event's shared-memory slot -- xs[slot] = na | nj << 20 | di0 << 40 |
-// commit delta << 46 | sink offset << 56, the record's data word = the list
+// commit delta << 45 | sink offset << 56, the record's data word = the list
 // pointer -- and after the entities' events of the pass a WARP computes each job in
 // the order simian_lanl_weighted_sum defines and adds it to the sink, an entity's
 // jobs in commit order.  (Every event of an entity in a pass has a commit delta
@@ -1207,10 +1207,10 @@ __device__ __forceinline__ bool key_lt(unsigned long long a1, unsigned long long
 // line: the additions into the sink keep their commit order.)
 #define JOB_NA(x) ((uint32_t)(x) & 0xFFFFFu)
 #define JOB_NJ(x) ((uint32_t)((x) >> 20) & 0xFFFFFu)
-#define JOB_DI0(x) ((uint32_t)((x) >> 40) & 0x3Fu)
-#define JOB_DELTA(x) ((uint32_t)((x) >> 46) & 0x3FFu)
+#define JOB_DI0(x) ((uint32_t)((x) >> 40) & 0x1Fu)
+#define JOB_DELTA(x) ((uint32_t)((x) >> 45) & 0x7FFu)
 #define JOB_SINK_OFF(x) ((int)(signed char)((x) >> 56))
-static_assert(NREFS <= 1024, "commit delta of a parked job: 10 bits");
+static_assert(NREFS <= 2048, "commit delta of a parked job: 11 bits");
 
 __device__ __forceinline__ bool simian_defer_weighted_sum(DevCtx<true> &ctx, const double *list,
                                                           uint32_t na, uint32_t nj, uint32_t di0,
@@ -1218,13 +1218,13 @@ __device__ __forceinline__ bool simian_defer_weighted_sum(DevCtx<true> &ctx, con
   if (!ctx.job_sh || ctx.job_slot == SIMIAN_NONE) return false;
   const unsigned long long delta = ctx.commit_idx - ctx.job_count0;
   const long long off = sink - list; // in doubles
-  if (na == 0 || na >= (1u << 20) || nj >= (1u << 20) || di0 >= 64u || delta >= 1024ull ||
+  if (na == 0 || na >= (1u << 20) || nj >= (1u << 20) || di0 >= 32u || delta >= 2048ull ||
       off < -128 || off > 127 || (unsigned long long)na * nj >= (1ull << 32))
     return false;
   WindowShared &sh = *ctx.job_sh;
   SLOT_HI(sh, ctx.job_slot).y = (unsigned long long)list; // (the event's data has been read)
   sh.xs[ctx.job_slot] = (unsigned long long)na | ((unsigned long long)nj << 20) |
-                        ((unsigned long long)di0 << 40) | (delta << 46) |
+                        ((unsigned long long)di0 << 40) | (delta << 45) |
                         ((unsigned long long)(unsigned char)(signed char)off << 56);
   if (ctx.c.jobs) atomicAdd(&sh.pass_jobs, 1u);
   return true;
@@ -2174,14 +2174,14 @@ __device__ __forceinline__ void process_pass(const DevCfg &c, WindowShared &sh, 
   const WinState &W = sh.W;
   if (c.all_pure) {
     // A1, one thread per EVENT: rank (kept in a register), tie check, trace word
-    uint32_t rkpack = 0; // EV_PER_THREAD ranks, 8 bits each
+    unsigned long long rkpack = 0; // EV_PER_THREAD ranks, 8 bits each
 #pragma unroll 1
     for (int u = 0; u < EV_PER_THREAD; u++) {
       uint32_t i = tid + u * NTHREADS;
       if (live & (1u << u)) {
         uint32_t r = rank_event(c, sh, ta, slot0, i);
         if (r > 255u) set_error(c, SIMIAN_ERR_ENTITY_BURST);
-        rkpack |= (r & 255u) << (8 * u);
+        rkpack |= (unsigned long long)(r & 255u) << (8 * u);
       }
     }
     cp_async_wait_all(); // the entities' {count, hash} (link_due)
@@ -2201,7 +2201,7 @@ __device__ __forceinline__ void process_pass(const DevCfg &c, WindowShared &sh, 
         if (lv) {
           RecBits r = slot_get(sh, tid + u * NTHREADS);
           const unsigned long long ci =
-              SH_CORE(sh)[r.dst() - slot0].count + ((rkpack >> (8 * u)) & 255u);
+              SH_CORE(sh)[r.dst() - slot0].count + (uint32_t)((rkpack >> (8 * u)) & 255ull);
           if (ci >> 48) set_error(c, SIMIAN_ERR_ENTITY_BURST); // (2.8e14 commits of one entity)
           r.q2 = (r.q2 & 0xFFFFull) | (ci << 16);
           st_rec(out + p0 + __popc(m & ((1u << lane) - 1u)), r);
@@ -2219,7 +2219,7 @@ __device__ __forceinline__ void process_pass(const DevCfg &c, WindowShared &sh, 
 #pragma unroll 1
     for (int u = 0; u < EV_PER_THREAD; u++) {
       uint32_t i = tid + u * NTHREADS;
-      if (live & (1u << u)) run_event<WIDE>(c, sh, ta, slot0, i, (rkpack >> (8 * u)) & 255u);
+      if (live & (1u << u)) run_event<WIDE>(c, sh, ta, slot0, i, (uint32_t)((rkpack >> (8 * u)) & 255ull));
     }
     PHASE(4); // (no barrier: phase B reads only the slots its own thread staged)
     // B (K4) with C (trace chain) folded while the claims are in flight
@@ -2289,7 +2289,7 @@ __device__ __forceinline__ void process_pass(const DevCfg &c, WindowShared &sh, 
 #pragma unroll 1
       for (;;) {
         // the next job of this entity (warp-uniform walk of its short list)
-        uint32_t bj = LIST_END, bd = 1024u;
+        uint32_t bj = LIST_END, bd = 2048u;
         for (uint32_t j = first; j != LIST_END; j = sh.nxt[j]) {
           const unsigned long long x = sh.xs[j];
           if (x) {
@@ -2308,7 +2308,7 @@ __device__ __forceinline__ void process_pass(const DevCfg &c, WindowShared &sh, 
           if ((tid & 31) == 0)
             st_rec_2x16(c.jobs + ((size_t)run_base + emitted_jobs),
                         (unsigned long long)list, key,
-                        x & ~(0x3FFull << 46), // (na, nj, di0, sink offset; the commit delta is spent)
+                        x & ~(0x7FFull << 45), // (na, nj, di0, sink offset; the commit delta is spent)
                         emitted_jobs == 0 ? (unsigned long long)run_len : 0ull);
           emitted_jobs++;
           continue;

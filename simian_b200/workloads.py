@@ -76,15 +76,20 @@ import numpy as np  # noqa: E402
 
 LANL_CLASS = "PDES_LANL_Node"
 LANL_TIME_BINS = 16  # SIMIAN_LANL_TIME_BINS
-# simian_lanl_state_t (include/simian_models.h), 168 bytes; the list follows it
+# simian_lanl_state_t (include/simian_models.h), 288 bytes; the list follows it
 LANL_STATE_DTYPE = np.dtype([
     ("local_intersend_delay", "<f8"), ("q_target", "<f8"),
     ("last_scheduled", "<f8"), ("ops", "<f8"), ("ops_max", "<f8"),
     ("ops_min", "<f8"), ("ops_mean", "<f8"), ("value_sink", "<f8"),
     ("q_size", "<i8"), ("send_count", "<u8"), ("receive_count", "<u8"),
     ("ops_count", "<u8"), ("list_size", "<u4"), ("active_elements", "<u4"),
-    ("time_sends", "<u4", (LANL_TIME_BINS,))])
-assert LANL_STATE_DTYPE.itemsize == 168
+    ("time_sends", "<u4", (LANL_TIME_BINS,)),
+    # the global statistics entity 0 collects when the fan-in runs on the event path
+    ("stats_received", "<u8"), ("gsend_count", "<u8"), ("greceive_count", "<u8"),
+    ("gops_count", "<u8"), ("gops_max", "<f8"), ("gops_min", "<f8"), ("gops_mean", "<f8"),
+    ("gtime_sends", "<u4", (LANL_TIME_BINS,))])
+LANL_STATE_BYTES = LANL_STATE_DTYPE.itemsize
+assert LANL_STATE_BYTES == 288
 
 
 def lanl_list_size(n_ent, m_ent, p_list=0.0):
@@ -108,13 +113,15 @@ def lanl_engine_end(end_time, min_delay):
 def lanl_params_blob(first_id, n_ent, s_ent, q_avg, p_receive, m_ent, ops_ent,
                      ops_sigma, cache_friendliness, end_time, min_delay,
                      time_bins, svc_send, svc_receive, svc_finish,
-                     p_send=0.0, p_list=0.0, invert=False):
+                     p_send=0.0, p_list=0.0, invert=False, svc_output=0,
+                     stats_on_path=False):
     """Pack simian_lanl_params_t (include/simian_models.h), 120 bytes."""
     r_min = math.pow(1.0 - p_receive, n_ent)  # :196
-    blob = struct.pack("<II12dIHHHHI", first_id, n_ent, s_ent, q_avg, p_receive,
+    blob = struct.pack("<II12dIHHHHHH", first_id, n_ent, s_ent, q_avg, p_receive,
                        m_ent, ops_ent, ops_sigma, cache_friendliness, end_time,
                        min_delay, r_min, p_send, p_list, time_bins, svc_send,
-                       svc_receive, svc_finish, 0, 1 if invert else 0)
+                       svc_receive, svc_finish, svc_output, 1 if invert else 0,
+                       1 if stats_on_path else 0)
     assert len(blob) == 120
     return blob
 
@@ -122,29 +129,40 @@ def lanl_params_blob(first_id, n_ent, s_ent, q_avg, p_receive, m_ent, ops_ent,
 def build_lanl(eng, n_ent, s_ent=100.0, q_avg=1.0, p_receive=0.0, m_ent=1000.0,
                ops_ent=1000.0, ops_sigma=0.1, cache_friendliness=0.5,
                end_time=100.0, min_delay=1.0, time_bins=10, p_send=0.0,
-               p_list=0.0, invert=False):
+               p_list=0.0, invert=False, stats_on_path=False):
     """The "MAIN" of pdes_lanl_benchmarkV8.js:346-356: one addEntity loop whose
     constructors schedule FinishHandler and run the first SendHandler.  The
     engine must have been created with end = lanl_engine_end(end_time,
     min_delay).  p_send / invert / p_list: the geometric source and list-size
-    distributions (:209-221); every entity's state has room for the largest list."""
+    distributions (:209-221); every entity's state has room for the largest list.
+    stats_on_path: FinishHandler sends the statistics message to OutputHandler of
+    entity 0 as an event with a payload (:311-342; the engine needs option
+    payloads = 1; models of a few dozen entities: all messages are due at entity 0
+    in one window)."""
     assert time_bins <= LANL_TIME_BINS
     eng.define_class(LANL_CLASS, lanl_state_bytes(n_ent, m_ent, p_list))
     eng.add_entities(LANL_CLASS, 0, n_ent)
     eng.attach_service(LANL_CLASS, "SendHandler", "lanl_send")
     eng.attach_service(LANL_CLASS, "ReceiveHandler", "lanl_receive")
     eng.attach_service(LANL_CLASS, "FinishHandler", "lanl_finish")
+    svc_output = 0
+    if stats_on_path:
+        eng.attach_service(LANL_CLASS, "OutputHandler", "lanl_output")
+        svc_output = eng.intern_service("OutputHandler")
     ids = [eng.intern_service(s) for s in
            ("SendHandler", "ReceiveHandler", "FinishHandler")]
     eng.set_class_params(LANL_CLASS, lanl_params_blob(
         eng.first_id(LANL_CLASS), n_ent, s_ent, q_avg, p_receive, m_ent,
         ops_ent, ops_sigma, cache_friendliness, end_time, min_delay, time_bins,
-        *ids, p_send=p_send, p_list=p_list, invert=invert))
+        *ids, p_send=p_send, p_list=p_list, invert=invert, svc_output=svc_output,
+        stats_on_path=stats_on_path))
     # each constructor sends FinishHandler + up to ceil(q_target) timers + 1 request;
     # with a geometric source distribution the busiest entity's q_target is
     # q_avg * n_ent * p_send (the sum over the entities stays about q_avg * n_ent)
     per = 3 + int(math.ceil(q_avg))
     extra = int(math.ceil(q_avg * n_ent * p_send)) if p_send else 0
+    if stats_on_path:  # the messages of the fan-in: header + 7 + time_bins payload words each
+        extra += n_ent * (8 + time_bins)
     eng.construct_entities(LANL_CLASS, "lanl_construct", n_ent * per + extra)
     return eng
 
@@ -153,8 +171,8 @@ def lanl_states(raw, n_ent, m_ent, p_list=0.0):
     """split simian_read_state bytes into (struct array, lists[n, max list_size])"""
     sb = lanl_state_bytes(n_ent, m_ent, p_list)
     a = np.frombuffer(bytes(raw), dtype=np.uint8).reshape(n_ent, sb)
-    st = a[:, :168].copy().view(LANL_STATE_DTYPE).reshape(n_ent)
-    lists = a[:, 168:].copy().view("<f8").reshape(n_ent, -1)
+    st = a[:, :LANL_STATE_BYTES].copy().view(LANL_STATE_DTYPE).reshape(n_ent)
+    lists = a[:, LANL_STATE_BYTES:].copy().view("<f8").reshape(n_ent, -1)
     return st, lists
 
 
@@ -186,6 +204,14 @@ def lanl_report(state, time_bins, out):
         out.write("%10d %10d %10d %10d %10.5g %10d    %s\n" % (
             i, sends, recvs, _js_int(r["ops_min"]), float(r["ops_mean"]), _js_int(r["ops_max"]),
             "[" + ",".join(map(str, bins)) + "]"))
+    if n and int(state[0]["stats_received"]) == n:
+        # the fan-in ran ON the event path (stats_on_path): the totals are the ones
+        # OutputHandler of entity 0 accumulated (pdes_lanl_benchmarkV8.js:321-330)
+        e0 = state[0]
+        g_send, g_recv, g_ops = (int(e0["gsend_count"]), int(e0["greceive_count"]),
+                                 int(e0["gops_count"]))
+        g_mean, g_min, g_max = float(e0["gops_mean"]), float(e0["gops_min"]), float(e0["gops_max"])
+        g_bins = np.array([int(x) for x in e0["gtime_sends"][:time_bins]], dtype=np.int64)
     out.write("===================== LANL PDES BENCHMARK  Collected Stats from All Ranks "
               "=======================\n")
     out.write("%10s %10s %10s %10s %10s %10s %10s    '%s'\n" % (

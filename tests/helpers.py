@@ -55,7 +55,7 @@ LANL_KEYS = ("n_ent", "s_ent", "q_avg", "p_receive", "m_ent", "ops_ent",
              "time_bins")
 
 
-LANL_OPT_KEYS = ("p_send", "p_list", "invert")
+LANL_OPT_KEYS = ("p_send", "p_list", "invert", "stats_on_path")
 
 
 def build_lanl_case(eng, case):
@@ -92,6 +92,8 @@ def run_oracle_lanl(oracle_mod, case, size=1, tie_mode=1):
 def run_engine_lanl(case, **options):
     from simian_b200 import capi
     from simian_b200.workloads import lanl_engine_end
+    if case.get("stats_on_path"):
+        options = dict(options, payloads=1)   # the statistics messages carry payloads
     e = capi.Engine(case.get("name", "lanl"), 0.0,
                     lanl_engine_end(case["end_time"], case["min_delay"]),
                     case["min_delay"], seed=case.get("seed", 1), **options)
@@ -117,6 +119,15 @@ def assert_lanl_golden(case, st, counts, hashes, state, lists):
         assert [float(x).hex() for x in state[k]] == g[k], k
     assert [[int(x) for x in row] for row in state["time_sends"]] == g["time_sends"]
     assert [[float(x).hex() for x in row[:4]] for row in lists] == g["list_head"]
+    if "global_stats" in case:  # the fan-in on the event path: what entity 0 collected
+        gs, e0 = case["global_stats"], state[0]
+        assert int(e0["stats_received"]) == gs["stats_received"] == case["n_ent"]
+        for k in ("gsend_count", "greceive_count", "gops_count"):
+            assert int(e0[k]) == gs[k], k
+        for k in ("gops_max", "gops_min", "gops_mean"):
+            assert float(e0[k]).hex() == gs[k], k
+        assert [int(x) for x in e0["gtime_sends"]] == gs["gtime_sends"]
+        assert int(e0["gsend_count"]) == int(state["send_count"].sum())
 
 
 # ---- hello.js (two classes) ----------------------------------------------------
