@@ -32,7 +32,7 @@ o = om.Oracle("bounce", 0.0, END, MIN_DELAY, seed=5, tie_mode=1)
 build(o)
 so = o.run()
 co, ho = o.read_counts("Ring", N), o.read_trace_hashes("Ring", N)
-e = capi.Engine("bounce", 0.0, END, MIN_DELAY, seed=5)
+e = capi.Engine("bounce", 0.0, END, MIN_DELAY, seed=5, payloads=1)  # (the ticks carry payloads)
 build(e)
 se = e.run()
 ce, he = e.read_counts("Ring", N), e.read_trace_hashes("Ring", N)
