@@ -190,6 +190,5 @@ struct DevCfg {
   // own, higher occupancy.  null: the window kernel computes them itself.
   simian_event_t *jobs; // [job_cap]: ONE array for all blocks (k_sums balances over it);
                         // a CTA reserves the range of a pass with one atomic on acc->job_total
-  uint32_t *job_n;      // (unused)
   uint32_t job_cap, pad4_;
 };

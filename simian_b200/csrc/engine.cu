@@ -509,7 +509,6 @@ int setup_layout(simian_engine *e) {
     CK(cudaMemsetAsync(c.stage_n, 0, sizeof(uint32_t) * (size_t)c.n_blocks, e->stream));
   }
   c.jobs = nullptr;
-  c.job_n = nullptr;
   c.job_cap = 0;
   if (!c.all_pure && !e->loop &&
       (e->split_sums < 0 ? SIMIAN_SPLIT_SUMS_DEFAULT != 0 : e->split_sums != 0)) {

@@ -2154,11 +2154,6 @@ __device__ __forceinline__ void append_staged(const DevCfg &c, SH &sh, AppendCtx
   }
 }
 
-// the entity block a first slot belongs to
-__device__ __forceinline__ uint32_t blockIdx_of_block(const DevCfg &c, uint32_t slot0) {
-  return (uint32_t)__umul64hi((unsigned long long)slot0, c.epb_inv);
-}
-
 // K3 + K4 + trace chain for the m due events one pass collected into the
 // shared-memory slots (entities [e_lo, e_hi) of the block).  CTA-uniform.
 // `live`: bit u = slot (threadIdx.x + u * NTHREADS) holds a due event of this thread.
