@@ -110,6 +110,11 @@ const char *simian_last_error(simian_engine *e);
  *                     (req_service_blob / payload(k) of the handler context; the words
  *                     travel as continuation records, include/simian_spec.h).  Default 0:
  *                     the window kernel then never looks at a record's flags
+ *   "l2_persist"      2 (default): the hot metadata of the calendar -- cell head words, entity
+ *                     core states, block page stacks -- is one allocation kept resident in
+ *                     L2 by a persisting access-policy window on the engine's stream
+ *                     (removed when the engine lets go of the stream); 1: the head words
+ *                     only; 0: off.  Config 2: 15.76 -> 15.08 ms per step
  *   "split_sums"      models with stateful handlers: the sums a handler defers
  *                     (simian_defer_weighted_sum, the LANL receive handler) are computed by
  *                     k_sums behind the window kernel -- one global job array, a persistent

@@ -193,6 +193,10 @@ struct simian_engine {
   int split_sums = -1;
   uint64_t job_cap = 0; // option "sum_jobs": descriptors per window (0: four per entity)
   uint32_t sums_ctas = 888; // grid of k_sums: the CTAs resident at once
+  void *hot_base = nullptr; // the hot-metadata slab (setup_layout) and its size
+  size_t hot_bytes = 0;
+  bool l2_applied = false;
+  int l2_persist = 2; // option "l2_persist": persisting L2 window over the cell head words
   int payloads = 0; // option "payloads": handlers may send / read payload words (continuation records)
   bool split_on = false; // in force for this layout
   uint32_t rest_ctas = 444; // grid of k_window_rest: the CTAs resident at once
@@ -343,6 +347,8 @@ void teardown_layout(simian_engine *e) {
     h.d_params = nullptr;
   }
   e->d_digest = nullptr;
+  e->hot_base = nullptr;
+  e->hot_bytes = 0;
   e->laid_out = false;
 }
 
@@ -469,17 +475,32 @@ int setup_layout(simian_engine *e) {
   if (n_pages > 0xFFFFFFFFull / PAGE) n_pages = 0xFFFFFFFFull / PAGE;
   c.n_pages = (uint32_t)n_pages;
   size_t n_cells = (size_t)(ring + 2) * c.n_blocks;
-  if (dev_alloc(e, &c.core, c.n_slots)) return e->err_code;
-  if (dev_alloc(e, &c.cell_state, n_cells)) return e->err_code;
+  // the hot metadata -- cell head words (the target of every append's claim), entity
+  // core states, block page stacks -- in ONE allocation, so that one persisting L2
+  // access window covers it (option "l2_persist")
+  {
+    auto up = [](size_t b) { return (b + 511) & ~(size_t)511; };
+    const size_t b_cells = up(n_cells * sizeof(unsigned long long));
+    const size_t b_core = up((size_t)c.n_slots * sizeof(EntityCore));
+    const size_t b_bc = up((size_t)c.n_blocks * SIMIAN_BC * sizeof(uint32_t));
+    const size_t b_cnt = up((size_t)c.n_blocks * sizeof(uint32_t));
+    const size_t b_snap = up((size_t)c.n_blocks * sizeof(unsigned long long));
+    uint8_t *slab = nullptr;
+    e->hot_bytes = b_cells + b_core + b_bc + b_cnt + b_snap;
+    if (dev_alloc(e, &slab, e->hot_bytes)) return e->err_code;
+    e->hot_base = slab;
+    c.cell_state = (unsigned long long *)slab;
+    c.core = (EntityCore *)(slab + b_cells);
+    c.bcache = (uint32_t *)(slab + b_cells + b_core);
+    c.bcount = (uint32_t *)(slab + b_cells + b_core + b_bc);
+    c.snap = (unsigned long long *)(slab + b_cells + b_core + b_bc + b_cnt);
+  }
   if (dev_alloc(e, &c.pool, (size_t)c.n_pages * PAGE)) return e->err_code;
   if (dev_alloc(e, &c.page_next, c.n_pages)) return e->err_code;
   if (dev_alloc(e, &c.free_ring, c.n_pages)) return e->err_code;
-  if (dev_alloc(e, &c.snap, c.n_blocks)) return e->err_code;
   if (dev_alloc(e, &c.win, 2)) return e->err_code;
   if (dev_alloc(e, &c.acc, 1)) return e->err_code;
   if (dev_alloc(e, &c.part, SIMIAN_PART_SLOTS)) return e->err_code;
-  if (dev_alloc(e, &c.bcache, (size_t)c.n_blocks * SIMIAN_BC)) return e->err_code;
-  if (dev_alloc(e, &c.bcount, c.n_blocks)) return e->err_code;
   if (dev_alloc(e, &e->d_digest, 2)) return e->err_code;
   // split window: only models of pure handlers, not beside the deferred pull (its
   // pull CTAs ride in k_window) or the persistent loop
@@ -579,6 +600,47 @@ int ingest_records(simian_engine *e, const simian_event_t *d, uint64_t n, cudaSt
   return 0;
 }
 
+// option "l2_persist" (default 2): keep the hot metadata of the calendar resident in L2 --
+// a persisting access-policy window on the engine's stream.  2: the whole hot slab (cell
+// head words = the target of every append's claim, entity core states, block page
+// stacks, row snapshot; 34 MB for config 2); 1: the head words only; 0: off.  Measured on
+// config 2: 15.76 -> 15.32 (1) -> 15.08 ms (2) per step.  Best effort: a failure here is
+// not a failure of the run.  The window is removed from the stream when the engine lets
+// go of it (the stream may be the caller's).
+void clear_l2_policy(simian_engine *e) {
+  if (!e->l2_applied || !e->stream) return;
+  cudaStreamAttrValue av = {};
+  av.accessPolicyWindow.num_bytes = 0; // (disables the window)
+  cudaStreamSetAttribute(e->stream, cudaStreamAttributeAccessPolicyWindow, &av);
+  cudaCtxResetPersistingL2Cache();
+  cudaGetLastError();
+  e->l2_applied = false;
+}
+
+void apply_l2_policy(simian_engine *e) {
+  if (e->l2_persist <= 0 || !e->hot_base || !e->stream) return;
+  const DevCfg &c = e->cfg;
+  int max_win = 0, l2 = 0;
+  cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, e->device);
+  cudaDeviceGetAttribute(&l2, cudaDevAttrMaxPersistingL2CacheSize, e->device);
+  const size_t heads = (size_t)(c.ring + 2) * c.n_blocks * sizeof(unsigned long long);
+  // the whole slab when it fits the persisting part of the L2, else the head words
+  size_t bytes = (e->l2_persist > 1 && e->hot_bytes <= (size_t)l2) ? e->hot_bytes : heads;
+  if (max_win <= 0 || l2 <= 0) return;
+  if (bytes > (size_t)max_win) bytes = (size_t)max_win;
+  const size_t set_aside = bytes < (size_t)l2 ? bytes : (size_t)l2;
+  cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, set_aside);
+  cudaStreamAttrValue av = {};
+  av.accessPolicyWindow.base_ptr = e->hot_base; // (the cell head words come first)
+  av.accessPolicyWindow.num_bytes = bytes;
+  av.accessPolicyWindow.hitRatio = set_aside >= bytes ? 1.0f : (float)set_aside / (float)bytes;
+  av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+  av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+  if (cudaStreamSetAttribute(e->stream, cudaStreamAttributeAccessPolicyWindow, &av) == cudaSuccess)
+    e->l2_applied = true;
+  cudaGetLastError();
+}
+
 // allocate the HBM layout, initialise it, replay schedService, set up window 0
 int setup(simian_engine *e) {
   if (e->set_up) return 0;
@@ -616,6 +678,7 @@ int setup(simian_engine *e) {
   e->win_ix = 0;
   e->launches = 0;
   e->set_up = true;
+  apply_l2_policy(e);
   return 0;
 }
 
@@ -732,6 +795,7 @@ void simian_destroy(simian_engine *e) {
   if (!e) return;
   cudaSetDevice(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
+  clear_l2_policy(e);
   // peer mappings stay open in the process-wide cache (simian_trim_cache closes them)
   for (auto &a : e->allocs)
     if (!cache_give(e->device, a.second, a.first)) cudaFree(a.first);
@@ -769,6 +833,7 @@ int simian_set_option(simian_engine *e, const char *key, double v) {
   else if (k == "deferred_pull") e->deferred_pull = v != 0;
   else if (k == "split_handlers") e->split = v != 0;
   else if (k == "payloads") e->payloads = v != 0;
+  else if (k == "l2_persist") e->l2_persist = (int)v; // 1: cell head words, 2: the whole hot slab
   else if (k == "pdl_exchange") e->pdl_exchange = v != 0;
   else if (k == "split_sums") e->split_sums = v != 0;
   else if (k == "sum_jobs") e->job_cap = v < 1 ? 1 : (uint64_t)v;
@@ -782,10 +847,12 @@ int simian_set_stream(simian_engine *e, void *s) {
   if (e->stream) {
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
+    clear_l2_policy(e);
   }
   if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
   e->stream = (cudaStream_t)s;
   e->own_stream = false;
+  if (e->set_up) apply_l2_policy(e);
   return 0;
 }
 
