@@ -110,6 +110,10 @@ const char *simian_last_error(simian_engine *e);
  *                     (req_service_blob / payload(k) of the handler context; the words
  *                     travel as continuation records, include/simian_spec.h).  Default 0:
  *                     the window kernel then never looks at a record's flags
+ *   "fused_advance"   size == 1: 1 = the last CTA of the window kernel computes the next window,
+ *                     0 = a one-CTA launch of its own does (k_lbts): the window kernel's CTAs
+ *                     then end without fence + ticket + barrier.  Default: by the number of
+ *                     entity blocks (own launch from 592 on: config 2 15.07 -> 14.77 ms)
  *   "l2_persist"      2 (default): the hot metadata of the calendar -- cell head words, entity
  *                     core states, block page stacks -- is one allocation kept resident in
  *                     L2 by a persisting access-policy window on the engine's stream

@@ -195,6 +195,7 @@ struct simian_engine {
   uint32_t sums_ctas = 888; // grid of k_sums: the CTAs resident at once
   void *hot_base = nullptr; // the hot-metadata slab (setup_layout) and its size
   size_t hot_bytes = 0;
+  int fused_advance = -1; // option "fused_advance": the last CTA of k_window does the LBTS step (-1: by size)
   bool l2_applied = false;
   int l2_persist = 2; // option "l2_persist": persisting L2 window over the cell head words
   int payloads = 0; // option "payloads": handlers may send / read payload words (continuation records)
@@ -843,6 +844,7 @@ int simian_set_option(simian_engine *e, const char *key, double v) {
   else if (k == "deferred_pull") e->deferred_pull = v != 0;
   else if (k == "split_handlers") e->split = v != 0;
   else if (k == "payloads") e->payloads = v != 0;
+  else if (k == "fused_advance") e->fused_advance = v != 0;
   else if (k == "l2_persist") e->l2_persist = (int)v; // 1: cell head words, 2: the whole hot slab
   else if (k == "pdl_exchange") e->pdl_exchange = v != 0;
   else if (k == "split_sums") e->split_sums = v != 0;
@@ -1278,11 +1280,24 @@ static int launch_window(simian_engine *e, int fuse, uint32_t pull_blocks, bool 
   }
   lc.gridDim = dim3(e->cfg.n_blocks + pull_blocks);
   lc.dynamicSmemBytes = e->smem_bytes;
+  // size == 1: the LBTS step by the last CTA of k_window (fence + ticket + barrier in every
+  // CTA) or as a one-CTA launch of its own (k_lbts).  Measured: config 2 (2048 CTAs per
+  // window) 15.07 -> 14.77 ms, config 5 (4096) 40.1 -> 38.9 ms with the launch of its own;
+  // config 1 (2 CTAs) 2.13 -> 2.30 s.  Default: its own launch from 592 entity blocks on.
+  const bool own_lbts = fuse == 1 && (e->fused_advance < 0 ? e->cfg.n_blocks >= 592u
+                                                           : e->fused_advance == 0);
+  const int fuse_k = own_lbts ? 0 : fuse;
   if (e->cfg.blobs) // (its own instantiation: the ordinary kernel never looks at record flags)
-    CK(cudaLaunchKernelEx(&lc, k_window_blobs, e->cfg, e->win_ix, fuse, pull_blocks));
+    CK(cudaLaunchKernelEx(&lc, k_window_blobs, e->cfg, e->win_ix, fuse_k, pull_blocks));
   else
-    CK(cudaLaunchKernelEx(&lc, k_window, e->cfg, e->win_ix, fuse, pull_blocks));
+    CK(cudaLaunchKernelEx(&lc, k_window, e->cfg, e->win_ix, fuse_k, pull_blocks));
   e->launches++;
+  if (own_lbts) { // the LBTS step as a launch of its own
+    lc.gridDim = dim3(1);
+    lc.dynamicSmemBytes = 0;
+    CK(cudaLaunchKernelEx(&lc, k_lbts, e->cfg, e->win_ix));
+    e->launches++;
+  }
   if (e->cfg.jobs) { // the sums the window's handlers deferred
     lc.gridDim = dim3(e->sums_ctas);
     lc.dynamicSmemBytes = 0;

@@ -3106,6 +3106,42 @@ __global__ void __launch_bounds__(NTHREADS, SIMIAN_MINBLOCKS)
 }
 #endif
 
+// size == 1, option "fused_advance" = 0: the LBTS step of window win_ix (what the last CTA
+// of k_window does otherwise: simian.js:143-147) as a launch of its own, one CTA.  The
+// CTAs of k_window then end without the fence + ticket + barrier of the last-CTA
+// pattern -- a fixed cost per CTA that counts when a window is many waves of short CTAs.
+struct __align__(16) LbtsShared {
+  WinState W;
+  unsigned long long min_key;
+  long long scan_j, t_last;
+};
+__global__ void __launch_bounds__(NTHREADS) k_lbts(const __grid_constant__ DevCfg c, uint32_t win_ix) {
+  __shared__ LbtsShared sh;
+  cudaTriggerProgrammaticLaunchCompletion();
+  cudaGridDependencySynchronize();
+  const WinState *Wg = &c.win[win_ix & 1u];
+  if (Wg->done) return;
+  if (ld_cg(&c.acc->error)) return; // sticky error: the window does not advance
+  if (threadIdx.x < (int)(sizeof(WinState) / 8))
+    reinterpret_cast<unsigned long long *>(&sh.W)[threadIdx.x] =
+        reinterpret_cast<const unsigned long long *>(Wg)[threadIdx.x];
+  if (threadIdx.x == 0) sh.t_last = clock64();
+  __syncthreads();
+  const WinState &W = sh.W;
+  reduce_parts(c, sh);
+  WinState *Wn = &c.win[(win_ix + 1u) & 1u];
+  if (W.redist) {
+    setup_next_window(c, W, Wn, W.gmin, 0.0, true);
+  } else {
+    unsigned long long cand, far;
+    local_min_candidate(c, W, sh, cand, far);
+    double gmin = cand == SIMIAN_KEY_NONE ? c.inf_time : simian_key_time(cand); // simian.js:147
+    double farT = far == SIMIAN_KEY_NONE ? __longlong_as_double(0x7FF0000000000000LL)
+                                         : simian_key_time(far);
+    setup_next_window(c, W, Wn, gmin, farT, false);
+  }
+}
+
 __global__ void __launch_bounds__(NTHREADS) k_local_min(const __grid_constant__ DevCfg c, uint32_t win_ix,
                                                         int publish) {
   extern __shared__ __align__(128) unsigned char smem_raw[];

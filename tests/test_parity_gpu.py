@@ -475,3 +475,14 @@ def test_payloads_need_the_option(oracle_mod):
         run_blobs(e, case)
     assert ei.value.code == 16
     e.close()
+
+
+@pytest.mark.parametrize("case,opts", SPLIT_CASES, ids=lambda c: c.get("name", "") if "n" in c else None)
+def test_lbts_step_as_its_own_launch_matches_oracle(case, opts, oracle_mod):
+    """option fused_advance = 0 (the default from 592 entity blocks on): the window
+    kernel's CTAs end without the last-CTA pattern and a one-CTA launch (k_lbts) computes
+    the next window -- bursts, far list and redistribution passes included"""
+    so, co, ho = run_oracle_phold(oracle_mod, case)
+    se, ce, he = run_engine_phold(case, fused_advance=0, persistent_loop=0, **opts)
+    assert_parity(so, co, ho, se, ce, he)
+    assert se["kernel_launches"] >= 2 * se["windows"]
