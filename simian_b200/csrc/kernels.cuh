@@ -2561,8 +2561,27 @@ __device__ __forceinline__ void window_cta_body(const DevCfg &c, WindowShared &s
     }
     PHASE(6);
   }
+  // ---- K1: CTA reduction of the accumulators into this CTA's BlockPart: the warps add
+  // their sums BEFORE the barrier the recycle phase needs anyway, one thread per field
+  // sends them off behind it (independent, result-less atomics) -- no barrier of its own
+  accumulate_block(sh, ta);
   __syncthreads();
   if (SPLIT && tid == 0) c.stage_n[b] = staged ? sh.total : 0u;
+  if (tid >= NTHREADS - 10) {
+    BlockPart *p = &c.part[b % SIMIAN_PART_SLOTS];
+    switch (tid - (NTHREADS - 10)) {
+      case 0: if (sh.min_key != SIMIAN_KEY_NONE) atomicMin(&p->min_key, sh.min_key); break;
+      case 1: if (sh.max_key) atomicMax(&p->max_key, sh.max_key); break;
+      case 2: if (sh.committed) atomicAdd(&p->committed, sh.committed); break;
+      case 3: if (sh.emitted) atomicAdd(&p->emitted, sh.emitted); break;
+      case 4: if (sh.dropped) atomicAdd(&p->dropped, sh.dropped); break;
+      case 5: if (sh.ties) atomicAdd(&p->ties, sh.ties); break;
+      case 6: if (sh.dties) atomicAdd(&p->dties, sh.dties); break;
+      case 7: if (sh.appended) atomicAdd(&p->appended, sh.appended); break;
+      case 8: if (sh.ax.far_appends) atomicAdd(&p->far_appends, sh.ax.far_appends); break;
+      default: if (sh.ax.page_allocs) atomicAdd(&p->page_allocs, sh.ax.page_allocs); break;
+    }
+  }
   // ---- recycle: the pages of rows [tb_clean, tb_hi) go onto the block's own
   // page stack (what does not fit: to the global ring), heads are cleared.  The
   // stack lives in HBM (bcache[b]); the entries below the ones popped in this
@@ -2620,26 +2639,6 @@ __device__ __forceinline__ void window_cta_body(const DevCfg &c, WindowShared &s
   }
 
   PHASE(7);
-  // ---- K1: CTA reduction of the accumulators into this CTA's BlockPart
-  {
-    accumulate_block(sh, ta);
-  }
-  __syncthreads();
-  if (tid < 10) { // one thread per field: independent, result-less atomics
-    BlockPart *p = &c.part[b % SIMIAN_PART_SLOTS];
-    switch (tid) {
-      case 0: if (sh.min_key != SIMIAN_KEY_NONE) atomicMin(&p->min_key, sh.min_key); break;
-      case 1: if (sh.max_key) atomicMax(&p->max_key, sh.max_key); break;
-      case 2: if (sh.committed) atomicAdd(&p->committed, sh.committed); break;
-      case 3: if (sh.emitted) atomicAdd(&p->emitted, sh.emitted); break;
-      case 4: if (sh.dropped) atomicAdd(&p->dropped, sh.dropped); break;
-      case 5: if (sh.ties) atomicAdd(&p->ties, sh.ties); break;
-      case 6: if (sh.dties) atomicAdd(&p->dties, sh.dties); break;
-      case 7: if (sh.appended) atomicAdd(&p->appended, sh.appended); break;
-      case 8: if (sh.ax.far_appends) atomicAdd(&p->far_appends, sh.ax.far_appends); break;
-      default: if (sh.ax.page_allocs) atomicAdd(&p->page_allocs, sh.ax.page_allocs); break;
-    }
-  }
   PHASE(8);
 }
 
