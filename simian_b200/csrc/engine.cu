@@ -1322,6 +1322,19 @@ int simian_window_process_lbts(simian_engine *e, int publish) {
     if (bpp < 4u) bpp = 4u;
     pull_blocks = bpp * (uint32_t)(e->size - 1);
   }
+  // as for size == 1 (launch_window): from 592 entity blocks on, the LBTS candidate is
+  // computed (and published) by a one-CTA launch of its own instead of the last CTA of
+  // the window kernel -- the CTAs then end without fence + ticket + barrier
+  const bool own_lbts = pull_blocks == 0 && (e->fused_advance < 0 ? e->cfg.n_blocks >= 592u
+                                                                  : e->fused_advance == 0);
+  if (own_lbts) {
+    int rc = launch_window(e, 0, 0u, e->pdl_exchange != 0);
+    if (rc) return rc;
+    k_local_min<<<1, NTHREADS, e->smem_bytes, e->stream>>>(e->cfg, e->win_ix, publish ? 1 : 0);
+    CK(cudaGetLastError());
+    e->launches++;
+    return 0;
+  }
   return launch_window(e, publish ? 3 : 2, pull_blocks, e->pdl_exchange != 0);
 }
 
