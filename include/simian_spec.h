@@ -68,7 +68,7 @@ typedef struct
   uint16_t handler; /* interned service name              (name)             */
   uint16_t flags;
   uint32_t seq;     /* per-source emission counter: tie-break only           */
-  uint64_t data;    /* fixed 8-byte payload               (data)             */
+  uint64_t data;    /* 8-byte payload, or the word count of a longer one (data) */
 } simian_event_t;
 
 /* ------------------------------------------------------------ bit helpers */

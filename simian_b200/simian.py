@@ -24,7 +24,7 @@ entity model would write 16 M lines.
 
 What changes: service handlers are not host closures but CUDA device functions
 compiled into libsimian_b200.so, bound BY NAME (`device_fn("phold_generate")`),
-and `data` is a fixed 8-byte payload (an int).  Process-oriented coroutines
+and `data` is an 8-byte payload (an int; longer payloads: handler-side req_service_blob).  Process-oriented coroutines
 (entity.js:74-205) are out of scope.
 """
 import struct
