@@ -19,7 +19,9 @@
 #ifndef SIMIAN_EPB
 #define SIMIAN_EPB 512 // entities per block by default (one CTA owns one block)
 #endif
+#ifndef SIMIAN_EPB_MAX
 #define SIMIAN_EPB_MAX 1024 // option "block_entities": models with few due events per window
+#endif
 #ifndef SIMIAN_THREADS
 #define SIMIAN_THREADS 256 // threads per CTA of the window kernel
 #endif
